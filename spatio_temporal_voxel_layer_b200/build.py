@@ -1,0 +1,61 @@
+"""Build libstvl_b200.so (CUDA kernels + C-ABI) in-tree for sm_100a with nvcc.
+
+    python -m spatio_temporal_voxel_layer_b200.build [--force]
+
+The .so is git-ignored but travels to the GPU box with the repo snapshot.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+REPO_ROOT = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libstvl_b200.so")
+SOURCES = ["stvl_kernels.cu", "stvl_api.cu", "stvl_geometry.cpp"]
+HEADERS = ["stvl_device.cuh", "stvl_kernels.h", "stvl_geometry.h"]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-fmad=false",                       # device: never contract a*b+c (bit-exact parity with the CPU path)
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
+    "-shared", "-cudart", "static",
+    "-x", "cu",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC or put /usr/local/cuda/bin on PATH)")
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(REPO_ROOT, "include", "stvl_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(REPO_ROOT, "include"), "-I", CSRC]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, f) for f in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        sys.stderr.write(res.stderr)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

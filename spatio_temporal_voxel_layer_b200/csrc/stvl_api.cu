@@ -1,0 +1,971 @@
+// stvl_api.cu — C-ABI of the B200 voxel grid (see include/stvl_b200.h): device memory, streams,
+// allocator bookkeeping and the call sequencing around the kernels in stvl_kernels.cu.
+//
+// There is deliberately no CPU path in this file: every data-path entry point launches CUDA kernels and
+// fails with STVL_ERR_NO_DEVICE / STVL_ERR_CUDA when that is impossible.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <vector>
+
+#include "stvl_b200.h"
+#include "stvl_device.cuh"
+#include "stvl_geometry.h"
+#include "stvl_kernels.h"
+
+using namespace stvl;
+
+// the ctypes / cgo-style bindings rely on these layouts (tests/test_cabi_host.py)
+static_assert(sizeof(stvl_config_t) == 56 && sizeof(stvl_reading_t) == 104 && sizeof(stvl_sweep_stats_t) == 88 &&
+              sizeof(stvl_costmap_params_t) == 40 && sizeof(stvl_costmap_result_t) == 48 && sizeof(stvl_frustum_t) == 304 &&
+              sizeof(stvl_pool_stats_t) == 88, "C-ABI struct layout changed");
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char * fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess) return fail(STVL_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+uint32_t pow2_ceil(uint64_t v)
+{
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return (uint32_t)std::min<uint64_t>(p, 1ull << 31);
+}
+
+template <typename T>
+struct DevBuf {
+  T * p = nullptr;
+  size_t cap = 0;   // elements
+};
+
+}  // namespace
+
+struct stvl_grid {
+  stvl_config_t cfg{};
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_copy_done = nullptr, ev_mark_done = nullptr;
+  GridView v{};
+  Counters * h_ctr = nullptr;       // pinned mirror
+  Counters last{};                  // counters at the last fetch
+  // staging
+  DevBuf<uint8_t> stage;
+  DevBuf<DevFrustum> frustums;
+  static constexpr int kFrustumRing = 4;
+  DevFrustum * h_frustums[kFrustumRing] = {nullptr, nullptr, nullptr, nullptr};   // pinned, kMaxFrustums each
+  cudaEvent_t ev_frustums[kFrustumRing] = {nullptr, nullptr, nullptr, nullptr};   // "copy out of slot i finished"
+  int frustum_slot = 0;
+  DevBuf<float> points;
+  DevBuf<int32_t> cleared, ambiguous;
+  DevBuf<uint8_t> costmap;
+  DevBuf<int32_t> col_ix, col_iy;
+  DevBuf<uint32_t> col_cnt;
+  DevBuf<int32_t> dump_x, dump_y, dump_z;
+  DevBuf<double> dump_t;
+  // host bookkeeping
+  uint32_t out_flags = STVL_OUT_CLEARED | STVL_OUT_AMBIGUOUS;
+  uint64_t active_upper = 0;        // upper bound of active voxels
+  uint64_t added_since_sweep = 0;   // points marked / voxels loaded after the last enqueued sweep
+  bool counters_fresh = true;       // `last` reflects the device state
+  bool marks_unverified = false;    // a Mark ran since the allocator flags were last checked
+  std::vector<MarkBatch> replay;    // batches of the unverified Mark (device data still intact)
+  double time_bound = 0.0;          // every stored mark time is <= this ...
+  bool time_bound_inf = false;      // ... unless a sweep may have raised times
+  bool swept = false;
+  uint64_t launches = 0;
+  size_t device_bytes = 0;
+  double vs = 0, inv_vs = 0, half_vs = 0;
+};
+
+namespace {
+
+template <typename T>
+int ensure(stvl_grid * g, DevBuf<T> & b, size_t n)
+{
+  if (n <= b.cap) return STVL_OK;
+  size_t ncap = std::max<size_t>(n, b.cap * 2);
+  ncap = std::max<size_t>(ncap, 1024);
+  if (b.p) { CU(cudaStreamSynchronize(g->stream)); CU(cudaStreamSynchronize(g->copy_stream)); CU(cudaFree(b.p)); g->device_bytes -= b.cap * sizeof(T); b.p = nullptr; b.cap = 0; }
+  CU(cudaMalloc(&b.p, ncap * sizeof(T)));
+  b.cap = ncap;
+  g->device_bytes += ncap * sizeof(T);
+  return STVL_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) { ok = cudaGetDevice(&prev) == cudaSuccess && (prev == dev || cudaSetDevice(dev) == cudaSuccess); }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+#define ENTER(g)                                                              \
+  if (!(g)) return fail(STVL_ERR_INVALID, "null grid handle");               \
+  DeviceGuard guard__((g)->device);                                          \
+  if (!guard__.ok) return fail(STVL_ERR_CUDA, "cudaSetDevice(%d) failed", (g)->device)
+
+int alloc_pool(stvl_grid * g, uint32_t leaf_capacity, GridView * nv)
+{
+  GridView v = g->v;
+  v.leaf_capacity = leaf_capacity;
+  const uint32_t hcap = pow2_ceil((uint64_t)leaf_capacity * 4);
+  v.hash_mask = hcap - 1;
+  CU(cudaMalloc(&v.hash_keys, (size_t)hcap * 8));
+  CU(cudaMalloc(&v.hash_vals, (size_t)hcap * 4));
+  CU(cudaMalloc(&v.leaf_key, (size_t)leaf_capacity * 8));
+  CU(cudaMalloc(&v.leaf_hpos, (size_t)leaf_capacity * 4));
+  CU(cudaMalloc(&v.leaf_tile, (size_t)leaf_capacity * 4));
+  CU(cudaMalloc(&v.leaf_mask, (size_t)leaf_capacity * 64));
+  CU(cudaMalloc(&v.leaf_time, (size_t)leaf_capacity * kLeafVoxels * 8));
+  CU(cudaMalloc(&v.free_slots, (size_t)leaf_capacity * 4));
+  *nv = v;
+  return STVL_OK;
+}
+size_t pool_bytes(const GridView & v)
+{
+  return ((size_t)v.hash_mask + 1) * 12 + (size_t)v.leaf_capacity * (8 + 4 + 4 + 64 + kLeafVoxels * 8 + 4);
+}
+void free_pool(GridView & v)
+{
+  cudaFree(v.hash_keys); cudaFree(v.hash_vals); cudaFree(v.leaf_key); cudaFree(v.leaf_hpos);
+  cudaFree(v.leaf_tile); cudaFree(v.leaf_mask); cudaFree(v.leaf_time); cudaFree(v.free_slots);
+  v.hash_keys = nullptr; v.hash_vals = nullptr; v.leaf_key = nullptr; v.leaf_hpos = nullptr;
+  v.leaf_tile = nullptr; v.leaf_mask = nullptr; v.leaf_time = nullptr; v.free_slots = nullptr;
+}
+int alloc_tiles(stvl_grid * g, uint32_t tile_capacity, GridView * nv)
+{
+  GridView v = *nv;
+  (void)g;
+  v.tile_capacity = tile_capacity;
+  const uint32_t hcap = pow2_ceil((uint64_t)tile_capacity * 4);
+  v.tile_hash_mask = hcap - 1;
+  CU(cudaMalloc(&v.tile_hash_keys, (size_t)hcap * 8));
+  CU(cudaMalloc(&v.tile_hash_vals, (size_t)hcap * 4));
+  CU(cudaMalloc(&v.tile_key, (size_t)tile_capacity * 8));
+  CU(cudaMalloc(&v.tile_count, (size_t)tile_capacity * 256));
+  *nv = v;
+  return STVL_OK;
+}
+size_t tile_bytes(const GridView & v) { return ((size_t)v.tile_hash_mask + 1) * 12 + (size_t)v.tile_capacity * (8 + 256); }
+void free_tiles(GridView & v)
+{
+  cudaFree(v.tile_hash_keys); cudaFree(v.tile_hash_vals); cudaFree(v.tile_key); cudaFree(v.tile_count);
+  v.tile_hash_keys = nullptr; v.tile_hash_vals = nullptr; v.tile_key = nullptr; v.tile_count = nullptr;
+}
+
+// wipe the whole store (ResetGrid / creation)
+int clear_pool(stvl_grid * g)
+{
+  GridView & v = g->v;
+  cudaStream_t s = g->stream;
+  CU(cudaMemsetAsync(v.hash_keys, 0xFF, ((size_t)v.hash_mask + 1) * 8, s));
+  CU(cudaMemsetAsync(v.hash_vals, 0xFF, ((size_t)v.hash_mask + 1) * 4, s));
+  CU(cudaMemsetAsync(v.leaf_key, 0xFF, (size_t)v.leaf_capacity * 8, s));
+  CU(cudaMemsetAsync(v.leaf_mask, 0, (size_t)v.leaf_capacity * 64, s));
+  CU(cudaMemsetAsync(v.leaf_time, 0, (size_t)v.leaf_capacity * kLeafVoxels * 8, s));
+  CU(cudaMemsetAsync(v.tile_hash_keys, 0xFF, ((size_t)v.tile_hash_mask + 1) * 8, s));
+  CU(cudaMemsetAsync(v.tile_hash_vals, 0xFF, ((size_t)v.tile_hash_mask + 1) * 4, s));
+  CU(cudaMemsetAsync(v.tile_count, 0, (size_t)v.tile_capacity * 256, s));
+  CU(cudaMemsetAsync(v.ctr, 0, sizeof(Counters), s));
+  g->last = Counters{};
+  g->counters_fresh = true;
+  g->marks_unverified = false;
+  g->replay.clear();
+  g->active_upper = 0;
+  g->added_since_sweep = 0;
+  g->time_bound = 0.0;
+  g->time_bound_inf = false;
+  g->swept = false;
+  return STVL_OK;
+}
+
+// copy the device counters to the host mirror and wait for the stream
+int fetch_counters(stvl_grid * g)
+{
+  CU(cudaMemcpyAsync(g->h_ctr, g->v.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, g->stream));
+  CU(cudaStreamSynchronize(g->stream));
+  g->last = *g->h_ctr;
+  g->counters_fresh = true;
+  // tighten the active-voxel bound: survivors of the last sweep + everything added after it
+  if (g->swept) g->active_upper = g->last.n_survived + g->added_since_sweep;
+  return STVL_OK;
+}
+
+int rebuild_leaf_hash(stvl_grid * g)
+{
+  GridView & v = g->v;
+  CU(cudaMemsetAsync(v.hash_keys, 0xFF, ((size_t)v.hash_mask + 1) * 8, g->stream));
+  CU(cudaMemsetAsync(v.hash_vals, 0xFF, ((size_t)v.hash_mask + 1) * 4, g->stream));
+  CU(launch_rebuild_hash(v, v.leaf_capacity, g->sm_count, g->stream));
+  g->launches += 1;
+  return STVL_OK;
+}
+int rebuild_tiles(stvl_grid * g)
+{
+  GridView & v = g->v;
+  CU(cudaMemsetAsync(v.tile_hash_keys, 0xFF, ((size_t)v.tile_hash_mask + 1) * 8, g->stream));
+  CU(cudaMemsetAsync(v.tile_hash_vals, 0xFF, ((size_t)v.tile_hash_mask + 1) * 4, g->stream));
+  CU(cudaMemsetAsync(v.tile_count, 0, (size_t)v.tile_capacity * 256, g->stream));
+  CU(cudaMemsetAsync(&v.ctr->tile_n, 0, 4, g->stream));
+  CU(cudaMemsetAsync(&v.ctr->tile_overflow, 0, 4, g->stream));
+  CU(launch_reassign_tiles(v, v.leaf_capacity, g->sm_count, g->stream));
+  g->launches += 1;
+  return STVL_OK;
+}
+
+// double the leaf pool (keeps every leaf in its slot), then rebuild the hash at the new size
+int grow_leaves(stvl_grid * g)
+{
+  GridView old = g->v;
+  if (old.leaf_capacity >= (1u << 28)) return fail(STVL_ERR_CAPACITY, "leaf pool cannot grow beyond 2^28 leaves");
+  const uint32_t ncap = old.leaf_capacity * 2;
+  GridView nv{};
+  int rc = alloc_pool(g, ncap, &nv);
+  if (rc != STVL_OK) return fail(STVL_ERR_CAPACITY, "growing the leaf pool to %u leaves failed: %s", ncap, g_err);
+  cudaStream_t s = g->stream;
+  const size_t oc = old.leaf_capacity, nc = ncap;
+  CU(cudaMemcpyAsync(nv.leaf_key, old.leaf_key, oc * 8, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemsetAsync(nv.leaf_key + oc, 0xFF, (nc - oc) * 8, s));
+  CU(cudaMemcpyAsync(nv.leaf_tile, old.leaf_tile, oc * 4, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(nv.leaf_mask, old.leaf_mask, oc * 64, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemsetAsync(nv.leaf_mask + oc * 16, 0, (nc - oc) * 64, s));
+  CU(cudaMemcpyAsync(nv.leaf_time, old.leaf_time, oc * kLeafVoxels * 8, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemsetAsync(nv.leaf_time + oc * kLeafVoxels, 0, (nc - oc) * kLeafVoxels * 8, s));
+  CU(cudaMemcpyAsync(nv.free_slots, old.free_slots, oc * 4, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemsetAsync(&old.ctr->leaf_overflow, 0, 4, s));
+  g->device_bytes += pool_bytes(nv);
+  g->v = nv;
+  rc = rebuild_leaf_hash(g);
+  if (rc != STVL_OK) return rc;
+  CU(cudaStreamSynchronize(s));
+  g->device_bytes -= pool_bytes(old);
+  free_pool(old);
+  return STVL_OK;
+}
+int grow_tiles(stvl_grid * g)
+{
+  GridView old = g->v;
+  GridView nv = g->v;
+  int rc = alloc_tiles(g, old.tile_capacity * 2, &nv);
+  if (rc != STVL_OK) return fail(STVL_ERR_CAPACITY, "growing the column tile pool failed: %s", g_err);
+  g->device_bytes += tile_bytes(nv);
+  g->v = nv;
+  rc = rebuild_tiles(g);
+  if (rc != STVL_OK) return rc;
+  CU(cudaStreamSynchronize(g->stream));
+  g->device_bytes -= tile_bytes(old);
+  free_tiles(old);
+  return STVL_OK;
+}
+
+int launch_batches(stvl_grid * g, const std::vector<MarkBatch> & batches)
+{
+  for (const MarkBatch & b : batches) {
+    CU(launch_mark(g->v, b, g->stream));
+    g->launches += 1;
+  }
+  return STVL_OK;
+}
+
+// Make sure the last Mark did not run out of leaves / tiles; if it did, grow and replay it (Mark is idempotent:
+// same bits, same times).  Needs the counters, so it synchronises unless they are already fresh.
+int verify_marks(stvl_grid * g)
+{
+  if (!g->marks_unverified) return STVL_OK;
+  for (int attempt = 0; attempt < 32; ++attempt) {
+    if (!g->counters_fresh) { int rc = fetch_counters(g); if (rc != STVL_OK) return rc; }
+    if (!g->last.leaf_overflow && !g->last.tile_overflow) {
+      g->marks_unverified = false;
+      g->replay.clear();
+      return STVL_OK;
+    }
+    if (g->last.leaf_overflow) { int rc = grow_leaves(g); if (rc != STVL_OK) return rc; }
+    if (g->last.tile_overflow) { int rc = grow_tiles(g); if (rc != STVL_OK) return rc; }
+    int rc = launch_batches(g, g->replay);
+    if (rc != STVL_OK) return rc;
+    g->counters_fresh = false;
+  }
+  return fail(STVL_ERR_CAPACITY, "leaf pool still exhausted after repeated growth");
+}
+
+// after any fetch: housekeeping decisions that only need the counters
+int after_fetch(stvl_grid * g)
+{
+  int rc = verify_marks(g);
+  if (rc != STVL_OK) return rc;
+  return STVL_OK;
+}
+
+uint32_t slots_upper(const stvl_grid * g) { return g->v.leaf_capacity; }
+uint32_t tiles_upper(const stvl_grid * g) { return g->v.tile_capacity; }
+
+int build_batches(stvl_grid * g, const stvl_reading_t * readings, uint32_t n, const std::vector<const uint8_t *> & dev_ptrs,
+                  std::vector<MarkBatch> * out, uint64_t * total_points, double * max_now, bool * monotone)
+{
+  MarkBatch cur{};
+  double prev_now = -std::numeric_limits<double>::infinity();
+  *monotone = true;
+  *total_points = 0;
+  *max_now = -std::numeric_limits<double>::infinity();
+  for (uint32_t i = 0; i < n; ++i) {
+    const stvl_reading_t & r = readings[i];
+    if (!r.marking || r.n_points == 0) continue;   // `if (obs._marking)`, reference .cpp:273
+    if (!(r.now >= prev_now)) *monotone = false;
+    if (!(r.now > 0.0) || !std::isfinite(r.now)) *monotone = false;
+    prev_now = r.now;
+    *max_now = std::max(*max_now, r.now);
+    if (cur.n_readings == kMaxBatchReadings) { out->push_back(cur); cur = MarkBatch{}; }
+    DevReading & d = cur.r[cur.n_readings++];
+    d.data = dev_ptrs[i];
+    d.n_points = r.n_points;
+    d.point_step = r.point_step; d.off_x = r.off_x; d.off_y = r.off_y; d.off_z = r.off_z;
+    d.ox = r.origin[0]; d.oy = r.origin[1]; d.oz = r.origin[2];
+    d.now = r.now;
+    d.zmin = r.min_obstacle_height; d.zmax = r.max_obstacle_height;
+    d.mark_range_2 = (float)(r.obstacle_range * r.obstacle_range);   // `float mark_range_2 = range * range`, .cpp:274
+    d.filter = r.filter;
+    d.first_block = cur.total_blocks;
+    d.vec4 = (r.point_step == 16 && r.off_x == 0 && r.off_y == 4 && r.off_z == 8 && ((uintptr_t)d.data & 15) == 0) ? 1u : 0u;
+    cur.total_blocks += mark_blocks_for(r.n_points);
+    *total_points += r.n_points;
+  }
+  if (cur.n_readings) out->push_back(cur);
+  (void)g;
+  return STVL_OK;
+}
+
+int validate_readings(const stvl_reading_t * readings, uint32_t n)
+{
+  if (n && !readings) return fail(STVL_ERR_INVALID, "readings is NULL");
+  for (uint32_t i = 0; i < n; ++i) {
+    const stvl_reading_t & r = readings[i];
+    if (!r.marking || r.n_points == 0) continue;
+    if (!r.data) return fail(STVL_ERR_INVALID, "reading %u: data is NULL", i);
+    if (r.point_step < 12 || r.off_x + 4 > r.point_step || r.off_y + 4 > r.point_step || r.off_z + 4 > r.point_step)
+      return fail(STVL_ERR_INVALID, "reading %u: x/y/z offsets (%u,%u,%u) do not fit point_step %u", i, r.off_x, r.off_y, r.off_z, r.point_step);
+    if (r.filter == STVL_FILTER_VOXEL) return fail(STVL_ERR_INVALID, "reading %u: the VOXEL pre-filter is not fused into Mark yet; filter upstream or use PASSTHROUGH/NONE", i);
+    if (r.filter != STVL_FILTER_NONE && r.filter != STVL_FILTER_PASSTHROUGH) return fail(STVL_ERR_INVALID, "reading %u: unknown filter %d", i, r.filter);
+    if (r.n_points > (1ull << 40)) return fail(STVL_ERR_INVALID, "reading %u: n_points too large", i);
+  }
+  return STVL_OK;
+}
+
+int run_mark(stvl_grid * g, const stvl_reading_t * readings, uint32_t n, const std::vector<const uint8_t *> & dev_ptrs)
+{
+  std::vector<MarkBatch> batches;
+  uint64_t total_points = 0;
+  double max_now = 0;
+  bool monotone = true;
+  int rc = build_batches(g, readings, n, dev_ptrs, &batches, &total_points, &max_now, &monotone);
+  if (rc != STVL_OK) return rc;
+  if (batches.empty()) return STVL_OK;
+  // batched launches resolve "later reading overwrites" by atomicMax, which is only the same thing when clocks are
+  // monotone and no stored time exceeds them; otherwise one launch per reading with plain stores (exact overwrite).
+  double first_now = batches[0].r[0].now;
+  const bool use_max = monotone && !g->time_bound_inf && first_now >= g->time_bound;
+  if (use_max) {
+    for (MarkBatch & b : batches) b.use_atomic_max = 1;
+  } else {
+    std::vector<MarkBatch> seq;
+    for (const MarkBatch & b : batches)
+      for (uint32_t k = 0; k < b.n_readings; ++k) {
+        MarkBatch one{};
+        one.n_readings = 1;
+        one.r[0] = b.r[k];
+        one.r[0].first_block = 0;
+        one.total_blocks = mark_blocks_for(b.r[k].n_points);
+        one.use_atomic_max = 0;
+        seq.push_back(one);
+      }
+    batches.swap(seq);
+  }
+  rc = launch_batches(g, batches);
+  if (rc != STVL_OK) return rc;
+  CU(cudaEventRecord(g->ev_mark_done, g->stream));
+  g->replay = batches;
+  g->marks_unverified = true;
+  g->counters_fresh = false;
+  g->active_upper += total_points;
+  g->added_since_sweep += total_points;
+  if (!g->time_bound_inf) g->time_bound = std::max(g->time_bound, max_now);
+  return STVL_OK;
+}
+
+void world_bbox(const stvl_grid * g, const int32_t idx[4], double out[4])
+{
+  for (int k = 0; k < 4; ++k) out[k] = (double)idx[k] * g->vs + g->half_vs;
+}
+
+CostmapDev to_dev(const stvl_costmap_params_t & p)
+{
+  CostmapDev d;
+  d.origin_x = p.origin_x; d.origin_y = p.origin_y; d.resolution = p.resolution;
+  d.size_x = p.size_x; d.size_y = p.size_y; d.mark_threshold = p.mark_threshold;
+  d.default_value = p.default_value; d.lethal = p.lethal_value;
+  return d;
+}
+
+void fill_costmap_result(const stvl_grid * g, stvl_costmap_result_t * res)
+{
+  if (!res) return;
+  std::memset(res, 0, sizeof(*res));
+  res->n_marked_columns = g->last.n_marked;
+  res->has_bounds = g->last.n_marked > 0;
+  if (res->has_bounds) {
+    const int32_t idx[4] = {g->last.mk_min_x, g->last.mk_min_y, g->last.mk_max_x, g->last.mk_max_y};
+    world_bbox(g, idx, res->touched);
+  }
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+int stvl_abi_version(void) { return STVL_ABI_VERSION; }
+const char * stvl_last_error(void) { return g_err; }
+
+int stvl_device_count(int * count)
+{
+  if (!count) return fail(STVL_ERR_INVALID, "count is NULL");
+  *count = 0;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return STVL_OK; }
+  for (int d = 0; d < n; ++d) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++*count;
+  }
+  return STVL_OK;
+}
+
+int stvl_create(const stvl_config_t * cfg, stvl_grid_t ** out)
+{
+  if (!cfg || !out) return fail(STVL_ERR_INVALID, "cfg/out is NULL");
+  *out = nullptr;
+  if (!(cfg->voxel_size > 0.f) || !std::isfinite(cfg->voxel_size)) return fail(STVL_ERR_INVALID, "voxel_size must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(STVL_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
+  }
+  int dev = cfg->device;
+  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) return fail(STVL_ERR_CUDA, "cudaGetDevice failed"); }
+  if (dev >= ndev) return fail(STVL_ERR_INVALID, "device %d out of range (%d devices)", dev, ndev);
+  int major = 0, minor = 0, sms = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (major != 10) return fail(STVL_ERR_NO_DEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a only", dev, major, minor);
+
+  stvl_grid * g = new (std::nothrow) stvl_grid();
+  if (!g) return fail(STVL_ERR_INVALID, "out of host memory");
+  g->cfg = *cfg;
+  g->device = dev;
+  g->sm_count = sms > 0 ? sms : 148;
+  DeviceGuard guard(dev);
+  if (!guard.ok) { delete g; return fail(STVL_ERR_CUDA, "cudaSetDevice(%d) failed", dev); }
+  // `_voxel_size(voxel_size)`: float widened to double (reference .cpp:51,54); OpenVDB caches 1/scale
+  g->vs = (double)cfg->voxel_size;
+  g->inv_vs = 1.0 / g->vs;
+  g->half_vs = g->vs / 2.0;
+
+  auto bail = [&](int rc) { stvl_destroy(g); return rc; };
+#define CUB(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return bail(fail(STVL_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__))); } while (0)
+  CUB(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+  CUB(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
+  CUB(cudaEventCreateWithFlags(&g->ev_copy_done, cudaEventDisableTiming));
+  CUB(cudaEventCreateWithFlags(&g->ev_mark_done, cudaEventDisableTiming));
+  CUB(cudaMallocHost(&g->h_ctr, sizeof(Counters)));
+  for (int i = 0; i < stvl_grid::kFrustumRing; ++i) {
+    CUB(cudaMallocHost(&g->h_frustums[i], sizeof(DevFrustum) * kMaxFrustums));
+    CUB(cudaEventCreateWithFlags(&g->ev_frustums[i], cudaEventDisableTiming));
+  }
+  CUB(cudaMalloc(&g->v.ctr, sizeof(Counters)));
+  g->device_bytes += sizeof(Counters);
+
+  const uint32_t leaf_cap = cfg->leaf_capacity ? std::max<uint32_t>(cfg->leaf_capacity, 64u) : (1u << 17);
+  GridView nv = g->v;
+  nv.vs = g->vs; nv.inv_vs = g->inv_vs; nv.half_vs = g->half_vs;
+  nv.voxel_decay = cfg->voxel_decay; nv.decay_model = cfg->decay_model;
+  nv.shard_index = cfg->shard_index; nv.shard_count = cfg->shard_count; nv.shard_width = std::max(cfg->shard_width, 1);
+  g->v = nv;
+  int rc = alloc_pool(g, leaf_cap, &nv);
+  if (rc != STVL_OK) { free_pool(nv); return bail(rc); }
+  g->v = nv;
+  rc = alloc_tiles(g, std::max<uint32_t>(leaf_cap / 2, 64u), &nv);
+  if (rc != STVL_OK) { g->v = nv; return bail(rc); }
+  g->v = nv;
+  g->device_bytes += pool_bytes(g->v) + tile_bytes(g->v);
+  rc = clear_pool(g);
+  if (rc != STVL_OK) return bail(rc);
+  if (cfg->max_points) { rc = ensure(g, g->stage, (size_t)cfg->max_points * 16); if (rc != STVL_OK) return bail(rc); }
+  CUB(cudaStreamSynchronize(g->stream));
+#undef CUB
+  *out = g;
+  return STVL_OK;
+}
+
+int stvl_destroy(stvl_grid_t * g)
+{
+  if (!g) return STVL_OK;
+  DeviceGuard guard(g->device);
+  if (g->stream) cudaStreamSynchronize(g->stream);
+  if (g->copy_stream) cudaStreamSynchronize(g->copy_stream);
+  free_pool(g->v);
+  free_tiles(g->v);
+  cudaFree(g->v.ctr);
+  cudaFree(g->stage.p); cudaFree(g->frustums.p); cudaFree(g->points.p); cudaFree(g->cleared.p); cudaFree(g->ambiguous.p);
+  cudaFree(g->costmap.p); cudaFree(g->col_ix.p); cudaFree(g->col_iy.p); cudaFree(g->col_cnt.p);
+  cudaFree(g->dump_x.p); cudaFree(g->dump_y.p); cudaFree(g->dump_z.p); cudaFree(g->dump_t.p);
+  if (g->h_ctr) cudaFreeHost(g->h_ctr);
+  for (int i = 0; i < stvl_grid::kFrustumRing; ++i) {
+    if (g->h_frustums[i]) cudaFreeHost(g->h_frustums[i]);
+    if (g->ev_frustums[i]) cudaEventDestroy(g->ev_frustums[i]);
+  }
+  if (g->ev_copy_done) cudaEventDestroy(g->ev_copy_done);
+  if (g->ev_mark_done) cudaEventDestroy(g->ev_mark_done);
+  if (g->stream) cudaStreamDestroy(g->stream);
+  if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
+  cudaGetLastError();
+  delete g;
+  return STVL_OK;
+}
+
+int stvl_build_depth_frustum(double vfov, double hfov, double min_dist, double max_dist, const double origin[3],
+                             const double quat_xyzw[4], double accel_factor, stvl_frustum_t * out)
+{
+  if (!origin || !quat_xyzw || !out) return fail(STVL_ERR_INVALID, "NULL argument");
+  return build_depth_frustum(vfov, hfov, min_dist, max_dist, origin, quat_xyzw, accel_factor, out);
+}
+int stvl_build_lidar_frustum(double vfov, double vfov_padding, double hfov, double min_dist, double max_dist,
+                             const double origin[3], const double quat_xyzw[4], double accel_factor, stvl_frustum_t * out)
+{
+  if (!origin || !quat_xyzw || !out) return fail(STVL_ERR_INVALID, "NULL argument");
+  return build_lidar_frustum(vfov, vfov_padding, hfov, min_dist, max_dist, origin, quat_xyzw, accel_factor, out);
+}
+
+int stvl_set_outputs(stvl_grid_t * g, uint32_t flags)
+{
+  if (!g) return fail(STVL_ERR_INVALID, "null grid handle");
+  g->out_flags = flags;
+  return STVL_OK;
+}
+
+int stvl_clear_frustums(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums)
+{
+  ENTER(g);
+  if (n_frustums && !frustums) return fail(STVL_ERR_INVALID, "frustums is NULL");
+  if (n_frustums > (uint32_t)kMaxFrustums) return fail(STVL_ERR_INVALID, "at most %d clearing frustums per sweep", kMaxFrustums);
+  // the allocator flags of the previous Mark must be known before its voxels are swept
+  int rc = verify_marks(g);
+  if (rc != STVL_OK) return rc;
+  // hash / tile maintenance, decided from the last known counters
+  if (g->last.n_tombs > (g->v.hash_mask + 1) / 8) { rc = rebuild_leaf_hash(g); if (rc != STVL_OK) return rc; g->last.n_tombs = 0; }
+  if (g->last.tile_n > g->v.tile_capacity / 4 * 3) {
+    rc = rebuild_tiles(g); if (rc != STVL_OK) return rc;
+    rc = fetch_counters(g); if (rc != STVL_OK) return rc;
+    if (g->last.tile_n > g->v.tile_capacity / 2) { rc = grow_tiles(g); if (rc != STVL_OK) return rc; }
+  }
+  // frustum blocks -> device (the previous sweep that read d_frustums is ordered before on the stream)
+  bool may_raise = false;
+  if (n_frustums) {
+    rc = ensure(g, g->frustums, n_frustums);
+    if (rc != STVL_OK) return rc;
+    // ring of pinned staging slots: a slot is reused only after the copy that read it has finished
+    const int slot = g->frustum_slot;
+    g->frustum_slot = (slot + 1) % stvl_grid::kFrustumRing;
+    CU(cudaEventSynchronize(g->ev_frustums[slot]));
+    DevFrustum * hf = g->h_frustums[slot];
+    for (uint32_t i = 0; i < n_frustums; ++i) {
+      prepare_frustum(frustums[i], g->vs, &hf[i]);
+      if (!(frustums[i].accel_factor >= 0.0)) may_raise = true;
+    }
+    CU(cudaMemcpyAsync(g->frustums.p, hf, sizeof(DevFrustum) * n_frustums, cudaMemcpyHostToDevice, g->stream));
+    CU(cudaEventRecord(g->ev_frustums[slot], g->stream));
+  }
+  // stored times only ever go down in a sweep if now >= every stored time and all factors are >= 0
+  if (!(now >= g->time_bound) || may_raise) g->time_bound_inf = true;
+
+  SweepOutputs out{};
+  const uint64_t bound = g->active_upper;
+  if (g->cfg.pub_voxels) {
+    rc = ensure(g, g->points, (size_t)bound * 3 + 3); if (rc != STVL_OK) return rc;
+    out.points = g->points.p; out.points_cap = bound;
+  }
+  if (g->out_flags & STVL_OUT_CLEARED) {
+    rc = ensure(g, g->cleared, (size_t)bound * 2 + 2); if (rc != STVL_OK) return rc;
+    out.cleared = g->cleared.p; out.cleared_cap = bound;
+  }
+  if (g->out_flags & STVL_OUT_AMBIGUOUS) {
+    const size_t cap = 65536;
+    rc = ensure(g, g->ambiguous, cap * 3); if (rc != STVL_OK) return rc;
+    out.ambiguous = g->ambiguous.p; out.ambiguous_cap = cap;
+  }
+  CU(launch_sweep(g->v, g->frustums.p, (int)n_frustums, now, out, slots_upper(g), g->sm_count, g->stream));
+  g->launches += 2;
+  g->counters_fresh = false;
+  g->swept = true;
+  g->added_since_sweep = 0;
+  return STVL_OK;
+}
+
+int stvl_mark(stvl_grid_t * g, const stvl_reading_t * readings, uint32_t n_readings)
+{
+  ENTER(g);
+  int rc = validate_readings(readings, n_readings);
+  if (rc != STVL_OK) return rc;
+  // a second Mark before the first was verified would overwrite its staged input: verify first
+  rc = verify_marks(g);
+  if (rc != STVL_OK) return rc;
+  size_t total = 0;
+  std::vector<size_t> offs(n_readings, 0);
+  for (uint32_t i = 0; i < n_readings; ++i) {
+    const stvl_reading_t & r = readings[i];
+    if (!r.marking || r.n_points == 0) continue;
+    offs[i] = total;
+    total += ((size_t)r.n_points * r.point_step + 255) & ~(size_t)255;
+  }
+  if (total == 0) return STVL_OK;
+  rc = ensure(g, g->stage, total);
+  if (rc != STVL_OK) return rc;
+  // H2D on the copy stream (overlaps a sweep still running on the main stream); the staging buffer may only be
+  // overwritten once the previous Mark kernel has consumed it
+  CU(cudaStreamWaitEvent(g->copy_stream, g->ev_mark_done, 0));
+  std::vector<const uint8_t *> dev_ptrs(n_readings, nullptr);
+  for (uint32_t i = 0; i < n_readings; ++i) {
+    const stvl_reading_t & r = readings[i];
+    if (!r.marking || r.n_points == 0) continue;
+    dev_ptrs[i] = g->stage.p + offs[i];
+    CU(cudaMemcpyAsync(g->stage.p + offs[i], r.data, (size_t)r.n_points * r.point_step, cudaMemcpyHostToDevice, g->copy_stream));
+  }
+  CU(cudaEventRecord(g->ev_copy_done, g->copy_stream));
+  CU(cudaStreamWaitEvent(g->stream, g->ev_copy_done, 0));
+  rc = run_mark(g, readings, n_readings, dev_ptrs);
+  if (rc != STVL_OK) return rc;
+  // the caller owns the clouds again as soon as they are on the device
+  CU(cudaEventSynchronize(g->ev_copy_done));
+  return STVL_OK;
+}
+
+int stvl_mark_device(stvl_grid_t * g, const stvl_reading_t * readings, uint32_t n_readings)
+{
+  ENTER(g);
+  int rc = validate_readings(readings, n_readings);
+  if (rc != STVL_OK) return rc;
+  rc = verify_marks(g);
+  if (rc != STVL_OK) return rc;
+  std::vector<const uint8_t *> dev_ptrs(n_readings, nullptr);
+  for (uint32_t i = 0; i < n_readings; ++i) dev_ptrs[i] = static_cast<const uint8_t *>(readings[i].data);
+  return run_mark(g, readings, n_readings, dev_ptrs);
+}
+
+int stvl_costmap_device(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_t * costmap_dev, stvl_costmap_result_t * res)
+{
+  ENTER(g);
+  if (!p || !costmap_dev) return fail(STVL_ERR_INVALID, "NULL argument");
+  if (!(p->resolution > 0)) return fail(STVL_ERR_INVALID, "resolution must be positive");
+  CU(launch_costmap(g->v, to_dev(*p), costmap_dev, tiles_upper(g), g->sm_count, g->stream));
+  g->launches += 2;
+  int rc = fetch_counters(g);
+  if (rc != STVL_OK) return rc;
+  fill_costmap_result(g, res);
+  return after_fetch(g);
+}
+
+int stvl_costmap(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_t * costmap, stvl_costmap_result_t * res)
+{
+  ENTER(g);
+  if (!p) return fail(STVL_ERR_INVALID, "NULL argument");
+  if (!(p->resolution > 0)) return fail(STVL_ERR_INVALID, "resolution must be positive");
+  const size_t bytes = (size_t)p->size_x * p->size_y;
+  int rc = ensure(g, g->costmap, std::max<size_t>(bytes, 1));
+  if (rc != STVL_OK) return rc;
+  CU(launch_costmap(g->v, to_dev(*p), g->costmap.p, tiles_upper(g), g->sm_count, g->stream));
+  g->launches += 2;
+  if (costmap && bytes) CU(cudaMemcpyAsync(costmap, g->costmap.p, bytes, cudaMemcpyDeviceToHost, g->stream));
+  rc = fetch_counters(g);
+  if (rc != STVL_OK) return rc;
+  fill_costmap_result(g, res);
+  return after_fetch(g);
+}
+
+int stvl_get_sweep_stats(stvl_grid_t * g, stvl_sweep_stats_t * out)
+{
+  ENTER(g);
+  if (!out) return fail(STVL_ERR_INVALID, "out is NULL");
+  int rc = fetch_counters(g);
+  if (rc != STVL_OK) return rc;
+  std::memset(out, 0, sizeof(*out));
+  const Counters & c = g->last;
+  out->n_swept = c.n_swept; out->n_survived = c.n_survived; out->n_cleared = c.n_cleared;
+  out->n_rewritten = c.n_rewritten; out->n_ambiguous = c.n_ambiguous;
+  if (c.n_cleared) {
+    out->cleared_bbox_index[0] = c.cb_min_x; out->cleared_bbox_index[1] = c.cb_min_y;
+    out->cleared_bbox_index[2] = c.cb_max_x; out->cleared_bbox_index[3] = c.cb_max_y;
+    world_bbox(g, out->cleared_bbox_index, out->cleared_bbox_world);
+  }
+  return after_fetch(g);
+}
+
+int stvl_get_columns(stvl_grid_t * g, int32_t * ix, int32_t * iy, uint32_t * count, uint64_t cap, uint64_t * n)
+{
+  ENTER(g);
+  if (!n) return fail(STVL_ERR_INVALID, "n is NULL");
+  int rc;
+  if (cap) {
+    rc = ensure(g, g->col_ix, cap); if (rc != STVL_OK) return rc;
+    rc = ensure(g, g->col_iy, cap); if (rc != STVL_OK) return rc;
+    rc = ensure(g, g->col_cnt, cap); if (rc != STVL_OK) return rc;
+  }
+  CU(launch_columns(g->v, cap ? g->col_ix.p : nullptr, cap ? g->col_iy.p : nullptr, cap ? g->col_cnt.p : nullptr, cap,
+                    tiles_upper(g), g->sm_count, g->stream));
+  g->launches += 2;
+  rc = fetch_counters(g);
+  if (rc != STVL_OK) return rc;
+  *n = g->last.n_columns_out;
+  const uint64_t m = std::min<uint64_t>(*n, cap);
+  if (m) {
+    if (ix) CU(cudaMemcpyAsync(ix, g->col_ix.p, m * 4, cudaMemcpyDeviceToHost, g->stream));
+    if (iy) CU(cudaMemcpyAsync(iy, g->col_iy.p, m * 4, cudaMemcpyDeviceToHost, g->stream));
+    if (count) CU(cudaMemcpyAsync(count, g->col_cnt.p, m * 4, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+  }
+  rc = after_fetch(g);
+  if (rc != STVL_OK) return rc;
+  return *n > cap && cap ? fail(STVL_ERR_RANGE, "column buffer too small: %llu > %llu", (unsigned long long)*n, (unsigned long long)cap) : STVL_OK;
+}
+
+int stvl_get_cleared(stvl_grid_t * g, int32_t * ix, int32_t * iy, uint64_t cap, uint64_t * n)
+{
+  ENTER(g);
+  if (!n) return fail(STVL_ERR_INVALID, "n is NULL");
+  int rc = fetch_counters(g);
+  if (rc != STVL_OK) return rc;
+  *n = (g->out_flags & STVL_OUT_CLEARED) ? g->last.n_cleared_out : 0;
+  const uint64_t m = std::min<uint64_t>(*n, cap);
+  if (m && (ix || iy)) {
+    std::vector<int32_t> tmp(m * 2);
+    CU(cudaMemcpy(tmp.data(), g->cleared.p, m * 8, cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < m; ++i) { if (ix) ix[i] = tmp[2 * i]; if (iy) iy[i] = tmp[2 * i + 1]; }
+  }
+  rc = after_fetch(g);
+  if (rc != STVL_OK) return rc;
+  return *n > cap && cap ? fail(STVL_ERR_RANGE, "cleared buffer too small") : STVL_OK;
+}
+
+int stvl_get_points(stvl_grid_t * g, float * xyz, uint64_t cap, uint64_t * n)
+{
+  ENTER(g);
+  if (!n) return fail(STVL_ERR_INVALID, "n is NULL");
+  int rc = fetch_counters(g);
+  if (rc != STVL_OK) return rc;
+  *n = g->cfg.pub_voxels ? g->last.n_points_out : 0;
+  const uint64_t m = std::min<uint64_t>(*n, cap);
+  if (m && xyz) CU(cudaMemcpy(xyz, g->points.p, m * 12, cudaMemcpyDeviceToHost));
+  rc = after_fetch(g);
+  if (rc != STVL_OK) return rc;
+  return *n > cap && cap ? fail(STVL_ERR_RANGE, "point buffer too small") : STVL_OK;
+}
+
+int stvl_get_ambiguous(stvl_grid_t * g, int32_t * ix, int32_t * iy, int32_t * iz, uint64_t cap, uint64_t * n)
+{
+  ENTER(g);
+  if (!n) return fail(STVL_ERR_INVALID, "n is NULL");
+  int rc = fetch_counters(g);
+  if (rc != STVL_OK) return rc;
+  *n = (g->out_flags & STVL_OUT_AMBIGUOUS) ? std::min<uint64_t>(g->last.n_ambiguous_out, 65536) : 0;
+  const uint64_t m = std::min<uint64_t>(*n, cap);
+  if (m) {
+    std::vector<int32_t> tmp(m * 3);
+    CU(cudaMemcpy(tmp.data(), g->ambiguous.p, m * 12, cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < m; ++i) { if (ix) ix[i] = tmp[3 * i]; if (iy) iy[i] = tmp[3 * i + 1]; if (iz) iz[i] = tmp[3 * i + 2]; }
+  }
+  return after_fetch(g);
+}
+
+int stvl_reset(stvl_grid_t * g)
+{
+  ENTER(g);
+  int rc = clear_pool(g);
+  if (rc != STVL_OK) return rc;
+  CU(cudaStreamSynchronize(g->stream));
+  return STVL_OK;
+}
+
+int stvl_reset_area(stvl_grid_t * g, double start_x, double start_y, double end_x, double end_y, int invert_area)
+{
+  ENTER(g);
+  int rc = verify_marks(g);
+  if (rc != STVL_OK) return rc;
+  CU(launch_reset_area(g->v, start_x, start_y, end_x, end_y, invert_area, slots_upper(g), g->sm_count, g->stream));
+  g->launches += 1;
+  return STVL_OK;
+}
+
+int stvl_active_count(stvl_grid_t * g, uint64_t * n)
+{
+  ENTER(g);
+  if (!n) return fail(STVL_ERR_INVALID, "n is NULL");
+  int rc = verify_marks(g);
+  if (rc != STVL_OK) return rc;
+  CU(cudaMemsetAsync(&g->v.ctr->n_active, 0, 8, g->stream));
+  CU(cudaMemsetAsync(&g->v.ctr->live_leaves, 0, 4, g->stream));
+  CU(launch_count_active(g->v, slots_upper(g), g->sm_count, g->stream));
+  g->launches += 1;
+  rc = fetch_counters(g);
+  if (rc != STVL_OK) return rc;
+  *n = g->last.n_active;
+  if (!g->swept) g->active_upper = g->last.n_active;
+  return STVL_OK;
+}
+
+int stvl_get_voxels(stvl_grid_t * g, int32_t * ix, int32_t * iy, int32_t * iz, double * t, uint64_t cap, uint64_t * n)
+{
+  ENTER(g);
+  if (!n) return fail(STVL_ERR_INVALID, "n is NULL");
+  int rc = verify_marks(g);
+  if (rc != STVL_OK) return rc;
+  if (cap) {
+    rc = ensure(g, g->dump_x, cap); if (rc != STVL_OK) return rc;
+    rc = ensure(g, g->dump_y, cap); if (rc != STVL_OK) return rc;
+    rc = ensure(g, g->dump_z, cap); if (rc != STVL_OK) return rc;
+    rc = ensure(g, g->dump_t, cap); if (rc != STVL_OK) return rc;
+  }
+  CU(cudaMemsetAsync(&g->v.ctr->n_voxels_out, 0, 8, g->stream));
+  CU(launch_dump_voxels(g->v, cap ? g->dump_x.p : nullptr, cap ? g->dump_y.p : nullptr, cap ? g->dump_z.p : nullptr,
+                        cap ? g->dump_t.p : nullptr, cap, slots_upper(g), g->sm_count, g->stream));
+  g->launches += 1;
+  rc = fetch_counters(g);
+  if (rc != STVL_OK) return rc;
+  *n = g->last.n_voxels_out;
+  const uint64_t m = std::min<uint64_t>(*n, cap);
+  if (m) {
+    if (ix) CU(cudaMemcpyAsync(ix, g->dump_x.p, m * 4, cudaMemcpyDeviceToHost, g->stream));
+    if (iy) CU(cudaMemcpyAsync(iy, g->dump_y.p, m * 4, cudaMemcpyDeviceToHost, g->stream));
+    if (iz) CU(cudaMemcpyAsync(iz, g->dump_z.p, m * 4, cudaMemcpyDeviceToHost, g->stream));
+    if (t) CU(cudaMemcpyAsync(t, g->dump_t.p, m * 8, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+  }
+  return *n > cap && cap ? fail(STVL_ERR_RANGE, "voxel buffer too small") : STVL_OK;
+}
+
+int stvl_load_voxels(stvl_grid_t * g, const int32_t * ix, const int32_t * iy, const int32_t * iz, const double * t, uint64_t n)
+{
+  ENTER(g);
+  if (n == 0) return STVL_OK;
+  if (!ix || !iy || !iz || !t) return fail(STVL_ERR_INVALID, "NULL argument");
+  int rc = verify_marks(g);
+  if (rc != STVL_OK) return rc;
+  rc = ensure(g, g->dump_x, n); if (rc != STVL_OK) return rc;
+  rc = ensure(g, g->dump_y, n); if (rc != STVL_OK) return rc;
+  rc = ensure(g, g->dump_z, n); if (rc != STVL_OK) return rc;
+  rc = ensure(g, g->dump_t, n); if (rc != STVL_OK) return rc;
+  CU(cudaMemcpyAsync(g->dump_x.p, ix, n * 4, cudaMemcpyHostToDevice, g->stream));
+  CU(cudaMemcpyAsync(g->dump_y.p, iy, n * 4, cudaMemcpyHostToDevice, g->stream));
+  CU(cudaMemcpyAsync(g->dump_z.p, iz, n * 4, cudaMemcpyHostToDevice, g->stream));
+  CU(cudaMemcpyAsync(g->dump_t.p, t, n * 8, cudaMemcpyHostToDevice, g->stream));
+  double tmax = -std::numeric_limits<double>::infinity();
+  for (uint64_t i = 0; i < n; ++i) tmax = std::max(tmax, t[i]);
+  for (int attempt = 0; attempt < 32; ++attempt) {
+    CU(launch_load_voxels(g->v, g->dump_x.p, g->dump_y.p, g->dump_z.p, g->dump_t.p, n, g->stream));
+    g->launches += 1;
+    rc = fetch_counters(g);
+    if (rc != STVL_OK) return rc;
+    if (!g->last.leaf_overflow && !g->last.tile_overflow) break;
+    if (g->last.leaf_overflow) { rc = grow_leaves(g); if (rc != STVL_OK) return rc; }
+    if (g->last.tile_overflow) { rc = grow_tiles(g); if (rc != STVL_OK) return rc; }
+    if (attempt == 31) return fail(STVL_ERR_CAPACITY, "leaf pool still exhausted after repeated growth");
+  }
+  g->active_upper += n;
+  g->added_since_sweep += n;
+  if (!(tmax <= g->time_bound)) { if (std::isfinite(tmax)) g->time_bound = std::max(g->time_bound, tmax); else g->time_bound_inf = true; }
+  return STVL_OK;
+}
+
+double stvl_index_to_world(const stvl_grid_t * g, int32_t index)
+{
+  if (!g) return std::numeric_limits<double>::quiet_NaN();
+  return (double)index * g->vs + g->half_vs;
+}
+double stvl_voxel_size(const stvl_grid_t * g) { return g ? g->vs : std::numeric_limits<double>::quiet_NaN(); }
+
+int stvl_columns_to_dense(stvl_grid_t * g, int32_t ix0, int32_t iy0, uint32_t nx, uint32_t ny, uint32_t * dense_dev)
+{
+  ENTER(g);
+  if (!dense_dev) return fail(STVL_ERR_INVALID, "dense_dev is NULL");
+  CU(launch_columns_to_dense(g->v, ix0, iy0, nx, ny, dense_dev, tiles_upper(g), g->sm_count, g->stream));
+  g->launches += 1;
+  CU(cudaStreamSynchronize(g->stream));
+  return STVL_OK;
+}
+
+int stvl_costmap_from_dense(stvl_grid_t * g, const uint32_t * dense_dev, int32_t ix0, int32_t iy0, uint32_t nx, uint32_t ny,
+                            const stvl_costmap_params_t * p, uint8_t * costmap_dev, stvl_costmap_result_t * res)
+{
+  ENTER(g);
+  if (!dense_dev || !p || !costmap_dev) return fail(STVL_ERR_INVALID, "NULL argument");
+  CU(launch_costmap_from_dense(g->v, dense_dev, ix0, iy0, nx, ny, to_dev(*p), costmap_dev, g->sm_count, g->stream));
+  g->launches += 2;
+  int rc = fetch_counters(g);
+  if (rc != STVL_OK) return rc;
+  fill_costmap_result(g, res);
+  return after_fetch(g);
+}
+
+int stvl_get_pool_stats(stvl_grid_t * g, stvl_pool_stats_t * out)
+{
+  ENTER(g);
+  if (!out) return fail(STVL_ERR_INVALID, "out is NULL");
+  int rc = fetch_counters(g);
+  if (rc != STVL_OK) return rc;
+  std::memset(out, 0, sizeof(*out));
+  const Counters & c = g->last;
+  out->leaf_capacity = g->v.leaf_capacity;
+  out->leaves_free = c.free_n;
+  out->leaves_in_use = c.high_water - c.free_n;
+  out->hash_capacity = (uint64_t)g->v.hash_mask + 1;
+  out->hash_tombstones = c.n_tombs;
+  out->tiles_in_use = c.tile_n;
+  out->tile_capacity = g->v.tile_capacity;
+  out->points_dropped_out_of_range = c.dropped_range;
+  out->points_dropped_nonfinite = c.dropped_nonfinite;
+  out->kernel_launches = g->launches;
+  out->device_bytes = g->device_bytes;
+  return after_fetch(g);
+}
+
+int stvl_get_stream(stvl_grid_t * g, void ** stream)
+{
+  if (!g || !stream) return fail(STVL_ERR_INVALID, "NULL argument");
+  *stream = (void *)g->stream;
+  return STVL_OK;
+}
+
+int stvl_synchronize(stvl_grid_t * g)
+{
+  ENTER(g);
+  CU(cudaStreamSynchronize(g->copy_stream));
+  CU(cudaStreamSynchronize(g->stream));
+  return STVL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,241 @@
+// stvl_device.cuh — device-side data layout of the B200 sparse voxel grid.
+//
+// The reference keeps mark times in an openvdb::DoubleGrid (5-4-3 tree with 8^3
+// leaves; reference spatio_temporal_voxel_grid.hpp:182, .cpp:80).  Here the store
+// is a GPU hash of 8x8x8 LEAVES:
+//
+//   leaf hash   : open addressing, 64-bit packed leaf coordinate -> pool slot
+//   leaf pool   : per slot  key (8 B) | value mask 512 bit (64 B) | 512 mark times f64 (4 KB)
+//                 local index li = (lx*8 + ly)*8 + lz  (z fastest: a voxel column is one 64 B run)
+//   column tiles: one per (bx,by) leaf column: 64 x u32 per-(x,y) voxel counts, refilled by
+//                 every clear sweep (the reference's _cost_map, .cpp:227-251)
+//
+// Only mask words and the 32 B sectors of touched times ever move through HBM, a
+// cleared voxel is one bit flip (no compaction pass), and frustum culling happens
+// once per leaf instead of once per voxel.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace stvl {
+
+constexpr int kLeafDim = 8;
+constexpr int kLeafVoxels = 512;
+constexpr int kLeafBias = 1 << 20;              // leaf coords in [-2^20, 2^20)
+constexpr uint64_t kEmptyKey = ~0ull;
+constexpr uint64_t kTombKey = ~0ull - 1;
+constexpr uint32_t kInvalidSlot = 0xFFFFFFFFu;  // hash value not yet published
+constexpr uint32_t kOverflowSlot = 0xFFFFFFFEu; // pool exhausted when this leaf was requested
+constexpr int kMaxFrustums = 512;
+constexpr int kMaxBatchReadings = 16;
+
+// -------- device-resident counters (one struct, zero-initialised) -----------------
+struct Counters {
+  // leaf pool allocator
+  uint32_t alloc_cursor;   // leaves requested by the running Mark kernel
+  uint32_t free_n;         // entries on the free stack
+  uint32_t high_water;     // slots [0, high_water) have been handed out at least once
+  uint32_t n_tombs;        // tombstones in the leaf hash
+  uint32_t leaf_overflow;  // a Mark ran out of leaves (host grows the pool and replays)
+  uint32_t done_ctr;       // last-block-done ticket
+  // tile pool
+  uint32_t tile_n;
+  uint32_t tile_overflow;
+  // dropped input points
+  unsigned long long dropped_range, dropped_nonfinite;
+  // last sweep
+  unsigned long long n_swept, n_survived, n_cleared, n_rewritten, n_ambiguous;
+  int32_t cb_min_x, cb_min_y, cb_max_x, cb_max_y;
+  unsigned long long n_points_out, n_cleared_out, n_ambiguous_out;
+  // costmap / column queries
+  unsigned long long n_marked;
+  int32_t mk_min_x, mk_min_y, mk_max_x, mk_max_y;
+  unsigned long long n_columns_out;
+  // dumps
+  unsigned long long n_voxels_out, n_active;
+  uint32_t live_leaves;
+  uint32_t pad0;
+};
+
+// -------- grid view handed to every kernel ----------------------------------------
+struct GridView {
+  // leaf hash
+  uint64_t * hash_keys;
+  uint32_t * hash_vals;
+  uint32_t hash_mask;      // capacity - 1 (power of two)
+  // leaf pool
+  uint64_t * leaf_key;     // kEmptyKey = slot is free
+  uint32_t * leaf_hpos;    // position of the leaf in the hash (for tombstoning)
+  uint32_t * leaf_tile;    // column tile of the leaf
+  uint32_t * leaf_mask;    // 16 x u32 per leaf
+  double * leaf_time;      // 512 per leaf
+  uint32_t * free_slots;
+  uint32_t leaf_capacity;
+  // column tiles
+  uint64_t * tile_hash_keys;
+  uint32_t * tile_hash_vals;
+  uint32_t tile_hash_mask;
+  uint64_t * tile_key;
+  uint32_t * tile_count;   // 64 per tile
+  uint32_t tile_capacity;
+  Counters * ctr;
+  // constants
+  double vs, inv_vs, half_vs;
+  double voxel_decay;
+  int decay_model;
+  // spatial shard (multi-GPU): keep leaf iff floor_mod(floor_div(bx, shard_width), shard_count) == shard_index
+  int shard_index, shard_count, shard_width;
+};
+
+// -------- frustum as the sweep kernel sees it --------------------------------------
+struct DevFrustum {
+  int32_t type;          // 0 depth, 1 lidar, -1 never inside
+  int32_t cull;          // 1: aabb / bounding data below are valid
+  double c16f;           // (1./6.) * accel_factor, reference .cpp:338
+  double p[36];          // stvl_frustum_t::p
+  int32_t lo[3], hi[3];  // conservative voxel-index AABB (inclusive)
+  double aux[4];         // lidar: min_d, max_d, tan(vFOV/2), |pad|
+};
+
+// -------- one marking reading on the device -----------------------------------------
+struct DevReading {
+  const uint8_t * data;
+  unsigned long long n_points;
+  uint32_t point_step, off_x, off_y, off_z;
+  double ox, oy, oz;
+  double now;
+  double zmin, zmax;
+  float mark_range_2;
+  int32_t filter;         // STVL_FILTER_PASSTHROUGH applies the z window in-kernel
+  uint32_t first_block;   // first CTA of this reading in the batched launch
+  uint32_t vec4;          // 1: point_step==16, offsets 0/4/8, 16 B aligned -> float4 loads
+};
+struct MarkBatch {
+  DevReading r[kMaxBatchReadings];
+  uint32_t n_readings;
+  uint32_t total_blocks;
+  uint32_t use_atomic_max;  // 1: batched mode (monotone clocks), 0: plain stores
+  uint32_t pad;
+};
+
+// -------- helpers -------------------------------------------------------------------
+__host__ __device__ inline uint64_t pack_leaf_key(int bx, int by, int bz)
+{
+  return ((uint64_t)(uint32_t)(bx + kLeafBias) << 42) | ((uint64_t)(uint32_t)(by + kLeafBias) << 21) |
+         (uint64_t)(uint32_t)(bz + kLeafBias);
+}
+__host__ __device__ inline void unpack_leaf_key(uint64_t k, int & bx, int & by, int & bz)
+{
+  bx = (int)((k >> 42) & 0x1FFFFF) - kLeafBias;
+  by = (int)((k >> 21) & 0x1FFFFF) - kLeafBias;
+  bz = (int)(k & 0x1FFFFF) - kLeafBias;
+}
+__host__ __device__ inline uint64_t pack_tile_key(int bx, int by)
+{
+  return ((uint64_t)(uint32_t)(bx + kLeafBias) << 21) | (uint64_t)(uint32_t)(by + kLeafBias);
+}
+__host__ __device__ inline void unpack_tile_key(uint64_t k, int & bx, int & by)
+{
+  bx = (int)((k >> 21) & 0x1FFFFF) - kLeafBias;
+  by = (int)(k & 0x1FFFFF) - kLeafBias;
+}
+__host__ __device__ inline bool leaf_coord_ok(int b) { return b >= -kLeafBias && b < kLeafBias; }
+__host__ __device__ inline uint64_t mix64(uint64_t x)
+{
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+  x ^= x >> 33;
+  return x;
+}
+__host__ __device__ inline int floor_div(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+__host__ __device__ inline bool shard_owns(int bx, int shard_index, int shard_count, int shard_width)
+{
+  if (shard_count <= 1) return true;
+  int s = floor_div(bx, shard_width) % shard_count;
+  if (s < 0) s += shard_count;
+  return s == shard_index;
+}
+
+#ifdef __CUDACC__
+// IndexToWorld, reference .cpp:446-460: OpenVDB indexToWorld (coord*vs) THEN + vs/2 — two roundings, never an FMA.
+__device__ __forceinline__ double index_to_world(int i, double vs, double half_vs)
+{
+  return __dadd_rn(__dmul_rn((double)i, vs), half_vs);
+}
+
+// DepthCameraFrustum::IsInside, reference depth_camera_frustum.cpp:286-304 (+ Dot :322-339).
+// The reference normalises p_delta per plane (1 sqrt + 3 div).  sign(n . normalize(d)) can only differ from
+// sign(n . d) inside a band of a few ulp around zero, so the un-normalised dot decides everywhere outside a
+// 1e-12 relative guard band; inside the band the reference's exact operation sequence is replayed
+// (correctly-rounded sqrt/div, no FMA), so the result is bit-identical to the CPU path everywhere.
+__device__ __forceinline__ bool depth_is_inside(const double * __restrict__ pl, double x, double y, double z)
+{
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double nx = pl[6 * k + 0], ny = pl[6 * k + 1], nz = pl[6 * k + 2];
+    double dx = __dsub_rn(x, pl[6 * k + 3]);
+    double dy = __dsub_rn(y, pl[6 * k + 4]);
+    double dz = __dsub_rn(z, pl[6 * k + 5]);
+    const double tx = nx * dx, ty = ny * dy, tz = nz * dz;
+    const double s = tx + ty + tz;
+    const double band = 1e-12 * (fabs(tx) + fabs(ty) + fabs(tz));
+    if (s > band) return false;
+    if (s >= -band) {
+      // exact replay: Eigen normalize() = divide by sqrt(squaredNorm) when squaredNorm > 0,
+      // squaredNorm = (x*x + y*y) + z*z; Dot = (nx*dx + ny*dy) + nz*dz
+      const double z2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+      if (z2 > 0.0) {
+        const double n = __dsqrt_rn(z2);
+        dx = __ddiv_rn(dx, n); dy = __ddiv_rn(dy, n); dz = __ddiv_rn(dz, n);
+      }
+      const double dot = __dadd_rn(__dadd_rn(__dmul_rn(nx, dx), __dmul_rn(ny, dy)), __dmul_rn(nz, dz));
+      if (dot > 0.) return false;
+    }
+  }
+  return true;
+}
+
+// Eigen QuaternionBase::_transformVector (q * v): uv = qv x v; uv += uv; v + w*uv + qv x uv — no FMA.
+__device__ __forceinline__ void quat_rotate_exact(double qx, double qy, double qz, double qw,
+                                                  double vx, double vy, double vz,
+                                                  double & rx, double & ry, double & rz)
+{
+  double ux = __dsub_rn(__dmul_rn(qy, vz), __dmul_rn(qz, vy));
+  double uy = __dsub_rn(__dmul_rn(qz, vx), __dmul_rn(qx, vz));
+  double uz = __dsub_rn(__dmul_rn(qx, vy), __dmul_rn(qy, vx));
+  ux = __dadd_rn(ux, ux); uy = __dadd_rn(uy, uy); uz = __dadd_rn(uz, uz);
+  const double cx = __dsub_rn(__dmul_rn(qy, uz), __dmul_rn(qz, uy));
+  const double cy = __dsub_rn(__dmul_rn(qz, ux), __dmul_rn(qx, uz));
+  const double cz = __dsub_rn(__dmul_rn(qx, uy), __dmul_rn(qy, ux));
+  rx = __dadd_rn(__dadd_rn(vx, __dmul_rn(qw, ux)), cx);
+  ry = __dadd_rn(__dadd_rn(vy, __dmul_rn(qw, uy)), cy);
+  rz = __dadd_rn(__dadd_rn(vz, __dmul_rn(qw, uz)), cz);
+}
+
+// ThreeDimensionalLidarFrustum::IsInside, reference three_dimensional_lidar_frustum.cpp:77-116.
+// `ambiguous` is raised when the hFOV test hinged on atan() within 1e-12 rad (CUDA vs glibc libm may differ there).
+__device__ __forceinline__ bool lidar_is_inside(const double * __restrict__ p, double x, double y, double z, bool & ambiguous)
+{
+  double tx, ty, tz;
+  quat_rotate_exact(p[3], p[4], p[5], p[6], __dsub_rn(x, p[0]), __dsub_rn(y, p[1]), __dsub_rn(z, p[2]), tx, ty, tz);
+  const double r2 = __dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty));
+  if (r2 > p[10] || r2 < p[9]) return false;
+  const double v_padded = __dadd_rn(fabs(tz), p[7]);
+  if (__ddiv_rn(__dmul_rn(v_padded, v_padded), r2) > p[8]) return false;
+  if (p[12] == 0.0) {
+    const double half_pi = 1.5707963267948966;   // M_PI / 2
+    if (tx > 0) {
+      const double a = fabs(atan(__ddiv_rn(ty, tx)));
+      if (fabs(a - p[11]) <= 1e-12) ambiguous = true;
+      if (a > p[11]) return false;
+    } else {
+      const double a = __dadd_rn(fabs(atan(__ddiv_rn(tx, ty))), half_pi);
+      if (fabs(a - p[11]) <= 1e-12) ambiguous = true;
+      if (a > p[11]) return false;
+    }
+  }
+  return true;
+}
+#endif  // __CUDACC__
+
+}  // namespace stvl

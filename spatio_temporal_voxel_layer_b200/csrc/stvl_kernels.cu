@@ -1,0 +1,897 @@
+// stvl_kernels.cu — sm_100a kernels of the per-cycle voxel update.
+//
+//   mark_kernel            Mark / operator()            reference spatio_temporal_voxel_grid.cpp:254-309
+//   sweep_kernel           ClearFrustums sweep          reference .cpp:96-224 (+ frustum IsInside)
+//   costmap_kernel         UpdateROSCostmap grid loop   reference spatio_temporal_voxel_layer.cpp:699-718
+//   reset_area_kernel      ResetGridArea                reference .cpp:397-418
+//   + small utility kernels (column compaction, dumps, hash rebuild, dense scatter for the multi-GPU merge)
+//
+// Everything is integer / FP64 scalar work bound by HBM traffic: no tensor cores.  All
+// arithmetic whose result feeds a comparison or a stored value uses the _rn intrinsics
+// (never contracted into FMA) in the reference's operation order, see SURVEY.md §7.
+#include "stvl_device.cuh"
+#include "stvl_kernels.h"
+
+namespace stvl {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+// =====================================================================================
+// hash helpers
+// =====================================================================================
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t * p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t * p) { return *reinterpret_cast<const volatile uint64_t *>(p); }
+
+// find-or-insert the column tile of leaf column (bx,by); tiles are never freed between rebuilds
+__device__ uint32_t tile_find_or_insert(const GridView & g, int bx, int by)
+{
+  const uint64_t key = pack_tile_key(bx, by);
+  uint32_t h = (uint32_t)mix64(key) & g.tile_hash_mask;
+  for (uint32_t probe = 0; probe <= g.tile_hash_mask; ++probe) {
+    uint64_t k = ld_volatile_u64(&g.tile_hash_keys[h]);
+    if (k == kEmptyKey) {
+      const uint64_t old = atomicCAS((unsigned long long *)&g.tile_hash_keys[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
+      if (old == kEmptyKey) {
+        const uint32_t t = atomicAdd(&g.ctr->tile_n, 1u);
+        if (t >= g.tile_capacity) {
+          atomicExch(&g.ctr->tile_overflow, 1u);
+          __threadfence();
+          *reinterpret_cast<volatile uint32_t *>(&g.tile_hash_vals[h]) = kOverflowSlot;
+          return kOverflowSlot;
+        }
+        g.tile_key[t] = key;
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t *>(&g.tile_hash_vals[h]) = t;
+        return t;
+      }
+      k = old;
+    }
+    if (k == key) {
+      uint32_t v;
+      while ((v = ld_volatile_u32(&g.tile_hash_vals[h])) == kInvalidSlot) { __nanosleep(20); }
+      return v;
+    }
+    h = (h + 1) & g.tile_hash_mask;
+  }
+  atomicExch(&g.ctr->tile_overflow, 1u);
+  return kOverflowSlot;
+}
+
+// hand out a leaf slot: first the free stack (as it stood when the kernel started), then fresh slots
+__device__ __forceinline__ uint32_t leaf_alloc(const GridView & g, uint32_t free_n0, uint32_t high_water0)
+{
+  const uint32_t i = atomicAdd(&g.ctr->alloc_cursor, 1u);
+  uint32_t slot;
+  if (i < free_n0) {
+    slot = g.free_slots[free_n0 - 1 - i];
+  } else {
+    const unsigned long long s = (unsigned long long)high_water0 + (i - free_n0);
+    slot = s >= g.leaf_capacity ? kOverflowSlot : (uint32_t)s;
+  }
+  return slot;
+}
+
+// find-or-insert a leaf; returns its pool slot (or kOverflowSlot)
+__device__ uint32_t leaf_find_or_insert(const GridView & g, uint64_t key, int bx, int by, uint32_t free_n0, uint32_t high_water0)
+{
+  uint32_t h = (uint32_t)mix64(key) & g.hash_mask;
+  for (uint32_t probe = 0; probe <= g.hash_mask; ++probe) {
+    uint64_t k = ld_volatile_u64(&g.hash_keys[h]);
+    if (k == kEmptyKey) {
+      const uint64_t old = atomicCAS((unsigned long long *)&g.hash_keys[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
+      if (old == kEmptyKey) {
+        const uint32_t slot = leaf_alloc(g, free_n0, high_water0);
+        if (slot == kOverflowSlot) {
+          atomicExch(&g.ctr->leaf_overflow, 1u);
+        } else {
+          const uint32_t tile = tile_find_or_insert(g, bx, by);
+          g.leaf_key[slot] = key;
+          g.leaf_hpos[slot] = h;
+          g.leaf_tile[slot] = tile;
+        }
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t *>(&g.hash_vals[h]) = slot;
+        return slot;
+      }
+      k = old;
+    }
+    if (k == key) {
+      uint32_t v;
+      while ((v = ld_volatile_u32(&g.hash_vals[h])) == kInvalidSlot) { __nanosleep(20); }
+      return v;
+    }
+    h = (h + 1) & g.hash_mask;   // other key or tombstone: keep probing
+  }
+  atomicExch(&g.ctr->leaf_overflow, 1u);
+  return kOverflowSlot;
+}
+
+// read-only lookup
+__device__ uint32_t leaf_find(const GridView & g, uint64_t key)
+{
+  uint32_t h = (uint32_t)mix64(key) & g.hash_mask;
+  for (uint32_t probe = 0; probe <= g.hash_mask; ++probe) {
+    const uint64_t k = g.hash_keys[h];
+    if (k == kEmptyKey) return kInvalidSlot;
+    if (k == key) return g.hash_vals[h];
+    h = (h + 1) & g.hash_mask;
+  }
+  return kInvalidSlot;
+}
+
+// last CTA of a kernel that allocated leaves folds the cursor into the allocator state
+__device__ __forceinline__ void alloc_epilogue(const GridView & g)
+{
+  __shared__ bool is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t ticket = atomicAdd(&g.ctr->done_ctr, 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    Counters * c = g.ctr;
+    const uint32_t cursor = ld_volatile_u32(&c->alloc_cursor);
+    const uint32_t free_n = ld_volatile_u32(&c->free_n);
+    const uint32_t hw = ld_volatile_u32(&c->high_water);
+    const uint32_t from_free = cursor < free_n ? cursor : free_n;
+    unsigned long long nhw = (unsigned long long)hw + (cursor - from_free);
+    if (nhw > g.leaf_capacity) nhw = g.leaf_capacity;
+    c->free_n = free_n - from_free;
+    c->high_water = (uint32_t)nhw;
+    c->alloc_cursor = 0;
+    c->done_ctr = 0;
+    __threadfence();
+  }
+}
+
+// =====================================================================================
+// Mark — reference .cpp:269-309
+// =====================================================================================
+struct PointXYZ { float x, y, z; bool ok; };
+
+__device__ __forceinline__ PointXYZ load_point(const DevReading & r, unsigned long long i)
+{
+  PointXYZ p;
+  if (i >= r.n_points) { p.x = p.y = p.z = 0.f; p.ok = false; return p; }
+  if (r.vec4) {
+    // coalesced 128-bit streaming load: the cloud is read exactly once
+    const float4 v = __ldcs(reinterpret_cast<const float4 *>(r.data) + i);
+    p.x = v.x; p.y = v.y; p.z = v.z;
+  } else {
+    const uint8_t * b = r.data + i * r.point_step;
+    if (((reinterpret_cast<uintptr_t>(b) | r.off_x | r.off_y | r.off_z) & 3u) == 0) {
+      p.x = __ldcs(reinterpret_cast<const float *>(b + r.off_x));
+      p.y = __ldcs(reinterpret_cast<const float *>(b + r.off_y));
+      p.z = __ldcs(reinterpret_cast<const float *>(b + r.off_z));
+    } else {
+      uint32_t w[3];
+      const uint32_t off[3] = {r.off_x, r.off_y, r.off_z};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const uint8_t * q = b + off[a];
+        w[a] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+      }
+      p.x = __uint_as_float(w[0]); p.y = __uint_as_float(w[1]); p.z = __uint_as_float(w[2]);
+    }
+  }
+  p.ok = true;
+  return p;
+}
+
+constexpr int kMarkThreads = 256;
+constexpr int kMarkPointsPerThread = 4;
+constexpr int kMarkPointsPerBlock = kMarkThreads * kMarkPointsPerThread;
+
+__global__ void __launch_bounds__(kMarkThreads)
+mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch)
+{
+  // which reading does this CTA belong to?
+  int ri = 0;
+#pragma unroll 1
+  for (int k = 1; k < (int)batch.n_readings; ++k) if (blockIdx.x >= batch.r[k].first_block) ri = k;
+  const DevReading & r = batch.r[ri];
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t free_n0 = g.ctr->free_n;
+  const uint32_t high_water0 = g.ctr->high_water;
+  const unsigned long long base = (unsigned long long)(blockIdx.x - r.first_block) * kMarkPointsPerBlock;
+
+  // issue all loads of this thread first (memory-level parallelism), then quantise
+  PointXYZ pts[kMarkPointsPerThread];
+#pragma unroll
+  for (int k = 0; k < kMarkPointsPerThread; ++k) pts[k] = load_point(r, base + (unsigned long long)k * kMarkThreads + threadIdx.x);
+
+  const unsigned long long now_bits = (unsigned long long)__double_as_longlong(r.now);
+  unsigned int drop_range = 0, drop_nonfinite = 0;
+
+#pragma unroll
+  for (int k = 0; k < kMarkPointsPerThread; ++k) {
+    const float fx = pts[k].x, fy = pts[k].y, fz = pts[k].z;
+    bool valid = pts[k].ok;
+    if (valid && !(isfinite(fx) && isfinite(fy) && isfinite(fz))) { valid = false; ++drop_nonfinite; }
+    if (valid && r.filter == 2) {   // PassThrough z window, reference measurement_buffer.cpp:165-175
+      const double zd = (double)fz;
+      if (zd < r.zmin || zd > r.zmax) valid = false;
+    }
+    int ix = 0, iy = 0, iz = 0;
+    if (valid) {
+      // .cpp:285-291  (double arithmetic, narrowed to float, compared against the float range^2 and 0.0001)
+      const double dx = __dsub_rn((double)fx, r.ox), dy = __dsub_rn((double)fy, r.oy), dz = __dsub_rn((double)fz, r.oz);
+      const float distance_2 = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+      if (distance_2 > r.mark_range_2 || (double)distance_2 < 0.0001) valid = false;
+    }
+    if (valid) {
+      // .cpp:293-303: shift negatives by one voxel (z tests y's sign — sic), multiply by 1/vs, truncate toward zero
+      const double X = fx < 0 ? __dsub_rn((double)fx, g.vs) : (double)fx;
+      const double Y = fy < 0 ? __dsub_rn((double)fy, g.vs) : (double)fy;
+      const double Z = fy < 0 ? __dsub_rn((double)fz, g.vs) : (double)fz;
+      const double gx = __dmul_rn(X, g.inv_vs), gy = __dmul_rn(Y, g.inv_vs), gz = __dmul_rn(Z, g.inv_vs);
+      const double lim = 8388608.0;   // 2^23 voxels = 2^20 leaves
+      if (fabs(gx) >= lim || fabs(gy) >= lim || fabs(gz) >= lim) { valid = false; ++drop_range; }
+      else { ix = __double2int_rz(gx); iy = __double2int_rz(gy); iz = __double2int_rz(gz); }
+    }
+    const int bx = ix >> 3, by = iy >> 3, bz = iz >> 3;
+    if (valid && !shard_owns(bx, g.shard_index, g.shard_count, g.shard_width)) valid = false;
+
+    // warp-level dedupe: one hash lookup per distinct leaf, one write per distinct voxel
+    const unsigned act = __ballot_sync(kFull, valid);
+    if (valid) {
+      const uint64_t key = pack_leaf_key(bx, by, bz);
+      const unsigned li = (unsigned)(((ix & 7) * 8 + (iy & 7)) * 8 + (iz & 7));
+      const unsigned peers = __match_any_sync(act, (unsigned long long)key);
+      const int leader = __ffs(peers) - 1;
+      uint32_t slot = 0;
+      if ((int)lane == leader) slot = leaf_find_or_insert(g, key, bx, by, free_n0, high_water0);
+      slot = __shfl_sync(peers, slot, leader);
+      const unsigned same = __match_any_sync(peers, li);
+      if (slot != kOverflowSlot && (int)lane == __ffs(same) - 1) {
+        atomicOr(&g.leaf_mask[(size_t)slot * 16 + (li >> 5)], 1u << (li & 31));
+        double * tp = &g.leaf_time[(size_t)slot * kLeafVoxels + li];
+        if (batch.use_atomic_max) atomicMax(reinterpret_cast<unsigned long long *>(tp), now_bits);
+        else *tp = r.now;   // MarkGridPoint: setValueOn overwrite, .cpp:421-430
+      }
+    }
+  }
+  if (drop_range) atomicAdd(&g.ctr->dropped_range, (unsigned long long)drop_range);
+  if (drop_nonfinite) atomicAdd(&g.ctr->dropped_nonfinite, (unsigned long long)drop_nonfinite);
+  alloc_epilogue(g);
+}
+
+// bulk load of (index, time) pairs — MarkGridPoint semantics (overwrite), for tests / restore
+__global__ void __launch_bounds__(256)
+load_voxels_kernel(const GridView g, const int32_t * __restrict__ vx, const int32_t * __restrict__ vy,
+                   const int32_t * __restrict__ vz, const double * __restrict__ vt, unsigned long long n)
+{
+  const uint32_t free_n0 = g.ctr->free_n;
+  const uint32_t high_water0 = g.ctr->high_water;
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int ix = vx[i], iy = vy[i], iz = vz[i];
+    const int bx = ix >> 3, by = iy >> 3, bz = iz >> 3;
+    if (!(leaf_coord_ok(bx) && leaf_coord_ok(by) && leaf_coord_ok(bz))) {
+      atomicAdd(&g.ctr->dropped_range, 1ull);
+    } else if (shard_owns(bx, g.shard_index, g.shard_count, g.shard_width)) {
+      const uint32_t slot = leaf_find_or_insert(g, pack_leaf_key(bx, by, bz), bx, by, free_n0, high_water0);
+      if (slot != kOverflowSlot) {
+        const unsigned li = (unsigned)(((ix & 7) * 8 + (iy & 7)) * 8 + (iz & 7));
+        atomicOr(&g.leaf_mask[(size_t)slot * 16 + (li >> 5)], 1u << (li & 31));
+        g.leaf_time[(size_t)slot * kLeafVoxels + li] = vt[i];
+      }
+    }
+  }
+  alloc_epilogue(g);
+}
+
+// =====================================================================================
+// Clear sweep — reference .cpp:149-224
+// =====================================================================================
+constexpr int kSweepThreads = 256;
+constexpr int kSweepWarps = kSweepThreads / 32;
+
+// classify a whole leaf against one frustum: 0 = no voxel centre can be inside, 1 = test per voxel, 2 = all inside
+__device__ __forceinline__ int classify_leaf(const DevFrustum & f, int bx, int by, int bz, double vs, double half_vs)
+{
+  if (f.type < 0) return 0;
+  if (!f.cull) return 1;
+  const int x0 = bx * 8, y0 = by * 8, z0 = bz * 8;
+  if (x0 + 7 < f.lo[0] || x0 > f.hi[0] || y0 + 7 < f.lo[1] || y0 > f.hi[1] || z0 + 7 < f.lo[2] || z0 > f.hi[2]) return 0;
+  // bounding sphere of the 512 voxel centres (conservative radius)
+  const double cx = ((double)x0 + 3.5) * vs + half_vs, cy = ((double)y0 + 3.5) * vs + half_vs, cz = ((double)z0 + 3.5) * vs + half_vs;
+  const double rad = 6.0621778264910705 * vs * 1.000001 + 1e-6;   // 3.5*sqrt(3)
+  if (f.type == 0) {
+    bool all_in = true;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double s = f.p[6 * k] * (cx - f.p[6 * k + 3]) + f.p[6 * k + 1] * (cy - f.p[6 * k + 4]) + f.p[6 * k + 2] * (cz - f.p[6 * k + 5]);
+      if (s > rad) return 0;
+      if (s > -rad) all_in = false;
+    }
+    return all_in ? 2 : 1;
+  }
+  // lidar hourglass: radial range and vertical cone, in the sensor frame (approximate transform + margins)
+  double tx, ty, tz;
+  quat_rotate_exact(f.p[3], f.p[4], f.p[5], f.p[6], cx - f.p[0], cy - f.p[1], cz - f.p[2], tx, ty, tz);
+  const double rc = sqrt(tx * tx + ty * ty);
+  if (rc - rad > f.aux[1] || rc + rad < f.aux[0]) return 0;
+  const double zmin = fabs(tz) - rad;
+  if (zmin > 0 && zmin - f.aux[3] > f.aux[2] * (rc + rad) + 1e-6) return 0;
+  return 1;
+}
+
+__device__ __forceinline__ void free_leaf(const GridView & g, uint32_t slot)
+{
+  const uint32_t h = g.leaf_hpos[slot];
+  g.hash_keys[h] = kTombKey;
+  g.hash_vals[h] = kInvalidSlot;
+  g.leaf_key[slot] = kEmptyKey;
+  const uint32_t i = atomicAdd(&g.ctr->free_n, 1u);
+  g.free_slots[i] = slot;
+  atomicAdd(&g.ctr->n_tombs, 1u);
+}
+
+__global__ void __launch_bounds__(kSweepThreads)
+sweep_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gmem, const int n_frustums, const double now,
+             const SweepOutputs out)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DevFrustum * fr = reinterpret_cast<DevFrustum *>(smem_raw);
+  __shared__ uint16_t s_list[kSweepWarps][kLeafVoxels];
+  __shared__ uint32_t s_mask[kSweepWarps][16];
+  __shared__ uint32_t s_part[kSweepWarps][kMaxFrustums / 32];
+  __shared__ uint32_t s_full[kSweepWarps][kMaxFrustums / 32];
+
+  // stage the frustum parameter blocks (planes / hourglass parameters) in shared memory
+  {
+    const int words = n_frustums * (int)(sizeof(DevFrustum) / 8);
+    const double * src = reinterpret_cast<const double *>(frustums_gmem);
+    double * dst = reinterpret_cast<double *>(fr);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned warp = threadIdx.x >> 5;
+  const uint32_t n_slots = g.ctr->high_water;
+  const uint32_t warps_total = gridDim.x * kSweepWarps;
+  const int n_chunks = (n_frustums + 31) >> 5;
+
+  unsigned int c_swept = 0, c_surv = 0, c_clear = 0, c_rewr = 0, c_amb = 0;
+  int bb_min_x = INT_MAX, bb_min_y = INT_MAX, bb_max_x = INT_MIN, bb_max_y = INT_MIN;
+
+  for (uint32_t slot = blockIdx.x * kSweepWarps + warp; slot < n_slots; slot += warps_total) {
+    const uint64_t key = g.leaf_key[slot];
+    if (key == kEmptyKey) continue;   // free slot
+    // each lane owns two voxel columns = 16 mask bits = local indices [lane*16, lane*16+16)
+    const uint32_t m16 = reinterpret_cast<const uint16_t *>(g.leaf_mask + (size_t)slot * 16)[lane];
+    if (__ballot_sync(kFull, m16 != 0) == 0) {
+      if (lane == 0) free_leaf(g, slot);   // nothing left in this leaf: pruneGrid, .cpp:223
+      continue;
+    }
+    // redistribute the active voxels evenly over the lanes: per-lane popcount, warp scan, index list in smem
+    const int cnt = __popc(m16);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(kFull, incl, d); if ((int)lane >= d) incl += v; }
+    const int total = __shfl_sync(kFull, incl, 31);
+    {
+      int pos = incl - cnt;
+      uint32_t m = m16;
+      while (m) { const int b = __ffs(m) - 1; m &= m - 1; s_list[warp][pos++] = (uint16_t)(lane * 16 + b); }
+    }
+    if (lane < 16) s_mask[warp][lane] = g.leaf_mask[(size_t)slot * 16 + lane];
+
+    int bx, by, bz;
+    unpack_leaf_key(key, bx, by, bz);
+    // leaf-level culling: one lane per frustum
+    unsigned any_cand = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+      const int f = c * 32 + (int)lane;
+      const int cls = f < n_frustums ? classify_leaf(fr[f], bx, by, bz, g.vs, g.half_vs) : 0;
+      const unsigned pm = __ballot_sync(kFull, cls == 1), fm = __ballot_sync(kFull, cls == 2);
+      if (lane == 0) { s_part[warp][c] = pm; s_full[warp][c] = fm; }
+      any_cand |= pm | fm;
+    }
+    __syncwarp();
+
+    const double * tbase = g.leaf_time + (size_t)slot * kLeafVoxels;
+    for (int i0 = 0; i0 < total; i0 += 32) {
+      const int i = i0 + (int)lane;
+      const bool have = i < total;
+      bool cleared = false, survived = false;
+      int ix = 0, iy = 0, iz = 0;
+      unsigned li = 0;
+      if (have) {
+        li = s_list[warp][i];
+        const double v = __ldcs(tbase + li);
+        ix = bx * 8 + (int)(li >> 6); iy = by * 8 + (int)((li >> 3) & 7); iz = bz * 8 + (int)(li & 7);
+        ++c_swept;
+        // .cpp:167-169
+        const double t = __dsub_rn(now, v);
+        double base_dur;
+        bool amb = false;
+        if (g.decay_model == 0) base_dur = __dsub_rn(g.voxel_decay, t);
+        else if (g.decay_model == 1) base_dur = __dmul_rn(g.voxel_decay, exp(-t));
+        else base_dur = g.voxel_decay;
+        // .cpp:171-198: first containing frustum, in reading order, decides
+        int hit = -1;
+        if (any_cand) {
+          const double wx = index_to_world(ix, g.vs, g.half_vs), wy = index_to_world(iy, g.vs, g.half_vs), wz = index_to_world(iz, g.vs, g.half_vs);
+          for (int c = 0; c < n_chunks && hit < 0; ++c) {
+            const unsigned fm = s_full[warp][c];
+            unsigned m = s_part[warp][c] | fm;
+            while (m) {
+              const int b = __ffs(m) - 1; m &= m - 1;
+              const int f = c * 32 + b;
+              bool in;
+              if ((fm >> b) & 1u) in = true;
+              else if (fr[f].type == 0) in = depth_is_inside(fr[f].p, wx, wy, wz);
+              else in = lidar_is_inside(fr[f].p, wx, wy, wz, amb);
+              if (in) { hit = f; break; }
+            }
+          }
+        }
+        if (hit >= 0) {
+          // .cpp:179-197; GetFrustumAcceleration .cpp:334-341 = ((1./6.)*factor) * ((t*t)*t)
+          const double accel = __dmul_rn(fr[hit].c16f, __dmul_rn(__dmul_rn(t, t), t));
+          const double tud = __dsub_rn(base_dur, accel);
+          if (g.decay_model == 1 && fabs(tud) <= 1e-12 * fmax(fabs(base_dur), fabs(accel))) amb = true;
+          if (tud < 0.) cleared = true;
+          else {
+            const double nv = __dsub_rn(v, accel);
+            if (__double_as_longlong(nv) != __double_as_longlong(v)) { g.leaf_time[(size_t)slot * kLeafVoxels + li] = nv; ++c_rewr; }
+          }
+        } else if (base_dur < 0.) {
+          cleared = true;   // .cpp:203-211
+        }
+        survived = !cleared;
+        if (cleared) {
+          atomicAnd(&s_mask[warp][li >> 5], ~(1u << (li & 31)));
+          ++c_clear;
+          bb_min_x = min(bb_min_x, ix); bb_max_x = max(bb_max_x, ix);
+          bb_min_y = min(bb_min_y, iy); bb_max_y = max(bb_max_y, iy);
+        } else {
+          ++c_surv;
+        }
+        if (amb) {
+          ++c_amb;
+          if (out.ambiguous) {
+            const unsigned long long a = atomicAdd(&g.ctr->n_ambiguous_out, 1ull);
+            if (a < out.ambiguous_cap) { out.ambiguous[3 * a] = ix; out.ambiguous[3 * a + 1] = iy; out.ambiguous[3 * a + 2] = iz; }
+          }
+        }
+      }
+      // optional lists: warp-aggregated appends
+      if (out.points) {   // PopulateCostmapAndPointcloud .cpp:234-240: Point32 = (float) voxel centre
+        const unsigned sm = __ballot_sync(kFull, survived);
+        if (sm) {
+          unsigned long long b0 = 0;
+          if (lane == (unsigned)(__ffs(sm) - 1)) b0 = atomicAdd(&g.ctr->n_points_out, (unsigned long long)__popc(sm));
+          b0 = __shfl_sync(kFull, b0, __ffs(sm) - 1);
+          if (survived) {
+            const unsigned long long o = b0 + __popc(sm & ((1u << lane) - 1));
+            if (o < out.points_cap) {
+              out.points[3 * o] = (float)index_to_world(ix, g.vs, g.half_vs);
+              out.points[3 * o + 1] = (float)index_to_world(iy, g.vs, g.half_vs);
+              out.points[3 * o + 2] = (float)index_to_world(iz, g.vs, g.half_vs);
+            }
+          }
+        }
+      }
+      if (out.cleared) {   // cleared_cells.insert, .cpp:213-215
+        const unsigned cm = __ballot_sync(kFull, cleared);
+        if (cm) {
+          unsigned long long b0 = 0;
+          if (lane == (unsigned)(__ffs(cm) - 1)) b0 = atomicAdd(&g.ctr->n_cleared_out, (unsigned long long)__popc(cm));
+          b0 = __shfl_sync(kFull, b0, __ffs(cm) - 1);
+          if (cleared) {
+            const unsigned long long o = b0 + __popc(cm & ((1u << lane) - 1));
+            if (o < out.cleared_cap) { out.cleared[2 * o] = ix; out.cleared[2 * o + 1] = iy; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // write back changed mask words; count survivors per (x,y) column into the leaf's column tile
+    uint32_t w = 0;
+    if (lane < 16) {
+      w = s_mask[warp][lane];
+      if (w != g.leaf_mask[(size_t)slot * 16 + lane]) g.leaf_mask[(size_t)slot * 16 + lane] = w;
+    }
+    const bool leaf_alive = __ballot_sync(kFull, w != 0) != 0;
+    if (!leaf_alive) {
+      if (lane == 0) free_leaf(g, slot);
+    } else {
+      const uint32_t tile = g.leaf_tile[slot];
+      if (tile != kOverflowSlot) {
+        const uint32_t two = reinterpret_cast<const uint16_t *>(s_mask[warp])[lane];
+        const int c0 = __popc(two & 0xFFu), c1 = __popc(two >> 8);
+        // PopulateCostmapAndPointcloud .cpp:242-250: _cost_map[(x,y)] += 1 per surviving voxel
+        if (c0) atomicAdd(&g.tile_count[(size_t)tile * 64 + 2 * lane], (uint32_t)c0);
+        if (c1) atomicAdd(&g.tile_count[(size_t)tile * 64 + 2 * lane + 1], (uint32_t)c1);
+      }
+    }
+    __syncwarp();
+  }
+
+  // block-level reduction of the statistics
+  __shared__ unsigned int s_red[5];
+  __shared__ int s_bb[4];
+  if (threadIdx.x == 0) { s_red[0] = s_red[1] = s_red[2] = s_red[3] = s_red[4] = 0; s_bb[0] = s_bb[1] = INT_MAX; s_bb[2] = s_bb[3] = INT_MIN; }
+  __syncthreads();
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    c_swept += __shfl_xor_sync(kFull, c_swept, d); c_surv += __shfl_xor_sync(kFull, c_surv, d);
+    c_clear += __shfl_xor_sync(kFull, c_clear, d); c_rewr += __shfl_xor_sync(kFull, c_rewr, d);
+    c_amb += __shfl_xor_sync(kFull, c_amb, d);
+    bb_min_x = min(bb_min_x, __shfl_xor_sync(kFull, bb_min_x, d)); bb_min_y = min(bb_min_y, __shfl_xor_sync(kFull, bb_min_y, d));
+    bb_max_x = max(bb_max_x, __shfl_xor_sync(kFull, bb_max_x, d)); bb_max_y = max(bb_max_y, __shfl_xor_sync(kFull, bb_max_y, d));
+  }
+  if (lane == 0) {
+    atomicAdd(&s_red[0], c_swept); atomicAdd(&s_red[1], c_surv); atomicAdd(&s_red[2], c_clear);
+    atomicAdd(&s_red[3], c_rewr); atomicAdd(&s_red[4], c_amb);
+    atomicMin(&s_bb[0], bb_min_x); atomicMin(&s_bb[1], bb_min_y); atomicMax(&s_bb[2], bb_max_x); atomicMax(&s_bb[3], bb_max_y);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Counters * c = g.ctr;
+    if (s_red[0]) atomicAdd(&c->n_swept, (unsigned long long)s_red[0]);
+    if (s_red[1]) atomicAdd(&c->n_survived, (unsigned long long)s_red[1]);
+    if (s_red[2]) {
+      atomicAdd(&c->n_cleared, (unsigned long long)s_red[2]);
+      atomicMin(&c->cb_min_x, s_bb[0]); atomicMin(&c->cb_min_y, s_bb[1]);
+      atomicMax(&c->cb_max_x, s_bb[2]); atomicMax(&c->cb_max_y, s_bb[3]);
+    }
+    if (s_red[3]) atomicAdd(&c->n_rewritten, (unsigned long long)s_red[3]);
+    if (s_red[4]) atomicAdd(&c->n_ambiguous, (unsigned long long)s_red[4]);
+  }
+}
+
+// zero the column tiles and the per-sweep counters before a sweep
+__global__ void __launch_bounds__(256) sweep_prologue_kernel(const GridView g)
+{
+  const uint32_t n_words = g.ctr->tile_n < g.tile_capacity ? g.ctr->tile_n * 64u : g.tile_capacity * 64u;
+  uint4 * t4 = reinterpret_cast<uint4 *>(g.tile_count);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words / 4; i += gridDim.x * blockDim.x) t4[i] = make_uint4(0, 0, 0, 0);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    Counters * c = g.ctr;
+    c->n_swept = c->n_survived = c->n_cleared = c->n_rewritten = c->n_ambiguous = 0;
+    c->cb_min_x = c->cb_min_y = INT_MAX; c->cb_max_x = c->cb_max_y = INT_MIN;
+    c->n_points_out = c->n_cleared_out = c->n_ambiguous_out = 0;
+  }
+}
+
+// =====================================================================================
+// Costmap — reference spatio_temporal_voxel_layer.cpp:699-718 (grid loop) on the tile counts
+// =====================================================================================
+// nav2 Costmap2D::worldToMap (external): wx >= origin, (unsigned)((wx-origin)/resolution) < size
+__device__ __forceinline__ bool world_to_map(double wx, double wy, const CostmapDev & p, unsigned & mx, unsigned & my)
+{
+  if (wx < p.origin_x || wy < p.origin_y) return false;
+  mx = __double2uint_rz(__ddiv_rn(__dsub_rn(wx, p.origin_x), p.resolution));
+  my = __double2uint_rz(__ddiv_rn(__dsub_rn(wy, p.origin_y), p.resolution));
+  return mx < p.size_x && my < p.size_y;
+}
+
+__device__ __forceinline__ void costmap_reduce_and_publish(Counters * c, unsigned n, int mnx, int mny, int mxx, int mxy)
+{
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    n += __shfl_xor_sync(kFull, n, d);
+    mnx = min(mnx, __shfl_xor_sync(kFull, mnx, d)); mny = min(mny, __shfl_xor_sync(kFull, mny, d));
+    mxx = max(mxx, __shfl_xor_sync(kFull, mxx, d)); mxy = max(mxy, __shfl_xor_sync(kFull, mxy, d));
+  }
+  if ((threadIdx.x & 31) == 0 && n) {
+    atomicAdd(&c->n_marked, (unsigned long long)n);
+    atomicMin(&c->mk_min_x, mnx); atomicMin(&c->mk_min_y, mny); atomicMax(&c->mk_max_x, mxx); atomicMax(&c->mk_max_y, mxy);
+  }
+}
+
+__global__ void __launch_bounds__(256) costmap_kernel(const GridView g, const CostmapDev p, uint8_t * __restrict__ costmap)
+{
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t n_tiles = min(g.ctr->tile_n, g.tile_capacity);
+  const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+  unsigned n = 0;
+  int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
+  for (uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tiles; t += warps_total) {
+    const uint2 cc = reinterpret_cast<const uint2 *>(g.tile_count + (size_t)t * 64)[lane];   // columns 2*lane, 2*lane+1
+    if ((cc.x | cc.y) == 0) continue;
+    int bx, by;
+    unpack_tile_key(g.tile_key[t], bx, by);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const uint32_t cnt = k ? cc.y : cc.x;
+      const int col = 2 * (int)lane + k;
+      if (cnt == 0 || (int)cnt < p.mark_threshold) continue;   // static_cast<int>(count) >= _mark_threshold, :712
+      const int ix = bx * 8 + (col >> 3), iy = by * 8 + (col & 7);
+      unsigned mx, my;
+      if (world_to_map(index_to_world(ix, g.vs, g.half_vs), index_to_world(iy, g.vs, g.half_vs), p, mx, my)) {
+        costmap[(size_t)my * p.size_x + mx] = p.lethal;   // :715
+        ++n; mnx = min(mnx, ix); mny = min(mny, iy); mxx = max(mxx, ix); mxy = max(mxy, iy);   // touch(), :716
+      }
+    }
+  }
+  costmap_reduce_and_publish(g.ctr, n, mnx, mny, mxx, mxy);
+}
+
+__global__ void costmap_prologue_kernel(const GridView g)
+{
+  Counters * c = g.ctr;
+  c->n_marked = 0;
+  c->mk_min_x = c->mk_min_y = INT_MAX; c->mk_max_x = c->mk_max_y = INT_MIN;
+  c->n_columns_out = 0;
+}
+
+// occupied columns of the last sweep as (ix, iy, count) — GetFlattenedCostmap, reference .cpp:312-317
+__global__ void __launch_bounds__(256) columns_kernel(const GridView g, int32_t * __restrict__ oix, int32_t * __restrict__ oiy,
+                                                      uint32_t * __restrict__ ocnt, unsigned long long cap)
+{
+  const uint32_t n_tiles = min(g.ctr->tile_n, g.tile_capacity);
+  const unsigned long long total = (unsigned long long)n_tiles * 64;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t cnt = g.tile_count[i];
+    if (!cnt) continue;
+    const unsigned long long o = atomicAdd(&g.ctr->n_columns_out, 1ull);
+    if (o < cap) {
+      int bx, by;
+      unpack_tile_key(g.tile_key[i >> 6], bx, by);
+      const int col = (int)(i & 63);
+      if (oix) oix[o] = bx * 8 + (col >> 3);
+      if (oiy) oiy[o] = by * 8 + (col & 7);
+      if (ocnt) ocnt[o] = cnt;
+    }
+  }
+}
+
+// multi-GPU merge: scatter-add this shard's column counts into a dense window (then reduced over NVLink)
+__global__ void __launch_bounds__(256) columns_to_dense_kernel(const GridView g, int ix0, int iy0, uint32_t nx, uint32_t ny, uint32_t * __restrict__ dense)
+{
+  const uint32_t n_tiles = min(g.ctr->tile_n, g.tile_capacity);
+  const unsigned long long total = (unsigned long long)n_tiles * 64;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t cnt = g.tile_count[i];
+    if (!cnt) continue;
+    int bx, by;
+    unpack_tile_key(g.tile_key[i >> 6], bx, by);
+    const int col = (int)(i & 63);
+    const long long dx = (long long)(bx * 8 + (col >> 3)) - ix0, dy = (long long)(by * 8 + (col & 7)) - iy0;
+    if (dx >= 0 && dy >= 0 && dx < (long long)nx && dy < (long long)ny) atomicAdd(&dense[(size_t)dy * nx + dx], cnt);
+  }
+}
+
+__global__ void __launch_bounds__(256) costmap_from_dense_kernel(const GridView g, const uint32_t * __restrict__ dense, int ix0, int iy0,
+                                                                 uint32_t nx, uint32_t ny, const CostmapDev p, uint8_t * __restrict__ costmap)
+{
+  const unsigned long long total = (unsigned long long)nx * ny;
+  unsigned n = 0;
+  int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t cnt = dense[i];
+    if (cnt == 0 || (int)cnt < p.mark_threshold) continue;
+    const int ix = ix0 + (int)(i % nx), iy = iy0 + (int)(i / nx);
+    unsigned mx, my;
+    if (world_to_map(index_to_world(ix, g.vs, g.half_vs), index_to_world(iy, g.vs, g.half_vs), p, mx, my)) {
+      costmap[(size_t)my * p.size_x + mx] = p.lethal;
+      ++n; mnx = min(mnx, ix); mny = min(mny, iy); mxx = max(mxx, ix); mxy = max(mxy, iy);
+    }
+  }
+  costmap_reduce_and_publish(g.ctr, n, mnx, mny, mxx, mxy);
+}
+
+// =====================================================================================
+// ResetGridArea — reference .cpp:397-418 (x,y only: whole voxel columns are cleared)
+// =====================================================================================
+__global__ void __launch_bounds__(256) reset_area_kernel(const GridView g, double sx, double sy, double ex, double ey, int invert)
+{
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t n_slots = g.ctr->high_water;
+  const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); slot < n_slots; slot += warps_total) {
+    const uint64_t key = g.leaf_key[slot];
+    if (key == kEmptyKey) continue;
+    int bx, by, bz;
+    unpack_leaf_key(key, bx, by, bz);
+    uint16_t * m = reinterpret_cast<uint16_t *>(g.leaf_mask + (size_t)slot * 16) + lane;
+    uint32_t m16 = *m;
+    if (!m16) continue;
+    const uint32_t before = m16;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int col = 2 * (int)lane + k;
+      const double wx = index_to_world(bx * 8 + (col >> 3), g.vs, g.half_vs), wy = index_to_world(by * 8 + (col & 7), g.vs, g.half_vs);
+      const bool in_x = wx > sx && wx < ex, in_y = wy > sy && wy < ey;
+      const bool in_range = in_x && in_y;
+      if (in_range == (invert != 0)) m16 &= k ? 0x00FFu : 0xFF00u;
+    }
+    if (m16 != before) *m = (uint16_t)m16;
+  }
+}
+
+// =====================================================================================
+// dumps, counts, maintenance
+// =====================================================================================
+__global__ void __launch_bounds__(256) count_active_kernel(const GridView g)
+{
+  const uint32_t n_slots = g.ctr->high_water;
+  unsigned long long n = 0;
+  unsigned live = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned long long)n_slots * 16; i += (unsigned long long)gridDim.x * blockDim.x) {
+    if (g.leaf_key[i >> 4] == kEmptyKey) continue;
+    n += __popc(g.leaf_mask[i]);
+    if ((i & 15) == 0) ++live;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { n += __shfl_xor_sync(kFull, n, d); live += __shfl_xor_sync(kFull, live, d); }
+  if ((threadIdx.x & 31) == 0) { if (n) atomicAdd(&g.ctr->n_active, n); if (live) atomicAdd(&g.ctr->live_leaves, live); }
+}
+
+__global__ void __launch_bounds__(256) dump_voxels_kernel(const GridView g, int32_t * __restrict__ ox, int32_t * __restrict__ oy,
+                                                          int32_t * __restrict__ oz, double * __restrict__ ot, unsigned long long cap)
+{
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t n_slots = g.ctr->high_water;
+  const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); slot < n_slots; slot += warps_total) {
+    const uint64_t key = g.leaf_key[slot];
+    if (key == kEmptyKey) continue;
+    int bx, by, bz;
+    unpack_leaf_key(key, bx, by, bz);
+    uint32_t m = reinterpret_cast<const uint16_t *>(g.leaf_mask + (size_t)slot * 16)[lane];
+    const int cnt = __popc(m);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(kFull, incl, d); if ((int)lane >= d) incl += v; }
+    const int total = __shfl_sync(kFull, incl, 31);
+    if (!total) continue;
+    unsigned long long b0 = 0;
+    if (lane == 0) b0 = atomicAdd(&g.ctr->n_voxels_out, (unsigned long long)total);
+    b0 = __shfl_sync(kFull, b0, 0);
+    unsigned long long o = b0 + (incl - cnt);
+    while (m) {
+      const int b = __ffs(m) - 1; m &= m - 1;
+      const unsigned li = lane * 16 + b;
+      if (o < cap) {
+        if (ox) ox[o] = bx * 8 + (int)(li >> 6);
+        if (oy) oy[o] = by * 8 + (int)((li >> 3) & 7);
+        if (oz) oz[o] = bz * 8 + (int)(li & 7);
+        if (ot) ot[o] = g.leaf_time[(size_t)slot * kLeafVoxels + li];
+      }
+      ++o;
+    }
+  }
+}
+
+// re-insert every live leaf into a freshly cleared hash (drops tombstones / overflow markers)
+__global__ void __launch_bounds__(256) rebuild_hash_kernel(const GridView g)
+{
+  const uint32_t n_slots = g.ctr->high_water;
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += gridDim.x * blockDim.x) {
+    const uint64_t key = g.leaf_key[slot];
+    if (key == kEmptyKey) continue;
+    uint32_t h = (uint32_t)mix64(key) & g.hash_mask;
+    for (;;) {
+      const uint64_t old = atomicCAS((unsigned long long *)&g.hash_keys[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
+      if (old == kEmptyKey) { g.hash_vals[h] = slot; g.leaf_hpos[slot] = h; break; }
+      h = (h + 1) & g.hash_mask;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) g.ctr->n_tombs = 0;
+}
+
+// after the tile pool was rebuilt from scratch: give every live leaf its tile again
+__global__ void __launch_bounds__(256) reassign_tiles_kernel(const GridView g)
+{
+  const uint32_t n_slots = g.ctr->high_water;
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += gridDim.x * blockDim.x) {
+    const uint64_t key = g.leaf_key[slot];
+    if (key == kEmptyKey) continue;
+    int bx, by, bz;
+    unpack_leaf_key(key, bx, by, bz);
+    g.leaf_tile[slot] = tile_find_or_insert(g, bx, by);
+  }
+}
+
+// =====================================================================================
+// host-callable launchers
+// =====================================================================================
+static inline int grid_for(unsigned long long work_items, int per_block, int max_blocks)
+{
+  unsigned long long b = (work_items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > (unsigned long long)max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, cudaStream_t s)
+{
+  if (batch.total_blocks == 0) return cudaSuccess;
+  mark_kernel<<<batch.total_blocks, kMarkThreads, 0, s>>>(g, batch);
+  return cudaGetLastError();
+}
+uint32_t mark_blocks_for(unsigned long long n_points)
+{
+  return (uint32_t)((n_points + kMarkPointsPerBlock - 1) / kMarkPointsPerBlock);
+}
+cudaError_t launch_load_voxels(const GridView & g, const int32_t * x, const int32_t * y, const int32_t * z, const double * t,
+                               unsigned long long n, cudaStream_t s)
+{
+  if (n == 0) return cudaSuccess;
+  load_voxels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g, x, y, z, t, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, int n_frustums, double now, const SweepOutputs & out,
+                         uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s)
+{
+  sweep_prologue_kernel<<<sm_count * 2, 256, 0, s>>>(g);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const size_t dyn = (size_t)n_frustums * sizeof(DevFrustum);
+  if (dyn > 48 * 1024) {
+    e = cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+  }
+  const int blocks = grid_for(leaf_slots_upper_bound, kSweepWarps, sm_count * 8);
+  sweep_kernel<<<blocks, kSweepThreads, dyn, s>>>(g, frustums_dev, n_frustums, now, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_costmap(const GridView & g, const CostmapDev & p, uint8_t * costmap_dev, uint32_t tiles_upper_bound, int sm_count, cudaStream_t s)
+{
+  cudaError_t e = cudaMemsetAsync(costmap_dev, p.default_value, (size_t)p.size_x * p.size_y, s);   // Costmap2D::resetMaps, :705
+  if (e != cudaSuccess) return e;
+  costmap_prologue_kernel<<<1, 1, 0, s>>>(g);
+  costmap_kernel<<<grid_for(tiles_upper_bound, 8, sm_count * 8), 256, 0, s>>>(g, p, costmap_dev);
+  return cudaGetLastError();
+}
+cudaError_t launch_columns(const GridView & g, int32_t * ix, int32_t * iy, uint32_t * cnt, unsigned long long cap,
+                           uint32_t tiles_upper_bound, int sm_count, cudaStream_t s)
+{
+  costmap_prologue_kernel<<<1, 1, 0, s>>>(g);
+  columns_kernel<<<grid_for((unsigned long long)tiles_upper_bound * 64, 256, sm_count * 8), 256, 0, s>>>(g, ix, iy, cnt, cap);
+  return cudaGetLastError();
+}
+cudaError_t launch_columns_to_dense(const GridView & g, int ix0, int iy0, uint32_t nx, uint32_t ny, uint32_t * dense,
+                                    uint32_t tiles_upper_bound, int sm_count, cudaStream_t s)
+{
+  columns_to_dense_kernel<<<grid_for((unsigned long long)tiles_upper_bound * 64, 256, sm_count * 8), 256, 0, s>>>(g, ix0, iy0, nx, ny, dense);
+  return cudaGetLastError();
+}
+cudaError_t launch_costmap_from_dense(const GridView & g, const uint32_t * dense, int ix0, int iy0, uint32_t nx, uint32_t ny,
+                                      const CostmapDev & p, uint8_t * costmap_dev, int sm_count, cudaStream_t s)
+{
+  cudaError_t e = cudaMemsetAsync(costmap_dev, p.default_value, (size_t)p.size_x * p.size_y, s);
+  if (e != cudaSuccess) return e;
+  costmap_prologue_kernel<<<1, 1, 0, s>>>(g);
+  costmap_from_dense_kernel<<<grid_for((unsigned long long)nx * ny, 256, sm_count * 8), 256, 0, s>>>(g, dense, ix0, iy0, nx, ny, p, costmap_dev);
+  return cudaGetLastError();
+}
+cudaError_t launch_reset_area(const GridView & g, double sx, double sy, double ex, double ey, int invert,
+                              uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s)
+{
+  reset_area_kernel<<<grid_for(leaf_slots_upper_bound, 8, sm_count * 8), 256, 0, s>>>(g, sx, sy, ex, ey, invert);
+  return cudaGetLastError();
+}
+cudaError_t launch_count_active(const GridView & g, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s)
+{
+  count_active_kernel<<<grid_for((unsigned long long)leaf_slots_upper_bound * 16, 256, sm_count * 8), 256, 0, s>>>(g);
+  return cudaGetLastError();
+}
+cudaError_t launch_dump_voxels(const GridView & g, int32_t * x, int32_t * y, int32_t * z, double * t, unsigned long long cap,
+                               uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s)
+{
+  dump_voxels_kernel<<<grid_for(leaf_slots_upper_bound, 8, sm_count * 8), 256, 0, s>>>(g, x, y, z, t, cap);
+  return cudaGetLastError();
+}
+cudaError_t launch_rebuild_hash(const GridView & g, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s)
+{
+  rebuild_hash_kernel<<<grid_for(leaf_slots_upper_bound, 256, sm_count * 8), 256, 0, s>>>(g);
+  return cudaGetLastError();
+}
+cudaError_t launch_reassign_tiles(const GridView & g, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s)
+{
+  reassign_tiles_kernel<<<grid_for(leaf_slots_upper_bound, 256, sm_count * 8), 256, 0, s>>>(g);
+  return cudaGetLastError();
+}
+
+}  // namespace stvl

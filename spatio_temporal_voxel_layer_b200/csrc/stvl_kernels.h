@@ -1,0 +1,48 @@
+// stvl_kernels.h — launch interface between the C-ABI host code (stvl_api.cu) and the kernels.
+#pragma once
+#include <climits>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "stvl_device.cuh"
+
+namespace stvl {
+
+// optional per-sweep lists (NULL = not wanted)
+struct SweepOutputs {
+  float * points;            // survivors' voxel centres, xyz float32 (GetOccupancyPointCloud)
+  unsigned long long points_cap;
+  int32_t * cleared;         // (ix,iy) per cleared voxel (cleared_cells)
+  unsigned long long cleared_cap;
+  int32_t * ambiguous;       // (ix,iy,iz) of libm-dependent razor-edge decisions
+  unsigned long long ambiguous_cap;
+};
+
+struct CostmapDev {
+  double origin_x, origin_y, resolution;
+  uint32_t size_x, size_y;
+  int32_t mark_threshold;
+  uint8_t default_value, lethal;
+};
+
+cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, cudaStream_t s);
+uint32_t mark_blocks_for(unsigned long long n_points);
+cudaError_t launch_load_voxels(const GridView & g, const int32_t * x, const int32_t * y, const int32_t * z, const double * t,
+                               unsigned long long n, cudaStream_t s);
+cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, int n_frustums, double now, const SweepOutputs & out,
+                         uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s);
+cudaError_t launch_costmap(const GridView & g, const CostmapDev & p, uint8_t * costmap_dev, uint32_t tiles_upper_bound, int sm_count, cudaStream_t s);
+cudaError_t launch_columns(const GridView & g, int32_t * ix, int32_t * iy, uint32_t * cnt, unsigned long long cap,
+                           uint32_t tiles_upper_bound, int sm_count, cudaStream_t s);
+cudaError_t launch_columns_to_dense(const GridView & g, int ix0, int iy0, uint32_t nx, uint32_t ny, uint32_t * dense,
+                                    uint32_t tiles_upper_bound, int sm_count, cudaStream_t s);
+cudaError_t launch_costmap_from_dense(const GridView & g, const uint32_t * dense, int ix0, int iy0, uint32_t nx, uint32_t ny,
+                                      const CostmapDev & p, uint8_t * costmap_dev, int sm_count, cudaStream_t s);
+cudaError_t launch_reset_area(const GridView & g, double sx, double sy, double ex, double ey, int invert,
+                              uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s);
+cudaError_t launch_count_active(const GridView & g, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s);
+cudaError_t launch_dump_voxels(const GridView & g, int32_t * x, int32_t * y, int32_t * z, double * t, unsigned long long cap,
+                               uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s);
+cudaError_t launch_rebuild_hash(const GridView & g, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s);
+cudaError_t launch_reassign_tiles(const GridView & g, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s);
+
+}  // namespace stvl

@@ -1,0 +1,208 @@
+"""Known-answer tests that pin the CPU oracle to the reference SOURCE (the reference ships no tests or
+golden vectors: SURVEY.md §4/§8c — "parity unpinned").  Every expected value below was derived by hand
+from the cited reference lines, independently of oracle/stvl_oracle.cpp.
+Paths: GRID = spatio_temporal_voxel_layer/src/spatio_temporal_voxel_grid.cpp,
+DEPTH = .../src/frustum_models/depth_camera_frustum.cpp, LIDAR = .../three_dimensional_lidar_frustum.cpp,
+LAYER = .../src/spatio_temporal_voxel_layer.cpp."""
+import math
+
+import numpy as np
+import pytest
+
+
+def test_voxel_size_is_float_rounded(oracle):
+    # GRID:51,54 — ctor takes `const float &`, member is double
+    g = oracle.OracleGrid(0.05)
+    assert g.voxel_size == 0.05000000074505806
+    assert 1.0 / g.voxel_size == 19.99999970197678
+    g2 = oracle.OracleGrid(0.02)
+    assert g2.voxel_size == 0.019999999552965164
+
+
+@pytest.mark.parametrize("pt,expected", [
+    ((1.0, 0.0, 0.0), (19, 0, 0)),        # 1.0 * 19.99999970197678 = 19.9999997 -> trunc 19 (not floor(1/0.05)=20)
+    ((-0.05, 0.0, 0.0), (-2, 0, 0)),      # negative: shifted by -vs first, then truncated toward zero (GRID:293)
+    ((0.3, -0.2, 0.7), (6, -5, 12)),      # z is shifted because y < 0 (sic, GRID:295): (0.7-0.05)*20 = 12.99 -> 12
+    ((0.3, 0.2, -0.7), (6, 4, -13)),      # z negative but y >= 0: NOT shifted: -0.7*20 = -13.99 -> -13
+    ((-1e-3, 1e-3, 0.0), (-1, 0, 0)),     # (-0.001-0.05)*20 = -1.02 -> -1
+    ((0.0, 0.0, 0.0), (0, 0, 0)),
+])
+def test_quantisation_quirks(oracle, pt, expected):
+    g = oracle.OracleGrid(0.05)
+    # independent restatement in numpy float64 of GRID:293-303
+    vs = float(np.float32(0.05))
+    f = [float(np.float32(v)) for v in pt]
+    x = f[0] - vs if f[0] < 0 else f[0]
+    y = f[1] - vs if f[1] < 0 else f[1]
+    z = f[2] - vs if f[1] < 0 else f[2]
+    manual = tuple(int(math.trunc(v * (1.0 / vs))) for v in (x, y, z))
+    assert manual == expected
+    assert g.quantise(*pt) == expected
+
+
+def test_index_to_world_two_roundings(oracle):
+    # GRID:446-460: coord*vs, then + vs/2
+    g = oracle.OracleGrid(0.05)
+    vs = g.voxel_size
+    for i in (-754, -1, 0, 7, 19, 100003):
+        w = g.index_to_world(i, i, i)
+        assert w[0] == i * vs + vs / 2.0
+
+
+def test_decay_models(oracle):
+    # GRID:320-331: 0 linear, 1 exponential, anything else persistent
+    assert oracle.OracleGrid(0.05, decay_model=0, voxel_decay=15.0).decay_duration(4.0) == 11.0
+    assert oracle.OracleGrid(0.05, decay_model=1, voxel_decay=15.0).decay_duration(4.0) == 15.0 * math.exp(-4.0)
+    assert oracle.OracleGrid(0.05, decay_model=2, voxel_decay=15.0).decay_duration(4.0) == 15.0
+    assert oracle.OracleGrid(0.05, decay_model=-1, voxel_decay=15.0).decay_duration(4.0) == 15.0
+    # GRID:334-341: 1/6 * factor * t^3 in that association
+    assert oracle.frustum_acceleration(3.0, 5.0) == (1. / 6. * 5.0) * ((3.0 * 3.0) * 3.0)
+
+
+def test_depth_frustum_membership(oracle):
+    # camera at the origin, identity orientation: +Z forward (DEPTH:76-95).  Side planes contain pairs of the corner
+    # rays R_x(+-v/2) R_y(+-h/2) Z = (+-sin h2, -+sin v2 cos h2, cos v2 cos h2), hence lateral bounds
+    # |x|/z <= tan(h2)/cos(v2) and |y|/z <= tan(v2); near/far planes are z = d * cos(v2) * cos(h2).
+    v, h, dmin, dmax = 0.8745, 1.048, 0.1, 7.0
+    f = oracle.depth_frustum(v, h, dmin, dmax, [0, 0, 0], [0, 0, 0, 1], 5.0)
+    assert int(f["type"][0]) == 0
+    bx = math.tan(h / 2) / math.cos(v / 2)
+    by = math.tan(v / 2)
+    zf = dmax * math.cos(v / 2) * math.cos(h / 2)
+    zn = dmin * math.cos(v / 2) * math.cos(h / 2)
+    pts, exp = [], []
+    for z in (0.5, 1.0, 3.0):
+        for s in (1, -1):
+            pts += [[s * (bx - 0.01) * z, 0, z], [s * (bx + 0.01) * z, 0, z], [0, s * (by - 0.01) * z, z], [0, s * (by + 0.01) * z, z]]
+            exp += [True, False, True, False]
+    pts += [[0, 0, zf - 0.01], [0, 0, zf + 0.01], [0, 0, zn + 0.005], [0, 0, zn - 0.005], [0, 0, -1.0]]
+    exp += [True, False, True, False, False]
+    assert oracle.is_inside(f, pts).tolist() == exp
+    # the plane block: far normal +Z, near normal -Z (DEPTH:142-149)
+    p = f["p"][0].reshape(6, 6)
+    np.testing.assert_allclose(p[4, :3], [0, 0, 1], atol=1e-15)
+    np.testing.assert_allclose(p[5, :3], [0, 0, -1], atol=1e-15)
+    np.testing.assert_allclose(p[4, 5], zf, rtol=1e-15)
+
+
+def test_depth_frustum_pose(oracle):
+    # rotate the camera 90 deg about Y (+Z forward becomes +X) and move it to (10, -3, 1) (DEPTH:160-174)
+    q = [0, math.sin(math.pi / 4), 0, math.cos(math.pi / 4)]
+    f = oracle.depth_frustum(0.8745, 1.048, 0.1, 7.0, [10, -3, 1], q, 0.0)
+    assert oracle.is_inside(f, [[12, -3, 1], [8, -3, 1], [10, -3, 3], [10.5, -3.0, 1.05]]).tolist() == [True, False, False, True]
+
+
+def test_bogus_frustum_is_never_inside(oracle):
+    # DEPTH:71-74, 289-291
+    f = oracle.depth_frustum(0.0, 0.0, 0.1, 7.0, [0, 0, 0], [0, 0, 0, 1], 0.0)
+    assert int(f["type"][0]) == -1
+    assert not oracle.is_inside(f, [[0, 0, 1]]).any()
+
+
+def test_lidar_hourglass_membership(oracle):
+    # LIDAR:77-116: min/max are RADIAL XY distances; vertical test (|z|+pad)^2 / r^2 <= tan^2(vFOV/2)
+    v, pad = 0.523, 0.05
+    f = oracle.lidar_frustum(v, pad, 6.29, 1.0, 8.0, [0, 0, 0], [0, 0, 0, 1], 5.0)
+    t = math.tan(v / 2)
+    pts = [[2, 0, 0], [2, 0, 2 * t - pad - 0.01], [2, 0, 2 * t - pad + 0.01], [0.5, 0, 0], [9, 0, 0], [-3, 4, 0.5],
+           [0, -7.9, 0], [0, 8.1, 0], [2, 0, -(2 * t - pad - 0.01)]]
+    exp = [True, True, False, False, False, True, True, False, True]
+    assert oracle.is_inside(f, pts).tolist() == exp
+    # a 90 degree wedge (hFOV = pi/2): only |azimuth| <= pi/4 in front (+X) passes (LIDAR:104-113)
+    w = oracle.lidar_frustum(v, pad, math.pi / 2, 1.0, 8.0, [0, 0, 0], [0, 0, 0, 1], 5.0)
+    pts = [[3, 0, 0], [3, 2.9, 0], [3, 3.1, 0], [-3, 0, 0], [0, 3, 0]]
+    assert oracle.is_inside(w, pts).tolist() == [True, True, False, False, False]
+
+
+def test_mark_range_and_overwrite(oracle):
+    # GRID:274-291: skip if distance^2 (float) > range^2 (float) or < 0.0001; GRID:428: later marks overwrite
+    g = oracle.OracleGrid(0.05)
+    cloud = np.array([[1.0, 0, 0.5], [2.9, 0, 0.5], [3.2, 0, 0.5], [0.005, 0.0, 0.5], [1.0, 0, 0.5]], np.float32)
+    g.mark(cloud, origin=(0, 0, 0.5), obstacle_range=3.0, now=100.0)
+    ix, iy, iz, t = g.voxels()
+    assert sorted(zip(ix.tolist(), iy.tolist(), iz.tolist())) == [(19, 0, 9), (58, 0, 9)]   # 0.5*19.9999997 -> 9 ; 2.9f*19.9999997 = 58.000001 -> 58
+    assert (t == 100.0).all()
+    g.mark(cloud[:1], origin=(0, 0, 0.5), obstacle_range=3.0, now=101.5)
+    ix, iy, iz, t = g.voxels()
+    assert dict(zip(ix.tolist(), t.tolist())) == {19: 101.5, 58: 100.0}
+    # marking == 0 -> reading ignored (GRID:273)
+    g.mark(np.array([[2.0, 0, 0.5]], np.float32), origin=(0, 0, 0.5), obstacle_range=3.0, now=102.0, marking=0.0)
+    assert g.active_count() == 2
+
+
+def test_sweep_semantics_and_costmap_order(oracle):
+    # GRID:149-224 + SURVEY §3.1: the costmap of a cycle reflects the survivors of THAT cycle's sweep, before Mark
+    g = oracle.OracleGrid(0.05, decay_model=0, voxel_decay=15.0, pub_voxels=True)
+    g.clear_frustums(10.0)                     # empty grid: early return (GRID:104-108)
+    assert len(g.costmap()[0]) == 0
+    cloud = np.array([[1.0, 0.02, 0.5], [1.0, 0.02, 0.56], [2.0, 0.02, 0.5]], np.float32)
+    g.mark(cloud, origin=(0, 0, 0.5), obstacle_range=3.0, now=10.0)
+    assert len(g.costmap()[0]) == 0            # Mark never touches _cost_map
+    g.clear_frustums(12.0)
+    x, y, c = g.costmap()
+    vs = g.voxel_size
+    got = {(round(a, 9), round(b, 9)): int(n) for a, b, n in zip(x, y, c)}
+    assert got == {(round(19 * vs + vs / 2, 9), round(vs / 2, 9)): 2, (round(39 * vs + vs / 2, 9), round(vs / 2, 9)): 1}
+    assert len(g.points()) == 3
+    # strict `<`: a voxel exactly at its decay time survives (GRID:203), one ulp later it is cleared
+    g.clear_frustums(25.0)
+    assert g.active_count() == 3
+    g.clear_frustums(math.nextafter(25.0, 26.0))
+    assert g.active_count() == 0
+    assert len(g.cleared()[0]) == 2            # two distinct (x,y) columns were cleared
+
+
+def test_frustum_acceleration_first_frustum_wins(oracle):
+    # GRID:171-198: the first containing frustum decides; survivor's mark time becomes value - accel
+    g = oracle.OracleGrid(0.05, decay_model=0, voxel_decay=15.0)
+    g.load_voxels([20], [0], [10], [100.0])    # centre (1.025, 0.025, 0.525)
+    q = [0, math.sin(math.pi / 4), 0, math.cos(math.pi / 4)]   # looking along +X
+    f_slow = oracle.depth_frustum(0.8745, 1.048, 0.1, 7.0, [0, 0, 0.5], q, 1.0)
+    f_fast = oracle.depth_frustum(0.8745, 1.048, 0.1, 7.0, [0, 0, 0.5], q, 100.0)
+    g.clear_frustums(102.0, np.concatenate([f_slow, f_fast]))
+    t = g.voxels()[3]
+    assert t[0] == 100.0 - (1. / 6. * 1.0) * ((2.0 * 2.0) * 2.0)
+    g2 = oracle.OracleGrid(0.05, decay_model=0, voxel_decay=15.0)
+    g2.load_voxels([20], [0], [10], [100.0])
+    g2.clear_frustums(102.0, np.concatenate([f_fast, f_slow]))   # 15 - 2 - 133.3 < 0 -> cleared
+    assert g2.active_count() == 0
+
+
+def test_update_ros_costmap(oracle):
+    # LAYER:699-725 with nav2 worldToMap: threshold per voxel column, bounds touch marked and cleared cells
+    g = oracle.OracleGrid(0.05)
+    g.load_voxels([0, 0, 0, 5, -3, 400], [0, 0, 0, 5, -3, 0], [1, 2, 3, 1, 1, 1], [10.0] * 6)
+    g.clear_frustums(11.0)
+    cm, b, n = g.update_ros_costmap(-1.0, -1.0, 0.05, 100, 100, mark_threshold=0, default_value=255)
+    vs = g.voxel_size
+    assert n == 3 and cm.sum() == 254 * 3 + 255 * (100 * 100 - 3)      # column x=400 is outside the 5 m map
+    assert cm[int((0 * vs + vs / 2 + 1.0) / 0.05), int((0 * vs + vs / 2 + 1.0) / 0.05)] == 254
+    assert cm[int((-3 * vs + vs / 2 + 1.0) / 0.05), int((-3 * vs + vs / 2 + 1.0) / 0.05)] == 254
+    np.testing.assert_array_equal(b, [-3 * vs + vs / 2, -3 * vs + vs / 2, 5 * vs + vs / 2, 5 * vs + vs / 2])
+    cm, b, n = g.update_ros_costmap(-1.0, -1.0, 0.05, 100, 100, mark_threshold=2, default_value=0)
+    assert n == 1 and cm.sum() == 254
+
+
+def test_reset_area(oracle):
+    # GRID:397-418: strict inequalities on voxel centres; invert flips
+    g = oracle.OracleGrid(0.05)
+    g.load_voxels([0, 10, 20, 30], [0, 0, 0, 0], [1, 1, 1, 1], [1.0] * 4)
+    # with invert_area == false the test `in_range == invert_area` clears everything OUTSIDE the rectangle
+    g.reset_area(0.4, -1.0, 1.2, 1.0, invert=False)
+    assert sorted(g.voxels()[0].tolist()) == [10, 20]
+    g.reset_area(0.4, -1.0, 0.8, 1.0, invert=True)    # invert: clear INSIDE
+    assert sorted(g.voxels()[0].tolist()) == [20]
+    assert g.reset() and g.active_count() == 0
+
+
+def test_passthrough_and_voxel_filters(oracle):
+    # measurement_buffer.cpp:153-175
+    cloud = np.array([[0.01, 0.01, 0.5], [0.02, 0.02, 0.52], [0.30, 0.0, 0.5], [0.0, 0.0, 0.1], [0.0, 0.0, 2.5],
+                      [np.nan, 0, 1.0]], np.float32)
+    p = oracle.filter_passthrough(cloud, 0.3, 2.0)
+    assert p.shape == (3, 3) and np.array_equal(p, cloud[:3, :3])
+    v = oracle.filter_voxel(cloud, 0.05, 0.3, 2.0, 0)
+    assert v.shape == (2, 3)
+    c = (cloud[0, :3] + cloud[1, :3]) / np.float32(2)
+    assert any(np.array_equal(r, c) for r in v) and any(np.array_equal(r, cloud[2, :3]) for r in v)
+    assert oracle.filter_voxel(cloud, 0.05, 0.3, 2.0, 2).shape == (1, 3)
