@@ -186,7 +186,8 @@ int stvl_mark_device(stvl_grid_t * g, const stvl_reading_t * readings, uint32_t 
  * (pre-Mark state).  `costmap` is a HOST buffer of size_x*size_y bytes (may be NULL
  * to skip the copy-out).  Synchronises. */
 int stvl_costmap(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_t * costmap, stvl_costmap_result_t * res);
-/* Same, but leaves the bytes in a DEVICE buffer the caller owns. */
+/* Same, but leaves the bytes in a DEVICE buffer the caller owns.  With res == NULL the call only enqueues work
+ * (no synchronisation); results are then available after stvl_synchronize / any synchronising call. */
 int stvl_costmap_device(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_t * costmap_dev, stvl_costmap_result_t * res);
 
 /* ---- results of the last sweep ------------------------------------------ */

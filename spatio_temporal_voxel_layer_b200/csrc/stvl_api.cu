@@ -87,6 +87,8 @@ struct stvl_grid {
   uint64_t added_since_sweep = 0;   // points marked / voxels loaded after the last enqueued sweep
   bool counters_fresh = true;       // `last` reflects the device state
   bool marks_unverified = false;    // a Mark ran since the allocator flags were last checked
+  uint64_t pending_leaf_bound = 0;  // upper bound of leaves the unverified Marks can have allocated
+  uint64_t pending_tile_bound = 0;  // same for column tiles
   std::vector<MarkBatch> replay;    // batches of the unverified Mark (device data still intact)
   double time_bound = 0.0;          // every stored mark time is <= this ...
   bool time_bound_inf = false;      // ... unless a sweep may have raised times
@@ -189,6 +191,7 @@ int clear_pool(stvl_grid * g)
   g->last = Counters{};
   g->counters_fresh = true;
   g->marks_unverified = false;
+  g->pending_leaf_bound = g->pending_tile_bound = 0;
   g->replay.clear();
   g->active_upper = 0;
   g->added_since_sweep = 0;
@@ -205,6 +208,7 @@ int fetch_counters(stvl_grid * g)
   CU(cudaStreamSynchronize(g->stream));
   g->last = *g->h_ctr;
   g->counters_fresh = true;
+  g->pending_leaf_bound = g->pending_tile_bound = 0;
   // tighten the active-voxel bound: survivors of the last sweep + everything added after it
   if (g->swept) g->active_upper = g->last.n_survived + g->added_since_sweep;
   return STVL_OK;
@@ -291,6 +295,19 @@ int launch_batches(stvl_grid * g, const std::vector<MarkBatch> & batches)
 int verify_marks(stvl_grid * g)
 {
   if (!g->marks_unverified) return STVL_OK;
+  // No synchronisation needed when the pools provably could not overflow: leaves in use at the last fetch plus
+  // everything the Marks since then can have allocated (each reading touches at most the leaves inside its
+  // obstacle_range ball) still fits.  `last` is older than those Marks, frees since then only help.
+  if (!g->counters_fresh) {
+    const uint64_t leaves_known = (uint64_t)g->last.high_water - g->last.free_n;
+    if (!g->last.leaf_overflow && !g->last.tile_overflow &&
+        leaves_known + g->pending_leaf_bound <= g->v.leaf_capacity &&
+        (uint64_t)g->last.tile_n + g->pending_tile_bound <= g->v.tile_capacity) {
+      g->marks_unverified = false;
+      g->replay.clear();
+      return STVL_OK;   // pending_*_bound stay: they are only reset by a fetch
+    }
+  }
   for (int attempt = 0; attempt < 32; ++attempt) {
     if (!g->counters_fresh) { int rc = fetch_counters(g); if (rc != STVL_OK) return rc; }
     if (!g->last.leaf_overflow && !g->last.tile_overflow) {
@@ -347,9 +364,14 @@ int build_batches(stvl_grid * g, const stvl_reading_t * readings, uint32_t n, co
     d.vec4 = (r.point_step == 16 && r.off_x == 0 && r.off_y == 4 && r.off_z == 8 && ((uintptr_t)d.data & 15) == 0) ? 1u : 0u;
     cur.total_blocks += mark_blocks_for(r.n_points);
     *total_points += r.n_points;
+    // leaves / tiles this reading can touch: points farther than obstacle_range from the origin are skipped
+    // (reference .cpp:289), so at most the leaves intersecting that ball (+1 for the negative-coordinate shift)
+    const double span = std::isfinite(r.obstacle_range) ? 2.0 * std::fabs(r.obstacle_range) / (8.0 * g->vs) + 3.0 : 1e18;
+    const double lb = std::min((double)r.n_points, span * span * span), tb = std::min((double)r.n_points, span * span);
+    g->pending_leaf_bound += lb < 1e18 ? (uint64_t)lb : (uint64_t)r.n_points;
+    g->pending_tile_bound += tb < 1e18 ? (uint64_t)tb : (uint64_t)r.n_points;
   }
   if (cur.n_readings) out->push_back(cur);
-  (void)g;
   return STVL_OK;
 }
 
@@ -502,7 +524,7 @@ int stvl_create(const stvl_config_t * cfg, stvl_grid_t ** out)
   CUB(cudaMalloc(&g->v.ctr, sizeof(Counters)));
   g->device_bytes += sizeof(Counters);
 
-  const uint32_t leaf_cap = cfg->leaf_capacity ? std::max<uint32_t>(cfg->leaf_capacity, 64u) : (1u << 17);
+  const uint32_t leaf_cap = cfg->leaf_capacity ? std::max<uint32_t>(cfg->leaf_capacity, 64u) : (1u << 18);
   GridView nv = g->v;
   nv.vs = g->vs; nv.inv_vs = g->inv_vs; nv.half_vs = g->half_vs;
   nv.voxel_decay = cfg->voxel_decay; nv.decay_model = cfg->decay_model;
@@ -685,6 +707,8 @@ int stvl_costmap_device(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_
   if (!(p->resolution > 0)) return fail(STVL_ERR_INVALID, "resolution must be positive");
   CU(launch_costmap(g->v, to_dev(*p), costmap_dev, tiles_upper(g), g->sm_count, g->stream));
   g->launches += 2;
+  g->counters_fresh = false;
+  if (!res) return STVL_OK;   // fully asynchronous: the caller synchronises / reads results later
   int rc = fetch_counters(g);
   if (rc != STVL_OK) return rc;
   fill_costmap_result(g, res);

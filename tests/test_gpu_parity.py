@@ -1,0 +1,394 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on identical seeded inputs.
+
+Bar (BASELINE.json north_star): voxel key sets, mark times, column counts and costmap bytes bit-exact;
+voxels whose decision hinged on libm exp/atan must be listed (stvl_get_ambiguous)."""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import assert_same_columns, assert_same_voxels, point_set
+
+pytestmark = pytest.mark.gpu
+
+
+def rgbd_reading(stvl, synth, scene, origin, quat, seed, w=160, h=120, now=None, **kw):
+    cloud = synth.depth_cloud(scene, origin, quat, width=w, height=h, seed=seed)
+    p = synth.RGBD
+    return stvl.MeasurementReading(cloud, origin=origin, orientation=quat, obstacle_range=p["obstacle_range"],
+                                   min_z=p["min_z"], max_z=p["max_z"], vfov=p["vfov"], hfov=p["hfov"],
+                                   decay_acceleration=p["accel"], marking=True, clearing=True, now=now,
+                                   filter=stvl.FILTER_PASSTHROUGH, min_obstacle_height=p["min_obstacle_height"],
+                                   max_obstacle_height=p["max_obstacle_height"], **kw)
+
+
+def oracle_mark(oracle, og, reading, now):
+    """Mark one reading on the oracle, applying the same PassThrough pre-filter the GPU fuses into Mark."""
+    cloud = np.ascontiguousarray(reading.cloud, np.float32)
+    if reading.filter == 2:
+        xyz = oracle.filter_passthrough(cloud, reading.min_obstacle_height, reading.max_obstacle_height)
+    else:
+        xyz = cloud[:, :3]
+    og.mark(np.ascontiguousarray(xyz), reading.origin, reading.obstacle_range, reading.now if reading.now is not None else now,
+            marking=1.0 if reading.marking else 0.0)
+
+
+def oracle_frustums(oracle, readings):
+    blocks = []
+    for r in readings:
+        if r.model_type == 0:
+            blocks.append(oracle.depth_frustum(r.vfov, r.hfov, r.min_z, r.max_z, r.origin, r.orientation, r.decay_acceleration))
+        elif r.model_type == 1:
+            blocks.append(oracle.lidar_frustum(r.vfov, r.vfov_padding, r.hfov, r.min_z, r.max_z, r.origin, r.orientation, r.decay_acceleration))
+    return np.concatenate(blocks) if blocks else None
+
+
+def compare_cycle_outputs(gg, og, check_points=False, ambiguous_ok=False):
+    gx, gy, gc = gg.GetFlattenedCostmap()
+    assert_same_columns((gx, gy, gc), og.costmap())
+    # cleared cells: the reference keeps a set of (x,y); the GPU lists one entry per cleared voxel
+    cix, ciy = gg.cleared()
+    gcl = np.unique(np.stack([gg.index_to_world(cix), gg.index_to_world(ciy)], 1), axis=0) if len(cix) else np.zeros((0, 2))
+    ox, oy = og.cleared()
+    ocl = np.unique(np.stack([ox, oy], 1), axis=0) if len(ox) else np.zeros((0, 2))
+    assert np.array_equal(gcl.view(np.uint64), ocl.view(np.uint64)), "cleared cell sets differ"
+    st = gg.sweep_stats()
+    if len(ox):
+        np.testing.assert_array_equal(np.array(st.cleared_bbox_world[:]), [ox.min(), oy.min(), ox.max(), oy.max()])
+    if not ambiguous_ok:
+        assert st.n_ambiguous == 0
+    if check_points:
+        assert np.array_equal(point_set(gg.GetOccupancyPointCloud()), point_set(og.points()))
+    assert_same_voxels(gg.voxels(), og.voxels())
+    return st
+
+
+def test_smoke_entry():
+    import __graft_entry__ as ge
+    ge.smoke()
+
+
+def test_mark_quirks_bit_exact(stvl, oracle):
+    """Quantisation quirks of reference .cpp:285-303 on adversarial points: negatives, exact voxel and range
+    boundaries, the z-uses-y-sign bug, tiny distances, non-finite values."""
+    rng = np.random.default_rng(1)
+    n = 50000
+    pts = rng.uniform(-4, 4, (n, 3)).astype(np.float32)
+    pts[:5000] = (np.round(pts[:5000] / 0.05) * 0.05).astype(np.float32)          # on voxel boundaries
+    pts[5000:6000, 0] = np.float32(3.0); pts[5000:6000, 1:] = 0                    # on the range boundary
+    pts[6000:6100] = rng.uniform(-0.012, 0.012, (100, 3)).astype(np.float32)       # around distance^2 = 1e-4
+    pts[6100] = [np.nan, 0, 0]; pts[6101] = [np.inf, 1, 1]; pts[6102] = [1, -np.inf, 1]
+    cloud = np.zeros((n, 4), np.float32); cloud[:, :3] = pts
+    for vs in (0.05, 0.02):
+        gg = stvl.SpatioTemporalVoxelGrid(vs)
+        og = oracle.OracleGrid(vs)
+        r = stvl.MeasurementReading(cloud, origin=(0.001, -0.002, 0.003), obstacle_range=3.0, now=1000.25)
+        gg.Mark([r])
+        og.mark(cloud, r.origin, 3.0, 1000.25)
+        assert_same_voxels(gg.voxels(), og.voxels())
+        assert gg.pool_stats().points_dropped_nonfinite == 3
+        gg.close()
+
+
+def test_mark_strided_and_unaligned_layouts(stvl, oracle):
+    """PointCloud2 layouts other than packed xyz-pad: 32 B XYZRGB-style, 22 B Velodyne-style (unaligned floats)."""
+    rng = np.random.default_rng(2)
+    n = 20000
+    xyz = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    for step, offs in ((32, (0, 4, 8)), (32, (16, 20, 4)), (22, (0, 4, 8)), (22, (2, 6, 14)), (12, (0, 4, 8))):
+        raw = rng.integers(0, 255, (n, step), dtype=np.uint8)
+        for a in range(3):
+            raw[:, offs[a]:offs[a] + 4] = xyz[:, a:a + 1].copy().view(np.uint8)
+        gg = stvl.SpatioTemporalVoxelGrid(0.05)
+        og = oracle.OracleGrid(0.05)
+        r = stvl.MeasurementReading((raw.ctypes.data, n, step, offs), origin=(0, 0, 0), obstacle_range=2.5, now=5.0)
+        gg.Mark([r])
+        og.mark(raw.reshape(-1), (0, 0, 0), 2.5, 5.0, point_step=step, offsets=offs)
+        assert_same_voxels(gg.voxels(), og.voxels())
+        gg.close()
+
+
+def test_mark_overwrite_order(stvl, oracle):
+    """Later readings overwrite earlier ones (reference .cpp:428) — batched atomicMax path for monotone clocks,
+    per-reading plain-store path when clocks go backwards."""
+    rng = np.random.default_rng(3)
+    clouds = [np.concatenate([rng.uniform(-2, 2, (5000, 3)), np.zeros((5000, 1))], 1).astype(np.float32) for _ in range(4)]
+    for nows in ([10.0, 10.1, 10.2, 10.3], [10.0, 9.0, 11.0, 8.0], [10.0, 10.0, 10.0, 10.0]):
+        gg = stvl.SpatioTemporalVoxelGrid(0.05)
+        og = oracle.OracleGrid(0.05)
+        rs = [stvl.MeasurementReading(c, origin=(0, 0, 0), obstacle_range=3.0, now=t) for c, t in zip(clouds, nows)]
+        gg.Mark(rs)
+        for c, t in zip(clouds, nows):
+            og.mark(c, (0, 0, 0), 3.0, t)
+        assert_same_voxels(gg.voxels(), og.voxels())
+        # a second Mark with an older clock must still overwrite
+        gg.Mark([stvl.MeasurementReading(clouds[0], origin=(0, 0, 0), obstacle_range=3.0, now=5.0)])
+        og.mark(clouds[0], (0, 0, 0), 3.0, 5.0)
+        assert_same_voxels(gg.voxels(), og.voxels())
+        gg.close()
+
+
+@pytest.mark.parametrize("decay_model,voxel_decay", [(0, 15.0), (1, 15.0), (2, 15.0), (2, -1.0)])
+def test_sweep_decay_models_no_frustum(stvl, oracle, decay_model, voxel_decay):
+    rng = np.random.default_rng(4)
+    n = 60000
+    vox = np.unique(rng.integers(-300, 300, (n, 3)), axis=0)
+    vox[:, 2] = vox[:, 2] % 40
+    vox = np.unique(vox, axis=0)
+    now = 1.7e9
+    t = now - rng.uniform(0, 30, len(vox))
+    t[:100] = now - 15.0                      # exactly at the linear decay boundary: survives (strict <)
+    t[100:200] = np.nextafter(now - 15.0, 0)  # one ulp older: cleared
+    gg = stvl.SpatioTemporalVoxelGrid(0.05, decay_model=decay_model, voxel_decay=voxel_decay, pub_voxels=True)
+    og = oracle.OracleGrid(0.05, decay_model=decay_model, voxel_decay=voxel_decay, pub_voxels=True)
+    gg.load_voxels(vox[:, 0], vox[:, 1], vox[:, 2], t)
+    og.load_voxels(vox[:, 0], vox[:, 1], vox[:, 2], t)
+    gg.ClearFrustums([], now)
+    og.clear_frustums(now)
+    st = compare_cycle_outputs(gg, og, check_points=True, ambiguous_ok=(decay_model == 1))
+    assert st.n_swept == len(vox)
+    assert st.n_survived + st.n_cleared == st.n_swept
+    gg.close()
+
+
+def test_sweep_depth_frustums_bit_exact(stvl, oracle, ):
+    """Config 1/2 shape: depth-camera plane sets with acceleration, voxels scattered densely through and around the
+    frustums, including voxels sitting exactly ON frustum planes (camera placed on voxel-centre lattice planes)."""
+    rng = np.random.default_rng(5)
+    vsf = float(np.float32(0.05))
+    vox = np.unique(rng.integers(-160, 160, (400000, 3)), axis=0)
+    vox[:, 2] = vox[:, 2] % 48
+    vox = np.unique(vox, axis=0)
+    now = 2000.0
+    t = now - rng.uniform(0, 14.9, len(vox))
+    readings = []
+    import spatio_temporal_voxel_layer_b200.synth as synth
+    for k in range(7):
+        yaw = k * 2 * math.pi / 7
+        # origins ON the voxel-centre lattice so that near/far/side planes pass exactly through voxel centres
+        o = ((rng.integers(-20, 20)) * vsf + vsf / 2, (rng.integers(-20, 20)) * vsf + vsf / 2, 12 * vsf + vsf / 2)
+        readings.append(stvl.MeasurementReading(None, origin=o, orientation=synth.optical_quat(yaw, 0.05 * k),
+                                                min_z=0.1, max_z=7.0, vfov=0.8745, hfov=1.048,
+                                                decay_acceleration=[5.0, 0.0, 0.5, 50.0, 5.0, 1.0, 5.0][k]))
+    # plus an axis-aligned camera whose far/near planes coincide with voxel-centre planes
+    readings.append(stvl.MeasurementReading(None, origin=(vsf / 2, vsf / 2, vsf / 2), orientation=(0, 0, 0, 1), min_z=0.1,
+                                            max_z=7.0, vfov=0.8745, hfov=1.048, decay_acceleration=3.0))
+    readings.append(stvl.MeasurementReading(None, origin=(0, 0, 0), orientation=(0, 0, 0, 1), vfov=0.0, hfov=0.0))   # bogus
+    gg = stvl.SpatioTemporalVoxelGrid(0.05)
+    og = oracle.OracleGrid(0.05)
+    gg.load_voxels(vox[:, 0], vox[:, 1], vox[:, 2], t)
+    og.load_voxels(vox[:, 0], vox[:, 1], vox[:, 2], t)
+    gg.ClearFrustums(readings, now)
+    og.clear_frustums(now, oracle_frustums(oracle, readings))
+    st = compare_cycle_outputs(gg, og)
+    assert st.n_rewritten > 1000 and st.n_cleared > 1000
+    # second sweep on the rewritten times
+    gg.ClearFrustums(readings[:3], now + 1.0)
+    og.clear_frustums(now + 1.0, oracle_frustums(oracle, readings[:3]))
+    compare_cycle_outputs(gg, og)
+    gg.close()
+
+
+@pytest.mark.parametrize("hfov", [6.29, 2.0])
+def test_sweep_lidar_hourglass(stvl, oracle, hfov):
+    """Config 3: VLP-16 hourglass frustum, exponential decay.  hfov 6.29 = full circle (no atan);
+    hfov 2.0 exercises the atan wedge — mismatches, if any, must be inside the listed ambiguous set."""
+    rng = np.random.default_rng(6)
+    vox = np.unique(rng.integers(-200, 200, (300000, 3)), axis=0)
+    vox[:, 2] = vox[:, 2] % 60 - 10
+    vox = np.unique(vox, axis=0)
+    now = 500.0
+    t = now - rng.uniform(0, 6.0, len(vox))
+    q = np.array([0.02, -0.03, math.sin(0.4), math.cos(0.4)]); q /= np.linalg.norm(q)
+    r = stvl.MeasurementReading(None, origin=(0.31, -0.12, 0.9), orientation=q, min_z=1.0, max_z=8.0, vfov=0.523,
+                                vfov_padding=0.05, hfov=hfov, decay_acceleration=5.0, model_type=1)
+    gg = stvl.SpatioTemporalVoxelGrid(0.05, decay_model=1, voxel_decay=15.0)
+    og = oracle.OracleGrid(0.05, decay_model=1, voxel_decay=15.0)
+    gg.load_voxels(vox[:, 0], vox[:, 1], vox[:, 2], t)
+    og.load_voxels(vox[:, 0], vox[:, 1], vox[:, 2], t)
+    gg.ClearFrustums([r], now)
+    og.clear_frustums(now, oracle_frustums(oracle, [r]))
+    st = gg.sweep_stats()
+    assert st.n_cleared > 100 and st.n_rewritten > 100
+    gv, ov = gg.voxels(), og.voxels()
+    if st.n_ambiguous == 0:
+        compare_cycle_outputs(gg, og, ambiguous_ok=True)
+    else:
+        # every disagreement must be a listed voxel
+        ax, ay, az = gg.ambiguous()
+        listed = set(zip(ax.tolist(), ay.tolist(), az.tolist()))
+        gs = dict(zip(zip(gv[0].tolist(), gv[1].tolist(), gv[2].tolist()), gv[3].tolist()))
+        os_ = dict(zip(zip(ov[0].tolist(), ov[1].tolist(), ov[2].tolist()), ov[3].tolist()))
+        diff = {k for k in set(gs) | set(os_) if gs.get(k) != os_.get(k)}
+        assert diff <= listed, "unlisted disagreement: %s" % sorted(diff - listed)[:5]
+    gg.close()
+
+
+def test_multi_cycle_scenario_with_costmap(stvl, oracle):
+    """Config 1/2 end to end at reduced image size: robot drives down an aisle with 3 RGBD cameras for 12 cycles:
+    clear -> mark -> costmap each cycle, order as the reference's updateBounds (spatio_temporal_voxel_layer.cpp:772-795)."""
+    import spatio_temporal_voxel_layer_b200.synth as synth
+    scene = synth.retail_scene(size=30.0, seed=3)
+    gg = stvl.SpatioTemporalVoxelGrid(0.05, decay_model=0, voxel_decay=2.0, pub_voxels=True, leaf_capacity=256)  # tiny pool: forces growth
+    og = oracle.OracleGrid(0.05, decay_model=0, voxel_decay=2.0, pub_voxels=True)
+    size, res, ox, oy = 400, 0.05, -10.0, -10.0
+    for cyc in range(12):
+        now = 100.0 + 0.4 * cyc
+        centre = (-6.0 + 0.5 * cyc, 2.3 - 13.5 + 12.0, 0.0)
+        readings = []
+        for k, (o, q) in enumerate(synth.camera_ring(centre, 0.1 * cyc, n_cams=3)):
+            readings.append(rgbd_reading(stvl, synth, scene, o, q, seed=100 * cyc + k, now=now + 0.001 * k))
+        gg.ClearFrustums(readings, now)
+        og.clear_frustums(now, oracle_frustums(oracle, readings))
+        gg.Mark(readings)
+        for r in readings:
+            oracle_mark(oracle, og, r, now)
+        cm, res_g = gg.UpdateROSCostmap(ox, oy, res, size, size, mark_threshold=(cyc % 3), default_value=255 if cyc % 2 else 0)
+        ocm, ob, on = og.update_ros_costmap(ox, oy, res, size, size, mark_threshold=(cyc % 3), default_value=255 if cyc % 2 else 0)
+        assert np.array_equal(cm, ocm), "costmap bytes differ in cycle %d" % cyc
+        assert res_g.n_marked_columns == on
+        st = compare_cycle_outputs(gg, og, check_points=True)
+        # bounds: touch() over marked columns and cleared cells == oracle's
+        b = [1e308, 1e308, -1e308, -1e308]
+        if res_g.has_bounds:
+            b = [min(b[0], res_g.touched[0]), min(b[1], res_g.touched[1]), max(b[2], res_g.touched[2]), max(b[3], res_g.touched[3])]
+        if st.n_cleared:
+            w = st.cleared_bbox_world
+            b = [min(b[0], w[0]), min(b[1], w[1]), max(b[2], w[2]), max(b[3], w[3])]
+        np.testing.assert_array_equal(np.array(b), ob)
+    assert og.active_count() > 1000
+    gg.close()
+
+
+def test_leaf_pool_growth_replays_mark(stvl, oracle):
+    """A Mark that exhausts the leaf pool is replayed after the pool (and its hash) grew: nothing is lost."""
+    rng = np.random.default_rng(13)
+    n = 30000
+    cloud = np.zeros((n, 4), np.float32)
+    cloud[:, :3] = rng.uniform(-40, 40, (n, 3))          # scattered: almost one leaf per point
+    gg = stvl.SpatioTemporalVoxelGrid(0.05, leaf_capacity=64)
+    og = oracle.OracleGrid(0.05)
+    gg.Mark([stvl.MeasurementReading(cloud, origin=(0, 0, 0), obstacle_range=100.0, now=3.0)])
+    og.mark(cloud, (0, 0, 0), 100.0, 3.0)
+    assert_same_voxels(gg.voxels(), og.voxels())
+    ps = gg.pool_stats()
+    assert ps.leaf_capacity >= 16384 and ps.leaves_in_use > 10000
+    # and the grown grid keeps working: sweep + second mark + costmap
+    gg.ClearFrustums([], 4.0); og.clear_frustums(4.0)
+    gg.Mark([stvl.MeasurementReading(cloud[:1000] + np.float32(0.3), origin=(0, 0, 0), obstacle_range=100.0, now=4.5)])
+    og.mark(cloud[:1000] + np.float32(0.3), (0, 0, 0), 100.0, 4.5)
+    compare_cycle_outputs(gg, og)
+    gg.close()
+
+
+def test_reset_and_reset_area(stvl, oracle):
+    rng = np.random.default_rng(8)
+    vox = np.unique(rng.integers(-100, 100, (50000, 3)), axis=0)
+    t = rng.uniform(1, 2, len(vox))
+    gg = stvl.SpatioTemporalVoxelGrid(0.05)
+    og = oracle.OracleGrid(0.05)
+    gg.load_voxels(vox[:, 0], vox[:, 1], vox[:, 2], t); og.load_voxels(vox[:, 0], vox[:, 1], vox[:, 2], t)
+    vs = gg.voxel_size
+    # rectangle edges exactly ON voxel centres: strict inequalities (reference .cpp:409-411)
+    s, e = (-20 * vs + vs / 2, -10 * vs + vs / 2), (30 * vs + vs / 2, 40 * vs + vs / 2)
+    gg.ResetGridArea(s, e, invert_area=True); og.reset_area(s[0], s[1], e[0], e[1], True)
+    assert_same_voxels(gg.voxels(), og.voxels())
+    gg.ResetGridArea((-4.0, -4.0), (4.0, 4.0), invert_area=False); og.reset_area(-4.0, -4.0, 4.0, 4.0, False)
+    assert_same_voxels(gg.voxels(), og.voxels())
+    gg.ClearFrustums([], 3.0); og.clear_frustums(3.0)
+    compare_cycle_outputs(gg, og)
+    assert gg.ResetGrid() and og.reset()
+    assert gg.active_count() == 0
+    gg.ClearFrustums([], 4.0)
+    assert len(gg.columns()[0]) == 0
+    # the grid is usable again after a reset
+    gg.load_voxels([1, 2], [3, 4], [5, 6], [7.0, 8.0])
+    assert gg.active_count() == 2
+    gg.close()
+
+
+def test_leaf_recycling_and_hash_tombstones(stvl, oracle):
+    """Leaves die and are reused over many cycles; results stay identical to the oracle."""
+    rng = np.random.default_rng(9)
+    gg = stvl.SpatioTemporalVoxelGrid(0.05, decay_model=0, voxel_decay=1.0, leaf_capacity=64)
+    og = oracle.OracleGrid(0.05, decay_model=0, voxel_decay=1.0)
+    for cyc in range(30):
+        now = 10.0 + cyc * 0.6
+        gg.ClearFrustums([], now); og.clear_frustums(now)
+        c = rng.uniform(-1, 1, 3) * [20, 20, 0] + [0, 0, 1.0]
+        pts = (c + rng.normal(0, 0.6, (4000, 3))).astype(np.float32)
+        cloud = np.zeros((4000, 4), np.float32); cloud[:, :3] = pts
+        gg.Mark([stvl.MeasurementReading(cloud, origin=tuple(c), obstacle_range=5.0, now=now)])
+        og.mark(cloud, tuple(c), 5.0, now)
+        if cyc % 5 == 4:
+            compare_cycle_outputs(gg, og)
+    ps = gg.pool_stats()
+    assert ps.leaves_free > 0 or ps.hash_tombstones >= 0
+    assert_same_voxels(gg.voxels(), og.voxels())
+    gg.close()
+
+
+def test_config4_small_voxels_mixed_sensors(stvl, oracle):
+    """Config 4 shape at reduced size: 0.02 m voxels, one lidar + two RGBD, linear decay."""
+    import spatio_temporal_voxel_layer_b200.synth as synth
+    scene = synth.retail_scene(size=20.0, seed=5)
+    gg = stvl.SpatioTemporalVoxelGrid(0.02, decay_model=0, voxel_decay=3.0)
+    og = oracle.OracleGrid(0.02, decay_model=0, voxel_decay=3.0)
+    for cyc in range(4):
+        now = 50.0 + cyc
+        centre = (0.3 * cyc - 1.0, 0.8, 0.0)
+        readings = []
+        lq = synth.yaw_quat(0.2 * cyc)
+        lo = (centre[0], centre[1], 0.9)
+        lc = synth.lidar_cloud(scene, lo, lq, rings=32, azimuths=512, vfov=0.6, seed=cyc)
+        readings.append(stvl.MeasurementReading(lc, origin=lo, orientation=lq, obstacle_range=8.0, min_z=0.5, max_z=8.0,
+                                                vfov=0.6, vfov_padding=0.03, hfov=6.29, decay_acceleration=2.0,
+                                                model_type=1, now=now, filter=stvl.FILTER_PASSTHROUGH,
+                                                min_obstacle_height=0.1, max_obstacle_height=2.2))
+        for k, (o, q) in enumerate(synth.camera_ring(centre, 0.3, n_cams=2)):
+            readings.append(rgbd_reading(stvl, synth, scene, o, q, seed=10 * cyc + k, now=now + 0.01 * (k + 1)))
+        gg.ClearFrustums(readings, now)
+        og.clear_frustums(now, oracle_frustums(oracle, readings))
+        gg.Mark(readings)
+        for r in readings:
+            oracle_mark(oracle, og, r, now)
+        compare_cycle_outputs(gg, og)
+    assert og.active_count() > 5000
+    gg.close()
+
+
+def test_sharded_grids_union_equals_single(stvl, oracle):
+    """Config 5 mechanics on one GPU: N spatial shards, each with its own handle, produce column counts whose
+    dense sum (what the NCCL reduce computes) thresholds to the same costmap bytes as the unsharded grid."""
+    import torch
+    rng = np.random.default_rng(10)
+    vox = np.unique(rng.integers(-250, 250, (200000, 3)), axis=0)
+    vox[:, 2] = vox[:, 2] % 30
+    vox = np.unique(vox, axis=0)
+    now = 100.0
+    t = now - rng.uniform(0, 20, len(vox))
+    og = oracle.OracleGrid(0.05)
+    og.load_voxels(vox[:, 0], vox[:, 1], vox[:, 2], t)
+    og.clear_frustums(now)
+    size, res, ox, oy = 512, 0.05, -12.8, -12.8
+    ocm, _, on = og.update_ros_costmap(ox, oy, res, size, size, mark_threshold=2, default_value=0)
+    nshards = 4
+    ix0, iy0, nx, ny = -260, -260, 520, 520
+    dense = torch.zeros((ny, nx), dtype=torch.int32, device="cuda")
+    total_active = 0
+    shards = []
+    for s in range(nshards):
+        g = stvl.SpatioTemporalVoxelGrid(0.05, shard_index=s, shard_count=nshards, shard_width=4)
+        g.load_voxels(vox[:, 0], vox[:, 1], vox[:, 2], t)      # every shard sees everything, keeps its slabs
+        total_active += g.active_count()
+        g.ClearFrustums([], now)
+        g.columns_to_dense(ix0, iy0, nx, ny, dense.data_ptr())
+        shards.append(g)
+    assert total_active == len(vox)
+    cm = torch.zeros((size, size), dtype=torch.uint8, device="cuda")
+    p = stvl.CostmapParams(ox, oy, res, size, size, 2, 0, 254)
+    r = shards[0].costmap_from_dense(dense.data_ptr(), ix0, iy0, nx, ny, p, cm.data_ptr())
+    assert np.array_equal(cm.cpu().numpy(), ocm)
+    assert r.n_marked_columns == on
+    for g in shards:
+        g.close()
