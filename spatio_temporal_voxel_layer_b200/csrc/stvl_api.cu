@@ -93,6 +93,7 @@ struct stvl_grid {
   double time_bound = 0.0;          // every stored mark time is <= this ...
   bool time_bound_inf = false;      // ... unless a sweep may have raised times
   bool swept = false;
+  bool alloc_dirty = false;         // a Mark / load kernel handed out leaves that are not folded into the allocator yet
   uint64_t launches = 0;
   size_t device_bytes = 0;
   double vs = 0, inv_vs = 0, half_vs = 0;
@@ -131,27 +132,28 @@ int alloc_pool(stvl_grid * g, uint32_t leaf_capacity, GridView * nv)
   v.leaf_capacity = leaf_capacity;
   const uint32_t hcap = pow2_ceil((uint64_t)leaf_capacity * 4);
   v.hash_mask = hcap - 1;
-  CU(cudaMalloc(&v.hash_keys, (size_t)hcap * 8));
-  CU(cudaMalloc(&v.hash_vals, (size_t)hcap * 4));
+  CU(cudaMalloc(&v.hash, (size_t)hcap * sizeof(HashEntry)));
   CU(cudaMalloc(&v.leaf_key, (size_t)leaf_capacity * 8));
   CU(cudaMalloc(&v.leaf_hpos, (size_t)leaf_capacity * 4));
   CU(cudaMalloc(&v.leaf_tile, (size_t)leaf_capacity * 4));
   CU(cudaMalloc(&v.leaf_mask, (size_t)leaf_capacity * 64));
   CU(cudaMalloc(&v.leaf_time, (size_t)leaf_capacity * kLeafVoxels * 8));
+  CU(cudaMalloc(&v.leaf_tmin, (size_t)leaf_capacity * 8));
   CU(cudaMalloc(&v.free_slots, (size_t)leaf_capacity * 4));
+  CU(cudaMalloc(&v.sweep_queue, (size_t)leaf_capacity * 4));
   *nv = v;
   return STVL_OK;
 }
 size_t pool_bytes(const GridView & v)
 {
-  return ((size_t)v.hash_mask + 1) * 12 + (size_t)v.leaf_capacity * (8 + 4 + 4 + 64 + kLeafVoxels * 8 + 4);
+  return ((size_t)v.hash_mask + 1) * sizeof(HashEntry) + (size_t)v.leaf_capacity * (8 + 4 + 4 + 64 + kLeafVoxels * 8 + 8 + 4 + 4);
 }
 void free_pool(GridView & v)
 {
-  cudaFree(v.hash_keys); cudaFree(v.hash_vals); cudaFree(v.leaf_key); cudaFree(v.leaf_hpos);
-  cudaFree(v.leaf_tile); cudaFree(v.leaf_mask); cudaFree(v.leaf_time); cudaFree(v.free_slots);
-  v.hash_keys = nullptr; v.hash_vals = nullptr; v.leaf_key = nullptr; v.leaf_hpos = nullptr;
-  v.leaf_tile = nullptr; v.leaf_mask = nullptr; v.leaf_time = nullptr; v.free_slots = nullptr;
+  cudaFree(v.hash); cudaFree(v.leaf_key); cudaFree(v.leaf_hpos);
+  cudaFree(v.leaf_tile); cudaFree(v.leaf_mask); cudaFree(v.leaf_time); cudaFree(v.leaf_tmin); cudaFree(v.free_slots); cudaFree(v.sweep_queue);
+  v.hash = nullptr; v.leaf_key = nullptr; v.leaf_hpos = nullptr;
+  v.leaf_tile = nullptr; v.leaf_mask = nullptr; v.leaf_time = nullptr; v.leaf_tmin = nullptr; v.free_slots = nullptr; v.sweep_queue = nullptr;
 }
 int alloc_tiles(stvl_grid * g, uint32_t tile_capacity, GridView * nv)
 {
@@ -179,8 +181,7 @@ int clear_pool(stvl_grid * g)
 {
   GridView & v = g->v;
   cudaStream_t s = g->stream;
-  CU(cudaMemsetAsync(v.hash_keys, 0xFF, ((size_t)v.hash_mask + 1) * 8, s));
-  CU(cudaMemsetAsync(v.hash_vals, 0xFF, ((size_t)v.hash_mask + 1) * 4, s));
+  CU(cudaMemsetAsync(v.hash, 0xFF, ((size_t)v.hash_mask + 1) * sizeof(HashEntry), s));
   CU(cudaMemsetAsync(v.leaf_key, 0xFF, (size_t)v.leaf_capacity * 8, s));
   CU(cudaMemsetAsync(v.leaf_mask, 0, (size_t)v.leaf_capacity * 64, s));
   CU(cudaMemsetAsync(v.leaf_time, 0, (size_t)v.leaf_capacity * kLeafVoxels * 8, s));
@@ -198,12 +199,24 @@ int clear_pool(stvl_grid * g)
   g->time_bound = 0.0;
   g->time_bound_inf = false;
   g->swept = false;
+  g->alloc_dirty = false;
+  return STVL_OK;
+}
+
+// fold the allocation cursor of the last Mark / load kernel into free_n / high_water (1-thread kernel, stream ordered)
+int ensure_folded(stvl_grid * g)
+{
+  if (!g->alloc_dirty) return STVL_OK;
+  CU(launch_fold_alloc(g->v, g->stream));
+  g->launches += 1;
+  g->alloc_dirty = false;
   return STVL_OK;
 }
 
 // copy the device counters to the host mirror and wait for the stream
 int fetch_counters(stvl_grid * g)
 {
+  { int rc = ensure_folded(g); if (rc != STVL_OK) return rc; }
   CU(cudaMemcpyAsync(g->h_ctr, g->v.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, g->stream));
   CU(cudaStreamSynchronize(g->stream));
   g->last = *g->h_ctr;
@@ -216,15 +229,16 @@ int fetch_counters(stvl_grid * g)
 
 int rebuild_leaf_hash(stvl_grid * g)
 {
+  { int rc = ensure_folded(g); if (rc != STVL_OK) return rc; }
   GridView & v = g->v;
-  CU(cudaMemsetAsync(v.hash_keys, 0xFF, ((size_t)v.hash_mask + 1) * 8, g->stream));
-  CU(cudaMemsetAsync(v.hash_vals, 0xFF, ((size_t)v.hash_mask + 1) * 4, g->stream));
+  CU(cudaMemsetAsync(v.hash, 0xFF, ((size_t)v.hash_mask + 1) * sizeof(HashEntry), g->stream));
   CU(launch_rebuild_hash(v, v.leaf_capacity, g->sm_count, g->stream));
   g->launches += 1;
   return STVL_OK;
 }
 int rebuild_tiles(stvl_grid * g)
 {
+  { int rc = ensure_folded(g); if (rc != STVL_OK) return rc; }
   GridView & v = g->v;
   CU(cudaMemsetAsync(v.tile_hash_keys, 0xFF, ((size_t)v.tile_hash_mask + 1) * 8, g->stream));
   CU(cudaMemsetAsync(v.tile_hash_vals, 0xFF, ((size_t)v.tile_hash_mask + 1) * 4, g->stream));
@@ -254,6 +268,7 @@ int grow_leaves(stvl_grid * g)
   CU(cudaMemsetAsync(nv.leaf_mask + oc * 16, 0, (nc - oc) * 64, s));
   CU(cudaMemcpyAsync(nv.leaf_time, old.leaf_time, oc * kLeafVoxels * 8, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemsetAsync(nv.leaf_time + oc * kLeafVoxels, 0, (nc - oc) * kLeafVoxels * 8, s));
+  CU(cudaMemcpyAsync(nv.leaf_tmin, old.leaf_tmin, oc * 8, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemcpyAsync(nv.free_slots, old.free_slots, oc * 4, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemsetAsync(&old.ctr->leaf_overflow, 0, 4, s));
   g->device_bytes += pool_bytes(nv);
@@ -284,8 +299,11 @@ int grow_tiles(stvl_grid * g)
 int launch_batches(stvl_grid * g, const std::vector<MarkBatch> & batches)
 {
   for (const MarkBatch & b : batches) {
-    CU(launch_mark(g->v, b, g->stream));
+    int rc = ensure_folded(g);   // every allocating kernel starts from a folded allocator
+    if (rc != STVL_OK) return rc;
+    CU(launch_mark(g->v, b, g->sm_count, g->stream));
     g->launches += 1;
+    g->alloc_dirty = true;
   }
   return STVL_OK;
 }
@@ -332,8 +350,16 @@ int after_fetch(stvl_grid * g)
   return STVL_OK;
 }
 
-uint32_t slots_upper(const stvl_grid * g) { return g->v.leaf_capacity; }
-uint32_t tiles_upper(const stvl_grid * g) { return g->v.tile_capacity; }
+// upper bounds of the pool slots / tiles in use, for grid sizing (exact counters at the last fetch + what the Marks
+// since then can have added)
+uint32_t slots_upper(const stvl_grid * g)
+{
+  return (uint32_t)std::min<uint64_t>(g->v.leaf_capacity, (uint64_t)g->last.high_water + g->pending_leaf_bound + 1);
+}
+uint32_t tiles_upper(const stvl_grid * g)
+{
+  return (uint32_t)std::min<uint64_t>(g->v.tile_capacity, (uint64_t)g->last.tile_n + g->pending_tile_bound + 1);
+}
 
 int build_batches(stvl_grid * g, const stvl_reading_t * readings, uint32_t n, const std::vector<const uint8_t *> & dev_ptrs,
                   std::vector<MarkBatch> * out, uint64_t * total_points, double * max_now, bool * monotone)
@@ -351,6 +377,7 @@ int build_batches(stvl_grid * g, const stvl_reading_t * readings, uint32_t n, co
     prev_now = r.now;
     *max_now = std::max(*max_now, r.now);
     if (cur.n_readings == kMaxBatchReadings) { out->push_back(cur); cur = MarkBatch{}; }
+    cur.min_now = cur.n_readings ? std::min(cur.min_now, r.now) : r.now;
     DevReading & d = cur.r[cur.n_readings++];
     d.data = dev_ptrs[i];
     d.n_points = r.n_points;
@@ -358,6 +385,11 @@ int build_batches(stvl_grid * g, const stvl_reading_t * readings, uint32_t n, co
     d.ox = r.origin[0]; d.oy = r.origin[1]; d.oz = r.origin[2];
     d.now = r.now;
     d.zmin = r.min_obstacle_height; d.zmax = r.max_obstacle_height;
+    // (double)z < zmin  <=>  z < roundup_f32(zmin)   and   (double)z > zmax  <=>  z > rounddown_f32(zmax)   for float z
+    d.zmin_f = (float)d.zmin; if ((double)d.zmin_f < d.zmin) d.zmin_f = std::nextafterf(d.zmin_f, INFINITY);
+    d.zmax_f = (float)d.zmax; if ((double)d.zmax_f > d.zmax) d.zmax_f = std::nextafterf(d.zmax_f, -INFINITY);
+    if (std::isnan(d.zmin)) d.zmin_f = -INFINITY;   // comparisons with NaN limits are false upstream: nothing is rejected
+    if (std::isnan(d.zmax)) d.zmax_f = INFINITY;
     d.mark_range_2 = (float)(r.obstacle_range * r.obstacle_range);   // `float mark_range_2 = range * range`, .cpp:274
     d.filter = r.filter;
     d.first_block = cur.total_blocks;
@@ -416,6 +448,7 @@ int run_mark(stvl_grid * g, const stvl_reading_t * readings, uint32_t n, const s
         one.r[0].first_block = 0;
         one.total_blocks = mark_blocks_for(b.r[k].n_points);
         one.use_atomic_max = 0;
+        one.min_now = b.r[k].now;
         seq.push_back(one);
       }
     batches.swap(seq);
@@ -628,6 +661,14 @@ int stvl_clear_frustums(stvl_grid_t * g, double now, const stvl_frustum_t * frus
   if (!(now >= g->time_bound) || may_raise) g->time_bound_inf = true;
 
   SweepOutputs out{};
+  // list buffers are sized by the active-voxel bound; in a long run without synchronising calls that bound only
+  // grows (by the points marked), so tighten it with one counter fetch before paying for a reallocation
+  const bool wants_lists = g->cfg.pub_voxels || (g->out_flags & STVL_OUT_CLEARED);
+  if (wants_lists && !g->counters_fresh &&
+      ((g->cfg.pub_voxels && g->active_upper > g->points.cap / 3) || ((g->out_flags & STVL_OUT_CLEARED) && g->active_upper > g->cleared.cap / 2))) {
+    rc = fetch_counters(g);
+    if (rc != STVL_OK) return rc;
+  }
   const uint64_t bound = g->active_upper;
   if (g->cfg.pub_voxels) {
     rc = ensure(g, g->points, (size_t)bound * 3 + 3); if (rc != STVL_OK) return rc;
@@ -643,7 +684,8 @@ int stvl_clear_frustums(stvl_grid_t * g, double now, const stvl_frustum_t * frus
     out.ambiguous = g->ambiguous.p; out.ambiguous_cap = cap;
   }
   CU(launch_sweep(g->v, g->frustums.p, (int)n_frustums, now, out, slots_upper(g), g->sm_count, g->stream));
-  g->launches += 2;
+  g->launches += 3;
+  g->alloc_dirty = false;   // the sweep prologue folds the allocator
   g->counters_fresh = false;
   g->swept = true;
   g->added_since_sweep = 0;
@@ -840,6 +882,8 @@ int stvl_reset_area(stvl_grid_t * g, double start_x, double start_y, double end_
   ENTER(g);
   int rc = verify_marks(g);
   if (rc != STVL_OK) return rc;
+  rc = ensure_folded(g);
+  if (rc != STVL_OK) return rc;
   CU(launch_reset_area(g->v, start_x, start_y, end_x, end_y, invert_area, slots_upper(g), g->sm_count, g->stream));
   g->launches += 1;
   return STVL_OK;
@@ -850,6 +894,8 @@ int stvl_active_count(stvl_grid_t * g, uint64_t * n)
   ENTER(g);
   if (!n) return fail(STVL_ERR_INVALID, "n is NULL");
   int rc = verify_marks(g);
+  if (rc != STVL_OK) return rc;
+  rc = ensure_folded(g);
   if (rc != STVL_OK) return rc;
   CU(cudaMemsetAsync(&g->v.ctr->n_active, 0, 8, g->stream));
   CU(cudaMemsetAsync(&g->v.ctr->live_leaves, 0, 4, g->stream));
@@ -874,6 +920,8 @@ int stvl_get_voxels(stvl_grid_t * g, int32_t * ix, int32_t * iy, int32_t * iz, d
     rc = ensure(g, g->dump_z, cap); if (rc != STVL_OK) return rc;
     rc = ensure(g, g->dump_t, cap); if (rc != STVL_OK) return rc;
   }
+  rc = ensure_folded(g);
+  if (rc != STVL_OK) return rc;
   CU(cudaMemsetAsync(&g->v.ctr->n_voxels_out, 0, 8, g->stream));
   CU(launch_dump_voxels(g->v, cap ? g->dump_x.p : nullptr, cap ? g->dump_y.p : nullptr, cap ? g->dump_z.p : nullptr,
                         cap ? g->dump_t.p : nullptr, cap, slots_upper(g), g->sm_count, g->stream));
@@ -910,8 +958,11 @@ int stvl_load_voxels(stvl_grid_t * g, const int32_t * ix, const int32_t * iy, co
   double tmax = -std::numeric_limits<double>::infinity();
   for (uint64_t i = 0; i < n; ++i) tmax = std::max(tmax, t[i]);
   for (int attempt = 0; attempt < 32; ++attempt) {
+    rc = ensure_folded(g);
+    if (rc != STVL_OK) return rc;
     CU(launch_load_voxels(g->v, g->dump_x.p, g->dump_y.p, g->dump_z.p, g->dump_t.p, n, g->stream));
     g->launches += 1;
+    g->alloc_dirty = true;
     rc = fetch_counters(g);
     if (rc != STVL_OK) return rc;
     if (!g->last.leaf_overflow && !g->last.tile_overflow) break;

@@ -37,7 +37,7 @@ struct Counters {
   uint32_t high_water;     // slots [0, high_water) have been handed out at least once
   uint32_t n_tombs;        // tombstones in the leaf hash
   uint32_t leaf_overflow;  // a Mark ran out of leaves (host grows the pool and replays)
-  uint32_t done_ctr;       // last-block-done ticket
+  uint32_t queue_n;        // leaves queued by the sweep's triage pass for the per-voxel pass
   // tile pool
   uint32_t tile_n;
   uint32_t tile_overflow;
@@ -57,11 +57,16 @@ struct Counters {
   uint32_t pad0;
 };
 
+struct __align__(16) HashEntry {
+  unsigned long long key;   // packed leaf coordinate, kEmptyKey or kTombKey
+  uint32_t val;             // pool slot; kInvalidSlot until published
+  uint32_t pad;
+};
+
 // -------- grid view handed to every kernel ----------------------------------------
 struct GridView {
-  // leaf hash
-  uint64_t * hash_keys;
-  uint32_t * hash_vals;
+  // leaf hash: 16 B entries {key, slot} so that one 128-bit load resolves a probe
+  HashEntry * hash;
   uint32_t hash_mask;      // capacity - 1 (power of two)
   // leaf pool
   uint64_t * leaf_key;     // kEmptyKey = slot is free
@@ -69,7 +74,10 @@ struct GridView {
   uint32_t * leaf_tile;    // column tile of the leaf
   uint32_t * leaf_mask;    // 16 x u32 per leaf
   double * leaf_time;      // 512 per leaf
+  double * leaf_tmin;      // lower bound of the mark times stored in the leaf (-inf = unknown): lets a sweep skip the
+                           // 4 KB time block of leaves in which nothing can expire
   uint32_t * free_slots;
+  uint32_t * sweep_queue;  // leaf slots that need the per-voxel pass of the current sweep
   uint32_t leaf_capacity;
   // column tiles
   uint64_t * tile_hash_keys;
@@ -107,6 +115,7 @@ struct DevReading {
   double zmin, zmax;
   float mark_range_2;
   int32_t filter;         // STVL_FILTER_PASSTHROUGH applies the z window in-kernel
+  float zmin_f, zmax_f;   // float thresholds EXACTLY equivalent to the double window for float z: zmin rounded up, zmax rounded down
   uint32_t first_block;   // first CTA of this reading in the batched launch
   uint32_t vec4;          // 1: point_step==16, offsets 0/4/8, 16 B aligned -> float4 loads
 };
@@ -116,6 +125,7 @@ struct MarkBatch {
   uint32_t total_blocks;
   uint32_t use_atomic_max;  // 1: batched mode (monotone clocks), 0: plain stores
   uint32_t pad;
+  double min_now;           // smallest clock sample in the batch: initial leaf_tmin of leaves created by it
 };
 
 // -------- helpers -------------------------------------------------------------------

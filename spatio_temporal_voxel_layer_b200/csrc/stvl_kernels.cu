@@ -9,12 +9,18 @@
 // Everything is integer / FP64 scalar work bound by HBM traffic: no tensor cores.  All
 // arithmetic whose result feeds a comparison or a stored value uses the _rn intrinsics
 // (never contracted into FMA) in the reference's operation order, see SURVEY.md §7.
+#include <math_constants.h>
+
 #include "stvl_device.cuh"
 #include "stvl_kernels.h"
 
 namespace stvl {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
+
+// fire-and-forget global reductions (no return value, no scoreboard wait)
+__device__ __forceinline__ void red_or_u32(uint32_t * p, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_max_u64(unsigned long long * p, unsigned long long v) { asm volatile("red.global.max.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
 
 // =====================================================================================
 // hash helpers
@@ -71,14 +77,19 @@ __device__ __forceinline__ uint32_t leaf_alloc(const GridView & g, uint32_t free
   return slot;
 }
 
-// find-or-insert a leaf; returns its pool slot (or kOverflowSlot)
-__device__ uint32_t leaf_find_or_insert(const GridView & g, uint64_t key, int bx, int by, uint32_t free_n0, uint32_t high_water0)
+// find-or-insert a leaf; returns its pool slot (or kOverflowSlot).  Probes use ordinary (L1-cacheable) 128-bit loads:
+// a stale line can only show EMPTY where a key has since been published (the CAS then returns the truth) or an
+// unpublished slot (then the volatile spin below reads L2); keys never change while a Mark kernel runs.
+__device__ uint32_t leaf_find_or_insert(const GridView & g, uint64_t key, int bx, int by, uint32_t free_n0, uint32_t high_water0,
+                                        double tmin_init)
 {
   uint32_t h = (uint32_t)mix64(key) & g.hash_mask;
   for (uint32_t probe = 0; probe <= g.hash_mask; ++probe) {
-    uint64_t k = ld_volatile_u64(&g.hash_keys[h]);
+    const uint4 e = *reinterpret_cast<const uint4 *>(&g.hash[h]);
+    uint64_t k = (uint64_t)e.x | ((uint64_t)e.y << 32);
+    uint32_t v = e.z;
     if (k == kEmptyKey) {
-      const uint64_t old = atomicCAS((unsigned long long *)&g.hash_keys[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
+      const uint64_t old = atomicCAS(&g.hash[h].key, (unsigned long long)kEmptyKey, (unsigned long long)key);
       if (old == kEmptyKey) {
         const uint32_t slot = leaf_alloc(g, free_n0, high_water0);
         if (slot == kOverflowSlot) {
@@ -88,16 +99,17 @@ __device__ uint32_t leaf_find_or_insert(const GridView & g, uint64_t key, int bx
           g.leaf_key[slot] = key;
           g.leaf_hpos[slot] = h;
           g.leaf_tile[slot] = tile;
+          g.leaf_tmin[slot] = tmin_init;
         }
         __threadfence();
-        *reinterpret_cast<volatile uint32_t *>(&g.hash_vals[h]) = slot;
+        *reinterpret_cast<volatile uint32_t *>(&g.hash[h].val) = slot;
         return slot;
       }
       k = old;
+      v = kInvalidSlot;
     }
     if (k == key) {
-      uint32_t v;
-      while ((v = ld_volatile_u32(&g.hash_vals[h])) == kInvalidSlot) { __nanosleep(20); }
+      while (v == kInvalidSlot) { v = ld_volatile_u32(&g.hash[h].val); if (v == kInvalidSlot) __nanosleep(20); }
       return v;
     }
     h = (h + 1) & g.hash_mask;   // other key or tombstone: keep probing
@@ -106,46 +118,22 @@ __device__ uint32_t leaf_find_or_insert(const GridView & g, uint64_t key, int bx
   return kOverflowSlot;
 }
 
-// read-only lookup
-__device__ uint32_t leaf_find(const GridView & g, uint64_t key)
+// fold the leaves handed out by the previous Mark / load kernel into the allocator state.  Runs single-threaded
+// between kernels (stream order), so allocating kernels need no per-block epilogue.
+__device__ __forceinline__ void fold_alloc(const GridView & g)
 {
-  uint32_t h = (uint32_t)mix64(key) & g.hash_mask;
-  for (uint32_t probe = 0; probe <= g.hash_mask; ++probe) {
-    const uint64_t k = g.hash_keys[h];
-    if (k == kEmptyKey) return kInvalidSlot;
-    if (k == key) return g.hash_vals[h];
-    h = (h + 1) & g.hash_mask;
-  }
-  return kInvalidSlot;
+  Counters * c = g.ctr;
+  const uint32_t cursor = c->alloc_cursor;
+  if (cursor == 0) return;
+  const uint32_t free_n = c->free_n, hw = c->high_water;
+  const uint32_t from_free = cursor < free_n ? cursor : free_n;
+  unsigned long long nhw = (unsigned long long)hw + (cursor - from_free);
+  if (nhw > g.leaf_capacity) nhw = g.leaf_capacity;
+  c->free_n = free_n - from_free;
+  c->high_water = (uint32_t)nhw;
+  c->alloc_cursor = 0;
 }
-
-// last CTA of a kernel that allocated leaves folds the cursor into the allocator state
-__device__ __forceinline__ void alloc_epilogue(const GridView & g)
-{
-  __shared__ bool is_last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const uint32_t ticket = atomicAdd(&g.ctr->done_ctr, 1u);
-    is_last = (ticket == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (is_last && threadIdx.x == 0) {
-    __threadfence();
-    Counters * c = g.ctr;
-    const uint32_t cursor = ld_volatile_u32(&c->alloc_cursor);
-    const uint32_t free_n = ld_volatile_u32(&c->free_n);
-    const uint32_t hw = ld_volatile_u32(&c->high_water);
-    const uint32_t from_free = cursor < free_n ? cursor : free_n;
-    unsigned long long nhw = (unsigned long long)hw + (cursor - from_free);
-    if (nhw > g.leaf_capacity) nhw = g.leaf_capacity;
-    c->free_n = free_n - from_free;
-    c->high_water = (uint32_t)nhw;
-    c->alloc_cursor = 0;
-    c->done_ctr = 0;
-    __threadfence();
-  }
-}
+__global__ void fold_alloc_kernel(const GridView g) { fold_alloc(g); }
 
 // =====================================================================================
 // Mark — reference .cpp:269-309
@@ -184,79 +172,249 @@ __device__ __forceinline__ PointXYZ load_point(const DevReading & r, unsigned lo
 constexpr int kMarkThreads = 256;
 constexpr int kMarkPointsPerThread = 4;
 constexpr int kMarkPointsPerBlock = kMarkThreads * kMarkPointsPerThread;
+constexpr int kMarkTable = 64;        // block-local leaf table (shared memory)
+constexpr int kMarkProbes = 8;
 
-__global__ void __launch_bounds__(kMarkThreads)
-mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch)
+// write one voxel straight to the global store (fallback when the block-local table is full)
+__device__ __forceinline__ void mark_voxel_direct(const GridView & g, uint64_t key, unsigned l, double now, unsigned long long now_bits,
+                                                  bool use_max, uint32_t free_n0, uint32_t high_water0, double tmin_init)
 {
-  // which reading does this CTA belong to?
+  int bx, by, bz;
+  unpack_leaf_key(key, bx, by, bz);
+  const uint32_t slot = leaf_find_or_insert(g, key, bx, by, free_n0, high_water0, tmin_init);
+  if (slot == kOverflowSlot) return;
+  atomicOr(&g.leaf_mask[(size_t)slot * 16 + (l >> 5)], 1u << (l & 31));
+  double * tp = &g.leaf_time[(size_t)slot * kLeafVoxels + l];
+  if (use_max) atomicMax(reinterpret_cast<unsigned long long *>(tp), now_bits);
+  else {
+    *tp = now;   // MarkGridPoint: setValueOn overwrite, .cpp:421-430
+    if (g.leaf_tmin[slot] > now) g.leaf_tmin[slot] = -CUDART_INF;   // clocks are not monotone here
+  }
+}
+
+// Mark — persistent CTAs; each owns a contiguous range of 1024-point chunks of the batched clouds:
+//   1. coalesced 128-bit streaming loads of the cloud; the loads of the NEXT chunk are issued before the current one
+//      is processed, so every resident warp always has 2 KB of the cloud in flight
+//   2. range / z-window tests and key quantisation in the reference's exact arithmetic (.cpp:285-303), written
+//      branch-free so the four points of a thread advance together
+//   3. block-level dedupe in shared memory: a depth image puts ~100 points into every voxel and ~1000 into every
+//      8^3 leaf, so the CTA ORs its points into a small table of {leaf key, 512-bit mask} that lives across chunks
+//   4. flush (at the end of the range, or when the range crosses into the next reading): one global hash probe per
+//      distinct leaf, one 32-bit OR per touched mask word and one 64-bit max (or store) per distinct voxel
+struct MarkParams {   // the per-reading constants a CTA keeps in shared memory
+  double ox, oy, oz, now;
+  float zmin_f, zmax_f, mark_range_2, range2_reject, oxf, oyf, ozf;
+  int filter;
+};
+__device__ __forceinline__ void mark_params_from(MarkParams & p, const DevReading & r)
+{
+  p.ox = r.ox; p.oy = r.oy; p.oz = r.oz; p.now = r.now;
+  p.zmin_f = r.zmin_f; p.zmax_f = r.zmax_f; p.mark_range_2 = r.mark_range_2; p.filter = r.filter;
+  p.oxf = (float)r.ox; p.oyf = (float)r.oy; p.ozf = (float)r.oz;
+  // single-precision screening threshold: points whose float distance^2 exceeds it are certainly out of range
+  // (float evaluation error << 1e-3 relative at map-scale coordinates); everything else takes the exact double test
+  const float m = fmaxf(fmaxf(fabsf(p.oxf), fabsf(p.oyf)), fmaxf(fabsf(p.ozf), 1.0f));
+  p.range2_reject = r.mark_range_2 * 1.001f + 1e-3f + 1e-5f * m * (sqrtf(fmaxf(r.mark_range_2, 0.f)) + 1.0f);
+  if (!(p.range2_reject == p.range2_reject)) p.range2_reject = CUDART_INF_F;
+}
+
+__device__ __forceinline__ int mark_reading_of(const MarkBatch & batch, uint32_t chunk)
+{
   int ri = 0;
 #pragma unroll 1
-  for (int k = 1; k < (int)batch.n_readings; ++k) if (blockIdx.x >= batch.r[k].first_block) ri = k;
-  const DevReading & r = batch.r[ri];
+  for (int k = 1; k < (int)batch.n_readings; ++k) if (chunk >= batch.r[k].first_block) ri = k;
+  return ri;
+}
+
+__global__ void __launch_bounds__(kMarkThreads, 4)
+mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uint32_t chunks_per_cta)
+{
+  __shared__ unsigned long long s_key[kMarkTable];
+  __shared__ uint32_t s_mask[kMarkTable][16];
+  __shared__ uint32_t s_slot[kMarkTable];
+  __shared__ unsigned int s_drop[2];
+  __shared__ MarkParams s_par;
+  // the reading descriptors are copied from the (dynamically indexed, slow) kernel-parameter bank to shared memory once
+  __shared__ DevReading s_r[kMaxBatchReadings];
+  {
+    const uint32_t words = batch.n_readings * (uint32_t)(sizeof(DevReading) / 8);
+    const unsigned long long * src = reinterpret_cast<const unsigned long long *>(&batch.r[0]);
+    unsigned long long * dst = reinterpret_cast<unsigned long long *>(&s_r[0]);
+    for (uint32_t i = threadIdx.x; i < words; i += kMarkThreads) dst[i] = src[i];
+  }
+  __syncthreads();
+
   const unsigned lane = threadIdx.x & 31;
   const uint32_t free_n0 = g.ctr->free_n;
   const uint32_t high_water0 = g.ctr->high_water;
-  const unsigned long long base = (unsigned long long)(blockIdx.x - r.first_block) * kMarkPointsPerBlock;
-
-  // issue all loads of this thread first (memory-level parallelism), then quantise
-  PointXYZ pts[kMarkPointsPerThread];
-#pragma unroll
-  for (int k = 0; k < kMarkPointsPerThread; ++k) pts[k] = load_point(r, base + (unsigned long long)k * kMarkThreads + threadIdx.x);
-
-  const unsigned long long now_bits = (unsigned long long)__double_as_longlong(r.now);
+  const bool use_max = batch.use_atomic_max != 0;
   unsigned int drop_range = 0, drop_nonfinite = 0;
+  uint64_t last_key = kEmptyKey;   // this thread's most recent leaf and its table entry
+  int last_e = -1;
 
+  const uint32_t chunk_begin = blockIdx.x * chunks_per_cta;
+  const uint32_t chunk_end = min(chunk_begin + chunks_per_cta, batch.total_blocks);
+  if (chunk_begin >= chunk_end) return;
+
+  // block-local table and the first reading's parameters
+  if (threadIdx.x < kMarkTable) s_key[threadIdx.x] = kEmptyKey;
+  if (threadIdx.x < 2) s_drop[threadIdx.x] = 0;
 #pragma unroll
-  for (int k = 0; k < kMarkPointsPerThread; ++k) {
-    const float fx = pts[k].x, fy = pts[k].y, fz = pts[k].z;
-    bool valid = pts[k].ok;
-    if (valid && !(isfinite(fx) && isfinite(fy) && isfinite(fz))) { valid = false; ++drop_nonfinite; }
-    if (valid && r.filter == 2) {   // PassThrough z window, reference measurement_buffer.cpp:165-175
-      const double zd = (double)fz;
-      if (zd < r.zmin || zd > r.zmax) valid = false;
+  for (int i = threadIdx.x; i < kMarkTable * 16; i += kMarkThreads) (&s_mask[0][0])[i] = 0;
+  int ri = 0;
+#pragma unroll 1
+  for (int q = 1; q < (int)batch.n_readings; ++q) if (chunk_begin >= s_r[q].first_block) ri = q;
+  if (threadIdx.x == 0) mark_params_from(s_par, s_r[ri]);
+
+  PointXYZ nxt[kMarkPointsPerThread];
+  {
+    const DevReading & r0 = s_r[ri];
+    const unsigned long long base = (unsigned long long)(chunk_begin - r0.first_block) * kMarkPointsPerBlock;
+#pragma unroll
+    for (int k = 0; k < kMarkPointsPerThread; ++k) nxt[k] = load_point(r0, base + (unsigned long long)k * kMarkThreads + threadIdx.x);
+  }
+  __syncthreads();
+
+  for (uint32_t chunk = chunk_begin; chunk < chunk_end; ++chunk) {
+    PointXYZ pts[kMarkPointsPerThread];
+#pragma unroll
+    for (int k = 0; k < kMarkPointsPerThread; ++k) pts[k] = nxt[k];
+    // prefetch the next chunk of this CTA (it may already belong to the next reading)
+    const bool last = chunk + 1 == chunk_end;
+    int ri_next = ri;
+    if (!last) {
+      if (ri + 1 < (int)batch.n_readings && chunk + 1 >= s_r[ri + 1].first_block) ri_next = ri + 1;
+      const DevReading & rn = s_r[ri_next];
+      const unsigned long long base = (unsigned long long)(chunk + 1 - rn.first_block) * kMarkPointsPerBlock;
+#pragma unroll
+      for (int k = 0; k < kMarkPointsPerThread; ++k) nxt[k] = load_point(rn, base + (unsigned long long)k * kMarkThreads + threadIdx.x);
     }
-    int ix = 0, iy = 0, iz = 0;
-    if (valid) {
+
+    // ---- cheap rejection first (branch-free): depth images are full of invalid pixels and floor / ceiling returns
+    const double ox = s_par.ox, oy = s_par.oy, oz = s_par.oz;
+    const float range2 = s_par.mark_range_2, range2_reject = s_par.range2_reject;
+    const float oxf = s_par.oxf, oyf = s_par.oyf, ozf = s_par.ozf;
+    const bool zwin = s_par.filter == 2;
+    const float zlo = zwin ? s_par.zmin_f : -CUDART_INF_F, zhi = zwin ? s_par.zmax_f : CUDART_INF_F;
+    bool pre[kMarkPointsPerThread];
+#pragma unroll
+    for (int k = 0; k < kMarkPointsPerThread; ++k) {
+      const float fx = pts[k].x, fy = pts[k].y, fz = pts[k].z;
+      const bool finite = isfinite(fx) && isfinite(fy) && isfinite(fz);
+      drop_nonfinite += (pts[k].ok && !finite) ? 1u : 0u;
+      // PassThrough z window (reference measurement_buffer.cpp:165-175) on exactly equivalent float thresholds, and a
+      // single-precision range screen that only ever rejects points the exact test below would reject too
+      const float ax = fx - oxf, ay = fy - oyf, az = fz - ozf;
+      const float d2f = ax * ax + ay * ay + az * az;
+      pre[k] = pts[k].ok && finite && !(fz < zlo || fz > zhi) && !(d2f > range2_reject);
+    }
+    // ---- exact arithmetic + block-local dedupe for the survivors ------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < kMarkPointsPerThread; ++k) {
+      if (!pre[k]) continue;
+      const float fx = pts[k].x, fy = pts[k].y, fz = pts[k].z;
+      const double xd = (double)fx, yd = (double)fy, zd = (double)fz;
       // .cpp:285-291  (double arithmetic, narrowed to float, compared against the float range^2 and 0.0001)
-      const double dx = __dsub_rn((double)fx, r.ox), dy = __dsub_rn((double)fy, r.oy), dz = __dsub_rn((double)fz, r.oz);
+      const double dx = __dsub_rn(xd, ox), dy = __dsub_rn(yd, oy), dz = __dsub_rn(zd, oz);
       const float distance_2 = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-      if (distance_2 > r.mark_range_2 || (double)distance_2 < 0.0001) valid = false;
-    }
-    if (valid) {
+      if (distance_2 > range2 || (double)distance_2 < 0.0001) continue;
       // .cpp:293-303: shift negatives by one voxel (z tests y's sign — sic), multiply by 1/vs, truncate toward zero
-      const double X = fx < 0 ? __dsub_rn((double)fx, g.vs) : (double)fx;
-      const double Y = fy < 0 ? __dsub_rn((double)fy, g.vs) : (double)fy;
-      const double Z = fy < 0 ? __dsub_rn((double)fz, g.vs) : (double)fz;
+      const double X = fx < 0 ? __dsub_rn(xd, g.vs) : xd;
+      const double Y = fy < 0 ? __dsub_rn(yd, g.vs) : yd;
+      const double Z = fy < 0 ? __dsub_rn(zd, g.vs) : zd;
       const double gx = __dmul_rn(X, g.inv_vs), gy = __dmul_rn(Y, g.inv_vs), gz = __dmul_rn(Z, g.inv_vs);
       const double lim = 8388608.0;   // 2^23 voxels = 2^20 leaves
-      if (fabs(gx) >= lim || fabs(gy) >= lim || fabs(gz) >= lim) { valid = false; ++drop_range; }
-      else { ix = __double2int_rz(gx); iy = __double2int_rz(gy); iz = __double2int_rz(gz); }
-    }
-    const int bx = ix >> 3, by = iy >> 3, bz = iz >> 3;
-    if (valid && !shard_owns(bx, g.shard_index, g.shard_count, g.shard_width)) valid = false;
-
-    // warp-level dedupe: one hash lookup per distinct leaf, one write per distinct voxel
-    const unsigned act = __ballot_sync(kFull, valid);
-    if (valid) {
+      if (!(fabs(gx) < lim && fabs(gy) < lim && fabs(gz) < lim)) { ++drop_range; continue; }
+      const int ix = __double2int_rz(gx), iy = __double2int_rz(gy), iz = __double2int_rz(gz);
+      const int bx = ix >> 3, by = iy >> 3, bz = iz >> 3;
+      if (g.shard_count > 1 && !shard_owns(bx, g.shard_index, g.shard_count, g.shard_width)) continue;
       const uint64_t key = pack_leaf_key(bx, by, bz);
-      const unsigned li = (unsigned)(((ix & 7) * 8 + (iy & 7)) * 8 + (iz & 7));
-      const unsigned peers = __match_any_sync(act, (unsigned long long)key);
-      const int leader = __ffs(peers) - 1;
-      uint32_t slot = 0;
-      if ((int)lane == leader) slot = leaf_find_or_insert(g, key, bx, by, free_n0, high_water0);
-      slot = __shfl_sync(peers, slot, leader);
-      const unsigned same = __match_any_sync(peers, li);
-      if (slot != kOverflowSlot && (int)lane == __ffs(same) - 1) {
-        atomicOr(&g.leaf_mask[(size_t)slot * 16 + (li >> 5)], 1u << (li & 31));
-        double * tp = &g.leaf_time[(size_t)slot * kLeafVoxels + li];
-        if (batch.use_atomic_max) atomicMax(reinterpret_cast<unsigned long long *>(tp), now_bits);
-        else *tp = r.now;   // MarkGridPoint: setValueOn overwrite, .cpp:421-430
+      const unsigned l = (unsigned)(((ix & 7) * 8 + (iy & 7)) * 8 + (iz & 7));
+      // find-or-claim the leaf in the block-local table (consecutive points of a thread mostly share their leaf)
+      int e = -1;
+      if (key == last_key) e = last_e;
+      else {
+        uint32_t h = ((uint32_t)bx * 73856093u ^ (uint32_t)by * 19349663u ^ (uint32_t)bz * 83492791u) & (kMarkTable - 1);
+#pragma unroll 1
+        for (int p = 0; p < kMarkProbes; ++p) {
+          unsigned long long cur = s_key[h];
+          if (cur == kEmptyKey) cur = atomicCAS(&s_key[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
+          if (cur == key || cur == kEmptyKey) { e = (int)h; break; }
+          h = (h + 1) & (kMarkTable - 1);
+        }
+        last_key = key; last_e = e;
+      }
+      if (e >= 0) {
+        const uint32_t bit = 1u << (l & 31);
+        if (!(s_mask[e][l >> 5] & bit)) atomicOr(&s_mask[e][l >> 5], bit);
+      } else {   // table full (scattered cloud): straight to the global store
+        mark_voxel_direct(g, key, l, s_par.now, (unsigned long long)__double_as_longlong(s_par.now), use_max, free_n0, high_water0, batch.min_now);
       }
     }
+
+    // ---- flush at the end of the range or when the next chunk belongs to another reading -----------------------------
+    if (last || ri_next != ri) {
+      __syncthreads();
+      if (threadIdx.x < kMarkTable) {   // one thread per distinct leaf resolves (or creates) it in the global hash
+        const unsigned long long key = s_key[threadIdx.x];
+        uint32_t slot = kOverflowSlot;
+        if (key != kEmptyKey) {
+          int bx, by, bz;
+          unpack_leaf_key(key, bx, by, bz);
+          slot = leaf_find_or_insert(g, key, bx, by, free_n0, high_water0, batch.min_now);
+        }
+        s_slot[threadIdx.x] = slot;
+      }
+      __syncthreads();
+      // per touched mask word one 32-bit OR, per distinct voxel one 64-bit max (batched launch, monotone clocks) or a
+      // plain store (per-reading launches: exact overwrite semantics of MarkGridPoint, .cpp:421-430)
+      const double now = s_par.now;
+      const unsigned long long now_bits = (unsigned long long)__double_as_longlong(now);
+#pragma unroll
+      for (int i = threadIdx.x; i < kMarkTable * 16; i += kMarkThreads) {
+        uint32_t m = (&s_mask[0][0])[i];
+        if (!m) continue;
+        (&s_mask[0][0])[i] = 0;
+        const uint32_t slot = s_slot[i >> 4];
+        if (slot == kOverflowSlot) continue;
+        const unsigned w = i & 15;
+        red_or_u32(&g.leaf_mask[(size_t)slot * 16 + w], m);
+        double * tp = g.leaf_time + (size_t)slot * kLeafVoxels + w * 32;
+        if (!use_max && g.leaf_tmin[slot] > now) g.leaf_tmin[slot] = -CUDART_INF;   // clocks are not monotone here
+        while (m) {
+          const int b = __ffs(m) - 1; m &= m - 1;
+          if (use_max) red_max_u64(reinterpret_cast<unsigned long long *>(tp + b), now_bits);
+          else tp[b] = now;
+        }
+      }
+      __syncthreads();
+      if (!last) {   // next reading: fresh table, new parameters
+        if (threadIdx.x < kMarkTable) s_key[threadIdx.x] = kEmptyKey;
+        last_key = kEmptyKey; last_e = -1;
+        if (threadIdx.x == 0) mark_params_from(s_par, s_r[ri_next]);
+        __syncthreads();
+      }
+    }
+    ri = ri_next;
   }
-  if (drop_range) atomicAdd(&g.ctr->dropped_range, (unsigned long long)drop_range);
-  if (drop_nonfinite) atomicAdd(&g.ctr->dropped_nonfinite, (unsigned long long)drop_nonfinite);
-  alloc_epilogue(g);
+
+  // dropped-point statistics: warp reduce, shared-memory add, one global atomic per CTA
+  if (__ballot_sync(kFull, (drop_range | drop_nonfinite) != 0)) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      drop_range += __shfl_xor_sync(kFull, drop_range, d);
+      drop_nonfinite += __shfl_xor_sync(kFull, drop_nonfinite, d);
+    }
+    if (lane == 0) {
+      if (drop_range) atomicAdd(&s_drop[0], drop_range);
+      if (drop_nonfinite) atomicAdd(&s_drop[1], drop_nonfinite);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_drop[0]) atomicAdd(&g.ctr->dropped_range, (unsigned long long)s_drop[0]);
+    if (s_drop[1]) atomicAdd(&g.ctr->dropped_nonfinite, (unsigned long long)s_drop[1]);
+  }
 }
 
 // bulk load of (index, time) pairs — MarkGridPoint semantics (overwrite), for tests / restore
@@ -273,15 +431,15 @@ load_voxels_kernel(const GridView g, const int32_t * __restrict__ vx, const int3
     if (!(leaf_coord_ok(bx) && leaf_coord_ok(by) && leaf_coord_ok(bz))) {
       atomicAdd(&g.ctr->dropped_range, 1ull);
     } else if (shard_owns(bx, g.shard_index, g.shard_count, g.shard_width)) {
-      const uint32_t slot = leaf_find_or_insert(g, pack_leaf_key(bx, by, bz), bx, by, free_n0, high_water0);
+      const uint32_t slot = leaf_find_or_insert(g, pack_leaf_key(bx, by, bz), bx, by, free_n0, high_water0, -CUDART_INF);
       if (slot != kOverflowSlot) {
+        if (g.leaf_tmin[slot] != -CUDART_INF) g.leaf_tmin[slot] = -CUDART_INF;   // arbitrary times: bound unknown
         const unsigned li = (unsigned)(((ix & 7) * 8 + (iy & 7)) * 8 + (iz & 7));
         atomicOr(&g.leaf_mask[(size_t)slot * 16 + (li >> 5)], 1u << (li & 31));
         g.leaf_time[(size_t)slot * kLeafVoxels + li] = vt[i];
       }
     }
   }
-  alloc_epilogue(g);
 }
 
 // =====================================================================================
@@ -323,17 +481,146 @@ __device__ __forceinline__ int classify_leaf(const DevFrustum & f, int bx, int b
 __device__ __forceinline__ void free_leaf(const GridView & g, uint32_t slot)
 {
   const uint32_t h = g.leaf_hpos[slot];
-  g.hash_keys[h] = kTombKey;
-  g.hash_vals[h] = kInvalidSlot;
+  g.hash[h].key = kTombKey;
+  g.hash[h].val = kInvalidSlot;
   g.leaf_key[slot] = kEmptyKey;
   const uint32_t i = atomicAdd(&g.ctr->free_n, 1u);
   g.free_slots[i] = slot;
   atomicAdd(&g.ctr->n_tombs, 1u);
 }
 
+// block-level reduction of the per-thread sweep statistics into the device counters
+struct SweepAcc {
+  unsigned int swept = 0, surv = 0, clear = 0, rewr = 0, amb = 0;
+  int min_x = INT_MAX, min_y = INT_MAX, max_x = INT_MIN, max_y = INT_MIN;
+};
+__device__ __forceinline__ void sweep_publish(const GridView & g, SweepAcc a)
+{
+  __shared__ unsigned int s_red[5];
+  __shared__ int s_bb[4];
+  if (threadIdx.x == 0) { s_red[0] = s_red[1] = s_red[2] = s_red[3] = s_red[4] = 0; s_bb[0] = s_bb[1] = INT_MAX; s_bb[2] = s_bb[3] = INT_MIN; }
+  __syncthreads();
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    a.swept += __shfl_xor_sync(kFull, a.swept, d); a.surv += __shfl_xor_sync(kFull, a.surv, d);
+    a.clear += __shfl_xor_sync(kFull, a.clear, d); a.rewr += __shfl_xor_sync(kFull, a.rewr, d);
+    a.amb += __shfl_xor_sync(kFull, a.amb, d);
+    a.min_x = min(a.min_x, __shfl_xor_sync(kFull, a.min_x, d)); a.min_y = min(a.min_y, __shfl_xor_sync(kFull, a.min_y, d));
+    a.max_x = max(a.max_x, __shfl_xor_sync(kFull, a.max_x, d)); a.max_y = max(a.max_y, __shfl_xor_sync(kFull, a.max_y, d));
+  }
+  if ((threadIdx.x & 31) == 0 && (a.swept | a.surv | a.clear | a.rewr | a.amb)) {
+    atomicAdd(&s_red[0], a.swept); atomicAdd(&s_red[1], a.surv); atomicAdd(&s_red[2], a.clear);
+    atomicAdd(&s_red[3], a.rewr); atomicAdd(&s_red[4], a.amb);
+    atomicMin(&s_bb[0], a.min_x); atomicMin(&s_bb[1], a.min_y); atomicMax(&s_bb[2], a.max_x); atomicMax(&s_bb[3], a.max_y);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Counters * c = g.ctr;
+    if (s_red[0]) atomicAdd(&c->n_swept, (unsigned long long)s_red[0]);
+    if (s_red[1]) atomicAdd(&c->n_survived, (unsigned long long)s_red[1]);
+    if (s_red[2]) {
+      atomicAdd(&c->n_cleared, (unsigned long long)s_red[2]);
+      atomicMin(&c->cb_min_x, s_bb[0]); atomicMin(&c->cb_min_y, s_bb[1]);
+      atomicMax(&c->cb_max_x, s_bb[2]); atomicMax(&c->cb_max_y, s_bb[3]);
+    }
+    if (s_red[3]) atomicAdd(&c->n_rewritten, (unsigned long long)s_red[3]);
+    if (s_red[4]) atomicAdd(&c->n_ambiguous, (unsigned long long)s_red[4]);
+  }
+}
+
+__device__ __forceinline__ void stage_frustums(DevFrustum * fr, const DevFrustum * __restrict__ frustums_gmem, int n_frustums)
+{
+  // the frustum parameter blocks (plane sets / hourglass parameters) live in shared memory for the whole kernel
+  const int words = n_frustums * (int)(sizeof(DevFrustum) / 8);
+  const double * src = reinterpret_cast<const double *>(frustums_gmem);
+  double * dst = reinterpret_cast<double *>(fr);
+  for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+}
+
+// can a leaf whose oldest mark time is tmin contain a voxel that expires by decay alone?  The decay duration is
+// non-increasing in a voxel's age for the linear model; the exponential / persistent ones never go negative for
+// voxel_decay >= 0 (reference .cpp:320-331).  tmin = -inf ("unknown") always answers yes.
+__device__ __forceinline__ bool leaf_may_expire(const GridView & g, double now, double tmin)
+{
+  if (g.decay_model == 0) return __dsub_rn(g.voxel_decay, __dsub_rn(now, tmin)) < 0.;
+  return !(g.voxel_decay >= 0.0);
+}
+
+// Sweep, pass 1 — ONE THREAD PER LEAF, coalesced streaming over the dense per-leaf arrays (key, tmin, tile, 64 B value
+// mask).  A leaf outside every frustum's bounding box whose oldest voxel is too young to expire cannot change: its
+// survivors are counted straight from the mask and its 4 KB time block is never touched.  Every other leaf goes to
+// the global work queue of pass 2.
 __global__ void __launch_bounds__(kSweepThreads)
-sweep_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gmem, const int n_frustums, const double now,
-             const SweepOutputs out)
+sweep_triage_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gmem, const int n_frustums, const double now,
+                    const int force_full)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DevFrustum * fr = reinterpret_cast<DevFrustum *>(smem_raw);
+  stage_frustums(fr, frustums_gmem, n_frustums);
+  const uint32_t n_slots = g.ctr->high_water;
+  SweepAcc acc;
+  for (uint32_t slot = blockIdx.x * kSweepThreads + threadIdx.x; slot < n_slots; slot += gridDim.x * kSweepThreads) {
+    const uint64_t key = g.leaf_key[slot];
+    if (key == kEmptyKey) continue;   // free slot
+    const double tmin = g.leaf_tmin[slot];
+    const uint32_t tile = g.leaf_tile[slot];
+    const uint4 * mp = reinterpret_cast<const uint4 *>(g.leaf_mask + (size_t)slot * 16);
+    uint4 mw[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) mw[q] = mp[q];
+    uint32_t any = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) any |= mw[q].x | mw[q].y | mw[q].z | mw[q].w;
+    if (any == 0) { free_leaf(g, slot); continue; }   // nothing left in this leaf: pruneGrid, .cpp:223
+    bool full_path = force_full || leaf_may_expire(g, now, tmin);
+    if (!full_path) {
+      int bx, by, bz;
+      unpack_leaf_key(key, bx, by, bz);
+      const int x0 = bx * 8, y0 = by * 8, z0 = bz * 8;
+      for (int f = 0; f < n_frustums && !full_path; ++f) {
+        const DevFrustum & F = fr[f];
+        if (F.type < 0) continue;
+        full_path = !F.cull || !(x0 + 7 < F.lo[0] || x0 > F.hi[0] || y0 + 7 < F.lo[1] || y0 > F.hi[1] || z0 + 7 < F.lo[2] || z0 > F.hi[2]);
+      }
+    }
+    if (full_path) {
+      g.sweep_queue[atomicAdd(&g.ctr->queue_n, 1u)] = slot;
+      continue;
+    }
+    // PopulateCostmapAndPointcloud .cpp:242-250 for every (surviving) voxel: per-column popcounts, two adjacent u32
+    // column counters per 64-bit reduction (no carry: counts stay < 2^32)
+    unsigned cnt = 0;
+    unsigned long long * tc = reinterpret_cast<unsigned long long *>(g.tile_count + (size_t)tile * 64);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t wv[4] = {mw[q].x, mw[q].y, mw[q].z, mw[q].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t x = wv[j];
+        if (!x) continue;
+        cnt += __popc(x);
+        x = x - ((x >> 1) & 0x55555555u);
+        x = (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
+        x = (x + (x >> 4)) & 0x0F0F0F0Fu;   // four per-column counts, one per byte
+        if (tile != kOverflowSlot) {
+          const unsigned long long lo = (unsigned long long)(x & 0xFFu) | ((unsigned long long)((x >> 8) & 0xFFu) << 32);
+          const unsigned long long hi = (unsigned long long)((x >> 16) & 0xFFu) | ((unsigned long long)(x >> 24) << 32);
+          if (lo) atomicAdd(tc + (q * 4 + j) * 2, lo);
+          if (hi) atomicAdd(tc + (q * 4 + j) * 2 + 1, hi);
+        }
+      }
+    }
+    acc.swept += cnt; acc.surv += cnt;
+  }
+  sweep_publish(g, acc);
+}
+
+// Sweep, pass 2 — ONE WARP PER QUEUED LEAF: leaf-level frustum classification, exact per-voxel frustum tests, decay,
+// rewrite of accelerated mark times, clearing (reference .cpp:158-221).
+__global__ void __launch_bounds__(kSweepThreads, 4)
+sweep_leaf_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gmem, const int n_frustums, const double now,
+                  const SweepOutputs out)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevFrustum * fr = reinterpret_cast<DevFrustum *>(smem_raw);
@@ -341,46 +628,24 @@ sweep_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gmem, co
   __shared__ uint32_t s_mask[kSweepWarps][16];
   __shared__ uint32_t s_part[kSweepWarps][kMaxFrustums / 32];
   __shared__ uint32_t s_full[kSweepWarps][kMaxFrustums / 32];
-
-  // stage the frustum parameter blocks (planes / hourglass parameters) in shared memory
-  {
-    const int words = n_frustums * (int)(sizeof(DevFrustum) / 8);
-    const double * src = reinterpret_cast<const double *>(frustums_gmem);
-    double * dst = reinterpret_cast<double *>(fr);
-    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
-  }
-  __syncthreads();
+  const uint32_t n_queued = g.ctr->queue_n;
+  if (blockIdx.x * kSweepWarps >= n_queued) return;   // nothing for this CTA (uniform per block)
+  stage_frustums(fr, frustums_gmem, n_frustums);
 
   const unsigned lane = threadIdx.x & 31;
   const unsigned warp = threadIdx.x >> 5;
-  const uint32_t n_slots = g.ctr->high_water;
-  const uint32_t warps_total = gridDim.x * kSweepWarps;
   const int n_chunks = (n_frustums + 31) >> 5;
-
+  const bool skip_model_ok = !out.points;
+  const uint16_t * mask16 = reinterpret_cast<const uint16_t *>(g.leaf_mask);
   unsigned int c_swept = 0, c_surv = 0, c_clear = 0, c_rewr = 0, c_amb = 0;
   int bb_min_x = INT_MAX, bb_min_y = INT_MAX, bb_max_x = INT_MIN, bb_max_y = INT_MIN;
 
-  for (uint32_t slot = blockIdx.x * kSweepWarps + warp; slot < n_slots; slot += warps_total) {
+  for (uint32_t qi = blockIdx.x * kSweepWarps + warp; qi < n_queued; qi += gridDim.x * kSweepWarps) {
+    const uint32_t slot = g.sweep_queue[qi];
     const uint64_t key = g.leaf_key[slot];
-    if (key == kEmptyKey) continue;   // free slot
-    // each lane owns two voxel columns = 16 mask bits = local indices [lane*16, lane*16+16)
-    const uint32_t m16 = reinterpret_cast<const uint16_t *>(g.leaf_mask + (size_t)slot * 16)[lane];
-    if (__ballot_sync(kFull, m16 != 0) == 0) {
-      if (lane == 0) free_leaf(g, slot);   // nothing left in this leaf: pruneGrid, .cpp:223
-      continue;
-    }
-    // redistribute the active voxels evenly over the lanes: per-lane popcount, warp scan, index list in smem
-    const int cnt = __popc(m16);
-    int incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(kFull, incl, d); if ((int)lane >= d) incl += v; }
-    const int total = __shfl_sync(kFull, incl, 31);
-    {
-      int pos = incl - cnt;
-      uint32_t m = m16;
-      while (m) { const int b = __ffs(m) - 1; m &= m - 1; s_list[warp][pos++] = (uint16_t)(lane * 16 + b); }
-    }
-    if (lane < 16) s_mask[warp][lane] = g.leaf_mask[(size_t)slot * 16 + lane];
+    const uint32_t m16 = mask16[(size_t)slot * 32 + lane];   // each lane owns two voxel columns = local indices [lane*16, lane*16+16)
+    const uint32_t tile = g.leaf_tile[slot];
+    const double tmin = g.leaf_tmin[slot];
 
     int bx, by, bz;
     unpack_leaf_key(key, bx, by, bz);
@@ -393,9 +658,41 @@ sweep_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gmem, co
       if (lane == 0) { s_part[warp][c] = pm; s_full[warp][c] = fm; }
       any_cand |= pm | fm;
     }
+    // temporal culling: outside every frustum and too young to expire -> the 4 KB time block is never touched
+    if (!any_cand && skip_model_ok) {
+      if (!leaf_may_expire(g, now, tmin)) {
+        const unsigned cnt = __popc(m16);
+        c_swept += cnt; c_surv += cnt;
+        if (tile != kOverflowSlot) {
+          const unsigned long long c0 = __popc(m16 & 0xFFu), c1 = __popc(m16 >> 8);
+          if (c0 | c1) atomicAdd(reinterpret_cast<unsigned long long *>(g.tile_count + (size_t)tile * 64 + 2 * lane), c0 | (c1 << 32));
+        }
+        continue;
+      }
+    }
+    // redistribute the active voxels evenly over the lanes: per-lane popcount, warp scan, index list in smem
+    const int cnt = __popc(m16);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(kFull, incl, d); if ((int)lane >= d) incl += v; }
+    const int total = __shfl_sync(kFull, incl, 31);
+    {
+      int pos = incl - cnt;
+      uint32_t m = m16;
+      while (m) { const int b = __ffs(m) - 1; m &= m - 1; s_list[warp][pos++] = (uint16_t)(lane * 16 + b); }
+    }
+    // the 16 mask words of the leaf (lane j < 16 holds word j), assembled from the 16-bit halves by shuffles
+    uint32_t w_orig;
+    {
+      const uint32_t lo = __shfl_sync(kFull, m16, (2 * lane) & 31), hi = __shfl_sync(kFull, m16, (2 * lane + 1) & 31);
+      w_orig = lo | (hi << 16);
+    }
+    if (lane < 16) s_mask[warp][lane] = w_orig;
+
     __syncwarp();
 
     const double * tbase = g.leaf_time + (size_t)slot * kLeafVoxels;
+    double vmin = CUDART_INF;   // smallest mark time among this leaf's survivors
     for (int i0 = 0; i0 < total; i0 += 32) {
       const int i = i0 + (int)lane;
       const bool have = i < total;
@@ -441,9 +738,12 @@ sweep_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gmem, co
           else {
             const double nv = __dsub_rn(v, accel);
             if (__double_as_longlong(nv) != __double_as_longlong(v)) { g.leaf_time[(size_t)slot * kLeafVoxels + li] = nv; ++c_rewr; }
+            vmin = fmin(vmin, nv);
           }
         } else if (base_dur < 0.) {
           cleared = true;   // .cpp:203-211
+        } else {
+          vmin = fmin(vmin, v);
         }
         survived = !cleared;
         if (cleared) {
@@ -497,55 +797,28 @@ sweep_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gmem, co
     uint32_t w = 0;
     if (lane < 16) {
       w = s_mask[warp][lane];
-      if (w != g.leaf_mask[(size_t)slot * 16 + lane]) g.leaf_mask[(size_t)slot * 16 + lane] = w;
+      if (w != w_orig) g.leaf_mask[(size_t)slot * 16 + lane] = w;
     }
     const bool leaf_alive = __ballot_sync(kFull, w != 0) != 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) vmin = fmin(vmin, __shfl_xor_sync(kFull, vmin, d));
+    if (leaf_alive && lane == 0 && !(vmin == tmin)) g.leaf_tmin[slot] = vmin;   // exact lower bound again
     if (!leaf_alive) {
       if (lane == 0) free_leaf(g, slot);
-    } else {
-      const uint32_t tile = g.leaf_tile[slot];
-      if (tile != kOverflowSlot) {
-        const uint32_t two = reinterpret_cast<const uint16_t *>(s_mask[warp])[lane];
-        const int c0 = __popc(two & 0xFFu), c1 = __popc(two >> 8);
-        // PopulateCostmapAndPointcloud .cpp:242-250: _cost_map[(x,y)] += 1 per surviving voxel
-        if (c0) atomicAdd(&g.tile_count[(size_t)tile * 64 + 2 * lane], (uint32_t)c0);
-        if (c1) atomicAdd(&g.tile_count[(size_t)tile * 64 + 2 * lane + 1], (uint32_t)c1);
-      }
+    } else if (tile != kOverflowSlot) {
+      const uint32_t two = reinterpret_cast<const uint16_t *>(s_mask[warp])[lane];
+      const unsigned long long c0 = __popc(two & 0xFFu), c1 = __popc(two >> 8);
+      // PopulateCostmapAndPointcloud .cpp:242-250: _cost_map[(x,y)] += 1 per surviving voxel.  The two adjacent
+      // u32 column counters of this lane are bumped by ONE 64-bit reduction (no carry: counts stay < 2^32)
+      if (c0 | c1) atomicAdd(reinterpret_cast<unsigned long long *>(g.tile_count + (size_t)tile * 64 + 2 * lane), c0 | (c1 << 32));
     }
     __syncwarp();
-  }
+  }   // queued leaves
 
-  // block-level reduction of the statistics
-  __shared__ unsigned int s_red[5];
-  __shared__ int s_bb[4];
-  if (threadIdx.x == 0) { s_red[0] = s_red[1] = s_red[2] = s_red[3] = s_red[4] = 0; s_bb[0] = s_bb[1] = INT_MAX; s_bb[2] = s_bb[3] = INT_MIN; }
-  __syncthreads();
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    c_swept += __shfl_xor_sync(kFull, c_swept, d); c_surv += __shfl_xor_sync(kFull, c_surv, d);
-    c_clear += __shfl_xor_sync(kFull, c_clear, d); c_rewr += __shfl_xor_sync(kFull, c_rewr, d);
-    c_amb += __shfl_xor_sync(kFull, c_amb, d);
-    bb_min_x = min(bb_min_x, __shfl_xor_sync(kFull, bb_min_x, d)); bb_min_y = min(bb_min_y, __shfl_xor_sync(kFull, bb_min_y, d));
-    bb_max_x = max(bb_max_x, __shfl_xor_sync(kFull, bb_max_x, d)); bb_max_y = max(bb_max_y, __shfl_xor_sync(kFull, bb_max_y, d));
-  }
-  if (lane == 0) {
-    atomicAdd(&s_red[0], c_swept); atomicAdd(&s_red[1], c_surv); atomicAdd(&s_red[2], c_clear);
-    atomicAdd(&s_red[3], c_rewr); atomicAdd(&s_red[4], c_amb);
-    atomicMin(&s_bb[0], bb_min_x); atomicMin(&s_bb[1], bb_min_y); atomicMax(&s_bb[2], bb_max_x); atomicMax(&s_bb[3], bb_max_y);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    Counters * c = g.ctr;
-    if (s_red[0]) atomicAdd(&c->n_swept, (unsigned long long)s_red[0]);
-    if (s_red[1]) atomicAdd(&c->n_survived, (unsigned long long)s_red[1]);
-    if (s_red[2]) {
-      atomicAdd(&c->n_cleared, (unsigned long long)s_red[2]);
-      atomicMin(&c->cb_min_x, s_bb[0]); atomicMin(&c->cb_min_y, s_bb[1]);
-      atomicMax(&c->cb_max_x, s_bb[2]); atomicMax(&c->cb_max_y, s_bb[3]);
-    }
-    if (s_red[3]) atomicAdd(&c->n_rewritten, (unsigned long long)s_red[3]);
-    if (s_red[4]) atomicAdd(&c->n_ambiguous, (unsigned long long)s_red[4]);
-  }
+  SweepAcc acc;
+  acc.swept = c_swept; acc.surv = c_surv; acc.clear = c_clear; acc.rewr = c_rewr; acc.amb = c_amb;
+  acc.min_x = bb_min_x; acc.min_y = bb_min_y; acc.max_x = bb_max_x; acc.max_y = bb_max_y;
+  sweep_publish(g, acc);
 }
 
 // zero the column tiles and the per-sweep counters before a sweep
@@ -556,9 +829,11 @@ __global__ void __launch_bounds__(256) sweep_prologue_kernel(const GridView g)
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words / 4; i += gridDim.x * blockDim.x) t4[i] = make_uint4(0, 0, 0, 0);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     Counters * c = g.ctr;
+    fold_alloc(g);
     c->n_swept = c->n_survived = c->n_cleared = c->n_rewritten = c->n_ambiguous = 0;
     c->cb_min_x = c->cb_min_y = INT_MAX; c->cb_max_x = c->cb_max_y = INT_MIN;
     c->n_points_out = c->n_cleared_out = c->n_ambiguous_out = 0;
+    c->queue_n = 0;
   }
 }
 
@@ -582,9 +857,18 @@ __device__ __forceinline__ void costmap_reduce_and_publish(Counters * c, unsigne
     mnx = min(mnx, __shfl_xor_sync(kFull, mnx, d)); mny = min(mny, __shfl_xor_sync(kFull, mny, d));
     mxx = max(mxx, __shfl_xor_sync(kFull, mxx, d)); mxy = max(mxy, __shfl_xor_sync(kFull, mxy, d));
   }
+  __shared__ unsigned int s_n;
+  __shared__ int s_b[4];
+  if (threadIdx.x == 0) { s_n = 0; s_b[0] = s_b[1] = INT_MAX; s_b[2] = s_b[3] = INT_MIN; }
+  __syncthreads();
   if ((threadIdx.x & 31) == 0 && n) {
-    atomicAdd(&c->n_marked, (unsigned long long)n);
-    atomicMin(&c->mk_min_x, mnx); atomicMin(&c->mk_min_y, mny); atomicMax(&c->mk_max_x, mxx); atomicMax(&c->mk_max_y, mxy);
+    atomicAdd(&s_n, n);
+    atomicMin(&s_b[0], mnx); atomicMin(&s_b[1], mny); atomicMax(&s_b[2], mxx); atomicMax(&s_b[3], mxy);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_n) {
+    atomicAdd(&c->n_marked, (unsigned long long)s_n);
+    atomicMin(&c->mk_min_x, s_b[0]); atomicMin(&c->mk_min_y, s_b[1]); atomicMax(&c->mk_max_x, s_b[2]); atomicMax(&c->mk_max_y, s_b[3]);
   }
 }
 
@@ -772,8 +1056,8 @@ __global__ void __launch_bounds__(256) rebuild_hash_kernel(const GridView g)
     if (key == kEmptyKey) continue;
     uint32_t h = (uint32_t)mix64(key) & g.hash_mask;
     for (;;) {
-      const uint64_t old = atomicCAS((unsigned long long *)&g.hash_keys[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
-      if (old == kEmptyKey) { g.hash_vals[h] = slot; g.leaf_hpos[slot] = h; break; }
+      const uint64_t old = atomicCAS(&g.hash[h].key, (unsigned long long)kEmptyKey, (unsigned long long)key);
+      if (old == kEmptyKey) { g.hash[h].val = slot; g.leaf_hpos[slot] = h; break; }
       h = (h + 1) & g.hash_mask;
     }
   }
@@ -804,10 +1088,25 @@ static inline int grid_for(unsigned long long work_items, int per_block, int max
   return (int)b;
 }
 
-cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, cudaStream_t s)
+cudaError_t launch_fold_alloc(const GridView & g, cudaStream_t s)
+{
+  fold_alloc_kernel<<<1, 1, 0, s>>>(g);
+  return cudaGetLastError();
+}
+cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s)
 {
   if (batch.total_blocks == 0) return cudaSuccess;
-  mark_kernel<<<batch.total_blocks, kMarkThreads, 0, s>>>(g, batch);
+  // persistent CTAs, as many as are resident at once: each loops over chunks with the next chunk's loads in flight
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mark_kernel, kMarkThreads, 0) != cudaSuccess || n < 1) n = 4;
+    per_sm = n;
+  }
+  const uint32_t resident = (uint32_t)sm_count * (uint32_t)per_sm;
+  const uint32_t chunks_per_cta = (batch.total_blocks + resident - 1) / resident;
+  const uint32_t grid = (batch.total_blocks + chunks_per_cta - 1) / chunks_per_cta;
+  mark_kernel<<<grid, kMarkThreads, 0, s>>>(g, batch, chunks_per_cta);
   return cudaGetLastError();
 }
 uint32_t mark_blocks_for(unsigned long long n_points)
@@ -828,12 +1127,19 @@ cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, in
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const size_t dyn = (size_t)n_frustums * sizeof(DevFrustum);
-  if (dyn > 48 * 1024) {
-    e = cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (dyn > 32 * 1024) {
+    e = cudaFuncSetAttribute(sweep_triage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(sweep_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
   }
-  const int blocks = grid_for(leaf_slots_upper_bound, kSweepWarps, sm_count * 8);
-  sweep_kernel<<<blocks, kSweepThreads, dyn, s>>>(g, frustums_dev, n_frustums, now, out);
+  // pass 1: one thread per leaf slot.  pub_voxels needs every survivor's coordinates: everything takes pass 2 then.
+  const int force_full = out.points ? 1 : 0;
+  sweep_triage_kernel<<<grid_for(leaf_slots_upper_bound, kSweepThreads, sm_count * 8), kSweepThreads, dyn, s>>>(g, frustums_dev, n_frustums, now, force_full);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  // pass 2: one warp per queued leaf; the queue length is only known on the device, CTAs without work exit at once
+  sweep_leaf_kernel<<<grid_for(leaf_slots_upper_bound, kSweepWarps, sm_count * 4), kSweepThreads, dyn, s>>>(g, frustums_dev, n_frustums, now, out);
   return cudaGetLastError();
 }
 cudaError_t launch_costmap(const GridView & g, const CostmapDev & p, uint8_t * costmap_dev, uint32_t tiles_upper_bound, int sm_count, cudaStream_t s)

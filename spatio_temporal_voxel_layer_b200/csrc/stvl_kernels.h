@@ -24,7 +24,8 @@ struct CostmapDev {
   uint8_t default_value, lethal;
 };
 
-cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, cudaStream_t s);
+cudaError_t launch_fold_alloc(const GridView & g, cudaStream_t s);
+cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s);
 uint32_t mark_blocks_for(unsigned long long n_points);
 cudaError_t launch_load_voxels(const GridView & g, const int32_t * x, const int32_t * y, const int32_t * z, const double * t,
                                unsigned long long n, cudaStream_t s);
