@@ -1,0 +1,6 @@
+#ifndef STVL_SHIM_GEOMETRY_MSGS_QUATERNION_HPP_
+#define STVL_SHIM_GEOMETRY_MSGS_QUATERNION_HPP_
+namespace geometry_msgs { namespace msg {
+struct Quaternion { double x = 0, y = 0, z = 0, w = 1; };
+} }
+#endif
