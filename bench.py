@@ -221,10 +221,9 @@ def bench_ours(args):
 
     # dense column-count window for the multi-GPU merge (voxel-column index space)
     if world > 1:
-        ix0 = int(math.floor(cp["origin_x"] / vs)) - 2
-        iy0 = int(math.floor(cp["origin_y"] / vs)) - 2
-        nx = int(math.ceil(cp["size_x"] * cp["resolution"] / vs)) + 4
-        ny = int(math.ceil(cp["size_y"] * cp["resolution"] / vs)) + 4
+        from spatio_temporal_voxel_layer_b200 import sharding
+        ix0, iy0, nx, ny = sharding.dense_window(cp["origin_x"], cp["origin_y"], cp["resolution"], cp["size_x"], cp["size_y"],
+                                                 w.voxel_size)
         dense = torch.zeros((ny, nx), dtype=torch.int32, device="cuda")
 
     # per ring slot: the C-ABI argument arrays are built once; a step only refreshes the clock samples
@@ -259,7 +258,7 @@ def bench_ours(args):
         dense.zero_()
         torch.cuda.current_stream().synchronize()
         g.columns_to_dense(ix0, iy0, nx, ny, dense.data_ptr())
-        dist.reduce(dense, dst=0, op=dist.ReduceOp.SUM)
+        sharding.merge_counts(dist, dense, dst=0)
         torch.cuda.current_stream().synchronize()
         if rank == 0:
             return g.costmap_from_dense(dense.data_ptr(), ix0, iy0, nx, ny, params, costmap_dev.data_ptr())
