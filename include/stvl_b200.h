@@ -227,9 +227,10 @@ double stvl_voxel_size(const stvl_grid_t * g);
 /* ---- multi-GPU merge of the column counts ---------------- */
 /* Scatter-add the last sweep's column counts into a dense DEVICE grid of nx*ny uint32 covering voxel
  * columns [ix0, ix0+nx) x [iy0, iy0+ny) (row-major, y slow).  The caller zeroes / reduces the grid
- * (ncclReduce over NVLink) between ranks. */
+ * (ncclReduce over NVLink) between ranks.  Asynchronous on the handle's stream (stvl_get_stream): enqueue the
+ * collective in stream order after it. */
 int stvl_columns_to_dense(stvl_grid_t * g, int32_t ix0, int32_t iy0, uint32_t nx, uint32_t ny, uint32_t * dense_dev);
-/* Threshold a (reduced) dense column-count grid into costmap bytes, same rule as stvl_costmap. */
+/* Threshold a (reduced) dense column-count grid into costmap bytes, same rule as stvl_costmap.  res == NULL: enqueue only. */
 int stvl_costmap_from_dense(stvl_grid_t * g, const uint32_t * dense_dev, int32_t ix0, int32_t iy0, uint32_t nx, uint32_t ny,
                             const stvl_costmap_params_t * p, uint8_t * costmap_dev, stvl_costmap_result_t * res);
 

@@ -382,8 +382,8 @@ class SpatioTemporalVoxelGrid:
     def columns_to_dense(self, ix0, iy0, nx, ny, dense_dev_ptr):
         _check(self.L.stvl_columns_to_dense(self.h, ix0, iy0, nx, ny, dense_dev_ptr))
 
-    def costmap_from_dense(self, dense_dev_ptr, ix0, iy0, nx, ny, params, costmap_dev_ptr):
-        res = CostmapResult()
+    def costmap_from_dense(self, dense_dev_ptr, ix0, iy0, nx, ny, params, costmap_dev_ptr, sync=True):
+        res = CostmapResult() if sync else None
         _check(self.L.stvl_costmap_from_dense(self.h, dense_dev_ptr, ix0, iy0, nx, ny, C.byref(params),
-                                              costmap_dev_ptr, C.byref(res)))
+                                              costmap_dev_ptr, C.byref(res) if sync else None))
         return res

@@ -989,8 +989,7 @@ int stvl_columns_to_dense(stvl_grid_t * g, int32_t ix0, int32_t iy0, uint32_t nx
   if (!dense_dev) return fail(STVL_ERR_INVALID, "dense_dev is NULL");
   CU(launch_columns_to_dense(g->v, ix0, iy0, nx, ny, dense_dev, tiles_upper(g), g->sm_count, g->stream));
   g->launches += 1;
-  CU(cudaStreamSynchronize(g->stream));
-  return STVL_OK;
+  return STVL_OK;   // asynchronous on the handle's stream (stvl_get_stream): order the collective after it
 }
 
 int stvl_costmap_from_dense(stvl_grid_t * g, const uint32_t * dense_dev, int32_t ix0, int32_t iy0, uint32_t nx, uint32_t ny,
@@ -1000,6 +999,8 @@ int stvl_costmap_from_dense(stvl_grid_t * g, const uint32_t * dense_dev, int32_t
   if (!dense_dev || !p || !costmap_dev) return fail(STVL_ERR_INVALID, "NULL argument");
   CU(launch_costmap_from_dense(g->v, dense_dev, ix0, iy0, nx, ny, to_dev(*p), costmap_dev, g->sm_count, g->stream));
   g->launches += 2;
+  g->counters_fresh = false;
+  if (!res) return STVL_OK;   // fully asynchronous
   int rc = fetch_counters(g);
   if (rc != STVL_OK) return rc;
   fill_costmap_result(g, res);

@@ -9,6 +9,7 @@
 // Everything is integer / FP64 scalar work bound by HBM traffic: no tensor cores.  All
 // arithmetic whose result feeds a comparison or a stored value uses the _rn intrinsics
 // (never contracted into FMA) in the reference's operation order, see SURVEY.md §7.
+#include <cuda_pipeline.h>
 #include <math_constants.h>
 
 #include "stvl_device.cuh"
@@ -140,11 +141,12 @@ __global__ void fold_alloc_kernel(const GridView g) { fold_alloc(g); }
 // =====================================================================================
 struct PointXYZ { float x, y, z; bool ok; };
 
+template <bool kVec4>
 __device__ __forceinline__ PointXYZ load_point(const DevReading & r, unsigned long long i)
 {
   PointXYZ p;
   if (i >= r.n_points) { p.x = p.y = p.z = 0.f; p.ok = false; return p; }
-  if (r.vec4) {
+  if (kVec4 || r.vec4) {
     // coalesced 128-bit streaming load: the cloud is read exactly once
     const float4 v = __ldcs(reinterpret_cast<const float4 *>(r.data) + i);
     p.x = v.x; p.y = v.y; p.z = v.z;
@@ -174,6 +176,7 @@ constexpr int kMarkPointsPerThread = 4;
 constexpr int kMarkPointsPerBlock = kMarkThreads * kMarkPointsPerThread;
 constexpr int kMarkTable = 64;        // block-local leaf table (shared memory)
 constexpr int kMarkProbes = 8;
+constexpr size_t kMarkStageBytes = 2 * (size_t)kMarkPointsPerBlock * 16;   // two cp.async stages of one chunk each
 
 // write one voxel straight to the global store (fallback when the block-local table is full)
 __device__ __forceinline__ void mark_voxel_direct(const GridView & g, uint64_t key, unsigned l, double now, unsigned long long now_bits,
@@ -226,7 +229,8 @@ __device__ __forceinline__ int mark_reading_of(const MarkBatch & batch, uint32_t
   return ri;
 }
 
-__global__ void __launch_bounds__(kMarkThreads, 4)
+template <bool kVec4>   // kVec4: every reading of the batch is a packed x,y,z,pad float4 cloud (the RGBD / depth-image layout)
+__global__ void __launch_bounds__(kMarkThreads, kVec4 ? 5 : 4)
 mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uint32_t chunks_per_cta)
 {
   __shared__ unsigned long long s_key[kMarkTable];
@@ -266,28 +270,56 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
   for (int q = 1; q < (int)batch.n_readings; ++q) if (chunk_begin >= s_r[q].first_block) ri = q;
   if (threadIdx.x == 0) mark_params_from(s_par, s_r[ri]);
 
-  PointXYZ nxt[kMarkPointsPerThread];
-  {
-    const DevReading & r0 = s_r[ri];
-    const unsigned long long base = (unsigned long long)(chunk_begin - r0.first_block) * kMarkPointsPerBlock;
+  // Cloud staging.  Packed float4 clouds (kVec4) are streamed global -> shared memory with cp.async (LDGSTS), two
+  // 16 KB stages per CTA: the next chunk is in flight while the current one is processed and the copies hold no
+  // registers, which buys a fifth resident CTA per SM.  Other PointCloud2 layouts prefetch through registers.
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  float4 * s_stage = reinterpret_cast<float4 *>(s_dyn);   // [2][kMarkPointsPerBlock] when kVec4
+  PointXYZ nxt[kVec4 ? 1 : kMarkPointsPerThread];
+  auto prefetch = [&](const DevReading & rd, uint32_t chunk_id, int stage) {
+    const unsigned long long base = (unsigned long long)(chunk_id - rd.first_block) * kMarkPointsPerBlock;
+    if constexpr (kVec4) {
 #pragma unroll
-    for (int k = 0; k < kMarkPointsPerThread; ++k) nxt[k] = load_point(r0, base + (unsigned long long)k * kMarkThreads + threadIdx.x);
-  }
+      for (int k = 0; k < kMarkPointsPerThread; ++k) {
+        const unsigned long long i = base + (unsigned long long)k * kMarkThreads + threadIdx.x;
+        if (i < rd.n_points)
+          __pipeline_memcpy_async(&s_stage[stage * kMarkPointsPerBlock + k * kMarkThreads + threadIdx.x],
+                                  reinterpret_cast<const float4 *>(rd.data) + i, 16);
+      }
+      __pipeline_commit();
+    } else {
+#pragma unroll
+      for (int k = 0; k < kMarkPointsPerThread; ++k) nxt[k] = load_point<false>(rd, base + (unsigned long long)k * kMarkThreads + threadIdx.x);
+    }
+  };
+  prefetch(s_r[ri], chunk_begin, 0);
   __syncthreads();
 
   for (uint32_t chunk = chunk_begin; chunk < chunk_end; ++chunk) {
+    const int stage = (int)((chunk - chunk_begin) & 1u);
     PointXYZ pts[kMarkPointsPerThread];
+    if constexpr (!kVec4) {
 #pragma unroll
-    for (int k = 0; k < kMarkPointsPerThread; ++k) pts[k] = nxt[k];
+      for (int k = 0; k < kMarkPointsPerThread; ++k) pts[k] = nxt[k];
+    }
     // prefetch the next chunk of this CTA (it may already belong to the next reading)
     const bool last = chunk + 1 == chunk_end;
     int ri_next = ri;
     if (!last) {
       if (ri + 1 < (int)batch.n_readings && chunk + 1 >= s_r[ri + 1].first_block) ri_next = ri + 1;
-      const DevReading & rn = s_r[ri_next];
-      const unsigned long long base = (unsigned long long)(chunk + 1 - rn.first_block) * kMarkPointsPerBlock;
+      prefetch(s_r[ri_next], chunk + 1, stage ^ 1);
+    }
+    if constexpr (kVec4) {
+      // every thread only reads what it copied itself: waiting for its own cp.async group is enough
+      if (last) __pipeline_wait_prior(0); else __pipeline_wait_prior(1);
+      const unsigned long long base = (unsigned long long)(chunk - s_r[ri].first_block) * kMarkPointsPerBlock;
+      const unsigned long long n_pts = s_r[ri].n_points;
 #pragma unroll
-      for (int k = 0; k < kMarkPointsPerThread; ++k) nxt[k] = load_point(rn, base + (unsigned long long)k * kMarkThreads + threadIdx.x);
+      for (int k = 0; k < kMarkPointsPerThread; ++k) {
+        const float4 v = s_stage[stage * kMarkPointsPerBlock + k * kMarkThreads + threadIdx.x];
+        pts[k].x = v.x; pts[k].y = v.y; pts[k].z = v.z;
+        pts[k].ok = base + (unsigned long long)k * kMarkThreads + threadIdx.x < n_pts;
+      }
     }
 
     // ---- cheap rejection first (branch-free): depth images are full of invalid pixels and floor / ceiling returns
@@ -561,14 +593,15 @@ sweep_triage_kernel(const GridView g, const DevFrustum * __restrict__ frustums_g
   const uint32_t n_slots = g.ctr->high_water;
   SweepAcc acc;
   for (uint32_t slot = blockIdx.x * kSweepThreads + threadIdx.x; slot < n_slots; slot += gridDim.x * kSweepThreads) {
+    // all loads of the leaf are independent of each other: one DRAM round trip per leaf
     const uint64_t key = g.leaf_key[slot];
-    if (key == kEmptyKey) continue;   // free slot
     const double tmin = g.leaf_tmin[slot];
     const uint32_t tile = g.leaf_tile[slot];
     const uint4 * mp = reinterpret_cast<const uint4 *>(g.leaf_mask + (size_t)slot * 16);
     uint4 mw[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) mw[q] = mp[q];
+    if (key == kEmptyKey) continue;   // free slot
     uint32_t any = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) any |= mw[q].x | mw[q].y | mw[q].z | mw[q].w;
@@ -581,7 +614,9 @@ sweep_triage_kernel(const GridView g, const DevFrustum * __restrict__ frustums_g
       for (int f = 0; f < n_frustums && !full_path; ++f) {
         const DevFrustum & F = fr[f];
         if (F.type < 0) continue;
-        full_path = !F.cull || !(x0 + 7 < F.lo[0] || x0 > F.hi[0] || y0 + 7 < F.lo[1] || y0 > F.hi[1] || z0 + 7 < F.lo[2] || z0 > F.hi[2]);
+        if (F.cull && (x0 + 7 < F.lo[0] || x0 > F.hi[0] || y0 + 7 < F.lo[1] || y0 > F.hi[1] || z0 + 7 < F.lo[2] || z0 > F.hi[2])) continue;
+        // inside the frustum's bounding box: bounding sphere of the leaf against the plane set / hourglass
+        full_path = classify_leaf(F, bx, by, bz, g.vs, g.half_vs) != 0;
       }
     }
     if (full_path) {
@@ -628,6 +663,7 @@ sweep_leaf_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gme
   __shared__ uint32_t s_mask[kSweepWarps][16];
   __shared__ uint32_t s_part[kSweepWarps][kMaxFrustums / 32];
   __shared__ uint32_t s_full[kSweepWarps][kMaxFrustums / 32];
+  __shared__ double s_val[kSweepWarps][128];
   const uint32_t n_queued = g.ctr->queue_n;
   if (blockIdx.x * kSweepWarps >= n_queued) return;   // nothing for this CTA (uniform per block)
   stage_frustums(fr, frustums_gmem, n_frustums);
@@ -694,6 +730,18 @@ sweep_leaf_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gme
     const double * tbase = g.leaf_time + (size_t)slot * kLeafVoxels;
     double vmin = CUDART_INF;   // smallest mark time among this leaf's survivors
     for (int i0 = 0; i0 < total; i0 += 32) {
+      // the mark times of up to four 32-voxel batches are requested together (one DRAM round trip per 128 voxels)
+      if ((i0 & 127) == 0) {
+        double pv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = i0 + u * 32 + (int)lane;
+          pv[u] = j < total ? __ldcs(tbase + s_list[warp][j]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s_val[warp][u * 32 + lane] = pv[u];
+        __syncwarp();
+      }
       const int i = i0 + (int)lane;
       const bool have = i < total;
       bool cleared = false, survived = false;
@@ -701,7 +749,7 @@ sweep_leaf_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gme
       unsigned li = 0;
       if (have) {
         li = s_list[warp][i];
-        const double v = __ldcs(tbase + li);
+        const double v = s_val[warp][(i0 & 127) + lane];
         ix = bx * 8 + (int)(li >> 6); iy = by * 8 + (int)((li >> 3) & 7); iz = bz * 8 + (int)(li & 7);
         ++c_swept;
         // .cpp:167-169
@@ -1096,17 +1144,23 @@ cudaError_t launch_fold_alloc(const GridView & g, cudaStream_t s)
 cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s)
 {
   if (batch.total_blocks == 0) return cudaSuccess;
+  bool all_vec4 = true;
+  for (uint32_t i = 0; i < batch.n_readings; ++i) all_vec4 = all_vec4 && batch.r[i].vec4 != 0;
   // persistent CTAs, as many as are resident at once: each loops over chunks with the next chunk's loads in flight
-  static int per_sm = 0;
-  if (per_sm == 0) {
+  static int per_sm[2] = {0, 0};
+  int & occ = per_sm[all_vec4 ? 1 : 0];
+  if (occ == 0) {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mark_kernel, kMarkThreads, 0) != cudaSuccess || n < 1) n = 4;
-    per_sm = n;
+    if (all_vec4) cudaFuncSetAttribute(mark_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMarkStageBytes);
+    const cudaError_t e = all_vec4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mark_kernel<true>, kMarkThreads, kMarkStageBytes)
+                                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mark_kernel<false>, kMarkThreads, 0);
+    occ = (e == cudaSuccess && n >= 1) ? n : 4;
   }
-  const uint32_t resident = (uint32_t)sm_count * (uint32_t)per_sm;
+  const uint32_t resident = (uint32_t)sm_count * (uint32_t)occ;
   const uint32_t chunks_per_cta = (batch.total_blocks + resident - 1) / resident;
   const uint32_t grid = (batch.total_blocks + chunks_per_cta - 1) / chunks_per_cta;
-  mark_kernel<<<grid, kMarkThreads, 0, s>>>(g, batch, chunks_per_cta);
+  if (all_vec4) mark_kernel<true><<<grid, kMarkThreads, kMarkStageBytes, s>>>(g, batch, chunks_per_cta);
+  else mark_kernel<false><<<grid, kMarkThreads, 0, s>>>(g, batch, chunks_per_cta);
   return cudaGetLastError();
 }
 uint32_t mark_blocks_for(unsigned long long n_points)

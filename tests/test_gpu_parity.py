@@ -383,6 +383,7 @@ def test_sharded_grids_union_equals_single(stvl, oracle):
         total_active += g.active_count()
         g.ClearFrustums([], now)
         g.columns_to_dense(ix0, iy0, nx, ny, dense.data_ptr())
+        g.synchronize()      # the scatter is asynchronous on the handle's stream
         shards.append(g)
     assert total_active == len(vox)
     cm = torch.zeros((size, size), dtype=torch.uint8, device="cuda")
