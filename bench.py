@@ -264,26 +264,24 @@ def bench_ours(args):
                 return g.costmap_from_dense(dense.data_ptr(), ix0, iy0, nx, ny, params, costmap_dev.data_ptr(), sync=sync_result)
         return None
 
-    stage_ev = []   # (clear_start, mark_start, costmap_start, end) per timed step of the value leg
 
     params_ref = C.byref(params)
     cm_dev_ptr, cm_host_ptr = costmap_dev.data_ptr(), costmap_host.data_ptr()
-    ev_pool = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)] if world == 1 else []
 
     def step_device(step, timed):
-        evs = ev_pool[len(stage_ev)] if (timed and world == 1 and not args.no_stage_events) else None
-        if evs: evs[0].record(stream)
-        arr = enqueue_clear_mark(step, True)
-        if evs: evs[1].record(stream)
-        check(L.stvl_mark_device(h, arr, n_cams))
-        if evs: evs[2].record(stream)
+        """One cycle with device-resident clouds.  N=1: ONE C-ABI call (stvl_update_cycle_device) enqueues clear -> mark ->
+        costmap; nothing synchronises.  The library itself brackets the Mark kernel with CUDA events (stvl_enable_timing)."""
         if world == 1:
-            check(L.stvl_costmap_device(h, params_ref, cm_dev_ptr, None))
+            slot = step % ring
+            now = w.now0 + w.dt * (step + 1)
+            arr = args_dev[slot]
+            for k in range(n_cams):
+                arr[k].now = now + 1e-4 * k
+            check(L.stvl_update_cycle_device(h, now, fr_ptrs[slot], n_cams, arr, n_cams, params_ref, cm_dev_ptr))
         else:
+            arr = enqueue_clear_mark(step, True)
+            check(L.stvl_mark_device(h, arr, n_cams))
             merge_and_write(False)
-        if evs:
-            evs[3].record(stream)
-            stage_ev.append(evs)
 
     def step_host(step):
         arr = enqueue_clear_mark(step, False)
@@ -313,6 +311,8 @@ def bench_ours(args):
         step_device(step_no, False); step_no += 1
     barrier()
     launches0 = g.pool_stats().kernel_launches
+    g.enable_timing(stvl.TIME_MARK)      # the dominant kernel is event-timed inside the timed region
+    g.timing()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -327,7 +327,14 @@ def bench_ours(args):
     t_wall = time.perf_counter() - t_wall0
     dev_ms = e0.elapsed_time(e1)   # every rank's work (incl. the NCCL reduce) is ordered on the library's stream
     clocks = sampler.stop() if rank == 0 else None
+    t_mark = g.timing()
     launches = g.pool_stats().kernel_launches - launches0
+    # stage breakdown: the same K cycles once more with every stage bracketed (not part of `value`)
+    g.enable_timing(stvl.TIME_SWEEP | stvl.TIME_MARK | stvl.TIME_COSTMAP)
+    for _ in range(args.steps):
+        step_device(step_no, False); step_no += 1
+    t_all = g.timing()
+    g.enable_timing(0)
     st = g.sweep_stats()
     active = g.active_count()
 
@@ -365,21 +372,27 @@ def bench_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        if world == 1 and stage_ev:
-            clear_ms = [a[0].elapsed_time(a[1]) for a in stage_ev]
-            mark_ms = [a[1].elapsed_time(a[2]) for a in stage_ev]
-            cost_ms = [a[2].elapsed_time(a[3]) for a in stage_ev]
-            mark_s = statistics.mean(mark_ms) / 1e3
-            clear_s = statistics.mean(clear_ms) / 1e3
+        if t_mark.n_mark:
+            mark_s = t_mark.mark_ms / t_mark.n_mark / 1e3
             algo_mark = w.points_per_cycle * 16          # 16 B read per input point
             algo_clear = st.n_swept * 16                 # 16 B per active voxel (key + time)
+            traffic = None
+            try:
+                with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                    traffic = json.load(f).get("mark_kernel_dram_bytes_per_launch")
+            except Exception:
+                pass
             line["roofline"] = {"bound": "hbm", "kernel": "mark_kernel", "achieved": algo_mark / mark_s / 1e9, "peak": peak,
-                                "unit": "GB/s", "frac": algo_mark / mark_s / 1e9 / peak, "traffic": None,
+                                "unit": "GB/s", "frac": algo_mark / mark_s / 1e9 / peak, "traffic": traffic,
                                 "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_mark,
-                                "stage_ms": {"clear": statistics.mean(clear_ms), "mark": statistics.mean(mark_ms),
-                                             "costmap": statistics.mean(cost_ms)},
-                                "sweep_kernel": {"achieved": algo_clear / clear_s / 1e9, "frac": algo_clear / clear_s / 1e9 / peak,
-                                                 "algorithmic_bytes_per_launch": int(algo_clear)}}
+                                "kernel_ms": t_mark.mark_ms / t_mark.n_mark, "launches_timed": int(t_mark.n_mark)}
+            if t_all.n_sweep and t_all.n_costmap and t_all.n_mark:
+                sweep_s = t_all.sweep_ms / t_all.n_sweep / 1e3
+                line["roofline"]["stage_ms"] = {"clear": t_all.sweep_ms / t_all.n_sweep, "mark": t_all.mark_ms / t_all.n_mark,
+                                                "costmap": t_all.costmap_ms / t_all.n_costmap,
+                                                "note": "separate pass of the same cycles with every stage bracketed by CUDA events inside the library"}
+                line["roofline"]["sweep_kernels"] = {"achieved": algo_clear / sweep_s / 1e9, "frac": algo_clear / sweep_s / 1e9 / peak,
+                                                     "algorithmic_bytes_per_launch": int(algo_clear)}
         # cpu baseline: bounded sample of the same cycles on the host (rank 0, N=1 only)
         if world == 1 and not args.no_cpu_baseline:
             wb = w
@@ -402,7 +415,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-cycles", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-stage-events", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

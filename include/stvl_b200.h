@@ -190,6 +190,12 @@ int stvl_costmap(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_t * cos
  * (no synchronisation); results are then available after stvl_synchronize / any synchronising call. */
 int stvl_costmap_device(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_t * costmap_dev, stvl_costmap_result_t * res);
 
+/* One whole update cycle with device-resident inputs, in the reference's order (stvl/src/spatio_temporal_voxel_layer.cpp:
+ * 772-795): stvl_clear_frustums, stvl_mark_device, stvl_costmap_device(res = NULL).  Enqueue only, no synchronisation. */
+int stvl_update_cycle_device(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
+                             const stvl_reading_t * readings, uint32_t n_readings,
+                             const stvl_costmap_params_t * p, uint8_t * costmap_dev);
+
 /* ---- results of the last sweep ------------------------------------------ */
 /* Which optional per-sweep lists the sweep kernel builds (default: STVL_OUT_CLEARED | STVL_OUT_AMBIGUOUS;
  * the occupancy point list follows cfg.pub_voxels).  Counts and the cleared bounding box are always produced. */
@@ -242,6 +248,15 @@ typedef struct stvl_pool_stats {
   uint64_t device_bytes;    /* device memory held */
 } stvl_pool_stats_t;
 int stvl_get_pool_stats(stvl_grid_t * g, stvl_pool_stats_t * out);
+/* Per-stage device timing: when enabled, the library brackets the selected stages' kernels with CUDA events on its
+ * stream.  stvl_get_timing synchronises, adds up the finished intervals since the last call and resets. */
+enum { STVL_TIME_SWEEP = 1, STVL_TIME_MARK = 2, STVL_TIME_COSTMAP = 4 };
+typedef struct stvl_timing {
+  double sweep_ms, mark_ms, costmap_ms;       /* summed kernel time per stage */
+  uint64_t n_sweep, n_mark, n_costmap;        /* intervals summed */
+} stvl_timing_t;
+int stvl_enable_timing(stvl_grid_t * g, uint32_t stage_mask);
+int stvl_get_timing(stvl_grid_t * g, stvl_timing_t * out);
 /* raw CUDA stream (cudaStream_t) the handle launches on — for CUDA-event timing by the caller */
 int stvl_get_stream(stvl_grid_t * g, void ** stream);
 /* block until all queued work of the handle is done */

@@ -24,6 +24,7 @@ DECAY_LINEAR, DECAY_EXPONENTIAL, DECAY_PERSISTENT = 0, 1, 2
 MODEL_DEPTH_CAMERA, MODEL_3D_LIDAR = 0, 1
 FILTER_NONE, FILTER_VOXEL, FILTER_PASSTHROUGH = 0, 1, 2
 OUT_CLEARED, OUT_AMBIGUOUS = 1, 2
+TIME_SWEEP, TIME_MARK, TIME_COSTMAP = 1, 2, 4
 LETHAL_OBSTACLE, NO_INFORMATION, FREE_SPACE = 254, 255, 0
 
 FRUSTUM_DTYPE = np.dtype([("type", "<i4"), ("reserved", "<i4"), ("accel_factor", "<f8"), ("p", "<f8", (36,))])
@@ -68,6 +69,11 @@ class CostmapResult(C.Structure):
                 ("touched", C.c_double * 4)]
 
 
+class Timing(C.Structure):
+    _fields_ = [("sweep_ms", C.c_double), ("mark_ms", C.c_double), ("costmap_ms", C.c_double),
+                ("n_sweep", C.c_uint64), ("n_mark", C.c_uint64), ("n_costmap", C.c_uint64)]
+
+
 class PoolStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "leaf_capacity", "leaves_in_use", "leaves_free", "hash_capacity", "hash_tombstones", "tiles_in_use",
@@ -82,6 +88,7 @@ EXPORTED_SYMBOLS = [
     "stvl_get_cleared", "stvl_get_points", "stvl_get_ambiguous", "stvl_reset", "stvl_reset_area", "stvl_active_count",
     "stvl_get_voxels", "stvl_load_voxels", "stvl_index_to_world", "stvl_voxel_size", "stvl_columns_to_dense",
     "stvl_costmap_from_dense", "stvl_get_pool_stats", "stvl_get_stream", "stvl_synchronize",
+    "stvl_update_cycle_device", "stvl_enable_timing", "stvl_get_timing",
 ]
 
 _lib = None
@@ -136,6 +143,9 @@ def load_library(build_if_missing=True):
     L.stvl_get_pool_stats.argtypes = [vp, C.POINTER(PoolStats)]
     L.stvl_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.stvl_synchronize.argtypes = [vp]
+    L.stvl_update_cycle_device.argtypes = [vp, d, vp, u32, C.POINTER(Reading), u32, C.POINTER(CostmapParams), vp]
+    L.stvl_enable_timing.argtypes = [vp, u32]
+    L.stvl_get_timing.argtypes = [vp, C.POINTER(Timing)]
     _lib = L
     return L
 
@@ -372,6 +382,14 @@ class SpatioTemporalVoxelGrid:
 
     def synchronize(self):
         _check(self.L.stvl_synchronize(self.h))
+
+    def enable_timing(self, mask):
+        _check(self.L.stvl_enable_timing(self.h, mask))
+
+    def timing(self):
+        t = Timing()
+        _check(self.L.stvl_get_timing(self.h, C.byref(t)))
+        return t
 
     # ---- device-resident variants (bench `value`, multi-GPU merge) ---------------------
     def costmap_device(self, params, costmap_dev_ptr):

@@ -4,6 +4,7 @@
 // There is deliberately no CPU path in this file: every data-path entry point launches CUDA kernels and
 // fails with STVL_ERR_NO_DEVICE / STVL_ERR_CUDA when that is impossible.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -93,9 +94,16 @@ struct stvl_grid {
   double time_bound = 0.0;          // every stored mark time is <= this ...
   bool time_bound_inf = false;      // ... unless a sweep may have raised times
   bool swept = false;
+  uint32_t * tile_buf[2] = {nullptr, nullptr};   // double-buffered column tiles (see GridView::tile_count)
+  int sweep_parity = 0;
   bool alloc_dirty = false;         // a Mark / load kernel handed out leaves that are not folded into the allocator yet
   uint64_t launches = 0;
   size_t device_bytes = 0;
+  // optional per-stage timing (stvl_enable_timing)
+  uint32_t timing_mask = 0;
+  struct TimedInterval { cudaEvent_t a, b; int stage; };
+  std::vector<TimedInterval> timing_pending;
+  std::vector<cudaEvent_t> timing_pool;
   double vs = 0, inv_vs = 0, half_vs = 0;
 };
 
@@ -125,6 +133,31 @@ struct DeviceGuard {
   if (!(g)) return fail(STVL_ERR_INVALID, "null grid handle");               \
   DeviceGuard guard__((g)->device);                                          \
   if (!guard__.ok) return fail(STVL_ERR_CUDA, "cudaSetDevice(%d) failed", (g)->device)
+
+// RAII bracket of one stage's launches with CUDA events (no-op unless the stage is selected)
+struct StageTimer {
+  stvl_grid * g;
+  int stage;
+  cudaEvent_t a = nullptr, b = nullptr;
+  StageTimer(stvl_grid * g_, int stage_) : g(g_), stage(stage_)
+  {
+    if (!(g->timing_mask & (uint32_t)stage)) return;
+    auto get = [&]() {
+      cudaEvent_t e = nullptr;
+      if (!g->timing_pool.empty()) { e = g->timing_pool.back(); g->timing_pool.pop_back(); }
+      else if (cudaEventCreate(&e) != cudaSuccess) e = nullptr;
+      return e;
+    };
+    a = get(); b = get();
+    if (a && b) cudaEventRecord(a, g->stream);
+  }
+  ~StageTimer()
+  {
+    if (!a || !b) return;
+    cudaEventRecord(b, g->stream);
+    g->timing_pending.push_back({a, b, stage});
+  }
+};
 
 int alloc_pool(stvl_grid * g, uint32_t leaf_capacity, GridView * nv)
 {
@@ -165,15 +198,42 @@ int alloc_tiles(stvl_grid * g, uint32_t tile_capacity, GridView * nv)
   CU(cudaMalloc(&v.tile_hash_keys, (size_t)hcap * 8));
   CU(cudaMalloc(&v.tile_hash_vals, (size_t)hcap * 4));
   CU(cudaMalloc(&v.tile_key, (size_t)tile_capacity * 8));
-  CU(cudaMalloc(&v.tile_count, (size_t)tile_capacity * 256));
+  CU(cudaMalloc(&v.tile_count, (size_t)tile_capacity * 256 * 2));   // two buffers back to back
+  v.tile_count_next = v.tile_count + (size_t)tile_capacity * 64;
   *nv = v;
   return STVL_OK;
 }
-size_t tile_bytes(const GridView & v) { return ((size_t)v.tile_hash_mask + 1) * 12 + (size_t)v.tile_capacity * (8 + 256); }
+size_t tile_bytes(const GridView & v) { return ((size_t)v.tile_hash_mask + 1) * 12 + (size_t)v.tile_capacity * (8 + 512); }
 void free_tiles(GridView & v)
 {
-  cudaFree(v.tile_hash_keys); cudaFree(v.tile_hash_vals); cudaFree(v.tile_key); cudaFree(v.tile_count);
-  v.tile_hash_keys = nullptr; v.tile_hash_vals = nullptr; v.tile_key = nullptr; v.tile_count = nullptr;
+  cudaFree(v.tile_hash_keys); cudaFree(v.tile_hash_vals); cudaFree(v.tile_key);
+  cudaFree(v.tile_count < v.tile_count_next ? v.tile_count : v.tile_count_next);
+  v.tile_hash_keys = nullptr; v.tile_hash_vals = nullptr; v.tile_key = nullptr; v.tile_count = nullptr; v.tile_count_next = nullptr;
+}
+
+// sentinel state of the counters (bounding boxes start empty)
+int init_counters(stvl_grid * g)
+{
+  Counters c;
+  std::memset(&c, 0, sizeof(c));
+  for (int k = 0; k < 2; ++k) { c.sw[k].cb_min_x = c.sw[k].cb_min_y = INT_MAX; c.sw[k].cb_max_x = c.sw[k].cb_max_y = INT_MIN; }
+  c.cm_acc.mk_min_x = c.cm_acc.mk_min_y = INT_MAX; c.cm_acc.mk_max_x = c.cm_acc.mk_max_y = INT_MIN;
+  c.cm = c.cm_acc;
+  *g->h_ctr = c;
+  CU(cudaMemcpyAsync(g->v.ctr, g->h_ctr, sizeof(Counters), cudaMemcpyHostToDevice, g->stream));
+  CU(cudaStreamSynchronize(g->stream));
+  g->last = c;
+  return STVL_OK;
+}
+// point the view at the tile buffer / counter set of sweep parity p
+void select_sweep_buffers(stvl_grid * g, int p)
+{
+  uint32_t * base = g->v.tile_count < g->v.tile_count_next ? g->v.tile_count : g->v.tile_count_next;
+  uint32_t * other = base + (size_t)g->v.tile_capacity * 64;
+  g->v.tile_count = p ? other : base;
+  g->v.tile_count_next = p ? base : other;
+  g->v.sw_cur = p;
+  g->sweep_parity = p;
 }
 
 // wipe the whole store (ResetGrid / creation)
@@ -187,9 +247,9 @@ int clear_pool(stvl_grid * g)
   CU(cudaMemsetAsync(v.leaf_time, 0, (size_t)v.leaf_capacity * kLeafVoxels * 8, s));
   CU(cudaMemsetAsync(v.tile_hash_keys, 0xFF, ((size_t)v.tile_hash_mask + 1) * 8, s));
   CU(cudaMemsetAsync(v.tile_hash_vals, 0xFF, ((size_t)v.tile_hash_mask + 1) * 4, s));
-  CU(cudaMemsetAsync(v.tile_count, 0, (size_t)v.tile_capacity * 256, s));
-  CU(cudaMemsetAsync(v.ctr, 0, sizeof(Counters), s));
-  g->last = Counters{};
+  select_sweep_buffers(g, 0);
+  CU(cudaMemsetAsync(v.tile_count, 0, (size_t)v.tile_capacity * 512, s));
+  { int rc = init_counters(g); if (rc != STVL_OK) return rc; }
   g->counters_fresh = true;
   g->marks_unverified = false;
   g->pending_leaf_bound = g->pending_tile_bound = 0;
@@ -223,7 +283,7 @@ int fetch_counters(stvl_grid * g)
   g->counters_fresh = true;
   g->pending_leaf_bound = g->pending_tile_bound = 0;
   // tighten the active-voxel bound: survivors of the last sweep + everything added after it
-  if (g->swept) g->active_upper = g->last.n_survived + g->added_since_sweep;
+  if (g->swept) g->active_upper = g->last.sw[g->sweep_parity].n_survived + g->added_since_sweep;
   return STVL_OK;
 }
 
@@ -242,7 +302,7 @@ int rebuild_tiles(stvl_grid * g)
   GridView & v = g->v;
   CU(cudaMemsetAsync(v.tile_hash_keys, 0xFF, ((size_t)v.tile_hash_mask + 1) * 8, g->stream));
   CU(cudaMemsetAsync(v.tile_hash_vals, 0xFF, ((size_t)v.tile_hash_mask + 1) * 4, g->stream));
-  CU(cudaMemsetAsync(v.tile_count, 0, (size_t)v.tile_capacity * 256, g->stream));
+  { const int p = g->sweep_parity; select_sweep_buffers(g, 0); CU(cudaMemsetAsync(v.tile_count, 0, (size_t)v.tile_capacity * 512, g->stream)); select_sweep_buffers(g, p); }
   CU(cudaMemsetAsync(&v.ctr->tile_n, 0, 4, g->stream));
   CU(cudaMemsetAsync(&v.ctr->tile_overflow, 0, 4, g->stream));
   CU(launch_reassign_tiles(v, v.leaf_capacity, g->sm_count, g->stream));
@@ -288,6 +348,7 @@ int grow_tiles(stvl_grid * g)
   if (rc != STVL_OK) return fail(STVL_ERR_CAPACITY, "growing the column tile pool failed: %s", g_err);
   g->device_bytes += tile_bytes(nv);
   g->v = nv;
+  select_sweep_buffers(g, g->sweep_parity);
   rc = rebuild_tiles(g);
   if (rc != STVL_OK) return rc;
   CU(cudaStreamSynchronize(g->stream));
@@ -298,12 +359,12 @@ int grow_tiles(stvl_grid * g)
 
 int launch_batches(stvl_grid * g, const std::vector<MarkBatch> & batches)
 {
+  StageTimer timer__(g, STVL_TIME_MARK);
   for (const MarkBatch & b : batches) {
-    int rc = ensure_folded(g);   // every allocating kernel starts from a folded allocator
+    int rc = ensure_folded(g);   // (only a preceding bulk load leaves the allocator unfolded; Mark kernels fold themselves)
     if (rc != STVL_OK) return rc;
     CU(launch_mark(g->v, b, g->sm_count, g->stream));
     g->launches += 1;
-    g->alloc_dirty = true;
   }
   return STVL_OK;
 }
@@ -483,10 +544,10 @@ void fill_costmap_result(const stvl_grid * g, stvl_costmap_result_t * res)
 {
   if (!res) return;
   std::memset(res, 0, sizeof(*res));
-  res->n_marked_columns = g->last.n_marked;
-  res->has_bounds = g->last.n_marked > 0;
+  res->n_marked_columns = g->last.cm.n_marked;
+  res->has_bounds = g->last.cm.n_marked > 0;
   if (res->has_bounds) {
-    const int32_t idx[4] = {g->last.mk_min_x, g->last.mk_min_y, g->last.mk_max_x, g->last.mk_max_y};
+    const int32_t idx[4] = {g->last.cm.mk_min_x, g->last.cm.mk_min_y, g->last.cm.mk_max_x, g->last.cm.mk_max_y};
     world_bbox(g, idx, res->touched);
   }
 }
@@ -596,6 +657,8 @@ int stvl_destroy(stvl_grid_t * g)
     if (g->h_frustums[i]) cudaFreeHost(g->h_frustums[i]);
     if (g->ev_frustums[i]) cudaEventDestroy(g->ev_frustums[i]);
   }
+  for (auto & iv : g->timing_pending) { cudaEventDestroy(iv.a); cudaEventDestroy(iv.b); }
+  for (auto e : g->timing_pool) cudaEventDestroy(e);
   if (g->ev_copy_done) cudaEventDestroy(g->ev_copy_done);
   if (g->ev_mark_done) cudaEventDestroy(g->ev_mark_done);
   if (g->stream) cudaStreamDestroy(g->stream);
@@ -683,9 +746,12 @@ int stvl_clear_frustums(stvl_grid_t * g, double now, const stvl_frustum_t * frus
     rc = ensure(g, g->ambiguous, cap * 3); if (rc != STVL_OK) return rc;
     out.ambiguous = g->ambiguous.p; out.ambiguous_cap = cap;
   }
+  rc = ensure_folded(g);
+  if (rc != STVL_OK) return rc;
+  select_sweep_buffers(g, g->sweep_parity ^ 1);   // this sweep's tile buffer / counter set (re-armed by the previous sweep)
+  StageTimer timer__(g, STVL_TIME_SWEEP);
   CU(launch_sweep(g->v, g->frustums.p, (int)n_frustums, now, out, slots_upper(g), g->sm_count, g->stream));
-  g->launches += 3;
-  g->alloc_dirty = false;   // the sweep prologue folds the allocator
+  g->launches += 2;
   g->counters_fresh = false;
   g->swept = true;
   g->added_since_sweep = 0;
@@ -747,8 +813,11 @@ int stvl_costmap_device(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_
   ENTER(g);
   if (!p || !costmap_dev) return fail(STVL_ERR_INVALID, "NULL argument");
   if (!(p->resolution > 0)) return fail(STVL_ERR_INVALID, "resolution must be positive");
-  CU(launch_costmap(g->v, to_dev(*p), costmap_dev, tiles_upper(g), g->sm_count, g->stream));
-  g->launches += 2;
+  {
+    StageTimer timer__(g, STVL_TIME_COSTMAP);
+    CU(launch_costmap(g->v, to_dev(*p), costmap_dev, tiles_upper(g), g->sm_count, g->stream));
+  }
+  g->launches += 1;
   g->counters_fresh = false;
   if (!res) return STVL_OK;   // fully asynchronous: the caller synchronises / reads results later
   int rc = fetch_counters(g);
@@ -765,8 +834,11 @@ int stvl_costmap(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_t * cos
   const size_t bytes = (size_t)p->size_x * p->size_y;
   int rc = ensure(g, g->costmap, std::max<size_t>(bytes, 1));
   if (rc != STVL_OK) return rc;
-  CU(launch_costmap(g->v, to_dev(*p), g->costmap.p, tiles_upper(g), g->sm_count, g->stream));
-  g->launches += 2;
+  {
+    StageTimer timer__(g, STVL_TIME_COSTMAP);
+    CU(launch_costmap(g->v, to_dev(*p), g->costmap.p, tiles_upper(g), g->sm_count, g->stream));
+  }
+  g->launches += 1;
   if (costmap && bytes) CU(cudaMemcpyAsync(costmap, g->costmap.p, bytes, cudaMemcpyDeviceToHost, g->stream));
   rc = fetch_counters(g);
   if (rc != STVL_OK) return rc;
@@ -781,7 +853,7 @@ int stvl_get_sweep_stats(stvl_grid_t * g, stvl_sweep_stats_t * out)
   int rc = fetch_counters(g);
   if (rc != STVL_OK) return rc;
   std::memset(out, 0, sizeof(*out));
-  const Counters & c = g->last;
+  const SweepCtr & c = g->last.sw[g->sweep_parity];
   out->n_swept = c.n_swept; out->n_survived = c.n_survived; out->n_cleared = c.n_cleared;
   out->n_rewritten = c.n_rewritten; out->n_ambiguous = c.n_ambiguous;
   if (c.n_cleared) {
@@ -826,7 +898,7 @@ int stvl_get_cleared(stvl_grid_t * g, int32_t * ix, int32_t * iy, uint64_t cap, 
   if (!n) return fail(STVL_ERR_INVALID, "n is NULL");
   int rc = fetch_counters(g);
   if (rc != STVL_OK) return rc;
-  *n = (g->out_flags & STVL_OUT_CLEARED) ? g->last.n_cleared_out : 0;
+  *n = (g->out_flags & STVL_OUT_CLEARED) ? g->last.sw[g->sweep_parity].n_cleared_out : 0;
   const uint64_t m = std::min<uint64_t>(*n, cap);
   if (m && (ix || iy)) {
     std::vector<int32_t> tmp(m * 2);
@@ -844,7 +916,7 @@ int stvl_get_points(stvl_grid_t * g, float * xyz, uint64_t cap, uint64_t * n)
   if (!n) return fail(STVL_ERR_INVALID, "n is NULL");
   int rc = fetch_counters(g);
   if (rc != STVL_OK) return rc;
-  *n = g->cfg.pub_voxels ? g->last.n_points_out : 0;
+  *n = g->cfg.pub_voxels ? g->last.sw[g->sweep_parity].n_points_out : 0;
   const uint64_t m = std::min<uint64_t>(*n, cap);
   if (m && xyz) CU(cudaMemcpy(xyz, g->points.p, m * 12, cudaMemcpyDeviceToHost));
   rc = after_fetch(g);
@@ -858,7 +930,7 @@ int stvl_get_ambiguous(stvl_grid_t * g, int32_t * ix, int32_t * iy, int32_t * iz
   if (!n) return fail(STVL_ERR_INVALID, "n is NULL");
   int rc = fetch_counters(g);
   if (rc != STVL_OK) return rc;
-  *n = (g->out_flags & STVL_OUT_AMBIGUOUS) ? std::min<uint64_t>(g->last.n_ambiguous_out, 65536) : 0;
+  *n = (g->out_flags & STVL_OUT_AMBIGUOUS) ? std::min<uint64_t>(g->last.sw[g->sweep_parity].n_ambiguous_out, 65536) : 0;
   const uint64_t m = std::min<uint64_t>(*n, cap);
   if (m) {
     std::vector<int32_t> tmp(m * 3);
@@ -998,7 +1070,7 @@ int stvl_costmap_from_dense(stvl_grid_t * g, const uint32_t * dense_dev, int32_t
   ENTER(g);
   if (!dense_dev || !p || !costmap_dev) return fail(STVL_ERR_INVALID, "NULL argument");
   CU(launch_costmap_from_dense(g->v, dense_dev, ix0, iy0, nx, ny, to_dev(*p), costmap_dev, g->sm_count, g->stream));
-  g->launches += 2;
+  g->launches += 1;
   g->counters_fresh = false;
   if (!res) return STVL_OK;   // fully asynchronous
   int rc = fetch_counters(g);
@@ -1027,6 +1099,44 @@ int stvl_get_pool_stats(stvl_grid_t * g, stvl_pool_stats_t * out)
   out->kernel_launches = g->launches;
   out->device_bytes = g->device_bytes;
   return after_fetch(g);
+}
+
+int stvl_update_cycle_device(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
+                             const stvl_reading_t * readings, uint32_t n_readings,
+                             const stvl_costmap_params_t * p, uint8_t * costmap_dev)
+{
+  int rc = stvl_clear_frustums(g, now, frustums, n_frustums);
+  if (rc != STVL_OK) return rc;
+  rc = stvl_mark_device(g, readings, n_readings);
+  if (rc != STVL_OK) return rc;
+  return stvl_costmap_device(g, p, costmap_dev, nullptr);
+}
+
+int stvl_enable_timing(stvl_grid_t * g, uint32_t stage_mask)
+{
+  if (!g) return fail(STVL_ERR_INVALID, "null grid handle");
+  g->timing_mask = stage_mask;
+  return STVL_OK;
+}
+
+int stvl_get_timing(stvl_grid_t * g, stvl_timing_t * out)
+{
+  ENTER(g);
+  if (!out) return fail(STVL_ERR_INVALID, "out is NULL");
+  std::memset(out, 0, sizeof(*out));
+  CU(cudaStreamSynchronize(g->stream));
+  for (const auto & iv : g->timing_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, iv.a, iv.b) == cudaSuccess) {
+      if (iv.stage == STVL_TIME_SWEEP) { out->sweep_ms += ms; ++out->n_sweep; }
+      else if (iv.stage == STVL_TIME_MARK) { out->mark_ms += ms; ++out->n_mark; }
+      else { out->costmap_ms += ms; ++out->n_costmap; }
+    }
+    g->timing_pool.push_back(iv.a);
+    g->timing_pool.push_back(iv.b);
+  }
+  g->timing_pending.clear();
+  return STVL_OK;
 }
 
 int stvl_get_stream(stvl_grid_t * g, void ** stream)

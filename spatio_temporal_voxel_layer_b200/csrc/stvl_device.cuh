@@ -29,7 +29,18 @@ constexpr uint32_t kOverflowSlot = 0xFFFFFFFEu; // pool exhausted when this leaf
 constexpr int kMaxFrustums = 512;
 constexpr int kMaxBatchReadings = 16;
 
-// -------- device-resident counters (one struct, zero-initialised) -----------------
+// -------- device-resident counters ---------------------------------------------------
+// Results of one clear sweep.  Two sets: sweep k accumulates into set k&1 while its first kernel re-arms the other
+// set for sweep k+1, so no separate "zero the counters" launch is needed.
+struct SweepCtr {
+  unsigned long long n_swept, n_survived, n_cleared, n_rewritten, n_ambiguous;
+  int32_t cb_min_x, cb_min_y, cb_max_x, cb_max_y;
+  unsigned long long n_points_out, n_cleared_out, n_ambiguous_out;
+};
+struct CostmapCtr {
+  unsigned long long n_marked;
+  int32_t mk_min_x, mk_min_y, mk_max_x, mk_max_y;
+};
 struct Counters {
   // leaf pool allocator
   uint32_t alloc_cursor;   // leaves requested by the running Mark kernel
@@ -41,15 +52,13 @@ struct Counters {
   // tile pool
   uint32_t tile_n;
   uint32_t tile_overflow;
+  // last-CTA-done tickets (each kernel's last CTA commits / re-arms shared state)
+  uint32_t mark_ticket, leaf_ticket, cm_ticket, pad1;
   // dropped input points
   unsigned long long dropped_range, dropped_nonfinite;
-  // last sweep
-  unsigned long long n_swept, n_survived, n_cleared, n_rewritten, n_ambiguous;
-  int32_t cb_min_x, cb_min_y, cb_max_x, cb_max_y;
-  unsigned long long n_points_out, n_cleared_out, n_ambiguous_out;
-  // costmap / column queries
-  unsigned long long n_marked;
-  int32_t mk_min_x, mk_min_y, mk_max_x, mk_max_y;
+  SweepCtr sw[2];
+  CostmapCtr cm_acc;       // accumulators of the running costmap kernel
+  CostmapCtr cm;           // published result of the last costmap kernel
   unsigned long long n_columns_out;
   // dumps
   unsigned long long n_voxels_out, n_active;
@@ -84,7 +93,9 @@ struct GridView {
   uint32_t * tile_hash_vals;
   uint32_t tile_hash_mask;
   uint64_t * tile_key;
-  uint32_t * tile_count;   // 64 per tile
+  uint32_t * tile_count;   // 64 per tile: the buffer the LAST sweep filled (what costmap / column queries read)
+  uint32_t * tile_count_next;   // the other buffer: zeroed during a sweep for the one after it
+  int sw_cur;              // which SweepCtr set / tile buffer the current (last) sweep uses
   uint32_t tile_capacity;
   Counters * ctr;
   // constants

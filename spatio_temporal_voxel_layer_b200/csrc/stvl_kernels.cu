@@ -124,9 +124,9 @@ __device__ uint32_t leaf_find_or_insert(const GridView & g, uint64_t key, int bx
 __device__ __forceinline__ void fold_alloc(const GridView & g)
 {
   Counters * c = g.ctr;
-  const uint32_t cursor = c->alloc_cursor;
+  const uint32_t cursor = ld_volatile_u32(&c->alloc_cursor);
   if (cursor == 0) return;
-  const uint32_t free_n = c->free_n, hw = c->high_water;
+  const uint32_t free_n = ld_volatile_u32(&c->free_n), hw = ld_volatile_u32(&c->high_water);
   const uint32_t from_free = cursor < free_n ? cursor : free_n;
   unsigned long long nhw = (unsigned long long)hw + (cursor - from_free);
   if (nhw > g.leaf_capacity) nhw = g.leaf_capacity;
@@ -258,7 +258,7 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
 
   const uint32_t chunk_begin = blockIdx.x * chunks_per_cta;
   const uint32_t chunk_end = min(chunk_begin + chunks_per_cta, batch.total_blocks);
-  if (chunk_begin >= chunk_end) return;
+  if (chunk_begin >= chunk_end) return;   // cannot happen: the grid is sized so that every CTA owns >= 1 chunk
 
   // block-local table and the first reading's parameters
   if (threadIdx.x < kMarkTable) s_key[threadIdx.x] = kEmptyKey;
@@ -446,6 +446,14 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
   if (threadIdx.x == 0) {
     if (s_drop[0]) atomicAdd(&g.ctr->dropped_range, (unsigned long long)s_drop[0]);
     if (s_drop[1]) atomicAdd(&g.ctr->dropped_nonfinite, (unsigned long long)s_drop[1]);
+    // the last CTA commits the leaves handed out by this launch to the allocator state
+    __threadfence();
+    if (atomicAdd(&g.ctr->mark_ticket, 1u) == gridDim.x - 1) {
+      __threadfence();
+      fold_alloc(g);
+      g.ctr->mark_ticket = 0;
+      __threadfence();
+    }
   }
 }
 
@@ -547,7 +555,7 @@ __device__ __forceinline__ void sweep_publish(const GridView & g, SweepAcc a)
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    Counters * c = g.ctr;
+    SweepCtr * c = &g.ctr->sw[g.sw_cur];
     if (s_red[0]) atomicAdd(&c->n_swept, (unsigned long long)s_red[0]);
     if (s_red[1]) atomicAdd(&c->n_survived, (unsigned long long)s_red[1]);
     if (s_red[2]) {
@@ -591,6 +599,18 @@ sweep_triage_kernel(const GridView g, const DevFrustum * __restrict__ frustums_g
   DevFrustum * fr = reinterpret_cast<DevFrustum *>(smem_raw);
   stage_frustums(fr, frustums_gmem, n_frustums);
   const uint32_t n_slots = g.ctr->high_water;
+  // re-arm the state of the NEXT sweep while this one runs: zero the other tile buffer and the other counter set
+  {
+    const uint32_t n_words = (g.ctr->tile_n < g.tile_capacity ? g.ctr->tile_n : g.tile_capacity) * 64u;
+    uint4 * t4 = reinterpret_cast<uint4 *>(g.tile_count_next);
+    for (uint32_t i = blockIdx.x * kSweepThreads + threadIdx.x; i < n_words / 4; i += gridDim.x * kSweepThreads) t4[i] = make_uint4(0, 0, 0, 0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      SweepCtr * c = &g.ctr->sw[g.sw_cur ^ 1];
+      c->n_swept = c->n_survived = c->n_cleared = c->n_rewritten = c->n_ambiguous = 0;
+      c->cb_min_x = c->cb_min_y = INT_MAX; c->cb_max_x = c->cb_max_y = INT_MIN;
+      c->n_points_out = c->n_cleared_out = c->n_ambiguous_out = 0;
+    }
+  }
   SweepAcc acc;
   for (uint32_t slot = blockIdx.x * kSweepThreads + threadIdx.x; slot < n_slots; slot += gridDim.x * kSweepThreads) {
     // all loads of the leaf are independent of each other: one DRAM round trip per leaf
@@ -651,6 +671,17 @@ sweep_triage_kernel(const GridView g, const DevFrustum * __restrict__ frustums_g
   sweep_publish(g, acc);
 }
 
+// every CTA of pass 2 read queue_n when it started; the last one to finish empties the queue for the next sweep
+__device__ __forceinline__ void leaf_pass_done(const GridView & g)
+{
+  __threadfence();
+  if (atomicAdd(&g.ctr->leaf_ticket, 1u) == gridDim.x - 1) {
+    g.ctr->queue_n = 0;
+    g.ctr->leaf_ticket = 0;
+    __threadfence();
+  }
+}
+
 // Sweep, pass 2 — ONE WARP PER QUEUED LEAF: leaf-level frustum classification, exact per-voxel frustum tests, decay,
 // rewrite of accelerated mark times, clearing (reference .cpp:158-221).
 __global__ void __launch_bounds__(kSweepThreads, 4)
@@ -664,24 +695,38 @@ sweep_leaf_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gme
   __shared__ uint32_t s_part[kSweepWarps][kMaxFrustums / 32];
   __shared__ uint32_t s_full[kSweepWarps][kMaxFrustums / 32];
   __shared__ double s_val[kSweepWarps][128];
-  const uint32_t n_queued = g.ctr->queue_n;
-  if (blockIdx.x * kSweepWarps >= n_queued) return;   // nothing for this CTA (uniform per block)
-  stage_frustums(fr, frustums_gmem, n_frustums);
-
   const unsigned lane = threadIdx.x & 31;
   const unsigned warp = threadIdx.x >> 5;
+  const uint16_t * mask16 = reinterpret_cast<const uint16_t *>(g.leaf_mask);
+  // Shorten the dependent-load chain of a warp's first leaf: its queue entry and leaf header are requested
+  // speculatively, together with the queue length and the frustum blocks (a stale queue entry is still a valid slot
+  // index, so the wasted loads are harmless).
+  const uint32_t qi0 = blockIdx.x * kSweepWarps + warp;
+  uint32_t slot0 = qi0 < g.leaf_capacity ? g.sweep_queue[qi0] : 0u;
+  if (slot0 >= g.leaf_capacity) slot0 = 0;
+  const uint64_t key0 = g.leaf_key[slot0];
+  const uint32_t m16_0 = mask16[(size_t)slot0 * 32 + lane];
+  const uint32_t tile0 = g.leaf_tile[slot0];
+  const double tmin0 = g.leaf_tmin[slot0];
+  const uint32_t n_queued = g.ctr->queue_n;
+  if (blockIdx.x * kSweepWarps >= n_queued) {   // nothing for this CTA (uniform per block)
+    if (threadIdx.x == 0) leaf_pass_done(g);
+    return;
+  }
+  stage_frustums(fr, frustums_gmem, n_frustums);
+
   const int n_chunks = (n_frustums + 31) >> 5;
   const bool skip_model_ok = !out.points;
-  const uint16_t * mask16 = reinterpret_cast<const uint16_t *>(g.leaf_mask);
   unsigned int c_swept = 0, c_surv = 0, c_clear = 0, c_rewr = 0, c_amb = 0;
   int bb_min_x = INT_MAX, bb_min_y = INT_MAX, bb_max_x = INT_MIN, bb_max_y = INT_MIN;
 
   for (uint32_t qi = blockIdx.x * kSweepWarps + warp; qi < n_queued; qi += gridDim.x * kSweepWarps) {
-    const uint32_t slot = g.sweep_queue[qi];
-    const uint64_t key = g.leaf_key[slot];
-    const uint32_t m16 = mask16[(size_t)slot * 32 + lane];   // each lane owns two voxel columns = local indices [lane*16, lane*16+16)
-    const uint32_t tile = g.leaf_tile[slot];
-    const double tmin = g.leaf_tmin[slot];
+    const bool first = qi == qi0;
+    const uint32_t slot = first ? slot0 : g.sweep_queue[qi];
+    const uint64_t key = first ? key0 : g.leaf_key[slot];
+    const uint32_t m16 = first ? m16_0 : mask16[(size_t)slot * 32 + lane];   // each lane owns two voxel columns = local indices [lane*16, lane*16+16)
+    const uint32_t tile = first ? tile0 : g.leaf_tile[slot];
+    const double tmin = first ? tmin0 : g.leaf_tmin[slot];
 
     int bx, by, bz;
     unpack_leaf_key(key, bx, by, bz);
@@ -805,7 +850,7 @@ sweep_leaf_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gme
         if (amb) {
           ++c_amb;
           if (out.ambiguous) {
-            const unsigned long long a = atomicAdd(&g.ctr->n_ambiguous_out, 1ull);
+            const unsigned long long a = atomicAdd(&g.ctr->sw[g.sw_cur].n_ambiguous_out, 1ull);
             if (a < out.ambiguous_cap) { out.ambiguous[3 * a] = ix; out.ambiguous[3 * a + 1] = iy; out.ambiguous[3 * a + 2] = iz; }
           }
         }
@@ -815,7 +860,7 @@ sweep_leaf_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gme
         const unsigned sm = __ballot_sync(kFull, survived);
         if (sm) {
           unsigned long long b0 = 0;
-          if (lane == (unsigned)(__ffs(sm) - 1)) b0 = atomicAdd(&g.ctr->n_points_out, (unsigned long long)__popc(sm));
+          if (lane == (unsigned)(__ffs(sm) - 1)) b0 = atomicAdd(&g.ctr->sw[g.sw_cur].n_points_out, (unsigned long long)__popc(sm));
           b0 = __shfl_sync(kFull, b0, __ffs(sm) - 1);
           if (survived) {
             const unsigned long long o = b0 + __popc(sm & ((1u << lane) - 1));
@@ -831,7 +876,7 @@ sweep_leaf_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gme
         const unsigned cm = __ballot_sync(kFull, cleared);
         if (cm) {
           unsigned long long b0 = 0;
-          if (lane == (unsigned)(__ffs(cm) - 1)) b0 = atomicAdd(&g.ctr->n_cleared_out, (unsigned long long)__popc(cm));
+          if (lane == (unsigned)(__ffs(cm) - 1)) b0 = atomicAdd(&g.ctr->sw[g.sw_cur].n_cleared_out, (unsigned long long)__popc(cm));
           b0 = __shfl_sync(kFull, b0, __ffs(cm) - 1);
           if (cleared) {
             const unsigned long long o = b0 + __popc(cm & ((1u << lane) - 1));
@@ -867,22 +912,7 @@ sweep_leaf_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gme
   acc.swept = c_swept; acc.surv = c_surv; acc.clear = c_clear; acc.rewr = c_rewr; acc.amb = c_amb;
   acc.min_x = bb_min_x; acc.min_y = bb_min_y; acc.max_x = bb_max_x; acc.max_y = bb_max_y;
   sweep_publish(g, acc);
-}
-
-// zero the column tiles and the per-sweep counters before a sweep
-__global__ void __launch_bounds__(256) sweep_prologue_kernel(const GridView g)
-{
-  const uint32_t n_words = g.ctr->tile_n < g.tile_capacity ? g.ctr->tile_n * 64u : g.tile_capacity * 64u;
-  uint4 * t4 = reinterpret_cast<uint4 *>(g.tile_count);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words / 4; i += gridDim.x * blockDim.x) t4[i] = make_uint4(0, 0, 0, 0);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    Counters * c = g.ctr;
-    fold_alloc(g);
-    c->n_swept = c->n_survived = c->n_cleared = c->n_rewritten = c->n_ambiguous = 0;
-    c->cb_min_x = c->cb_min_y = INT_MAX; c->cb_max_x = c->cb_max_y = INT_MIN;
-    c->n_points_out = c->n_cleared_out = c->n_ambiguous_out = 0;
-    c->queue_n = 0;
-  }
+  if (threadIdx.x == 0) leaf_pass_done(g);
 }
 
 // =====================================================================================
@@ -914,9 +944,24 @@ __device__ __forceinline__ void costmap_reduce_and_publish(Counters * c, unsigne
     atomicMin(&s_b[0], mnx); atomicMin(&s_b[1], mny); atomicMax(&s_b[2], mxx); atomicMax(&s_b[3], mxy);
   }
   __syncthreads();
-  if (threadIdx.x == 0 && s_n) {
-    atomicAdd(&c->n_marked, (unsigned long long)s_n);
-    atomicMin(&c->mk_min_x, s_b[0]); atomicMin(&c->mk_min_y, s_b[1]); atomicMax(&c->mk_max_x, s_b[2]); atomicMax(&c->mk_max_y, s_b[3]);
+  if (threadIdx.x == 0) {
+    if (s_n) {
+      atomicAdd(&c->cm_acc.n_marked, (unsigned long long)s_n);
+      atomicMin(&c->cm_acc.mk_min_x, s_b[0]); atomicMin(&c->cm_acc.mk_min_y, s_b[1]);
+      atomicMax(&c->cm_acc.mk_max_x, s_b[2]); atomicMax(&c->cm_acc.mk_max_y, s_b[3]);
+    }
+    // the last CTA publishes the result and re-arms the accumulators (no separate prologue launch)
+    __threadfence();
+    if (atomicAdd(&c->cm_ticket, 1u) == gridDim.x - 1) {
+      __threadfence();
+      volatile CostmapCtr * a = &c->cm_acc;
+      c->cm.n_marked = a->n_marked;
+      c->cm.mk_min_x = a->mk_min_x; c->cm.mk_min_y = a->mk_min_y; c->cm.mk_max_x = a->mk_max_x; c->cm.mk_max_y = a->mk_max_y;
+      a->n_marked = 0;
+      a->mk_min_x = INT_MAX; a->mk_min_y = INT_MAX; a->mk_max_x = INT_MIN; a->mk_max_y = INT_MIN;
+      c->cm_ticket = 0;
+      __threadfence();
+    }
   }
 }
 
@@ -948,13 +993,7 @@ __global__ void __launch_bounds__(256) costmap_kernel(const GridView g, const Co
   costmap_reduce_and_publish(g.ctr, n, mnx, mny, mxx, mxy);
 }
 
-__global__ void costmap_prologue_kernel(const GridView g)
-{
-  Counters * c = g.ctr;
-  c->n_marked = 0;
-  c->mk_min_x = c->mk_min_y = INT_MAX; c->mk_max_x = c->mk_max_y = INT_MIN;
-  c->n_columns_out = 0;
-}
+__global__ void columns_prologue_kernel(const GridView g) { g.ctr->n_columns_out = 0; }
 
 // occupied columns of the last sweep as (ix, iy, count) — GetFlattenedCostmap, reference .cpp:312-317
 __global__ void __launch_bounds__(256) columns_kernel(const GridView g, int32_t * __restrict__ oix, int32_t * __restrict__ oiy,
@@ -1177,9 +1216,7 @@ cudaError_t launch_load_voxels(const GridView & g, const int32_t * x, const int3
 cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, int n_frustums, double now, const SweepOutputs & out,
                          uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s)
 {
-  sweep_prologue_kernel<<<sm_count * 2, 256, 0, s>>>(g);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  cudaError_t e;
   const size_t dyn = (size_t)n_frustums * sizeof(DevFrustum);
   if (dyn > 32 * 1024) {
     e = cudaFuncSetAttribute(sweep_triage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -1200,14 +1237,14 @@ cudaError_t launch_costmap(const GridView & g, const CostmapDev & p, uint8_t * c
 {
   cudaError_t e = cudaMemsetAsync(costmap_dev, p.default_value, (size_t)p.size_x * p.size_y, s);   // Costmap2D::resetMaps, :705
   if (e != cudaSuccess) return e;
-  costmap_prologue_kernel<<<1, 1, 0, s>>>(g);
-  costmap_kernel<<<grid_for(tiles_upper_bound, 8, sm_count * 8), 256, 0, s>>>(g, p, costmap_dev);
+  // 64 tiles per CTA (8 per warp): the per-CTA statistics reduction is amortised and the grid stays a fraction of a wave
+  costmap_kernel<<<grid_for(tiles_upper_bound, 64, sm_count * 4), 256, 0, s>>>(g, p, costmap_dev);
   return cudaGetLastError();
 }
 cudaError_t launch_columns(const GridView & g, int32_t * ix, int32_t * iy, uint32_t * cnt, unsigned long long cap,
                            uint32_t tiles_upper_bound, int sm_count, cudaStream_t s)
 {
-  costmap_prologue_kernel<<<1, 1, 0, s>>>(g);
+  columns_prologue_kernel<<<1, 1, 0, s>>>(g);
   columns_kernel<<<grid_for((unsigned long long)tiles_upper_bound * 64, 256, sm_count * 8), 256, 0, s>>>(g, ix, iy, cnt, cap);
   return cudaGetLastError();
 }
@@ -1222,7 +1259,6 @@ cudaError_t launch_costmap_from_dense(const GridView & g, const uint32_t * dense
 {
   cudaError_t e = cudaMemsetAsync(costmap_dev, p.default_value, (size_t)p.size_x * p.size_y, s);
   if (e != cudaSuccess) return e;
-  costmap_prologue_kernel<<<1, 1, 0, s>>>(g);
   costmap_from_dense_kernel<<<grid_for((unsigned long long)nx * ny, 256, sm_count * 8), 256, 0, s>>>(g, dense, ix0, iy0, nx, ny, p, costmap_dev);
   return cudaGetLastError();
 }
