@@ -401,10 +401,18 @@ def bench_ours(args):
             line["cpu_baseline"] = {"value": len(times) / sum(times), "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": "%d full config-2 cycles after 1 warm-up, oracle/stvl_oracle.cpp single thread (the reference path is single-threaded); host %s x%s" % (len(times), model, ncpu)}
         print(json.dumps(line))
-    g.close()
+    # tear down in dependency order: tensors that were used on the library's stream are released while that stream is
+    # still alive (the caching allocator records events on it), then the process group, then the grid
+    barrier()
+    if world > 1:
+        del dense
+    del costmap_dev, costmap_host, dev_clouds, host_clouds
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    g.close()
 
 
 def main():

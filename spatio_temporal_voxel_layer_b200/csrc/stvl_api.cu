@@ -78,6 +78,8 @@ struct stvl_grid {
   DevBuf<float> points;
   DevBuf<int32_t> cleared, ambiguous;
   DevBuf<uint8_t> costmap;
+  size_t costmap_clean_bytes = 0;     // the internal costmap buffer is already filled with costmap_clean_value ...
+  int costmap_clean_value = -1;       // ... over this many bytes (re-armed after every copy-out)
   DevBuf<int32_t> col_ix, col_iy;
   DevBuf<uint32_t> col_cnt;
   DevBuf<int32_t> dump_x, dump_y, dump_z;
@@ -815,7 +817,7 @@ int stvl_costmap_device(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_
   if (!(p->resolution > 0)) return fail(STVL_ERR_INVALID, "resolution must be positive");
   {
     StageTimer timer__(g, STVL_TIME_COSTMAP);
-    CU(launch_costmap(g->v, to_dev(*p), costmap_dev, tiles_upper(g), g->sm_count, g->stream));
+    CU(launch_costmap(g->v, to_dev(*p), costmap_dev, tiles_upper(g), g->sm_count, g->stream, true));
   }
   g->launches += 1;
   g->counters_fresh = false;
@@ -832,16 +834,25 @@ int stvl_costmap(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_t * cos
   if (!p) return fail(STVL_ERR_INVALID, "NULL argument");
   if (!(p->resolution > 0)) return fail(STVL_ERR_INVALID, "resolution must be positive");
   const size_t bytes = (size_t)p->size_x * p->size_y;
+  const uint8_t * before = g->costmap.p;
   int rc = ensure(g, g->costmap, std::max<size_t>(bytes, 1));
   if (rc != STVL_OK) return rc;
+  if (g->costmap.p != before) g->costmap_clean_value = -1;   // fresh allocation: contents unknown
   {
     StageTimer timer__(g, STVL_TIME_COSTMAP);
-    CU(launch_costmap(g->v, to_dev(*p), g->costmap.p, tiles_upper(g), g->sm_count, g->stream));
+    const bool prefilled = g->costmap_clean_value == (int)p->default_value && g->costmap_clean_bytes == bytes;
+    CU(launch_costmap(g->v, to_dev(*p), g->costmap.p, tiles_upper(g), g->sm_count, g->stream, !prefilled));
   }
   g->launches += 1;
   if (costmap && bytes) CU(cudaMemcpyAsync(costmap, g->costmap.p, bytes, cudaMemcpyDeviceToHost, g->stream));
   rc = fetch_counters(g);
   if (rc != STVL_OK) return rc;
+  // resetMaps for the NEXT cycle, off the critical path (runs while the caller works on this cycle's bytes)
+  if (bytes) {
+    CU(cudaMemsetAsync(g->costmap.p, p->default_value, bytes, g->stream));
+    g->costmap_clean_value = (int)p->default_value;
+    g->costmap_clean_bytes = bytes;
+  }
   fill_costmap_result(g, res);
   return after_fetch(g);
 }

@@ -191,27 +191,34 @@ __device__ __forceinline__ double index_to_world(int i, double vs, double half_v
 // (correctly-rounded sqrt/div, no FMA), so the result is bit-identical to the CPU path everywhere.
 __device__ __forceinline__ bool depth_is_inside(const double * __restrict__ pl, double x, double y, double z)
 {
+  // pass 1, branch-free: the six planes are independent chains (a lone warp on a dense leaf is latency bound, so
+  // instruction-level parallelism matters more than early exit)
+  bool outside = false;
+  unsigned in_band = 0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
-    const double nx = pl[6 * k + 0], ny = pl[6 * k + 1], nz = pl[6 * k + 2];
-    double dx = __dsub_rn(x, pl[6 * k + 3]);
-    double dy = __dsub_rn(y, pl[6 * k + 4]);
-    double dz = __dsub_rn(z, pl[6 * k + 5]);
-    const double tx = nx * dx, ty = ny * dy, tz = nz * dz;
+    const double dx = __dsub_rn(x, pl[6 * k + 3]), dy = __dsub_rn(y, pl[6 * k + 4]), dz = __dsub_rn(z, pl[6 * k + 5]);
+    const double tx = pl[6 * k + 0] * dx, ty = pl[6 * k + 1] * dy, tz = pl[6 * k + 2] * dz;
     const double s = tx + ty + tz;
     const double band = 1e-12 * (fabs(tx) + fabs(ty) + fabs(tz));
-    if (s > band) return false;
-    if (s >= -band) {
-      // exact replay: Eigen normalize() = divide by sqrt(squaredNorm) when squaredNorm > 0,
-      // squaredNorm = (x*x + y*y) + z*z; Dot = (nx*dx + ny*dy) + nz*dz
-      const double z2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-      if (z2 > 0.0) {
-        const double n = __dsqrt_rn(z2);
-        dx = __ddiv_rn(dx, n); dy = __ddiv_rn(dy, n); dz = __ddiv_rn(dz, n);
-      }
-      const double dot = __dadd_rn(__dadd_rn(__dmul_rn(nx, dx), __dmul_rn(ny, dy)), __dmul_rn(nz, dz));
-      if (dot > 0.) return false;
+    outside = outside || (s > band);
+    in_band |= (s >= -band && s <= band) ? (1u << k) : 0u;
+  }
+  if (outside) return false;   // some plane certainly has n . normalize(d) > 0
+  // pass 2 (rare): planes whose dot is within the guard band replay the reference's exact operation sequence:
+  // Eigen normalize() = divide by sqrt(squaredNorm) when squaredNorm > 0, squaredNorm = (x*x + y*y) + z*z;
+  // Dot = (nx*dx + ny*dy) + nz*dz
+  while (in_band) {
+    const int k = __ffs(in_band) - 1;
+    in_band &= in_band - 1;
+    double dx = __dsub_rn(x, pl[6 * k + 3]), dy = __dsub_rn(y, pl[6 * k + 4]), dz = __dsub_rn(z, pl[6 * k + 5]);
+    const double z2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    if (z2 > 0.0) {
+      const double n = __dsqrt_rn(z2);
+      dx = __ddiv_rn(dx, n); dy = __ddiv_rn(dy, n); dz = __ddiv_rn(dz, n);
     }
+    const double dot = __dadd_rn(__dadd_rn(__dmul_rn(pl[6 * k + 0], dx), __dmul_rn(pl[6 * k + 1], dy)), __dmul_rn(pl[6 * k + 2], dz));
+    if (dot > 0.) return false;
   }
   return true;
 }

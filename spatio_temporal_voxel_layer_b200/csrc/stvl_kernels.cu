@@ -965,6 +965,7 @@ __device__ __forceinline__ void costmap_reduce_and_publish(Counters * c, unsigne
   }
 }
 
+constexpr int kCostmapTilesPerWarp = 8;
 __global__ void __launch_bounds__(256) costmap_kernel(const GridView g, const CostmapDev p, uint8_t * __restrict__ costmap)
 {
   const unsigned lane = threadIdx.x & 31;
@@ -972,21 +973,34 @@ __global__ void __launch_bounds__(256) costmap_kernel(const GridView g, const Co
   const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
   unsigned n = 0;
   int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
-  for (uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tiles; t += warps_total) {
-    const uint2 cc = reinterpret_cast<const uint2 *>(g.tile_count + (size_t)t * 64)[lane];   // columns 2*lane, 2*lane+1
-    if ((cc.x | cc.y) == 0) continue;
-    int bx, by;
-    unpack_tile_key(g.tile_key[t], bx, by);
+  // each warp owns batches of 8 consecutive tiles; the 8 x 256 B count rows and the 8 tile keys are requested together
+  // (one DRAM round trip per batch instead of one per tile)
+  for (uint32_t t0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kCostmapTilesPerWarp; t0 < n_tiles;
+       t0 += warps_total * kCostmapTilesPerWarp) {
+    uint2 cc[kCostmapTilesPerWarp];
+    unsigned long long keys[kCostmapTilesPerWarp];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const uint32_t cnt = k ? cc.y : cc.x;
-      const int col = 2 * (int)lane + k;
-      if (cnt == 0 || (int)cnt < p.mark_threshold) continue;   // static_cast<int>(count) >= _mark_threshold, :712
-      const int ix = bx * 8 + (col >> 3), iy = by * 8 + (col & 7);
-      unsigned mx, my;
-      if (world_to_map(index_to_world(ix, g.vs, g.half_vs), index_to_world(iy, g.vs, g.half_vs), p, mx, my)) {
-        costmap[(size_t)my * p.size_x + mx] = p.lethal;   // :715
-        ++n; mnx = min(mnx, ix); mny = min(mny, iy); mxx = max(mxx, ix); mxy = max(mxy, iy);   // touch(), :716
+    for (int u = 0; u < kCostmapTilesPerWarp; ++u) {
+      const uint32_t t = t0 + u;
+      cc[u] = t < n_tiles ? reinterpret_cast<const uint2 *>(g.tile_count + (size_t)t * 64)[lane] : make_uint2(0, 0);   // columns 2*lane, 2*lane+1
+      keys[u] = t < n_tiles ? g.tile_key[t] : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < kCostmapTilesPerWarp; ++u) {
+      if ((cc[u].x | cc[u].y) == 0) continue;
+      int bx, by;
+      unpack_tile_key(keys[u], bx, by);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const uint32_t cnt = k ? cc[u].y : cc[u].x;
+        const int col = 2 * (int)lane + k;
+        if (cnt == 0 || (int)cnt < p.mark_threshold) continue;   // static_cast<int>(count) >= _mark_threshold, :712
+        const int ix = bx * 8 + (col >> 3), iy = by * 8 + (col & 7);
+        unsigned mx, my;
+        if (world_to_map(index_to_world(ix, g.vs, g.half_vs), index_to_world(iy, g.vs, g.half_vs), p, mx, my)) {
+          costmap[(size_t)my * p.size_x + mx] = p.lethal;   // :715
+          ++n; mnx = min(mnx, ix); mny = min(mny, iy); mxx = max(mxx, ix); mxy = max(mxy, iy);   // touch(), :716
+        }
       }
     }
   }
@@ -1233,10 +1247,13 @@ cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, in
   sweep_leaf_kernel<<<grid_for(leaf_slots_upper_bound, kSweepWarps, sm_count * 4), kSweepThreads, dyn, s>>>(g, frustums_dev, n_frustums, now, out);
   return cudaGetLastError();
 }
-cudaError_t launch_costmap(const GridView & g, const CostmapDev & p, uint8_t * costmap_dev, uint32_t tiles_upper_bound, int sm_count, cudaStream_t s)
+cudaError_t launch_costmap(const GridView & g, const CostmapDev & p, uint8_t * costmap_dev, uint32_t tiles_upper_bound, int sm_count, cudaStream_t s,
+                           bool fill_default)
 {
-  cudaError_t e = cudaMemsetAsync(costmap_dev, p.default_value, (size_t)p.size_x * p.size_y, s);   // Costmap2D::resetMaps, :705
-  if (e != cudaSuccess) return e;
+  if (fill_default) {
+    const cudaError_t e = cudaMemsetAsync(costmap_dev, p.default_value, (size_t)p.size_x * p.size_y, s);   // Costmap2D::resetMaps, :705
+    if (e != cudaSuccess) return e;
+  }
   // 64 tiles per CTA (8 per warp): the per-CTA statistics reduction is amortised and the grid stays a fraction of a wave
   costmap_kernel<<<grid_for(tiles_upper_bound, 64, sm_count * 4), 256, 0, s>>>(g, p, costmap_dev);
   return cudaGetLastError();

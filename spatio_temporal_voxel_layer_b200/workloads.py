@@ -81,3 +81,78 @@ class Config2:
         ox, oy = self.scene.lo[:, 0].min() - 1.0, self.scene.lo[:, 1].min() - 1.0
         return dict(origin_x=float(ox), origin_y=float(oy), resolution=res, size_x=size, size_y=size,
                     mark_threshold=0, default_value=0)
+
+
+class Config5:
+    """BASELINE config 5: warehouse map, ~50 M active voxels at 0.02 m (thin vertical rack faces: no solid 8^3 blocks),
+    7 RGBD cameras on the robot (small mark load), linear decay.  The map is built procedurally as disjoint sheets, so the
+    voxel arrays are unique by construction.  `x_range` restricts generation to a spatial slab (multi-GPU shards)."""
+    name = "config5: warehouse ~50M voxels, 0.02 m, 7xRGBD 160x120 mark load, linear decay 15 s"
+    voxel_size = 0.02
+    decay_model = 0
+    voxel_decay = 15.0
+    n_cams = 7
+
+    def __init__(self, target=50_000_000, now0=1.7e9, dt=0.01, seed=1005, ring=4, width=160, height=120,
+                 size_x=200.0, size_y=120.0):
+        self.p = synth.RGBD
+        self.now0, self.dt = now0, dt
+        self.size_x, self.size_y = size_x, size_y
+        self.vs = float(np.float32(self.voxel_size))
+        self.seed = seed
+        self.target = target
+        zlo, zhi = int(math.ceil(0.3 / self.vs)), int(math.floor(2.0 / self.vs))
+        self.z_range = (zlo, zhi)
+        nz = zhi - zlo + 1
+        # rack rows along x, every 3 m in y, two faces per row (0.6 m apart)
+        n_faces = max(2, int(math.ceil(target / ((size_x - 4.0) / self.vs * nz))))
+        self.faces = []
+        y = -size_y / 2 + 2.0
+        while len(self.faces) < n_faces and y < size_y / 2 - 2.0:
+            for dy in (0.0, 0.6):
+                if len(self.faces) < n_faces:
+                    self.faces.append(int(math.floor((y + dy) / self.vs)))
+            y += 3.0
+        self.x_lo, self.x_hi = int(math.floor((-size_x / 2 + 2.0) / self.vs)), int(math.floor((size_x / 2 - 2.0) / self.vs))
+        # robot in the aisle next to a central rack row; clouds from a local box scene
+        yc = self.faces[len(self.faces) // 2] * self.vs
+        boxes = [((-20.0, yc - 0.6, 0.0), (20.0, yc, 2.2)), ((-20.0, yc + 2.4, 0.0), (20.0, yc + 3.0, 2.2))]
+        self.scene = synth.Scene(boxes)
+        self.cycles = []
+        for c in range(ring):
+            centre = (-3.0 + 1.5 * c, yc + 1.2, 0.0)
+            poses = synth.camera_ring(centre, 0.05 + 0.11 * c, n_cams=self.n_cams)
+            clouds = [synth.depth_cloud(self.scene, o, q, width=width, height=height, seed=seed + 16 * c + k)
+                      for k, (o, q) in enumerate(poses)]
+            self.cycles.append(Cycle(0.0, poses, clouds))
+
+    def voxels(self, x_range=None):
+        """(ix, iy, iz, t) of the seeded map, optionally restricted to voxel x indices in [x_range[0], x_range[1])."""
+        xlo, xhi = self.x_lo, self.x_hi + 1
+        if x_range is not None:
+            xlo, xhi = max(xlo, x_range[0]), min(xhi, x_range[1])
+        if xhi <= xlo:
+            z = np.zeros(0, np.int32)
+            return z, z, z, np.zeros(0, np.float64)
+        xs = np.arange(xlo, xhi, dtype=np.int32)
+        zs = np.arange(self.z_range[0], self.z_range[1] + 1, dtype=np.int32)
+        nx, nz, nf = len(xs), len(zs), len(self.faces)
+        ix = np.broadcast_to(xs[None, :, None], (nf, nx, nz)).reshape(-1)
+        iz = np.broadcast_to(zs[None, None, :], (nf, nx, nz)).reshape(-1)
+        iy = np.broadcast_to(np.asarray(self.faces, np.int32)[:, None, None], (nf, nx, nz)).reshape(-1)
+        rng = np.random.default_rng(self.seed)
+        t = self.now0 - rng.uniform(0.0, self.voxel_decay, ix.shape[0])
+        return np.ascontiguousarray(ix), np.ascontiguousarray(iy), np.ascontiguousarray(iz), t
+
+    @property
+    def points_per_cycle(self):
+        return sum(len(c) for c in self.cycles[0].clouds)
+
+    def cycle(self, step):
+        c = self.cycles[step % len(self.cycles)]
+        return self.now0 + self.dt * (step + 1), c.poses, c.clouds
+
+    def costmap_params(self):
+        res = 0.02
+        return dict(origin_x=-self.size_x / 2, origin_y=-self.size_y / 2, resolution=res,
+                    size_x=int(round(self.size_x / res)), size_y=int(round(self.size_y / res)), mark_threshold=0, default_value=0)
