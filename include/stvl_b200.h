@@ -110,7 +110,7 @@ typedef struct stvl_reading {
   double obstacle_range;   /* _obstacle_range_in_m */
   double now;              /* per-reading clock sample (.cpp:275) */
   int32_t marking;         /* _marking truthiness (.cpp:273) */
-  int32_t filter;          /* STVL_FILTER_*; NONE = cloud was filtered upstream already */
+  int32_t filter;          /* STVL_FILTER_*; NONE = cloud was filtered upstream already; PASSTHROUGH / VOXEL run on the device */
   double min_obstacle_height, max_obstacle_height; /* z window of the filter */
   int32_t voxel_min_points; /* VOXEL filter only */
   int32_t reserved;

@@ -17,6 +17,7 @@
 #include "stvl_device.cuh"
 #include "stvl_geometry.h"
 #include "stvl_kernels.h"
+#include "stvl_voxel_filter.h"
 
 using namespace stvl;
 
@@ -78,6 +79,11 @@ struct stvl_grid {
   DevBuf<float> points;
   DevBuf<int32_t> cleared, ambiguous;
   DevBuf<uint8_t> costmap;
+  // VOXEL pre-filter scratch (keys / point indices double-buffered for the radix sort, CUB temp, filtered clouds)
+  DevBuf<unsigned long long> vf_keys_a, vf_keys_b;
+  DevBuf<uint32_t> vf_vals_a, vf_vals_b;
+  DevBuf<uint8_t> vf_temp;
+  DevBuf<float4> vf_out;
   size_t costmap_clean_bytes = 0;     // the internal costmap buffer is already filled with costmap_clean_value ...
   int costmap_clean_value = -1;       // ... over this many bytes (re-armed after every copy-out)
   DevBuf<int32_t> col_ix, col_iy;
@@ -479,15 +485,55 @@ int validate_readings(const stvl_reading_t * readings, uint32_t n)
     if (!r.data) return fail(STVL_ERR_INVALID, "reading %u: data is NULL", i);
     if (r.point_step < 12 || r.off_x + 4 > r.point_step || r.off_y + 4 > r.point_step || r.off_z + 4 > r.point_step)
       return fail(STVL_ERR_INVALID, "reading %u: x/y/z offsets (%u,%u,%u) do not fit point_step %u", i, r.off_x, r.off_y, r.off_z, r.point_step);
-    if (r.filter == STVL_FILTER_VOXEL) return fail(STVL_ERR_INVALID, "reading %u: the VOXEL pre-filter is not fused into Mark yet; filter upstream or use PASSTHROUGH/NONE", i);
-    if (r.filter != STVL_FILTER_NONE && r.filter != STVL_FILTER_PASSTHROUGH) return fail(STVL_ERR_INVALID, "reading %u: unknown filter %d", i, r.filter);
+    if (r.filter != STVL_FILTER_NONE && r.filter != STVL_FILTER_PASSTHROUGH && r.filter != STVL_FILTER_VOXEL) return fail(STVL_ERR_INVALID, "reading %u: unknown filter %d", i, r.filter);
+    if (r.filter == STVL_FILTER_VOXEL && r.n_points > 0x7FFFFFFFull) return fail(STVL_ERR_INVALID, "reading %u: too many points for the VOXEL filter", i);
     if (r.n_points > (1ull << 40)) return fail(STVL_ERR_INVALID, "reading %u: n_points too large", i);
   }
   return STVL_OK;
 }
 
-int run_mark(stvl_grid * g, const stvl_reading_t * readings, uint32_t n, const std::vector<const uint8_t *> & dev_ptrs)
+// VOXEL pre-filter (reference measurement_buffer.cpp:153-164) for the readings that ask for it: each such reading is
+// replaced by its filtered cloud (one float4 slot per input point, see stvl_voxel_filter.cu) before Mark sees it.
+int apply_voxel_filters(stvl_grid * g, std::vector<stvl_reading_t> & rs, std::vector<const uint8_t *> & dev_ptrs)
 {
+  size_t total = 0, max_n = 0;
+  for (const stvl_reading_t & r : rs)
+    if (r.marking && r.n_points && r.filter == STVL_FILTER_VOXEL) { total += (size_t)r.n_points; max_n = std::max<size_t>(max_n, (size_t)r.n_points); }
+  if (total == 0) return STVL_OK;
+  int rc;
+  rc = ensure(g, g->vf_keys_a, max_n); if (rc != STVL_OK) return rc;
+  rc = ensure(g, g->vf_keys_b, max_n); if (rc != STVL_OK) return rc;
+  rc = ensure(g, g->vf_vals_a, max_n); if (rc != STVL_OK) return rc;
+  rc = ensure(g, g->vf_vals_b, max_n); if (rc != STVL_OK) return rc;
+  const size_t temp_bytes = voxel_filter_temp_bytes(max_n);
+  rc = ensure(g, g->vf_temp, temp_bytes + 256); if (rc != STVL_OK) return rc;
+  rc = ensure(g, g->vf_out, total); if (rc != STVL_OK) return rc;
+  size_t off = 0;
+  for (size_t i = 0; i < rs.size(); ++i) {
+    stvl_reading_t & r = rs[i];
+    if (!(r.marking && r.n_points && r.filter == STVL_FILTER_VOXEL)) continue;
+    CU(launch_voxel_filter(dev_ptrs[i], r.n_points, r.point_step, r.off_x, r.off_y, r.off_z, g->cfg.voxel_size,
+                           r.min_obstacle_height, r.max_obstacle_height, r.voxel_min_points, r.origin,
+                           g->vf_keys_a.p, g->vf_keys_b.p, g->vf_vals_a.p, g->vf_vals_b.p, g->vf_temp.p, temp_bytes,
+                           g->vf_out.p + off, g->stream));
+    g->launches += 3;
+    dev_ptrs[i] = reinterpret_cast<const uint8_t *>(g->vf_out.p + off);
+    r.point_step = 16; r.off_x = 0; r.off_y = 4; r.off_z = 8;
+    r.filter = STVL_FILTER_NONE;   // the z window was applied by the filter
+    off += (size_t)r.n_points;
+  }
+  return STVL_OK;
+}
+
+int run_mark(stvl_grid * g, const stvl_reading_t * readings_in, uint32_t n, const std::vector<const uint8_t *> & dev_ptrs_in)
+{
+  std::vector<stvl_reading_t> rs(readings_in, readings_in + n);
+  std::vector<const uint8_t *> dev_ptrs(dev_ptrs_in);
+  {
+    const int rc = apply_voxel_filters(g, rs, dev_ptrs);
+    if (rc != STVL_OK) return rc;
+  }
+  const stvl_reading_t * readings = rs.data();
   std::vector<MarkBatch> batches;
   uint64_t total_points = 0;
   double max_now = 0;
@@ -654,6 +700,7 @@ int stvl_destroy(stvl_grid_t * g)
   cudaFree(g->stage.p); cudaFree(g->frustums.p); cudaFree(g->points.p); cudaFree(g->cleared.p); cudaFree(g->ambiguous.p);
   cudaFree(g->costmap.p); cudaFree(g->col_ix.p); cudaFree(g->col_iy.p); cudaFree(g->col_cnt.p);
   cudaFree(g->dump_x.p); cudaFree(g->dump_y.p); cudaFree(g->dump_z.p); cudaFree(g->dump_t.p);
+  cudaFree(g->vf_keys_a.p); cudaFree(g->vf_keys_b.p); cudaFree(g->vf_vals_a.p); cudaFree(g->vf_vals_b.p); cudaFree(g->vf_temp.p); cudaFree(g->vf_out.p);
   if (g->h_ctr) cudaFreeHost(g->h_ctr);
   for (int i = 0; i < stvl_grid::kFrustumRing; ++i) {
     if (g->h_frustums[i]) cudaFreeHost(g->h_frustums[i]);

@@ -393,3 +393,35 @@ def test_sharded_grids_union_equals_single(stvl, oracle):
     assert r.n_marked_columns == on
     for g in shards:
         g.close()
+
+
+@pytest.mark.parametrize("vs,min_points", [(0.05, 0), (0.05, 3), (0.02, 1)])
+def test_voxel_filter_then_mark(stvl, oracle, vs, min_points):
+    """Config 4: the VOXEL pre-filter of BufferROSCloud (PCL VoxelGrid, reference measurement_buffer.cpp:153-164) on the
+    device, then Mark.  Centroids are float sums in ascending point order (the oracle's definition), so the resulting
+    voxel sets and mark times are bit-exact."""
+    import spatio_temporal_voxel_layer_b200.synth as synth
+    rng = np.random.default_rng(31)
+    scene = synth.retail_scene(size=20.0, seed=9)
+    o, q = (0.3, 0.8, 0.7), synth.optical_quat(0.9)
+    cloud = synth.depth_cloud(scene, o, q, width=320, height=240, seed=5)           # organised, with NaN misses
+    lid = synth.lidar_cloud(scene, (0.3, 0.8, 0.9), synth.yaw_quat(0.2), rings=32, azimuths=1024, vfov=0.6, seed=6)
+    extra = np.zeros((4000, 4), np.float32); extra[:, :3] = rng.uniform(-2.5, 2.5, (4000, 3))
+    gg = stvl.SpatioTemporalVoxelGrid(vs)
+    og = oracle.OracleGrid(vs)
+    leaf = np.float32(vs)
+    for k, (c, origin, zl) in enumerate(((cloud, o, (0.3, 2.0)), (lid, (0.3, 0.8, 0.9), (0.1, 2.2)), (extra, (0.0, 0.0, 0.5), (-1.0, 1.5)))):
+        now = 77.0 + k
+        r = stvl.MeasurementReading(c, origin=origin, obstacle_range=4.0, now=now, filter=stvl.FILTER_VOXEL,
+                                    min_obstacle_height=zl[0], max_obstacle_height=zl[1])
+        arr = (stvl.Reading * 1)()
+        keep = []
+        r._fill(arr[0], now, keep)
+        arr[0].voxel_min_points = min_points
+        stvl._check(gg.L.stvl_mark(gg.h, arr, 1))
+        cent = oracle.filter_voxel(c, leaf, zl[0], zl[1], min_points)
+        og.mark(cent, origin, 4.0, now)
+    assert og.active_count() > 500
+    assert_same_voxels(gg.voxels(), og.voxels())
+    assert gg.pool_stats().points_dropped_nonfinite == 0     # filtered slots carry the sensor origin, not NaN
+    gg.close()
