@@ -425,3 +425,41 @@ def test_voxel_filter_then_mark(stvl, oracle, vs, min_points):
     assert_same_voxels(gg.voxels(), og.voxels())
     assert gg.pool_stats().points_dropped_nonfinite == 0     # filtered slots carry the sensor origin, not NaN
     gg.close()
+
+
+def test_config2_full_size_parity_and_properties(stvl, oracle):
+    """BASELINE config 2 at FULL size (7 x 640x480 clouds = 2,150,400 points per cycle, 710,765 seeded voxels): two complete
+    cycles bit-compared with the oracle, plus size-independent properties: sweep conservation, Mark idempotence."""
+    from spatio_temporal_voxel_layer_b200 import workloads
+    w = workloads.Config2(n_poses=1, ring=2)
+    p = w.p
+    assert w.points_per_cycle == 7 * 640 * 480 and len(w.seed_vox[0]) == workloads.RETAIL_VOXELS
+    gg = stvl.SpatioTemporalVoxelGrid(0.05, 0.0, 0, 15.0, leaf_capacity=1 << 16)
+    og = oracle.OracleGrid(0.05, 0.0, 0, 15.0, False)
+    gg.load_voxels(*w.seed_vox, w.seed_t)
+    og.load_voxels(*w.seed_vox, w.seed_t)
+    cp = w.costmap_params()
+    for step in range(2):
+        now, poses, clouds = w.cycle(step * 40)      # 0.4 s apart so that voxels expire between the cycles
+        rs = [stvl.MeasurementReading(c, origin=o, orientation=q, obstacle_range=p["obstacle_range"], min_z=p["min_z"],
+                                      max_z=p["max_z"], vfov=p["vfov"], hfov=p["hfov"], decay_acceleration=p["accel"],
+                                      now=now + 1e-4 * k, filter=stvl.FILTER_PASSTHROUGH,
+                                      min_obstacle_height=p["min_obstacle_height"], max_obstacle_height=p["max_obstacle_height"])
+              for k, ((o, q), c) in enumerate(zip(poses, clouds))]
+        gg.ClearFrustums(rs, now)
+        og.clear_frustums(now, oracle_frustums(oracle, rs))
+        st = gg.sweep_stats()
+        assert st.n_swept == st.n_survived + st.n_cleared and st.n_ambiguous == 0
+        gg.Mark(rs)
+        for r in rs:
+            oracle_mark(oracle, og, r, now)
+        cm, res = gg.UpdateROSCostmap(cp["origin_x"], cp["origin_y"], cp["resolution"], cp["size_x"], cp["size_y"], 0, 0)
+        ocm, ob, on = og.update_ros_costmap(cp["origin_x"], cp["origin_y"], cp["resolution"], cp["size_x"], cp["size_y"], 0, 0)
+        assert np.array_equal(cm, ocm) and res.n_marked_columns == on
+    assert_same_voxels(gg.voxels(), og.voxels())
+    # Mark is idempotent: the same readings again change nothing
+    before = gg.voxels()
+    gg.Mark(rs)
+    assert_same_voxels(gg.voxels(), before)
+    assert st.n_swept > 600000 and st.n_cleared > 100 and st.n_rewritten > 100
+    gg.close()
