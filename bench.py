@@ -219,13 +219,6 @@ def bench_ours(args):
     bytes_h2d = sum(c.numel() * 4 for c in host_clouds[0]) + 7 * 304
     bytes_d2h = cp["size_x"] * cp["size_y"] + 256
 
-    # dense column-count window for the multi-GPU merge (voxel-column index space)
-    if world > 1:
-        from spatio_temporal_voxel_layer_b200 import sharding
-        ix0, iy0, nx, ny = sharding.dense_window(cp["origin_x"], cp["origin_y"], cp["resolution"], cp["size_x"], cp["size_y"],
-                                                 w.voxel_size)
-        dense = torch.zeros((ny, nx), dtype=torch.int32, device="cuda")
-
     # per ring slot: the C-ABI argument arrays are built once; a step only refreshes the clock samples
     def build_args(src):
         out = []
@@ -253,20 +246,22 @@ def bench_ours(args):
         check(L.stvl_clear_frustums(h, now, fr_ptrs[slot], n_cams))
         return arr
 
-    def merge_and_write(sync_result):
-        """N>1: column counts -> dense window -> NCCL reduce over NVLink -> rank 0 thresholds into bytes.  Everything is
-        enqueued in order on the library's stream (torch's current stream inside this block): no host synchronisation."""
-        with torch.cuda.stream(stream):
-            dense.zero_()
-            g.columns_to_dense(ix0, iy0, nx, ny, dense.data_ptr())
-            sharding.merge_counts(dist, dense, dst=0)
-            if rank == 0:
-                return g.costmap_from_dense(dense.data_ptr(), ix0, iy0, nx, ny, params, costmap_dev.data_ptr(), sync=sync_result)
-        return None
-
-
     params_ref = C.byref(params)
     cm_dev_ptr, cm_host_ptr = costmap_dev.data_ptr(), costmap_host.data_ptr()
+    if world > 1:   # one NCCL communicator per handle, id created by rank 0
+        uid = [stvl.SpatioTemporalVoxelGrid.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        g.comm_init(uid[0], rank, world)
+
+    def merge_pipelined():
+        """Device-resident leg, N>1: the library scatters this rank's column counts into a u8 window, reduces it to rank 0 with
+        NCCL on a side stream while its main stream already sweeps and marks the next cycle (column tiles are double-buffered),
+        and rank 0 thresholds cycle k's merged counts with call k+1.  Enqueue only."""
+        check(L.stvl_costmap_sharded_device(h, params_ref, cm_dev_ptr, 0, 1, 1))
+
+    def merge_drain():
+        check(L.stvl_costmap_sharded_flush(h, params_ref, cm_dev_ptr, 0))
+
 
     def step_device(step, timed):
         """One cycle with device-resident clouds.  N=1: ONE C-ABI call (stvl_update_cycle_device) enqueues clear -> mark ->
@@ -281,7 +276,7 @@ def bench_ours(args):
         else:
             arr = enqueue_clear_mark(step, True)
             check(L.stvl_mark_device(h, arr, n_cams))
-            merge_and_write(False)
+            merge_pipelined()
 
     def step_host(step):
         arr = enqueue_clear_mark(step, False)
@@ -290,7 +285,8 @@ def bench_ours(args):
             res = stvl.CostmapResult()
             check(L.stvl_costmap(h, params_ref, cm_host_ptr, C.byref(res)))
             return res
-        res = merge_and_write(True)
+        check(L.stvl_costmap_sharded_device(h, params_ref, cm_dev_ptr, 0, 1, 0))   # blocking merge: this cycle's bytes
+        res = None
         if rank == 0:
             with torch.cuda.stream(stream):
                 costmap_host.copy_(costmap_dev, non_blocking=True)
@@ -322,6 +318,8 @@ def bench_ours(args):
     e0.record(stream)
     for _ in range(args.steps):
         step_device(step_no, True); step_no += 1
+    if world > 1:
+        merge_drain()                      # the last cycle's bytes are part of the timed region
     e1.record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -338,6 +336,9 @@ def bench_ours(args):
     st = g.sweep_stats()
     active = g.active_count()
 
+    if world > 1:
+        merge_drain()
+    barrier()
     # ---- e2e leg: host clouds in, host costmap bytes out ---------------------------------------------------------------
     for _ in range(args.warmup):
         step_host(step_no); step_no += 1
@@ -367,7 +368,7 @@ def bench_ours(args):
                        "l2_policy": "inputs larger than L2: ring of %d distinct cycles x %.1f MB of clouds; leaf pool %.1f GB" % (
                            ring, w.points_per_cycle * 16 / 1e6, g.pool_stats().device_bytes / 1e9),
                        "costmap_cells": cp["size_x"] * cp["size_y"],
-                       "parallelism": "1 GPU" if world == 1 else "%d spatial x-slab shards + NCCL reduce of column counts" % world},
+                       "parallelism": "1 GPU" if world == 1 else "%d spatial x-slab shards + in-library NCCL reduce of the u8 column-count window, pipelined one cycle behind on a side stream" % world},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": bytes_h2d, "d2h_bytes_per_step": bytes_d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -405,7 +406,9 @@ def bench_ours(args):
     # still alive (the caching allocator records events on it), then the process group, then the grid
     barrier()
     if world > 1:
-        del dense
+        merge_drain()
+        torch.cuda.synchronize()
+        g.comm_destroy()
     del costmap_dev, costmap_host, dev_clouds, host_clouds
     torch.cuda.synchronize()
     torch.cuda.empty_cache()

@@ -91,9 +91,10 @@ def main():
     params = stvl.CostmapParams(cp["origin_x"], cp["origin_y"], cp["resolution"], cp["size_x"], cp["size_y"], 0, 0, 254)
     costmap_dev = torch.zeros((cp["size_y"], cp["size_x"]), dtype=torch.uint8, device="cuda")
     stream = torch.cuda.ExternalStream(g.stream())
-    if world > 1:
-        wx0, wy0, nx, ny = sharding.dense_window(cp["origin_x"], cp["origin_y"], cp["resolution"], cp["size_x"], cp["size_y"], w.voxel_size)
-        dense = torch.zeros((ny, nx), dtype=torch.int32, device="cuda")
+    if world > 1:   # in-library NCCL merge: one communicator per handle, id from rank 0
+        uid = [stvl.SpatioTemporalVoxelGrid.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        g.comm_init(uid[0], rank, world)
     L, h = g.L, g.h
     fr_ptrs = [f.ctypes.data_as(C.c_void_p) for f in frustums]
 
@@ -108,12 +109,8 @@ def main():
         else:
             stvl._check(L.stvl_clear_frustums(h, now, fr_ptrs[slot], w.n_cams))
             stvl._check(L.stvl_mark_device(h, arr, w.n_cams))
-            with torch.cuda.stream(stream):
-                dense.zero_()
-                g.columns_to_dense(wx0, wy0, nx, ny, dense.data_ptr())
-                sharding.merge_counts(dist, dense, dst=0)
-                if rank == 0:
-                    g.costmap_from_dense(dense.data_ptr(), wx0, wy0, nx, ny, params, costmap_dev.data_ptr(), sync=False)
+            # u8 column-count window, reduce pipelined one cycle behind on the library's side stream
+            stvl._check(L.stvl_costmap_sharded_device(h, C.byref(params), costmap_dev.data_ptr(), 0, 1, 1))
 
     def barrier():
         g.synchronize(); torch.cuda.synchronize()
@@ -131,6 +128,8 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         cycle(n); n += 1
+    if world > 1:
+        stvl._check(L.stvl_costmap_sharded_flush(h, C.byref(params), costmap_dev.data_ptr(), 0))
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -163,7 +162,7 @@ def main():
         print(json.dumps(line))
     barrier()
     if world > 1:
-        del dense
+        g.comm_destroy()
     del costmap_dev, dev_clouds
     torch.cuda.synchronize()
     torch.cuda.empty_cache()

@@ -240,6 +240,23 @@ int stvl_columns_to_dense(stvl_grid_t * g, int32_t ix0, int32_t iy0, uint32_t nx
 int stvl_costmap_from_dense(stvl_grid_t * g, const uint32_t * dense_dev, int32_t ix0, int32_t iy0, uint32_t nx, uint32_t ny,
                             const stvl_costmap_params_t * p, uint8_t * costmap_dev, stvl_costmap_result_t * res);
 
+/* In-library variant of the same merge (what the C++ host side uses): NCCL is loaded at run time (dlopen of
+ * libnccl.so.2 — the copy already in the process when one is, e.g. torch's) and the reduce runs on a side stream.
+ *   stvl_nccl_unique_id : rank 0 creates the id; the caller ships its 128 bytes to the other ranks (any channel)
+ *   stvl_comm_init      : collective; one communicator per handle
+ *   stvl_costmap_sharded_device : scatter this rank's column counts into a window over the costmap (count_bytes 1 or 4
+ *       per cell; 1 saturates at 255 and is exact for disjoint shards / thresholds <= 255), ncclReduce(sum) to `root`,
+ *       root thresholds into costmap_dev (same rule as stvl_costmap).  pipelined == 0: everything of THIS cycle, in stream
+ *       order.  pipelined == 1: the reduce of this call overlaps the next cycle's sweep and Mark (the column tiles are
+ *       double-buffered), and root writes the bytes of the PREVIOUS call; stvl_costmap_sharded_flush writes the last ones.
+ * All enqueue-only (no host synchronisation). */
+int stvl_nccl_unique_id(uint8_t id[128]);
+int stvl_comm_init(stvl_grid_t * g, const uint8_t id[128], int rank, int n_ranks);
+int stvl_comm_destroy(stvl_grid_t * g);
+int stvl_costmap_sharded_device(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_t * costmap_dev, int root,
+                                int count_bytes, int pipelined);
+int stvl_costmap_sharded_flush(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_t * costmap_dev, int root);
+
 /* ---- diagnostics ---------------------------------------------------------- */
 typedef struct stvl_pool_stats {
   uint64_t leaf_capacity, leaves_in_use, leaves_free, hash_capacity, hash_tombstones;

@@ -89,6 +89,7 @@ EXPORTED_SYMBOLS = [
     "stvl_get_voxels", "stvl_load_voxels", "stvl_index_to_world", "stvl_voxel_size", "stvl_columns_to_dense",
     "stvl_costmap_from_dense", "stvl_get_pool_stats", "stvl_get_stream", "stvl_synchronize",
     "stvl_update_cycle_device", "stvl_enable_timing", "stvl_get_timing",
+    "stvl_nccl_unique_id", "stvl_comm_init", "stvl_comm_destroy", "stvl_costmap_sharded_device", "stvl_costmap_sharded_flush",
 ]
 
 _lib = None
@@ -146,6 +147,11 @@ def load_library(build_if_missing=True):
     L.stvl_update_cycle_device.argtypes = [vp, d, vp, u32, C.POINTER(Reading), u32, C.POINTER(CostmapParams), vp]
     L.stvl_enable_timing.argtypes = [vp, u32]
     L.stvl_get_timing.argtypes = [vp, C.POINTER(Timing)]
+    L.stvl_nccl_unique_id.argtypes = [vp]
+    L.stvl_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.stvl_comm_destroy.argtypes = [vp]
+    L.stvl_costmap_sharded_device.argtypes = [vp, C.POINTER(CostmapParams), vp, C.c_int, C.c_int, C.c_int]
+    L.stvl_costmap_sharded_flush.argtypes = [vp, C.POINTER(CostmapParams), vp, C.c_int]
     _lib = L
     return L
 
@@ -382,6 +388,26 @@ class SpatioTemporalVoxelGrid:
 
     def synchronize(self):
         _check(self.L.stvl_synchronize(self.h))
+
+    # ---- in-library NCCL merge of the sharded column counts -------------------------------------------------------
+    @staticmethod
+    def nccl_unique_id():
+        buf = (C.c_uint8 * 128)()
+        _check(load_library().stvl_nccl_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, n_ranks):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(self.L.stvl_comm_init(self.h, buf, rank, n_ranks))
+
+    def comm_destroy(self):
+        _check(self.L.stvl_comm_destroy(self.h))
+
+    def costmap_sharded_device(self, params, costmap_dev_ptr, root=0, count_bytes=4, pipelined=False):
+        _check(self.L.stvl_costmap_sharded_device(self.h, C.byref(params), costmap_dev_ptr, root, count_bytes, int(pipelined)))
+
+    def costmap_sharded_flush(self, params, costmap_dev_ptr, root=0):
+        _check(self.L.stvl_costmap_sharded_flush(self.h, C.byref(params), costmap_dev_ptr, root))
 
     def enable_timing(self, mask):
         _check(self.L.stvl_enable_timing(self.h, mask))

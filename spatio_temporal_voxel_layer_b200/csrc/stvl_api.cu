@@ -13,6 +13,9 @@
 #include <new>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the symbols are resolved with dlopen at run time
+
 #include "stvl_b200.h"
 #include "stvl_device.cuh"
 #include "stvl_geometry.h"
@@ -107,6 +110,16 @@ struct stvl_grid {
   bool alloc_dirty = false;         // a Mark / load kernel handed out leaves that are not folded into the allocator yet
   uint64_t launches = 0;
   size_t device_bytes = 0;
+  // in-library sharded merge (stvl_comm_init / stvl_costmap_sharded_device)
+  ncclComm_t comm = nullptr;
+  int comm_rank = 0, comm_n = 1;
+  cudaStream_t merge_stream = nullptr;
+  cudaEvent_t ev_scatter[2] = {nullptr, nullptr}, ev_reduce[2] = {nullptr, nullptr};
+  DevBuf<uint8_t> window[2];
+  uint64_t win_k = 0;
+  int win_pending = -1;                 // window whose reduce is in flight and not thresholded yet
+  int win_geom[4] = {0, 0, 0, 0};       // ix0, iy0, nx, ny of the pending window
+  int win_count_bytes = 4;
   // optional per-stage timing (stvl_enable_timing)
   uint32_t timing_mask = 0;
   struct TimedInterval { cudaEvent_t a, b; int stage; };
@@ -602,6 +615,66 @@ void fill_costmap_result(const stvl_grid * g, stvl_costmap_result_t * res)
 
 }  // namespace
 
+// ---- NCCL, loaded at run time -------------------------------------------------------------------------------------------
+struct NcclApi {
+  void * lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char * (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi * nccl_api()
+{
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    // prefer the copy that is already in the process (e.g. the one torch bundles), else the system library
+    api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!api.lib) api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) {
+      api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.lib, "ncclGetUniqueId"));
+      api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.lib, "ncclCommInitRank"));
+      api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
+      api.Reduce = reinterpret_cast<decltype(api.Reduce)>(dlsym(api.lib, "ncclReduce"));
+      api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
+      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Reduce && api.GetErrorString;
+    }
+  }
+  return api.ok ? &api : nullptr;
+}
+#define NC(expr)                                                                                        \
+  do {                                                                                                  \
+    ncclResult_t r__ = (expr);                                                                          \
+    if (r__ != ncclSuccess) return fail(STVL_ERR_CUDA, "%s: %s", #expr, nccl_api()->GetErrorString(r__)); \
+  } while (0)
+
+// voxel-column window that covers every column whose centre can map into the costmap (same rule as sharding.dense_window)
+void window_geometry(const stvl_grid * g, const stvl_costmap_params_t & p, int geom[4])
+{
+  geom[0] = (int)std::floor(p.origin_x / g->vs) - 2;
+  geom[1] = (int)std::floor(p.origin_y / g->vs) - 2;
+  geom[2] = (int)std::ceil(p.size_x * p.resolution / g->vs) + 5;
+  geom[3] = (int)std::ceil(p.size_y * p.resolution / g->vs) + 5;
+}
+
+// root: threshold the reduced window `b` into costmap bytes once its reduce has finished
+int threshold_window(stvl_grid * g, int b, const stvl_costmap_params_t & p, uint8_t * costmap_dev, int root)
+{
+  CU(cudaStreamWaitEvent(g->stream, g->ev_reduce[b], 0));
+  if (g->comm_rank == root && costmap_dev) {
+    StageTimer timer__(g, STVL_TIME_COSTMAP);
+    CU(launch_costmap_from_window(g->v, g->window[b].p, g->win_count_bytes, g->win_geom[0], g->win_geom[1], (uint32_t)g->win_geom[2],
+                                  (uint32_t)g->win_geom[3], to_dev(p), costmap_dev, g->sm_count, g->stream));
+    g->launches += 1;
+    g->counters_fresh = false;
+  }
+  return STVL_OK;
+}
+
 // =====================================================================================
 extern "C" {
 
@@ -694,6 +767,8 @@ int stvl_destroy(stvl_grid_t * g)
   DeviceGuard guard(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
   if (g->copy_stream) cudaStreamSynchronize(g->copy_stream);
+  if (g->comm) stvl_comm_destroy(g);
+  cudaFree(g->window[0].p); cudaFree(g->window[1].p);
   free_pool(g->v);
   free_tiles(g->v);
   cudaFree(g->v.ctr);
@@ -1135,6 +1210,115 @@ int stvl_costmap_from_dense(stvl_grid_t * g, const uint32_t * dense_dev, int32_t
   if (rc != STVL_OK) return rc;
   fill_costmap_result(g, res);
   return after_fetch(g);
+}
+
+int stvl_nccl_unique_id(uint8_t id[128])
+{
+  if (!id) return fail(STVL_ERR_INVALID, "id is NULL");
+  NcclApi * n = nccl_api();
+  if (!n) return fail(STVL_ERR_INVALID, "libnccl.so.2 could not be loaded");
+  ncclUniqueId u;
+  NC(n->GetUniqueId(&u));
+  static_assert(sizeof(u) == 128, "ncclUniqueId size");
+  std::memcpy(id, &u, 128);
+  return STVL_OK;
+}
+
+int stvl_comm_init(stvl_grid_t * g, const uint8_t id[128], int rank, int n_ranks)
+{
+  ENTER(g);
+  if (!id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(STVL_ERR_INVALID, "bad communicator arguments");
+  NcclApi * n = nccl_api();
+  if (!n) return fail(STVL_ERR_INVALID, "libnccl.so.2 could not be loaded");
+  if (g->comm) return fail(STVL_ERR_INVALID, "communicator already initialised");
+  ncclUniqueId u;
+  std::memcpy(&u, id, 128);
+  NC(n->CommInitRank(&g->comm, n_ranks, u, rank));
+  g->comm_rank = rank; g->comm_n = n_ranks;
+  CU(cudaStreamCreateWithFlags(&g->merge_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; ++k) {
+    CU(cudaEventCreateWithFlags(&g->ev_scatter[k], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&g->ev_reduce[k], cudaEventDisableTiming));
+  }
+  return STVL_OK;
+}
+
+int stvl_comm_destroy(stvl_grid_t * g)
+{
+  ENTER(g);
+  if (!g->comm) return STVL_OK;
+  CU(cudaStreamSynchronize(g->stream));
+  CU(cudaStreamSynchronize(g->merge_stream));
+  nccl_api()->CommDestroy(g->comm);
+  g->comm = nullptr;
+  for (int k = 0; k < 2; ++k) { cudaEventDestroy(g->ev_scatter[k]); cudaEventDestroy(g->ev_reduce[k]); g->ev_scatter[k] = g->ev_reduce[k] = nullptr; }
+  cudaStreamDestroy(g->merge_stream);
+  g->merge_stream = nullptr;
+  g->win_pending = -1;
+  return STVL_OK;
+}
+
+int stvl_costmap_sharded_device(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_t * costmap_dev, int root,
+                                int count_bytes, int pipelined)
+{
+  ENTER(g);
+  if (!p) return fail(STVL_ERR_INVALID, "NULL argument");
+  if (!g->comm) return fail(STVL_ERR_INVALID, "stvl_comm_init has not been called");
+  if (count_bytes != 1 && count_bytes != 4) return fail(STVL_ERR_INVALID, "count_bytes must be 1 or 4");
+  if (root < 0 || root >= g->comm_n) return fail(STVL_ERR_INVALID, "bad root");
+  if (!(p->resolution > 0)) return fail(STVL_ERR_INVALID, "resolution must be positive");
+  int geom[4];
+  window_geometry(g, *p, geom);
+  const size_t cells = (size_t)geom[2] * geom[3];
+  if (g->win_pending >= 0 && (count_bytes != g->win_count_bytes || std::memcmp(geom, g->win_geom, sizeof(geom)) != 0)) {
+    // the costmap moved or changed size while a window was in flight: finish that one first
+    int rc = stvl_costmap_sharded_flush(g, p, nullptr, root);
+    if (rc != STVL_OK) return rc;
+  }
+  const int b = (int)(g->win_k & 1);
+  if (g->window[b].cap < cells * (size_t)count_bytes) {
+    CU(cudaStreamSynchronize(g->merge_stream));
+    int rc = ensure(g, g->window[b], cells * (size_t)count_bytes);
+    if (rc != STVL_OK) return rc;
+  }
+  std::memcpy(g->win_geom, geom, sizeof(geom));
+  g->win_count_bytes = count_bytes;
+  // the reduce that used this window two calls ago must be done before it is overwritten
+  CU(cudaStreamWaitEvent(g->stream, g->ev_reduce[b], 0));
+  CU(launch_columns_to_window(g->v, geom[0], geom[1], (uint32_t)geom[2], (uint32_t)geom[3], g->window[b].p, count_bytes,
+                              tiles_upper(g), g->sm_count, g->stream));
+  g->launches += 1;
+  CU(cudaEventRecord(g->ev_scatter[b], g->stream));
+  NcclApi * n = nccl_api();
+  const ncclDataType_t dt = count_bytes == 1 ? ncclUint8 : ncclUint32;
+  g->win_k += 1;
+  if (!pipelined) {
+    if (g->win_pending >= 0) { int rc = threshold_window(g, g->win_pending, *p, nullptr, root); if (rc != STVL_OK) return rc; g->win_pending = -1; }
+    NC(n->Reduce(g->window[b].p, g->window[b].p, cells, dt, ncclSum, root, g->comm, g->stream));
+    CU(cudaEventRecord(g->ev_reduce[b], g->stream));
+    return threshold_window(g, b, *p, costmap_dev, root);
+  }
+  // pipelined: the reduce runs on the side stream behind the scatter; the library's stream goes on with the next cycle
+  CU(cudaStreamWaitEvent(g->merge_stream, g->ev_scatter[b], 0));
+  NC(n->Reduce(g->window[b].p, g->window[b].p, cells, dt, ncclSum, root, g->comm, g->merge_stream));
+  CU(cudaEventRecord(g->ev_reduce[b], g->merge_stream));
+  if (g->win_pending >= 0) {
+    int rc = threshold_window(g, g->win_pending, *p, costmap_dev, root);   // the PREVIOUS call's bytes
+    if (rc != STVL_OK) return rc;
+  }
+  g->win_pending = b;
+  return STVL_OK;
+}
+
+int stvl_costmap_sharded_flush(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_t * costmap_dev, int root)
+{
+  ENTER(g);
+  if (!p) return fail(STVL_ERR_INVALID, "NULL argument");
+  if (!g->comm) return fail(STVL_ERR_INVALID, "stvl_comm_init has not been called");
+  if (g->win_pending < 0) return STVL_OK;
+  const int b = g->win_pending;
+  g->win_pending = -1;
+  return threshold_window(g, b, *p, costmap_dev, root);
 }
 
 int stvl_get_pool_stats(stvl_grid_t * g, stvl_pool_stats_t * out)

@@ -39,6 +39,10 @@ cudaError_t launch_columns_to_dense(const GridView & g, int ix0, int iy0, uint32
                                     uint32_t tiles_upper_bound, int sm_count, cudaStream_t s);
 cudaError_t launch_costmap_from_dense(const GridView & g, const uint32_t * dense, int ix0, int iy0, uint32_t nx, uint32_t ny,
                                       const CostmapDev & p, uint8_t * costmap_dev, int sm_count, cudaStream_t s);
+cudaError_t launch_columns_to_window(const GridView & g, int ix0, int iy0, uint32_t nx, uint32_t ny, void * win, int count_bytes,
+                                     uint32_t tiles_upper_bound, int sm_count, cudaStream_t s);
+cudaError_t launch_costmap_from_window(const GridView & g, const void * win, int count_bytes, int ix0, int iy0, uint32_t nx, uint32_t ny,
+                                       const CostmapDev & p, uint8_t * costmap_dev, int sm_count, cudaStream_t s);
 cudaError_t launch_reset_area(const GridView & g, double sx, double sy, double ex, double ey, int invert,
                               uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s);
 cudaError_t launch_count_active(const GridView & g, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s);

@@ -1,0 +1,76 @@
+"""Run under torchrun on >= 2 GPUs (tests/test_multi_gpu.py launches it): the in-library NCCL merge of spatially sharded
+grids must reproduce the costmap bytes of one unsharded grid — u32 and u8 count windows, blocking and pipelined."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import spatio_temporal_voxel_layer_b200 as stvl  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    rng = np.random.default_rng(77)
+    vox = np.unique(rng.integers(-300, 300, (250000, 3)), axis=0)
+    vox[:, 2] = vox[:, 2] % 20
+    vox = np.unique(vox, axis=0)
+    size, res, ox, oy = 640, 0.05, -16.0, -16.0
+    params = stvl.CostmapParams(ox, oy, res, size, size, 2, 0, 254)
+
+    g = stvl.SpatioTemporalVoxelGrid(0.05, voxel_decay=15.0, shard_index=rank, shard_count=world, shard_width=6)
+    uid = [stvl.SpatioTemporalVoxelGrid.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    g.comm_init(uid[0], rank, world)
+    ref = stvl.SpatioTemporalVoxelGrid(0.05, voxel_decay=15.0) if rank == 0 else None
+    cm = torch.zeros((size, size), dtype=torch.uint8, device="cuda")
+    cm_ref = torch.zeros((size, size), dtype=torch.uint8, device="cuda")
+    now = 100.0
+    ok = True
+    expected = []
+    for cyc in range(4):
+        t = now - rng.uniform(0, 20, len(vox))            # same stream of random numbers on every rank
+        g.ResetGrid(); g.load_voxels(vox[:, 0], vox[:, 1], vox[:, 2], t)
+        g.ClearFrustums([], now)
+        if rank == 0:
+            ref.ResetGrid(); ref.load_voxels(vox[:, 0], vox[:, 1], vox[:, 2], t)
+            ref.ClearFrustums([], now)
+            ref.costmap_device(params, cm_ref.data_ptr())
+            ref.synchronize()
+            expected.append(cm_ref.clone())
+        if cyc < 2:   # blocking merge, u32 then u8 windows
+            g.costmap_sharded_device(params, cm.data_ptr(), root=0, count_bytes=4 if cyc == 0 else 1, pipelined=False)
+            g.synchronize()
+            if rank == 0:
+                ok = ok and torch.equal(cm, expected[cyc]) and int((cm == 254).sum()) > 1000
+        else:          # pipelined: the bytes of cycle k arrive with call k+1 (or the flush)
+            g.costmap_sharded_device(params, cm.data_ptr(), root=0, count_bytes=1, pipelined=True)
+            g.synchronize()
+            if rank == 0 and cyc == 3:
+                ok = ok and torch.equal(cm, expected[2])
+        now += 1.0
+    g.costmap_sharded_flush(params, cm.data_ptr(), root=0)
+    g.synchronize()
+    if rank == 0:
+        ok = ok and torch.equal(cm, expected[3])
+    n_local = torch.tensor([g.active_count()], device="cuda")
+    dist.all_reduce(n_local)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    if rank == 0:
+        print("MULTI_GPU_OK" if bool(flag.item()) else "MULTI_GPU_MISMATCH", "ranks", world, "voxels", int(n_local.item()))
+    g.comm_destroy()
+    g.close()
+    if ref is not None:
+        ref.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
