@@ -254,10 +254,10 @@ def bench_ours(args):
         g.comm_init(uid[0], rank, world)
 
     def merge_pipelined():
-        """Device-resident leg, N>1: the library scatters this rank's column counts into a u8 window, reduces it to rank 0 with
-        NCCL on a side stream while its main stream already sweeps and marks the next cycle (column tiles are double-buffered),
+        """Device-resident leg, N>1: every rank thresholds its own voxel columns (x-slab shards own whole columns) and the library reduces the
+        {0, lethal} bytes to rank 0 with NCCL (max) on a side stream while its main stream already sweeps and marks the next cycle (column tiles are double-buffered),
         and rank 0 thresholds cycle k's merged counts with call k+1.  Enqueue only."""
-        check(L.stvl_costmap_sharded_device(h, params_ref, cm_dev_ptr, 0, 1, 1))
+        check(L.stvl_costmap_sharded_device(h, params_ref, cm_dev_ptr, 0, 0, 1))
 
     def merge_drain():
         check(L.stvl_costmap_sharded_flush(h, params_ref, cm_dev_ptr, 0))
@@ -285,7 +285,7 @@ def bench_ours(args):
             res = stvl.CostmapResult()
             check(L.stvl_costmap(h, params_ref, cm_host_ptr, C.byref(res)))
             return res
-        check(L.stvl_costmap_sharded_device(h, params_ref, cm_dev_ptr, 0, 1, 0))   # blocking merge: this cycle's bytes
+        check(L.stvl_costmap_sharded_device(h, params_ref, cm_dev_ptr, 0, 0, 0))   # blocking merge: this cycle's bytes
         res = None
         if rank == 0:
             with torch.cuda.stream(stream):
@@ -368,7 +368,7 @@ def bench_ours(args):
                        "l2_policy": "inputs larger than L2: ring of %d distinct cycles x %.1f MB of clouds; leaf pool %.1f GB" % (
                            ring, w.points_per_cycle * 16 / 1e6, g.pool_stats().device_bytes / 1e9),
                        "costmap_cells": cp["size_x"] * cp["size_y"],
-                       "parallelism": "1 GPU" if world == 1 else "%d spatial x-slab shards + in-library NCCL reduce of the u8 column-count window, pipelined one cycle behind on a side stream" % world},
+                       "parallelism": "1 GPU" if world == 1 else "%d spatial x-slab shards + in-library NCCL merge of the per-shard column results (bytes mode), pipelined one cycle behind on a side stream" % world},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": bytes_h2d, "d2h_bytes_per_step": bytes_d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -109,8 +109,8 @@ def main():
         else:
             stvl._check(L.stvl_clear_frustums(h, now, fr_ptrs[slot], w.n_cams))
             stvl._check(L.stvl_mark_device(h, arr, w.n_cams))
-            # u8 column-count window, reduce pipelined one cycle behind on the library's side stream
-            stvl._check(L.stvl_costmap_sharded_device(h, C.byref(params), costmap_dev.data_ptr(), 0, 1, 1))
+            # bytes mode: local thresholding + NCCL max into rank 0's costmap, pipelined one cycle behind on the side stream
+            stvl._check(L.stvl_costmap_sharded_device(h, C.byref(params), costmap_dev.data_ptr(), 0, 0, 1))
 
     def barrier():
         g.synchronize(); torch.cuda.synchronize()

@@ -246,7 +246,10 @@ int stvl_costmap_from_dense(stvl_grid_t * g, const uint32_t * dense_dev, int32_t
  *   stvl_comm_init      : collective; one communicator per handle
  *   stvl_costmap_sharded_device : scatter this rank's column counts into a window over the costmap (count_bytes 1 or 4
  *       per cell; 1 saturates at 255 and is exact for disjoint shards / thresholds <= 255), ncclReduce(sum) to `root`,
- *       root thresholds into costmap_dev (same rule as stvl_costmap).  pipelined == 0: everything of THIS cycle, in stream
+ *       root thresholds into costmap_dev (same rule as stvl_costmap).  count_bytes == 0 ("bytes mode", for shards that
+ *       own whole voxel columns such as x-slabs): every rank thresholds its own columns into {0, lethal} bytes and
+ *       ncclReduce(max) assembles them in the root's window, which is then copied to costmap_dev; no 4 B/cell count window
+ *       is moved and the root does not re-scan one.  pipelined == 0: everything of THIS cycle, in stream
  *       order.  pipelined == 1: the reduce of this call overlaps the next cycle's sweep and Mark (the column tiles are
  *       double-buffered), and root writes the bytes of the PREVIOUS call; stvl_costmap_sharded_flush writes the last ones.
  * All enqueue-only (no host synchronisation). */

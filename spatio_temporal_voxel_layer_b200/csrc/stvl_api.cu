@@ -665,6 +665,19 @@ void window_geometry(const stvl_grid * g, const stvl_costmap_params_t & p, int g
 int threshold_window(stvl_grid * g, int b, const stvl_costmap_params_t & p, uint8_t * costmap_dev, int root)
 {
   CU(cudaStreamWaitEvent(g->stream, g->ev_reduce[b], 0));
+  if (g->win_count_bytes == 0) {
+    // bytes mode: the reduce left the merged {0, lethal} bytes in the root's window; copy them out, and give unknown-space
+    // layers (default_value != 0) their default where nothing was marked
+    if (g->comm_rank == root && costmap_dev) {
+      const size_t bytes = (size_t)p.size_x * p.size_y;
+      CU(cudaMemcpyAsync(costmap_dev, g->window[b].p, bytes, cudaMemcpyDeviceToDevice, g->stream));
+      if (p.default_value != 0) {
+        CU(launch_fill_where_zero(costmap_dev, bytes, p.default_value, g->sm_count, g->stream));
+        g->launches += 1;
+      }
+    }
+    return STVL_OK;
+  }
   if (g->comm_rank == root && costmap_dev) {
     StageTimer timer__(g, STVL_TIME_COSTMAP);
     CU(launch_costmap_from_window(g->v, g->window[b].p, g->win_count_bytes, g->win_geom[0], g->win_geom[1], (uint32_t)g->win_geom[2],
@@ -1264,11 +1277,12 @@ int stvl_costmap_sharded_device(stvl_grid_t * g, const stvl_costmap_params_t * p
   ENTER(g);
   if (!p) return fail(STVL_ERR_INVALID, "NULL argument");
   if (!g->comm) return fail(STVL_ERR_INVALID, "stvl_comm_init has not been called");
-  if (count_bytes != 1 && count_bytes != 4) return fail(STVL_ERR_INVALID, "count_bytes must be 1 or 4");
+  if (count_bytes != 0 && count_bytes != 1 && count_bytes != 4) return fail(STVL_ERR_INVALID, "count_bytes must be 0 (bytes mode), 1 or 4");
   if (root < 0 || root >= g->comm_n) return fail(STVL_ERR_INVALID, "bad root");
   if (!(p->resolution > 0)) return fail(STVL_ERR_INVALID, "resolution must be positive");
   int geom[4];
   window_geometry(g, *p, geom);
+  if (count_bytes == 0) { geom[0] = geom[1] = 0; geom[2] = (int)p->size_x; geom[3] = (int)p->size_y; }   // the window IS a costmap
   const size_t cells = (size_t)geom[2] * geom[3];
   if (g->win_pending >= 0 && (count_bytes != g->win_count_bytes || std::memcmp(geom, g->win_geom, sizeof(geom)) != 0)) {
     // the costmap moved or changed size while a window was in flight: finish that one first
@@ -1276,31 +1290,44 @@ int stvl_costmap_sharded_device(stvl_grid_t * g, const stvl_costmap_params_t * p
     if (rc != STVL_OK) return rc;
   }
   const int b = (int)(g->win_k & 1);
-  if (g->window[b].cap < cells * (size_t)count_bytes) {
+  const size_t cell_bytes = count_bytes == 0 ? 1 : (size_t)count_bytes;
+  if (g->window[b].cap < cells * cell_bytes) {
     CU(cudaStreamSynchronize(g->merge_stream));
-    int rc = ensure(g, g->window[b], cells * (size_t)count_bytes);
+    int rc = ensure(g, g->window[b], cells * cell_bytes);
     if (rc != STVL_OK) return rc;
   }
   std::memcpy(g->win_geom, geom, sizeof(geom));
   g->win_count_bytes = count_bytes;
   // the reduce that used this window two calls ago must be done before it is overwritten
   CU(cudaStreamWaitEvent(g->stream, g->ev_reduce[b], 0));
-  CU(launch_columns_to_window(g->v, geom[0], geom[1], (uint32_t)geom[2], (uint32_t)geom[3], g->window[b].p, count_bytes,
-                              tiles_upper(g), g->sm_count, g->stream));
+  if (count_bytes == 0) {
+    // bytes mode (shards that own whole voxel columns, i.e. x / y slabs): threshold locally into {0, lethal} bytes —
+    // exactly stvl_costmap with default 0 — and let the reduce (max) assemble the costmap in the root's buffer
+    CostmapDev d = to_dev(*p);
+    d.default_value = 0;
+    StageTimer timer__(g, STVL_TIME_COSTMAP);
+    CU(launch_costmap(g->v, d, g->window[b].p, tiles_upper(g), g->sm_count, g->stream, true));
+    g->counters_fresh = false;
+  } else {
+    CU(launch_columns_to_window(g->v, geom[0], geom[1], (uint32_t)geom[2], (uint32_t)geom[3], g->window[b].p, count_bytes,
+                                tiles_upper(g), g->sm_count, g->stream));
+  }
   g->launches += 1;
   CU(cudaEventRecord(g->ev_scatter[b], g->stream));
   NcclApi * n = nccl_api();
-  const ncclDataType_t dt = count_bytes == 1 ? ncclUint8 : ncclUint32;
+  const ncclDataType_t dt = count_bytes == 4 ? ncclUint32 : ncclUint8;
+  const ncclRedOp_t op = count_bytes == 0 ? ncclMax : ncclSum;
+  void * recv = g->window[b].p;   // in place
   g->win_k += 1;
   if (!pipelined) {
     if (g->win_pending >= 0) { int rc = threshold_window(g, g->win_pending, *p, nullptr, root); if (rc != STVL_OK) return rc; g->win_pending = -1; }
-    NC(n->Reduce(g->window[b].p, g->window[b].p, cells, dt, ncclSum, root, g->comm, g->stream));
+    NC(n->Reduce(g->window[b].p, recv, cells, dt, op, root, g->comm, g->stream));
     CU(cudaEventRecord(g->ev_reduce[b], g->stream));
     return threshold_window(g, b, *p, costmap_dev, root);
   }
   // pipelined: the reduce runs on the side stream behind the scatter; the library's stream goes on with the next cycle
   CU(cudaStreamWaitEvent(g->merge_stream, g->ev_scatter[b], 0));
-  NC(n->Reduce(g->window[b].p, g->window[b].p, cells, dt, ncclSum, root, g->comm, g->merge_stream));
+  NC(n->Reduce(g->window[b].p, recv, cells, dt, op, root, g->comm, g->merge_stream));
   CU(cudaEventRecord(g->ev_reduce[b], g->merge_stream));
   if (g->win_pending >= 0) {
     int rc = threshold_window(g, g->win_pending, *p, costmap_dev, root);   // the PREVIOUS call's bytes

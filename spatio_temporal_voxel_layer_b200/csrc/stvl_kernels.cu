@@ -1337,6 +1337,15 @@ cudaError_t launch_costmap_from_window(const GridView & g, const void * win, int
   else costmap_from_window_kernel<uint32_t><<<blocks, 256, 0, s>>>(g, static_cast<const uint32_t *>(win), ix0, iy0, nx, ny, p, costmap_dev);
   return cudaGetLastError();
 }
+__global__ void __launch_bounds__(256) fill_where_zero_kernel(uint8_t * __restrict__ p, size_t n, uint8_t v)
+{
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) if (p[i] == 0) p[i] = v;
+}
+cudaError_t launch_fill_where_zero(uint8_t * p, size_t n, uint8_t v, int sm_count, cudaStream_t s)
+{
+  fill_where_zero_kernel<<<grid_for(n, 256 * 16, sm_count * 8), 256, 0, s>>>(p, n, v);
+  return cudaGetLastError();
+}
 cudaError_t launch_reset_area(const GridView & g, double sx, double sy, double ex, double ey, int invert,
                               uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s)
 {

@@ -43,6 +43,7 @@ cudaError_t launch_columns_to_window(const GridView & g, int ix0, int iy0, uint3
                                      uint32_t tiles_upper_bound, int sm_count, cudaStream_t s);
 cudaError_t launch_costmap_from_window(const GridView & g, const void * win, int count_bytes, int ix0, int iy0, uint32_t nx, uint32_t ny,
                                        const CostmapDev & p, uint8_t * costmap_dev, int sm_count, cudaStream_t s);
+cudaError_t launch_fill_where_zero(uint8_t * p, size_t n, uint8_t v, int sm_count, cudaStream_t s);
 cudaError_t launch_reset_area(const GridView & g, double sx, double sy, double ex, double ey, int invert,
                               uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s);
 cudaError_t launch_count_active(const GridView & g, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s);

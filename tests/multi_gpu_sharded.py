@@ -33,7 +33,9 @@ def main():
     now = 100.0
     ok = True
     expected = []
-    for cyc in range(4):
+    n_cycles = 8
+    # cycles 0-2: blocking merge with u32 / u8 count windows and bytes mode; 3-4: pipelined u8 counts; 5-7: pipelined bytes mode
+    for cyc in range(n_cycles):
         t = now - rng.uniform(0, 20, len(vox))            # same stream of random numbers on every rank
         g.ResetGrid(); g.load_voxels(vox[:, 0], vox[:, 1], vox[:, 2], t)
         g.ClearFrustums([], now)
@@ -43,21 +45,26 @@ def main():
             ref.costmap_device(params, cm_ref.data_ptr())
             ref.synchronize()
             expected.append(cm_ref.clone())
-        if cyc < 2:   # blocking merge, u32 then u8 windows
-            g.costmap_sharded_device(params, cm.data_ptr(), root=0, count_bytes=4 if cyc == 0 else 1, pipelined=False)
+        if cyc < 3:
+            g.costmap_sharded_device(params, cm.data_ptr(), root=0, count_bytes=(4, 1, 0)[cyc], pipelined=False)
             g.synchronize()
             if rank == 0:
                 ok = ok and torch.equal(cm, expected[cyc]) and int((cm == 254).sum()) > 1000
-        else:          # pipelined: the bytes of cycle k arrive with call k+1 (or the flush)
-            g.costmap_sharded_device(params, cm.data_ptr(), root=0, count_bytes=1, pipelined=True)
+        else:
+            if cyc == 5:   # mode switch: drain the count-window pipeline first
+                g.costmap_sharded_flush(params, cm.data_ptr(), root=0)
+                g.synchronize()
+                if rank == 0:
+                    ok = ok and torch.equal(cm, expected[4])
+            g.costmap_sharded_device(params, cm.data_ptr(), root=0, count_bytes=1 if cyc < 5 else 0, pipelined=True)
             g.synchronize()
-            if rank == 0 and cyc == 3:
-                ok = ok and torch.equal(cm, expected[2])
+            if rank == 0 and cyc in (4, 6, 7):   # the bytes of cycle k arrive with call k+1
+                ok = ok and torch.equal(cm, expected[cyc - 1])
         now += 1.0
     g.costmap_sharded_flush(params, cm.data_ptr(), root=0)
     g.synchronize()
     if rank == 0:
-        ok = ok and torch.equal(cm, expected[3])
+        ok = ok and torch.equal(cm, expected[n_cycles - 1])
     n_local = torch.tensor([g.active_count()], device="cuda")
     dist.all_reduce(n_local)
     flag = torch.tensor([1 if ok else 0], device="cuda")
