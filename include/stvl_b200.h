@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define STVL_ABI_VERSION 1
+#define STVL_ABI_VERSION 2
 
 /* status codes */
 enum {
@@ -113,7 +113,11 @@ typedef struct stvl_reading {
   int32_t filter;          /* STVL_FILTER_*; NONE = cloud was filtered upstream already; PASSTHROUGH / VOXEL run on the device */
   double min_obstacle_height, max_obstacle_height; /* z window of the filter */
   int32_t voxel_min_points; /* VOXEL filter only */
-  int32_t reserved;
+  int32_t has_transform;    /* != 0: the cloud is still in the sensor frame; apply `transform` first (then the filter, then Mark) */
+  /* tf2::doTransform(cloud, cld_global, tf_stamped) of BufferROSCloud (stvl/src/measurement_buffer.cpp:141-146) on the
+   * device: row-major 3x4 float affine [R | t] (tf2_sensor_msgs builds an Eigen::Transform<float,3,Affine> from the
+   * TransformStamped and applies it to every x,y,z in FLOAT): out_i = ((m[i][0]*x + m[i][1]*y) + m[i][2]*z) + m[i][3]. */
+  float transform[12];
 } stvl_reading_t;
 
 /* Result of one clear sweep. */
@@ -170,6 +174,11 @@ int stvl_build_lidar_frustum(double vfov, double vfov_padding, double hfov,
                              double min_dist, double max_dist,
                              const double origin[3], const double quat_xyzw[4],
                              double accel_factor, stvl_frustum_t * out);
+
+/* The float affine tf2::doTransform applies to a cloud for a TransformStamped (translation, rotation quaternion x,y,z,w)
+ * — stvl/src/measurement_buffer.cpp:141-146; tf2_sensor_msgs builds Translation3f * Quaternionf (Eigen, float).
+ * Fills the row-major 3x4 `transform` of stvl_reading_t. */
+int stvl_build_transform(const double translation[3], const double quat_xyzw[4], float transform[12]);
 
 /* ---- the per-cycle hot path --------------------------------------------- */
 /* ClearFrustums + TemporalClearAndGenerateCostmap (.cpp:96-224): one sweep over the

@@ -72,6 +72,10 @@ def lib():
     L.oracle_frustum_acceleration.argtypes = [d, d]
     L.oracle_filter_passthrough.restype = u64
     L.oracle_filter_passthrough.argtypes = [vp, u64, u32, u32, u32, u32, d, d, vp]
+    L.oracle_transform_from_quat.restype = None
+    L.oracle_transform_from_quat.argtypes = [vp, vp, vp]
+    L.oracle_transform_cloud.restype = None
+    L.oracle_transform_cloud.argtypes = [vp, u64, u32, u32, u32, u32, vp, vp]
     L.oracle_filter_voxel.restype = u64
     L.oracle_filter_voxel.argtypes = [vp, u64, u32, u32, u32, u32, f32, d, d, C.c_int, vp]
     _lib = L
@@ -206,6 +210,26 @@ class OracleGrid:
 
 def frustum_acceleration(t, factor):
     return lib().oracle_frustum_acceleration(t, factor)
+
+
+def transform_from_quat(translation, quat_xyzw):
+    """tf2 TransformStamped -> row-major 3x4 float affine as tf2_sensor_msgs builds it (Eigen, float)."""
+    t = np.ascontiguousarray(translation, np.float64)
+    q = np.ascontiguousarray(quat_xyzw, np.float64)
+    m = np.zeros(12, np.float32)
+    lib().oracle_transform_from_quat(_ptr(t), _ptr(q), _ptr(m))
+    return m
+
+
+def transform_cloud(cloud, m):
+    """tf2::doTransform of every x,y,z (reference measurement_buffer.cpp:141-146); other columns are carried over."""
+    a = np.ascontiguousarray(cloud, np.float32)
+    m = np.ascontiguousarray(m, np.float32)
+    out = np.zeros((a.shape[0], 3), np.float32)
+    lib().oracle_transform_cloud(_ptr(a), a.shape[0], a.shape[1] * 4, 0, 4, 8, _ptr(m), _ptr(out))
+    res = a.copy()
+    res[:, :3] = out
+    return res
 
 
 def filter_passthrough(cloud, lo, hi):

@@ -739,6 +739,41 @@ double oracle_frustum_acceleration(double t, double factor) { return OracleGrid:
 // BUFFER:153-175 cloud pre-filters (PCL, restated).  in: n points at point_step with
 // float x,y,z offsets.  out_xyz: caller buffer of n*3 floats.  Returns kept count.
 // ---------------------------------------------------------------------------------
+// BUFFER:141-146  tf2::doTransform(cloud, *cld_global, tf_stamped).  The algorithm lives in tf2_sensor_msgs (ROS 2
+// geometry2, not vendored in the reference; package.xml depends on tf2_sensor_msgs without a pin): it builds
+//   Eigen::Transform<float,3,Isometry> t = Translation3f(tx,ty,tz) * Quaternionf(w,x,y,z)
+// and writes t * Vector3f(x,y,z) for every point.  Restated: Eigen's Quaternion::toRotationMatrix in float, then
+// out_i = ((m_i0*x + m_i1*y) + m_i2*z) + t_i (Eigen's 3x3 coefficient product sums left to right; no FMA contraction —
+// this file is built with -ffp-contract=off).  Parity unpinned like the rest of the oracle.
+void oracle_transform_from_quat(const double * translation, const double * quat_xyzw, float * m)
+{
+  const float x = (float)quat_xyzw[0], y = (float)quat_xyzw[1], z = (float)quat_xyzw[2], w = (float)quat_xyzw[3];
+  const float tx = 2.0f * x, ty = 2.0f * y, tz = 2.0f * z;
+  const float twx = tx * w, twy = ty * w, twz = tz * w;
+  const float txx = tx * x, txy = ty * x, txz = tz * x;
+  const float tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  m[0] = 1.0f - (tyy + tzz); m[1] = txy - twz;          m[2] = txz + twy;           m[3] = (float)translation[0];
+  m[4] = txy + twz;          m[5] = 1.0f - (txx + tzz); m[6] = tyz - twx;           m[7] = (float)translation[1];
+  m[8] = txz - twy;          m[9] = tyz + twx;          m[10] = 1.0f - (txx + tyy); m[11] = (float)translation[2];
+}
+// in: n points (float x,y,z at the given offsets); out_xyz: n*3 floats, every point transformed (NaN stays NaN)
+void oracle_transform_cloud(const void * data, uint64_t n, uint32_t point_step, uint32_t off_x, uint32_t off_y,
+                            uint32_t off_z, const float * m, float * out_xyz)
+{
+  const uint8_t * d = static_cast<const uint8_t *>(data);
+  for (uint64_t i = 0; i < n; ++i) {
+    float x, y, z;
+    std::memcpy(&x, d + i * point_step + off_x, 4);
+    std::memcpy(&y, d + i * point_step + off_y, 4);
+    std::memcpy(&z, d + i * point_step + off_z, 4);
+    for (int r = 0; r < 3; ++r) {
+      const float a = m[4 * r] * x, b = m[4 * r + 1] * y, c = m[4 * r + 2] * z;
+      const float s1 = a + b;
+      const float s2 = s1 + c;
+      out_xyz[3 * i + r] = s2 + m[4 * r + 3];
+    }
+  }
+}
 // pcl::PassThrough<PCLPointCloud2> on "z", limits [lo,hi], keep_organized=false:
 // drops points with non-finite x/y/z, and points whose z is outside the limits.
 uint64_t oracle_filter_passthrough(const void * data, uint64_t n, uint32_t point_step,

@@ -49,7 +49,7 @@ class Reading(C.Structure):
                 ("off_y", C.c_uint32), ("off_z", C.c_uint32), ("origin", C.c_double * 3),
                 ("obstacle_range", C.c_double), ("now", C.c_double), ("marking", C.c_int32), ("filter", C.c_int32),
                 ("min_obstacle_height", C.c_double), ("max_obstacle_height", C.c_double),
-                ("voxel_min_points", C.c_int32), ("reserved", C.c_int32)]
+                ("voxel_min_points", C.c_int32), ("has_transform", C.c_int32), ("transform", C.c_float * 12)]
 
 
 class SweepStats(C.Structure):
@@ -83,7 +83,7 @@ class PoolStats(C.Structure):
 # every symbol include/stvl_b200.h declares
 EXPORTED_SYMBOLS = [
     "stvl_abi_version", "stvl_last_error", "stvl_device_count", "stvl_create", "stvl_destroy",
-    "stvl_build_depth_frustum", "stvl_build_lidar_frustum", "stvl_clear_frustums", "stvl_mark", "stvl_mark_device",
+    "stvl_build_depth_frustum", "stvl_build_lidar_frustum", "stvl_build_transform", "stvl_clear_frustums", "stvl_mark", "stvl_mark_device",
     "stvl_costmap", "stvl_costmap_device", "stvl_set_outputs", "stvl_get_sweep_stats", "stvl_get_columns",
     "stvl_get_cleared", "stvl_get_points", "stvl_get_ambiguous", "stvl_reset", "stvl_reset_area", "stvl_active_count",
     "stvl_get_voxels", "stvl_load_voxels", "stvl_index_to_world", "stvl_voxel_size", "stvl_columns_to_dense",
@@ -118,6 +118,7 @@ def load_library(build_if_missing=True):
     L.stvl_destroy.argtypes = [vp]
     L.stvl_build_depth_frustum.argtypes = [d, d, d, d, vp, vp, d, vp]
     L.stvl_build_lidar_frustum.argtypes = [d, d, d, d, d, vp, vp, d, vp]
+    L.stvl_build_transform.argtypes = [vp, vp, vp]
     L.stvl_clear_frustums.argtypes = [vp, d, vp, u32]
     L.stvl_mark.argtypes = [vp, C.POINTER(Reading), u32]
     L.stvl_mark_device.argtypes = [vp, C.POINTER(Reading), u32]
@@ -189,6 +190,15 @@ def build_lidar_frustum(vfov, vpad, hfov, min_d, max_d, origin, quat_xyzw, accel
     return out
 
 
+def build_transform(translation, quat_xyzw):
+    """Row-major 3x4 float affine of a TransformStamped, as tf2::doTransform applies it to a cloud (host only)."""
+    t = np.ascontiguousarray(translation, np.float64)
+    q = np.ascontiguousarray(quat_xyzw, np.float64)
+    m = np.zeros(12, np.float32)
+    _check(load_library().stvl_build_transform(_ptr(t), _ptr(q), _ptr(m)))
+    return m
+
+
 class MeasurementReading:
     """observation::MeasurementReading (reference measurement_reading.h:60-125), numpy-backed.
 
@@ -198,7 +208,7 @@ class MeasurementReading:
     def __init__(self, cloud=None, origin=(0.0, 0.0, 0.0), orientation=(0.0, 0.0, 0.0, 1.0), obstacle_range=2.5,
                  min_z=0.0, max_z=10.0, vfov=0.7, vfov_padding=0.0, hfov=1.04, decay_acceleration=0.0,
                  marking=True, clearing=False, model_type=MODEL_DEPTH_CAMERA, now=None,
-                 filter=FILTER_NONE, min_obstacle_height=0.0, max_obstacle_height=3.0):
+                 filter=FILTER_NONE, min_obstacle_height=0.0, max_obstacle_height=3.0, transform=None, voxel_min_points=0):
         self.cloud = cloud
         self.origin = tuple(float(v) for v in origin)
         self.orientation = tuple(float(v) for v in orientation)
@@ -211,6 +221,8 @@ class MeasurementReading:
         self.now = now
         self.filter = filter
         self.min_obstacle_height, self.max_obstacle_height = float(min_obstacle_height), float(max_obstacle_height)
+        self.transform = None if transform is None else np.ascontiguousarray(transform, np.float32).reshape(12)
+        self.voxel_min_points = int(voxel_min_points)
 
     def frustum(self):
         if self.model_type == MODEL_DEPTH_CAMERA:
@@ -240,6 +252,11 @@ class MeasurementReading:
         r.filter = self.filter
         r.min_obstacle_height = self.min_obstacle_height
         r.max_obstacle_height = self.max_obstacle_height
+        r.voxel_min_points = self.voxel_min_points
+        r.has_transform = 0 if self.transform is None else 1
+        if self.transform is not None:
+            for i in range(12):
+                r.transform[i] = float(self.transform[i])
 
 
 class SpatioTemporalVoxelGrid:

@@ -25,7 +25,7 @@
 using namespace stvl;
 
 // the ctypes / cgo-style bindings rely on these layouts (tests/test_cabi_host.py)
-static_assert(sizeof(stvl_config_t) == 56 && sizeof(stvl_reading_t) == 104 && sizeof(stvl_sweep_stats_t) == 88 &&
+static_assert(sizeof(stvl_config_t) == 56 && sizeof(stvl_reading_t) == 152 && sizeof(stvl_sweep_stats_t) == 88 &&
               sizeof(stvl_costmap_params_t) == 40 && sizeof(stvl_costmap_result_t) == 48 && sizeof(stvl_frustum_t) == 304 &&
               sizeof(stvl_pool_stats_t) == 88, "C-ABI struct layout changed");
 
@@ -474,6 +474,8 @@ int build_batches(stvl_grid * g, const stvl_reading_t * readings, uint32_t n, co
     if (std::isnan(d.zmax)) d.zmax_f = INFINITY;
     d.mark_range_2 = (float)(r.obstacle_range * r.obstacle_range);   // `float mark_range_2 = range * range`, .cpp:274
     d.filter = r.filter;
+    d.has_tf = r.has_transform ? 1u : 0u;
+    for (int k = 0; k < 12; ++k) d.tf[k] = r.transform[k];
     d.first_block = cur.total_blocks;
     d.vec4 = (r.point_step == 16 && r.off_x == 0 && r.off_y == 4 && r.off_z == 8 && ((uintptr_t)d.data & 15) == 0) ? 1u : 0u;
     cur.total_blocks += mark_blocks_for(r.n_points);
@@ -526,13 +528,14 @@ int apply_voxel_filters(stvl_grid * g, std::vector<stvl_reading_t> & rs, std::ve
     stvl_reading_t & r = rs[i];
     if (!(r.marking && r.n_points && r.filter == STVL_FILTER_VOXEL)) continue;
     CU(launch_voxel_filter(dev_ptrs[i], r.n_points, r.point_step, r.off_x, r.off_y, r.off_z, g->cfg.voxel_size,
-                           r.min_obstacle_height, r.max_obstacle_height, r.voxel_min_points, r.origin,
+                           r.min_obstacle_height, r.max_obstacle_height, r.voxel_min_points, r.origin, r.has_transform ? r.transform : nullptr,
                            g->vf_keys_a.p, g->vf_keys_b.p, g->vf_vals_a.p, g->vf_vals_b.p, g->vf_temp.p, temp_bytes,
                            g->vf_out.p + off, g->stream));
     g->launches += 3;
     dev_ptrs[i] = reinterpret_cast<const uint8_t *>(g->vf_out.p + off);
     r.point_step = 16; r.off_x = 0; r.off_y = 4; r.off_z = 8;
     r.filter = STVL_FILTER_NONE;   // the z window was applied by the filter
+    r.has_transform = 0;           // ... and so was the sensor -> global transform
     off += (size_t)r.n_points;
   }
   return STVL_OK;
@@ -816,6 +819,25 @@ int stvl_build_lidar_frustum(double vfov, double vfov_padding, double hfov, doub
 {
   if (!origin || !quat_xyzw || !out) return fail(STVL_ERR_INVALID, "NULL argument");
   return build_lidar_frustum(vfov, vfov_padding, hfov, min_dist, max_dist, origin, quat_xyzw, accel_factor, out);
+}
+
+int stvl_build_transform(const double translation[3], const double quat_xyzw[4], float m[12])
+{
+  if (!translation || !quat_xyzw || !m) return fail(STVL_ERR_INVALID, "NULL argument");
+  // Eigen::Quaternionf::toRotationMatrix, in float, products before sums (host code: built with -ffp-contract=off)
+  const float qx = (float)quat_xyzw[0], qy = (float)quat_xyzw[1], qz = (float)quat_xyzw[2], qw = (float)quat_xyzw[3];
+  const float dx = 2.0f * qx, dy = 2.0f * qy, dz = 2.0f * qz;
+  const float wx = dx * qw, wy = dy * qw, wz = dz * qw;
+  const float xx = dx * qx, xy = dy * qx, xz = dz * qx;
+  const float yy = dy * qy, yz = dz * qy, zz = dz * qz;
+  const float rot[9] = {1.0f - (yy + zz), xy - wz, xz + wy,
+                        xy + wz, 1.0f - (xx + zz), yz - wx,
+                        xz - wy, yz + wx, 1.0f - (xx + yy)};
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) m[4 * r + c] = rot[3 * r + c];
+    m[4 * r + 3] = (float)translation[r];
+  }
+  return STVL_OK;
 }
 
 int stvl_set_outputs(stvl_grid_t * g, uint32_t flags)

@@ -127,6 +127,9 @@ struct DevReading {
   float mark_range_2;
   int32_t filter;         // STVL_FILTER_PASSTHROUGH applies the z window in-kernel
   float zmin_f, zmax_f;   // float thresholds EXACTLY equivalent to the double window for float z: zmin rounded up, zmax rounded down
+  float tf[12];           // sensor -> global float affine (row-major 3x4), applied first when has_tf
+  uint32_t has_tf;
+  uint32_t pad_tf;
   uint32_t first_block;   // first CTA of this reading in the batched launch
   uint32_t vec4;          // 1: point_step==16, offsets 0/4/8, 16 B aligned -> float4 loads
 };
@@ -178,6 +181,16 @@ __host__ __device__ inline bool shard_owns(int bx, int shard_index, int shard_co
 }
 
 #ifdef __CUDACC__
+// tf2::doTransform of one point in float (reference measurement_buffer.cpp:141-146; tf2_sensor_msgs applies an
+// Eigen::Transform<float,3,Affine>): out_i = ((m_i0*x + m_i1*y) + m_i2*z) + m_i3, no FMA
+__device__ __forceinline__ void transform_point(const float * __restrict__ m, float & x, float & y, float & z)
+{
+  const float ox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fmul_rn(m[2], z)), m[3]);
+  const float oy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], x), __fmul_rn(m[5], y)), __fmul_rn(m[6], z)), m[7]);
+  const float oz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], x), __fmul_rn(m[9], y)), __fmul_rn(m[10], z)), m[11]);
+  x = ox; y = oy; z = oz;
+}
+
 // IndexToWorld, reference .cpp:446-460: OpenVDB indexToWorld (coord*vs) THEN + vs/2 — two roundings, never an FMA.
 __device__ __forceinline__ double index_to_world(int i, double vs, double half_vs)
 {

@@ -208,12 +208,16 @@ struct MarkParams {   // the per-reading constants a CTA keeps in shared memory
   double ox, oy, oz, now;
   float zmin_f, zmax_f, mark_range_2, range2_reject, oxf, oyf, ozf;
   int filter;
+  int has_tf;
+  float tf[12];
 };
 __device__ __forceinline__ void mark_params_from(MarkParams & p, const DevReading & r)
 {
   p.ox = r.ox; p.oy = r.oy; p.oz = r.oz; p.now = r.now;
   p.zmin_f = r.zmin_f; p.zmax_f = r.zmax_f; p.mark_range_2 = r.mark_range_2; p.filter = r.filter;
   p.oxf = (float)r.ox; p.oyf = (float)r.oy; p.ozf = (float)r.oz;
+  p.has_tf = (int)r.has_tf;
+  for (int i = 0; i < 12; ++i) p.tf[i] = r.tf[i];
   // single-precision screening threshold: points whose float distance^2 exceeds it are certainly out of range
   // (float evaluation error << 1e-3 relative at map-scale coordinates); everything else takes the exact double test
   const float m = fmaxf(fmaxf(fabsf(p.oxf), fabsf(p.oyf)), fmaxf(fabsf(p.ozf), 1.0f));
@@ -328,6 +332,10 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
     const float oxf = s_par.oxf, oyf = s_par.oyf, ozf = s_par.ozf;
     const bool zwin = s_par.filter == 2;
     const float zlo = zwin ? s_par.zmin_f : -CUDART_INF_F, zhi = zwin ? s_par.zmax_f : CUDART_INF_F;
+    if (s_par.has_tf) {   // cloud still in the sensor frame: tf2::doTransform first (measurement_buffer.cpp:141-146)
+#pragma unroll
+      for (int k = 0; k < kMarkPointsPerThread; ++k) transform_point(s_par.tf, pts[k].x, pts[k].y, pts[k].z);
+    }
     bool pre[kMarkPointsPerThread];
 #pragma unroll
     for (int k = 0; k < kMarkPointsPerThread; ++k) {

@@ -12,15 +12,17 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <math_constants.h>
 
+#include "stvl_device.cuh"
 #include "stvl_voxel_filter.h"
 
 namespace stvl {
 
 namespace {
 constexpr unsigned long long kNoBin = ~0ull;
+struct VfTransform { int on; float m[12]; };
 
 __device__ __forceinline__ void load_xyz(const uint8_t * data, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz,
-                                         unsigned long long i, float & x, float & y, float & z)
+                                         unsigned long long i, float & x, float & y, float & z, const VfTransform & tf)
 {
   const uint8_t * b = data + i * step;
   uint32_t w[3];
@@ -32,16 +34,17 @@ __device__ __forceinline__ void load_xyz(const uint8_t * data, uint32_t step, ui
     else w[a] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
   }
   x = __uint_as_float(w[0]); y = __uint_as_float(w[1]); z = __uint_as_float(w[2]);
+  if (tf.on) transform_point(tf.m, x, y, z);
 }
 
 __global__ void __launch_bounds__(256) vf_keys_kernel(const uint8_t * __restrict__ data, unsigned long long n, uint32_t step,
                                                       uint32_t ox, uint32_t oy, uint32_t oz, float inv_leaf, double zlo, double zhi,
-                                                      unsigned long long * __restrict__ keys, uint32_t * __restrict__ vals)
+                                                      unsigned long long * __restrict__ keys, uint32_t * __restrict__ vals, const VfTransform tf)
 {
   const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float x, y, z;
-  load_xyz(data, step, ox, oy, oz, i, x, y, z);
+  load_xyz(data, step, ox, oy, oz, i, x, y, z, tf);
   unsigned long long key = kNoBin;
   // PCL: skip non-finite points and points whose filter field is outside the limits (value > max || value < min)
   if (isfinite(x) && isfinite(y) && isfinite(z) && !((double)z < zlo || (double)z > zhi)) {
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(256) vf_keys_kernel(const uint8_t * __restrict
 __global__ void __launch_bounds__(256) vf_centroid_kernel(const uint8_t * __restrict__ data, unsigned long long n, uint32_t step,
                                                           uint32_t ox, uint32_t oy, uint32_t oz,
                                                           const unsigned long long * __restrict__ keys, const uint32_t * __restrict__ vals,
-                                                          int min_points, float4 fill, float4 * __restrict__ out)
+                                                          int min_points, float4 fill, float4 * __restrict__ out, const VfTransform tf)
 {
   const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(256) vf_centroid_kernel(const uint8_t * __rest
     unsigned long long c = 0;
     for (unsigned long long m = j; m < n && keys[m] == key; ++m, ++c) {
       float x, y, z;
-      load_xyz(data, step, ox, oy, oz, vals[m], x, y, z);
+      load_xyz(data, step, ox, oy, oz, vals[m], x, y, z, tf);
       sx = __fadd_rn(sx, x); sy = __fadd_rn(sy, y); sz = __fadd_rn(sz, z);
     }
     if (c >= (unsigned long long)(min_points > 0 ? min_points : 0)) {
@@ -91,20 +94,23 @@ size_t voxel_filter_temp_bytes(unsigned long long n)
 }
 
 cudaError_t launch_voxel_filter(const uint8_t * data, unsigned long long n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz,
-                                float leaf, double zlo, double zhi, int min_points, const double origin[3],
+                                float leaf, double zlo, double zhi, int min_points, const double origin[3], const float * transform,
                                 unsigned long long * keys_a, unsigned long long * keys_b, uint32_t * vals_a, uint32_t * vals_b,
                                 void * temp, size_t temp_bytes, float4 * out, cudaStream_t s)
 {
   if (n == 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((n + 255) / 256);
   const float inv_leaf = 1.0f / leaf;   // PCL: inverse_leaf_size_ = 1 / leaf_size_ (float)
-  vf_keys_kernel<<<blocks, 256, 0, s>>>(data, n, step, ox, oy, oz, inv_leaf, zlo, zhi, keys_a, vals_a);
+  VfTransform tf;
+  tf.on = transform != nullptr;
+  for (int i = 0; i < 12; ++i) tf.m[i] = transform ? transform[i] : 0.f;
+  vf_keys_kernel<<<blocks, 256, 0, s>>>(data, n, step, ox, oy, oz, inv_leaf, zlo, zhi, keys_a, vals_a, tf);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_a, keys_b, vals_a, vals_b, (int)n, 0, 63, s);
   if (e != cudaSuccess) return e;
   const float4 fill = make_float4((float)origin[0], (float)origin[1], (float)origin[2], 0.f);
-  vf_centroid_kernel<<<blocks, 256, 0, s>>>(data, n, step, ox, oy, oz, keys_b, vals_b, min_points, fill, out);
+  vf_centroid_kernel<<<blocks, 256, 0, s>>>(data, n, step, ox, oy, oz, keys_b, vals_b, min_points, fill, out, tf);
   return cudaGetLastError();
 }
 

@@ -15,6 +15,7 @@
 
 #include "rclcpp/rclcpp.hpp"
 #include "spatio_temporal_voxel_layer/measurement_reading.h"
+#include "stvl_b200.h"
 
 namespace buffer
 {
@@ -49,7 +50,30 @@ public:
     const geometry_msgs::msg::Point & origin, const geometry_msgs::msg::Quaternion & orientation,
     std::shared_ptr<sensor_msgs::msg::PointCloud2> cloud)
   {
+    BufferCloudImpl(origin, orientation, cloud, false);
+  }
+
+  // The same with the cloud still in the SENSOR frame: (translation, rotation) is the sensor -> global TransformStamped
+  // the reference looks up at :101-116/:141-145.  The sensor origin (0,0,0 in its own frame) maps to the translation,
+  // its orientation to the rotation; the cloud's doTransform (:146) runs on the device inside Mark.
+  void BufferSensorFrameCloud(
+    const geometry_msgs::msg::Point & translation, const geometry_msgs::msg::Quaternion & rotation,
+    std::shared_ptr<sensor_msgs::msg::PointCloud2> cloud)
+  {
+    BufferCloudImpl(translation, rotation, cloud, true);
+  }
+
+private:
+  void BufferCloudImpl(
+    const geometry_msgs::msg::Point & origin, const geometry_msgs::msg::Quaternion & orientation,
+    std::shared_ptr<sensor_msgs::msg::PointCloud2> cloud, bool sensor_frame)
+  {
     observation::MeasurementReading r;
+    if (sensor_frame) {
+      const double t[3] = {origin.x, origin.y, origin.z};
+      const double q[4] = {orientation.x, orientation.y, orientation.z, orientation.w};
+      r._has_device_transform = stvl_build_transform(t, q, r._device_transform) == 0;
+    }
     r._origin = origin;
     r._orientation = orientation;
     r._obstacle_range_in_m = _obstacle_range;
@@ -76,6 +100,7 @@ public:
     RemoveStaleObservations();
   }
 
+public:
   // GetReadings (measurement_buffer.cpp:193-204)
   void GetReadings(std::vector<observation::MeasurementReading> & observations)
   {

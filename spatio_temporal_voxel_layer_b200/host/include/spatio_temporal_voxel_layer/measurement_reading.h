@@ -54,6 +54,10 @@ struct MeasurementReading
   int _device_filter = 0;
   double _min_obstacle_height = 0.0, _max_obstacle_height = 0.0;
   int _voxel_min_points = 0;
+  // the cloud is still in the sensor frame: tf2::doTransform (measurement_buffer.cpp:141-146) deferred to the device as
+  // well — row-major 3x4 float affine (stvl_build_transform)
+  bool _has_device_transform = false;
+  float _device_transform[12] = {0};
 };
 }  // namespace observation
 #endif  // SPATIO_TEMPORAL_VOXEL_LAYER__MEASUREMENT_READING_H_

@@ -149,6 +149,8 @@ bool SpatioTemporalVoxelGrid::MarkReadings(const observation::MeasurementReading
     r.min_obstacle_height = o._min_obstacle_height;
     r.max_obstacle_height = o._max_obstacle_height;
     r.voxel_min_points = o._voxel_min_points;
+    r.has_transform = o._has_device_transform ? 1 : 0;
+    std::memcpy(r.transform, o._device_transform, sizeof(r.transform));
     readings.push_back(r);
   }
   if (readings.empty()) {

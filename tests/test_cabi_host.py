@@ -20,12 +20,12 @@ def test_library_exports_every_declared_symbol(stvl):
     assert declared == set(stvl.EXPORTED_SYMBOLS), declared ^ set(stvl.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(L, name), "missing export " + name
-    assert L.stvl_abi_version() == 1
+    assert L.stvl_abi_version() == 2
 
 
 def test_struct_layouts_match_header(stvl):
     assert C.sizeof(stvl.Config) == 56
-    assert C.sizeof(stvl.Reading) == 104
+    assert C.sizeof(stvl.Reading) == 152
     assert C.sizeof(stvl.SweepStats) == 88
     assert C.sizeof(stvl.CostmapParams) == 40
     assert C.sizeof(stvl.CostmapResult) == 48
@@ -98,3 +98,23 @@ def test_product_does_not_reference_oracle():
                 if re.search(r"oracle_py|libstvl_oracle|stvl_oracle|from oracle|import oracle", text):
                     offenders.append(os.path.join(d, f))
     assert not offenders, offenders
+
+
+def test_build_transform_matches_oracle_and_known_answers(stvl, oracle):
+    """stvl_build_transform (host only) against the oracle's restatement of tf2_sensor_msgs' float affine, plus
+    hand-checked answers: identity rotation is a pure float translation, a +90 deg yaw maps x -> y."""
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        t = rng.uniform(-50, 50, 3)
+        assert np.array_equal(stvl.build_transform(t, q).view(np.uint32), oracle.transform_from_quat(t, q).view(np.uint32))
+    m = stvl.build_transform((1.5, -2.25, 0.125), (0, 0, 0, 1))
+    assert np.array_equal(m.reshape(3, 4), np.array([[1, 0, 0, 1.5], [0, 1, 0, -2.25], [0, 0, 1, 0.125]], np.float32))
+    pts = np.array([[0.1, 0.2, 0.3, 0.0], [np.nan, 1.0, 1.0, 0.0]], np.float32)
+    out = oracle.transform_cloud(pts, m)
+    assert out[0, 0] == np.float32(0.1) + np.float32(1.5) and out[0, 1] == np.float32(0.2) + np.float32(-2.25)
+    assert np.isnan(out[1, :3]).all()     # 0 * NaN = NaN: a NaN coordinate poisons the whole point, as in Eigen's product
+    s = math.sqrt(0.5)
+    m = stvl.build_transform((0, 0, 0), (0, 0, s, s)).reshape(3, 4)
+    out = oracle.transform_cloud(np.array([[2.0, 0.0, 1.0, 0.0]], np.float32), m)
+    assert abs(out[0, 0]) < 1e-6 and abs(out[0, 1] - 2.0) < 1e-6 and out[0, 2] == 1.0

@@ -427,6 +427,50 @@ def test_voxel_filter_then_mark(stvl, oracle, vs, min_points):
     gg.close()
 
 
+@pytest.mark.parametrize("filt", ["none", "passthrough", "voxel"])
+def test_sensor_frame_cloud_transformed_on_device(stvl, oracle, filt):
+    """BufferROSCloud's tf2::doTransform (reference measurement_buffer.cpp:141-146) folded into Mark: the reading carries
+    the sensor-frame cloud and the float affine; the device applies it before the filter and the quantisation.  Oracle:
+    transform_cloud -> filter -> Mark.  Bit-exact (float products summed left to right, no FMA)."""
+    import spatio_temporal_voxel_layer_b200.synth as synth
+    scene = synth.retail_scene(size=20.0, seed=11)
+    o, q = (0.4, -0.7, 0.8), synth.optical_quat(-2.1)
+    glob = synth.depth_cloud(scene, o, q, width=320, height=240, seed=8)            # global frame, NaN misses
+    m = stvl.build_transform(o, q)
+    assert np.array_equal(m.view(np.uint32), oracle.transform_from_quat(o, q).view(np.uint32))
+    rot = m.reshape(3, 4)[:, :3].astype(np.float64)
+    sensor = glob.copy()
+    sensor[:, :3] = ((glob[:, :3].astype(np.float64) - np.asarray(o)) @ rot).astype(np.float32)   # R^T (p - t)
+    fcode = {"none": stvl.FILTER_NONE, "passthrough": stvl.FILTER_PASSTHROUGH, "voxel": stvl.FILTER_VOXEL}[filt]
+    zl = (0.25, 1.9)
+    want = oracle.transform_cloud(sensor, m)
+    assert np.nanmax(np.abs(want[:, :3] - glob[:, :3])) < 1e-4
+    if filt == "passthrough":
+        want = oracle.filter_passthrough(want, *zl)
+    elif filt == "voxel":
+        want = oracle.filter_voxel(want, np.float32(0.05), zl[0], zl[1], 2)
+    og = oracle.OracleGrid(0.05)
+    og.mark(want, o, 3.5, 12.5)
+    assert og.active_count() > 300
+    # host-pointer call, packed 16-byte points
+    gg = stvl.SpatioTemporalVoxelGrid(0.05)
+    r = stvl.MeasurementReading(sensor, origin=o, orientation=q, obstacle_range=3.5, now=12.5, filter=fcode,
+                                min_obstacle_height=zl[0], max_obstacle_height=zl[1], transform=m, voxel_min_points=2)
+    gg.Mark([r], now=12.5)
+    assert_same_voxels(gg.voxels(), og.voxels())
+    gg.close()
+    # strided 20-byte points with x,y,z at 4,8,12 (the scalar-load variant of the kernel)
+    wide = np.zeros((len(sensor), 5), np.float32)
+    wide[:, 1:4] = sensor[:, :3]
+    gg = stvl.SpatioTemporalVoxelGrid(0.05)
+    r = stvl.MeasurementReading((wide.ctypes.data, len(wide), 20, (4, 8, 12)), origin=o, orientation=q, obstacle_range=3.5,
+                                now=12.5, filter=fcode, min_obstacle_height=zl[0], max_obstacle_height=zl[1], transform=m,
+                                voxel_min_points=2)
+    gg.Mark([r], now=12.5)
+    assert_same_voxels(gg.voxels(), og.voxels())
+    gg.close()
+
+
 def test_config2_full_size_parity_and_properties(stvl, oracle):
     """BASELINE config 2 at FULL size (7 x 640x480 clouds = 2,150,400 points per cycle, 710,765 seeded voxels): two complete
     cycles bit-compared with the oracle, plus size-independent properties: sweep conservation, Mark idempotence."""
