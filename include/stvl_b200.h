@@ -200,10 +200,17 @@ int stvl_costmap(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_t * cos
 int stvl_costmap_device(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_t * costmap_dev, stvl_costmap_result_t * res);
 
 /* One whole update cycle with device-resident inputs, in the reference's order (stvl/src/spatio_temporal_voxel_layer.cpp:
- * 772-795): stvl_clear_frustums, stvl_mark_device, stvl_costmap_device(res = NULL).  Enqueue only, no synchronisation. */
+ * 772-795): the results are those of stvl_clear_frustums, stvl_mark_device, stvl_costmap_device(res = NULL), but the
+ * three stages are fused into three launches (the sweep's first kernel also resets the costmap bytes, the costmap pass
+ * rides on the Mark kernel, the kernels overlap by programmatic dependent launch).  Enqueue only, no synchronisation;
+ * the clouds must be complete on the device when the call is made (stream order on stvl_get_stream() suffices).
+ * stvl_get_costmap_result returns the marked-cell count / bounds afterwards. */
 int stvl_update_cycle_device(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
                              const stvl_reading_t * readings, uint32_t n_readings,
                              const stvl_costmap_params_t * p, uint8_t * costmap_dev);
+/* The result (marked columns, touched bounds — the touch() calls of spatio_temporal_voxel_layer.cpp:716) of the last
+ * costmap pass enqueued by stvl_costmap_device(res = NULL) or stvl_update_cycle_device.  Synchronises. */
+int stvl_get_costmap_result(stvl_grid_t * g, stvl_costmap_result_t * res);
 
 /* ---- results of the last sweep ------------------------------------------ */
 /* Which optional per-sweep lists the sweep kernel builds (default: STVL_OUT_CLEARED | STVL_OUT_AMBIGUOUS;

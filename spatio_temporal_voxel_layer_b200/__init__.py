@@ -17,7 +17,8 @@ from . import build as _build
 __all__ = ["load_library", "SpatioTemporalVoxelGrid", "MeasurementReading", "build_depth_frustum",
            "build_lidar_frustum", "FRUSTUM_DTYPE", "StvlError", "device_count", "EXPORTED_SYMBOLS"]
 
-LIB_PATH = _build.LIB_PATH
+# STVL_B200_LIB selects another build of the same library (the profiling-only trace variant); never a different backend
+LIB_PATH = os.environ.get("STVL_B200_LIB") or _build.LIB_PATH
 
 STVL_OK = 0
 DECAY_LINEAR, DECAY_EXPONENTIAL, DECAY_PERSISTENT = 0, 1, 2
@@ -88,7 +89,7 @@ EXPORTED_SYMBOLS = [
     "stvl_get_cleared", "stvl_get_points", "stvl_get_ambiguous", "stvl_reset", "stvl_reset_area", "stvl_active_count",
     "stvl_get_voxels", "stvl_load_voxels", "stvl_index_to_world", "stvl_voxel_size", "stvl_columns_to_dense",
     "stvl_costmap_from_dense", "stvl_get_pool_stats", "stvl_get_stream", "stvl_synchronize",
-    "stvl_update_cycle_device", "stvl_enable_timing", "stvl_get_timing",
+    "stvl_update_cycle_device", "stvl_get_costmap_result", "stvl_enable_timing", "stvl_get_timing",
     "stvl_nccl_unique_id", "stvl_comm_init", "stvl_comm_destroy", "stvl_costmap_sharded_device", "stvl_costmap_sharded_flush",
 ]
 
@@ -146,6 +147,7 @@ def load_library(build_if_missing=True):
     L.stvl_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.stvl_synchronize.argtypes = [vp]
     L.stvl_update_cycle_device.argtypes = [vp, d, vp, u32, C.POINTER(Reading), u32, C.POINTER(CostmapParams), vp]
+    L.stvl_get_costmap_result.argtypes = [vp, C.POINTER(CostmapResult)]
     L.stvl_enable_timing.argtypes = [vp, u32]
     L.stvl_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.stvl_nccl_unique_id.argtypes = [vp]
@@ -313,6 +315,26 @@ class SpatioTemporalVoxelGrid:
         res = CostmapResult()
         _check(self.L.stvl_costmap(self.h, C.byref(p), _ptr(out), C.byref(res)))
         return out, res
+
+    def update_cycle_device(self, now, clearing_readings, marking_readings, origin_x, origin_y, resolution, size_x, size_y,
+                            costmap_dev_ptr, mark_threshold=0, default_value=FREE_SPACE):
+        """stvl_update_cycle_device: the fused clear -> mark -> costmap cycle on device-resident clouds (every marking
+        reading's cloud is a (data_ptr, n, step, offsets) tuple); enqueue only."""
+        fr = [b for b in (r.frustum() for r in clearing_readings) if b is not None]
+        blocks = np.concatenate(fr) if fr else np.zeros(0, FRUSTUM_DTYPE)
+        n = len(marking_readings)
+        arr = (Reading * max(n, 1))()
+        keep = []
+        for i, m in enumerate(marking_readings):
+            m._fill(arr[i], now, keep)
+        p = CostmapParams(origin_x, origin_y, resolution, size_x, size_y, mark_threshold, default_value, LETHAL_OBSTACLE)
+        _check(self.L.stvl_update_cycle_device(self.h, float(now), _ptr(blocks) if len(blocks) else None, len(blocks), arr, n,
+                                               C.byref(p), costmap_dev_ptr))
+
+    def costmap_result(self):
+        res = CostmapResult()
+        _check(self.L.stvl_get_costmap_result(self.h, C.byref(res)))
+        return res
 
     def GetFlattenedCostmap(self):
         """reference .cpp:312-317: dict-like arrays (x, y, count) of the last sweep's occupied voxel columns."""

@@ -42,20 +42,28 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    if not force and not needs_build():
+TRACE_LIB_PATH = os.path.join(PKG_DIR, "libstvl_b200_trace.so")
+
+
+def build_library(force=False, verbose=False, trace=False):
+    """trace=True builds the profiling-only variant (-DSTVL_TRACE: per-CTA %globaltimer phase stamps, read back by
+    profiles/trace_phases.py through STVL_B200_LIB) into a separate file; the product library never contains it."""
+    if not trace and not force and not needs_build():
         return LIB_PATH
+    out = TRACE_LIB_PATH if trace else LIB_PATH
     cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(REPO_ROOT, "include"), "-I", CSRC]
+    if trace:
+        cmd += ["-DSTVL_TRACE"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, f) for f in SOURCES]
+    cmd += ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))

@@ -378,13 +378,27 @@ int grow_tiles(stvl_grid * g)
   return STVL_OK;
 }
 
-int launch_batches(stvl_grid * g, const std::vector<MarkBatch> & batches)
+// The fused update cycle (stvl_update_cycle_device): the sweep's triage kernel resets the costmap bytes, the costmap pass
+// rides on the Mark kernel, and the kernels are chained by programmatic dependent launch.
+struct CycleFusion {
+  CostmapDev cm{};
+  uint8_t * costmap = nullptr;
+  bool pdl = false;            // the Mark launch directly follows this library's sweep kernels on the stream
+  bool costmap_done = false;   // out: a Mark launch carried the costmap pass
+};
+
+int launch_batches(stvl_grid * g, const std::vector<MarkBatch> & batches, CycleFusion * fz = nullptr)
 {
   StageTimer timer__(g, STVL_TIME_MARK);
-  for (const MarkBatch & b : batches) {
+  bool pdl = fz && fz->pdl && !(g->timing_mask & STVL_TIME_MARK);
+  for (size_t i = 0; i < batches.size(); ++i) {
+    if (g->alloc_dirty) pdl = false;   // a fold kernel goes in between
     int rc = ensure_folded(g);   // (only a preceding bulk load leaves the allocator unfolded; Mark kernels fold themselves)
     if (rc != STVL_OK) return rc;
-    CU(launch_mark(g->v, b, g->sm_count, g->stream));
+    const bool carry = fz && fz->costmap && !fz->costmap_done && i + 1 == batches.size();
+    CU(launch_mark(g->v, batches[i], g->sm_count, g->stream, pdl, carry ? &fz->cm : nullptr, carry ? fz->costmap : nullptr));
+    if (carry) fz->costmap_done = true;
+    pdl = false;                       // only the first launch follows the sweep
     g->launches += 1;
   }
   return STVL_OK;
@@ -477,6 +491,7 @@ int build_batches(stvl_grid * g, const stvl_reading_t * readings, uint32_t n, co
     d.has_tf = r.has_transform ? 1u : 0u;
     for (int k = 0; k < 12; ++k) d.tf[k] = r.transform[k];
     d.first_block = cur.total_blocks;
+    cur.first_block[cur.n_readings - 1] = cur.total_blocks;
     d.vec4 = (r.point_step == 16 && r.off_x == 0 && r.off_y == 4 && r.off_z == 8 && ((uintptr_t)d.data & 15) == 0) ? 1u : 0u;
     cur.total_blocks += mark_blocks_for(r.n_points);
     *total_points += r.n_points;
@@ -541,13 +556,16 @@ int apply_voxel_filters(stvl_grid * g, std::vector<stvl_reading_t> & rs, std::ve
   return STVL_OK;
 }
 
-int run_mark(stvl_grid * g, const stvl_reading_t * readings_in, uint32_t n, const std::vector<const uint8_t *> & dev_ptrs_in)
+int run_mark(stvl_grid * g, const stvl_reading_t * readings_in, uint32_t n, const std::vector<const uint8_t *> & dev_ptrs_in,
+             CycleFusion * fz = nullptr)
 {
   std::vector<stvl_reading_t> rs(readings_in, readings_in + n);
   std::vector<const uint8_t *> dev_ptrs(dev_ptrs_in);
   {
+    const uint64_t launches_before = g->launches;
     const int rc = apply_voxel_filters(g, rs, dev_ptrs);
     if (rc != STVL_OK) return rc;
+    if (fz && g->launches != launches_before) fz->pdl = false;   // filter kernels sit between the sweep and Mark
   }
   const stvl_reading_t * readings = rs.data();
   std::vector<MarkBatch> batches;
@@ -571,6 +589,7 @@ int run_mark(stvl_grid * g, const stvl_reading_t * readings_in, uint32_t n, cons
         one.n_readings = 1;
         one.r[0] = b.r[k];
         one.r[0].first_block = 0;
+        one.first_block[0] = 0;
         one.total_blocks = mark_blocks_for(b.r[k].n_points);
         one.use_atomic_max = 0;
         one.min_now = b.r[k].now;
@@ -578,9 +597,8 @@ int run_mark(stvl_grid * g, const stvl_reading_t * readings_in, uint32_t n, cons
       }
     batches.swap(seq);
   }
-  rc = launch_batches(g, batches);
+  rc = launch_batches(g, batches, fz);
   if (rc != STVL_OK) return rc;
-  CU(cudaEventRecord(g->ev_mark_done, g->stream));
   g->replay = batches;
   g->marks_unverified = true;
   g->counters_fresh = false;
@@ -847,9 +865,9 @@ int stvl_set_outputs(stvl_grid_t * g, uint32_t flags)
   return STVL_OK;
 }
 
-int stvl_clear_frustums(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums)
+namespace {
+int clear_frustums_impl(stvl_grid * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums, CycleFusion * fz)
 {
-  ENTER(g);
   if (n_frustums && !frustums) return fail(STVL_ERR_INVALID, "frustums is NULL");
   if (n_frustums > (uint32_t)kMaxFrustums) return fail(STVL_ERR_INVALID, "at most %d clearing frustums per sweep", kMaxFrustums);
   // the allocator flags of the previous Mark must be known before its voxels are swept
@@ -864,7 +882,15 @@ int stvl_clear_frustums(stvl_grid_t * g, double now, const stvl_frustum_t * frus
   }
   // frustum blocks -> device (the previous sweep that read d_frustums is ordered before on the stream)
   bool may_raise = false;
-  if (n_frustums) {
+  FrustumParams fparam;
+  const DevFrustum * frustums_dev = nullptr;
+  if (n_frustums && n_frustums <= (uint32_t)kParamFrustums) {
+    // small sets (the usual handful of sensors) travel as kernel parameters: no upload, no stream operation
+    for (uint32_t i = 0; i < n_frustums; ++i) {
+      prepare_frustum(frustums[i], g->vs, &fparam.f[i]);
+      if (!(frustums[i].accel_factor >= 0.0)) may_raise = true;
+    }
+  } else if (n_frustums) {
     rc = ensure(g, g->frustums, n_frustums);
     if (rc != STVL_OK) return rc;
     // ring of pinned staging slots: a slot is reused only after the copy that read it has finished
@@ -878,6 +904,7 @@ int stvl_clear_frustums(stvl_grid_t * g, double now, const stvl_frustum_t * frus
     }
     CU(cudaMemcpyAsync(g->frustums.p, hf, sizeof(DevFrustum) * n_frustums, cudaMemcpyHostToDevice, g->stream));
     CU(cudaEventRecord(g->ev_frustums[slot], g->stream));
+    frustums_dev = g->frustums.p;
   }
   // stored times only ever go down in a sweep if now >= every stored time and all factors are >= 0
   if (!(now >= g->time_bound) || may_raise) g->time_bound_inf = true;
@@ -909,12 +936,25 @@ int stvl_clear_frustums(stvl_grid_t * g, double now, const stvl_frustum_t * frus
   if (rc != STVL_OK) return rc;
   select_sweep_buffers(g, g->sweep_parity ^ 1);   // this sweep's tile buffer / counter set (re-armed by the previous sweep)
   StageTimer timer__(g, STVL_TIME_SWEEP);
-  CU(launch_sweep(g->v, g->frustums.p, (int)n_frustums, now, out, slots_upper(g), g->sm_count, g->stream));
+  if (fz && fz->costmap) {
+    CU(launch_sweep(g->v, frustums_dev, &fparam, (int)n_frustums, now, out, slots_upper(g), g->sm_count, g->stream, fz->costmap,
+                    (size_t)fz->cm.size_x * fz->cm.size_y, (int)fz->cm.default_value));
+    fz->pdl = !(g->timing_mask & STVL_TIME_SWEEP);   // nothing may be enqueued between the leaf pass and Mark
+  } else {
+    CU(launch_sweep(g->v, frustums_dev, &fparam, (int)n_frustums, now, out, slots_upper(g), g->sm_count, g->stream));
+  }
   g->launches += 2;
   g->counters_fresh = false;
   g->swept = true;
   g->added_since_sweep = 0;
   return STVL_OK;
+}
+}  // namespace
+
+int stvl_clear_frustums(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums)
+{
+  ENTER(g);
+  return clear_frustums_impl(g, now, frustums, n_frustums, nullptr);
 }
 
 int stvl_mark(stvl_grid_t * g, const stvl_reading_t * readings, uint32_t n_readings)
@@ -938,6 +978,7 @@ int stvl_mark(stvl_grid_t * g, const stvl_reading_t * readings, uint32_t n_readi
   if (rc != STVL_OK) return rc;
   // H2D on the copy stream (overlaps a sweep still running on the main stream); the staging buffer may only be
   // overwritten once the previous Mark kernel has consumed it
+  CU(cudaEventRecord(g->ev_mark_done, g->stream));   // everything enqueued so far, the previous Mark kernel included
   CU(cudaStreamWaitEvent(g->copy_stream, g->ev_mark_done, 0));
   std::vector<const uint8_t *> dev_ptrs(n_readings, nullptr);
   for (uint32_t i = 0; i < n_readings; ++i) {
@@ -1396,11 +1437,41 @@ int stvl_update_cycle_device(stvl_grid_t * g, double now, const stvl_frustum_t *
                              const stvl_reading_t * readings, uint32_t n_readings,
                              const stvl_costmap_params_t * p, uint8_t * costmap_dev)
 {
-  int rc = stvl_clear_frustums(g, now, frustums, n_frustums);
+  ENTER(g);
+  if (!p || !costmap_dev) return fail(STVL_ERR_INVALID, "NULL argument");
+  if (!(p->resolution > 0)) return fail(STVL_ERR_INVALID, "resolution must be positive");
+  int rc = validate_readings(readings, n_readings);
   if (rc != STVL_OK) return rc;
-  rc = stvl_mark_device(g, readings, n_readings);
+  // Fused form of clear -> mark -> costmap, three launches: the triage kernel also resets the costmap bytes, the leaf
+  // pass and Mark are chained by programmatic dependent launch (Mark's cloud streaming overlaps the sweep's tail; it
+  // waits for the sweep before it touches the grid) and the costmap pass rides on the Mark kernel.  The clouds must be
+  // complete on the device before this call is enqueued (stream order on stvl_get_stream() is enough).
+  CycleFusion fz;
+  fz.cm = to_dev(*p);
+  fz.costmap = costmap_dev;
+  rc = clear_frustums_impl(g, now, frustums, n_frustums, &fz);
   if (rc != STVL_OK) return rc;
-  return stvl_costmap_device(g, p, costmap_dev, nullptr);
+  std::vector<const uint8_t *> dev_ptrs(n_readings, nullptr);
+  for (uint32_t i = 0; i < n_readings; ++i) dev_ptrs[i] = static_cast<const uint8_t *>(readings[i].data);
+  rc = run_mark(g, readings, n_readings, dev_ptrs, &fz);
+  if (rc != STVL_OK) return rc;
+  if (!fz.costmap_done) {   // nothing to mark in this cycle: the plain costmap kernel (the bytes are reset already)
+    StageTimer timer__(g, STVL_TIME_COSTMAP);
+    CU(launch_costmap(g->v, fz.cm, costmap_dev, tiles_upper(g), g->sm_count, g->stream, false));
+    g->launches += 1;
+  }
+  g->counters_fresh = false;
+  return STVL_OK;
+}
+
+int stvl_get_costmap_result(stvl_grid_t * g, stvl_costmap_result_t * res)
+{
+  ENTER(g);
+  if (!res) return fail(STVL_ERR_INVALID, "NULL argument");
+  int rc = fetch_counters(g);
+  if (rc != STVL_OK) return rc;
+  fill_costmap_result(g, res);
+  return after_fetch(g);
 }
 
 int stvl_enable_timing(stvl_grid_t * g, uint32_t stage_mask)

@@ -116,6 +116,13 @@ struct DevFrustum {
   double aux[4];         // lidar: min_d, max_d, tan(vFOV/2), |pad|
 };
 
+// up to kParamFrustums prepared frustum blocks travel as a kernel parameter (no upload, no stream operation between
+// the kernels of consecutive cycles); larger sets go through a device buffer
+constexpr int kParamFrustums = 8;
+struct FrustumParams {
+  DevFrustum f[kParamFrustums];
+};
+
 // -------- one marking reading on the device -----------------------------------------
 struct DevReading {
   const uint8_t * data;
@@ -134,6 +141,7 @@ struct DevReading {
   uint32_t vec4;          // 1: point_step==16, offsets 0/4/8, 16 B aligned -> float4 loads
 };
 struct MarkBatch {
+  uint32_t first_block[kMaxBatchReadings];   // copy of r[k].first_block, one cache line: every CTA scans it to find its reading
   DevReading r[kMaxBatchReadings];
   uint32_t n_readings;
   uint32_t total_blocks;

@@ -11,6 +11,7 @@
 // (never contracted into FMA) in the reference's operation order, see SURVEY.md §7.
 #include <cuda_pipeline.h>
 #include <math_constants.h>
+#include <utility>
 
 #include "stvl_device.cuh"
 #include "stvl_kernels.h"
@@ -22,6 +23,13 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 // fire-and-forget global reductions (no return value, no scoreboard wait)
 __device__ __forceinline__ void red_or_u32(uint32_t * p, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_max_u64(unsigned long long * p, unsigned long long v) { asm volatile("red.global.max.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream is still running, once every CTA of the predecessor has executed
+// launch_dependents (or exited).  It must not touch anything the predecessor writes before pdl_wait(), which returns
+// when the predecessor grid has completed and its writes are visible.  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // =====================================================================================
 // hash helpers
@@ -136,6 +144,125 @@ __device__ __forceinline__ void fold_alloc(const GridView & g)
 }
 __global__ void fold_alloc_kernel(const GridView g) { fold_alloc(g); }
 
+// Opt-in phase tracing for profiling builds only (python -m spatio_temporal_voxel_layer_b200.build --trace builds a
+// SEPARATE libstvl_b200_trace.so; the product library compiles none of this).  Thread 0 of every CTA stamps
+// %globaltimer at a few phase boundaries; profiles/trace_phases.py turns the stamps into a per-kernel timeline.
+#ifdef STVL_TRACE
+__device__ unsigned long long g_trace[4][1024][8];
+__device__ __forceinline__ void trace_stamp(int kernel, int phase)
+{
+  if (threadIdx.x == 0 && blockIdx.x < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_trace[kernel][blockIdx.x][phase] = t;
+    if (phase == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_trace[kernel][blockIdx.x][7] = sm; }
+  }
+}
+extern "C" int stvl_debug_trace(void * out, size_t bytes)
+{
+  if (bytes != sizeof(g_trace)) return -1;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+  if (cudaMemcpyFromSymbol(out, g_trace, sizeof(g_trace)) != cudaSuccess) return -3;
+  return 0;
+}
+#define TRACE(k, ph) trace_stamp(k, ph)
+#else
+#define TRACE(k, ph) ((void)0)
+#endif
+
+// =====================================================================================
+// Costmap — reference spatio_temporal_voxel_layer.cpp:699-718 (grid loop) on the tile counts
+// =====================================================================================
+// nav2 Costmap2D::worldToMap (external): wx >= origin, (unsigned)((wx-origin)/resolution) < size
+__device__ __forceinline__ bool world_to_map(double wx, double wy, const CostmapDev & p, unsigned & mx, unsigned & my)
+{
+  if (wx < p.origin_x || wy < p.origin_y) return false;
+  mx = __double2uint_rz(__ddiv_rn(__dsub_rn(wx, p.origin_x), p.resolution));
+  my = __double2uint_rz(__ddiv_rn(__dsub_rn(wy, p.origin_y), p.resolution));
+  return mx < p.size_x && my < p.size_y;
+}
+
+// last CTA of the costmap pass: publish the result and re-arm the accumulators (no separate prologue launch)
+__device__ __forceinline__ void costmap_publish_result(Counters * c)
+{
+  volatile CostmapCtr * a = &c->cm_acc;
+  c->cm.n_marked = a->n_marked;
+  c->cm.mk_min_x = a->mk_min_x; c->cm.mk_min_y = a->mk_min_y; c->cm.mk_max_x = a->mk_max_x; c->cm.mk_max_y = a->mk_max_y;
+  a->n_marked = 0;
+  a->mk_min_x = INT_MAX; a->mk_min_y = INT_MAX; a->mk_max_x = INT_MIN; a->mk_max_y = INT_MIN;
+}
+
+// The grid loop of UpdateROSCostmap (:708-717) for `n_batch` consecutive column tiles starting at t0, by one warp: the
+// count rows (256 B each, two columns per lane) and tile keys of the whole batch are requested together.
+template <int kBatch>
+__device__ __forceinline__ void costmap_tile_batch(const GridView & g, const CostmapDev & p, uint8_t * __restrict__ costmap, uint32_t t0,
+                                                   uint32_t n_tiles, unsigned lane, unsigned & n, int & mnx, int & mny, int & mxx, int & mxy)
+{
+  uint2 cc[kBatch];
+  unsigned long long keys[kBatch];
+#pragma unroll
+  for (int u = 0; u < kBatch; ++u) {
+    const uint32_t t = t0 + u;
+    cc[u] = t < n_tiles ? reinterpret_cast<const uint2 *>(g.tile_count + (size_t)t * 64)[lane] : make_uint2(0, 0);   // columns 2*lane, 2*lane+1
+    keys[u] = t < n_tiles ? g.tile_key[t] : 0ull;
+  }
+#pragma unroll
+  for (int u = 0; u < kBatch; ++u) {
+    if ((cc[u].x | cc[u].y) == 0) continue;
+    int bx, by;
+    unpack_tile_key(keys[u], bx, by);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const uint32_t cnt = k ? cc[u].y : cc[u].x;
+      const int col = 2 * (int)lane + k;
+      if (cnt == 0 || (int)cnt < p.mark_threshold) continue;   // static_cast<int>(count) >= _mark_threshold, :712
+      const int ix = bx * 8 + (col >> 3), iy = by * 8 + (col & 7);
+      unsigned mx, my;
+      if (world_to_map(index_to_world(ix, g.vs, g.half_vs), index_to_world(iy, g.vs, g.half_vs), p, mx, my)) {
+        costmap[(size_t)my * p.size_x + mx] = p.lethal;   // :715
+        ++n; mnx = min(mnx, ix); mny = min(mny, iy); mxx = max(mxx, ix); mxy = max(mxy, iy);   // touch(), :716
+      }
+    }
+  }
+}
+
+// block reduction of the marked-cell count / bounds into the device accumulators; with own_ticket the last CTA of the
+// grid also publishes (the fused Mark + costmap kernel publishes on Mark's ticket instead)
+__device__ __forceinline__ void costmap_reduce_and_publish(Counters * c, unsigned n, int mnx, int mny, int mxx, int mxy, bool own_ticket = true)
+{
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    n += __shfl_xor_sync(kFull, n, d);
+    mnx = min(mnx, __shfl_xor_sync(kFull, mnx, d)); mny = min(mny, __shfl_xor_sync(kFull, mny, d));
+    mxx = max(mxx, __shfl_xor_sync(kFull, mxx, d)); mxy = max(mxy, __shfl_xor_sync(kFull, mxy, d));
+  }
+  __shared__ unsigned int s_n;
+  __shared__ int s_b[4];
+  if (threadIdx.x == 0) { s_n = 0; s_b[0] = s_b[1] = INT_MAX; s_b[2] = s_b[3] = INT_MIN; }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0 && n) {
+    atomicAdd(&s_n, n);
+    atomicMin(&s_b[0], mnx); atomicMin(&s_b[1], mny); atomicMax(&s_b[2], mxx); atomicMax(&s_b[3], mxy);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_n) {
+      atomicAdd(&c->cm_acc.n_marked, (unsigned long long)s_n);
+      atomicMin(&c->cm_acc.mk_min_x, s_b[0]); atomicMin(&c->cm_acc.mk_min_y, s_b[1]);
+      atomicMax(&c->cm_acc.mk_max_x, s_b[2]); atomicMax(&c->cm_acc.mk_max_y, s_b[3]);
+    }
+    if (!own_ticket) return;
+    __threadfence();
+    if (atomicAdd(&c->cm_ticket, 1u) == gridDim.x - 1) {
+      __threadfence();
+      costmap_publish_result(c);
+      c->cm_ticket = 0;
+      __threadfence();
+    }
+  }
+}
+
+
 // =====================================================================================
 // Mark — reference .cpp:269-309
 // =====================================================================================
@@ -233,46 +360,51 @@ __device__ __forceinline__ int mark_reading_of(const MarkBatch & batch, uint32_t
   return ri;
 }
 
-template <bool kVec4>   // kVec4: every reading of the batch is a packed x,y,z,pad float4 cloud (the RGBD / depth-image layout)
+// kVec4: every reading of the batch is a packed x,y,z,pad float4 cloud (the RGBD / depth-image layout).
+// kCostmap: the fused update cycle — this launch also runs the costmap pass over the column counts of the sweep that
+// precedes it (they are independent of Mark: the costmap reflects the pre-Mark survivors, reference .cpp:149-224 then
+// spatio_temporal_voxel_layer.cpp:699-718); the costmap bytes were reset by the sweep's triage kernel.
+template <bool kVec4, bool kCostmap>
 __global__ void __launch_bounds__(kMarkThreads, kVec4 ? 5 : 4)
-mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uint32_t chunks_per_cta)
+mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uint32_t chunks_per_cta,
+            const CostmapDev cm, uint8_t * __restrict__ costmap)
 {
   __shared__ unsigned long long s_key[kMarkTable];
   __shared__ uint32_t s_mask[kMarkTable][16];
   __shared__ uint32_t s_slot[kMarkTable];
   __shared__ unsigned int s_drop[2];
   __shared__ MarkParams s_par;
-  // the reading descriptors are copied from the (dynamically indexed, slow) kernel-parameter bank to shared memory once
-  __shared__ DevReading s_r[kMaxBatchReadings];
-  {
-    const uint32_t words = batch.n_readings * (uint32_t)(sizeof(DevReading) / 8);
-    const unsigned long long * src = reinterpret_cast<const unsigned long long *>(&batch.r[0]);
-    unsigned long long * dst = reinterpret_cast<unsigned long long *>(&s_r[0]);
-    for (uint32_t i = threadIdx.x; i < words; i += kMarkThreads) dst[i] = src[i];
-  }
-  __syncthreads();
-
+  TRACE(0, 0);
+  // The reading descriptors stay in the kernel-parameter bank and are only ever read with warp-uniform addresses
+  // (every thread of the CTA reads the same field of the same reading): per-thread addresses into the constant bank
+  // serialise, and copying the whole batch to shared memory that way cost every CTA ~2 us before its first load.
   const unsigned lane = threadIdx.x & 31;
-  const uint32_t free_n0 = g.ctr->free_n;
-  const uint32_t high_water0 = g.ctr->high_water;
   const bool use_max = batch.use_atomic_max != 0;
+  // Everything up to the first flush only reads the clouds and the kernel parameters, so under programmatic dependent
+  // launch it overlaps the tail of the sweep; the grid state (allocator counters, hash, leaves) is touched only after
+  // sync_with_predecessor().
+  uint32_t free_n0 = 0, high_water0 = 0;
+  bool grid_state_ok = false;
+  auto sync_with_predecessor = [&]() {
+    if (!grid_state_ok) {
+      pdl_wait();
+      free_n0 = ld_volatile_u32(&g.ctr->free_n);
+      high_water0 = ld_volatile_u32(&g.ctr->high_water);
+      grid_state_ok = true;
+    }
+  };
   unsigned int drop_range = 0, drop_nonfinite = 0;
+  unsigned cm_n = 0;               // fused costmap pass: marked cells and their index bounds
+  int cm_mnx = INT_MAX, cm_mny = INT_MAX, cm_mxx = INT_MIN, cm_mxy = INT_MIN;
   uint64_t last_key = kEmptyKey;   // this thread's most recent leaf and its table entry
   int last_e = -1;
 
   const uint32_t chunk_begin = blockIdx.x * chunks_per_cta;
   const uint32_t chunk_end = min(chunk_begin + chunks_per_cta, batch.total_blocks);
   if (chunk_begin >= chunk_end) return;   // cannot happen: the grid is sized so that every CTA owns >= 1 chunk
-
-  // block-local table and the first reading's parameters
-  if (threadIdx.x < kMarkTable) s_key[threadIdx.x] = kEmptyKey;
-  if (threadIdx.x < 2) s_drop[threadIdx.x] = 0;
-#pragma unroll
-  for (int i = threadIdx.x; i < kMarkTable * 16; i += kMarkThreads) (&s_mask[0][0])[i] = 0;
   int ri = 0;
 #pragma unroll 1
-  for (int q = 1; q < (int)batch.n_readings; ++q) if (chunk_begin >= s_r[q].first_block) ri = q;
-  if (threadIdx.x == 0) mark_params_from(s_par, s_r[ri]);
+  for (int q = 1; q < (int)batch.n_readings; ++q) if (chunk_begin >= batch.first_block[q]) ri = q;
 
   // Cloud staging.  Packed float4 clouds (kVec4) are streamed global -> shared memory with cp.async (LDGSTS), two
   // 16 KB stages per CTA: the next chunk is in flight while the current one is processed and the copies hold no
@@ -280,15 +412,17 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
   extern __shared__ __align__(16) unsigned char s_dyn[];
   float4 * s_stage = reinterpret_cast<float4 *>(s_dyn);   // [2][kMarkPointsPerBlock] when kVec4
   PointXYZ nxt[kVec4 ? 1 : kMarkPointsPerThread];
-  auto prefetch = [&](const DevReading & rd, uint32_t chunk_id, int stage) {
-    const unsigned long long base = (unsigned long long)(chunk_id - rd.first_block) * kMarkPointsPerBlock;
+  auto prefetch = [&](int rix, uint32_t chunk_id, int stage) {
+    const DevReading & rd = batch.r[rix];
+    const unsigned long long base = (unsigned long long)(chunk_id - batch.first_block[rix]) * kMarkPointsPerBlock;
     if constexpr (kVec4) {
+      const unsigned long long n_pts = rd.n_points;
+      const float4 * src = reinterpret_cast<const float4 *>(rd.data);
 #pragma unroll
       for (int k = 0; k < kMarkPointsPerThread; ++k) {
         const unsigned long long i = base + (unsigned long long)k * kMarkThreads + threadIdx.x;
-        if (i < rd.n_points)
-          __pipeline_memcpy_async(&s_stage[stage * kMarkPointsPerBlock + k * kMarkThreads + threadIdx.x],
-                                  reinterpret_cast<const float4 *>(rd.data) + i, 16);
+        if (i < n_pts)
+          __pipeline_memcpy_async(&s_stage[stage * kMarkPointsPerBlock + k * kMarkThreads + threadIdx.x], src + i, 16);
       }
       __pipeline_commit();
     } else {
@@ -296,8 +430,16 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
       for (int k = 0; k < kMarkPointsPerThread; ++k) nxt[k] = load_point<false>(rd, base + (unsigned long long)k * kMarkThreads + threadIdx.x);
     }
   };
-  prefetch(s_r[ri], chunk_begin, 0);
+  // the first chunk's loads go out before anything else is set up
+  prefetch(ri, chunk_begin, 0);
+  // block-local table and the first reading's parameters
+  if (threadIdx.x < kMarkTable) s_key[threadIdx.x] = kEmptyKey;
+  if (threadIdx.x < 2) s_drop[threadIdx.x] = 0;
+#pragma unroll
+  for (int i = threadIdx.x; i < kMarkTable * 16; i += kMarkThreads) (&s_mask[0][0])[i] = 0;
+  if (threadIdx.x == 0) mark_params_from(s_par, batch.r[ri]);
   __syncthreads();
+  TRACE(0, 1);
 
   for (uint32_t chunk = chunk_begin; chunk < chunk_end; ++chunk) {
     const int stage = (int)((chunk - chunk_begin) & 1u);
@@ -310,14 +452,14 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
     const bool last = chunk + 1 == chunk_end;
     int ri_next = ri;
     if (!last) {
-      if (ri + 1 < (int)batch.n_readings && chunk + 1 >= s_r[ri + 1].first_block) ri_next = ri + 1;
-      prefetch(s_r[ri_next], chunk + 1, stage ^ 1);
+      if (ri + 1 < (int)batch.n_readings && chunk + 1 >= batch.first_block[ri + 1]) ri_next = ri + 1;
+      prefetch(ri_next, chunk + 1, stage ^ 1);
     }
     if constexpr (kVec4) {
       // every thread only reads what it copied itself: waiting for its own cp.async group is enough
       if (last) __pipeline_wait_prior(0); else __pipeline_wait_prior(1);
-      const unsigned long long base = (unsigned long long)(chunk - s_r[ri].first_block) * kMarkPointsPerBlock;
-      const unsigned long long n_pts = s_r[ri].n_points;
+      const unsigned long long base = (unsigned long long)(chunk - batch.first_block[ri]) * kMarkPointsPerBlock;
+      const unsigned long long n_pts = batch.r[ri].n_points;
 #pragma unroll
       for (int k = 0; k < kMarkPointsPerThread; ++k) {
         const float4 v = s_stage[stage * kMarkPointsPerBlock + k * kMarkThreads + threadIdx.x];
@@ -326,6 +468,7 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
       }
     }
 
+    if (chunk == chunk_begin) TRACE(0, 2);   // first chunk's data has arrived
     // ---- cheap rejection first (branch-free): depth images are full of invalid pixels and floor / ceiling returns
     const double ox = s_par.ox, oy = s_par.oy, oz = s_par.oz;
     const float range2 = s_par.mark_range_2, range2_reject = s_par.range2_reject;
@@ -388,6 +531,7 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
         const uint32_t bit = 1u << (l & 31);
         if (!(s_mask[e][l >> 5] & bit)) atomicOr(&s_mask[e][l >> 5], bit);
       } else {   // table full (scattered cloud): straight to the global store
+        sync_with_predecessor();
         mark_voxel_direct(g, key, l, s_par.now, (unsigned long long)__double_as_longlong(s_par.now), use_max, free_n0, high_water0, batch.min_now);
       }
     }
@@ -395,6 +539,21 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
     // ---- flush at the end of the range or when the next chunk belongs to another reading -----------------------------
     if (last || ri_next != ri) {
       __syncthreads();
+      if (last) {
+        TRACE(0, 3);   // all chunks processed
+        pdl_launch_dependents();   // the next cycle's triage kernel may become resident and stage its parameters
+      }
+      sync_with_predecessor();
+      if constexpr (kCostmap) {
+        // the costmap pass rides on the warps that would otherwise idle while warps 0-1 resolve the leaves
+        if (last && threadIdx.x >= kMarkTable) {
+          const uint32_t n_tiles = min(ld_volatile_u32(&g.ctr->tile_n), g.tile_capacity);
+          constexpr uint32_t kCmWarps = (kMarkThreads - kMarkTable) / 32, kCmBatch = 4;
+          const uint32_t cw = blockIdx.x * kCmWarps + ((threadIdx.x - kMarkTable) >> 5);
+          for (uint32_t t0 = cw * kCmBatch; t0 < n_tiles; t0 += gridDim.x * kCmWarps * kCmBatch)
+            costmap_tile_batch<(int)kCmBatch>(g, cm, costmap, t0, n_tiles, lane, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy);
+        }
+      }
       if (threadIdx.x < kMarkTable) {   // one thread per distinct leaf resolves (or creates) it in the global hash
         const unsigned long long key = s_key[threadIdx.x];
         uint32_t slot = kOverflowSlot;
@@ -406,6 +565,7 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
         s_slot[threadIdx.x] = slot;
       }
       __syncthreads();
+      if (last) TRACE(0, 4);   // leaves resolved in the global hash
       // per touched mask word one 32-bit OR, per distinct voxel one 64-bit max (batched launch, monotone clocks) or a
       // plain store (per-reading launches: exact overwrite semantics of MarkGridPoint, .cpp:421-430)
       const double now = s_par.now;
@@ -431,13 +591,14 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
       if (!last) {   // next reading: fresh table, new parameters
         if (threadIdx.x < kMarkTable) s_key[threadIdx.x] = kEmptyKey;
         last_key = kEmptyKey; last_e = -1;
-        if (threadIdx.x == 0) mark_params_from(s_par, s_r[ri_next]);
+        if (threadIdx.x == 0) mark_params_from(s_par, batch.r[ri_next]);
         __syncthreads();
       }
     }
     ri = ri_next;
   }
 
+  TRACE(0, 5);   // flushed
   // dropped-point statistics: warp reduce, shared-memory add, one global atomic per CTA
   if (__ballot_sync(kFull, (drop_range | drop_nonfinite) != 0)) {
 #pragma unroll
@@ -451,17 +612,20 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
     }
   }
   __syncthreads();
+  if constexpr (kCostmap) costmap_reduce_and_publish(g.ctr, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy, false);
   if (threadIdx.x == 0) {
     if (s_drop[0]) atomicAdd(&g.ctr->dropped_range, (unsigned long long)s_drop[0]);
     if (s_drop[1]) atomicAdd(&g.ctr->dropped_nonfinite, (unsigned long long)s_drop[1]);
-    // the last CTA commits the leaves handed out by this launch to the allocator state
+    // the last CTA commits the leaves handed out by this launch to the allocator state (and publishes the costmap result)
     __threadfence();
     if (atomicAdd(&g.ctr->mark_ticket, 1u) == gridDim.x - 1) {
       __threadfence();
       fold_alloc(g);
+      if constexpr (kCostmap) costmap_publish_result(g.ctr);
       g.ctr->mark_ticket = 0;
       __threadfence();
     }
+    TRACE(0, 6);
   }
 }
 
@@ -576,7 +740,7 @@ __device__ __forceinline__ void sweep_publish(const GridView & g, SweepAcc a)
   }
 }
 
-__device__ __forceinline__ void stage_frustums(DevFrustum * fr, const DevFrustum * __restrict__ frustums_gmem, int n_frustums)
+__device__ __forceinline__ void stage_frustums(DevFrustum * fr, const DevFrustum * frustums_gmem, int n_frustums)
 {
   // the frustum parameter blocks (plane sets / hourglass parameters) live in shared memory for the whole kernel
   const int words = n_frustums * (int)(sizeof(DevFrustum) / 8);
@@ -600,18 +764,40 @@ __device__ __forceinline__ bool leaf_may_expire(const GridView & g, double now, 
 // survivors are counted straight from the mask and its 4 KB time block is never touched.  Every other leaf goes to
 // the global work queue of pass 2.
 __global__ void __launch_bounds__(kSweepThreads)
-sweep_triage_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gmem, const int n_frustums, const double now,
-                    const int force_full)
+sweep_triage_kernel(const GridView g, const __grid_constant__ FrustumParams fparam, const DevFrustum * __restrict__ frustums_gmem,
+                    const int n_frustums, const double now, const int force_full, uint8_t * __restrict__ cm_reset,
+                    const unsigned long long cm_bytes, const int cm_value)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevFrustum * fr = reinterpret_cast<DevFrustum *>(smem_raw);
-  stage_frustums(fr, frustums_gmem, n_frustums);
+  TRACE(1, 0);
+  pdl_launch_dependents();   // the leaf pass may become resident now; it waits for this grid before reading the queue
+  // frustum blocks: from the kernel parameters (small sets) or from the device buffer an earlier stream operation
+  // filled; neither is written by the predecessor kernel, so they are staged before waiting for it
+  stage_frustums(fr, frustums_gmem ? frustums_gmem : fparam.f, n_frustums);
+  pdl_wait();                // launched programmatically behind the previous cycle's Mark kernel: the grid is ours from here
   const uint32_t n_slots = g.ctr->high_water;
+  TRACE(1, 1);
   // re-arm the state of the NEXT sweep while this one runs: zero the other tile buffer and the other counter set
   {
     const uint32_t n_words = (g.ctr->tile_n < g.tile_capacity ? g.ctr->tile_n : g.tile_capacity) * 64u;
     uint4 * t4 = reinterpret_cast<uint4 *>(g.tile_count_next);
     for (uint32_t i = blockIdx.x * kSweepThreads + threadIdx.x; i < n_words / 4; i += gridDim.x * kSweepThreads) t4[i] = make_uint4(0, 0, 0, 0);
+    // fused update cycle: Costmap2D::resetMaps (spatio_temporal_voxel_layer.cpp:705) for the costmap pass that rides on
+    // this cycle's Mark kernel — saves the memset launch between Mark and the costmap
+    if (cm_reset) {
+      const unsigned head = (unsigned)((16u - (unsigned)(reinterpret_cast<uintptr_t>(cm_reset) & 15u)) & 15u);
+      const unsigned long long h = head < cm_bytes ? head : cm_bytes;
+      const unsigned long long n16 = (cm_bytes - h) / 16;
+      const unsigned v = (unsigned)cm_value * 0x01010101u;
+      uint4 * c4 = reinterpret_cast<uint4 *>(cm_reset + h);
+      for (unsigned long long i = (unsigned long long)blockIdx.x * kSweepThreads + threadIdx.x; i < n16; i += (unsigned long long)gridDim.x * kSweepThreads)
+        c4[i] = make_uint4(v, v, v, v);
+      if (blockIdx.x == 0) {
+        for (unsigned long long i = threadIdx.x; i < h; i += kSweepThreads) cm_reset[i] = (uint8_t)cm_value;
+        for (unsigned long long i = h + n16 * 16 + threadIdx.x; i < cm_bytes; i += kSweepThreads) cm_reset[i] = (uint8_t)cm_value;
+      }
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       SweepCtr * c = &g.ctr->sw[g.sw_cur ^ 1];
       c->n_swept = c->n_survived = c->n_cleared = c->n_rewritten = c->n_ambiguous = 0;
@@ -620,6 +806,7 @@ sweep_triage_kernel(const GridView g, const DevFrustum * __restrict__ frustums_g
     }
   }
   SweepAcc acc;
+  TRACE(1, 2);
   for (uint32_t slot = blockIdx.x * kSweepThreads + threadIdx.x; slot < n_slots; slot += gridDim.x * kSweepThreads) {
     // all loads of the leaf are independent of each other: one DRAM round trip per leaf
     const uint64_t key = g.leaf_key[slot];
@@ -676,7 +863,10 @@ sweep_triage_kernel(const GridView g, const DevFrustum * __restrict__ frustums_g
     }
     acc.swept += cnt; acc.surv += cnt;
   }
+  __syncthreads();
+  TRACE(1, 3);
   sweep_publish(g, acc);
+  TRACE(1, 4);
 }
 
 // every CTA of pass 2 read queue_n when it started; the last one to finish empties the queue for the next sweep
@@ -693,8 +883,8 @@ __device__ __forceinline__ void leaf_pass_done(const GridView & g)
 // Sweep, pass 2 — ONE WARP PER QUEUED LEAF: leaf-level frustum classification, exact per-voxel frustum tests, decay,
 // rewrite of accelerated mark times, clearing (reference .cpp:158-221).
 __global__ void __launch_bounds__(kSweepThreads, 4)
-sweep_leaf_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gmem, const int n_frustums, const double now,
-                  const SweepOutputs out)
+sweep_leaf_kernel(const GridView g, const __grid_constant__ FrustumParams fparam, const DevFrustum * __restrict__ frustums_gmem,
+                  const int n_frustums, const double now, const SweepOutputs out)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevFrustum * fr = reinterpret_cast<DevFrustum *>(smem_raw);
@@ -706,9 +896,16 @@ sweep_leaf_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gme
   const unsigned lane = threadIdx.x & 31;
   const unsigned warp = threadIdx.x >> 5;
   const uint16_t * mask16 = reinterpret_cast<const uint16_t *>(g.leaf_mask);
+  TRACE(2, 0);
+  // Programmatic dependent launch: this grid becomes resident while the triage pass is still running and lets Mark do
+  // the same.  The frustum blocks were uploaded before the triage pass started, so they are staged before the wait.
+  pdl_launch_dependents();
+  stage_frustums(fr, frustums_gmem ? frustums_gmem : fparam.f, n_frustums);
+  pdl_wait();
+  TRACE(2, 1);
   // Shorten the dependent-load chain of a warp's first leaf: its queue entry and leaf header are requested
-  // speculatively, together with the queue length and the frustum blocks (a stale queue entry is still a valid slot
-  // index, so the wasted loads are harmless).
+  // speculatively, together with the queue length (a stale queue entry is still a valid slot index, so the wasted
+  // loads are harmless).
   const uint32_t qi0 = blockIdx.x * kSweepWarps + warp;
   uint32_t slot0 = qi0 < g.leaf_capacity ? g.sweep_queue[qi0] : 0u;
   if (slot0 >= g.leaf_capacity) slot0 = 0;
@@ -717,11 +914,11 @@ sweep_leaf_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gme
   const uint32_t tile0 = g.leaf_tile[slot0];
   const double tmin0 = g.leaf_tmin[slot0];
   const uint32_t n_queued = g.ctr->queue_n;
+  TRACE(2, 2);
   if (blockIdx.x * kSweepWarps >= n_queued) {   // nothing for this CTA (uniform per block)
     if (threadIdx.x == 0) leaf_pass_done(g);
     return;
   }
-  stage_frustums(fr, frustums_gmem, n_frustums);
 
   const int n_chunks = (n_frustums + 31) >> 5;
   const bool skip_model_ok = !out.points;
@@ -919,100 +1116,36 @@ sweep_leaf_kernel(const GridView g, const DevFrustum * __restrict__ frustums_gme
   SweepAcc acc;
   acc.swept = c_swept; acc.surv = c_surv; acc.clear = c_clear; acc.rewr = c_rewr; acc.amb = c_amb;
   acc.min_x = bb_min_x; acc.min_y = bb_min_y; acc.max_x = bb_max_x; acc.max_y = bb_max_y;
+  __syncthreads();
+  TRACE(2, 3);
   sweep_publish(g, acc);
   if (threadIdx.x == 0) leaf_pass_done(g);
+  TRACE(2, 4);
 }
 
 // =====================================================================================
-// Costmap — reference spatio_temporal_voxel_layer.cpp:699-718 (grid loop) on the tile counts
+// Costmap kernel (helpers: see above the Mark kernel, which can carry the costmap pass in the fused cycle)
 // =====================================================================================
-// nav2 Costmap2D::worldToMap (external): wx >= origin, (unsigned)((wx-origin)/resolution) < size
-__device__ __forceinline__ bool world_to_map(double wx, double wy, const CostmapDev & p, unsigned & mx, unsigned & my)
-{
-  if (wx < p.origin_x || wy < p.origin_y) return false;
-  mx = __double2uint_rz(__ddiv_rn(__dsub_rn(wx, p.origin_x), p.resolution));
-  my = __double2uint_rz(__ddiv_rn(__dsub_rn(wy, p.origin_y), p.resolution));
-  return mx < p.size_x && my < p.size_y;
-}
-
-__device__ __forceinline__ void costmap_reduce_and_publish(Counters * c, unsigned n, int mnx, int mny, int mxx, int mxy)
-{
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    n += __shfl_xor_sync(kFull, n, d);
-    mnx = min(mnx, __shfl_xor_sync(kFull, mnx, d)); mny = min(mny, __shfl_xor_sync(kFull, mny, d));
-    mxx = max(mxx, __shfl_xor_sync(kFull, mxx, d)); mxy = max(mxy, __shfl_xor_sync(kFull, mxy, d));
-  }
-  __shared__ unsigned int s_n;
-  __shared__ int s_b[4];
-  if (threadIdx.x == 0) { s_n = 0; s_b[0] = s_b[1] = INT_MAX; s_b[2] = s_b[3] = INT_MIN; }
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0 && n) {
-    atomicAdd(&s_n, n);
-    atomicMin(&s_b[0], mnx); atomicMin(&s_b[1], mny); atomicMax(&s_b[2], mxx); atomicMax(&s_b[3], mxy);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (s_n) {
-      atomicAdd(&c->cm_acc.n_marked, (unsigned long long)s_n);
-      atomicMin(&c->cm_acc.mk_min_x, s_b[0]); atomicMin(&c->cm_acc.mk_min_y, s_b[1]);
-      atomicMax(&c->cm_acc.mk_max_x, s_b[2]); atomicMax(&c->cm_acc.mk_max_y, s_b[3]);
-    }
-    // the last CTA publishes the result and re-arms the accumulators (no separate prologue launch)
-    __threadfence();
-    if (atomicAdd(&c->cm_ticket, 1u) == gridDim.x - 1) {
-      __threadfence();
-      volatile CostmapCtr * a = &c->cm_acc;
-      c->cm.n_marked = a->n_marked;
-      c->cm.mk_min_x = a->mk_min_x; c->cm.mk_min_y = a->mk_min_y; c->cm.mk_max_x = a->mk_max_x; c->cm.mk_max_y = a->mk_max_y;
-      a->n_marked = 0;
-      a->mk_min_x = INT_MAX; a->mk_min_y = INT_MAX; a->mk_max_x = INT_MIN; a->mk_max_y = INT_MIN;
-      c->cm_ticket = 0;
-      __threadfence();
-    }
-  }
-}
-
 constexpr int kCostmapTilesPerWarp = 8;
 __global__ void __launch_bounds__(256) costmap_kernel(const GridView g, const CostmapDev p, uint8_t * __restrict__ costmap)
 {
   const unsigned lane = threadIdx.x & 31;
+  TRACE(3, 0);
   const uint32_t n_tiles = min(g.ctr->tile_n, g.tile_capacity);
   const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+  TRACE(3, 1);
   unsigned n = 0;
   int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
   // each warp owns batches of 8 consecutive tiles; the 8 x 256 B count rows and the 8 tile keys are requested together
   // (one DRAM round trip per batch instead of one per tile)
   for (uint32_t t0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kCostmapTilesPerWarp; t0 < n_tiles;
        t0 += warps_total * kCostmapTilesPerWarp) {
-    uint2 cc[kCostmapTilesPerWarp];
-    unsigned long long keys[kCostmapTilesPerWarp];
-#pragma unroll
-    for (int u = 0; u < kCostmapTilesPerWarp; ++u) {
-      const uint32_t t = t0 + u;
-      cc[u] = t < n_tiles ? reinterpret_cast<const uint2 *>(g.tile_count + (size_t)t * 64)[lane] : make_uint2(0, 0);   // columns 2*lane, 2*lane+1
-      keys[u] = t < n_tiles ? g.tile_key[t] : 0ull;
-    }
-#pragma unroll
-    for (int u = 0; u < kCostmapTilesPerWarp; ++u) {
-      if ((cc[u].x | cc[u].y) == 0) continue;
-      int bx, by;
-      unpack_tile_key(keys[u], bx, by);
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const uint32_t cnt = k ? cc[u].y : cc[u].x;
-        const int col = 2 * (int)lane + k;
-        if (cnt == 0 || (int)cnt < p.mark_threshold) continue;   // static_cast<int>(count) >= _mark_threshold, :712
-        const int ix = bx * 8 + (col >> 3), iy = by * 8 + (col & 7);
-        unsigned mx, my;
-        if (world_to_map(index_to_world(ix, g.vs, g.half_vs), index_to_world(iy, g.vs, g.half_vs), p, mx, my)) {
-          costmap[(size_t)my * p.size_x + mx] = p.lethal;   // :715
-          ++n; mnx = min(mnx, ix); mny = min(mny, iy); mxx = max(mxx, ix); mxy = max(mxy, iy);   // touch(), :716
-        }
-      }
-    }
+    costmap_tile_batch<kCostmapTilesPerWarp>(g, p, costmap, t0, n_tiles, lane, n, mnx, mny, mxx, mxy);
   }
+  __syncthreads();
+  TRACE(3, 2);
   costmap_reduce_and_publish(g.ctr, n, mnx, mny, mxx, mxy);
+  TRACE(3, 3);
 }
 
 __global__ void columns_prologue_kernel(const GridView g) { g.ctr->n_columns_out = 0; }
@@ -1240,27 +1373,52 @@ cudaError_t launch_fold_alloc(const GridView & g, cudaStream_t s)
   fold_alloc_kernel<<<1, 1, 0, s>>>(g);
   return cudaGetLastError();
 }
-cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s)
+// launch with (optionally) the programmatic-stream-serialization attribute, see pdl_wait()
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_ex(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, bool pdl, Args &&... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
+template <bool kVec4, bool kCostmap>
+static cudaError_t launch_mark_variant(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s, bool pdl,
+                                       const CostmapDev & cm, uint8_t * costmap)
+{
+  static int occ = 0;
+  const size_t smem = kVec4 ? kMarkStageBytes : 0;
+  if (occ == 0) {
+    int n = 0;
+    if (kVec4) cudaFuncSetAttribute(mark_kernel<kVec4, kCostmap>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMarkStageBytes);
+    const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mark_kernel<kVec4, kCostmap>, kMarkThreads, smem);
+    occ = (e == cudaSuccess && n >= 1) ? n : 4;
+  }
+  // persistent CTAs, as many as are resident at once: each loops over chunks with the next chunk's loads in flight
+  const uint32_t resident = (uint32_t)sm_count * (uint32_t)occ;
+  const uint32_t chunks_per_cta = (batch.total_blocks + resident - 1) / resident;
+  const uint32_t grid = (batch.total_blocks + chunks_per_cta - 1) / chunks_per_cta;
+  return launch_ex(mark_kernel<kVec4, kCostmap>, grid, kMarkThreads, smem, s, pdl, g, batch, chunks_per_cta, cm, costmap);
+}
+// pdl: the caller guarantees that the kernel's inputs (clouds) were complete before the PREDECESSOR of this launch in the
+// stream started, and that the predecessor is one of this library's sweep kernels.  cm / costmap != NULL: fused costmap pass.
+cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s, bool pdl,
+                        const CostmapDev * cm, uint8_t * costmap)
 {
   if (batch.total_blocks == 0) return cudaSuccess;
   bool all_vec4 = true;
   for (uint32_t i = 0; i < batch.n_readings; ++i) all_vec4 = all_vec4 && batch.r[i].vec4 != 0;
-  // persistent CTAs, as many as are resident at once: each loops over chunks with the next chunk's loads in flight
-  static int per_sm[2] = {0, 0};
-  int & occ = per_sm[all_vec4 ? 1 : 0];
-  if (occ == 0) {
-    int n = 0;
-    if (all_vec4) cudaFuncSetAttribute(mark_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMarkStageBytes);
-    const cudaError_t e = all_vec4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mark_kernel<true>, kMarkThreads, kMarkStageBytes)
-                                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mark_kernel<false>, kMarkThreads, 0);
-    occ = (e == cudaSuccess && n >= 1) ? n : 4;
+  const CostmapDev none{};
+  if (cm && costmap) {
+    return all_vec4 ? launch_mark_variant<true, true>(g, batch, sm_count, s, pdl, *cm, costmap)
+                    : launch_mark_variant<false, true>(g, batch, sm_count, s, pdl, *cm, costmap);
   }
-  const uint32_t resident = (uint32_t)sm_count * (uint32_t)occ;
-  const uint32_t chunks_per_cta = (batch.total_blocks + resident - 1) / resident;
-  const uint32_t grid = (batch.total_blocks + chunks_per_cta - 1) / chunks_per_cta;
-  if (all_vec4) mark_kernel<true><<<grid, kMarkThreads, kMarkStageBytes, s>>>(g, batch, chunks_per_cta);
-  else mark_kernel<false><<<grid, kMarkThreads, 0, s>>>(g, batch, chunks_per_cta);
-  return cudaGetLastError();
+  return all_vec4 ? launch_mark_variant<true, false>(g, batch, sm_count, s, pdl, none, nullptr)
+                  : launch_mark_variant<false, false>(g, batch, sm_count, s, pdl, none, nullptr);
 }
 uint32_t mark_blocks_for(unsigned long long n_points)
 {
@@ -1273,9 +1431,13 @@ cudaError_t launch_load_voxels(const GridView & g, const int32_t * x, const int3
   load_voxels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g, x, y, z, t, n);
   return cudaGetLastError();
 }
-cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, int n_frustums, double now, const SweepOutputs & out,
-                         uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s)
+// frustums_dev == NULL: the (<= kParamFrustums) blocks travel in *fparam
+cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, const FrustumParams * fparam, int n_frustums, double now,
+                         const SweepOutputs & out, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s, uint8_t * costmap_reset,
+                         size_t costmap_bytes, int costmap_value)
 {
+  static const FrustumParams no_params{};
+  const FrustumParams & fp = (frustums_dev == nullptr && fparam) ? *fparam : no_params;
   cudaError_t e;
   const size_t dyn = (size_t)n_frustums * sizeof(DevFrustum);
   if (dyn > 32 * 1024) {
@@ -1286,12 +1448,15 @@ cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, in
   }
   // pass 1: one thread per leaf slot.  pub_voxels needs every survivor's coordinates: everything takes pass 2 then.
   const int force_full = out.points ? 1 : 0;
-  sweep_triage_kernel<<<grid_for(leaf_slots_upper_bound, kSweepThreads, sm_count * 8), kSweepThreads, dyn, s>>>(g, frustums_dev, n_frustums, now, force_full);
-  e = cudaGetLastError();
+  // Both passes are launched programmatically: everything they do before pdl_wait() only touches kernel parameters /
+  // the frustum buffer, so the attribute is safe whatever precedes them on the stream.
+  e = launch_ex(sweep_triage_kernel, (unsigned)grid_for(leaf_slots_upper_bound, kSweepThreads, sm_count * 8), kSweepThreads, dyn, s, true,
+                g, fp, frustums_dev, n_frustums, now, force_full, costmap_reset, (unsigned long long)costmap_bytes, costmap_value);
   if (e != cudaSuccess) return e;
-  // pass 2: one warp per queued leaf; the queue length is only known on the device, CTAs without work exit at once
-  sweep_leaf_kernel<<<grid_for(leaf_slots_upper_bound, kSweepWarps, sm_count * 4), kSweepThreads, dyn, s>>>(g, frustums_dev, n_frustums, now, out);
-  return cudaGetLastError();
+  // pass 2: one warp per queued leaf; the queue length is only known on the device, CTAs without work exit at once.
+  // Programmatic dependent launch: its CTAs become resident (and stage the frustum blocks) while pass 1 drains.
+  return launch_ex(sweep_leaf_kernel, (unsigned)grid_for(leaf_slots_upper_bound, kSweepWarps, sm_count * 4), kSweepThreads, dyn, s, true,
+                   g, fp, frustums_dev, n_frustums, now, out);
 }
 cudaError_t launch_costmap(const GridView & g, const CostmapDev & p, uint8_t * costmap_dev, uint32_t tiles_upper_bound, int sm_count, cudaStream_t s,
                            bool fill_default)

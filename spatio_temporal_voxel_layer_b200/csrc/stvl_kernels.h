@@ -25,12 +25,14 @@ struct CostmapDev {
 };
 
 cudaError_t launch_fold_alloc(const GridView & g, cudaStream_t s);
-cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s);
+cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s, bool pdl = false,
+                        const CostmapDev * fused_costmap = nullptr, uint8_t * costmap_dev = nullptr);
 uint32_t mark_blocks_for(unsigned long long n_points);
 cudaError_t launch_load_voxels(const GridView & g, const int32_t * x, const int32_t * y, const int32_t * z, const double * t,
                                unsigned long long n, cudaStream_t s);
-cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, int n_frustums, double now, const SweepOutputs & out,
-                         uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s);
+cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, const FrustumParams * fparam, int n_frustums, double now,
+                         const SweepOutputs & out, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s,
+                         uint8_t * costmap_reset = nullptr, size_t costmap_bytes = 0, int costmap_value = 0);
 cudaError_t launch_costmap(const GridView & g, const CostmapDev & p, uint8_t * costmap_dev, uint32_t tiles_upper_bound, int sm_count, cudaStream_t s,
                            bool fill_default);
 cudaError_t launch_columns(const GridView & g, int32_t * ix, int32_t * iy, uint32_t * cnt, unsigned long long cap,

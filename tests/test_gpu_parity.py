@@ -260,6 +260,68 @@ def test_multi_cycle_scenario_with_costmap(stvl, oracle):
     gg.close()
 
 
+@pytest.mark.parametrize("mixed_layouts", [False, True])
+def test_fused_update_cycle_matches_oracle(stvl, oracle, mixed_layouts):
+    """stvl_update_cycle_device — the three-launch fused cycle (triage kernel resets the costmap, leaf pass and Mark
+    chained by programmatic dependent launch, costmap pass carried by the Mark kernel) — against the oracle's
+    clear -> mark -> costmap, over 10 cycles with device-resident clouds.  Costmap bytes, marked-column count, touched
+    bounds, column counts, cleared cells and the voxel store must all be bit-identical; cycle 6 has nothing to mark
+    (the plain costmap kernel runs instead), a dirty costmap buffer checks the in-kernel reset."""
+    import torch
+    import spatio_temporal_voxel_layer_b200.synth as synth
+    scene = synth.retail_scene(size=30.0, seed=3)
+    gg = stvl.SpatioTemporalVoxelGrid(0.05, decay_model=0, voxel_decay=2.0, leaf_capacity=1 << 14)
+    og = oracle.OracleGrid(0.05, decay_model=0, voxel_decay=2.0)
+    size, res, ox, oy = 400, 0.05, -10.0, -10.0
+    stream = torch.cuda.ExternalStream(gg.stream())
+    cm_dev = torch.empty((size + 1) * size + 3, dtype=torch.uint8, device="cuda")[3:3 + size * size]   # deliberately unaligned
+    for cyc in range(10):
+        now = 100.0 + 0.4 * cyc
+        centre = (-6.0 + 0.5 * cyc, 2.3 - 13.5 + 12.0, 0.0)
+        readings = []
+        for k, (o, q) in enumerate(synth.camera_ring(centre, 0.1 * cyc, n_cams=3)):
+            readings.append(rgbd_reading(stvl, synth, scene, o, q, seed=100 * cyc + k, now=now + 0.001 * k))
+        marking = [] if cyc == 6 else readings
+        dev_readings, keep = [], []
+        for k, r in enumerate(marking):
+            host = np.ascontiguousarray(r.cloud, np.float32)
+            if mixed_layouts and k == 1:      # one strided cloud switches the whole batch to the scalar-load kernel variant
+                wide = np.zeros((len(host), 6), np.float32)
+                wide[:, 2:5] = host[:, :3]
+                t = torch.from_numpy(wide).cuda()
+                layout = (t.data_ptr(), len(host), 24, (8, 12, 16))
+            else:
+                t = torch.from_numpy(host).cuda()
+                layout = (t.data_ptr(), len(host), 16, (0, 4, 8))
+            keep.append(t)
+            dev_readings.append(stvl.MeasurementReading(layout, origin=r.origin, orientation=r.orientation, obstacle_range=r.obstacle_range,
+                                                        now=r.now, filter=r.filter, min_obstacle_height=r.min_obstacle_height,
+                                                        max_obstacle_height=r.max_obstacle_height))
+        with torch.cuda.stream(stream):
+            cm_dev.fill_(77)      # stale bytes: the cycle itself must reset them
+        thr, dflt = cyc % 3, (255 if cyc % 2 else 0)
+        gg.update_cycle_device(now, readings, dev_readings, ox, oy, res, size, size, cm_dev.data_ptr(), mark_threshold=thr, default_value=dflt)
+        og.clear_frustums(now, oracle_frustums(oracle, readings))
+        for r in marking:
+            oracle_mark(oracle, og, r, now)
+        ocm, ob, on = og.update_ros_costmap(ox, oy, res, size, size, mark_threshold=thr, default_value=dflt)
+        res_g = gg.costmap_result()
+        cm = cm_dev.cpu().numpy().reshape(size, size)
+        assert np.array_equal(cm, ocm), "costmap bytes differ in cycle %d" % cyc
+        assert res_g.n_marked_columns == on
+        st = compare_cycle_outputs(gg, og)
+        b = [1e308, 1e308, -1e308, -1e308]
+        if res_g.has_bounds:
+            b = [min(b[0], res_g.touched[0]), min(b[1], res_g.touched[1]), max(b[2], res_g.touched[2]), max(b[3], res_g.touched[3])]
+        if st.n_cleared:
+            w = st.cleared_bbox_world
+            b = [min(b[0], w[0]), min(b[1], w[1]), max(b[2], w[2]), max(b[3], w[3])]
+        np.testing.assert_array_equal(np.array(b), ob)
+        del keep
+    assert og.active_count() > 1000
+    gg.close()
+
+
 def test_leaf_pool_growth_replays_mark(stvl, oracle):
     """A Mark that exhausts the leaf pool is replayed after the pool (and its hash) grew: nothing is lost."""
     rng = np.random.default_rng(13)
