@@ -30,6 +30,7 @@ PHASES = {
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cycles", type=int, default=60)
+    ap.add_argument("--staged", action="store_true", help="enqueue the cycle stage by stage (three C-ABI calls, no overlap) instead of the fused call")
     args = ap.parse_args()
     import torch
     import spatio_temporal_voxel_layer_b200 as stvl
@@ -68,8 +69,13 @@ def main():
         now = w.now0 + w.dt * (step + 1)
         for k in range(w.n_cams):
             arrs[slot][k].now = now + 1e-4 * k
-        stvl._check(L.stvl_update_cycle_device(h, now, fr[slot].ctypes.data_as(C.c_void_p), w.n_cams, arrs[slot], w.n_cams,
-                                               C.byref(params), costmap.data_ptr()))
+        if args.staged:
+            stvl._check(L.stvl_clear_frustums(h, now, fr[slot].ctypes.data_as(C.c_void_p), w.n_cams))
+            stvl._check(L.stvl_mark_device(h, arrs[slot], w.n_cams))
+            stvl._check(L.stvl_costmap_device(h, C.byref(params), costmap.data_ptr(), None))
+        else:
+            stvl._check(L.stvl_update_cycle_device(h, now, fr[slot].ctypes.data_as(C.c_void_p), w.n_cams, arrs[slot], w.n_cams,
+                                                   C.byref(params), costmap.data_ptr()))
         host_t.append(time.perf_counter() - th)
     e1.record(stream)
     g.synchronize()

@@ -474,6 +474,10 @@ int build_batches(stvl_grid * g, const stvl_reading_t * readings, uint32_t n, co
     *max_now = std::max(*max_now, r.now);
     if (cur.n_readings == kMaxBatchReadings) { out->push_back(cur); cur = MarkBatch{}; }
     cur.min_now = cur.n_readings ? std::min(cur.min_now, r.now) : r.now;
+    if (cur.n_readings == 0) {   // reference leaf of the batch's block-local table keys
+      const double lx = std::floor(r.origin[0] / (8.0 * g->vs));
+      cur.ref_bx = (std::isfinite(lx) && std::fabs(lx) < 1e9) ? (int32_t)lx : 0;
+    }
     DevReading & d = cur.r[cur.n_readings++];
     d.data = dev_ptrs[i];
     d.n_points = r.n_points;
@@ -487,6 +491,14 @@ int build_batches(stvl_grid * g, const stvl_reading_t * readings, uint32_t n, co
     if (std::isnan(d.zmin)) d.zmin_f = -INFINITY;   // comparisons with NaN limits are false upstream: nothing is rejected
     if (std::isnan(d.zmax)) d.zmax_f = INFINITY;
     d.mark_range_2 = (float)(r.obstacle_range * r.obstacle_range);   // `float mark_range_2 = range * range`, .cpp:274
+    // single-precision screening threshold: points whose float distance^2 exceeds it are certainly out of range (float
+    // evaluation error << 1e-3 relative at map-scale coordinates); everything else takes the exact double test
+    d.oxf = (float)d.ox; d.oyf = (float)d.oy; d.ozf = (float)d.oz;
+    {
+      const float m = std::fmax(std::fmax(std::fabs(d.oxf), std::fabs(d.oyf)), std::fmax(std::fabs(d.ozf), 1.0f));
+      d.range2_reject = d.mark_range_2 * 1.001f + 1e-3f + 1e-5f * m * (std::sqrt(std::fmax(d.mark_range_2, 0.f)) + 1.0f);
+      if (!(d.range2_reject == d.range2_reject)) d.range2_reject = INFINITY;
+    }
     d.filter = r.filter;
     d.has_tf = r.has_transform ? 1u : 0u;
     for (int k = 0; k < 12; ++k) d.tf[k] = r.transform[k];
@@ -590,6 +602,10 @@ int run_mark(stvl_grid * g, const stvl_reading_t * readings_in, uint32_t n, cons
         one.r[0] = b.r[k];
         one.r[0].first_block = 0;
         one.first_block[0] = 0;
+        {
+          const double lx = std::floor(b.r[k].ox / (8.0 * g->vs));
+          one.ref_bx = (std::isfinite(lx) && std::fabs(lx) < 1e9) ? (int32_t)lx : 0;
+        }
         one.total_blocks = mark_blocks_for(b.r[k].n_points);
         one.use_atomic_max = 0;
         one.min_now = b.r[k].now;

@@ -56,6 +56,9 @@ struct Counters {
   uint32_t mark_ticket, leaf_ticket, cm_ticket, pad1;
   // dropped input points
   unsigned long long dropped_range, dropped_nonfinite;
+  // Mark's last-CTA ticket: low 16 bits count the CTAs that are done, the upper 48 accumulate their non-finite point
+  // counts (one atomic per CTA for both; the last CTA folds the sum into dropped_nonfinite and re-arms it)
+  unsigned long long mark_ticket64;
   SweepCtr sw[2];
   CostmapCtr cm_acc;       // accumulators of the running costmap kernel
   CostmapCtr cm;           // published result of the last costmap kernel
@@ -134,9 +137,10 @@ struct DevReading {
   float mark_range_2;
   int32_t filter;         // STVL_FILTER_PASSTHROUGH applies the z window in-kernel
   float zmin_f, zmax_f;   // float thresholds EXACTLY equivalent to the double window for float z: zmin rounded up, zmax rounded down
+  float range2_reject;    // single-precision screen: a float distance^2 above this is certainly out of range
+  float oxf, oyf, ozf;    // (float) origin, for that screen
   float tf[12];           // sensor -> global float affine (row-major 3x4), applied first when has_tf
   uint32_t has_tf;
-  uint32_t pad_tf;
   uint32_t first_block;   // first CTA of this reading in the batched launch
   uint32_t vec4;          // 1: point_step==16, offsets 0/4/8, 16 B aligned -> float4 loads
 };
@@ -146,7 +150,7 @@ struct MarkBatch {
   uint32_t n_readings;
   uint32_t total_blocks;
   uint32_t use_atomic_max;  // 1: batched mode (monotone clocks), 0: plain stores
-  uint32_t pad;
+  int32_t ref_bx;           // reference leaf x of the batch (first reading's origin): block-local table keys store bx - ref_bx
   double min_now;           // smallest clock sample in the batch: initial leaf_tmin of leaves created by it
 };
 

@@ -11,6 +11,7 @@
 // (never contracted into FMA) in the reference's operation order, see SURVEY.md §7.
 #include <cuda_pipeline.h>
 #include <math_constants.h>
+#include <algorithm>
 #include <utility>
 
 #include "stvl_device.cuh"
@@ -301,8 +302,8 @@ __device__ __forceinline__ PointXYZ load_point(const DevReading & r, unsigned lo
 constexpr int kMarkThreads = 256;
 constexpr int kMarkPointsPerThread = 4;
 constexpr int kMarkPointsPerBlock = kMarkThreads * kMarkPointsPerThread;
-constexpr int kMarkTable = 64;        // block-local leaf table (shared memory)
-constexpr int kMarkProbes = 8;
+constexpr int kMarkTable = 128;       // block-local (reading, leaf) table (shared memory)
+constexpr int kMarkProbes = 16;
 constexpr size_t kMarkStageBytes = 2 * (size_t)kMarkPointsPerBlock * 16;   // two cp.async stages of one chunk each
 
 // write one voxel straight to the global store (fallback when the block-local table is full)
@@ -322,42 +323,34 @@ __device__ __forceinline__ void mark_voxel_direct(const GridView & g, uint64_t k
   }
 }
 
-// Mark — persistent CTAs; each owns a contiguous range of 1024-point chunks of the batched clouds:
-//   1. coalesced 128-bit streaming loads of the cloud; the loads of the NEXT chunk are issued before the current one
-//      is processed, so every resident warp always has 2 KB of the cloud in flight
+// Mark — persistent CTAs; CTA b processes the 1024-point chunks b, b + gridDim, b + 2 gridDim, ... of the batched clouds
+// (interleaved: neighbouring chunks of a depth image have the same share of invalid / out-of-range pixels, so every
+// CTA gets the same mix):
+//   1. packed clouds are streamed global -> shared memory with cp.async, the NEXT chunk in flight while the current one
+//      is processed; every thread only reads back what it copied itself, so the chunk loop has no barrier at all
 //   2. range / z-window tests and key quantisation in the reference's exact arithmetic (.cpp:285-303), written
 //      branch-free so the four points of a thread advance together
 //   3. block-level dedupe in shared memory: a depth image puts ~100 points into every voxel and ~1000 into every
-//      8^3 leaf, so the CTA ORs its points into a small table of {leaf key, 512-bit mask} that lives across chunks
-//   4. flush (at the end of the range, or when the range crosses into the next reading): one global hash probe per
-//      distinct leaf, one 32-bit OR per touched mask word and one 64-bit max (or store) per distinct voxel
-struct MarkParams {   // the per-reading constants a CTA keeps in shared memory
-  double ox, oy, oz, now;
-  float zmin_f, zmax_f, mark_range_2, range2_reject, oxf, oyf, ozf;
-  int filter;
-  int has_tf;
-  float tf[12];
-};
-__device__ __forceinline__ void mark_params_from(MarkParams & p, const DevReading & r)
-{
-  p.ox = r.ox; p.oy = r.oy; p.oz = r.oz; p.now = r.now;
-  p.zmin_f = r.zmin_f; p.zmax_f = r.zmax_f; p.mark_range_2 = r.mark_range_2; p.filter = r.filter;
-  p.oxf = (float)r.ox; p.oyf = (float)r.oy; p.ozf = (float)r.oz;
-  p.has_tf = (int)r.has_tf;
-  for (int i = 0; i < 12; ++i) p.tf[i] = r.tf[i];
-  // single-precision screening threshold: points whose float distance^2 exceeds it are certainly out of range
-  // (float evaluation error << 1e-3 relative at map-scale coordinates); everything else takes the exact double test
-  const float m = fmaxf(fmaxf(fabsf(p.oxf), fabsf(p.oyf)), fmaxf(fabsf(p.ozf), 1.0f));
-  p.range2_reject = r.mark_range_2 * 1.001f + 1e-3f + 1e-5f * m * (sqrtf(fmaxf(r.mark_range_2, 0.f)) + 1.0f);
-  if (!(p.range2_reject == p.range2_reject)) p.range2_reject = CUDART_INF_F;
-}
-
+//      8^3 leaf, so the CTA ORs its points into a table of {(reading, leaf), 512-bit mask} that lives across chunks
+//      (a 1024-point chunk of a depth image touches 4-10 leaves)
+//   4. ONE flush at the end: one global hash probe per distinct leaf, one 32-bit OR per touched mask word and one
+//      64-bit max (or store) per distinct voxel.  Nothing before the flush touches the grid, so all of 1-3 may overlap
+//      the sweep that precedes Mark on the stream (programmatic dependent launch).
 __device__ __forceinline__ int mark_reading_of(const MarkBatch & batch, uint32_t chunk)
 {
   int ri = 0;
 #pragma unroll 1
-  for (int k = 1; k < (int)batch.n_readings; ++k) if (chunk >= batch.r[k].first_block) ri = k;
+  for (int k = 1; k < (int)batch.n_readings; ++k) if (chunk >= batch.first_block[k]) ri = k;
   return ri;
+}
+
+// key of the block-local table: reading index (the mark time differs per reading) + leaf coordinate, x relative to the
+// batch's reference leaf so that everything fits 63 bits; leaves farther than 2^16 leaves from it bypass the table
+constexpr int kMarkRelBias = 1 << 16;
+__device__ __forceinline__ uint64_t pack_table_key(int ri, int rx, int by, int bz)
+{
+  return ((uint64_t)(uint32_t)ri << 59) | ((uint64_t)(uint32_t)(rx + kMarkRelBias) << 42) |
+         ((uint64_t)(uint32_t)(by + kLeafBias) << 21) | (uint64_t)(uint32_t)(bz + kLeafBias);
 }
 
 // kVec4: every reading of the batch is a packed x,y,z,pad float4 cloud (the RGBD / depth-image layout).
@@ -366,21 +359,21 @@ __device__ __forceinline__ int mark_reading_of(const MarkBatch & batch, uint32_t
 // spatio_temporal_voxel_layer.cpp:699-718); the costmap bytes were reset by the sweep's triage kernel.
 template <bool kVec4, bool kCostmap>
 __global__ void __launch_bounds__(kMarkThreads, kVec4 ? 5 : 4)
-mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uint32_t chunks_per_cta,
-            const CostmapDev cm, uint8_t * __restrict__ costmap)
+mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const CostmapDev cm, uint8_t * __restrict__ costmap)
 {
   __shared__ unsigned long long s_key[kMarkTable];
   __shared__ uint32_t s_mask[kMarkTable][16];
   __shared__ uint32_t s_slot[kMarkTable];
+  __shared__ double s_now[kMarkTable];
   __shared__ unsigned int s_drop[2];
-  __shared__ MarkParams s_par;
   TRACE(0, 0);
   // The reading descriptors stay in the kernel-parameter bank and are only ever read with warp-uniform addresses
   // (every thread of the CTA reads the same field of the same reading): per-thread addresses into the constant bank
   // serialise, and copying the whole batch to shared memory that way cost every CTA ~2 us before its first load.
   const unsigned lane = threadIdx.x & 31;
   const bool use_max = batch.use_atomic_max != 0;
-  // Everything up to the first flush only reads the clouds and the kernel parameters, so under programmatic dependent
+  const uint32_t total = batch.total_blocks;
+  // Everything up to the flush only reads the clouds and the kernel parameters, so under programmatic dependent
   // launch it overlaps the tail of the sweep; the grid state (allocator counters, hash, leaves) is touched only after
   // sync_with_predecessor().
   uint32_t free_n0 = 0, high_water0 = 0;
@@ -396,15 +389,8 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
   unsigned int drop_range = 0, drop_nonfinite = 0;
   unsigned cm_n = 0;               // fused costmap pass: marked cells and their index bounds
   int cm_mnx = INT_MAX, cm_mny = INT_MAX, cm_mxx = INT_MIN, cm_mxy = INT_MIN;
-  uint64_t last_key = kEmptyKey;   // this thread's most recent leaf and its table entry
+  uint64_t last_key = kEmptyKey;   // this thread's most recent table key and its entry
   int last_e = -1;
-
-  const uint32_t chunk_begin = blockIdx.x * chunks_per_cta;
-  const uint32_t chunk_end = min(chunk_begin + chunks_per_cta, batch.total_blocks);
-  if (chunk_begin >= chunk_end) return;   // cannot happen: the grid is sized so that every CTA owns >= 1 chunk
-  int ri = 0;
-#pragma unroll 1
-  for (int q = 1; q < (int)batch.n_readings; ++q) if (chunk_begin >= batch.first_block[q]) ri = q;
 
   // Cloud staging.  Packed float4 clouds (kVec4) are streamed global -> shared memory with cp.async (LDGSTS), two
   // 16 KB stages per CTA: the next chunk is in flight while the current one is processed and the copies hold no
@@ -431,35 +417,97 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
     }
   };
   // the first chunk's loads go out before anything else is set up
-  prefetch(ri, chunk_begin, 0);
-  // block-local table and the first reading's parameters
-  if (threadIdx.x < kMarkTable) s_key[threadIdx.x] = kEmptyKey;
+  uint32_t chunk = blockIdx.x;
+  int ri = 0;
+  if (chunk < total) {
+    ri = mark_reading_of(batch, chunk);
+    prefetch(ri, chunk, 0);
+  }
   if (threadIdx.x < 2) s_drop[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < kMarkTable; i += kMarkThreads) s_key[i] = kEmptyKey;
 #pragma unroll
   for (int i = threadIdx.x; i < kMarkTable * 16; i += kMarkThreads) (&s_mask[0][0])[i] = 0;
-  if (threadIdx.x == 0) mark_params_from(s_par, batch.r[ri]);
   __syncthreads();
   TRACE(0, 1);
 
-  for (uint32_t chunk = chunk_begin; chunk < chunk_end; ++chunk) {
-    const int stage = (int)((chunk - chunk_begin) & 1u);
+  // ---- flush: resolve the table's leaves in the global hash, push masks and times, empty the table ---------------------
+  auto flush = [&](const bool final) {
+    if (final) {
+      TRACE(0, 3);   // all chunks processed
+      pdl_launch_dependents();   // the next cycle's triage kernel may become resident and stage its parameters
+    }
+    sync_with_predecessor();
+    if constexpr (kCostmap) {
+      // the costmap pass rides on the warps that would otherwise idle while the first warps resolve the leaves
+      if (final && threadIdx.x >= kMarkTable) {
+        const uint32_t n_tiles = min(ld_volatile_u32(&g.ctr->tile_n), g.tile_capacity);
+        constexpr uint32_t kCmWarps = (kMarkThreads - kMarkTable) / 32, kCmBatch = 4;
+        const uint32_t cw = blockIdx.x * kCmWarps + ((threadIdx.x - kMarkTable) >> 5);
+        for (uint32_t t0 = cw * kCmBatch; t0 < n_tiles; t0 += gridDim.x * kCmWarps * kCmBatch)
+          costmap_tile_batch<(int)kCmBatch>(g, cm, costmap, t0, n_tiles, lane, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy);
+      }
+    }
+    if (threadIdx.x < kMarkTable) {   // one thread per distinct (reading, leaf) resolves (or creates) the leaf in the global hash
+      const unsigned long long tkey = s_key[threadIdx.x];
+      uint32_t slot = kOverflowSlot;
+      if (tkey != kEmptyKey) {
+        const int ri = (int)(tkey >> 59);
+        const int bx = (int)((tkey >> 42) & 0x1FFFF) - kMarkRelBias + batch.ref_bx;
+        const int by = (int)((tkey >> 21) & 0x1FFFFF) - kLeafBias, bz = (int)(tkey & 0x1FFFFF) - kLeafBias;
+        slot = leaf_find_or_insert(g, pack_leaf_key(bx, by, bz), bx, by, free_n0, high_water0, batch.min_now);
+        s_now[threadIdx.x] = batch.r[ri].now;
+        s_key[threadIdx.x] = kEmptyKey;
+      }
+      s_slot[threadIdx.x] = slot;
+    }
+    last_key = kEmptyKey; last_e = -1;
+    __syncthreads();
+    if (final) TRACE(0, 4);   // leaves resolved in the global hash
+    // per touched mask word one 32-bit OR, per distinct voxel one 64-bit max (batched launch, monotone clocks) or a
+    // plain store (per-reading launches: exact overwrite semantics of MarkGridPoint, .cpp:421-430)
+#pragma unroll
+    for (int i = threadIdx.x; i < kMarkTable * 16; i += kMarkThreads) {
+      uint32_t m = (&s_mask[0][0])[i];
+      if (!m) continue;
+      (&s_mask[0][0])[i] = 0;
+      const uint32_t slot = s_slot[i >> 4];
+      if (slot == kOverflowSlot) continue;
+      const double now = s_now[i >> 4];
+      const unsigned long long now_bits = (unsigned long long)__double_as_longlong(now);
+      const unsigned w = i & 15;
+      red_or_u32(&g.leaf_mask[(size_t)slot * 16 + w], m);
+      double * tp = g.leaf_time + (size_t)slot * kLeafVoxels + w * 32;
+      if (!use_max && g.leaf_tmin[slot] > now) g.leaf_tmin[slot] = -CUDART_INF;   // clocks are not monotone here
+      while (m) {
+        const int b = __ffs(m) - 1; m &= m - 1;
+        if (use_max) red_max_u64(reinterpret_cast<unsigned long long *>(tp + b), now_bits);
+        else tp[b] = now;
+      }
+    }
+    __syncthreads();
+  };
+
+  for (uint32_t it = 0; chunk < total; ++it) {
+    const int stage = (int)(it & 1u);
     PointXYZ pts[kMarkPointsPerThread];
     if constexpr (!kVec4) {
 #pragma unroll
       for (int k = 0; k < kMarkPointsPerThread; ++k) pts[k] = nxt[k];
     }
-    // prefetch the next chunk of this CTA (it may already belong to the next reading)
-    const bool last = chunk + 1 == chunk_end;
+    // start the loads of this CTA's next chunk
+    const uint32_t chunk_next = chunk + gridDim.x;
+    const bool last = chunk_next >= total;
     int ri_next = ri;
     if (!last) {
-      if (ri + 1 < (int)batch.n_readings && chunk + 1 >= batch.first_block[ri + 1]) ri_next = ri + 1;
-      prefetch(ri_next, chunk + 1, stage ^ 1);
+      ri_next = mark_reading_of(batch, chunk_next);
+      prefetch(ri_next, chunk_next, stage ^ 1);
     }
+    const DevReading & par = batch.r[ri];   // warp-uniform parameter-bank reads
     if constexpr (kVec4) {
       // every thread only reads what it copied itself: waiting for its own cp.async group is enough
       if (last) __pipeline_wait_prior(0); else __pipeline_wait_prior(1);
       const unsigned long long base = (unsigned long long)(chunk - batch.first_block[ri]) * kMarkPointsPerBlock;
-      const unsigned long long n_pts = batch.r[ri].n_points;
+      const unsigned long long n_pts = par.n_points;
 #pragma unroll
       for (int k = 0; k < kMarkPointsPerThread; ++k) {
         const float4 v = s_stage[stage * kMarkPointsPerBlock + k * kMarkThreads + threadIdx.x];
@@ -467,17 +515,17 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
         pts[k].ok = base + (unsigned long long)k * kMarkThreads + threadIdx.x < n_pts;
       }
     }
+    if (it == 0) TRACE(0, 2);   // first chunk's data has arrived
 
-    if (chunk == chunk_begin) TRACE(0, 2);   // first chunk's data has arrived
     // ---- cheap rejection first (branch-free): depth images are full of invalid pixels and floor / ceiling returns
-    const double ox = s_par.ox, oy = s_par.oy, oz = s_par.oz;
-    const float range2 = s_par.mark_range_2, range2_reject = s_par.range2_reject;
-    const float oxf = s_par.oxf, oyf = s_par.oyf, ozf = s_par.ozf;
-    const bool zwin = s_par.filter == 2;
-    const float zlo = zwin ? s_par.zmin_f : -CUDART_INF_F, zhi = zwin ? s_par.zmax_f : CUDART_INF_F;
-    if (s_par.has_tf) {   // cloud still in the sensor frame: tf2::doTransform first (measurement_buffer.cpp:141-146)
+    const double ox = par.ox, oy = par.oy, oz = par.oz, now_r = par.now;
+    const float range2 = par.mark_range_2, range2_reject = par.range2_reject;
+    const float oxf = par.oxf, oyf = par.oyf, ozf = par.ozf;
+    const bool zwin = par.filter == 2;
+    const float zlo = zwin ? par.zmin_f : -CUDART_INF_F, zhi = zwin ? par.zmax_f : CUDART_INF_F;
+    if (par.has_tf) {   // cloud still in the sensor frame: tf2::doTransform first (measurement_buffer.cpp:141-146)
 #pragma unroll
-      for (int k = 0; k < kMarkPointsPerThread; ++k) transform_point(s_par.tf, pts[k].x, pts[k].y, pts[k].z);
+      for (int k = 0; k < kMarkPointsPerThread; ++k) transform_point(par.tf, pts[k].x, pts[k].y, pts[k].z);
     }
     bool pre[kMarkPointsPerThread];
 #pragma unroll
@@ -511,92 +559,40 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
       const int ix = __double2int_rz(gx), iy = __double2int_rz(gy), iz = __double2int_rz(gz);
       const int bx = ix >> 3, by = iy >> 3, bz = iz >> 3;
       if (g.shard_count > 1 && !shard_owns(bx, g.shard_index, g.shard_count, g.shard_width)) continue;
-      const uint64_t key = pack_leaf_key(bx, by, bz);
       const unsigned l = (unsigned)(((ix & 7) * 8 + (iy & 7)) * 8 + (iz & 7));
-      // find-or-claim the leaf in the block-local table (consecutive points of a thread mostly share their leaf)
+      // find-or-claim the (reading, leaf) in the block-local table (consecutive points of a thread mostly share it)
+      const int rx = bx - batch.ref_bx;
+      const bool in_reach = rx >= -kMarkRelBias && rx < kMarkRelBias;
+      const uint64_t key = pack_table_key(ri, rx, by, bz);
       int e = -1;
-      if (key == last_key) e = last_e;
-      else {
-        uint32_t h = ((uint32_t)bx * 73856093u ^ (uint32_t)by * 19349663u ^ (uint32_t)bz * 83492791u) & (kMarkTable - 1);
+      if (in_reach) {
+        if (key == last_key) e = last_e;
+        else {
+          uint32_t h = ((uint32_t)bx * 73856093u ^ (uint32_t)by * 19349663u ^ (uint32_t)bz * 83492791u ^ (uint32_t)ri * 2654435761u) & (kMarkTable - 1);
 #pragma unroll 1
-        for (int p = 0; p < kMarkProbes; ++p) {
-          unsigned long long cur = s_key[h];
-          if (cur == kEmptyKey) cur = atomicCAS(&s_key[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
-          if (cur == key || cur == kEmptyKey) { e = (int)h; break; }
-          h = (h + 1) & (kMarkTable - 1);
+          for (int p = 0; p < kMarkProbes; ++p) {
+            unsigned long long cur = s_key[h];
+            if (cur == kEmptyKey) cur = atomicCAS(&s_key[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
+            if (cur == key || cur == kEmptyKey) { e = (int)h; break; }
+            h = (h + 1) & (kMarkTable - 1);
+          }
+          last_key = key; last_e = e;
         }
-        last_key = key; last_e = e;
       }
       if (e >= 0) {
         const uint32_t bit = 1u << (l & 31);
         if (!(s_mask[e][l >> 5] & bit)) atomicOr(&s_mask[e][l >> 5], bit);
-      } else {   // table full (scattered cloud): straight to the global store
+      } else {   // table full (scattered cloud) or leaf out of the table's reach: straight to the global store
         sync_with_predecessor();
-        mark_voxel_direct(g, key, l, s_par.now, (unsigned long long)__double_as_longlong(s_par.now), use_max, free_n0, high_water0, batch.min_now);
+        mark_voxel_direct(g, pack_leaf_key(bx, by, bz), l, now_r, (unsigned long long)__double_as_longlong(now_r), use_max,
+                          free_n0, high_water0, batch.min_now);
       }
     }
-
-    // ---- flush at the end of the range or when the next chunk belongs to another reading -----------------------------
-    if (last || ri_next != ri) {
-      __syncthreads();
-      if (last) {
-        TRACE(0, 3);   // all chunks processed
-        pdl_launch_dependents();   // the next cycle's triage kernel may become resident and stage its parameters
-      }
-      sync_with_predecessor();
-      if constexpr (kCostmap) {
-        // the costmap pass rides on the warps that would otherwise idle while warps 0-1 resolve the leaves
-        if (last && threadIdx.x >= kMarkTable) {
-          const uint32_t n_tiles = min(ld_volatile_u32(&g.ctr->tile_n), g.tile_capacity);
-          constexpr uint32_t kCmWarps = (kMarkThreads - kMarkTable) / 32, kCmBatch = 4;
-          const uint32_t cw = blockIdx.x * kCmWarps + ((threadIdx.x - kMarkTable) >> 5);
-          for (uint32_t t0 = cw * kCmBatch; t0 < n_tiles; t0 += gridDim.x * kCmWarps * kCmBatch)
-            costmap_tile_batch<(int)kCmBatch>(g, cm, costmap, t0, n_tiles, lane, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy);
-        }
-      }
-      if (threadIdx.x < kMarkTable) {   // one thread per distinct leaf resolves (or creates) it in the global hash
-        const unsigned long long key = s_key[threadIdx.x];
-        uint32_t slot = kOverflowSlot;
-        if (key != kEmptyKey) {
-          int bx, by, bz;
-          unpack_leaf_key(key, bx, by, bz);
-          slot = leaf_find_or_insert(g, key, bx, by, free_n0, high_water0, batch.min_now);
-        }
-        s_slot[threadIdx.x] = slot;
-      }
-      __syncthreads();
-      if (last) TRACE(0, 4);   // leaves resolved in the global hash
-      // per touched mask word one 32-bit OR, per distinct voxel one 64-bit max (batched launch, monotone clocks) or a
-      // plain store (per-reading launches: exact overwrite semantics of MarkGridPoint, .cpp:421-430)
-      const double now = s_par.now;
-      const unsigned long long now_bits = (unsigned long long)__double_as_longlong(now);
-#pragma unroll
-      for (int i = threadIdx.x; i < kMarkTable * 16; i += kMarkThreads) {
-        uint32_t m = (&s_mask[0][0])[i];
-        if (!m) continue;
-        (&s_mask[0][0])[i] = 0;
-        const uint32_t slot = s_slot[i >> 4];
-        if (slot == kOverflowSlot) continue;
-        const unsigned w = i & 15;
-        red_or_u32(&g.leaf_mask[(size_t)slot * 16 + w], m);
-        double * tp = g.leaf_time + (size_t)slot * kLeafVoxels + w * 32;
-        if (!use_max && g.leaf_tmin[slot] > now) g.leaf_tmin[slot] = -CUDART_INF;   // clocks are not monotone here
-        while (m) {
-          const int b = __ffs(m) - 1; m &= m - 1;
-          if (use_max) red_max_u64(reinterpret_cast<unsigned long long *>(tp + b), now_bits);
-          else tp[b] = now;
-        }
-      }
-      __syncthreads();
-      if (!last) {   // next reading: fresh table, new parameters
-        if (threadIdx.x < kMarkTable) s_key[threadIdx.x] = kEmptyKey;
-        last_key = kEmptyKey; last_e = -1;
-        if (threadIdx.x == 0) mark_params_from(s_par, batch.r[ri_next]);
-        __syncthreads();
-      }
-    }
+    chunk = chunk_next;
     ri = ri_next;
   }
+  __syncthreads();
+  flush(true);
 
   TRACE(0, 5);   // flushed
   // dropped-point statistics: warp reduce, shared-memory add, one global atomic per CTA
@@ -614,15 +610,19 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const uin
   __syncthreads();
   if constexpr (kCostmap) costmap_reduce_and_publish(g.ctr, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy, false);
   if (threadIdx.x == 0) {
-    if (s_drop[0]) atomicAdd(&g.ctr->dropped_range, (unsigned long long)s_drop[0]);
-    if (s_drop[1]) atomicAdd(&g.ctr->dropped_nonfinite, (unsigned long long)s_drop[1]);
-    // the last CTA commits the leaves handed out by this launch to the allocator state (and publishes the costmap result)
+    if (s_drop[0]) atomicAdd(&g.ctr->dropped_range, (unsigned long long)s_drop[0]);   // rare: points beyond +-2^23 voxels
+    // One atomic per CTA: the ticket also carries this CTA's non-finite point count (every CTA of a depth image has some;
+    // separate counters on the same cache line tripled the same-address atomic traffic when all CTAs finish together).
+    // The last CTA commits the leaves handed out by this launch to the allocator state (and publishes the costmap result).
     __threadfence();
-    if (atomicAdd(&g.ctr->mark_ticket, 1u) == gridDim.x - 1) {
+    const unsigned long long mine = 1ull + ((unsigned long long)s_drop[1] << 16);
+    const unsigned long long before = atomicAdd(&g.ctr->mark_ticket64, mine);
+    if ((before & 0xFFFFull) == (unsigned long long)(gridDim.x - 1)) {
       __threadfence();
       fold_alloc(g);
       if constexpr (kCostmap) costmap_publish_result(g.ctr);
-      g.ctr->mark_ticket = 0;
+      g.ctr->dropped_nonfinite += (before + mine) >> 16;
+      g.ctr->mark_ticket64 = 0;
       __threadfence();
     }
     TRACE(0, 6);
@@ -1398,11 +1398,12 @@ static cudaError_t launch_mark_variant(const GridView & g, const MarkBatch & bat
     const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mark_kernel<kVec4, kCostmap>, kMarkThreads, smem);
     occ = (e == cudaSuccess && n >= 1) ? n : 4;
   }
-  // persistent CTAs, as many as are resident at once: each loops over chunks with the next chunk's loads in flight
+  // persistent CTAs, as many as are resident at once: CTA b takes chunks b, b + grid, ... with the next one's loads in flight
+  // (sized so that every CTA gets the same number of chunks, +-1)
   const uint32_t resident = (uint32_t)sm_count * (uint32_t)occ;
   const uint32_t chunks_per_cta = (batch.total_blocks + resident - 1) / resident;
-  const uint32_t grid = (batch.total_blocks + chunks_per_cta - 1) / chunks_per_cta;
-  return launch_ex(mark_kernel<kVec4, kCostmap>, grid, kMarkThreads, smem, s, pdl, g, batch, chunks_per_cta, cm, costmap);
+  const uint32_t grid = std::min<uint32_t>(65535u, (batch.total_blocks + chunks_per_cta - 1) / chunks_per_cta);
+  return launch_ex(mark_kernel<kVec4, kCostmap>, grid, kMarkThreads, smem, s, pdl, g, batch, cm, costmap);
 }
 // pdl: the caller guarantees that the kernel's inputs (clouds) were complete before the PREDECESSOR of this launch in the
 // stream started, and that the predecessor is one of this library's sweep kernels.  cm / costmap != NULL: fused costmap pass.
