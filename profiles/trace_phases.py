@@ -110,6 +110,21 @@ def main():
             if ok.any():
                 d = (b - a)[ok] / 1e3
                 print("     d(%s -> %s): median %.2f  p90 %.2f  max %.2f us" % (phases[ph - 1], phases[ph], np.median(d), np.percentile(d, 90), d.max()))
+    # the slowest CTAs of the leaf pass (blockIdx < n_dense_ctas = 2 x SMs take the dense leaves)
+    k = 2
+    a, b = tr[k, :, 2].astype(np.int64), tr[k, :, 3].astype(np.int64)
+    ok = (a > 0) & (b > a)
+    idx = np.nonzero(ok)[0]
+    d = (b - a)[ok] / 1e3
+    top = np.argsort(-d)[:12]
+    print("slowest leaf-pass CTAs (queue_n read -> leaves done): " + ", ".join(
+        "cta %d: %.2f us (warp0: %d leaves, lane0 %d voxels)" % (idx[t], d[t], tr[k, idx[t], 5], tr[k, idx[t], 6]) for t in top))
+    dd = d[idx < 296]
+    ds = d[idx >= 296]
+    if len(dd):
+        print("dense CTAs: n=%d median %.2f p90 %.2f max %.2f us" % (len(dd), np.median(dd), np.percentile(dd, 90), dd.max()))
+    if len(ds):
+        print("sparse CTAs: n=%d median %.2f p90 %.2f max %.2f us" % (len(ds), np.median(ds), np.percentile(ds, 90), ds.max()))
     g.close()
 
 

@@ -53,7 +53,8 @@ struct Counters {
   uint32_t tile_n;
   uint32_t tile_overflow;
   // last-CTA-done tickets (each kernel's last CTA commits / re-arms shared state)
-  uint32_t mark_ticket, leaf_ticket, cm_ticket, pad1;
+  uint32_t mark_ticket, leaf_ticket, cm_ticket;
+  uint32_t dense_n;        // densely populated leaves queued for pass 2, stored from the END of sweep_queue (four warps each)
   // dropped input points
   unsigned long long dropped_range, dropped_nonfinite;
   // Mark's last-CTA ticket: low 16 bits count the CTAs that are done, the upper 48 accumulate their non-finite point

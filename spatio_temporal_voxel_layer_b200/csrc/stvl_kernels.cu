@@ -167,8 +167,10 @@ extern "C" int stvl_debug_trace(void * out, size_t bytes)
   return 0;
 }
 #define TRACE(k, ph) trace_stamp(k, ph)
+#define TRACE_VAL(k, ph, v) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_trace[k][blockIdx.x][ph] = (unsigned long long)(v); } while (0)
 #else
 #define TRACE(k, ph) ((void)0)
+#define TRACE_VAL(k, ph, v) ((void)0)
 #endif
 
 // =====================================================================================
@@ -659,6 +661,7 @@ load_voxels_kernel(const GridView g, const int32_t * __restrict__ vx, const int3
 // =====================================================================================
 constexpr int kSweepThreads = 256;
 constexpr int kSweepWarps = kSweepThreads / 32;
+constexpr int kDenseLeafVoxels = 33;    // leaves with more than one 32-voxel batch take the CTA-per-leaf path of pass 2
 
 // classify a whole leaf against one frustum: 0 = no voxel centre can be inside, 1 = test per voxel, 2 = all inside
 __device__ __forceinline__ int classify_leaf(const DevFrustum & f, int bx, int by, int bz, double vs, double half_vs)
@@ -835,7 +838,14 @@ sweep_triage_kernel(const GridView g, const __grid_constant__ FrustumParams fpar
       }
     }
     if (full_path) {
-      g.sweep_queue[atomicAdd(&g.ctr->queue_n, 1u)] = slot;
+      // leaves with more than one 32-voxel batch are processed by a whole CTA (the per-voxel pass of a leaf is a long
+      // dependent chain of exact double arithmetic: ~2 us per batch, the critical path of the whole sweep when one
+      // warp walks 4-16 batches).  They are queued from the end of the queue array.
+      unsigned pc = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pc += __popc(mw[q].x) + __popc(mw[q].y) + __popc(mw[q].z) + __popc(mw[q].w);
+      if (pc >= (unsigned)kDenseLeafVoxels) g.sweep_queue[g.leaf_capacity - 1u - atomicAdd(&g.ctr->dense_n, 1u)] = slot;
+      else g.sweep_queue[atomicAdd(&g.ctr->queue_n, 1u)] = slot;
       continue;
     }
     // PopulateCostmapAndPointcloud .cpp:242-250 for every (surviving) voxel: per-column popcounts, two adjacent u32
@@ -875,26 +885,30 @@ __device__ __forceinline__ void leaf_pass_done(const GridView & g)
   __threadfence();
   if (atomicAdd(&g.ctr->leaf_ticket, 1u) == gridDim.x - 1) {
     g.ctr->queue_n = 0;
+    g.ctr->dense_n = 0;
     g.ctr->leaf_ticket = 0;
     __threadfence();
   }
 }
 
-// Sweep, pass 2 — ONE WARP PER QUEUED LEAF: leaf-level frustum classification, exact per-voxel frustum tests, decay,
-// rewrite of accelerated mark times, clearing (reference .cpp:158-221).
+// Sweep, pass 2 — ONE WARP PER QUEUED LEAF (CTAs >= n_dense_ctas) or ONE CTA PER DENSE LEAF, each of its eight warps
+// taking every eighth 32-voxel batch of the leaf's compacted voxel list (CTAs < n_dense_ctas): leaf-level frustum classification, exact per-voxel frustum tests,
+// decay, rewrite of accelerated mark times, clearing (reference .cpp:158-221).
 __global__ void __launch_bounds__(kSweepThreads, 4)
 sweep_leaf_kernel(const GridView g, const __grid_constant__ FrustumParams fparam, const DevFrustum * __restrict__ frustums_gmem,
-                  const int n_frustums, const double now, const SweepOutputs out)
+                  const int n_frustums, const double now, const SweepOutputs out, const uint32_t n_dense_ctas)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevFrustum * fr = reinterpret_cast<DevFrustum *>(smem_raw);
   __shared__ uint16_t s_list[kSweepWarps][kLeafVoxels];
-  __shared__ uint32_t s_mask[kSweepWarps][16];
+  __shared__ uint32_t s_mask[2][kSweepWarps][16];   // [iteration parity]: quarter 0 of a dense leaf reads its siblings' copies
   __shared__ uint32_t s_part[kSweepWarps][kMaxFrustums / 32];
   __shared__ uint32_t s_full[kSweepWarps][kMaxFrustums / 32];
   __shared__ double s_val[kSweepWarps][128];
+  __shared__ double s_pmin[2][kSweepWarps];   // dense leaves: [iteration parity][warp] smallest surviving time of the warp's batches
   const unsigned lane = threadIdx.x & 31;
   const unsigned warp = threadIdx.x >> 5;
+  const bool dense = blockIdx.x < n_dense_ctas;
   const uint16_t * mask16 = reinterpret_cast<const uint16_t *>(g.leaf_mask);
   TRACE(2, 0);
   // Programmatic dependent launch: this grid becomes resident while the triage pass is still running and lets Mark do
@@ -906,16 +920,19 @@ sweep_leaf_kernel(const GridView g, const __grid_constant__ FrustumParams fparam
   // Shorten the dependent-load chain of a warp's first leaf: its queue entry and leaf header are requested
   // speculatively, together with the queue length (a stale queue entry is still a valid slot index, so the wasted
   // loads are harmless).
-  const uint32_t qi0 = blockIdx.x * kSweepWarps + warp;
-  uint32_t slot0 = qi0 < g.leaf_capacity ? g.sweep_queue[qi0] : 0u;
+  // work items: dense CTA b takes dense leaf number b (stored from the end of the queue array), the others queue
+  // entry (blockIdx - n_dense_ctas) * 8 + warp
+  const uint32_t qi0 = dense ? blockIdx.x : (blockIdx.x - n_dense_ctas) * kSweepWarps + warp;
+  const uint32_t q_stride = dense ? n_dense_ctas : (gridDim.x - n_dense_ctas) * kSweepWarps;
+  uint32_t slot0 = qi0 < g.leaf_capacity ? g.sweep_queue[dense ? g.leaf_capacity - 1u - qi0 : qi0] : 0u;
   if (slot0 >= g.leaf_capacity) slot0 = 0;
   const uint64_t key0 = g.leaf_key[slot0];
   const uint32_t m16_0 = mask16[(size_t)slot0 * 32 + lane];
   const uint32_t tile0 = g.leaf_tile[slot0];
   const double tmin0 = g.leaf_tmin[slot0];
-  const uint32_t n_queued = g.ctr->queue_n;
+  const uint32_t n_queued = dense ? g.ctr->dense_n : g.ctr->queue_n;
   TRACE(2, 2);
-  if (blockIdx.x * kSweepWarps >= n_queued) {   // nothing for this CTA (uniform per block)
+  if ((dense ? blockIdx.x : (blockIdx.x - n_dense_ctas) * kSweepWarps) >= n_queued) {   // nothing for this CTA (uniform per block)
     if (threadIdx.x == 0) leaf_pass_done(g);
     return;
   }
@@ -925,11 +942,13 @@ sweep_leaf_kernel(const GridView g, const __grid_constant__ FrustumParams fparam
   unsigned int c_swept = 0, c_surv = 0, c_clear = 0, c_rewr = 0, c_amb = 0;
   int bb_min_x = INT_MAX, bb_min_y = INT_MAX, bb_max_x = INT_MIN, bb_max_y = INT_MIN;
 
-  for (uint32_t qi = blockIdx.x * kSweepWarps + warp; qi < n_queued; qi += gridDim.x * kSweepWarps) {
+  uint32_t iter = 0;
+  for (uint32_t qi = qi0; qi < n_queued; qi += q_stride, ++iter) {
     const bool first = qi == qi0;
-    const uint32_t slot = first ? slot0 : g.sweep_queue[qi];
+    const uint32_t slot = first ? slot0 : g.sweep_queue[dense ? g.leaf_capacity - 1u - qi : qi];
     const uint64_t key = first ? key0 : g.leaf_key[slot];
     const uint32_t m16 = first ? m16_0 : mask16[(size_t)slot * 32 + lane];   // each lane owns two voxel columns = local indices [lane*16, lane*16+16)
+    uint32_t (* const my_mask)[16] = s_mask[iter & 1];
     const uint32_t tile = first ? tile0 : g.leaf_tile[slot];
     const double tmin = first ? tmin0 : g.leaf_tmin[slot];
 
@@ -947,6 +966,7 @@ sweep_leaf_kernel(const GridView g, const __grid_constant__ FrustumParams fparam
     // temporal culling: outside every frustum and too young to expire -> the 4 KB time block is never touched
     if (!any_cand && skip_model_ok) {
       if (!leaf_may_expire(g, now, tmin)) {
+        if (dense && warp != 0) continue;   // (all warps of a dense leaf's CTA get here: one of them counts)
         const unsigned cnt = __popc(m16);
         c_swept += cnt; c_surv += cnt;
         if (tile != kOverflowSlot) {
@@ -973,19 +993,22 @@ sweep_leaf_kernel(const GridView g, const __grid_constant__ FrustumParams fparam
       const uint32_t lo = __shfl_sync(kFull, m16, (2 * lane) & 31), hi = __shfl_sync(kFull, m16, (2 * lane + 1) & 31);
       w_orig = lo | (hi << 16);
     }
-    if (lane < 16) s_mask[warp][lane] = w_orig;
+    if (lane < 16) my_mask[warp][lane] = w_orig;
 
     __syncwarp();
 
     const double * tbase = g.leaf_time + (size_t)slot * kLeafVoxels;
     double vmin = CUDART_INF;   // smallest mark time among this leaf's survivors
-    for (int i0 = 0; i0 < total; i0 += 32) {
-      // the mark times of up to four 32-voxel batches are requested together (one DRAM round trip per 128 voxels)
-      if ((i0 & 127) == 0) {
+    // 32-voxel batches of the compacted list: all of them (one warp per leaf) or every eighth (dense leaf, CTA per leaf)
+    const int bstep = dense ? kSweepWarps : 1;
+    int nb = 0;
+    for (int i0 = (dense ? (int)warp : 0) * 32; i0 < total; i0 += 32 * bstep, ++nb) {
+      // the mark times of this warp's next four batches are requested together (one DRAM round trip per 128 voxels)
+      if ((nb & 3) == 0) {
         double pv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int j = i0 + u * 32 + (int)lane;
+          const int j = i0 + u * 32 * bstep + (int)lane;
           pv[u] = j < total ? __ldcs(tbase + s_list[warp][j]) : 0.0;
         }
 #pragma unroll
@@ -999,7 +1022,7 @@ sweep_leaf_kernel(const GridView g, const __grid_constant__ FrustumParams fparam
       unsigned li = 0;
       if (have) {
         li = s_list[warp][i];
-        const double v = s_val[warp][(i0 & 127) + lane];
+        const double v = s_val[warp][(nb & 3) * 32 + lane];
         ix = bx * 8 + (int)(li >> 6); iy = by * 8 + (int)((li >> 3) & 7); iz = bz * 8 + (int)(li & 7);
         ++c_swept;
         // .cpp:167-169
@@ -1045,7 +1068,7 @@ sweep_leaf_kernel(const GridView g, const __grid_constant__ FrustumParams fparam
         }
         survived = !cleared;
         if (cleared) {
-          atomicAnd(&s_mask[warp][li >> 5], ~(1u << (li & 31)));
+          atomicAnd(&my_mask[warp][li >> 5], ~(1u << (li & 31)));
           ++c_clear;
           bb_min_x = min(bb_min_x, ix); bb_max_x = max(bb_max_x, ix);
           bb_min_y = min(bb_min_y, iy); bb_max_y = max(bb_max_y, iy);
@@ -1092,19 +1115,37 @@ sweep_leaf_kernel(const GridView g, const __grid_constant__ FrustumParams fparam
     }
     __syncwarp();
     // write back changed mask words; count survivors per (x,y) column into the leaf's column tile
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) vmin = fmin(vmin, __shfl_xor_sync(kFull, vmin, d));
+    if (dense) {
+      // The warps of a dense leaf's CTA each cleared bits in their own copy of the mask: they meet at a barrier (they
+      // all run the same iterations) and warp 0 combines the copies and takes the leaf-level decisions.  Everything
+      // shared is double-buffered by iteration parity: a warp can only write the same buffer again after the NEXT
+      // barrier, which warp 0 reaches after it has read this one.
+      if (lane == 0) s_pmin[iter & 1][warp] = vmin;
+      __syncthreads();
+      if (warp != 0) continue;
+#pragma unroll
+      for (int k = 1; k < kSweepWarps; ++k) vmin = fmin(vmin, s_pmin[iter & 1][k]);
+      if (lane < 16) {
+        uint32_t a = my_mask[0][lane];
+#pragma unroll
+        for (int k = 1; k < kSweepWarps; ++k) a &= my_mask[k][lane];
+        my_mask[0][lane] = a;
+      }
+      __syncwarp();
+    }
     uint32_t w = 0;
     if (lane < 16) {
-      w = s_mask[warp][lane];
+      w = my_mask[warp][lane];
       if (w != w_orig) g.leaf_mask[(size_t)slot * 16 + lane] = w;
     }
     const bool leaf_alive = __ballot_sync(kFull, w != 0) != 0;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) vmin = fmin(vmin, __shfl_xor_sync(kFull, vmin, d));
     if (leaf_alive && lane == 0 && !(vmin == tmin)) g.leaf_tmin[slot] = vmin;   // exact lower bound again
     if (!leaf_alive) {
       if (lane == 0) free_leaf(g, slot);
     } else if (tile != kOverflowSlot) {
-      const uint32_t two = reinterpret_cast<const uint16_t *>(s_mask[warp])[lane];
+      const uint32_t two = reinterpret_cast<const uint16_t *>(my_mask[warp])[lane];
       const unsigned long long c0 = __popc(two & 0xFFu), c1 = __popc(two >> 8);
       // PopulateCostmapAndPointcloud .cpp:242-250: _cost_map[(x,y)] += 1 per surviving voxel.  The two adjacent
       // u32 column counters of this lane are bumped by ONE 64-bit reduction (no carry: counts stay < 2^32)
@@ -1116,6 +1157,8 @@ sweep_leaf_kernel(const GridView g, const __grid_constant__ FrustumParams fparam
   SweepAcc acc;
   acc.swept = c_swept; acc.surv = c_surv; acc.clear = c_clear; acc.rewr = c_rewr; acc.amb = c_amb;
   acc.min_x = bb_min_x; acc.min_y = bb_min_y; acc.max_x = bb_max_x; acc.max_y = bb_max_y;
+  TRACE_VAL(2, 5, iter);       // leaves this warp went through
+  TRACE_VAL(2, 6, c_swept);    // voxels lane 0 of warp 0 tested
   __syncthreads();
   TRACE(2, 3);
   sweep_publish(g, acc);
@@ -1451,13 +1494,20 @@ cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, co
   const int force_full = out.points ? 1 : 0;
   // Both passes are launched programmatically: everything they do before pdl_wait() only touches kernel parameters /
   // the frustum buffer, so the attribute is safe whatever precedes them on the stream.
-  e = launch_ex(sweep_triage_kernel, (unsigned)grid_for(leaf_slots_upper_bound, kSweepThreads, sm_count * 8), kSweepThreads, dyn, s, true,
+  // Grid sizes: every kernel of the cycle is grid-stride, and under programmatic dependent launch a kernel only starts
+  // once ALL CTAs of its predecessor are resident — so the grids are kept to a fraction of a wave (the leaf pass and
+  // Mark get their turn early) unless the pool is large enough to need the extra memory parallelism.
+  const int triage_cap = sm_count * (leaf_slots_upper_bound > (1u << 18) ? 6 : 2);
+  e = launch_ex(sweep_triage_kernel, (unsigned)grid_for(leaf_slots_upper_bound, kSweepThreads, triage_cap), kSweepThreads, dyn, s, true,
                 g, fp, frustums_dev, n_frustums, now, force_full, costmap_reset, (unsigned long long)costmap_bytes, costmap_value);
   if (e != cudaSuccess) return e;
   // pass 2: one warp per queued leaf; the queue length is only known on the device, CTAs without work exit at once.
   // Programmatic dependent launch: its CTAs become resident (and stage the frustum blocks) while pass 1 drains.
-  return launch_ex(sweep_leaf_kernel, (unsigned)grid_for(leaf_slots_upper_bound, kSweepWarps, sm_count * 4), kSweepThreads, dyn, s, true,
-                   g, fp, frustums_dev, n_frustums, now, out);
+  // The first CTAs take the leaves with more than one 32-voxel batch (a CTA per leaf), the others one leaf per warp.
+  const unsigned n_dense_ctas = (unsigned)grid_for(leaf_slots_upper_bound, 1, sm_count * 2);
+  const unsigned n_sparse_ctas = (unsigned)grid_for(leaf_slots_upper_bound, kSweepWarps, sm_count * 2);
+  return launch_ex(sweep_leaf_kernel, n_dense_ctas + n_sparse_ctas, kSweepThreads, dyn, s, true,
+                   g, fp, frustums_dev, n_frustums, now, out, (uint32_t)n_dense_ctas);
 }
 cudaError_t launch_costmap(const GridView & g, const CostmapDev & p, uint8_t * costmap_dev, uint32_t tiles_upper_bound, int sm_count, cudaStream_t s,
                            bool fill_default)
