@@ -109,6 +109,7 @@ struct stvl_grid {
   int sweep_parity = 0;
   bool alloc_dirty = false;         // a Mark / load kernel handed out leaves that are not folded into the allocator yet
   uint64_t launches = 0;
+  uint32_t mark_cursor_sel = 0;     // chunk cursor of the next Mark launch (they alternate)
   size_t device_bytes = 0;
   // in-library sharded merge (stvl_comm_init / stvl_costmap_sharded_device)
   ncclComm_t comm = nullptr;
@@ -396,7 +397,10 @@ int launch_batches(stvl_grid * g, const std::vector<MarkBatch> & batches, CycleF
     int rc = ensure_folded(g);   // (only a preceding bulk load leaves the allocator unfolded; Mark kernels fold themselves)
     if (rc != STVL_OK) return rc;
     const bool carry = fz && fz->costmap && !fz->costmap_done && i + 1 == batches.size();
-    CU(launch_mark(g->v, batches[i], g->sm_count, g->stream, pdl, carry ? &fz->cm : nullptr, carry ? fz->costmap : nullptr));
+    MarkBatch b = batches[i];
+    b.cursor_sel = g->mark_cursor_sel;
+    g->mark_cursor_sel ^= 1u;
+    CU(launch_mark(g->v, b, g->sm_count, g->stream, pdl, carry ? &fz->cm : nullptr, carry ? fz->costmap : nullptr));
     if (carry) fz->costmap_done = true;
     pdl = false;                       // only the first launch follows the sweep
     g->launches += 1;

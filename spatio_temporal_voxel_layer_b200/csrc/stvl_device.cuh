@@ -55,6 +55,10 @@ struct Counters {
   // last-CTA-done tickets (each kernel's last CTA commits / re-arms shared state)
   uint32_t mark_ticket, leaf_ticket, cm_ticket;
   uint32_t dense_n;        // densely populated leaves queued for pass 2, stored from the END of sweep_queue (four warps each)
+  // next unclaimed 1024-point chunk of the running Mark kernel, re-armed by its last CTA.  Two cursors used alternately:
+  // under programmatic dependent launch the first CTAs of the next cycle's Mark may pull chunks while the last CTA of
+  // this one has not re-armed its cursor yet
+  uint32_t mark_cursor[2];
   // dropped input points
   unsigned long long dropped_range, dropped_nonfinite;
   // Mark's last-CTA ticket: low 16 bits count the CTAs that are done, the upper 48 accumulate their non-finite point
@@ -152,6 +156,8 @@ struct MarkBatch {
   uint32_t total_blocks;
   uint32_t use_atomic_max;  // 1: batched mode (monotone clocks), 0: plain stores
   int32_t ref_bx;           // reference leaf x of the batch (first reading's origin): block-local table keys store bx - ref_bx
+  uint32_t cursor_sel;      // which Counters::mark_cursor this launch uses (set at launch)
+  uint32_t pad;
   double min_now;           // smallest clock sample in the batch: initial leaf_tmin of leaves created by it
 };
 

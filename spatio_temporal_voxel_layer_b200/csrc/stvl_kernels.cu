@@ -325,11 +325,12 @@ __device__ __forceinline__ void mark_voxel_direct(const GridView & g, uint64_t k
   }
 }
 
-// Mark — persistent CTAs; CTA b processes the 1024-point chunks b, b + gridDim, b + 2 gridDim, ... of the batched clouds
-// (interleaved: neighbouring chunks of a depth image have the same share of invalid / out-of-range pixels, so every
-// CTA gets the same mix):
+// Mark — persistent CTAs that pull 1024-point chunks of the batched clouds from a device-side cursor:
 //   1. packed clouds are streamed global -> shared memory with cp.async, the NEXT chunk in flight while the current one
-//      is processed; every thread only reads back what it copied itself, so the chunk loop has no barrier at all
+//      is processed (the id of the chunk after that is requested from the cursor at the same time, so the atomic's
+//      latency is hidden too).  Dynamic chunks keep every resident CTA busy whatever the mix of valid / invalid pixels,
+//      and — under programmatic dependent launch — the CTAs that become resident early, while the sweep still occupies
+//      most of the SMs, take most of the work; CTAs that only become resident late find the cursor exhausted.
 //   2. range / z-window tests and key quantisation in the reference's exact arithmetic (.cpp:285-303), written
 //      branch-free so the four points of a thread advance together
 //   3. block-level dedupe in shared memory: a depth image puts ~100 points into every voxel and ~1000 into every
@@ -368,6 +369,7 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const Cos
   __shared__ uint32_t s_slot[kMarkTable];
   __shared__ double s_now[kMarkTable];
   __shared__ unsigned int s_drop[2];
+  __shared__ uint32_t s_ids[2];        // chunk ids handed to this CTA by the cursor (for iterations i+1, i+2)
   TRACE(0, 0);
   // The reading descriptors stay in the kernel-parameter bank and are only ever read with warp-uniform addresses
   // (every thread of the CTA reads the same field of the same reading): per-thread addresses into the constant bank
@@ -377,7 +379,13 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const Cos
   const uint32_t total = batch.total_blocks;
   // Everything up to the flush only reads the clouds and the kernel parameters, so under programmatic dependent
   // launch it overlaps the tail of the sweep; the grid state (allocator counters, hash, leaves) is touched only after
-  // sync_with_predecessor().
+  // sync_with_predecessor().  (The chunk cursor is only ever touched by Mark kernels, and consecutive launches alternate
+  // between two cursors, see Counters::mark_cursor.)
+  uint32_t * const cursor = &g.ctr->mark_cursor[batch.cursor_sel & 1u];
+  if (threadIdx.x == 0) {   // the first two chunks of this CTA: requested before anything else is set up
+    const uint32_t c0 = atomicAdd(cursor, 2u);
+    s_ids[0] = c0; s_ids[1] = c0 + 1;
+  }
   uint32_t free_n0 = 0, high_water0 = 0;
   bool grid_state_ok = false;
   auto sync_with_predecessor = [&]() {
@@ -418,18 +426,17 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const Cos
       for (int k = 0; k < kMarkPointsPerThread; ++k) nxt[k] = load_point<false>(rd, base + (unsigned long long)k * kMarkThreads + threadIdx.x);
     }
   };
-  // the first chunk's loads go out before anything else is set up
-  uint32_t chunk = blockIdx.x;
-  int ri = 0;
-  if (chunk < total) {
-    ri = mark_reading_of(batch, chunk);
-    prefetch(ri, chunk, 0);
-  }
   if (threadIdx.x < 2) s_drop[threadIdx.x] = 0;
   for (int i = threadIdx.x; i < kMarkTable; i += kMarkThreads) s_key[i] = kEmptyKey;
 #pragma unroll
   for (int i = threadIdx.x; i < kMarkTable * 16; i += kMarkThreads) (&s_mask[0][0])[i] = 0;
   __syncthreads();
+  uint32_t chunk = s_ids[0];
+  int ri = 0;
+  if (chunk < total) {
+    ri = mark_reading_of(batch, chunk);
+    prefetch(ri, chunk, 0);
+  }
   TRACE(0, 1);
 
   // ---- flush: resolve the table's leaves in the global hash, push masks and times, empty the table ---------------------
@@ -496,13 +503,15 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const Cos
 #pragma unroll
       for (int k = 0; k < kMarkPointsPerThread; ++k) pts[k] = nxt[k];
     }
-    // start the loads of this CTA's next chunk
-    const uint32_t chunk_next = chunk + gridDim.x;
+    // the next chunk of this CTA (handed out one iteration ago): start its loads; ask the cursor for the one after it
+    const uint32_t chunk_next = s_ids[stage ^ 1];
     const bool last = chunk_next >= total;
     int ri_next = ri;
+    uint32_t after_next = 0;
     if (!last) {
       ri_next = mark_reading_of(batch, chunk_next);
       prefetch(ri_next, chunk_next, stage ^ 1);
+      if (threadIdx.x == 0) after_next = atomicAdd(cursor, 1u);
     }
     const DevReading & par = batch.r[ri];   // warp-uniform parameter-bank reads
     if constexpr (kVec4) {
@@ -590,10 +599,11 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const Cos
                           free_n0, high_water0, batch.min_now);
       }
     }
+    if (!last && threadIdx.x == 0) s_ids[stage] = after_next;   // consumed two iterations from now
+    __syncthreads();   // (the only barrier of the chunk loop: hands the next chunk id to the other warps)
     chunk = chunk_next;
     ri = ri_next;
   }
-  __syncthreads();
   flush(true);
 
   TRACE(0, 5);   // flushed
@@ -625,6 +635,7 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const Cos
       if constexpr (kCostmap) costmap_publish_result(g.ctr);
       g.ctr->dropped_nonfinite += (before + mine) >> 16;
       g.ctr->mark_ticket64 = 0;
+      *cursor = 0;
       __threadfence();
     }
     TRACE(0, 6);
@@ -1438,14 +1449,18 @@ static cudaError_t launch_mark_variant(const GridView & g, const MarkBatch & bat
   if (occ == 0) {
     int n = 0;
     if (kVec4) cudaFuncSetAttribute(mark_kernel<kVec4, kCostmap>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMarkStageBytes);
+    // All kernels of the cycle ask for the same (maximum) shared-memory carve-out: they overlap on the same SMs under
+    // programmatic dependent launch, and an SM only changes its L1 / shared split when it is empty — with the default
+    // split of the sweep kernels only two of Mark's 43 KB CTAs fit next to them, and they would keep the SM from ever
+    // draining.
+    cudaFuncSetAttribute(mark_kernel<kVec4, kCostmap>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mark_kernel<kVec4, kCostmap>, kMarkThreads, smem);
     occ = (e == cudaSuccess && n >= 1) ? n : 4;
   }
-  // persistent CTAs, as many as are resident at once: CTA b takes chunks b, b + grid, ... with the next one's loads in flight
-  // (sized so that every CTA gets the same number of chunks, +-1)
+  // persistent CTAs, as many as are resident at once (never more than there are chunk pairs): each pulls chunks from
+  // the device-side cursor with the next chunk's loads in flight
   const uint32_t resident = (uint32_t)sm_count * (uint32_t)occ;
-  const uint32_t chunks_per_cta = (batch.total_blocks + resident - 1) / resident;
-  const uint32_t grid = std::min<uint32_t>(65535u, (batch.total_blocks + chunks_per_cta - 1) / chunks_per_cta);
+  const uint32_t grid = std::max<uint32_t>(1u, std::min<uint32_t>(std::min<uint32_t>(resident, 65535u), (batch.total_blocks + 1) / 2));
   return launch_ex(mark_kernel<kVec4, kCostmap>, grid, kMarkThreads, smem, s, pdl, g, batch, cm, costmap);
 }
 // pdl: the caller guarantees that the kernel's inputs (clouds) were complete before the PREDECESSOR of this launch in the
@@ -1483,6 +1498,12 @@ cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, co
   static const FrustumParams no_params{};
   const FrustumParams & fp = (frustums_dev == nullptr && fparam) ? *fparam : no_params;
   cudaError_t e;
+  static bool carveout_set = false;
+  if (!carveout_set) {   // see launch_mark_variant
+    cudaFuncSetAttribute(sweep_triage_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(sweep_leaf_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    carveout_set = true;
+  }
   const size_t dyn = (size_t)n_frustums * sizeof(DevFrustum);
   if (dyn > 32 * 1024) {
     e = cudaFuncSetAttribute(sweep_triage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
