@@ -71,6 +71,7 @@ struct stvl_grid {
   cudaEvent_t ev_copy_done = nullptr, ev_mark_done = nullptr;
   GridView v{};
   Counters * h_ctr = nullptr;       // pinned mirror
+  LiveCounters * h_live = nullptr;  // host-mapped, written by the kernels (grid-sizing estimates between fetches)
   Counters last{};                  // counters at the last fetch
   // staging
   DevBuf<uint8_t> stage;
@@ -379,6 +380,8 @@ int grow_tiles(stvl_grid * g)
   return STVL_OK;
 }
 
+uint32_t tiles_upper(const stvl_grid * g);
+
 // The fused update cycle (stvl_update_cycle_device): the sweep's triage kernel resets the costmap bytes, the costmap pass
 // rides on the Mark kernel, and the kernels are chained by programmatic dependent launch.
 struct CycleFusion {
@@ -396,7 +399,9 @@ int launch_batches(stvl_grid * g, const std::vector<MarkBatch> & batches, CycleF
     if (g->alloc_dirty) pdl = false;   // a fold kernel goes in between
     int rc = ensure_folded(g);   // (only a preceding bulk load leaves the allocator unfolded; Mark kernels fold themselves)
     if (rc != STVL_OK) return rc;
-    const bool carry = fz && fz->costmap && !fz->costmap_done && i + 1 == batches.size();
+    // the costmap pass rides on four warps of every Mark CTA: only worth it when Mark's grid is large enough for the tiles
+    const bool carry = fz && fz->costmap && !fz->costmap_done && i + 1 == batches.size() &&
+                       (uint64_t)tiles_upper(g) <= (uint64_t)mark_grid_for(batches[i], g->sm_count) * 64u;
     MarkBatch b = batches[i];
     b.cursor_sel = g->mark_cursor_sel;
     g->mark_cursor_sel ^= 1u;
@@ -452,13 +457,26 @@ int after_fetch(stvl_grid * g)
 
 // upper bounds of the pool slots / tiles in use, for grid sizing (exact counters at the last fetch + what the Marks
 // since then can have added)
+// Used for grid sizing only (every kernel strides over the real extents it reads on the device): between fetches the
+// proven bound only grows, so it is tightened with the kernels' own mirror of the counters plus slack for what the
+// cycles still in flight can add.
 uint32_t slots_upper(const stvl_grid * g)
 {
-  return (uint32_t)std::min<uint64_t>(g->v.leaf_capacity, (uint64_t)g->last.high_water + g->pending_leaf_bound + 1);
+  uint64_t n = std::min<uint64_t>(g->v.leaf_capacity, (uint64_t)g->last.high_water + g->pending_leaf_bound + 1);
+  if (g->h_live && !g->counters_fresh) {
+    const uint64_t live = *reinterpret_cast<const volatile uint32_t *>(&g->h_live->high_water);
+    if (live) n = std::min<uint64_t>(n, std::max<uint64_t>(live, g->last.high_water) * 5 / 4 + 8192);
+  }
+  return (uint32_t)n;
 }
 uint32_t tiles_upper(const stvl_grid * g)
 {
-  return (uint32_t)std::min<uint64_t>(g->v.tile_capacity, (uint64_t)g->last.tile_n + g->pending_tile_bound + 1);
+  uint64_t n = std::min<uint64_t>(g->v.tile_capacity, (uint64_t)g->last.tile_n + g->pending_tile_bound + 1);
+  if (g->h_live && !g->counters_fresh) {
+    const uint64_t live = *reinterpret_cast<const volatile uint32_t *>(&g->h_live->tile_n);
+    if (live) n = std::min<uint64_t>(n, std::max<uint64_t>(live, g->last.tile_n) * 5 / 4 + 2048);
+  }
+  return (uint32_t)n;
 }
 
 int build_batches(stvl_grid * g, const stvl_reading_t * readings, uint32_t n, const std::vector<const uint8_t *> & dev_ptrs,
@@ -786,6 +804,14 @@ int stvl_create(const stvl_config_t * cfg, stvl_grid_t ** out)
   CUB(cudaEventCreateWithFlags(&g->ev_copy_done, cudaEventDisableTiming));
   CUB(cudaEventCreateWithFlags(&g->ev_mark_done, cudaEventDisableTiming));
   CUB(cudaMallocHost(&g->h_ctr, sizeof(Counters)));
+  if (cudaHostAlloc(&g->h_live, sizeof(LiveCounters), cudaHostAllocMapped) == cudaSuccess) {
+    std::memset(g->h_live, 0, sizeof(LiveCounters));
+    LiveCounters * dev_live = nullptr;
+    if (cudaHostGetDevicePointer(&dev_live, g->h_live, 0) == cudaSuccess) g->v.live = dev_live;
+  } else {
+    g->h_live = nullptr;
+    cudaGetLastError();
+  }
   for (int i = 0; i < stvl_grid::kFrustumRing; ++i) {
     CUB(cudaMallocHost(&g->h_frustums[i], sizeof(DevFrustum) * kMaxFrustums));
     CUB(cudaEventCreateWithFlags(&g->ev_frustums[i], cudaEventDisableTiming));
@@ -831,6 +857,7 @@ int stvl_destroy(stvl_grid_t * g)
   cudaFree(g->dump_x.p); cudaFree(g->dump_y.p); cudaFree(g->dump_z.p); cudaFree(g->dump_t.p);
   cudaFree(g->vf_keys_a.p); cudaFree(g->vf_keys_b.p); cudaFree(g->vf_vals_a.p); cudaFree(g->vf_vals_b.p); cudaFree(g->vf_temp.p); cudaFree(g->vf_out.p);
   if (g->h_ctr) cudaFreeHost(g->h_ctr);
+  if (g->h_live) cudaFreeHost(g->h_live);
   for (int i = 0; i < stvl_grid::kFrustumRing; ++i) {
     if (g->h_frustums[i]) cudaFreeHost(g->h_frustums[i]);
     if (g->ev_frustums[i]) cudaEventDestroy(g->ev_frustums[i]);

@@ -74,6 +74,13 @@ struct Counters {
   uint32_t pad0;
 };
 
+// A few allocator counters mirrored into host-mapped pinned memory by the kernels that change them (plain posted
+// stores over PCIe, no stream operation): the host sizes its grids from them between synchronisations.  Estimates
+// only — every kernel takes its real extents from Counters on the device and strides over them.
+struct LiveCounters {
+  uint32_t high_water, free_n, tile_n, seq;
+};
+
 struct __align__(16) HashEntry {
   unsigned long long key;   // packed leaf coordinate, kEmptyKey or kTombKey
   uint32_t val;             // pool slot; kInvalidSlot until published
@@ -106,6 +113,7 @@ struct GridView {
   int sw_cur;              // which SweepCtr set / tile buffer the current (last) sweep uses
   uint32_t tile_capacity;
   Counters * ctr;
+  LiveCounters * live;     // host-mapped mirror (may be NULL)
   // constants
   double vs, inv_vs, half_vs;
   double voxel_decay;

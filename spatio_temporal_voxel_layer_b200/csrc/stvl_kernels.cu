@@ -142,6 +142,10 @@ __device__ __forceinline__ void fold_alloc(const GridView & g)
   c->free_n = free_n - from_free;
   c->high_water = (uint32_t)nhw;
   c->alloc_cursor = 0;
+  if (g.live) {   // mirror for the host's grid sizing
+    volatile LiveCounters * l = g.live;
+    l->high_water = (uint32_t)nhw; l->free_n = free_n - from_free; l->tile_n = ld_volatile_u32(&c->tile_n); l->seq = l->seq + 1;
+  }
 }
 __global__ void fold_alloc_kernel(const GridView g) { fold_alloc(g); }
 
@@ -928,22 +932,26 @@ sweep_leaf_kernel(const GridView g, const __grid_constant__ FrustumParams fparam
   stage_frustums(fr, frustums_gmem ? frustums_gmem : fparam.f, n_frustums);
   pdl_wait();
   TRACE(2, 1);
-  // Shorten the dependent-load chain of a warp's first leaf: its queue entry and leaf header are requested
-  // speculatively, together with the queue length (a stale queue entry is still a valid slot index, so the wasted
-  // loads are harmless).
   // work items: dense CTA b takes dense leaf number b (stored from the end of the queue array), the others queue
-  // entry (blockIdx - n_dense_ctas) * 8 + warp
-  const uint32_t qi0 = dense ? blockIdx.x : (blockIdx.x - n_dense_ctas) * kSweepWarps + warp;
-  const uint32_t q_stride = dense ? n_dense_ctas : (gridDim.x - n_dense_ctas) * kSweepWarps;
-  uint32_t slot0 = qi0 < g.leaf_capacity ? g.sweep_queue[dense ? g.leaf_capacity - 1u - qi0 : qi0] : 0u;
+  // entry (blockIdx - n_dense_ctas) * 8 + warp.  When there are more dense leaves than the dense CTAs can take in two
+  // rounds (large maps whose leaves all need the per-voxel pass) throughput matters, not the latency of one leaf: the
+  // dense CTAs then also work one leaf per warp (coop == false).
+  // Shorten the dependent-load chain of a warp's first leaf: its queue entry and leaf header are requested
+  // speculatively (assuming the cooperative mode for dense CTAs), together with the queue length; a stale queue entry
+  // is still a valid slot index, so wasted loads are harmless.
+  const uint32_t qi_spec = dense ? blockIdx.x : (blockIdx.x - n_dense_ctas) * kSweepWarps + warp;
+  uint32_t slot0 = qi_spec < g.leaf_capacity ? g.sweep_queue[dense ? g.leaf_capacity - 1u - qi_spec : qi_spec] : 0u;
   if (slot0 >= g.leaf_capacity) slot0 = 0;
   const uint64_t key0 = g.leaf_key[slot0];
   const uint32_t m16_0 = mask16[(size_t)slot0 * 32 + lane];
   const uint32_t tile0 = g.leaf_tile[slot0];
   const double tmin0 = g.leaf_tmin[slot0];
   const uint32_t n_queued = dense ? g.ctr->dense_n : g.ctr->queue_n;
+  const bool coop = dense && n_queued <= 2u * n_dense_ctas;
+  const uint32_t qi0 = coop ? blockIdx.x : (dense ? blockIdx.x : blockIdx.x - n_dense_ctas) * kSweepWarps + warp;
+  const uint32_t q_stride = coop ? n_dense_ctas : (dense ? n_dense_ctas : gridDim.x - n_dense_ctas) * kSweepWarps;
   TRACE(2, 2);
-  if ((dense ? blockIdx.x : (blockIdx.x - n_dense_ctas) * kSweepWarps) >= n_queued) {   // nothing for this CTA (uniform per block)
+  if ((coop ? blockIdx.x : (dense ? blockIdx.x : blockIdx.x - n_dense_ctas) * kSweepWarps) >= n_queued) {   // nothing for this CTA (uniform per block)
     if (threadIdx.x == 0) leaf_pass_done(g);
     return;
   }
@@ -955,7 +963,7 @@ sweep_leaf_kernel(const GridView g, const __grid_constant__ FrustumParams fparam
 
   uint32_t iter = 0;
   for (uint32_t qi = qi0; qi < n_queued; qi += q_stride, ++iter) {
-    const bool first = qi == qi0;
+    const bool first = qi == qi_spec && qi == qi0;   // the speculative loads above are this leaf's
     const uint32_t slot = first ? slot0 : g.sweep_queue[dense ? g.leaf_capacity - 1u - qi : qi];
     const uint64_t key = first ? key0 : g.leaf_key[slot];
     const uint32_t m16 = first ? m16_0 : mask16[(size_t)slot * 32 + lane];   // each lane owns two voxel columns = local indices [lane*16, lane*16+16)
@@ -977,7 +985,7 @@ sweep_leaf_kernel(const GridView g, const __grid_constant__ FrustumParams fparam
     // temporal culling: outside every frustum and too young to expire -> the 4 KB time block is never touched
     if (!any_cand && skip_model_ok) {
       if (!leaf_may_expire(g, now, tmin)) {
-        if (dense && warp != 0) continue;   // (all warps of a dense leaf's CTA get here: one of them counts)
+        if (coop && warp != 0) continue;   // (all warps of a dense leaf's CTA get here: one of them counts)
         const unsigned cnt = __popc(m16);
         c_swept += cnt; c_surv += cnt;
         if (tile != kOverflowSlot) {
@@ -1011,9 +1019,9 @@ sweep_leaf_kernel(const GridView g, const __grid_constant__ FrustumParams fparam
     const double * tbase = g.leaf_time + (size_t)slot * kLeafVoxels;
     double vmin = CUDART_INF;   // smallest mark time among this leaf's survivors
     // 32-voxel batches of the compacted list: all of them (one warp per leaf) or every eighth (dense leaf, CTA per leaf)
-    const int bstep = dense ? kSweepWarps : 1;
+    const int bstep = coop ? kSweepWarps : 1;
     int nb = 0;
-    for (int i0 = (dense ? (int)warp : 0) * 32; i0 < total; i0 += 32 * bstep, ++nb) {
+    for (int i0 = (coop ? (int)warp : 0) * 32; i0 < total; i0 += 32 * bstep, ++nb) {
       // the mark times of this warp's next four batches are requested together (one DRAM round trip per 128 voxels)
       if ((nb & 3) == 0) {
         double pv[4];
@@ -1128,7 +1136,7 @@ sweep_leaf_kernel(const GridView g, const __grid_constant__ FrustumParams fparam
     // write back changed mask words; count survivors per (x,y) column into the leaf's column tile
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) vmin = fmin(vmin, __shfl_xor_sync(kFull, vmin, d));
-    if (dense) {
+    if (coop) {
       // The warps of a dense leaf's CTA each cleared bits in their own copy of the mask: they meet at a barrier (they
       // all run the same iterations) and warp 0 combines the copies and takes the leaf-level decisions.  Everything
       // shared is double-buffered by iteration parity: a warp can only write the same buffer again after the NEXT
@@ -1479,6 +1487,11 @@ cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_coun
   return all_vec4 ? launch_mark_variant<true, false>(g, batch, sm_count, s, pdl, none, nullptr)
                   : launch_mark_variant<false, false>(g, batch, sm_count, s, pdl, none, nullptr);
 }
+uint32_t mark_grid_for(const MarkBatch & batch, int sm_count)
+{
+  // (launch_mark_variant's grid, with the nominal 5 resident CTAs per SM)
+  return std::max<uint32_t>(1u, std::min<uint32_t>(std::min<uint32_t>((uint32_t)sm_count * 5u, 65535u), (batch.total_blocks + 1) / 2));
+}
 uint32_t mark_blocks_for(unsigned long long n_points)
 {
   return (uint32_t)((n_points + kMarkPointsPerBlock - 1) / kMarkPointsPerBlock);
@@ -1518,15 +1531,16 @@ cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, co
   // Grid sizes: every kernel of the cycle is grid-stride, and under programmatic dependent launch a kernel only starts
   // once ALL CTAs of its predecessor are resident — so the grids are kept to a fraction of a wave (the leaf pass and
   // Mark get their turn early) unless the pool is large enough to need the extra memory parallelism.
-  const int triage_cap = sm_count * (leaf_slots_upper_bound > (1u << 18) ? 6 : 2);
+  const bool big = leaf_slots_upper_bound > (1u << 18);
+  const int triage_cap = sm_count * (big ? 8 : 2);
   e = launch_ex(sweep_triage_kernel, (unsigned)grid_for(leaf_slots_upper_bound, kSweepThreads, triage_cap), kSweepThreads, dyn, s, true,
                 g, fp, frustums_dev, n_frustums, now, force_full, costmap_reset, (unsigned long long)costmap_bytes, costmap_value);
   if (e != cudaSuccess) return e;
   // pass 2: one warp per queued leaf; the queue length is only known on the device, CTAs without work exit at once.
   // Programmatic dependent launch: its CTAs become resident (and stage the frustum blocks) while pass 1 drains.
   // The first CTAs take the leaves with more than one 32-voxel batch (a CTA per leaf), the others one leaf per warp.
-  const unsigned n_dense_ctas = (unsigned)grid_for(leaf_slots_upper_bound, 1, sm_count * 2);
-  const unsigned n_sparse_ctas = (unsigned)grid_for(leaf_slots_upper_bound, kSweepWarps, sm_count * 2);
+  const unsigned n_dense_ctas = (unsigned)grid_for(leaf_slots_upper_bound, 1, sm_count * (big ? 4 : 2));
+  const unsigned n_sparse_ctas = (unsigned)grid_for(leaf_slots_upper_bound, kSweepWarps, sm_count * (big ? 4 : 2));
   return launch_ex(sweep_leaf_kernel, n_dense_ctas + n_sparse_ctas, kSweepThreads, dyn, s, true,
                    g, fp, frustums_dev, n_frustums, now, out, (uint32_t)n_dense_ctas);
 }

@@ -28,6 +28,7 @@ cudaError_t launch_fold_alloc(const GridView & g, cudaStream_t s);
 cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s, bool pdl = false,
                         const CostmapDev * fused_costmap = nullptr, uint8_t * costmap_dev = nullptr);
 uint32_t mark_blocks_for(unsigned long long n_points);
+uint32_t mark_grid_for(const MarkBatch & batch, int sm_count);
 cudaError_t launch_load_voxels(const GridView & g, const int32_t * x, const int32_t * y, const int32_t * z, const double * t,
                                unsigned long long n, cudaStream_t s);
 cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, const FrustumParams * fparam, int n_frustums, double now,
