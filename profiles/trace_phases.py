@@ -95,7 +95,7 @@ def main():
         name, phases = PHASES[k]
         used = tr[k, :, 0] > 0
         n = int(used.sum())
-        sms = len(np.unique(tr[k, used, 7]))
+        sms = len(np.unique(tr[k, used, 7] & 0xFFFF))
         print("== %-15s %4d CTAs traced on %3d SMs" % (name, n, sms))
         for ph, label in enumerate(phases):
             v = tr[k, used, ph].astype(np.int64)
@@ -110,6 +110,21 @@ def main():
             if ok.any():
                 d = (b - a)[ok] / 1e3
                 print("     d(%s -> %s): median %.2f  p90 %.2f  max %.2f us" % (phases[ph - 1], phases[ph], np.median(d), np.percentile(d, 90), d.max()))
+    # Mark: when the CTAs became resident, how many chunks each took, how long a chunk took
+    mk = tr[0]
+    used = mk[:, 0] > 0
+    ent = (mk[used, 0].astype(np.int64) - t0) / 1e3
+    nch = (mk[used, 7] >> 16).astype(np.int64)
+    dur = (mk[used, 3].astype(np.int64) - mk[used, 2].astype(np.int64)) / 1e3
+    print("mark entry percentiles (us): p10 %.1f p25 %.1f p50 %.1f p75 %.1f p90 %.1f; CTAs with chunks: %d; chunks per CTA p10 %d p50 %d p90 %d max %d"
+          % (*np.percentile(ent, [10, 25, 50, 75, 90]), int((nch > 0).sum()), *np.percentile(nch[nch > 0], [10, 50, 90]), nch.max()))
+    ok = (nch > 0) & (dur > 0) & (dur < 1000)
+    per = dur[ok] / nch[ok]
+    print("time per chunk per CTA (us): p10 %.2f p50 %.2f p90 %.2f" % tuple(np.percentile(per, [10, 50, 90])))
+    for lo, hi in ((0, 24), (24, 28), (28, 32), (32, 100)):
+        sel = ok & (ent >= lo) & (ent < hi)
+        if sel.any():
+            print("  CTAs entering in [%d, %d) us: %d, chunks %d, time/chunk p50 %.2f" % (lo, hi, sel.sum(), nch[sel].sum(), np.median(dur[sel] / nch[sel])))
     # the slowest CTAs of the leaf pass (blockIdx < n_dense_ctas = 2 x SMs take the dense leaves)
     k = 2
     a, b = tr[k, :, 2].astype(np.int64), tr[k, :, 3].astype(np.int64)

@@ -500,7 +500,9 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const Cos
     __syncthreads();
   };
 
+  uint32_t n_chunks_done = 0;   // (only read by the trace build)
   for (uint32_t it = 0; chunk < total; ++it) {
+    ++n_chunks_done;
     const int stage = (int)(it & 1u);
     PointXYZ pts[kMarkPointsPerThread];
     if constexpr (!kVec4) {
@@ -611,6 +613,9 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const Cos
   flush(true);
 
   TRACE(0, 5);   // flushed
+#ifdef STVL_TRACE
+  if (threadIdx.x == 0 && blockIdx.x < 1024) g_trace[0][blockIdx.x][7] |= (unsigned long long)n_chunks_done << 16;
+#endif
   // dropped-point statistics: warp reduce, shared-memory add, one global atomic per CTA
   if (__ballot_sync(kFull, (drop_range | drop_nonfinite) != 0)) {
 #pragma unroll
