@@ -386,7 +386,7 @@ def bench_ours(args):
             algo_clear = st.n_swept * 16                 # 16 B per active voxel (key + time)
             traffic = None
             try:
-                with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                with open(os.path.join(ROOT, "profiles", "r1b_traffic.json")) as f:
                     traffic = json.load(f).get("mark_kernel_dram_bytes_per_launch")
             except Exception:
                 pass
