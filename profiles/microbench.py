@@ -16,8 +16,13 @@ from spatio_temporal_voxel_layer_b200 import synth, workloads
 
 def timed(stream, fn, reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fn(); fn()
-    torch.cuda.synchronize()
+    # keep the GPU busy for a while first: an idle B200 sits at low clocks and the first launches after a pause are
+    # 3x slower than in a running pipeline (which is what bench.py measures)
+    t_end = time.perf_counter() + 0.4
+    while time.perf_counter() < t_end:
+        for _ in range(20):
+            fn()
+        torch.cuda.synchronize()
     e0.record(stream)
     for _ in range(reps):
         fn()
@@ -59,12 +64,37 @@ def main():
     for name, args in variants.items():
         def run():
             a = args[state["i"] % len(args)]; state["i"] += 1
+            for k in range(len(a)):     # clocks must keep advancing, or the library falls back to one launch per reading
+                a[k].now = w.now0 + 1.0 + 1e-3 * state["i"] + 1e-5 * k
             stvl._check(L.stvl_mark_device(h, a, len(a)))
         g.timing()
         timed(stream, run, 40)
         t = g.timing()
         us = t.mark_ms / t.n_mark * 1e3
         print("mark  %-45s %8.1f us (kernel, library events) -> %7.1f GB/s algorithmic (16 B/pt)" % (name, us, n_pts * 16 / us / 1e3))
+    # Mark when the fixed costs (launch, set-up, one flush per CTA, last-CTA fold: ~15 us) are amortised: the same seven
+    # clouds replicated 8x per reading (16 readings of 1.23 M points = 19.7 M points = 315 MB per launch, > L2)
+    big_src = [torch.cat([real[s % len(real)][k % 7] for s in range(8)]) for k in range(16)]
+    arr = (stvl.Reading * 16)()
+    keep = []
+    for k, c in enumerate(big_src):
+        o, q = w.cycles[0].poses[k % 7]
+        stvl.MeasurementReading((c.data_ptr(), c.shape[0], 16, (0, 4, 8)), origin=o, orientation=q, obstacle_range=p["obstacle_range"],
+                                now=w.now0 + 3.0 + 1e-4 * k, filter=stvl.FILTER_PASSTHROUGH, min_obstacle_height=p["min_obstacle_height"],
+                                max_obstacle_height=p["max_obstacle_height"])._fill(arr[k], 0.0, keep)
+    n_big = sum(c.shape[0] for c in big_src)
+    def run_big():
+        state["i"] += 1
+        for k in range(16):
+            arr[k].now = w.now0 + 1.0 + 1e-3 * state["i"] + 1e-5 * k
+        stvl._check(L.stvl_mark_device(h, arr, 16))
+    timed(stream, run_big, 3)
+    g.timing()
+    timed(stream, run_big, 10)
+    t = g.timing()
+    us = t.mark_ms / t.n_mark * 1e3
+    print("mark  %-45s %8.1f us (kernel, library events) -> %7.1f GB/s algorithmic (16 B/pt)" % ("16 readings x 1.23 M points (315 MB)", us, n_big * 16 / us / 1e3))
+    del big_src
     # plain device copy of the same bytes as a yardstick
     src = torch.empty(n_pts * 4 * 8, dtype=torch.float32, device="cuda")
     dst = torch.empty(n_pts * 4, dtype=torch.float32, device="cuda")

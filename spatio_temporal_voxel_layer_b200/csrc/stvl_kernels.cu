@@ -374,6 +374,7 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const Cos
   __shared__ double s_now[kMarkTable];
   __shared__ unsigned int s_drop[2];
   __shared__ uint32_t s_ids[2];        // chunk ids handed to this CTA by the cursor (for iterations i+1, i+2)
+  __shared__ unsigned int s_fill;      // claimed table entries
   TRACE(0, 0);
   // The reading descriptors stay in the kernel-parameter bank and are only ever read with warp-uniform addresses
   // (every thread of the CTA reads the same field of the same reading): per-thread addresses into the constant bank
@@ -431,6 +432,7 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const Cos
     }
   };
   if (threadIdx.x < 2) s_drop[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_fill = 0;
   for (int i = threadIdx.x; i < kMarkTable; i += kMarkThreads) s_key[i] = kEmptyKey;
 #pragma unroll
   for (int i = threadIdx.x; i < kMarkTable * 16; i += kMarkThreads) (&s_mask[0][0])[i] = 0;
@@ -475,6 +477,7 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const Cos
     }
     last_key = kEmptyKey; last_e = -1;
     __syncthreads();
+    if (threadIdx.x == 0) s_fill = 0;   // (after the barrier: every thread has taken its flush decision from it)
     if (final) TRACE(0, 4);   // leaves resolved in the global hash
     // per touched mask word one 32-bit OR, per distinct voxel one 64-bit max (batched launch, monotone clocks) or a
     // plain store (per-reading launches: exact overwrite semantics of MarkGridPoint, .cpp:421-430)
@@ -589,7 +592,10 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const Cos
 #pragma unroll 1
           for (int p = 0; p < kMarkProbes; ++p) {
             unsigned long long cur = s_key[h];
-            if (cur == kEmptyKey) cur = atomicCAS(&s_key[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
+            if (cur == kEmptyKey) {
+              cur = atomicCAS(&s_key[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
+              if (cur == kEmptyKey) atomicAdd(&s_fill, 1u);
+            }
             if (cur == key || cur == kEmptyKey) { e = (int)h; break; }
             h = (h + 1) & (kMarkTable - 1);
           }
@@ -607,6 +613,10 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const Cos
     }
     if (!last && threadIdx.x == 0) s_ids[stage] = after_next;   // consumed two iterations from now
     __syncthreads();   // (the only barrier of the chunk loop: hands the next chunk id to the other warps)
+    // A filling table is flushed early: large clouds give a CTA dozens of chunks (a chunk of an organised cloud touches
+    // 4-10 leaves), and points that find the table full take the slow per-point path.  Under programmatic dependent
+    // launch this blocks until the sweep is done — the 3-4 chunks per CTA of a depth-camera cycle never get here.
+    if (!last && s_fill >= (unsigned)(kMarkTable * 5 / 8)) flush(false);
     chunk = chunk_next;
     ri = ri_next;
   }

@@ -322,6 +322,28 @@ def test_fused_update_cycle_matches_oracle(stvl, oracle, mixed_layouts):
     gg.close()
 
 
+def test_mark_large_scattered_clouds(stvl, oracle):
+    """Clouds large and scattered enough that every Mark CTA gets many chunks, fills its shared-memory table and has to
+    flush it early (and points that find the table full take the per-point path): two readings of 1.5 M points each,
+    uniformly random in a 5 m cube, the second overwriting the first where they overlap (later clock sample wins)."""
+    rng = np.random.default_rng(77)
+    gg = stvl.SpatioTemporalVoxelGrid(0.05, leaf_capacity=1 << 13)
+    og = oracle.OracleGrid(0.05)
+    readings = []
+    for k, centre in enumerate(((0.3, -0.2, 0.4), (1.1, 0.6, 0.2))):
+        cloud = np.zeros((1_500_000, 4), np.float32)
+        cloud[:, :3] = rng.uniform(-2.5, 2.5, (len(cloud), 3)) + np.asarray(centre, np.float32)
+        cloud[rng.integers(0, len(cloud), 5000), 1] = np.nan
+        now = 50.0 + 0.25 * k
+        readings.append(stvl.MeasurementReading(cloud, origin=centre, obstacle_range=4.0, now=now))
+        og.mark(cloud[np.isfinite(cloud[:, 1])], centre, 4.0, now)
+    gg.Mark(readings)
+    assert og.active_count() > 500_000
+    assert_same_voxels(gg.voxels(), og.voxels())
+    assert gg.pool_stats().points_dropped_nonfinite >= 9000
+    gg.close()
+
+
 def test_leaf_pool_growth_replays_mark(stvl, oracle):
     """A Mark that exhausts the leaf pool is replayed after the pool (and its hash) grew: nothing is lost."""
     rng = np.random.default_rng(13)
