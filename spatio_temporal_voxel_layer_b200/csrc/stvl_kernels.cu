@@ -874,8 +874,17 @@ sweep_triage_kernel(const GridView g, const __grid_constant__ FrustumParams fpar
       unsigned pc = 0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) pc += __popc(mw[q].x) + __popc(mw[q].y) + __popc(mw[q].z) + __popc(mw[q].w);
-      if (pc >= (unsigned)kDenseLeafVoxels) g.sweep_queue[g.leaf_capacity - 1u - atomicAdd(&g.ctr->dense_n, 1u)] = slot;
-      else g.sweep_queue[atomicAdd(&g.ctr->queue_n, 1u)] = slot;
+      // warp-aggregated queue pushes: one same-address atomic per warp and queue instead of one per leaf (several
+      // hundred returning atomics on one counter serialise for microseconds at the end of the kernel)
+      const bool is_dense = pc >= (unsigned)kDenseLeafVoxels;
+      const unsigned peers = __match_any_sync(__activemask(), is_dense ? 1 : 0);
+      const unsigned lane_id = threadIdx.x & 31;
+      const int leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if ((int)lane_id == leader) base = atomicAdd(is_dense ? &g.ctr->dense_n : &g.ctr->queue_n, (uint32_t)__popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      const uint32_t qpos = base + (uint32_t)__popc(peers & ((1u << lane_id) - 1u));
+      g.sweep_queue[is_dense ? g.leaf_capacity - 1u - qpos : qpos] = slot;
       continue;
     }
     // PopulateCostmapAndPointcloud .cpp:242-250 for every (surviving) voxel: per-column popcounts, two adjacent u32

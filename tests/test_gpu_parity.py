@@ -282,6 +282,7 @@ def test_fused_update_cycle_matches_oracle(stvl, oracle, mixed_layouts):
         for k, (o, q) in enumerate(synth.camera_ring(centre, 0.1 * cyc, n_cams=3)):
             readings.append(rgbd_reading(stvl, synth, scene, o, q, seed=100 * cyc + k, now=now + 0.001 * k))
         marking = [] if cyc == 6 else readings
+        clearing = readings * 3 if cyc == 4 else readings     # 9 frustums: more than fit the kernel parameters -> upload path
         dev_readings, keep = [], []
         for k, r in enumerate(marking):
             host = np.ascontiguousarray(r.cloud, np.float32)
@@ -294,16 +295,22 @@ def test_fused_update_cycle_matches_oracle(stvl, oracle, mixed_layouts):
                 t = torch.from_numpy(host).cuda()
                 layout = (t.data_ptr(), len(host), 16, (0, 4, 8))
             keep.append(t)
+            # cycle 8: one reading goes through the VOXEL pre-filter (extra kernels between the sweep and Mark)
+            filt = stvl.FILTER_VOXEL if (cyc == 8 and k == 2 and not (mixed_layouts and k == 1)) else r.filter
             dev_readings.append(stvl.MeasurementReading(layout, origin=r.origin, orientation=r.orientation, obstacle_range=r.obstacle_range,
-                                                        now=r.now, filter=r.filter, min_obstacle_height=r.min_obstacle_height,
-                                                        max_obstacle_height=r.max_obstacle_height))
+                                                        now=r.now, filter=filt, min_obstacle_height=r.min_obstacle_height,
+                                                        max_obstacle_height=r.max_obstacle_height, voxel_min_points=2))
         with torch.cuda.stream(stream):
             cm_dev.fill_(77)      # stale bytes: the cycle itself must reset them
         thr, dflt = cyc % 3, (255 if cyc % 2 else 0)
-        gg.update_cycle_device(now, readings, dev_readings, ox, oy, res, size, size, cm_dev.data_ptr(), mark_threshold=thr, default_value=dflt)
-        og.clear_frustums(now, oracle_frustums(oracle, readings))
-        for r in marking:
-            oracle_mark(oracle, og, r, now)
+        gg.update_cycle_device(now, clearing, dev_readings, ox, oy, res, size, size, cm_dev.data_ptr(), mark_threshold=thr, default_value=dflt)
+        og.clear_frustums(now, oracle_frustums(oracle, clearing))
+        for k, r in enumerate(marking):
+            if cyc == 8 and k == 2:
+                cent = oracle.filter_voxel(np.ascontiguousarray(r.cloud, np.float32), np.float32(0.05), r.min_obstacle_height, r.max_obstacle_height, 2)
+                og.mark(cent, r.origin, r.obstacle_range, r.now)
+            else:
+                oracle_mark(oracle, og, r, now)
         ocm, ob, on = og.update_ros_costmap(ox, oy, res, size, size, mark_threshold=thr, default_value=dflt)
         res_g = gg.costmap_result()
         cm = cm_dev.cpu().numpy().reshape(size, size)
