@@ -279,6 +279,16 @@ def bench_ours(args):
             for k in range(n_cams):
                 arr[k].now = now + 1e-4 * k
             check(L.stvl_update_cycle_device(h, now, fr_ptrs[slot], n_cams, arr, n_cams, params_ref, cm_dev_ptr))
+        elif fused:
+            # N>1: the same fused cycle on this rank's shard; its costmap pass writes the rank's {0, lethal} bytes into the
+            # reduce window and the library merges the windows into rank 0's costmap with NCCL (max) on a side stream,
+            # pipelined one cycle behind (stvl_update_cycle_sharded_device)
+            slot = step % ring
+            now = w.now0 + w.dt * (step + 1)
+            arr = args_dev[slot]
+            for k in range(n_cams):
+                arr[k].now = now + 1e-4 * k
+            check(L.stvl_update_cycle_sharded_device(h, now, fr_ptrs[slot], n_cams, arr, n_cams, params_ref, cm_dev_ptr, 0, 1))
         else:
             arr = enqueue_clear_mark(step, True)
             check(L.stvl_mark_device(h, arr, n_cams))
@@ -375,7 +385,7 @@ def bench_ours(args):
                        "l2_policy": "inputs larger than L2: ring of %d distinct cycles x %.1f MB of clouds; leaf pool %.1f GB" % (
                            ring, w.points_per_cycle * 16 / 1e6, g.pool_stats().device_bytes / 1e9),
                        "costmap_cells": cp["size_x"] * cp["size_y"],
-                       "parallelism": "1 GPU" if world == 1 else "%d spatial x-slab shards + in-library NCCL merge of the per-shard column results (bytes mode), pipelined one cycle behind on a side stream" % world},
+                       "parallelism": "1 GPU" if world == 1 else "%d spatial x-slab shards, fused cycle per shard + in-library NCCL merge of the per-shard costmap bytes (max), pipelined one cycle behind on a side stream" % world},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": bytes_h2d, "d2h_bytes_per_step": bytes_d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,

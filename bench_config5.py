@@ -107,10 +107,10 @@ def main():
         if world == 1:
             stvl._check(L.stvl_update_cycle_device(h, now, fr_ptrs[slot], w.n_cams, arr, w.n_cams, C.byref(params), costmap_dev.data_ptr()))
         else:
-            stvl._check(L.stvl_clear_frustums(h, now, fr_ptrs[slot], w.n_cams))
-            stvl._check(L.stvl_mark_device(h, arr, w.n_cams))
-            # bytes mode: local thresholding + NCCL max into rank 0's costmap, pipelined one cycle behind on the side stream
-            stvl._check(L.stvl_costmap_sharded_device(h, C.byref(params), costmap_dev.data_ptr(), 0, 0, 1))
+            # the fused cycle on this rank's slab; local {0, lethal} bytes + NCCL max into rank 0's costmap, pipelined one
+            # cycle behind on the side stream
+            stvl._check(L.stvl_update_cycle_sharded_device(h, now, fr_ptrs[slot], w.n_cams, arr, w.n_cams, C.byref(params),
+                                                           costmap_dev.data_ptr(), 0, 1))
 
     def barrier():
         g.synchronize(); torch.cuda.synchronize()

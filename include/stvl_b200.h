@@ -208,6 +208,13 @@ int stvl_costmap_device(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_
 int stvl_update_cycle_device(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
                              const stvl_reading_t * readings, uint32_t n_readings,
                              const stvl_costmap_params_t * p, uint8_t * costmap_dev);
+/* The same cycle on a spatial shard (stvl_config_t.shard_*, stvl_comm_init): the fused cycle writes this rank's
+ * {0, lethal} bytes into the reduce window and the windows are merged into `costmap_dev` on `root` exactly as by
+ * stvl_costmap_sharded_device(count_bytes = 0) — blocking, or pipelined one cycle behind on a side stream
+ * (stvl_costmap_sharded_flush drains the last one).  costmap_dev is only used on the root. */
+int stvl_update_cycle_sharded_device(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
+                                     const stvl_reading_t * readings, uint32_t n_readings,
+                                     const stvl_costmap_params_t * p, uint8_t * costmap_dev, int root, int pipelined);
 /* The result (marked columns, touched bounds — the touch() calls of spatio_temporal_voxel_layer.cpp:716) of the last
  * costmap pass enqueued by stvl_costmap_device(res = NULL) or stvl_update_cycle_device.  Synchronises. */
 int stvl_get_costmap_result(stvl_grid_t * g, stvl_costmap_result_t * res);

@@ -1480,21 +1480,18 @@ int stvl_get_pool_stats(stvl_grid_t * g, stvl_pool_stats_t * out)
   return after_fetch(g);
 }
 
-int stvl_update_cycle_device(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
-                             const stvl_reading_t * readings, uint32_t n_readings,
-                             const stvl_costmap_params_t * p, uint8_t * costmap_dev)
+namespace {
+// Fused form of clear -> mark -> costmap, three launches: the triage kernel also resets the costmap bytes, the leaf
+// pass and Mark are chained by programmatic dependent launch (Mark's cloud streaming overlaps the sweep's tail; it
+// waits for the sweep before it touches the grid) and the costmap pass rides on the Mark kernel.  The clouds must be
+// complete on the device before this call is enqueued (stream order on stvl_get_stream() is enough).
+int fused_cycle(stvl_grid * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums, const stvl_reading_t * readings,
+                uint32_t n_readings, const CostmapDev & cm, uint8_t * costmap_dev)
 {
-  ENTER(g);
-  if (!p || !costmap_dev) return fail(STVL_ERR_INVALID, "NULL argument");
-  if (!(p->resolution > 0)) return fail(STVL_ERR_INVALID, "resolution must be positive");
   int rc = validate_readings(readings, n_readings);
   if (rc != STVL_OK) return rc;
-  // Fused form of clear -> mark -> costmap, three launches: the triage kernel also resets the costmap bytes, the leaf
-  // pass and Mark are chained by programmatic dependent launch (Mark's cloud streaming overlaps the sweep's tail; it
-  // waits for the sweep before it touches the grid) and the costmap pass rides on the Mark kernel.  The clouds must be
-  // complete on the device before this call is enqueued (stream order on stvl_get_stream() is enough).
   CycleFusion fz;
-  fz.cm = to_dev(*p);
+  fz.cm = cm;
   fz.costmap = costmap_dev;
   rc = clear_frustums_impl(g, now, frustums, n_frustums, &fz);
   if (rc != STVL_OK) return rc;
@@ -1508,6 +1505,67 @@ int stvl_update_cycle_device(stvl_grid_t * g, double now, const stvl_frustum_t *
     g->launches += 1;
   }
   g->counters_fresh = false;
+  return STVL_OK;
+}
+}  // namespace
+
+int stvl_update_cycle_device(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
+                             const stvl_reading_t * readings, uint32_t n_readings,
+                             const stvl_costmap_params_t * p, uint8_t * costmap_dev)
+{
+  ENTER(g);
+  if (!p || !costmap_dev) return fail(STVL_ERR_INVALID, "NULL argument");
+  if (!(p->resolution > 0)) return fail(STVL_ERR_INVALID, "resolution must be positive");
+  return fused_cycle(g, now, frustums, n_frustums, readings, n_readings, to_dev(*p), costmap_dev);
+}
+
+int stvl_update_cycle_sharded_device(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
+                                     const stvl_reading_t * readings, uint32_t n_readings,
+                                     const stvl_costmap_params_t * p, uint8_t * costmap_dev, int root, int pipelined)
+{
+  ENTER(g);
+  if (!p) return fail(STVL_ERR_INVALID, "NULL argument");
+  if (!g->comm) return fail(STVL_ERR_INVALID, "stvl_comm_init has not been called");
+  if (root < 0 || root >= g->comm_n) return fail(STVL_ERR_INVALID, "bad root");
+  if (!(p->resolution > 0)) return fail(STVL_ERR_INVALID, "resolution must be positive");
+  // bytes mode of stvl_costmap_sharded_device with the fused cycle in front of it: the cycle's costmap pass writes this
+  // rank's {0, lethal} bytes straight into the reduce window
+  const int geom[4] = {0, 0, (int)p->size_x, (int)p->size_y};
+  const size_t cells = (size_t)p->size_x * p->size_y;
+  if (g->win_pending >= 0 && (g->win_count_bytes != 0 || std::memcmp(geom, g->win_geom, sizeof(geom)) != 0)) {
+    int rc = stvl_costmap_sharded_flush(g, p, nullptr, root);
+    if (rc != STVL_OK) return rc;
+  }
+  const int b = (int)(g->win_k & 1);
+  if (g->window[b].cap < cells) {
+    CU(cudaStreamSynchronize(g->merge_stream));
+    int rc = ensure(g, g->window[b], cells);
+    if (rc != STVL_OK) return rc;
+  }
+  std::memcpy(g->win_geom, geom, sizeof(geom));
+  g->win_count_bytes = 0;
+  CU(cudaStreamWaitEvent(g->stream, g->ev_reduce[b], 0));   // the reduce that used this window two calls ago
+  CostmapDev d = to_dev(*p);
+  d.default_value = 0;
+  int rc = fused_cycle(g, now, frustums, n_frustums, readings, n_readings, d, g->window[b].p);
+  if (rc != STVL_OK) return rc;
+  CU(cudaEventRecord(g->ev_scatter[b], g->stream));
+  NcclApi * n = nccl_api();
+  g->win_k += 1;
+  if (!pipelined) {
+    if (g->win_pending >= 0) { rc = threshold_window(g, g->win_pending, *p, nullptr, root); if (rc != STVL_OK) return rc; g->win_pending = -1; }
+    NC(n->Reduce(g->window[b].p, g->window[b].p, cells, ncclUint8, ncclMax, root, g->comm, g->stream));
+    CU(cudaEventRecord(g->ev_reduce[b], g->stream));
+    return threshold_window(g, b, *p, costmap_dev, root);
+  }
+  CU(cudaStreamWaitEvent(g->merge_stream, g->ev_scatter[b], 0));
+  NC(n->Reduce(g->window[b].p, g->window[b].p, cells, ncclUint8, ncclMax, root, g->comm, g->merge_stream));
+  CU(cudaEventRecord(g->ev_reduce[b], g->merge_stream));
+  if (g->win_pending >= 0) {
+    rc = threshold_window(g, g->win_pending, *p, costmap_dev, root);   // the PREVIOUS cycle's bytes
+    if (rc != STVL_OK) return rc;
+  }
+  g->win_pending = b;
   return STVL_OK;
 }
 

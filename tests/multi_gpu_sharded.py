@@ -65,8 +65,37 @@ def main():
     g.synchronize()
     if rank == 0:
         ok = ok and torch.equal(cm, expected[n_cycles - 1])
+    # fused sharded cycles (stvl_update_cycle_sharded_device): sweep + Mark of a device-resident cloud + costmap pass into
+    # the reduce window + NCCL merge, blocking then pipelined, against the unsharded grid's fused cycle
+    cloud = np.zeros((200000, 4), np.float32)
+    cloud[:, :3] = rng.uniform(-6.0, 6.0, (len(cloud), 3)).astype(np.float32)
+    cloud[:, 2] = np.abs(cloud[:, 2]) * 0.15
+    cloud_dev = torch.from_numpy(cloud).cuda()
+    fused_expected = []
+    for cyc in range(4):
+        now += 1.0
+        reading = stvl.MeasurementReading((cloud_dev.data_ptr(), len(cloud), 16, (0, 4, 8)), origin=(0.5 * cyc, 0.0, 0.5), obstacle_range=7.0,
+                                          now=now + 0.001)
+        if rank == 0:
+            ref.update_cycle_device(now, [], [reading], ox, oy, res, size, size, cm_ref.data_ptr(), mark_threshold=2, default_value=0)
+            ref.synchronize()
+            fused_expected.append(cm_ref.clone())
+        g.update_cycle_sharded_device(now, [], [reading], params, cm.data_ptr(), root=0, pipelined=cyc >= 2)
+        g.synchronize()
+        if rank == 0:
+            if cyc < 2:
+                ok = ok and torch.equal(cm, fused_expected[cyc]) and int((cm == 254).sum()) > 1000
+            elif cyc == 3:
+                ok = ok and torch.equal(cm, fused_expected[2])
+    g.costmap_sharded_flush(params, cm.data_ptr(), root=0)
+    g.synchronize()
+    if rank == 0:
+        ok = ok and torch.equal(cm, fused_expected[3])
+        n_ref = ref.active_count()
     n_local = torch.tensor([g.active_count()], device="cuda")
     dist.all_reduce(n_local)
+    if rank == 0:
+        ok = ok and int(n_local.item()) == n_ref          # the shards together hold exactly the unsharded grid's voxels
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     if rank == 0:
