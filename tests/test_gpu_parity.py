@@ -4,6 +4,8 @@ Bar (BASELINE.json north_star): voxel key sets, mark times, column counts and co
 voxels whose decision hinged on libm exp/atan must be listed (stvl_get_ambiguous)."""
 import math
 
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -348,6 +350,75 @@ def test_mark_large_scattered_clouds(stvl, oracle):
     assert og.active_count() > 500_000
     assert_same_voxels(gg.voxels(), og.voxels())
     assert gg.pool_stats().points_dropped_nonfinite >= 9000
+    gg.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_mixed_api_soak(stvl, oracle, seed):
+    """30 cycles on ONE handle with a random mix of everything the boundary offers — fused device cycles, stage-by-stage
+    cycles with host or device clouds, cycles that are only inspected several cycles later (no synchronisation in
+    between), stage timing switched on and off (it changes how kernels are chained), area resets, a full reset, a tiny
+    leaf pool that has to grow — bit-compared with the oracle whenever the state is read."""
+    import torch
+    import spatio_temporal_voxel_layer_b200.synth as synth
+    rng = np.random.default_rng(1000 + seed)
+    scene = synth.retail_scene(size=30.0, seed=3 + seed)
+    gg = stvl.SpatioTemporalVoxelGrid(0.05, decay_model=0, voxel_decay=1.5, leaf_capacity=128)
+    og = oracle.OracleGrid(0.05, decay_model=0, voxel_decay=1.5)
+    gg.set_outputs(0)
+    size, res, ox, oy = 400, 0.05, -10.0, -10.0
+    stream = torch.cuda.ExternalStream(gg.stream())
+    cm_dev = torch.zeros((size, size), dtype=torch.uint8, device="cuda")
+    keep_alive = []
+    now = 200.0
+    checked = 0
+    for cyc in range(30):
+        now += float(rng.uniform(0.05, 0.6))
+        centre = (-6.0 + 0.4 * cyc, 2.3 - 13.5 + 12.0 + float(rng.uniform(-0.3, 0.3)), 0.0)
+        n_cams = int(rng.integers(1, 4))
+        readings = [rgbd_reading(stvl, synth, scene, o, q, seed=1000 * seed + 10 * cyc + k, now=now + 0.001 * k, w=120, h=90)
+                    for k, (o, q) in enumerate(synth.camera_ring(centre, 0.2 * cyc, n_cams=n_cams))]
+        mode = int(rng.integers(0, 3))          # 0 fused device cycle, 1 stage-by-stage with host clouds, 2 with device clouds
+        gg.enable_timing(int(rng.integers(0, 8)) if rng.random() < 0.4 else 0)
+        thr, dflt = int(rng.integers(0, 3)), int(rng.choice([0, 255]))
+        dev_readings = []
+        if mode != 1:
+            for r in readings:
+                t = torch.from_numpy(np.ascontiguousarray(r.cloud, np.float32)).cuda()
+                keep_alive.append(t)
+                dev_readings.append(stvl.MeasurementReading((t.data_ptr(), t.shape[0], 16, (0, 4, 8)), origin=r.origin, orientation=r.orientation,
+                                                            obstacle_range=r.obstacle_range, now=r.now, filter=r.filter,
+                                                            min_obstacle_height=r.min_obstacle_height, max_obstacle_height=r.max_obstacle_height))
+        if mode == 0:
+            gg.update_cycle_device(now, readings, dev_readings, ox, oy, res, size, size, cm_dev.data_ptr(), mark_threshold=thr, default_value=dflt)
+        else:
+            gg.ClearFrustums(readings, now)
+            gg.Mark(readings if mode == 1 else dev_readings, device=(mode == 2))
+            p = stvl.CostmapParams(ox, oy, res, size, size, thr, dflt, 254)
+            stvl._check(gg.L.stvl_costmap_device(gg.h, ctypes.byref(p), cm_dev.data_ptr(), None))     # enqueue only
+        og.clear_frustums(now, oracle_frustums(oracle, readings))
+        for r in readings:
+            oracle_mark(oracle, og, r, now)
+        ocm, ob, on = og.update_ros_costmap(ox, oy, res, size, size, mark_threshold=thr, default_value=dflt)
+        if rng.random() < 0.5 or cyc == 29:      # read the state back only now and then: cycles pile up unsynchronised in between
+            res_g = gg.costmap_result()
+            assert np.array_equal(cm_dev.cpu().numpy(), ocm), "costmap bytes differ in cycle %d (mode %d)" % (cyc, mode)
+            assert res_g.n_marked_columns == on
+            assert_same_columns(gg.GetFlattenedCostmap(), og.costmap())
+            assert_same_voxels(gg.voxels(), og.voxels())
+            st = gg.sweep_stats()
+            assert st.n_swept == st.n_survived + st.n_cleared
+            keep_alive.clear()
+            checked += 1
+        if rng.random() < 0.15:
+            a = rng.uniform(-8, 4, 2)
+            inv = bool(rng.integers(0, 2))
+            gg.ResetGridArea((a[0], a[1]), (a[0] + 4.0, a[1] + 3.0), invert_area=inv)
+            og.reset_area(a[0], a[1], a[0] + 4.0, a[1] + 3.0, inv)
+        if cyc == 17:
+            assert gg.ResetGrid() and og.reset()
+    assert checked >= 8 and og.active_count() > 200
+    assert gg.pool_stats().leaf_capacity > 128      # the pool had to grow on the way
     gg.close()
 
 
