@@ -284,6 +284,12 @@ def test_fused_update_cycle_matches_oracle(stvl, oracle, mixed_layouts):
         for k, (o, q) in enumerate(synth.camera_ring(centre, 0.1 * cyc, n_cams=3)):
             readings.append(rgbd_reading(stvl, synth, scene, o, q, seed=100 * cyc + k, now=now + 0.001 * k))
         marking = [] if cyc == 6 else readings
+        if cyc == 2:      # 18 marking readings with increasing clocks: two batched Mark launches, the costmap pass rides on the last
+            marking = [stvl.MeasurementReading(r.cloud, origin=r.origin, orientation=r.orientation, obstacle_range=r.obstacle_range - 0.1 * (j // 3),
+                                               now=now + 0.001 * j, filter=r.filter, min_obstacle_height=r.min_obstacle_height,
+                                               max_obstacle_height=r.max_obstacle_height) for j, r in enumerate(readings * 6)]
+        elif cyc == 3:    # the same reading list twice: clocks not monotone -> one Mark launch per reading with plain stores
+            marking = readings * 2
         clearing = readings * 3 if cyc == 4 else readings     # 9 frustums: more than fit the kernel parameters -> upload path
         dev_readings, keep = [], []
         for k, r in enumerate(marking):
