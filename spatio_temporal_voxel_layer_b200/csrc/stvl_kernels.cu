@@ -144,7 +144,8 @@ __device__ __forceinline__ void fold_alloc(const GridView & g)
   c->alloc_cursor = 0;
   if (g.live) {   // mirror for the host's grid sizing
     volatile LiveCounters * l = g.live;
-    l->high_water = (uint32_t)nhw; l->free_n = free_n - from_free; l->tile_n = ld_volatile_u32(&c->tile_n); l->seq = l->seq + 1;
+    // (posted stores only: a LOAD from host-mapped memory here would put a PCIe round trip at the tail of the kernel)
+    l->high_water = (uint32_t)nhw; l->free_n = free_n - from_free; l->tile_n = ld_volatile_u32(&c->tile_n);
   }
 }
 __global__ void fold_alloc_kernel(const GridView g) { fold_alloc(g); }
