@@ -54,7 +54,7 @@ struct Counters {
   uint32_t tile_overflow;
   // last-CTA-done tickets (each kernel's last CTA commits / re-arms shared state)
   uint32_t mark_ticket, leaf_ticket, cm_ticket;
-  uint32_t dense_n;        // densely populated leaves queued for pass 2, stored from the END of sweep_queue (four warps each)
+  uint32_t dense_n;        // leaves with more than one 32-voxel batch queued for pass 2, stored from the END of sweep_queue (a CTA each)
   // next unclaimed 1024-point chunk of the running Mark kernel, re-armed by its last CTA.  Two cursors used alternately:
   // under programmatic dependent launch the first CTAs of the next cycle's Mark may pull chunks while the last CTA of
   // this one has not re-armed its cursor yet

@@ -1,10 +1,15 @@
 // stvl_kernels.cu — sm_100a kernels of the per-cycle voxel update.
 //
-//   mark_kernel            Mark / operator()            reference spatio_temporal_voxel_grid.cpp:254-309
-//   sweep_kernel           ClearFrustums sweep          reference .cpp:96-224 (+ frustum IsInside)
-//   costmap_kernel         UpdateROSCostmap grid loop   reference spatio_temporal_voxel_layer.cpp:699-718
-//   reset_area_kernel      ResetGridArea                reference .cpp:397-418
+//   mark_kernel<kVec4, kCostmap>   Mark / operator()            reference spatio_temporal_voxel_grid.cpp:254-309
+//                                  (kCostmap: also carries the costmap pass of the fused cycle)
+//   sweep_triage_kernel            ClearFrustums sweep, pass 1  reference .cpp:96-224: one thread per leaf, temporal / frustum
+//                                                               culling at leaf level, column counts of untouched leaves
+//   sweep_leaf_kernel              ClearFrustums sweep, pass 2  per-voxel decay + frustum IsInside for the queued leaves
+//   costmap_kernel                 UpdateROSCostmap grid loop   reference spatio_temporal_voxel_layer.cpp:699-718
+//   reset_area_kernel              ResetGridArea                reference .cpp:397-418
 //   + small utility kernels (column compaction, dumps, hash rebuild, dense scatter for the multi-GPU merge)
+//
+// The three kernels of a cycle are chained by programmatic dependent launch (pdl_wait / pdl_launch_dependents below).
 //
 // Everything is integer / FP64 scalar work bound by HBM traffic: no tensor cores.  All
 // arithmetic whose result feeds a comparison or a stored value uses the _rn intrinsics
@@ -941,7 +946,7 @@ sweep_leaf_kernel(const GridView g, const __grid_constant__ FrustumParams fparam
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevFrustum * fr = reinterpret_cast<DevFrustum *>(smem_raw);
   __shared__ uint16_t s_list[kSweepWarps][kLeafVoxels];
-  __shared__ uint32_t s_mask[2][kSweepWarps][16];   // [iteration parity]: quarter 0 of a dense leaf reads its siblings' copies
+  __shared__ uint32_t s_mask[2][kSweepWarps][16];   // [iteration parity]: warp 0 of a dense leaf's CTA reads its siblings' copies
   __shared__ uint32_t s_part[kSweepWarps][kMaxFrustums / 32];
   __shared__ uint32_t s_full[kSweepWarps][kMaxFrustums / 32];
   __shared__ double s_val[kSweepWarps][128];
