@@ -155,8 +155,12 @@ def main():
                 "warmup": args.warmup, "ms_per_step": float(tmax[0]) / args.steps, "scaling": "strong",
                 "active_voxels_swept": swept, "voxels_per_s": swept / (float(tmax[0]) / args.steps / 1e3),
                 "sweep_ms_max_rank": sweep_ms,
-                "sweep_roofline": {"algorithmic_bytes": swept * 16 // world, "achieved_gbs": swept * 16 / world / (sweep_ms / 1e3) / 1e9,
-                                   "frac_of_measured_peak": swept * 16 / world / (sweep_ms / 1e3) / 1e9 / peak},
+                # the sweep's first kernel also resets the costmap bytes of the fused cycle (Costmap2D::resetMaps): 16 B per
+                # active voxel + 1 B per costmap cell
+                "sweep_roofline": {"algorithmic_bytes": swept * 16 // world + cp["size_x"] * cp["size_y"],
+                                   "voxel_bytes": swept * 16 // world, "costmap_reset_bytes": cp["size_x"] * cp["size_y"],
+                                   "achieved_gbs": (swept * 16 / world + cp["size_x"] * cp["size_y"]) / (sweep_ms / 1e3) / 1e9,
+                                   "frac_of_measured_peak": (swept * 16 / world + cp["size_x"] * cp["size_y"]) / (sweep_ms / 1e3) / 1e9 / peak},
                 "costmap_cells": cp["size_x"] * cp["size_y"], "marked_cells": marked, "load_s": load_s,
                 "leaf_pool": {k: getattr(g.pool_stats(), k) for k in ("leaves_in_use", "leaf_capacity", "tiles_in_use", "device_bytes")}}
         print(json.dumps(line))

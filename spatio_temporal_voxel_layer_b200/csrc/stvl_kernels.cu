@@ -805,7 +805,7 @@ __device__ __forceinline__ bool leaf_may_expire(const GridView & g, double now, 
 __global__ void __launch_bounds__(kSweepThreads)
 sweep_triage_kernel(const GridView g, const __grid_constant__ FrustumParams fparam, const DevFrustum * __restrict__ frustums_gmem,
                     const int n_frustums, const double now, const int force_full, uint8_t * __restrict__ cm_reset,
-                    const unsigned long long cm_bytes, const int cm_value)
+                    const unsigned long long cm_bytes, const int cm_value, const unsigned dense_threshold)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevFrustum * fr = reinterpret_cast<DevFrustum *>(smem_raw);
@@ -882,7 +882,7 @@ sweep_triage_kernel(const GridView g, const __grid_constant__ FrustumParams fpar
       for (int q = 0; q < 4; ++q) pc += __popc(mw[q].x) + __popc(mw[q].y) + __popc(mw[q].z) + __popc(mw[q].w);
       // warp-aggregated queue pushes: one same-address atomic per warp and queue instead of one per leaf (several
       // hundred returning atomics on one counter serialise for microseconds at the end of the kernel)
-      const bool is_dense = pc >= (unsigned)kDenseLeafVoxels;
+      const bool is_dense = pc >= dense_threshold;
       const unsigned peers = __match_any_sync(__activemask(), is_dense ? 1 : 0);
       const unsigned lane_id = threadIdx.x & 31;
       const int leader = __ffs(peers) - 1;
@@ -1564,12 +1564,14 @@ cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, co
   const bool big = leaf_slots_upper_bound > (1u << 18);
   const int triage_cap = sm_count * (big ? 8 : 2);
   e = launch_ex(sweep_triage_kernel, (unsigned)grid_for(leaf_slots_upper_bound, kSweepThreads, triage_cap), kSweepThreads, dyn, s, true,
-                g, fp, frustums_dev, n_frustums, now, force_full, costmap_reset, (unsigned long long)costmap_bytes, costmap_value);
+                g, fp, frustums_dev, n_frustums, now, force_full, costmap_reset, (unsigned long long)costmap_bytes, costmap_value,
+                big ? 0xFFFFFFFFu : (unsigned)kDenseLeafVoxels);
   if (e != cudaSuccess) return e;
   // pass 2: one warp per queued leaf; the queue length is only known on the device, CTAs without work exit at once.
   // Programmatic dependent launch: its CTAs become resident (and stage the frustum blocks) while pass 1 drains.
   // The first CTAs take the leaves with more than one 32-voxel batch (a CTA per leaf), the others one leaf per warp.
-  const unsigned n_dense_ctas = (unsigned)grid_for(leaf_slots_upper_bound, 1, sm_count * (big ? 4 : 2));
+  // Large pools are throughput bound: no CTA-per-leaf mode there, every queued leaf gets a warp.
+  const unsigned n_dense_ctas = big ? 0u : (unsigned)grid_for(leaf_slots_upper_bound, 1, sm_count * 2);
   const unsigned n_sparse_ctas = (unsigned)grid_for(leaf_slots_upper_bound, kSweepWarps, sm_count * (big ? 4 : 2));
   return launch_ex(sweep_leaf_kernel, n_dense_ctas + n_sparse_ctas, kSweepThreads, dyn, s, true,
                    g, fp, frustums_dev, n_frustums, now, out, (uint32_t)n_dense_ctas);
