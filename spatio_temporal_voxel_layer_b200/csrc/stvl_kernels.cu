@@ -532,13 +532,16 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const Cos
     if constexpr (kVec4) {
       // every thread only reads what it copied itself: waiting for its own cp.async group is enough
       if (last) __pipeline_wait_prior(0); else __pipeline_wait_prior(1);
+      // points of this chunk that exist (only the reading's last chunk is short): one 64-bit subtraction per chunk, then
+      // 32-bit compares
       const unsigned long long base = (unsigned long long)(chunk - batch.first_block[ri]) * kMarkPointsPerBlock;
-      const unsigned long long n_pts = par.n_points;
+      const unsigned long long left = par.n_points - base;
+      const unsigned in_chunk = left < (unsigned long long)kMarkPointsPerBlock ? (unsigned)left : (unsigned)kMarkPointsPerBlock;
 #pragma unroll
       for (int k = 0; k < kMarkPointsPerThread; ++k) {
         const float4 v = s_stage[stage * kMarkPointsPerBlock + k * kMarkThreads + threadIdx.x];
         pts[k].x = v.x; pts[k].y = v.y; pts[k].z = v.z;
-        pts[k].ok = base + (unsigned long long)k * kMarkThreads + threadIdx.x < n_pts;
+        pts[k].ok = (unsigned)(k * kMarkThreads) + threadIdx.x < in_chunk;
       }
     }
     if (it == 0) TRACE(0, 2);   // first chunk's data has arrived
@@ -574,17 +577,21 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const Cos
       // .cpp:285-291  (double arithmetic, narrowed to float, compared against the float range^2 and 0.0001)
       const double dx = __dsub_rn(xd, ox), dy = __dsub_rn(yd, oy), dz = __dsub_rn(zd, oz);
       const float distance_2 = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-      if (distance_2 > range2 || (double)distance_2 < 0.0001) continue;
+      // (the remaining rejections are predicates, not branches: nearly every point that gets here passes them, and a
+      // warp runs the arithmetic below as long as one lane needs it anyway)
+      const bool in_range = !(distance_2 > range2 || (double)distance_2 < 0.0001);
       // .cpp:293-303: shift negatives by one voxel (z tests y's sign — sic), multiply by 1/vs, truncate toward zero
       const double X = fx < 0 ? __dsub_rn(xd, g.vs) : xd;
       const double Y = fy < 0 ? __dsub_rn(yd, g.vs) : yd;
       const double Z = fy < 0 ? __dsub_rn(zd, g.vs) : zd;
       const double gx = __dmul_rn(X, g.inv_vs), gy = __dmul_rn(Y, g.inv_vs), gz = __dmul_rn(Z, g.inv_vs);
       const double lim = 8388608.0;   // 2^23 voxels = 2^20 leaves
-      if (!(fabs(gx) < lim && fabs(gy) < lim && fabs(gz) < lim)) { ++drop_range; continue; }
-      const int ix = __double2int_rz(gx), iy = __double2int_rz(gy), iz = __double2int_rz(gz);
+      const bool in_lim = fabs(gx) < lim && fabs(gy) < lim && fabs(gz) < lim;
+      drop_range += (in_range && !in_lim) ? 1u : 0u;
+      const int ix = __double2int_rz(gx), iy = __double2int_rz(gy), iz = __double2int_rz(gz);   // (saturated garbage when !in_lim: masked)
       const int bx = ix >> 3, by = iy >> 3, bz = iz >> 3;
-      if (g.shard_count > 1 && !shard_owns(bx, g.shard_index, g.shard_count, g.shard_width)) continue;
+      const bool owns = g.shard_count <= 1 || shard_owns(bx, g.shard_index, g.shard_count, g.shard_width);
+      if (!(in_range && in_lim && owns)) continue;
       const unsigned l = (unsigned)(((ix & 7) * 8 + (iy & 7)) * 8 + (iz & 7));
       // find-or-claim the (reading, leaf) in the block-local table (consecutive points of a thread mostly share it)
       const int rx = bx - batch.ref_bx;
