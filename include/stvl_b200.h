@@ -215,6 +215,17 @@ int stvl_update_cycle_device(stvl_grid_t * g, double now, const stvl_frustum_t *
 int stvl_update_cycle_sharded_device(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
                                      const stvl_reading_t * readings, uint32_t n_readings,
                                      const stvl_costmap_params_t * p, uint8_t * costmap_dev, int root, int pipelined);
+/* SpatioTemporalVoxelLayer::updateCosts (stvl/src/spatio_temporal_voxel_layer.cpp:666-696) on DEVICE byte grids of
+ * p->size_x * p->size_y cells: if n_footprint >= 3, the footprint polygon (world x,y pairs, convex) is set to
+ * FREE_SPACE (0) in the layer's costmap — nav2 Costmap2D::setConvexPolygonCost(_transformed_footprint, FREE_SPACE), :682-684
+ * (nothing happens if a vertex is off the map; at most 64 vertices) — then, if master_dev != NULL, the window
+ * [min_i, max_i) x [min_j, max_j) of the layer's costmap is combined into the master grid: combination_method 0 =
+ * CostmapLayer::updateWithOverwrite, 1 = updateWithMax (:686-695), anything else leaves the master untouched.
+ * Enqueue only (ordered on stvl_get_stream()). */
+int stvl_update_costs_device(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_t * layer_costmap_dev, uint8_t * master_dev,
+                             const double * footprint_xy, uint32_t n_footprint, int combination_method,
+                             int32_t min_i, int32_t min_j, int32_t max_i, int32_t max_j);
+
 /* The result (marked columns, touched bounds — the touch() calls of spatio_temporal_voxel_layer.cpp:716) of the last
  * costmap pass enqueued by stvl_costmap_device(res = NULL) or stvl_update_cycle_device.  Synchronises. */
 int stvl_get_costmap_result(stvl_grid_t * g, stvl_costmap_result_t * res);

@@ -76,6 +76,10 @@ def lib():
     L.oracle_transform_from_quat.argtypes = [vp, vp, vp]
     L.oracle_transform_cloud.restype = None
     L.oracle_transform_cloud.argtypes = [vp, u64, u32, u32, u32, u32, vp, vp]
+    L.oracle_set_convex_polygon_cost.restype = C.c_int
+    L.oracle_set_convex_polygon_cost.argtypes = [vp, d, d, d, u32, u32, vp, u32, C.c_uint8]
+    L.oracle_update_costs.restype = None
+    L.oracle_update_costs.argtypes = [vp, vp, u32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.oracle_filter_voxel.restype = u64
     L.oracle_filter_voxel.argtypes = [vp, u64, u32, u32, u32, u32, f32, d, d, C.c_int, vp]
     _lib = L
@@ -210,6 +214,21 @@ class OracleGrid:
 
 def frustum_acceleration(t, factor):
     return lib().oracle_frustum_acceleration(t, factor)
+
+
+def set_convex_polygon_cost(costmap, origin_x, origin_y, resolution, polygon_xy, cost):
+    """nav2 Costmap2D::setConvexPolygonCost on a (size_y, size_x) uint8 array, in place; False (nothing changed) if a
+    vertex is off the map."""
+    poly = np.ascontiguousarray(polygon_xy, np.float64).reshape(-1, 2)
+    assert costmap.dtype == np.uint8 and costmap.flags["C_CONTIGUOUS"]
+    return bool(lib().oracle_set_convex_polygon_cost(_ptr(costmap), origin_x, origin_y, resolution, costmap.shape[1], costmap.shape[0],
+                                                     _ptr(poly), len(poly), cost))
+
+
+def update_costs(layer, master, min_i, min_j, max_i, max_j, method):
+    """nav2 CostmapLayer::updateWithOverwrite (0) / updateWithMax (1) of the window into `master`, in place."""
+    assert layer.dtype == np.uint8 and master.dtype == np.uint8 and layer.shape == master.shape
+    lib().oracle_update_costs(_ptr(layer), _ptr(master), layer.shape[1], min_i, min_j, max_i, max_j, method)
 
 
 def transform_from_quat(translation, quat_xyzw):

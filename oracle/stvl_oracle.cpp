@@ -859,3 +859,109 @@ uint64_t oracle_filter_voxel(const void * data, uint64_t n, uint32_t point_step,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------
+// LAYER:666-696 updateCosts: footprint clearing + combination into the master grid.  The byte-grid routines live in
+// nav2_costmap_2d (external, not vendored, version unpinned: package.xml depends on nav2_costmap_2d); restated from the
+// published sources of Costmap2D::setConvexPolygonCost / polygonOutlineCells / convexFillCells / raytraceLine /
+// bresenham2D and CostmapLayer::updateWithMax / updateWithOverwrite.  Parity unpinned like the rest of this file.
+// ---------------------------------------------------------------------------------
+namespace {
+struct MapLocation { unsigned x, y; };
+inline int sign_of(int v) { return v > 0 ? 1 : -1; }
+// Costmap2D::bresenham2D with the PolygonOutlineCells action (collect every visited cell)
+void bresenham2d(std::vector<MapLocation> & cells, unsigned size_x, unsigned abs_da, unsigned abs_db, int error_b, int offset_a,
+                 int offset_b, unsigned offset, unsigned max_length)
+{
+  const unsigned end = std::min(max_length, abs_da);
+  for (unsigned i = 0; i < end; ++i) {
+    cells.push_back(MapLocation{offset % size_x, offset / size_x});
+    offset += offset_a;
+    error_b += abs_db;
+    if ((unsigned)error_b >= abs_da) { offset += offset_b; error_b -= abs_da; }
+  }
+  cells.push_back(MapLocation{offset % size_x, offset / size_x});
+}
+// Costmap2D::raytraceLine(at, x0, y0, x1, y1) with max_length = UINT_MAX, min_length = 0
+void raytrace_line(std::vector<MapLocation> & cells, unsigned size_x, unsigned x0, unsigned y0, unsigned x1, unsigned y1)
+{
+  const int dx = (int)x1 - (int)x0, dy = (int)y1 - (int)y0;
+  const unsigned abs_dx = (unsigned)std::abs(dx), abs_dy = (unsigned)std::abs(dy);
+  const int offset_dx = sign_of(dx), offset_dy = sign_of(dy) * (int)size_x;
+  const unsigned offset = y0 * size_x + x0;
+  // dist / scale only matter for a finite max_length: scale = 1 here
+  if (abs_dx >= abs_dy) {
+    bresenham2d(cells, size_x, abs_dx, abs_dy, (int)(abs_dx / 2), offset_dx, offset_dy, offset, abs_dx);
+    return;
+  }
+  bresenham2d(cells, size_x, abs_dy, abs_dx, (int)(abs_dy / 2), offset_dy, offset_dx, offset, abs_dy);
+}
+}  // namespace
+
+extern "C" {
+// Costmap2D::setConvexPolygonCost: returns 0 (and changes nothing) if a vertex is off the map.  polygon_xy = n x (x, y).
+int oracle_set_convex_polygon_cost(uint8_t * costmap, double origin_x, double origin_y, double resolution, uint32_t size_x,
+                                   uint32_t size_y, const double * polygon_xy, uint32_t n, uint8_t cost)
+{
+  std::vector<MapLocation> map_polygon;
+  for (uint32_t i = 0; i < n; ++i) {
+    MapLocation loc;
+    if (!worldToMap(polygon_xy[2 * i], polygon_xy[2 * i + 1], origin_x, origin_y, resolution, size_x, size_y, loc.x, loc.y)) return 0;
+    map_polygon.push_back(loc);
+  }
+  std::vector<MapLocation> cells;
+  // convexFillCells
+  if (map_polygon.size() >= 3) {
+    // polygonOutlineCells: every edge, then the closing edge
+    for (size_t i = 0; i + 1 < map_polygon.size(); ++i)
+      raytrace_line(cells, size_x, map_polygon[i].x, map_polygon[i].y, map_polygon[i + 1].x, map_polygon[i + 1].y);
+    raytrace_line(cells, size_x, map_polygon.back().x, map_polygon.back().y, map_polygon[0].x, map_polygon[0].y);
+    // "quick bubble sort to sort points by x"
+    MapLocation swap;
+    size_t i = 0;
+    while (i + 1 < cells.size()) {
+      if (cells[i].x > cells[i + 1].x) {
+        swap = cells[i]; cells[i] = cells[i + 1]; cells[i + 1] = swap;
+        if (i > 0) --i;
+      } else {
+        ++i;
+      }
+    }
+    i = 0;
+    MapLocation min_pt, max_pt;
+    const unsigned min_x = cells[0].x, max_x = cells[cells.size() - 1].x;
+    // walk through each column and mark cells inside the polygon
+    for (unsigned x = min_x; x <= max_x; ++x) {
+      if (i + 1 >= cells.size()) break;
+      if (cells[i].y < cells[i + 1].y) { min_pt = cells[i]; max_pt = cells[i + 1]; }
+      else { min_pt = cells[i + 1]; max_pt = cells[i]; }
+      i += 2;
+      while (i < cells.size() && cells[i].x == x) {
+        if (cells[i].y < min_pt.y) min_pt = cells[i];
+        else if (cells[i].y > max_pt.y) max_pt = cells[i];
+        ++i;
+      }
+      for (unsigned y = min_pt.y; y <= max_pt.y; ++y) cells.push_back(MapLocation{x, y});
+    }
+  }
+  for (const MapLocation & c : cells) costmap[(size_t)c.y * size_x + c.x] = cost;
+  return 1;
+}
+
+// CostmapLayer::updateWithOverwrite (method 0) / updateWithMax (method 1) over [min_i,max_i) x [min_j,max_j); 255 = NO_INFORMATION
+void oracle_update_costs(const uint8_t * layer, uint8_t * master, uint32_t size_x, int min_i, int min_j, int max_i, int max_j, int method)
+{
+  for (int j = min_j; j < max_j; ++j) {
+    size_t it = (size_t)size_x * j + min_i;
+    for (int i = min_i; i < max_i; ++i, ++it) {
+      if (method == 0) {
+        if (layer[it] != 255) master[it] = layer[it];
+      } else if (method == 1) {
+        if (layer[it] == 255) continue;
+        const uint8_t old_cost = master[it];
+        if (old_cost == 255 || old_cost < layer[it]) master[it] = layer[it];
+      }
+    }
+  }
+}
+}  // extern "C"

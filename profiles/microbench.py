@@ -122,6 +122,12 @@ def main():
     cm = torch.zeros((cp_["size_y"], cp_["size_x"]), dtype=torch.uint8, device="cuda")
     us = timed(stream, lambda: stvl._check(L.stvl_costmap_device(h, C.byref(params), cm.data_ptr(), None)), 40)
     print("costmap %dx%d                                  %8.1f us" % (cp_["size_x"], cp_["size_y"], us))
+    # updateCosts on device byte grids: footprint polygon + updateWithMax of the whole 1600 x 1600 window
+    master = torch.zeros_like(cm)
+    fp = np.array([[0.35, 0.25], [-0.35, 0.25], [-0.35, -0.25], [0.35, -0.25]]) + np.array([cp_["origin_x"] + 40.0, cp_["origin_y"] + 40.0])
+    us = timed(stream, lambda: g.update_costs_device(params, cm.data_ptr(), master.data_ptr(), footprint_xy=fp, combination_method=1), 40)
+    print("updateCosts (footprint + updateWithMax) %dx%d      %8.1f us  -> %7.1f GB/s (2 B read + 1 B written per cell)" % (
+        cp_["size_x"], cp_["size_y"], us, cp_["size_x"] * cp_["size_y"] * 3 / us / 1e3))
     print("pool:", {k: getattr(g.pool_stats(), k) for k in ("leaves_in_use", "tiles_in_use", "kernel_launches")})
 
 

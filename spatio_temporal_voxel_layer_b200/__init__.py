@@ -89,7 +89,7 @@ EXPORTED_SYMBOLS = [
     "stvl_get_cleared", "stvl_get_points", "stvl_get_ambiguous", "stvl_reset", "stvl_reset_area", "stvl_active_count",
     "stvl_get_voxels", "stvl_load_voxels", "stvl_index_to_world", "stvl_voxel_size", "stvl_columns_to_dense",
     "stvl_costmap_from_dense", "stvl_get_pool_stats", "stvl_get_stream", "stvl_synchronize",
-    "stvl_update_cycle_device", "stvl_update_cycle_sharded_device", "stvl_get_costmap_result", "stvl_enable_timing", "stvl_get_timing",
+    "stvl_update_cycle_device", "stvl_update_cycle_sharded_device", "stvl_update_costs_device", "stvl_get_costmap_result", "stvl_enable_timing", "stvl_get_timing",
     "stvl_nccl_unique_id", "stvl_comm_init", "stvl_comm_destroy", "stvl_costmap_sharded_device", "stvl_costmap_sharded_flush",
 ]
 
@@ -148,6 +148,7 @@ def load_library(build_if_missing=True):
     L.stvl_synchronize.argtypes = [vp]
     L.stvl_update_cycle_device.argtypes = [vp, d, vp, u32, C.POINTER(Reading), u32, C.POINTER(CostmapParams), vp]
     L.stvl_get_costmap_result.argtypes = [vp, C.POINTER(CostmapResult)]
+    L.stvl_update_costs_device.argtypes = [vp, C.POINTER(CostmapParams), vp, vp, vp, u32, C.c_int, i32, i32, i32, i32]
     L.stvl_update_cycle_sharded_device.argtypes = [vp, d, vp, u32, C.POINTER(Reading), u32, C.POINTER(CostmapParams), vp, C.c_int, C.c_int]
     L.stvl_enable_timing.argtypes = [vp, u32]
     L.stvl_get_timing.argtypes = [vp, C.POINTER(Timing)]
@@ -343,6 +344,17 @@ class SpatioTemporalVoxelGrid:
             m._fill(arr[i], now, keep)
         _check(self.L.stvl_update_cycle_sharded_device(self.h, float(now), _ptr(blocks) if len(blocks) else None, len(blocks), arr, n,
                                                        C.byref(params), costmap_dev_ptr, int(root), 1 if pipelined else 0))
+
+    def update_costs_device(self, params, layer_costmap_dev_ptr, master_dev_ptr, footprint_xy=None, combination_method=1, window=None):
+        """SpatioTemporalVoxelLayer::updateCosts on device byte grids (reference spatio_temporal_voxel_layer.cpp:666-696):
+        footprint clearing in the layer's costmap, then updateWithOverwrite (0) / updateWithMax (1) of `window` =
+        (min_i, min_j, max_i, max_j) into the master grid.  Enqueue only."""
+        fp = None if footprint_xy is None else np.ascontiguousarray(footprint_xy, np.float64).reshape(-1, 2)
+        if window is None:
+            window = (0, 0, params.size_x, params.size_y)
+        _check(self.L.stvl_update_costs_device(self.h, C.byref(params), layer_costmap_dev_ptr, master_dev_ptr,
+                                               _ptr(fp) if fp is not None and len(fp) else None, 0 if fp is None else len(fp),
+                                               int(combination_method), *[int(v) for v in window]))
 
     def costmap_result(self):
         res = CostmapResult()

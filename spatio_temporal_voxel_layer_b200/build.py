@@ -13,7 +13,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libstvl_b200.so")
-SOURCES = ["stvl_kernels.cu", "stvl_voxel_filter.cu", "stvl_api.cu", "stvl_geometry.cpp"]
+SOURCES = ["stvl_kernels.cu", "stvl_voxel_filter.cu", "stvl_costs.cu", "stvl_api.cu", "stvl_geometry.cpp"]
 HEADERS = ["stvl_device.cuh", "stvl_kernels.h", "stvl_geometry.h", "stvl_voxel_filter.h"]
 
 NVCC_FLAGS = [

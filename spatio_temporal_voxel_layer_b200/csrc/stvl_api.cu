@@ -93,6 +93,7 @@ struct stvl_grid {
   DevBuf<int32_t> col_ix, col_iy;
   DevBuf<uint32_t> col_cnt;
   DevBuf<int32_t> dump_x, dump_y, dump_z;
+  DevBuf<int32_t> poly_cols;        // per-column y range of a footprint polygon's outline (stvl_update_costs_device)
   DevBuf<double> dump_t;
   // host bookkeeping
   uint32_t out_flags = STVL_OUT_CLEARED | STVL_OUT_AMBIGUOUS;
@@ -1566,6 +1567,33 @@ int stvl_update_cycle_sharded_device(stvl_grid_t * g, double now, const stvl_fru
     if (rc != STVL_OK) return rc;
   }
   g->win_pending = b;
+  return STVL_OK;
+}
+
+int stvl_update_costs_device(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_t * layer_costmap_dev, uint8_t * master_dev,
+                             const double * footprint_xy, uint32_t n_footprint, int combination_method,
+                             int32_t min_i, int32_t min_j, int32_t max_i, int32_t max_j)
+{
+  ENTER(g);
+  if (!p || !layer_costmap_dev) return fail(STVL_ERR_INVALID, "NULL argument");
+  if (!(p->resolution > 0)) return fail(STVL_ERR_INVALID, "resolution must be positive");
+  if (n_footprint && !footprint_xy) return fail(STVL_ERR_INVALID, "footprint_xy is NULL");
+  if (n_footprint > (uint32_t)kMaxPolygonVertices) return fail(STVL_ERR_INVALID, "at most %d footprint vertices", kMaxPolygonVertices);
+  if (master_dev && (min_i < 0 || min_j < 0 || max_i > (int64_t)p->size_x || max_j > (int64_t)p->size_y))
+    return fail(STVL_ERR_INVALID, "window [%d,%d) x [%d,%d) outside the %u x %u map", min_i, max_i, min_j, max_j, p->size_x, p->size_y);
+  if (n_footprint >= 3 && p->size_x && p->size_y) {
+    int rc = ensure(g, g->poly_cols, (size_t)p->size_x * 2);
+    if (rc != STVL_OK) return rc;
+    PolygonParams poly{};
+    poly.n = n_footprint;
+    for (uint32_t i = 0; i < 2 * n_footprint; ++i) poly.xy[i] = footprint_xy[i];
+    CU(launch_polygon_cost(layer_costmap_dev, to_dev(*p), poly, 0 /* FREE_SPACE */, g->poly_cols.p, g->poly_cols.p + p->size_x, g->stream));
+    g->launches += 1;
+  }
+  if (master_dev && (combination_method == 0 || combination_method == 1)) {
+    CU(launch_update_costs(layer_costmap_dev, master_dev, p->size_x, min_i, min_j, max_i, max_j, combination_method, g->sm_count, g->stream));
+    g->launches += 1;
+  }
   return STVL_OK;
 }
 

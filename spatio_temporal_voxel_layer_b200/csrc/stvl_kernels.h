@@ -24,6 +24,18 @@ struct CostmapDev {
   uint8_t default_value, lethal;
 };
 
+// updateCosts on device byte grids (stvl_costs.cu)
+constexpr int kMaxPolygonVertices = 64;
+struct PolygonParams {
+  double xy[2 * kMaxPolygonVertices];
+  uint32_t n;
+  uint32_t pad;
+};
+cudaError_t launch_polygon_cost(uint8_t * costmap_dev, const CostmapDev & p, const PolygonParams & poly, uint8_t cost, int32_t * colmin,
+                                int32_t * colmax, cudaStream_t s);
+cudaError_t launch_update_costs(const uint8_t * layer_dev, uint8_t * master_dev, uint32_t size_x, int min_i, int min_j, int max_i, int max_j,
+                                int method, int sm_count, cudaStream_t s);
+
 cudaError_t launch_fold_alloc(const GridView & g, cudaStream_t s);
 cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s, bool pdl = false,
                         const CostmapDev * fused_costmap = nullptr, uint8_t * costmap_dev = nullptr);

@@ -9,6 +9,8 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <cstdlib>
+#include "geometry_msgs/msg/point.hpp"
 #include "nav2_costmap_2d/cost_values.hpp"
 
 namespace nav2_costmap_2d
@@ -63,6 +65,71 @@ public:
     resetMaps();
   }
   mutex_t * getMutex() { return &access_; }
+
+  // setConvexPolygonCost / convexFillCells / polygonOutlineCells / raytraceLine / bresenham2D, as nav2 has them: map the
+  // vertices (a vertex off the map: return false, nothing set), collect the Bresenham outline of every edge and of the
+  // closing edge, sort the cells by x, fill every column between its lowest and highest outline cell.
+  struct MapLocation { unsigned int x, y; };
+  bool setConvexPolygonCost(const std::vector<geometry_msgs::msg::Point> & polygon, unsigned char cost_value)
+  {
+    std::vector<MapLocation> map_polygon;
+    for (const auto & pt : polygon) {
+      MapLocation loc;
+      if (!worldToMap(pt.x, pt.y, loc.x, loc.y)) return false;
+      map_polygon.push_back(loc);
+    }
+    std::vector<MapLocation> cells;
+    convexFillCells(map_polygon, cells);
+    for (const auto & c : cells) costmap_[getIndex(c.x, c.y)] = cost_value;
+    return true;
+  }
+  void polygonOutlineCells(const std::vector<MapLocation> & polygon, std::vector<MapLocation> & cells) const
+  {
+    for (size_t i = 0; i + 1 < polygon.size(); ++i) raytraceLine(cells, polygon[i].x, polygon[i].y, polygon[i + 1].x, polygon[i + 1].y);
+    if (!polygon.empty()) raytraceLine(cells, polygon.back().x, polygon.back().y, polygon[0].x, polygon[0].y);
+  }
+  void convexFillCells(const std::vector<MapLocation> & polygon, std::vector<MapLocation> & cells) const
+  {
+    if (polygon.size() < 3) return;
+    polygonOutlineCells(polygon, cells);
+    size_t i = 0;
+    while (i + 1 < cells.size()) {   // "quick bubble sort to sort points by x"
+      if (cells[i].x > cells[i + 1].x) { std::swap(cells[i], cells[i + 1]); if (i > 0) --i; } else { ++i; }
+    }
+    i = 0;
+    MapLocation min_pt, max_pt;
+    const unsigned int min_x = cells[0].x, max_x = cells[cells.size() - 1].x;
+    for (unsigned int x = min_x; x <= max_x; ++x) {
+      if (i + 1 >= cells.size()) break;
+      if (cells[i].y < cells[i + 1].y) { min_pt = cells[i]; max_pt = cells[i + 1]; } else { min_pt = cells[i + 1]; max_pt = cells[i]; }
+      i += 2;
+      while (i < cells.size() && cells[i].x == x) {
+        if (cells[i].y < min_pt.y) min_pt = cells[i]; else if (cells[i].y > max_pt.y) max_pt = cells[i];
+        ++i;
+      }
+      for (unsigned int y = min_pt.y; y <= max_pt.y; ++y) cells.push_back(MapLocation{x, y});
+    }
+  }
+  void raytraceLine(std::vector<MapLocation> & cells, unsigned int x0, unsigned int y0, unsigned int x1, unsigned int y1) const
+  {
+    const int dx = (int)x1 - (int)x0, dy = (int)y1 - (int)y0;
+    const unsigned int abs_dx = (unsigned int)std::abs(dx), abs_dy = (unsigned int)std::abs(dy);
+    const int offset_dx = dx > 0 ? 1 : -1, offset_dy = (dy > 0 ? 1 : -1) * (int)size_x_;
+    const unsigned int offset = y0 * size_x_ + x0;
+    if (abs_dx >= abs_dy) { bresenham2D(cells, abs_dx, abs_dy, (int)(abs_dx / 2), offset_dx, offset_dy, offset); return; }
+    bresenham2D(cells, abs_dy, abs_dx, (int)(abs_dy / 2), offset_dy, offset_dx, offset);
+  }
+  void bresenham2D(std::vector<MapLocation> & cells, unsigned int abs_da, unsigned int abs_db, int error_b, int offset_a, int offset_b,
+                   unsigned int offset) const
+  {
+    for (unsigned int i = 0; i < abs_da; ++i) {
+      cells.push_back(MapLocation{offset % size_x_, offset / size_x_});
+      offset += offset_a;
+      error_b += abs_db;
+      if ((unsigned int)error_b >= abs_da) { offset += offset_b; error_b -= abs_da; }
+    }
+    cells.push_back(MapLocation{offset % size_x_, offset / size_x_});
+  }
 
 protected:
   unsigned int size_x_ = 0, size_y_ = 0;

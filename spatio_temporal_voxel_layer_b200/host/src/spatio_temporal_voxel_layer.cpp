@@ -272,33 +272,7 @@ void SpatioTemporalVoxelLayer::updateCosts(
     current_ = true;
   }
   if (_update_footprint_enabled) {
-    // setConvexPolygonCost(_transformed_footprint, FREE_SPACE): cells under the footprint polygon are freed
-    if (_transformed_footprint.size() >= 3) {
-      double fx0 = 1e300, fy0 = 1e300, fx1 = -1e300, fy1 = -1e300;
-      for (const auto & p : _transformed_footprint) {
-        fx0 = std::min(fx0, p.x); fy0 = std::min(fy0, p.y); fx1 = std::max(fx1, p.x); fy1 = std::max(fy1, p.y);
-      }
-      for (unsigned int my = 0; my < getSizeInCellsY(); ++my) {
-        for (unsigned int mx = 0; mx < getSizeInCellsX(); ++mx) {
-          double wx, wy;
-          mapToWorld(mx, my, wx, wy);
-          if (wx < fx0 || wx > fx1 || wy < fy0 || wy > fy1) {continue;}
-          bool inside = true;   // convex polygon, either winding
-          int sign = 0;
-          const size_t n = _transformed_footprint.size();
-          for (size_t i = 0; i < n && inside; ++i) {
-            const auto & a = _transformed_footprint[i];
-            const auto & b = _transformed_footprint[(i + 1) % n];
-            const double cr = (b.x - a.x) * (wy - a.y) - (b.y - a.y) * (wx - a.x);
-            const int s = cr > 0 ? 1 : (cr < 0 ? -1 : 0);
-            if (s != 0) {
-              if (sign == 0) {sign = s;} else if (s != sign) {inside = false;}
-            }
-          }
-          if (inside) {costmap_[getIndex(mx, my)] = nav2_costmap_2d::FREE_SPACE;}
-        }
-      }
-    }
+    setConvexPolygonCost(_transformed_footprint, nav2_costmap_2d::FREE_SPACE);
   }
   switch (_combination_method) {
     case 0:

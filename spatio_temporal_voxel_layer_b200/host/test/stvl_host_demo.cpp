@@ -31,7 +31,7 @@ int main(int argc, char ** argv)
   float vs; int32_t decay_model, mark_threshold, track_unknown, publish; double voxel_decay;
   rd(in, vs); rd(in, decay_model); rd(in, voxel_decay); rd(in, mark_threshold); rd(in, track_unknown); rd(in, publish);
   lp.voxel_size = vs; lp.decay_model = decay_model; lp.voxel_decay = voxel_decay; lp.mark_threshold = mark_threshold;
-  lp.track_unknown_space = track_unknown != 0; lp.publish_voxel_map = publish != 0; lp.update_footprint_enabled = false;
+  lp.track_unknown_space = track_unknown != 0; lp.publish_voxel_map = publish != 0; lp.update_footprint_enabled = true;
   double ox, oy, res; uint32_t sx, sy;
   rd(in, ox); rd(in, oy); rd(in, res); rd(in, sx); rd(in, sy);
   uint32_t n_sources;
@@ -56,6 +56,13 @@ int main(int argc, char ** argv)
   SpatioTemporalVoxelLayer layer;
   layer.configure(lp, clock, &parent);
   layer.setFusedCostmap(!literal);
+  {
+    // a 0.7 m x 0.5 m robot footprint; the robot pose of a cycle is the first source's origin, yaw = 0.3 * cycle
+    std::vector<geometry_msgs::msg::Point> fp(4);
+    const double hx = 0.35, hy = 0.25;
+    fp[0].x = hx; fp[0].y = hy; fp[1].x = -hx; fp[1].y = hy; fp[2].x = -hx; fp[2].y = -hy; fp[3].x = hx; fp[3].y = -hy;
+    layer.setFootprint(fp);
+  }
   try {
     layer.onInitialize();
   } catch (const std::exception & e) {
@@ -70,9 +77,11 @@ int main(int argc, char ** argv)
   wr(out, n_cycles);
   for (uint32_t c = 0; c < n_cycles; ++c) {
     rd(in, now);
+    double robot_x = 0.0, robot_y = 0.0;
     for (uint32_t s = 0; s < n_sources; ++s) {
       geometry_msgs::msg::Point o; geometry_msgs::msg::Quaternion q;
       rd(in, o.x); rd(in, o.y); rd(in, o.z); rd(in, q.x); rd(in, q.y); rd(in, q.z); rd(in, q.w);
+      if (s == 0) { robot_x = o.x; robot_y = o.y; }
       uint32_t n_points;
       rd(in, n_points);
       auto cloud = std::make_shared<sensor_msgs::msg::PointCloud2>();
@@ -87,8 +96,10 @@ int main(int argc, char ** argv)
       layer.GetBuffer("source" + std::to_string(s))->BufferCloud(o, q, cloud);
     }
     double b[4] = {1e308, 1e308, -1e308, -1e308};
-    layer.updateBounds(0.0, 0.0, 0.0, &b[0], &b[1], &b[2], &b[3]);
-    // what the cycle produced: costmap bytes, bounds, flattened costmap, occupancy cloud size
+    layer.updateBounds(robot_x, robot_y, 0.3 * c, &b[0], &b[1], &b[2], &b[3]);
+    // master grid merge: updateCosts = footprint clearing in the layer's costmap + updateWithMax over the whole map
+    layer.updateCosts(*parent.getCostmap(), 0, 0, (int)sx, (int)sy);
+    // what the cycle produced: costmap bytes (after the footprint clearing), bounds, flattened costmap, occupancy cloud size
     const uint32_t cells = sx * sy;
     wr(out, cells);
     out.write(reinterpret_cast<const char *>(layer.getCharMap()), cells);
@@ -99,8 +110,6 @@ int main(int argc, char ** argv)
     for (const auto & kv : *cm) { wr(out, kv.first.x); wr(out, kv.first.y); const uint32_t cnt = kv.second; wr(out, cnt); }
     const uint64_t npts = layer.LastVoxelCloud() ? layer.LastVoxelCloud()->width : 0;
     wr(out, npts);
-    // master grid merge (updateCosts with updateWithMax over the whole map)
-    layer.updateCosts(*parent.getCostmap(), 0, 0, (int)sx, (int)sy);
   }
   // final state of the master costmap and the grid itself
   out.write(reinterpret_cast<const char *>(parent.getCostmap()->getCharMap()), (std::streamsize)sx * sy);

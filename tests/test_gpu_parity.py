@@ -428,6 +428,54 @@ def test_mixed_api_soak(stvl, oracle, seed):
     gg.close()
 
 
+def test_update_costs_on_device(stvl, oracle):
+    """SURVEY §8f rank 3 — SpatioTemporalVoxelLayer::updateCosts on device byte grids (stvl_update_costs_device): footprint
+    clearing (nav2 setConvexPolygonCost: Bresenham outline + column fill) and updateWithMax / updateWithOverwrite of a
+    window into the master grid, against the literal CPU restatement.  Random convex polygons of every size and
+    orientation, some with a vertex off the map (nothing may change), degenerate ones, unaligned windows."""
+    import torch
+    rng = np.random.default_rng(12)
+    gg = stvl.SpatioTemporalVoxelGrid(0.05)
+    sx, sy, res, ox, oy = 317, 251, 0.05, -7.3, -4.1
+    params = stvl.CostmapParams(ox, oy, res, sx, sy, 0, 0, 254)
+    n_filled = n_failed = 0
+    for it in range(60):
+        layer = rng.choice(np.array([0, 1, 99, 128, 253, 254, 255], np.uint8), (sy, sx), p=[0.5, 0.05, 0.05, 0.05, 0.05, 0.2, 0.1])
+        master = rng.integers(0, 256, (sy, sx)).astype(np.uint8)
+        # a convex polygon: points on an ellipse, random rotation / size / vertex count; every 6th one pokes out of the map
+        nv = int(rng.integers(3, 13))
+        ang = np.sort(rng.uniform(0, 2 * np.pi, nv))
+        if it % 7 == 3:
+            ang = ang[::-1].copy()                      # clockwise
+        a, b = rng.uniform(0.03, 3.0, 2)
+        cx = rng.uniform(ox + 3.2, ox + sx * res - 3.2) if it % 6 else ox + sx * res - 0.5
+        cy = rng.uniform(oy + 3.2, oy + sy * res - 3.2)
+        th = rng.uniform(0, np.pi)
+        px, py = a * np.cos(ang), b * np.sin(ang)
+        poly = np.stack([cx + px * np.cos(th) - py * np.sin(th), cy + px * np.sin(th) + py * np.cos(th)], 1)
+        if it == 10:
+            poly = np.repeat(poly[:1], 4, axis=0)       # all vertices in one cell
+        if it == 11:
+            poly = poly[:2]                             # not a polygon: nothing happens
+        method = int(rng.integers(0, 3))                # 2 = neither: master untouched
+        i0, j0 = int(rng.integers(0, sx // 2)), int(rng.integers(0, sy // 2))
+        window = (i0, j0, int(rng.integers(i0, sx + 1)), int(rng.integers(j0, sy + 1)))
+        want_layer, want_master = layer.copy(), master.copy()
+        ok = oracle.set_convex_polygon_cost(want_layer, ox, oy, res, poly, 0) if len(poly) >= 3 else False
+        n_filled += int(ok and (want_layer != layer).any())
+        n_failed += int(not ok)
+        if method in (0, 1):
+            oracle.update_costs(want_layer, want_master, *window, method)
+        layer_dev, master_dev = torch.from_numpy(layer).cuda(), torch.from_numpy(master).cuda()
+        torch.cuda.synchronize()
+        gg.update_costs_device(params, layer_dev.data_ptr(), master_dev.data_ptr(), footprint_xy=poly, combination_method=method, window=window)
+        gg.synchronize()
+        assert np.array_equal(layer_dev.cpu().numpy(), want_layer), "layer costmap differs (iteration %d, %d vertices)" % (it, len(poly))
+        assert np.array_equal(master_dev.cpu().numpy(), want_master), "master grid differs (iteration %d, method %d)" % (it, method)
+    assert n_filled >= 35 and n_failed >= 8
+    gg.close()
+
+
 def test_leaf_pool_growth_replays_mark(stvl, oracle):
     """A Mark that exhausts the leaf pool is replayed after the pool (and its hash) grew: nothing is lost."""
     rng = np.random.default_rng(13)

@@ -4,6 +4,7 @@ SpatioTemporalVoxelLayer plugin flow, driven through a scenario file by stvl_hos
 CPU: the host code compiles with plain g++ against the shim headers, links libstvl_b200.so and refuses to run without
 a GPU.  GPU: a multi-cycle scenario through updateBounds/updateCosts reproduces the oracle's costmap bytes, bounds and
 flattened costmap — with the fused GPU costmap path and with the reference's literal host loops."""
+import math
 import os
 import struct
 import subprocess
@@ -106,6 +107,7 @@ def test_plugin_cycle_matches_oracle(tmp_path, stvl, oracle, literal):
 
     og = oracle.OracleGrid(0.05, 255.0, 0, 1.5, True)
     master_ref = np.zeros(cfg["size_x"] * cfg["size_y"], np.uint8)   # the demo's master grid starts at 0
+    footprints = []
     for (now, readings), (cm, b, cols, npts) in zip(cycles, got):
         fr = np.concatenate([oracle.depth_frustum(p["vfov"], p["hfov"], p["min_z"], p["max_z"], o, q, p["accel"]) for o, q, _ in readings])
         og.clear_frustums(now, fr)
@@ -113,6 +115,16 @@ def test_plugin_cycle_matches_oracle(tmp_path, stvl, oracle, literal):
             og.mark(oracle.filter_passthrough(cloud, p["min_obstacle_height"], p["max_obstacle_height"]), o, p["obstacle_range"], now)
         ocm, ob, on = og.update_ros_costmap(cfg["origin_x"], cfg["origin_y"], cfg["resolution"], cfg["size_x"], cfg["size_y"],
                                             cfg["mark_threshold"], 255)
+        # updateFootprint (reference spatio_temporal_voxel_layer.cpp:529-548): the demo's 0.7 m x 0.5 m footprint at the
+        # first source's origin, yaw 0.3 * cycle, touches the bounds; updateCosts (:682-684) frees the cells under it
+        cyc = len(footprints)
+        rx, ry, yaw = readings[0][0][0], readings[0][0][1], 0.3 * cyc
+        fp = [(rx + (px * math.cos(yaw) - py * math.sin(yaw)), ry + (px * math.sin(yaw) + py * math.cos(yaw)))
+              for px, py in ((0.35, 0.25), (-0.35, 0.25), (-0.35, -0.25), (0.35, -0.25))]
+        footprints.append(fp)
+        for x, y in fp:
+            ob = np.array([min(ob[0], x), min(ob[1], y), max(ob[2], x), max(ob[3], y)])
+        assert oracle.set_convex_polygon_cost(ocm, cfg["origin_x"], cfg["origin_y"], cfg["resolution"], fp, 0)
         assert np.array_equal(cm, ocm.reshape(-1)), "layer costmap bytes differ"
         np.testing.assert_array_equal(b, ob)
         ox, oy, oc = og.costmap()

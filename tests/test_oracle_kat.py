@@ -206,3 +206,39 @@ def test_passthrough_and_voxel_filters(oracle):
     c = (cloud[0, :3] + cloud[1, :3]) / np.float32(2)
     assert any(np.array_equal(r, c) for r in v) and any(np.array_equal(r, cloud[2, :3]) for r in v)
     assert oracle.filter_voxel(cloud, 0.05, 0.3, 2.0, 2).shape == (1, 3)
+
+
+def test_update_costs_known_answers(oracle):
+    """updateCosts building blocks, hand-checked: setConvexPolygonCost fills the cells between the
+    Bresenham outlines column by column, fails without side effects when a vertex is off the map; updateWithMax never
+    lowers a cost and treats 255 as "no information" on both sides; updateWithOverwrite copies everything but 255."""
+    cm = np.full((12, 16), 254, np.uint8)
+    # axis-aligned rectangle, resolution 0.5, origin (-1, -2): vertices map to cells (3..9, 2..7)
+    assert oracle.set_convex_polygon_cost(cm, -1.0, -2.0, 0.5, [(0.6, -0.9), (3.9, -0.9), (3.9, 1.9), (0.6, 1.9)], 0)
+    want = np.full((12, 16), 254, np.uint8)
+    want[2:8, 3:10] = 0
+    assert np.array_equal(cm, want)
+    # a triangle: (2,2) -> (10,2) -> (2,10) in cells: column x holds rows 2 .. 12 - x (the hypotenuse is an exact diagonal)
+    cm = np.full((16, 16), 9, np.uint8)
+    assert oracle.set_convex_polygon_cost(cm, 0.0, 0.0, 1.0, [(2.5, 2.5), (10.5, 2.5), (2.5, 10.5)], 0)
+    for x in range(16):
+        col = np.nonzero(cm[:, x] == 0)[0]
+        if 2 <= x <= 10:
+            assert col.min() == 2 and col.max() == 12 - x and len(col) == 11 - x, (x, col)
+        else:
+            assert len(col) == 0
+    # a vertex off the map: nothing changes
+    before = cm.copy()
+    assert not oracle.set_convex_polygon_cost(cm, 0.0, 0.0, 1.0, [(2.5, 2.5), (20.5, 2.5), (2.5, 10.5)], 0)
+    assert np.array_equal(cm, before)
+    layer = np.array([[0, 100, 255, 254], [254, 255, 0, 50]], np.uint8)
+    master = np.array([[255, 200, 7, 10], [253, 1, 255, 60]], np.uint8)
+    m = master.copy()
+    oracle.update_costs(layer, m, 0, 0, 4, 2, 1)      # max
+    assert m.tolist() == [[0, 200, 7, 254], [254, 1, 0, 60]]
+    m = master.copy()
+    oracle.update_costs(layer, m, 0, 0, 4, 2, 0)      # overwrite
+    assert m.tolist() == [[0, 100, 7, 254], [254, 1, 0, 50]]
+    m = master.copy()
+    oracle.update_costs(layer, m, 1, 0, 3, 1, 0)      # window [1,3) x [0,1)
+    assert m.tolist() == [[255, 100, 7, 10], [253, 1, 255, 60]]
