@@ -84,20 +84,42 @@ polygon_cost_kernel(uint8_t * __restrict__ costmap, const CostmapDev p, const __
   }
 }
 
-// CostmapLayer::updateWithOverwrite (method 0) / updateWithMax (method 1) over the window; 255 = NO_INFORMATION
+// CostmapLayer::updateWithOverwrite (method 0) / updateWithMax (method 1) over the window; 255 = NO_INFORMATION.
+// Four cells per 32-bit word with the byte-wise SIMD intrinsics:
+//   take = (layer != 255) && (method 0 || master == 255 || master < layer);   master = take ? layer : master
+__device__ __forceinline__ uint32_t combine4(uint32_t c, uint32_t m, int method)
+{
+  const uint32_t known = ~__vcmpeq4(c, 0xFFFFFFFFu);
+  const uint32_t take = method == 0 ? known : (known & (__vcmpeq4(m, 0xFFFFFFFFu) | __vcmpgtu4(c, m)));
+  return (m & ~take) | (c & take);
+}
+// One thread per 16-byte aligned chunk of a window row (a row of the window starts and ends anywhere: the first and the
+// last chunk of a row are done byte by byte).
 __global__ void __launch_bounds__(256)
 update_costs_kernel(const uint8_t * __restrict__ layer, uint8_t * __restrict__ master, const uint32_t size_x, const int min_i, const int min_j,
-                    const int max_i, const int max_j, const int method)
+                    const int max_i, const int max_j, const int method, const unsigned chunks_per_row)
 {
-  const unsigned w = (unsigned)(max_i - min_i);
-  const unsigned long long total = (unsigned long long)w * (unsigned)(max_j - min_j);
+  const unsigned long long total = (unsigned long long)chunks_per_row * (unsigned)(max_j - min_j);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(layer) | reinterpret_cast<uintptr_t>(master)) & 15u) == 0 && (size_x & 15u) == 0;
   for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
-    const size_t it = (size_t)(min_j + (int)(t / w)) * size_x + (size_t)(min_i + (int)(t % w));
-    const uint8_t c = layer[it];
-    if (c == 255) continue;
-    if (method == 0) { master[it] = c; continue; }
-    const uint8_t old_cost = master[it];
-    if (old_cost == 255 || old_cost < c) master[it] = c;
+    const size_t row = (size_t)(min_j + (int)(t / chunks_per_row)) * size_x;
+    const int c0 = (min_i & ~15) + (int)(t % chunks_per_row) * 16;   // chunk [c0, c0 + 16) of the row
+    const int lo = max(c0, min_i), hi = min(c0 + 16, max_i);
+    if (aligned && lo == c0 && hi == c0 + 16) {
+      const uint4 c = *reinterpret_cast<const uint4 *>(layer + row + c0);
+      if ((c.x & c.y & c.z & c.w) == 0xFFFFFFFFu) continue;   // nothing known in this chunk
+      uint4 m = *reinterpret_cast<const uint4 *>(master + row + c0);
+      m.x = combine4(c.x, m.x, method); m.y = combine4(c.y, m.y, method); m.z = combine4(c.z, m.z, method); m.w = combine4(c.w, m.w, method);
+      *reinterpret_cast<uint4 *>(master + row + c0) = m;
+    } else {
+      for (int i = lo; i < hi; ++i) {
+        const uint8_t c = layer[row + i];
+        if (c == 255) continue;
+        if (method == 0) { master[row + i] = c; continue; }
+        const uint8_t old_cost = master[row + i];
+        if (old_cost == 255 || old_cost < c) master[row + i] = c;
+      }
+    }
   }
 }
 
@@ -111,11 +133,12 @@ cudaError_t launch_update_costs(const uint8_t * layer_dev, uint8_t * master_dev,
                                 int method, int sm_count, cudaStream_t s)
 {
   if (max_i <= min_i || max_j <= min_j) return cudaSuccess;
-  const unsigned long long total = (unsigned long long)(max_i - min_i) * (unsigned long long)(max_j - min_j);
-  unsigned long long blocks = (total + 256ull * 8 - 1) / (256ull * 8);
+  const unsigned chunks_per_row = (unsigned)((((max_i + 15) & ~15) - (min_i & ~15)) / 16);
+  const unsigned long long total = (unsigned long long)chunks_per_row * (unsigned long long)(max_j - min_j);
+  unsigned long long blocks = (total + 255) / 256;
   if (blocks < 1) blocks = 1;
-  if (blocks > (unsigned long long)sm_count * 8) blocks = (unsigned long long)sm_count * 8;
-  update_costs_kernel<<<(unsigned)blocks, 256, 0, s>>>(layer_dev, master_dev, size_x, min_i, min_j, max_i, max_j, method);
+  if (blocks > (unsigned long long)sm_count * 16) blocks = (unsigned long long)sm_count * 16;
+  update_costs_kernel<<<(unsigned)blocks, 256, 0, s>>>(layer_dev, master_dev, size_x, min_i, min_j, max_i, max_j, method, chunks_per_row);
   return cudaGetLastError();
 }
 

@@ -428,7 +428,8 @@ def test_mixed_api_soak(stvl, oracle, seed):
     gg.close()
 
 
-def test_update_costs_on_device(stvl, oracle):
+@pytest.mark.parametrize("sx,sy", [(317, 251), (320, 256)])     # odd row pitch: byte path; multiple of 16: 128-bit path
+def test_update_costs_on_device(stvl, oracle, sx, sy):
     """SURVEY §8f rank 3 — SpatioTemporalVoxelLayer::updateCosts on device byte grids (stvl_update_costs_device): footprint
     clearing (nav2 setConvexPolygonCost: Bresenham outline + column fill) and updateWithMax / updateWithOverwrite of a
     window into the master grid, against the literal CPU restatement.  Random convex polygons of every size and
@@ -436,7 +437,7 @@ def test_update_costs_on_device(stvl, oracle):
     import torch
     rng = np.random.default_rng(12)
     gg = stvl.SpatioTemporalVoxelGrid(0.05)
-    sx, sy, res, ox, oy = 317, 251, 0.05, -7.3, -4.1
+    res, ox, oy = 0.05, -7.3, -4.1
     params = stvl.CostmapParams(ox, oy, res, sx, sy, 0, 0, 254)
     n_filled = n_failed = 0
     for it in range(60):
