@@ -396,6 +396,15 @@ int launch_batches(stvl_grid * g, const std::vector<MarkBatch> & batches, CycleF
 {
   StageTimer timer__(g, STVL_TIME_MARK);
   bool pdl = fz && fz->pdl && !(g->timing_mask & STVL_TIME_MARK);
+  if (fz && fz->costmap && !fz->costmap_done && !batches.empty() && !g->alloc_dirty &&
+      (uint64_t)tiles_upper(g) > (uint64_t)mark_grid_for(batches.back(), g->sm_count) * 64u) {
+    // Mark's grid is too small to carry the costmap pass (small clouds, large map): the costmap kernel goes FIRST — it
+    // only needs the sweep — chained programmatically behind the leaf pass, and Mark behind it, so that Mark's cloud
+    // streaming overlaps it too (Mark's wait for this kernel implies the sweep: this kernel waited for it).
+    CU(launch_costmap(g->v, fz->cm, fz->costmap, tiles_upper(g), g->sm_count, g->stream, false, pdl));
+    fz->costmap_done = true;
+    g->launches += 1;
+  }
   for (size_t i = 0; i < batches.size(); ++i) {
     if (g->alloc_dirty) pdl = false;   // a fold kernel goes in between
     int rc = ensure_folded(g);   // (only a preceding bulk load leaves the allocator unfolded; Mark kernels fold themselves)

@@ -1230,6 +1230,10 @@ __global__ void __launch_bounds__(256) costmap_kernel(const GridView g, const Co
 {
   const unsigned lane = threadIdx.x & 31;
   TRACE(3, 0);
+  // (fused cycle with a small Mark grid: launched programmatically between the leaf pass and Mark — the column counts are
+  // ready when the sweep is, and Mark's cloud streaming overlaps this kernel as well; no-ops otherwise)
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t n_tiles = min(g.ctr->tile_n, g.tile_capacity);
   const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
   TRACE(3, 1);
@@ -1584,15 +1588,14 @@ cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, co
                    g, fp, frustums_dev, n_frustums, now, out, (uint32_t)n_dense_ctas);
 }
 cudaError_t launch_costmap(const GridView & g, const CostmapDev & p, uint8_t * costmap_dev, uint32_t tiles_upper_bound, int sm_count, cudaStream_t s,
-                           bool fill_default)
+                           bool fill_default, bool pdl)
 {
   if (fill_default) {
     const cudaError_t e = cudaMemsetAsync(costmap_dev, p.default_value, (size_t)p.size_x * p.size_y, s);   // Costmap2D::resetMaps, :705
     if (e != cudaSuccess) return e;
   }
   // 64 tiles per CTA (8 per warp): the per-CTA statistics reduction is amortised and the grid stays a fraction of a wave
-  costmap_kernel<<<grid_for(tiles_upper_bound, 64, sm_count * 4), 256, 0, s>>>(g, p, costmap_dev);
-  return cudaGetLastError();
+  return launch_ex(costmap_kernel, (unsigned)grid_for(tiles_upper_bound, 64, sm_count * 4), 256u, 0, s, pdl && !fill_default, g, p, costmap_dev);
 }
 cudaError_t launch_columns(const GridView & g, int32_t * ix, int32_t * iy, uint32_t * cnt, unsigned long long cap,
                            uint32_t tiles_upper_bound, int sm_count, cudaStream_t s)

@@ -47,7 +47,7 @@ cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, co
                          const SweepOutputs & out, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s,
                          uint8_t * costmap_reset = nullptr, size_t costmap_bytes = 0, int costmap_value = 0);
 cudaError_t launch_costmap(const GridView & g, const CostmapDev & p, uint8_t * costmap_dev, uint32_t tiles_upper_bound, int sm_count, cudaStream_t s,
-                           bool fill_default);
+                           bool fill_default, bool pdl = false);
 cudaError_t launch_columns(const GridView & g, int32_t * ix, int32_t * iy, uint32_t * cnt, unsigned long long cap,
                            uint32_t tiles_upper_bound, int sm_count, cudaStream_t s);
 cudaError_t launch_columns_to_dense(const GridView & g, int ix0, int iy0, uint32_t nx, uint32_t ny, uint32_t * dense,

@@ -359,6 +359,43 @@ def test_mark_large_scattered_clouds(stvl, oracle):
     gg.close()
 
 
+def test_fused_cycle_large_map_small_cloud(stvl, oracle):
+    """Config-5 shape at test size: far more voxel columns than a small cloud's Mark grid could take along, so the fused
+    cycle launches the costmap kernel between the leaf pass and Mark instead of carrying the pass on Mark."""
+    import torch
+    import spatio_temporal_voxel_layer_b200.synth as synth
+    rng = np.random.default_rng(5)
+    vox = np.unique(np.concatenate([rng.integers(-600, 600, (120000, 2)), rng.integers(2, 30, (120000, 1))], axis=1), axis=0)
+    gg = stvl.SpatioTemporalVoxelGrid(0.05, decay_model=0, voxel_decay=10.0)
+    og = oracle.OracleGrid(0.05, decay_model=0, voxel_decay=10.0)
+    gg.set_outputs(0)
+    t = 100.0 - rng.uniform(0, 12, len(vox))
+    gg.load_voxels(vox[:, 0], vox[:, 1], vox[:, 2], t); og.load_voxels(vox[:, 0], vox[:, 1], vox[:, 2], t)
+    size, res, ox, oy = 1280, 0.05, -32.0, -32.0
+    scene = synth.retail_scene(size=20.0, seed=2)
+    cm_dev = torch.zeros((size, size), dtype=torch.uint8, device="cuda")
+    keep = []
+    for cyc in range(3):
+        now = 100.5 + 1.5 * cyc
+        o, q = (0.5 * cyc, 0.3, 0.6), synth.optical_quat(0.4 * cyc)
+        r = rgbd_reading(stvl, synth, scene, o, q, seed=cyc, now=now, w=64, h=48)
+        tcl = torch.from_numpy(np.ascontiguousarray(r.cloud, np.float32)).cuda()
+        keep.append(tcl)
+        rd = stvl.MeasurementReading((tcl.data_ptr(), tcl.shape[0], 16, (0, 4, 8)), origin=r.origin, orientation=r.orientation,
+                                     obstacle_range=r.obstacle_range, now=now, filter=r.filter, min_obstacle_height=r.min_obstacle_height,
+                                     max_obstacle_height=r.max_obstacle_height)
+        gg.update_cycle_device(now, [r], [rd], ox, oy, res, size, size, cm_dev.data_ptr(), mark_threshold=1, default_value=255)
+        og.clear_frustums(now, oracle_frustums(oracle, [r]))
+        oracle_mark(oracle, og, r, now)
+        ocm, ob, on = og.update_ros_costmap(ox, oy, res, size, size, mark_threshold=1, default_value=255)
+        res_g = gg.costmap_result()
+        assert np.array_equal(cm_dev.cpu().numpy(), ocm), "costmap bytes differ in cycle %d" % cyc
+        assert res_g.n_marked_columns == on and on > 50000
+        assert_same_voxels(gg.voxels(), og.voxels())
+    assert gg.pool_stats().tiles_in_use > 20000
+    gg.close()
+
+
 @pytest.mark.parametrize("seed", [1, 2])
 def test_mixed_api_soak(stvl, oracle, seed):
     """30 cycles on ONE handle with a random mix of everything the boundary offers — fused device cycles, stage-by-stage
