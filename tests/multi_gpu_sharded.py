@@ -39,14 +39,16 @@ def main():
         t = now - rng.uniform(0, 20, len(vox))            # same stream of random numbers on every rank
         g.ResetGrid(); g.load_voxels(vox[:, 0], vox[:, 1], vox[:, 2], t)
         g.ClearFrustums([], now)
+        # cycle 2 (bytes mode, blocking) tracks unknown space: default value 255 where nothing is marked
+        pc = stvl.CostmapParams(ox, oy, res, size, size, 2, 255, 254) if cyc == 2 else params
         if rank == 0:
             ref.ResetGrid(); ref.load_voxels(vox[:, 0], vox[:, 1], vox[:, 2], t)
             ref.ClearFrustums([], now)
-            ref.costmap_device(params, cm_ref.data_ptr())
+            ref.costmap_device(pc, cm_ref.data_ptr())
             ref.synchronize()
             expected.append(cm_ref.clone())
         if cyc < 3:
-            g.costmap_sharded_device(params, cm.data_ptr(), root=0, count_bytes=(4, 1, 0)[cyc], pipelined=False)
+            g.costmap_sharded_device(pc, cm.data_ptr(), root=0, count_bytes=(4, 1, 0)[cyc], pipelined=False)
             g.synchronize()
             if rank == 0:
                 ok = ok and torch.equal(cm, expected[cyc]) and int((cm == 254).sum()) > 1000
