@@ -5,6 +5,7 @@
 // fails with STVL_ERR_NO_DEVICE / STVL_ERR_CUDA when that is impossible.
 #include <algorithm>
 #include <climits>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -62,6 +63,18 @@ struct DevBuf {
 };
 
 }  // namespace
+
+#ifdef STVL_TRACE
+// trace build only: wall-clock split of the host side of the fused call (printed by stvl_destroy)
+namespace { double g_host_us[4] = {0, 0, 0, 0}; unsigned long long g_host_calls = 0;
+inline double host_now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); } }
+#define HOST_T(var) const double var = host_now_us()
+#define HOST_ADD(i, a, b) (g_host_us[i] += (b) - (a))
+#else
+#define HOST_T(var) do {} while (0)
+#define HOST_ADD(i, a, b) do {} while (0)
+#endif
+
 
 struct stvl_grid {
   stvl_config_t cfg{};
@@ -415,7 +428,10 @@ int launch_batches(stvl_grid * g, const std::vector<MarkBatch> & batches, CycleF
     MarkBatch b = batches[i];
     b.cursor_sel = g->mark_cursor_sel;
     g->mark_cursor_sel ^= 1u;
+    HOST_T(tm0);
     CU(launch_mark(g->v, b, g->sm_count, g->stream, pdl, carry ? &fz->cm : nullptr, carry ? fz->costmap : nullptr));
+    HOST_T(tm1);
+    HOST_ADD(3, tm0, tm1);
     if (carry) fz->costmap_done = true;
     pdl = false;                       // only the first launch follows the sweep
     g->launches += 1;
@@ -853,6 +869,10 @@ int stvl_create(const stvl_config_t * cfg, stvl_grid_t ** out)
 
 int stvl_destroy(stvl_grid_t * g)
 {
+#ifdef STVL_TRACE
+  if (g_host_calls) std::fprintf(stderr, "[stvl trace] host side of %llu fused cycles: clear %.2f us (of which the two sweep launches %.2f), mark %.2f us (of which the Mark launch %.2f)\n",
+                                 g_host_calls, g_host_us[0] / g_host_calls, g_host_us[2] / g_host_calls, g_host_us[1] / g_host_calls, g_host_us[3] / g_host_calls);
+#endif
   if (!g) return STVL_OK;
   DeviceGuard guard(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
@@ -994,8 +1014,11 @@ int clear_frustums_impl(stvl_grid * g, double now, const stvl_frustum_t * frustu
   select_sweep_buffers(g, g->sweep_parity ^ 1);   // this sweep's tile buffer / counter set (re-armed by the previous sweep)
   StageTimer timer__(g, STVL_TIME_SWEEP);
   if (fz && fz->costmap) {
+    HOST_T(ts0);
     CU(launch_sweep(g->v, frustums_dev, &fparam, (int)n_frustums, now, out, slots_upper(g), g->sm_count, g->stream, fz->costmap,
                     (size_t)fz->cm.size_x * fz->cm.size_y, (int)fz->cm.default_value));
+    HOST_T(ts1);
+    HOST_ADD(2, ts0, ts1);
     fz->pdl = !(g->timing_mask & STVL_TIME_SWEEP);   // nothing may be enqueued between the leaf pass and Mark
   } else {
     CU(launch_sweep(g->v, frustums_dev, &fparam, (int)n_frustums, now, out, slots_upper(g), g->sm_count, g->stream));
@@ -1498,6 +1521,7 @@ namespace {
 int fused_cycle(stvl_grid * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums, const stvl_reading_t * readings,
                 uint32_t n_readings, const CostmapDev & cm, uint8_t * costmap_dev)
 {
+  HOST_T(t0);
   int rc = validate_readings(readings, n_readings);
   if (rc != STVL_OK) return rc;
   CycleFusion fz;
@@ -1505,10 +1529,16 @@ int fused_cycle(stvl_grid * g, double now, const stvl_frustum_t * frustums, uint
   fz.costmap = costmap_dev;
   rc = clear_frustums_impl(g, now, frustums, n_frustums, &fz);
   if (rc != STVL_OK) return rc;
+  HOST_T(t1);
   std::vector<const uint8_t *> dev_ptrs(n_readings, nullptr);
   for (uint32_t i = 0; i < n_readings; ++i) dev_ptrs[i] = static_cast<const uint8_t *>(readings[i].data);
   rc = run_mark(g, readings, n_readings, dev_ptrs, &fz);
   if (rc != STVL_OK) return rc;
+  HOST_T(t2);
+  HOST_ADD(0, t0, t1); HOST_ADD(1, t1, t2);
+#ifdef STVL_TRACE
+  ++g_host_calls;
+#endif
   if (!fz.costmap_done) {   // nothing to mark in this cycle: the plain costmap kernel (the bytes are reset already)
     StageTimer timer__(g, STVL_TIME_COSTMAP);
     CU(launch_costmap(g->v, fz.cm, costmap_dev, tiles_upper(g), g->sm_count, g->stream, false));
