@@ -192,7 +192,7 @@ def bench_ours(args):
     vs = float(np.float32(w.voxel_size))
     leaf_w = int(round(slab_pitch / (8 * vs)))      # slab width in leaves (200)
     grid_kw = dict(voxel_size=w.voxel_size, decay_model=w.decay_model, voxel_decay=w.voxel_decay, pub_voxels=False,
-                   device=local_rank, leaf_capacity=1 << 20)
+                   device=local_rank, leaf_capacity=1 << 22)
     if world > 1:   # spatial key-range shard: this rank keeps leaves with floor(bx / 200) mod N == rank
         grid_kw.update(shard_index=rank, shard_count=world, shard_width=leaf_w)
     g = stvl.SpatioTemporalVoxelGrid(**grid_kw)
