@@ -11,27 +11,21 @@
 namespace spatio_temporal_voxel_layer
 {
 
-/*****************************************************************************/
 SpatioTemporalVoxelLayer::SpatioTemporalVoxelLayer(void)
 : _publish_voxels(false), _mapping_mode(false), was_reset_(false), _voxel_size(0.05), _voxel_decay(-1.0),
   _combination_method(1), _mark_threshold(0), _decay_model(volume_grid::LINEAR), _update_footprint_enabled(true),
   _enabled(true), _fused_costmap(true), _last_map_save_time(0.0), _map_save_duration(60.0)
-/*****************************************************************************/
 {
 }
 
-/*****************************************************************************/
 SpatioTemporalVoxelLayer::~SpatioTemporalVoxelLayer(void)
-/*****************************************************************************/
 {
   _voxel_grid.reset();
 }
 
-/*****************************************************************************/
 void SpatioTemporalVoxelLayer::configure(
   const LayerParameters & params, rclcpp::Clock::SharedPtr clock, nav2_costmap_2d::LayeredCostmap * parent,
   const std::string & name)
-/*****************************************************************************/
 {
   _params = params;
   _clock = clock;
@@ -39,9 +33,7 @@ void SpatioTemporalVoxelLayer::configure(
   name_ = name;
 }
 
-/*****************************************************************************/
 void SpatioTemporalVoxelLayer::onInitialize(void)
-/*****************************************************************************/
 {
   // initializes the layer from its parameters
   _global_frame = layered_costmap_ ? layered_costmap_->getGlobalFrameID() : std::string("map");
@@ -95,202 +87,157 @@ void SpatioTemporalVoxelLayer::onInitialize(void)
   was_reset_ = false;
 }
 
-/*****************************************************************************/
 std::shared_ptr<buffer::MeasurementBuffer> SpatioTemporalVoxelLayer::GetBuffer(const std::string & source_name) const
-/*****************************************************************************/
 {
-  for (const auto & b : _observation_buffers) {
-    if (b->GetSourceName() == source_name) {return b;}
+  for (const auto & candidate : _observation_buffers) {
+    if (candidate->GetSourceName() == source_name) {return candidate;}
   }
   return nullptr;
 }
 
-/*****************************************************************************/
-bool SpatioTemporalVoxelLayer::GetMarkingObservations(
-  std::vector<observation::MeasurementReading> & marking_observations) const
-/*****************************************************************************/
+namespace
 {
-  // get marking observations and static marked areas
-  bool current = true;
-  for (unsigned int i = 0; i != _marking_buffers.size(); ++i) {
-    _marking_buffers[i]->Lock();
-    if (_marking_buffers[i]->IsEnabled()) {
-      _marking_buffers[i]->GetReadings(marking_observations);
-    }
-    current = current && _marking_buffers[i]->UpdatedAtExpectedRate();
-    _marking_buffers[i]->Unlock();
+// RAII for MeasurementBuffer::Lock / Unlock (upstream brackets every buffer access by hand)
+struct ScopedBufferLock
+{
+  explicit ScopedBufferLock(buffer::MeasurementBuffer & b) : _b(b) {_b.Lock();}
+  ~ScopedBufferLock() {_b.Unlock();}
+  buffer::MeasurementBuffer & _b;
+};
+
+// readings of every enabled buffer of `group`, appended to `out`; false if any buffer is behind its expected rate
+// (the body the reference repeats for the marking and the clearing buffers, :466-513)
+bool collectReadings(
+  const std::vector<std::shared_ptr<buffer::MeasurementBuffer>> & group, std::vector<observation::MeasurementReading> & out)
+{
+  bool all_current = true;
+  for (const auto & source : group) {
+    ScopedBufferLock guard(*source);
+    if (source->IsEnabled()) {source->GetReadings(out);}
+    if (!source->UpdatedAtExpectedRate()) {all_current = false;}
   }
-  marking_observations.insert(marking_observations.end(), _static_observations.begin(), _static_observations.end());
-  return current;
+  return all_current;
 }
 
-/*****************************************************************************/
-bool SpatioTemporalVoxelLayer::GetClearingObservations(
-  std::vector<observation::MeasurementReading> & clearing_observations) const
-/*****************************************************************************/
+// "clear_after_reading" sources forget their readings once a cycle has consumed them (:516-526)
+void dropConsumedReadings(const std::vector<std::shared_ptr<buffer::MeasurementBuffer>> & group)
 {
-  // get clearing observations
-  bool current = true;
-  for (unsigned int i = 0; i != _clearing_buffers.size(); ++i) {
-    _clearing_buffers[i]->Lock();
-    if (_clearing_buffers[i]->IsEnabled()) {
-      _clearing_buffers[i]->GetReadings(clearing_observations);
-    }
-    current = current && _clearing_buffers[i]->UpdatedAtExpectedRate();
-    _clearing_buffers[i]->Unlock();
+  for (const auto & source : group) {
+    ScopedBufferLock guard(*source);
+    if (source->ClearAfterReading()) {source->ResetAllMeasurements();}
   }
-  return current;
+}
+}  // namespace
+
+bool SpatioTemporalVoxelLayer::GetMarkingObservations(std::vector<observation::MeasurementReading> & marking_observations) const
+{
+  const bool all_current = collectReadings(_marking_buffers, marking_observations);
+  // statically added observations are marked every cycle on top of the sensor readings
+  for (const auto & fixed : _static_observations) {marking_observations.push_back(fixed);}
+  return all_current;
 }
 
-/*****************************************************************************/
+bool SpatioTemporalVoxelLayer::GetClearingObservations(std::vector<observation::MeasurementReading> & clearing_observations) const
+{
+  return collectReadings(_clearing_buffers, clearing_observations);
+}
+
 void SpatioTemporalVoxelLayer::ObservationsResetAfterReading() const
-/*****************************************************************************/
 {
-  for (unsigned int i = 0; i != _clearing_buffers.size(); ++i) {
-    _clearing_buffers[i]->Lock();
-    if (_clearing_buffers[i]->ClearAfterReading()) {
-      _clearing_buffers[i]->ResetAllMeasurements();
-    }
-    _clearing_buffers[i]->Unlock();
-  }
-  for (unsigned int i = 0; i != _marking_buffers.size(); ++i) {
-    _marking_buffers[i]->Lock();
-    if (_marking_buffers[i]->ClearAfterReading()) {
-      _marking_buffers[i]->ResetAllMeasurements();
-    }
-    _marking_buffers[i]->Unlock();
-  }
+  dropConsumedReadings(_clearing_buffers);
+  dropConsumedReadings(_marking_buffers);
 }
 
-/*****************************************************************************/
 bool SpatioTemporalVoxelLayer::updateFootprint(
   double robot_x, double robot_y, double robot_yaw, double * min_x, double * min_y, double * max_x, double * max_y)
-/*****************************************************************************/
 {
-  // updates layer costmap to include footprint for clearing in voxel grid
-  if (!_update_footprint_enabled) {
-    return false;
-  }
-  // nav2_costmap_2d::transformFootprint
-  const double cos_th = std::cos(robot_yaw), sin_th = std::sin(robot_yaw);
-  _transformed_footprint.clear();
-  for (const auto & p : _footprint) {
-    geometry_msgs::msg::Point q;
-    q.x = robot_x + (p.x * cos_th - p.y * sin_th);
-    q.y = robot_y + (p.x * sin_th + p.y * cos_th);
-    _transformed_footprint.push_back(q);
-  }
-  for (unsigned int i = 0; i < _transformed_footprint.size(); i++) {
-    touch(_transformed_footprint[i].x, _transformed_footprint[i].y, min_x, min_y, max_x, max_y);
+  if (!_update_footprint_enabled) {return false;}
+  // nav2_costmap_2d::transformFootprint: rotate the footprint by the robot's yaw, move it to the robot; every vertex
+  // extends the update bounds (:529-548)
+  const double c = std::cos(robot_yaw), s = std::sin(robot_yaw);
+  _transformed_footprint.resize(_footprint.size());
+  for (size_t k = 0; k < _footprint.size(); ++k) {
+    geometry_msgs::msg::Point & v = _transformed_footprint[k];
+    v.x = robot_x + (_footprint[k].x * c - _footprint[k].y * s);
+    v.y = robot_y + (_footprint[k].x * s + _footprint[k].y * c);
+    v.z = 0.0;
+    touch(v.x, v.y, min_x, min_y, max_x, max_y);
   }
   return true;
 }
 
-/*****************************************************************************/
 void SpatioTemporalVoxelLayer::reset(void)
-/*****************************************************************************/
 {
+  // layer reset (:590-606): default costs, empty grid, "not current" until the next updateCosts, fresh rate timers
   std::lock_guard<std::recursive_mutex> lock(_voxel_grid_lock);
-  // reset layer
   Costmap2D::resetMaps();
-  this->ResetGrid();
+  ResetGrid();
   current_ = false;
   was_reset_ = true;
-  for (auto & b : _observation_buffers) {
-    b->ResetLastUpdatedTime();
-  }
+  for (const auto & source : _observation_buffers) {source->ResetLastUpdatedTime();}
 }
 
-/*****************************************************************************/
 bool SpatioTemporalVoxelLayer::AddStaticObservations(const observation::MeasurementReading & obs)
-/*****************************************************************************/
 {
-  // observations to always be added to the map each update cycle not marked
   try {
     _static_observations.push_back(obs);
-    return true;
   } catch (...) {
     return false;
   }
+  return true;
 }
 
-/*****************************************************************************/
 bool SpatioTemporalVoxelLayer::RemoveStaticObservations(void)
-/*****************************************************************************/
 {
   _static_observations.clear();
   return true;
 }
 
-/*****************************************************************************/
 void SpatioTemporalVoxelLayer::ResetGrid(void)
-/*****************************************************************************/
 {
-  if (!_voxel_grid->ResetGrid()) {
-    std::cout << "Did not clear level set in " << getName() << "!" << std::endl;
-  }
+  if (_voxel_grid->ResetGrid()) {return;}
+  std::cout << "Did not clear level set in " << getName() << "!" << std::endl;
 }
 
-/*****************************************************************************/
 bool SpatioTemporalVoxelLayer::SaveGrid(const std::string & file_name, double & map_size_bytes)
-/*****************************************************************************/
 {
   std::lock_guard<std::recursive_mutex> lock(_voxel_grid_lock);
   return _voxel_grid->SaveGrid(file_name, map_size_bytes);
 }
 
-/*****************************************************************************/
 void SpatioTemporalVoxelLayer::matchSize(void)
-/*****************************************************************************/
 {
-  // match the master costmap size, volume_grid maintains full w/ expiration.
+  // only the 2-D layer follows the master's size; the voxel grid is unbounded and expires by itself
   CostmapLayer::matchSize();
 }
 
-/*****************************************************************************/
 void SpatioTemporalVoxelLayer::setFusedCostmap(bool on)
-/*****************************************************************************/
 {
   _fused_costmap = on;
-  if (_voxel_grid) {
-    _voxel_grid->SetExactClearedCells(!on);
-  }
+  if (_voxel_grid) {_voxel_grid->SetExactClearedCells(!on);}
 }
 
-/*****************************************************************************/
 void SpatioTemporalVoxelLayer::updateCosts(
   nav2_costmap_2d::Costmap2D & master_grid, int min_i, int min_j, int max_i, int max_j)
-/*****************************************************************************/
 {
-  // update costs in master_grid with costmap_
-  if (!_enabled) {
-    return;
-  }
-  // if not current due to reset, set current now after clearing
-  if (!current_ && was_reset_) {
-    was_reset_ = false;
+  if (!_enabled) {return;}
+  // a reset leaves the layer "not current" until its first merge into the master (:676-679)
+  if (was_reset_ && !current_) {
     current_ = true;
+    was_reset_ = false;
   }
-  if (_update_footprint_enabled) {
-    setConvexPolygonCost(_transformed_footprint, nav2_costmap_2d::FREE_SPACE);
-  }
-  switch (_combination_method) {
-    case 0:
-      updateWithOverwrite(master_grid, min_i, min_j, max_i, max_j);
-      break;
-    case 1:
-      updateWithMax(master_grid, min_i, min_j, max_i, max_j);
-      break;
-    default:
-      break;
+  // the robot cannot be an obstacle to itself (:682-684)
+  if (_update_footprint_enabled) {setConvexPolygonCost(_transformed_footprint, nav2_costmap_2d::FREE_SPACE);}
+  if (_combination_method == 0) {
+    updateWithOverwrite(master_grid, min_i, min_j, max_i, max_j);
+  } else if (_combination_method == 1) {
+    updateWithMax(master_grid, min_i, min_j, max_i, max_j);
   }
 }
 
-/*****************************************************************************/
 void SpatioTemporalVoxelLayer::UpdateROSCostmap(
   double * min_x, double * min_y, double * max_x, double * max_y,
   std::unordered_set<volume_grid::occupany_cell> & cleared_cells)
-/*****************************************************************************/
 {
   if (_fused_costmap) {
     // resetMaps + threshold + worldToMap + LETHAL write + touch, all on the device; the bytes land in costmap_
@@ -314,32 +261,38 @@ void SpatioTemporalVoxelLayer::UpdateROSCostmap(
     return;
   }
 
-  // the reference's literal host loops (:705-724)
+  // host path, semantically the reference's loops (:705-724): default costs everywhere, LETHAL where a voxel column holds
+  // at least mark_threshold voxels and lies on the map, bounds extended by every such column and every cleared cell
   Costmap2D::resetMaps();
-  std::unordered_map<volume_grid::occupany_cell, uint>::iterator it;
-  for (it = _voxel_grid->GetFlattenedCostmap()->begin(); it != _voxel_grid->GetFlattenedCostmap()->end(); ++it) {
-    uint map_x, map_y;
-    if (static_cast<int>(it->second) >= _mark_threshold && worldToMap(it->first.x, it->first.y, map_x, map_y)) {
-      costmap_[getIndex(map_x, map_y)] = nav2_costmap_2d::LETHAL_OBSTACLE;
-      touch(it->first.x, it->first.y, min_x, min_y, max_x, max_y);
-    }
+  for (const auto & column : *_voxel_grid->GetFlattenedCostmap()) {
+    if (static_cast<int>(column.second) < _mark_threshold) {continue;}
+    unsigned int mx = 0, my = 0;
+    if (!worldToMap(column.first.x, column.first.y, mx, my)) {continue;}
+    costmap_[getIndex(mx, my)] = nav2_costmap_2d::LETHAL_OBSTACLE;
+    touch(column.first.x, column.first.y, min_x, min_y, max_x, max_y);
   }
-  std::unordered_set<volume_grid::occupany_cell>::iterator cell;
-  for (cell = cleared_cells.begin(); cell != cleared_cells.end(); ++cell) {
-    touch(cell->x, cell->y, min_x, min_y, max_x, max_y);
-  }
+  for (const auto & freed : cleared_cells) {touch(freed.x, freed.y, min_x, min_y, max_x, max_y);}
 }
 
-/*****************************************************************************/
+namespace
+{
+// "%F-%r" of the wall clock: the file name upstream gives its periodic map dumps (:778-786)
+std::string wallClockStamp()
+{
+  const time_t t = time(nullptr);
+  struct tm parts;
+  localtime_r(&t, &parts);
+  char text[100];
+  strftime(text, sizeof(text), "%F-%r", &parts);
+  return text;
+}
+}  // namespace
+
 void SpatioTemporalVoxelLayer::updateBounds(
   double robot_x, double robot_y, double robot_yaw, double * min_x, double * min_y, double * max_x, double * max_y)
-/*****************************************************************************/
 {
-  // grabs new max bounds for the costmap
-  if (!_enabled) {
-    return;
-  }
-  // costmap mutex first, then the grid lock (clearArea dead-lock note, reference :736-742)
+  if (!_enabled) {return;}
+  // lock order as upstream (:736-742): the costmap's mutex, then the grid's (clearArea takes them the same way round)
   std::unique_lock<Costmap2D::mutex_t> cm_lock(*getMutex());
   std::lock_guard<std::recursive_mutex> lock(_voxel_grid_lock);
 
@@ -348,64 +301,46 @@ void SpatioTemporalVoxelLayer::updateBounds(
   }
   useExtraBounds(min_x, min_y, max_x, max_y);
 
-  bool current = true;
+  // this cycle's readings; the layer is "current" only if every source delivers at its expected rate
   std::vector<observation::MeasurementReading> marking_observations, clearing_observations;
-  current = GetMarkingObservations(marking_observations) && current;
-  current = GetClearingObservations(clearing_observations) && current;
+  const bool marking_current = GetMarkingObservations(marking_observations);
+  const bool clearing_current = GetClearingObservations(clearing_observations);
   ObservationsResetAfterReading();
-  current_ = current;
+  current_ = marking_current && clearing_current;
 
   std::unordered_set<volume_grid::occupany_cell> cleared_cells;
-
-  // navigation mode: clear observations, mapping mode: save maps and publish
-  bool should_save = false;
   if (_mapping_mode) {
-    should_save = _clock->now().seconds() - _last_map_save_time > _map_save_duration;
+    // mapping mode never clears; it dumps the grid every map_save_duration seconds instead (:764-786)
+    const double t = _clock->now().seconds();
+    if (t - _last_map_save_time > _map_save_duration) {
+      _last_map_save_time = t;
+      double bytes = 0.;
+      _voxel_grid->SaveGrid(wallClockStamp(), bytes);
+    }
+  } else {
+    _voxel_grid->ClearFrustums(clearing_observations, cleared_cells);   // decay + frustum acceleration (:773)
   }
-  if (!_mapping_mode) {
-    _voxel_grid->ClearFrustums(clearing_observations, cleared_cells);
-  } else if (should_save) {
-    _last_map_save_time = _clock->now().seconds();
-    time_t rawtime;
-    struct tm timeinfo;
-    char time_buffer[100];
-    time(&rawtime);
-    localtime_r(&rawtime, &timeinfo);
-    strftime(time_buffer, 100, "%F-%r", &timeinfo);
-    double bytes = 0.;
-    _voxel_grid->SaveGrid(time_buffer, bytes);
-  }
+  _voxel_grid->Mark(marking_observations);                              // (:792)
+  UpdateROSCostmap(min_x, min_y, max_x, max_y, cleared_cells);          // (:795)
 
-  // mark observations
-  _voxel_grid->Mark(marking_observations);
-
-  // update the ROS Layered Costmap
-  UpdateROSCostmap(min_x, min_y, max_x, max_y, cleared_cells);
-
-  // publish point cloud in navigation mode
   if (_publish_voxels && !_mapping_mode) {
-    std::unique_ptr<sensor_msgs::msg::PointCloud2> pc2 = std::make_unique<sensor_msgs::msg::PointCloud2>();
-    _voxel_grid->GetOccupancyPointCloud(pc2);
-    pc2->header.frame_id = _global_frame;
-    _last_voxel_cloud = std::move(pc2);
+    // navigation mode publishes the occupancy cloud on "voxel_grid" (:798-805); kept for the caller here
+    auto cloud = std::make_unique<sensor_msgs::msg::PointCloud2>();
+    _voxel_grid->GetOccupancyPointCloud(cloud);
+    cloud->header.frame_id = _global_frame;
+    _last_voxel_cloud = std::move(cloud);
   }
-
-  // update footprint
-  updateFootprint(robot_x, robot_y, robot_yaw, min_x, min_y, max_x, max_y);
+  updateFootprint(robot_x, robot_y, robot_yaw, min_x, min_y, max_x, max_y);   // (:808)
 }
 
-/*****************************************************************************/
 void SpatioTemporalVoxelLayer::clearArea(int start_x, int start_y, int end_x, int end_y, bool invert_area)
-/*****************************************************************************/
 {
-  // convert map coords to world coords
-  volume_grid::occupany_cell start_world(0, 0);
-  volume_grid::occupany_cell end_world(0, 0);
-  mapToWorld(start_x, start_y, start_world.x, start_world.y);
-  mapToWorld(end_x, end_y, end_world.x, end_world.y);
-
+  // the rectangle in world coordinates for the voxel grid, in cells for the 2-D layer (:950-963)
+  volume_grid::occupany_cell from(0, 0), to(0, 0);
+  mapToWorld(start_x, start_y, from.x, from.y);
+  mapToWorld(end_x, end_y, to.x, to.y);
   std::lock_guard<std::recursive_mutex> lock(_voxel_grid_lock);
-  _voxel_grid->ResetGridArea(start_world, end_world, invert_area);
+  _voxel_grid->ResetGridArea(from, to, invert_area);
   CostmapLayer::clearArea(start_x, start_y, end_x, end_y, invert_area);
 }
 
