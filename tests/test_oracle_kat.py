@@ -242,3 +242,53 @@ def test_update_costs_known_answers(oracle):
     m = master.copy()
     oracle.update_costs(layer, m, 1, 0, 3, 1, 0)      # window [1,3) x [0,1)
     assert m.tolist() == [[255, 100, 7, 10], [253, 1, 255, 60]]
+
+
+def test_polygon_fill_equals_column_extent_of_the_outline(oracle):
+    """The device kernel fills every column between the lowest and the highest Bresenham outline cell instead of
+    sorting the outline and scanning it like nav2's convexFillCells.  An independent numpy model of that rule must agree
+    with the literal restatement in the oracle on random convex polygons (both windings, slivers, single-cell ones)."""
+    rng = np.random.default_rng(3)
+
+    def outline(x0, y0, x1, y1):
+        dx, dy = x1 - x0, y1 - y0
+        adx, ady = abs(dx), abs(dy)
+        sx, sy = (1 if dx > 0 else -1), (1 if dy > 0 else -1)
+        cells, x, y = [], x0, y0
+        if adx >= ady:
+            err = adx // 2
+            for _ in range(adx):
+                cells.append((x, y)); x += sx; err += ady
+                if err >= adx:
+                    y += sy; err -= adx
+        else:
+            err = ady // 2
+            for _ in range(ady):
+                cells.append((x, y)); y += sy; err += adx
+                if err >= ady:
+                    x += sx; err -= ady
+        cells.append((x, y))
+        return cells
+
+    sx_, sy_, res, ox, oy = 97, 83, 0.1, -2.0, -3.0
+    for it in range(200):
+        nv = int(rng.integers(3, 10))
+        ang = np.sort(rng.uniform(0, 2 * np.pi, nv))
+        if it % 3 == 0:
+            ang = ang[::-1]
+        a, b = rng.uniform(0.02, 3.5, 2)
+        th = rng.uniform(0, np.pi)
+        cx, cy = rng.uniform(ox + 3.6, ox + sx_ * res - 3.6), rng.uniform(oy + 3.6, oy + sy_ * res - 3.6)
+        px, py = a * np.cos(ang), b * np.sin(ang)
+        poly = np.stack([cx + px * np.cos(th) - py * np.sin(th), cy + px * np.sin(th) + py * np.cos(th)], 1)
+        got = np.full((sy_, sx_), 200, np.uint8)
+        assert oracle.set_convex_polygon_cost(got, ox, oy, res, poly, 0)
+        m = [(int((x - ox) / res), int((y - oy) / res)) for x, y in poly]
+        lo, hi = {}, {}
+        for k in range(nv):
+            for (x, y) in outline(*m[k], *m[(k + 1) % nv]):
+                lo[x] = min(lo.get(x, y), y); hi[x] = max(hi.get(x, y), y)
+        want = np.full((sy_, sx_), 200, np.uint8)
+        for x in lo:
+            want[lo[x]:hi[x] + 1, x] = 0
+        assert np.array_equal(got, want), it
