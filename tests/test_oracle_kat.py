@@ -292,3 +292,37 @@ def test_polygon_fill_equals_column_extent_of_the_outline(oracle):
         for x in lo:
             want[lo[x]:hi[x] + 1, x] = 0
         assert np.array_equal(got, want), it
+
+
+def test_cloud_transform_against_numpy_float32(oracle):
+    """tf2::doTransform restatement: quaternion -> float matrix as Eigen's toRotationMatrix, then
+    ((m0*x + m1*y) + m2*z) + t per row with every operation rounded to float32 — checked against numpy float32 scalars
+    evaluated in that order, and against the double-precision rotation within float accuracy."""
+    rng = np.random.default_rng(21)
+    f = np.float32
+    for _ in range(20):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        t = rng.uniform(-30, 30, 3)
+        m = oracle.transform_from_quat(t, q)
+        x, y, z, w = (f(v) for v in q)
+        tx, ty, tz = f(2) * x, f(2) * y, f(2) * z
+        twx, twy, twz = tx * w, ty * w, tz * w
+        txx, txy, txz, tyy, tyz, tzz = tx * x, ty * x, tz * x, ty * y, tz * y, tz * z
+        want = np.array([[f(1) - (tyy + tzz), txy - twz, txz + twy, f(t[0])],
+                         [txy + twz, f(1) - (txx + tzz), tyz - twx, f(t[1])],
+                         [txz - twy, tyz + twx, f(1) - (txx + tyy), f(t[2])]], np.float32)
+        assert np.array_equal(m.reshape(3, 4).view(np.uint32), want.view(np.uint32))
+        pts = np.zeros((500, 4), np.float32)
+        pts[:, :3] = rng.uniform(-8, 8, (500, 3))
+        out = oracle.transform_cloud(pts, m)
+        for i in range(0, 500, 37):
+            px, py, pz = pts[i, :3]
+            for r in range(3):
+                ref = ((want[r, 0] * px + want[r, 1] * py) + want[r, 2] * pz) + want[r, 3]
+                assert out[i, r].view(np.uint32) == np.float32(ref).view(np.uint32)
+        # sanity against the exact rotation
+        xq, yq, zq, wq = q
+        R = np.array([[1 - 2 * (yq * yq + zq * zq), 2 * (xq * yq - zq * wq), 2 * (xq * zq + yq * wq)],
+                      [2 * (xq * yq + zq * wq), 1 - 2 * (xq * xq + zq * zq), 2 * (yq * zq - xq * wq)],
+                      [2 * (xq * zq - yq * wq), 2 * (yq * zq + xq * wq), 1 - 2 * (xq * xq + yq * yq)]])
+        assert np.abs(out[:, :3] - (pts[:, :3].astype(np.float64) @ R.T + t)).max() < 2e-4
