@@ -50,8 +50,47 @@ class ModelGrid:
                 return False
         return True
 
+    @staticmethod
+    def lidar_model(vfov, vpad, hfov, min_d, max_d, position, quat_xyzw):
+        """ThreeDimensionalLidarFrustum (LIDAR = .../frustum_models/three_dimensional_lidar_frustum.cpp:44-116) as a
+        predicate, built from the raw parameters — nothing of the oracle's frustum block is used."""
+        h_half, tan2 = hfov / 2.0, math.tan(vfov / 2.0) * math.tan(vfov / 2.0)
+        min2, max2, full = min_d * min_d, max_d * max_d, hfov > 6.27
+        qx, qy, qz, qw = -quat_xyzw[0], -quat_xyzw[1], -quat_xyzw[2], quat_xyzw[3]      # conjugate (LIDAR:72)
+        px, py, pz = position
+
+        def cross(a, b):
+            return (a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0])
+
+        def inside(x, y, z):
+            v = (x - px, y - py, z - pz)
+            uv = cross((qx, qy, qz), v)                  # Eigen: uv = 2 * (q.vec x v); v + w * uv + q.vec x uv
+            uv = (uv[0] + uv[0], uv[1] + uv[1], uv[2] + uv[2])
+            c2 = cross((qx, qy, qz), uv)
+            t = tuple((v[i] + qw * uv[i]) + c2[i] for i in range(3))
+            r2 = (t[0] * t[0]) + (t[1] * t[1])
+            if r2 > max2 or r2 < min2:
+                return False
+            vp = math.fabs(t[2]) + vpad
+            if r2 == 0.0:
+                if vp * vp > 0.0:                        # x / 0 = +inf > tan^2
+                    return False
+            elif (vp * vp / r2) > tan2:
+                return False
+            if not full:
+                half_pi = math.pi / 2
+                if t[0] > 0:
+                    if math.fabs(math.atan(t[1] / t[0])) > h_half:
+                        return False
+                else:
+                    ratio = (t[0] / t[1]) if t[1] != 0.0 else (math.copysign(math.inf, t[0]) if t[0] != 0.0 else math.nan)
+                    if math.fabs(math.atan(ratio)) + half_pi > h_half:
+                        return False
+            return True
+        return inside
+
     def clear_frustums(self, now, frustums):
-        # GRID:96-224; frustums: list of (36 plane doubles, accel_factor), in reading order
+        # GRID:96-224; frustums: list of (36 plane doubles OR a predicate, accel_factor), in reading order
         self.columns, self.cleared = {}, set()
         if not self.vox:
             return
@@ -67,7 +106,7 @@ class ModelGrid:
             cx, cy, cz = self.centre(key[0]), self.centre(key[1]), self.centre(key[2])
             gone = False
             for planes, factor in frustums:
-                if self.inside_depth(planes, cx, cy, cz):
+                if (planes(cx, cy, cz) if callable(planes) else self.inside_depth(planes, cx, cy, cz)):
                     accel = ((1. / 6.) * factor) * ((t * t) * t)     # GRID:334-341
                     if base - accel < 0.:
                         gone = True
@@ -141,3 +180,38 @@ def test_python_model_agrees_with_the_oracle(oracle):
         assert len(mg.vox) > 150
         if decay_model != 2:
             assert n_cleared_total > 0      # something actually expired / was accelerated away
+
+
+def test_python_model_agrees_with_the_oracle_lidar(oracle):
+    """The same with 3-D lidar frustums (hourglass model, full circle and a 2 rad wedge that goes through atan) next to a
+    depth camera, exponential decay: the lidar predicate is modelled from the raw sensor parameters."""
+    from spatio_temporal_voxel_layer_b200 import synth
+    p, v = synth.RGBD, synth.VLP16
+    scene = synth.retail_scene(size=12.0, seed=22)
+    og = oracle.OracleGrid(0.05, 0.0, 1, 0.9, False)
+    mg = ModelGrid(0.05, 1, 0.9)
+    n_cleared_total = 0
+    for cyc in range(5):
+        now = 80.0 + 0.5 * cyc
+        lo, lq = (-1.0 + 0.5 * cyc, 0.7, 0.9), synth.yaw_quat(0.7 * cyc)
+        co, cq = (-1.0 + 0.5 * cyc, 0.7, 0.6), synth.optical_quat(0.3 - 0.5 * cyc)
+        hfov = 6.29 if cyc % 2 == 0 else 2.0
+        lidar_cloud = synth.lidar_cloud(scene, lo, lq, rings=8, azimuths=180, seed=cyc)
+        depth = synth.depth_cloud(scene, co, cq, width=48, height=36, seed=30 + cyc)
+        lb = oracle.lidar_frustum(v["vfov"], v["vpad"], hfov, v["min_z"], v["max_z"], lo, lq, v["accel"])
+        db = oracle.depth_frustum(p["vfov"], p["hfov"], p["min_z"], p["max_z"], co, cq, p["accel"])
+        og.clear_frustums(now, np.concatenate([lb, db]))
+        mg.clear_frustums(now, [(ModelGrid.lidar_model(v["vfov"], v["vpad"], hfov, v["min_z"], v["max_z"], lo, lq), v["accel"]),
+                                (db["p"][0].tolist(), float(db["accel_factor"][0]))])
+        n_cleared_total += len(mg.cleared)
+        for k, (o, cloud, lim) in enumerate(((lo, lidar_cloud, v), (co, depth, p))):
+            pts = oracle.filter_passthrough(cloud, lim["min_obstacle_height"], lim["max_obstacle_height"])
+            og.mark(pts, o, lim["obstacle_range"], now + 1e-3 * k)
+            mg.mark(pts, o, lim["obstacle_range"], now + 1e-3 * k)
+        ix, iy, iz, t = og.voxels()
+        got = {(int(a), int(b), int(c)): float(tv) for a, b, c, tv in zip(ix, iy, iz, t)}
+        assert got.keys() == mg.vox.keys(), "cycle %d: key sets differ" % cyc
+        assert all(np.float64(got[k]).view(np.uint64) == np.float64(mg.vox[k]).view(np.uint64) for k in got)
+        x, y, c = og.costmap()
+        assert {(float(a), float(b)): int(n) for a, b, n in zip(x, y, c)} == mg.columns
+    assert len(mg.vox) > 150 and n_cleared_total > 0
