@@ -6,18 +6,25 @@
 
 A step is one full update cycle in the reference's order (spatio_temporal_voxel_layer.cpp:772-795):
 ClearFrustums(7 frustums) -> Mark(7 x 640x480 clouds) -> costmap bytes.  Workload at N=1 = BASELINE config 2.
-  value : cycles/s with the clouds already resident in HBM (CUDA events on the library's stream)
-  e2e   : cycles/s through the C-ABI with HOST buffers: pinned clouds copied H2D and the costmap bytes copied D2H
-          inside every step (wall clock, synchronised on both sides)
+
+The workload is NOT stationary (a 15 s linear decay empties a 710,765-voxel store that seven cameras on one robot cannot
+re-mark), so every leg runs in EPISODES: the store is reset and re-seeded to the 710,765 voxels, one untimed settle
+cycle runs, then EPISODE_CYCLES timed cycles at dt = 0.2 s — the store stays within 13 % of the seed in every
+timed cycle of every leg.  Both arms (--impl ours / reference) build the same workloads.Config2 object and run the same
+episodes, and the fused path's final state of an episode is compared bit for bit with the oracle's (`parity_checked`).
+
+  value : cycles/s with the clouds already resident in HBM (CUDA events on the library's stream around each episode's
+          timed cycles; the re-seed between episodes is not part of the path and is not timed)
+  e2e   : cycles/s through the C-ABI with HOST buffers: pinned clouds copied H2D and the costmap bytes copied D2H inside
+          every step (wall clock, synchronised on both sides of every episode)
   roofline : the dominant kernel's ALGORITHMIC bytes / its CUDA-event duration vs the measured HBM peak
-  cpu_baseline : the oracle (a port, 1 thread like the reference) on a bounded sample of the same cycles
+  cpu_baseline : the oracle (a port, 1 thread like the reference) on a bounded sample of the same episodes
 N > 1 (torchrun): weak scaling — every rank owns one config-2 slab of an N-times larger store (spatial key-range
-shards); per cycle the per-(x,y) column counts are merged with an NCCL reduce to rank 0, which writes the bytes.
+shards); per cycle the per-shard costmap cells are merged into rank 0's costmap inside the library.
 """
 import argparse
 import ctypes as C
 import json
-import math
 import os
 import statistics
 import subprocess
@@ -33,6 +40,9 @@ if ROOT not in sys.path:
 
 METRIC = "mark+clear+costmap cycles/s (7x640x480 RGBD, 0.05 m)"
 UNIT = "cycles/s"
+DT_HEADLINE = 0.2          # s between update cycles (the reference example runs its global costmap at 1 Hz)
+EPISODE_CYCLES = 10        # timed cycles per episode (2 s of simulated time: the store decays from 710,765 to ~620 k)
+SLAB_PITCH = 80.0          # m, x extent of one rank's slab at N > 1
 
 
 def measured_peak_gbs():
@@ -89,41 +99,93 @@ class ClockSampler:
             for n, v in zip(names, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        # the median over the samples taken under load (the sampler also sees the idle gaps of the re-seeds)
+        hot = [v for v in sm if v >= 0.9 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(hot) if hot else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------------
-def oracle_frustums(O, p, poses):
-    return np.concatenate([O.depth_frustum(p["vfov"], p["hfov"], p["min_z"], p["max_z"], o, q, p["accel"]) for o, q in poses])
+# the workload both arms share
+# ------------------------------------------------------------------------------------------------
+def make_workload(rank, world):
+    """Rank r's config-2 slab.  N=1: the store is centred on the origin (negative and positive coordinates);
+    N>1: slab r spans x in [80 r, 80 r + 80)."""
+    from spatio_temporal_voxel_layer_b200 import workloads
+    origin = (0.0, 0.0) if world == 1 else (SLAB_PITCH * rank + SLAB_PITCH / 2, 0.0)
+    return workloads.Config2(n_poses=4, ring=8, slab_origin=origin, seed=1002 + rank, dt=DT_HEADLINE)
 
 
-def run_oracle_cycles(w, n_warm, n_steps, threshold_params):
-    """The CPU restatement on the same cycles.  The PassThrough pre-filter runs upstream of the cycle in the reference
-    (MeasurementBuffer, another thread), so it is applied before the clock starts; the GPU path fuses it into Mark."""
-    from oracle import oracle_py as O
-    p = w.p
-    og = O.OracleGrid(w.voxel_size, 0.0, w.decay_model, w.voxel_decay, False)
-    og.load_voxels(*w.seed_vox, w.seed_t)
-    filtered = {}
-    times = []
-    cm = None
-    for step in range(n_warm + n_steps):
-        now, poses, clouds = w.cycle(step)
-        key = step % len(w.cycles)
-        if key not in filtered:
-            filtered[key] = [np.ascontiguousarray(O.filter_passthrough(c, p["min_obstacle_height"], p["max_obstacle_height"])) for c in clouds]
-        t0 = time.perf_counter()
-        og.clear_frustums(now, oracle_frustums(O, p, poses))
-        for k, ((o, q), xyz) in enumerate(zip(poses, filtered[key])):
-            og.mark(xyz, o, p["obstacle_range"], now + 1e-4 * k)
-        cm, _, _ = og.update_ros_costmap(threshold_params["origin_x"], threshold_params["origin_y"], threshold_params["resolution"],
-                                         threshold_params["size_x"], threshold_params["size_y"], threshold_params["mark_threshold"],
-                                         threshold_params["default_value"])
-        t1 = time.perf_counter()
-        if step >= n_warm:
-            times.append(t1 - t0)
-    return times, og, cm
+def costmap_geometry(w, world):
+    cp = w.costmap_params()
+    if world > 1:   # one costmap over all slabs (origin of slab 0's)
+        cp["size_x"] = int(1600 + (world - 1) * SLAB_PITCH / cp["resolution"])
+    return cp
+
+
+def shared_config(w, cp, world):
+    """`config` of the JSON line — identical in both arms."""
+    ring = len(w.cycles)
+    return {"workload": w.name, "dt_s": w.dt, "episode_cycles": EPISODE_CYCLES,
+            "episode": "store reset + re-seeded to %d voxels, 1 untimed settle cycle, then %d timed cycles; repeated until K steps are timed"
+                       % (len(w.seed_vox[0]), EPISODE_CYCLES),
+            "points_per_cycle": w.points_per_cycle, "seeded_voxels": len(w.seed_vox[0]),
+            "costmap_cells": cp["size_x"] * cp["size_y"], "mark_threshold": cp["mark_threshold"],
+            "l2_policy": "inputs larger than L2: ring of %d distinct cycles x %.1f MB of clouds" % (ring, w.points_per_cycle * 16 / 1e6),
+            "n_slabs": world}
+
+
+def episode_plan(n_steps):
+    plan = [EPISODE_CYCLES] * (n_steps // EPISODE_CYCLES)
+    if n_steps % EPISODE_CYCLES:
+        plan.append(n_steps % EPISODE_CYCLES)
+    return plan
+
+
+def cycle_inputs(w, j, dt=None):
+    """Cycle j of an episode (j = 0 is the settle cycle): (now, ring slot)."""
+    return w.now0 + (w.dt if dt is None else dt) * (j + 1), j % len(w.cycles)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle on the same episodes
+# ------------------------------------------------------------------------------------------------
+class OracleRunner:
+    def __init__(self, w, cp):
+        from oracle import oracle_py as O
+        self.O, self.w, self.cp = O, w, cp
+        self.filtered = {}
+        self.frustums = {}
+
+    def _inputs(self, slot):
+        """The PassThrough pre-filter runs upstream of the cycle in the reference (MeasurementBuffer, subscriber thread), so
+        it is applied before the clock starts; the GPU path fuses it into Mark."""
+        O, p = self.O, self.w.p
+        if slot not in self.filtered:
+            cyc = self.w.cycles[slot]
+            self.filtered[slot] = [np.ascontiguousarray(O.filter_passthrough(c, p["min_obstacle_height"], p["max_obstacle_height"])) for c in cyc.clouds]
+            self.frustums[slot] = np.concatenate([O.depth_frustum(p["vfov"], p["hfov"], p["min_z"], p["max_z"], o, q, p["accel"]) for o, q in cyc.poses])
+        return self.filtered[slot], self.frustums[slot]
+
+    def episode(self, n_cycles, dt=None):
+        """reset + seed + settle + n_cycles.  Returns (per-cycle seconds of the timed cycles, grid, last costmap, marked cells)."""
+        O, w, cp, p = self.O, self.w, self.cp, self.w.p
+        og = O.OracleGrid(w.voxel_size, 0.0, w.decay_model, w.voxel_decay, False)
+        og.load_voxels(*w.seed_vox, w.seed_t)
+        times, cm, n_marked = [], None, 0
+        for j in range(n_cycles + 1):
+            now, slot = cycle_inputs(w, j, dt)
+            clouds, fr = self._inputs(slot)
+            t0 = time.perf_counter()
+            og.clear_frustums(now, fr)
+            for k, ((o, q), xyz) in enumerate(zip(w.cycles[slot].poses, clouds)):
+                og.mark(xyz, o, p["obstacle_range"], now + 1e-4 * k)
+            cm, _, n_marked = og.update_ros_costmap(cp["origin_x"], cp["origin_y"], cp["resolution"], cp["size_x"], cp["size_y"],
+                                                    cp["mark_threshold"], cp["default_value"])
+            t1 = time.perf_counter()
+            if j >= 1:
+                times.append(t1 - t0)
+        return times, og, cm, n_marked
 
 
 def host_info():
@@ -140,14 +202,20 @@ def host_info():
 
 def bench_reference(args):
     """--impl reference: the reference's CPU path (restated: the real one needs OpenVDB/Eigen/PCL/ROS 2, absent here).
-    Single-threaded like the reference (one mutex-guarded loop)."""
+    Single-threaded like the reference (one mutex-guarded loop).  Same workload object, same episodes."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    from spatio_temporal_voxel_layer_b200 import workloads
-    w = workloads.Config2(n_poses=2, ring=4)
-    cp = w.costmap_params()
-    times, og, _ = run_oracle_cycles(w, args.warmup, args.steps, cp)
+    w = make_workload(0, world)
+    cp = costmap_geometry(w, world)
+    runner = OracleRunner(w, cp)
+    if args.warmup:
+        runner.episode(min(args.warmup, EPISODE_CYCLES))
+    times, og = [], None
+    for n in episode_plan(args.steps):
+        t, og, _, _ = runner.episode(n)
+        times += t
     total = sum(times)
     v = len(times) / total
     model, ncpu = host_info()
@@ -155,20 +223,28 @@ def bench_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w.name, "points_per_cycle": w.points_per_cycle, "active_voxels": int(og.active_count()),
-                   "host_cpu": model, "host_cpus": ncpu},
+        "config": shared_config(w, cp, world),
+        "details": {"active_voxels_end_of_episode": int(og.active_count()), "host_cpu": model, "host_cpus": ncpu},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": "%d full config-2 cycles after %d warm-up (oracle/stvl_oracle.cpp, 1 thread as upstream; PassThrough pre-filter excluded)" % (args.steps, args.warmup)},
+                         "sample": "%d config-2 cycles in episodes of %d after a warm-up episode (oracle/stvl_oracle.cpp, 1 thread as upstream; "
+                                   "PassThrough pre-filter excluded)" % (args.steps, EPISODE_CYCLES)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def sorted_voxels(v):
+    ix, iy, iz, t = (np.asarray(a) for a in v)
+    k = np.lexsort((iz, iy, ix))
+    return ix[k], iy[k], iz[k], t[k]
+
+
 def bench_ours(args):
     import torch
     import spatio_temporal_voxel_layer_b200 as stvl
-    from spatio_temporal_voxel_layer_b200 import workloads
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -183,23 +259,17 @@ def bench_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    # ---- workload: rank r owns slab r (a config-2 store shifted by 80 m in x) --------------------------------------
-    slab_pitch = 80.0
-    # N=1: the store is centred on the origin (negative and positive coordinates); N>1: slab r spans x in [80r, 80r+80)
-    slab_origin = (0.0, 0.0) if world == 1 else (slab_pitch * rank + slab_pitch / 2, 0.0)
-    w = workloads.Config2(n_poses=4, ring=8, slab_origin=slab_origin, seed=1002 + rank)
+    w = make_workload(rank, world)
     p = w.p
     vs = float(np.float32(w.voxel_size))
-    leaf_w = int(round(slab_pitch / (8 * vs)))      # slab width in leaves (200)
+    leaf_w = int(round(SLAB_PITCH / (8 * vs)))      # slab width in leaves (200)
     grid_kw = dict(voxel_size=w.voxel_size, decay_model=w.decay_model, voxel_decay=w.voxel_decay, pub_voxels=False,
-                   device=local_rank, leaf_capacity=1 << 22)
+                   device=local_rank, leaf_capacity=1 << 20)
     if world > 1:   # spatial key-range shard: this rank keeps leaves with floor(bx / 200) mod N == rank
         grid_kw.update(shard_index=rank, shard_count=world, shard_width=leaf_w)
     g = stvl.SpatioTemporalVoxelGrid(**grid_kw)
     # plugin flow: UpdateROSCostmap only touch()es the cleared cells, i.e. needs their bounding box (always produced)
     g.set_outputs(0)
-    g.load_voxels(*w.seed_vox, w.seed_t)
-    n_seed = g.active_count()
 
     ring = len(w.cycles)
     # clouds: pinned host copies (e2e leg) and device-resident copies (value leg)
@@ -208,9 +278,7 @@ def bench_ours(args):
     torch.cuda.synchronize()
     frustums = [np.concatenate([stvl.build_depth_frustum(p["vfov"], p["hfov"], p["min_z"], p["max_z"], o, q, p["accel"])
                                 for o, q in cyc.poses]) for cyc in w.cycles]
-    cp = w.costmap_params()
-    if world > 1:   # one costmap over all slabs
-        cp["size_x"] = int(1600 + (world - 1) * slab_pitch / cp["resolution"])
+    cp = costmap_geometry(w, world)
     params = stvl.CostmapParams(cp["origin_x"], cp["origin_y"], cp["resolution"], cp["size_x"], cp["size_y"],
                                 cp["mark_threshold"], cp["default_value"], 254)
     costmap_dev = torch.zeros((cp["size_y"], cp["size_x"]), dtype=torch.uint8, device="cuda")
@@ -236,16 +304,6 @@ def bench_ours(args):
     fr_ptrs = [f.ctypes.data_as(C.c_void_p) for f in frustums]
     L, h, check = g.L, g.h, stvl._check
     n_cams = w.n_cams
-
-    def enqueue_clear_mark(step, device):
-        slot = step % ring
-        now = w.now0 + w.dt * (step + 1)
-        arr = (args_dev if device else args_host)[slot]
-        for k in range(n_cams):
-            arr[k].now = now + 1e-4 * k
-        check(L.stvl_clear_frustums(h, now, fr_ptrs[slot], n_cams))
-        return arr
-
     params_ref = C.byref(params)
     cm_dev_ptr, cm_host_ptr = costmap_dev.data_ptr(), costmap_host.data_ptr()
     if world > 1:   # one NCCL communicator per handle, id created by rank 0
@@ -253,61 +311,47 @@ def bench_ours(args):
         dist.broadcast_object_list(uid, src=0)
         g.comm_init(uid[0], rank, world)
 
-    def merge_pipelined():
-        """Device-resident leg, N>1: every rank thresholds its own voxel columns (x-slab shards own whole columns) and the library reduces the
-        {0, lethal} bytes to rank 0 with NCCL (max) on a side stream while its main stream already sweeps and marks the next cycle (column tiles are double-buffered),
-        and rank 0 thresholds cycle k's merged counts with call k+1.  Enqueue only."""
-        check(L.stvl_costmap_sharded_device(h, params_ref, cm_dev_ptr, 0, 0, 1))
+    def stamp(arr, now):
+        for k in range(n_cams):
+            arr[k].now = now + 1e-4 * k
 
     def merge_drain():
-        check(L.stvl_costmap_sharded_flush(h, params_ref, cm_dev_ptr, 0))
+        if world > 1:
+            check(L.stvl_costmap_sharded_flush(h, params_ref, cm_dev_ptr, 0))
 
-
-    def step_device(step, fused=True):
-        """One cycle with device-resident clouds.  N=1: ONE C-ABI call (stvl_update_cycle_device) enqueues the fused
-        clear -> mark -> costmap cycle (three launches chained by programmatic dependent launch); nothing synchronises.
-        fused=False enqueues the same cycle stage by stage (used for the per-stage / per-kernel event timings: in the
-        fused cycle Mark overlaps the sweep, so a per-kernel duration is not defined there)."""
-        if world == 1 and not fused:
-            arr = enqueue_clear_mark(step, True)
+    def step_device(j, dt=None, fused=True):
+        """Cycle j of an episode with device-resident clouds.  N=1: ONE C-ABI call (stvl_update_cycle_device) enqueues the
+        fused clear -> mark -> costmap cycle; nothing synchronises.  fused=False enqueues the same cycle stage by stage (used
+        for the per-stage / per-kernel event timings).  N>1: the same fused cycle on this rank's shard + the in-library merge
+        into rank 0's costmap, pipelined one cycle behind (stvl_update_cycle_sharded_device)."""
+        now, slot = cycle_inputs(w, j, dt)
+        arr = args_dev[slot]
+        stamp(arr, now)
+        if world == 1 and fused:
+            check(L.stvl_update_cycle_device(h, now, fr_ptrs[slot], n_cams, arr, n_cams, params_ref, cm_dev_ptr))
+        elif world == 1:
+            check(L.stvl_clear_frustums(h, now, fr_ptrs[slot], n_cams))
             check(L.stvl_mark_device(h, arr, n_cams))
             check(L.stvl_costmap_device(h, params_ref, cm_dev_ptr, None))
-        elif world == 1:
-            slot = step % ring
-            now = w.now0 + w.dt * (step + 1)
-            arr = args_dev[slot]
-            for k in range(n_cams):
-                arr[k].now = now + 1e-4 * k
-            check(L.stvl_update_cycle_device(h, now, fr_ptrs[slot], n_cams, arr, n_cams, params_ref, cm_dev_ptr))
-        elif fused:
-            # N>1: the same fused cycle on this rank's shard; its costmap pass writes the rank's {0, lethal} bytes into the
-            # reduce window and the library merges the windows into rank 0's costmap with NCCL (max) on a side stream,
-            # pipelined one cycle behind (stvl_update_cycle_sharded_device)
-            slot = step % ring
-            now = w.now0 + w.dt * (step + 1)
-            arr = args_dev[slot]
-            for k in range(n_cams):
-                arr[k].now = now + 1e-4 * k
-            check(L.stvl_update_cycle_sharded_device(h, now, fr_ptrs[slot], n_cams, arr, n_cams, params_ref, cm_dev_ptr, 0, 1))
         else:
-            arr = enqueue_clear_mark(step, True)
-            check(L.stvl_mark_device(h, arr, n_cams))
-            merge_pipelined()
+            check(L.stvl_update_cycle_sharded_device(h, now, fr_ptrs[slot], n_cams, arr, n_cams, params_ref, cm_dev_ptr, 0, 1))
 
-    def step_host(step):
-        arr = enqueue_clear_mark(step, False)
+    def step_host(j):
+        """Cycle j through the host-buffer entry points: clouds H2D and costmap bytes D2H inside the step."""
+        now, slot = cycle_inputs(w, j)
+        arr = args_host[slot]
+        stamp(arr, now)
+        check(L.stvl_clear_frustums(h, now, fr_ptrs[slot], n_cams))
         check(L.stvl_mark(h, arr, n_cams))
         if world == 1:
             res = stvl.CostmapResult()
             check(L.stvl_costmap(h, params_ref, cm_host_ptr, C.byref(res)))
-            return res
+            return
         check(L.stvl_costmap_sharded_device(h, params_ref, cm_dev_ptr, 0, 0, 0))   # blocking merge: this cycle's bytes
-        res = None
         if rank == 0:
             with torch.cuda.stream(stream):
                 costmap_host.copy_(costmap_dev, non_blocking=True)
         g.synchronize()
-        return res
 
     def barrier():
         g.synchronize()
@@ -317,65 +361,144 @@ def bench_ours(args):
         g.synchronize()
         torch.cuda.synchronize()
 
+    def reseed(grid=None):
+        grid = grid or g
+        grid.ResetGrid()
+        grid.load_voxels(*w.seed_vox, w.seed_t)
+
+    def device_episode(n_cycles, dt=None, fused=True, timed=True):
+        """reset + seed + settle + n_cycles; returns (CUDA-event ms of the n_cycles, kernel launches inside them)."""
+        merge_drain()
+        reseed()
+        step_device(0, dt, fused)
+        merge_drain()
+        barrier()
+        l0 = g.pool_stats().kernel_launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for j in range(1, n_cycles + 1):
+            step_device(j, dt, fused)
+        merge_drain()                      # N>1: the last cycle's merge is part of the timed region
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1), g.pool_stats().kernel_launches - l0
+
     # ---- value leg: inputs resident in HBM ---------------------------------------------------------------------------
-    step_no = 0
-    for _ in range(args.warmup):
-        step_device(step_no); step_no += 1
-    barrier()
-    launches0 = g.pool_stats().kernel_launches
+    device_episode(min(args.warmup, EPISODE_CYCLES))           # warm-up episode (W cycles after the settle cycle)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_wall0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_device(step_no); step_no += 1
-    if world > 1:
-        merge_drain()                      # the last cycle's bytes are part of the timed region
-    e1.record(stream)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    dev_ms = e0.elapsed_time(e1)   # every rank's work (incl. the NCCL reduce) is ordered on the library's stream
-    # The timed region lasts a few milliseconds — less than one nvidia-smi sampling period — so the sampler keeps running
-    # while the very same cycle loop continues (untimed) for 8000 more cycles (~0.3 s): the clocks reported are those under this load.
-    launches = g.pool_stats().kernel_launches - launches0
-    for _ in range(8000):                  # (a fixed count: every rank must enqueue the same number of merges)
-        step_device(step_no); step_no += 1
-        if step_no % 100 == 0:
+    dev_ms, launches, episode_ms = 0.0, 0, []
+    n_seed = len(w.seed_vox[0])
+    for n in episode_plan(args.steps):
+        ms, nl = device_episode(n)
+        dev_ms += ms
+        launches += nl
+        episode_ms.append(ms / n)
+    st_end = g.sweep_stats()               # the last timed cycle's sweep
+    active_end = g.active_count()
+    # The timed region lasts a few hundred microseconds per episode — less than one nvidia-smi sampling period — so the
+    # sampler keeps running while the same cycle loop soaks for ~0.3 s (untimed, results discarded, store re-seeded after).
+    reseed()
+    for j in range(6000):                  # (a fixed count: every rank must enqueue the same number of merges)
+        step_device(j % EPISODE_CYCLES)
+        if j % 100 == 99:
             g.synchronize()
-    if world > 1:
-        merge_drain()
+    merge_drain()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
-        clocks["note"] = "nvidia-smi -lms 100 from the start of the timed region through 8000 more (untimed) cycles of the same loop"
-    # Per-kernel timing: K more cycles of the same ring, enqueued stage by stage with every stage bracketed by CUDA events
-    # inside the library (on the library's stream).  Not part of `value`.  The Mark kernel's duration for the roofline
-    # comes from here: standalone, serialised behind the sweep, inputs not in L2 (ring of 8 x 34.4 MB).
-    g.enable_timing(stvl.TIME_SWEEP | stvl.TIME_MARK | stvl.TIME_COSTMAP)
-    g.timing()
-    for _ in range(args.steps):
-        step_device(step_no, fused=False); step_no += 1
-    t_all = g.timing()
-    t_mark = t_all
-    g.enable_timing(0)
-    st = g.sweep_stats()
-    active = g.active_count()
+        clocks["note"] = "nvidia-smi -lms 100 over the timed episodes and an untimed 6000-cycle soak of the same loop on a re-seeded store (discarded)"
 
-    if world > 1:
-        merge_drain()
-    barrier()
+    # ---- per-stage / per-kernel timing on a fresh episode, stage by stage ----------------------------------------------
+    t_all = None
+    st_stage = None
+    if world == 1:
+        reseed()
+        step_device(0, fused=False)
+        barrier()
+        g.enable_timing(stvl.TIME_SWEEP | stvl.TIME_MARK | stvl.TIME_COSTMAP)
+        g.timing()
+        for j in range(1, EPISODE_CYCLES + 1):
+            step_device(j, fused=False)
+        t_all = g.timing()
+        g.enable_timing(0)
+        st_stage = g.sweep_stats()
+
+    # ---- sensitivity of the device-resident cycle to the cycle period (2-3 s of simulated time each, fresh seed) ----------
+    sensitivity = {}
+    if world == 1 and not args.no_sensitivity:
+        for dt, n in ((0.01, 200), (1.0, 3)):
+            ms, _ = device_episode(n, dt=dt)
+            sensitivity["dt_%g_s" % dt] = {"cycles": n, "us_per_cycle": 1e3 * ms / n, "cycles_per_s": n / (ms / 1e3),
+                                           "swept_last_cycle": int(g.sweep_stats().n_swept)}
+
+    # ---- parity: the fused path's state after one more episode vs the oracle's (full config-2 size) -----------------------
+    parity = None
+    oracle_times = []
+    if not args.no_parity:
+        device_episode(EPISODE_CYCLES)
+        if world > 1:
+            dist.broadcast(costmap_dev, src=0)      # the merged costmap: every rank checks its own slab's cells
+        gcm = costmap_dev.cpu().numpy()
+        gv = sorted_voxels(g.voxels())
+        gcols = g.columns()
+        runner = OracleRunner(w, cp)
+        n_ep = 1 if (world > 1 or args.no_cpu_baseline) else max(1, args.cpu_cycles // EPISODE_CYCLES)
+        og = ocm = None
+        for e in range(n_ep):
+            t, og_e, ocm_e, _ = runner.episode(EPISODE_CYCLES)
+            oracle_times += t
+            if e == 0:
+                og, ocm = og_e, ocm_e
+        ov = sorted_voxels(og.voxels())
+        ok_vox = all(np.array_equal(a.view(np.uint8), b.view(np.uint8)) for a, b in zip(gv, ov))
+        ox_, oy_, oc_ = og.costmap()         # GetFlattenedCostmap of the last sweep: world (x, y) doubles + count
+        okk = np.lexsort((oy_, ox_))
+        gx, gy = g.index_to_world(gcols[0]), g.index_to_world(gcols[1])
+        gk = np.lexsort((gy, gx))
+        ok_cols = (len(gx) == len(ox_) and np.array_equal(gx[gk].view(np.uint64), ox_[okk].view(np.uint64)) and
+                   np.array_equal(gy[gk].view(np.uint64), oy_[okk].view(np.uint64)) and np.array_equal(gcols[2][gk], oc_[okk]))
+        if world == 1:
+            ok_cm = bool(np.array_equal(gcm, ocm))
+        else:
+            # x cells of this rank's slab in the merged costmap (slab r spans [80 r, 80 r + 80) m from slab 0's origin - 37.5 - 1)
+            own = ocm == 254
+            ok_cm = bool(np.array_equal(gcm[own], ocm[own]))
+            counts = torch.tensor([int(own.sum())], device="cuda")
+            dist.all_reduce(counts)
+            ok_cm = ok_cm and int(counts.item()) == int((gcm == 254).sum())     # nothing marked that no slab's oracle marks
+        ok = bool(ok_vox and ok_cols and ok_cm)
+        if dist is not None:
+            f = torch.tensor([1 if ok else 0], device="cuda")
+            dist.all_reduce(f, op=dist.ReduceOp.MIN)
+            ok = bool(f.item())
+        parity = {"parity_checked": ok, "voxels_compared": int(len(gv[0])), "columns_compared": int(len(gcols[0])),
+                  "marked_cells": int((gcm == 254).sum()),
+                  "what": "after an episode of %d fused cycles on the 710,765-voxel seed: costmap bytes, per-column counts (keys as f64 bit patterns) "
+                          "and the voxel set with its mark times, all bit-exact against oracle/stvl_oracle.cpp on the same inputs%s"
+                          % (EPISODE_CYCLES, "" if world == 1 else "; every rank checks its own slab against the merged costmap")}
+        if not ok:
+            parity["detail"] = {"voxels": bool(ok_vox), "columns": bool(ok_cols), "costmap": bool(ok_cm)}
+
     # ---- e2e leg: host clouds in, host costmap bytes out ---------------------------------------------------------------
-    for _ in range(args.warmup):
-        step_host(step_no); step_no += 1
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        last_res = step_host(step_no); step_no += 1
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = 0.0
+    merge_drain()
+    reseed()
+    step_host(0)
+    for j in range(1, min(args.warmup, EPISODE_CYCLES) + 1):
+        step_host(j)
+    for n in episode_plan(args.steps):
+        reseed()
+        step_host(0)
+        barrier()
+        t0 = time.perf_counter()
+        for j in range(1, n + 1):
+            step_host(j)
+        barrier()
+        e2e_s += time.perf_counter() - t0
+    e2e_active_end = g.active_count()
 
     # max over ranks
     if dist is not None:
@@ -391,47 +514,50 @@ def bench_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w.name, "points_per_cycle": w.points_per_cycle, "seeded_voxels": int(n_seed),
-                       "active_voxels_end": int(active), "swept_last_cycle": int(st.n_swept),
-                       "l2_policy": "inputs larger than L2: ring of %d distinct cycles x %.1f MB of clouds; leaf pool %.1f GB" % (
-                           ring, w.points_per_cycle * 16 / 1e6, g.pool_stats().device_bytes / 1e9),
-                       "costmap_cells": cp["size_x"] * cp["size_y"],
-                       "parallelism": "1 GPU" if world == 1 else "%d spatial x-slab shards, fused cycle per shard + in-library NCCL merge of the per-shard costmap bytes (max), pipelined one cycle behind on a side stream" % world},
+            "config": shared_config(w, cp, world),
+            "details": {"seeded_voxels": int(n_seed), "active_voxels_end_of_last_timed_episode": int(active_end),
+                        "swept_last_timed_cycle": int(st_end.n_swept), "cleared_last_timed_cycle": int(st_end.n_cleared),
+                        "rewritten_last_timed_cycle": int(st_end.n_rewritten),
+                        "e2e_active_voxels_end": int(e2e_active_end), "us_per_cycle_by_episode": [round(1e3 * v, 2) for v in episode_ms],
+                        "leaf_pool_gb": g.pool_stats().device_bytes / 1e9,
+                        "parallelism": "1 GPU" if world == 1 else "%d spatial x-slab shards, fused cycle per shard + in-library merge of the per-shard costmap cells into rank 0, pipelined one cycle behind" % world},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": bytes_h2d, "d2h_bytes_per_step": bytes_d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        if t_mark.n_mark:
-            mark_s = t_mark.mark_ms / t_mark.n_mark / 1e3
+        if parity is not None:
+            line["parity_checked"] = parity["parity_checked"]
+            line["parity"] = parity
+        if sensitivity:
+            line["sensitivity"] = sensitivity
+        if t_all is not None and t_all.n_mark:
+            mark_s = t_all.mark_ms / t_all.n_mark / 1e3
             algo_mark = w.points_per_cycle * 16          # 16 B read per input point
-            algo_clear = st.n_swept * 16                 # 16 B per active voxel (key + time)
             traffic = None
             try:
-                with open(os.path.join(ROOT, "profiles", "r1b_traffic.json")) as f:
+                with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
                     traffic = json.load(f).get("mark_kernel_dram_bytes_per_launch")
             except Exception:
                 pass
             line["roofline"] = {"bound": "hbm", "kernel": "mark_kernel", "achieved": algo_mark / mark_s / 1e9, "peak": peak,
                                 "unit": "GB/s", "frac": algo_mark / mark_s / 1e9 / peak, "traffic": traffic,
                                 "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_mark,
-                                "kernel_ms": t_mark.mark_ms / t_mark.n_mark, "launches_timed": int(t_mark.n_mark),
-                                "timing": "CUDA events around the kernel on the library's stream, in a stage-by-stage pass of the same "
-                                          "cycles right after the timed region (in the fused cycle Mark overlaps the sweep by "
-                                          "programmatic dependent launch and has no duration of its own)"}
-            if t_all.n_sweep and t_all.n_costmap and t_all.n_mark:
+                                "kernel_ms": t_all.mark_ms / t_all.n_mark, "launches_timed": int(t_all.n_mark),
+                                "timing": "CUDA events around the kernel on the library's stream, in a stage-by-stage pass over a freshly "
+                                          "seeded episode (in the fused cycle Mark overlaps the sweep and has no duration of its own)"}
+            if t_all.n_sweep and t_all.n_costmap:
                 sweep_s = t_all.sweep_ms / t_all.n_sweep / 1e3
+                algo_clear = int(st_stage.n_swept) * 16      # 16 B per active voxel (key + time)
                 line["roofline"]["stage_ms"] = {"clear": t_all.sweep_ms / t_all.n_sweep, "mark": t_all.mark_ms / t_all.n_mark,
                                                 "costmap": t_all.costmap_ms / t_all.n_costmap,
-                                                "note": "stage-by-stage pass (stvl_clear_frustums, stvl_mark_device, stvl_costmap_device), serialised; the fused cycle of `value` overlaps them"}
+                                                "note": "stage-by-stage pass (stvl_clear_frustums, stvl_mark_device, stvl_costmap_device) on a freshly seeded episode, serialised; the fused cycle of `value` overlaps them"}
                 line["roofline"]["sweep_kernels"] = {"achieved": algo_clear / sweep_s / 1e9, "frac": algo_clear / sweep_s / 1e9 / peak,
-                                                     "algorithmic_bytes_per_launch": int(algo_clear)}
-        # cpu baseline: bounded sample of the same cycles on the host (rank 0, N=1 only)
-        if world == 1 and not args.no_cpu_baseline:
-            wb = w
-            times, og, ocm = run_oracle_cycles(wb, 1, args.cpu_cycles, cp)
+                                                     "algorithmic_bytes_per_launch": int(algo_clear), "swept_voxels": int(st_stage.n_swept)}
+        if world == 1 and not args.no_cpu_baseline and oracle_times:
             model, ncpu = host_info()
-            line["cpu_baseline"] = {"value": len(times) / sum(times), "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": "%d full config-2 cycles after 1 warm-up, oracle/stvl_oracle.cpp single thread (the reference path is single-threaded); host %s x%s" % (len(times), model, ncpu)}
+            line["cpu_baseline"] = {"value": len(oracle_times) / sum(oracle_times), "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": "%d config-2 cycles (episodes of %d on the re-seeded store), oracle/stvl_oracle.cpp single thread (the reference path is single-threaded); host %s x%s"
+                                              % (len(oracle_times), EPISODE_CYCLES, model, ncpu)}
         print(json.dumps(line))
     # tear down in dependency order: tensors that were used on the library's stream are released while that stream is
     # still alive (the caching allocator records events on it), then the process group, then the grid
@@ -455,8 +581,10 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-cycles", type=int, default=40)
+    ap.add_argument("--cpu-cycles", type=int, default=80)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-sensitivity", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

@@ -28,7 +28,10 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 
 // fire-and-forget global reductions (no return value, no scoreboard wait)
 __device__ __forceinline__ void red_or_u32(uint32_t * p, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void red_max_u64(unsigned long long * p, unsigned long long v) { asm volatile("red.global.max.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+// "later reading overwrites" as a SIGNED 64-bit max on the double's bit pattern: every clock sample of a batched launch is
+// > 0, and a stored time may have been pushed below zero by a sweep (value - accel, reference .cpp:190), whose bit pattern
+// is a negative integer — an unsigned max would keep the stale negative time
+__device__ __forceinline__ void red_max_s64(unsigned long long * p, unsigned long long v) { asm volatile("red.global.max.s64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
 
 // Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
 // start while its predecessor in the stream is still running, once every CTA of the predecessor has executed
@@ -328,7 +331,7 @@ __device__ __forceinline__ void mark_voxel_direct(const GridView & g, uint64_t k
   if (slot == kOverflowSlot) return;
   atomicOr(&g.leaf_mask[(size_t)slot * 16 + (l >> 5)], 1u << (l & 31));
   double * tp = &g.leaf_time[(size_t)slot * kLeafVoxels + l];
-  if (use_max) atomicMax(reinterpret_cast<unsigned long long *>(tp), now_bits);
+  if (use_max) atomicMax(reinterpret_cast<long long *>(tp), (long long)now_bits);
   else {
     *tp = now;   // MarkGridPoint: setValueOn overwrite, .cpp:421-430
     if (g.leaf_tmin[slot] > now) g.leaf_tmin[slot] = -CUDART_INF;   // clocks are not monotone here
@@ -502,7 +505,7 @@ mark_kernel(const GridView g, const __grid_constant__ MarkBatch batch, const Cos
       if (!use_max && g.leaf_tmin[slot] > now) g.leaf_tmin[slot] = -CUDART_INF;   // clocks are not monotone here
       while (m) {
         const int b = __ffs(m) - 1; m &= m - 1;
-        if (use_max) red_max_u64(reinterpret_cast<unsigned long long *>(tp + b), now_bits);
+        if (use_max) red_max_s64(reinterpret_cast<unsigned long long *>(tp + b), now_bits);
         else tp[b] = now;
       }
     }
@@ -688,9 +691,22 @@ load_voxels_kernel(const GridView g, const int32_t * __restrict__ vx, const int3
     if (!(leaf_coord_ok(bx) && leaf_coord_ok(by) && leaf_coord_ok(bz))) {
       atomicAdd(&g.ctr->dropped_range, 1ull);
     } else if (shard_owns(bx, g.shard_index, g.shard_count, g.shard_width)) {
-      const uint32_t slot = leaf_find_or_insert(g, pack_leaf_key(bx, by, bz), bx, by, free_n0, high_water0, -CUDART_INF);
+      const uint32_t slot = leaf_find_or_insert(g, pack_leaf_key(bx, by, bz), bx, by, free_n0, high_water0, CUDART_INF);
       if (slot != kOverflowSlot) {
-        if (g.leaf_tmin[slot] != -CUDART_INF) g.leaf_tmin[slot] = -CUDART_INF;   // arbitrary times: bound unknown
+        // keep the leaf's lower bound of mark times exact (CAS loop: loaded times are arbitrary doubles, NaN = unknown)
+        {
+          const double tv = vt[i];
+          unsigned long long * tp = reinterpret_cast<unsigned long long *>(&g.leaf_tmin[slot]);
+          unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tp);
+          for (;;) {
+            const double c = __longlong_as_double((long long)cur);
+            const double want = (tv == tv) ? fmin(c, tv) : -CUDART_INF;
+            if (__double_as_longlong(want) == (long long)cur) break;
+            const unsigned long long old = atomicCAS(tp, cur, (unsigned long long)__double_as_longlong(want));
+            if (old == cur) break;
+            cur = old;
+          }
+        }
         const unsigned li = (unsigned)(((ix & 7) * 8 + (iy & 7)) * 8 + (iz & 7));
         atomicOr(&g.leaf_mask[(size_t)slot * 16 + (li >> 5)], 1u << (li & 31));
         g.leaf_time[(size_t)slot * kLeafVoxels + li] = vt[i];
