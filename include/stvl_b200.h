@@ -187,7 +187,12 @@ int stvl_build_transform(const double translation[3], const double quat_xyzw[4],
 int stvl_clear_frustums(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums);
 /* Mark + operator() (.cpp:254-309).  Host clouds are copied to the device inside the call. */
 int stvl_mark(stvl_grid_t * g, const stvl_reading_t * readings, uint32_t n_readings);
-/* Same, but readings[i].data are DEVICE pointers already resident in HBM (16-byte aligned). */
+/* Same, but readings[i].data are DEVICE pointers already resident in HBM (16-byte aligned).
+ * LIFETIME: the call only enqueues work, and a Mark that runs out of leaf / tile pool is replayed after the pool has
+ * grown — detected at the next stvl_* call on the handle.  The device clouds handed to stvl_mark_device,
+ * stvl_update_cycle_device and stvl_update_cycle_sharded_device must therefore stay valid and UNMODIFIED until the next
+ * stvl_* call on the handle has returned (host clouds passed to stvl_mark are copied inside the call and are the
+ * caller's again when it returns). */
 int stvl_mark_device(stvl_grid_t * g, const stvl_reading_t * readings, uint32_t n_readings);
 /* UpdateROSCostmap's grid loop (stvl/src/spatio_temporal_voxel_layer.cpp:699-718) fused with
  * GetFlattenedCostmap: resetMaps to default_value, then lethal_value for every voxel column with
@@ -201,17 +206,21 @@ int stvl_costmap_device(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_
 
 /* One whole update cycle with device-resident inputs, in the reference's order (stvl/src/spatio_temporal_voxel_layer.cpp:
  * 772-795): the results are those of stvl_clear_frustums, stvl_mark_device, stvl_costmap_device(res = NULL), but the
- * three stages are fused into three launches (the sweep's first kernel also resets the costmap bytes, the costmap pass
- * rides on the Mark kernel, the kernels overlap by programmatic dependent launch).  Enqueue only, no synchronisation;
+ * three stages are fused into two launches (the sweep kernel also resets the costmap bytes, the costmap pass rides on
+ * dedicated warps of the Mark kernel, the kernels overlap by programmatic dependent launch).  Enqueue only, no synchronisation;
  * the clouds must be complete on the device when the call is made (stream order on stvl_get_stream() suffices).
  * stvl_get_costmap_result returns the marked-cell count / bounds afterwards. */
 int stvl_update_cycle_device(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
                              const stvl_reading_t * readings, uint32_t n_readings,
                              const stvl_costmap_params_t * p, uint8_t * costmap_dev);
-/* The same cycle on a spatial shard (stvl_config_t.shard_*, stvl_comm_init): the fused cycle writes this rank's
- * {0, lethal} bytes into the reduce window and the windows are merged into `costmap_dev` on `root` exactly as by
- * stvl_costmap_sharded_device(count_bytes = 0) — blocking, or pipelined one cycle behind on a side stream
- * (stvl_costmap_sharded_flush drains the last one).  costmap_dev is only used on the root. */
+/* The same cycle on a spatial shard (stvl_config_t.shard_*, stvl_comm_init).  x-slab shards own whole voxel columns, so
+ * the merged costmap is the union of the ranks' lethal cells: the fused cycle's costmap pass writes a packed BITMAP of the
+ * cells of this rank's own x interval (1 bit per cell), the bitmaps travel to `root` with one grouped ncclSend / ncclRecv,
+ * and the root expands them into the bytes of `costmap_dev` (lethal_value where any rank marked the cell, default_value
+ * elsewhere).  Blocking (pipelined = 0: the bytes are this cycle's when the call's work has run), or pipelined one cycle
+ * behind: exchange and expansion run on a side stream while the next cycle's kernels run, the bytes of cycle k are in
+ * `costmap_dev` (in stream order on stvl_get_stream()) after call k+1, and stvl_costmap_sharded_flush drains the last
+ * one.  costmap_dev is only used on the root.  Needs shard_count == the communicator's size. */
 int stvl_update_cycle_sharded_device(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
                                      const stvl_reading_t * readings, uint32_t n_readings,
                                      const stvl_costmap_params_t * p, uint8_t * costmap_dev, int root, int pipelined);
@@ -225,6 +234,18 @@ int stvl_update_cycle_sharded_device(stvl_grid_t * g, double now, const stvl_fru
 int stvl_update_costs_device(stvl_grid_t * g, const stvl_costmap_params_t * p, uint8_t * layer_costmap_dev, uint8_t * master_dev,
                              const double * footprint_xy, uint32_t n_footprint, int combination_method,
                              int32_t min_i, int32_t min_j, int32_t max_i, int32_t max_j);
+
+/* Pipelined form of the whole cycle for HOST buffers (what a costmap plugin that keeps its clouds and its costmap in host
+ * memory calls): readings[i].data are HOST clouds (pinned memory makes the copies asynchronous), `costmap_host` receives
+ * the size_x*size_y bytes.  The call enqueues H2D copy -> fused cycle -> D2H copy on three streams with double-buffered
+ * device staging and returns a ticket at once; cycle k+1's H2D copy overlaps cycle k's kernels and read-back.
+ * The clouds of a cycle and its costmap_host belong to the library until stvl_update_cycle_wait(ticket) has returned
+ * (which also delivers the marked-cell count / bounds of that cycle).  At most two cycles may be in flight: submitting a
+ * third waits for the oldest.  Cycles complete in submission order. */
+int stvl_update_cycle_async(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
+                            const stvl_reading_t * readings, uint32_t n_readings,
+                            const stvl_costmap_params_t * p, uint8_t * costmap_host, uint64_t * ticket);
+int stvl_update_cycle_wait(stvl_grid_t * g, uint64_t ticket, stvl_costmap_result_t * res);
 
 /* The result (marked columns, touched bounds — the touch() calls of spatio_temporal_voxel_layer.cpp:716) of the last
  * costmap pass enqueued by stvl_costmap_device(res = NULL) or stvl_update_cycle_device.  Synchronises. */

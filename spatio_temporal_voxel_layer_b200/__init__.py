@@ -89,7 +89,7 @@ EXPORTED_SYMBOLS = [
     "stvl_get_cleared", "stvl_get_points", "stvl_get_ambiguous", "stvl_reset", "stvl_reset_area", "stvl_active_count",
     "stvl_get_voxels", "stvl_load_voxels", "stvl_index_to_world", "stvl_voxel_size", "stvl_columns_to_dense",
     "stvl_costmap_from_dense", "stvl_get_pool_stats", "stvl_get_stream", "stvl_synchronize",
-    "stvl_update_cycle_device", "stvl_update_cycle_sharded_device", "stvl_update_costs_device", "stvl_get_costmap_result", "stvl_enable_timing", "stvl_get_timing",
+    "stvl_update_cycle_device", "stvl_update_cycle_sharded_device", "stvl_update_cycle_async", "stvl_update_cycle_wait", "stvl_update_costs_device", "stvl_get_costmap_result", "stvl_enable_timing", "stvl_get_timing",
     "stvl_nccl_unique_id", "stvl_comm_init", "stvl_comm_destroy", "stvl_costmap_sharded_device", "stvl_costmap_sharded_flush",
 ]
 
@@ -147,6 +147,8 @@ def load_library(build_if_missing=True):
     L.stvl_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.stvl_synchronize.argtypes = [vp]
     L.stvl_update_cycle_device.argtypes = [vp, d, vp, u32, C.POINTER(Reading), u32, C.POINTER(CostmapParams), vp]
+    L.stvl_update_cycle_async.argtypes = [vp, d, vp, u32, C.POINTER(Reading), u32, C.POINTER(CostmapParams), vp, C.POINTER(u64)]
+    L.stvl_update_cycle_wait.argtypes = [vp, u64, C.POINTER(CostmapResult)]
     L.stvl_get_costmap_result.argtypes = [vp, C.POINTER(CostmapResult)]
     L.stvl_update_costs_device.argtypes = [vp, C.POINTER(CostmapParams), vp, vp, vp, u32, C.c_int, i32, i32, i32, i32]
     L.stvl_update_cycle_sharded_device.argtypes = [vp, d, vp, u32, C.POINTER(Reading), u32, C.POINTER(CostmapParams), vp, C.c_int, C.c_int]
@@ -332,6 +334,30 @@ class SpatioTemporalVoxelGrid:
         p = CostmapParams(origin_x, origin_y, resolution, size_x, size_y, mark_threshold, default_value, LETHAL_OBSTACLE)
         _check(self.L.stvl_update_cycle_device(self.h, float(now), _ptr(blocks) if len(blocks) else None, len(blocks), arr, n,
                                                C.byref(p), costmap_dev_ptr))
+
+    def update_cycle_async(self, now, clearing_readings, marking_readings, params, costmap_host):
+        """stvl_update_cycle_async: the pipelined host-buffer cycle.  marking_readings carry HOST clouds (numpy arrays or
+        (ptr, n, step, offsets) tuples of pinned memory), costmap_host is a uint8 numpy array (size_y, size_x) that stays
+        alive until update_cycle_wait(ticket).  Returns the ticket."""
+        fr = [b for b in (r.frustum() for r in clearing_readings) if b is not None]
+        blocks = np.concatenate(fr) if fr else np.zeros(0, FRUSTUM_DTYPE)
+        n = len(marking_readings)
+        arr = (Reading * max(n, 1))()
+        keep = []
+        for i, m in enumerate(marking_readings):
+            m._fill(arr[i], now, keep)
+        t = C.c_uint64(0)
+        _check(self.L.stvl_update_cycle_async(self.h, float(now), _ptr(blocks) if len(blocks) else None, len(blocks), arr, n,
+                                              C.byref(params), _ptr(costmap_host), C.byref(t)))
+        self._async_keep = getattr(self, "_async_keep", {})
+        self._async_keep[t.value] = (keep, costmap_host)
+        return t.value
+
+    def update_cycle_wait(self, ticket):
+        res = CostmapResult()
+        _check(self.L.stvl_update_cycle_wait(self.h, ticket, C.byref(res)))
+        getattr(self, "_async_keep", {}).pop(ticket, None)
+        return res
 
     def update_cycle_sharded_device(self, now, clearing_readings, marking_readings, params, costmap_dev_ptr, root=0, pipelined=False):
         """stvl_update_cycle_sharded_device: the fused cycle on a spatial shard + in-library NCCL merge (bytes mode)."""

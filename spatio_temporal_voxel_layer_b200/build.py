@@ -13,8 +13,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libstvl_b200.so")
-SOURCES = ["stvl_kernels.cu", "stvl_voxel_filter.cu", "stvl_costs.cu", "stvl_api.cu", "stvl_geometry.cpp"]
-HEADERS = ["stvl_device.cuh", "stvl_kernels.h", "stvl_geometry.h", "stvl_voxel_filter.h"]
+SOURCES = ["stvl_mark.cu", "stvl_sweep.cu", "stvl_kernels.cu", "stvl_voxel_filter.cu", "stvl_costs.cu", "stvl_api.cu", "stvl_geometry.cpp"]
+HEADERS = ["stvl_device.cuh", "stvl_common.cuh", "stvl_kernels.h", "stvl_geometry.h", "stvl_voxel_filter.h"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
@@ -22,8 +22,7 @@ NVCC_FLAGS = [
     "-lineinfo",
     "-fmad=false",                       # device: never contract a*b+c (bit-exact parity with the CPU path)
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
-    "-shared", "-cudart", "static",
-    "-x", "cu",
+    "-cudart", "static",
 ]
 
 
@@ -45,25 +44,45 @@ def needs_build():
 TRACE_LIB_PATH = os.path.join(PKG_DIR, "libstvl_b200_trace.so")
 
 
-def build_library(force=False, verbose=False, trace=False):
-    """trace=True builds the profiling-only variant (-DSTVL_TRACE: per-CTA %globaltimer phase stamps, read back by
-    profiles/trace_phases.py through STVL_B200_LIB) into a separate file; the product library never contains it."""
-    if not trace and not force and not needs_build():
+def build_library(force=False, verbose=False, trace=False, csrc=None, out=None):
+    """Compile every source to an object file (in parallel) and link libstvl_b200.so.
+    trace=True builds the profiling-only variant (-DSTVL_TRACE: per-CTA %globaltimer phase stamps, read back by
+    profiles/trace_phases.py through STVL_B200_LIB) into a separate file; the product library never contains it.
+    csrc / out: build another source tree into another file (scratch builds during development)."""
+    if csrc is None and out is None and not trace and not force and not needs_build():
         return LIB_PATH
-    out = TRACE_LIB_PATH if trace else LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(REPO_ROOT, "include"), "-I", CSRC]
+    import concurrent.futures
+    import tempfile
+    src_dir = csrc or CSRC
+    out = out or (TRACE_LIB_PATH if trace else LIB_PATH)
+    base = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(REPO_ROOT, "include"), "-I", src_dir]
     if trace:
-        cmd += ["-DSTVL_TRACE"]
+        base += ["-DSTVL_TRACE"]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        base += ["-Xptxas", "-v"]
+    with tempfile.TemporaryDirectory(prefix="stvl_build_") as tmp:
+        def compile_one(f):
+            obj = os.path.join(tmp, f + ".o")
+            res = subprocess.run(base + ["-x", "cu", "-c", os.path.join(src_dir, f), "-o", obj], capture_output=True, text=True)
+            return f, obj, res
+        with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+            results = list(ex.map(compile_one, SOURCES))
+        log = ""
+        for f, obj, res in results:
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed on %s:\n%s%s" % (f, res.stdout, res.stderr))
+            log += res.stderr
+        link = [_nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + [obj for _, obj, _ in results]
+        res = subprocess.run(link, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     if verbose:
-        sys.stderr.write(res.stderr)
+        sys.stderr.write(log)
     return out
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))
+    def _opt(name):
+        return sys.argv[sys.argv.index(name) + 1] if name in sys.argv else None
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv,
+                        csrc=_opt("--csrc"), out=_opt("--out")))

@@ -122,9 +122,9 @@ struct stvl_grid {
   bool swept = false;
   uint32_t * tile_buf[2] = {nullptr, nullptr};   // double-buffered column tiles (see GridView::tile_count)
   int sweep_parity = 0;
-  bool alloc_dirty = false;         // a Mark / load kernel handed out leaves that are not folded into the allocator yet
   uint64_t launches = 0;
-  uint32_t mark_cursor_sel = 0;     // chunk cursor of the next Mark launch (they alternate)
+  uint32_t mark_cursor_sel = 0;     // chunk cursor of the next Mark launch (they alternate) ...
+  uint32_t mark_cursor_base[2] = {0, 0};   // ... and the value each cursor will have when its next launch starts
   size_t device_bytes = 0;
   // in-library sharded merge (stvl_comm_init / stvl_costmap_sharded_device)
   ncclComm_t comm = nullptr;
@@ -132,10 +132,32 @@ struct stvl_grid {
   cudaStream_t merge_stream = nullptr;
   cudaEvent_t ev_scatter[2] = {nullptr, nullptr}, ev_reduce[2] = {nullptr, nullptr};
   DevBuf<uint8_t> window[2];
+  // bitmap merge of the sharded fused cycle: this rank's packed cell bitmap (double-buffered) and, on the root, the
+  // staging area the other ranks' bitmaps are received into
+  DevBuf<uint32_t> bits[2];
+  DevBuf<uint32_t> bits_stage[2];
+  int bit_w_lo[kMaxShardRanks] = {0}, bit_w_hi[kMaxShardRanks] = {0};   // word interval of every rank for the current geometry
+  stvl_costmap_params_t bits_params{};   // geometry the intervals were computed for
+  bool bits_geom_valid = false;
+  int bits_pending = -1;                 // buffer whose exchange is in flight and not expanded yet
+  int bits_expanding = -1;               // buffer whose expansion was put on the side stream by the current call
+  cudaEvent_t ev_bits_done[2] = {nullptr, nullptr}, ev_expand[2] = {nullptr, nullptr}, ev_main_pos = nullptr;
+  uint64_t bits_k = 0;
   uint64_t win_k = 0;
   int win_pending = -1;                 // window whose reduce is in flight and not thresholded yet
   int win_geom[4] = {0, 0, 0, 0};       // ix0, iy0, nx, ny of the pending window
   int win_count_bytes = 4;
+  // pipelined host-buffer cycle (stvl_update_cycle_async): double-buffered staging of clouds / costmap bytes / results
+  struct AsyncSlot {
+    DevBuf<uint8_t> stage, costmap;
+    CostmapCtr * d_res = nullptr;        // device snapshot of the cycle's costmap result
+    CostmapCtr * h_res = nullptr;        // pinned
+    cudaEvent_t ev_h2d = nullptr, ev_cycle = nullptr, ev_d2h = nullptr;
+    bool busy = false;
+    uint64_t ticket = 0;
+  } aslot[2];
+  cudaStream_t d2h_stream = nullptr;
+  uint64_t next_ticket = 1;
   // optional per-stage timing (stvl_enable_timing)
   uint32_t timing_mask = 0;
   struct TimedInterval { cudaEvent_t a, b; int stage; };
@@ -209,21 +231,22 @@ int alloc_pool(stvl_grid * g, uint32_t leaf_capacity, GridView * nv)
   CU(cudaMalloc(&v.leaf_mask, (size_t)leaf_capacity * 64));
   CU(cudaMalloc(&v.leaf_time, (size_t)leaf_capacity * kLeafVoxels * 8));
   CU(cudaMalloc(&v.leaf_tmin, (size_t)leaf_capacity * 8));
-  CU(cudaMalloc(&v.free_slots, (size_t)leaf_capacity * 4));
-  CU(cudaMalloc(&v.sweep_queue, (size_t)leaf_capacity * 4));
+  const uint32_t ring = pow2_ceil(leaf_capacity);
+  v.free_ring_mask = ring - 1;
+  CU(cudaMalloc(&v.free_slots, (size_t)ring * 4));
   *nv = v;
   return STVL_OK;
 }
 size_t pool_bytes(const GridView & v)
 {
-  return ((size_t)v.hash_mask + 1) * sizeof(HashEntry) + (size_t)v.leaf_capacity * (8 + 4 + 4 + 64 + kLeafVoxels * 8 + 8 + 4 + 4);
+  return ((size_t)v.hash_mask + 1) * sizeof(HashEntry) + (size_t)v.leaf_capacity * (8 + 4 + 4 + 64 + kLeafVoxels * 8 + 8) + ((size_t)v.free_ring_mask + 1) * 4;
 }
 void free_pool(GridView & v)
 {
   cudaFree(v.hash); cudaFree(v.leaf_key); cudaFree(v.leaf_hpos);
-  cudaFree(v.leaf_tile); cudaFree(v.leaf_mask); cudaFree(v.leaf_time); cudaFree(v.leaf_tmin); cudaFree(v.free_slots); cudaFree(v.sweep_queue);
+  cudaFree(v.leaf_tile); cudaFree(v.leaf_mask); cudaFree(v.leaf_time); cudaFree(v.leaf_tmin); cudaFree(v.free_slots);
   v.hash = nullptr; v.leaf_key = nullptr; v.leaf_hpos = nullptr;
-  v.leaf_tile = nullptr; v.leaf_mask = nullptr; v.leaf_time = nullptr; v.leaf_tmin = nullptr; v.free_slots = nullptr; v.sweep_queue = nullptr;
+  v.leaf_tile = nullptr; v.leaf_mask = nullptr; v.leaf_time = nullptr; v.leaf_tmin = nullptr; v.free_slots = nullptr;
 }
 int alloc_tiles(stvl_grid * g, uint32_t tile_capacity, GridView * nv)
 {
@@ -296,24 +319,18 @@ int clear_pool(stvl_grid * g)
   g->time_bound = 0.0;
   g->time_bound_inf = false;
   g->swept = false;
-  g->alloc_dirty = false;
+  g->mark_cursor_sel = 0;
+  g->mark_cursor_base[0] = g->mark_cursor_base[1] = 0;   // (the counters, cursors included, were just zeroed)
   return STVL_OK;
 }
 
-// fold the allocation cursor of the last Mark / load kernel into free_n / high_water (1-thread kernel, stream ordered)
-int ensure_folded(stvl_grid * g)
-{
-  if (!g->alloc_dirty) return STVL_OK;
-  CU(launch_fold_alloc(g->v, g->stream));
-  g->launches += 1;
-  g->alloc_dirty = false;
-  return STVL_OK;
-}
+// leaves in use / slots handed out, from a counter snapshot
+inline uint32_t ctr_high_water(const stvl_grid * g, const Counters & c) { return std::min<uint32_t>(c.bump, g->v.leaf_capacity); }
+inline uint32_t ctr_free_n(const Counters & c) { return c.free_push - c.free_pop; }
 
 // copy the device counters to the host mirror and wait for the stream
 int fetch_counters(stvl_grid * g)
 {
-  { int rc = ensure_folded(g); if (rc != STVL_OK) return rc; }
   CU(cudaMemcpyAsync(g->h_ctr, g->v.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, g->stream));
   CU(cudaStreamSynchronize(g->stream));
   g->last = *g->h_ctr;
@@ -326,7 +343,6 @@ int fetch_counters(stvl_grid * g)
 
 int rebuild_leaf_hash(stvl_grid * g)
 {
-  { int rc = ensure_folded(g); if (rc != STVL_OK) return rc; }
   GridView & v = g->v;
   CU(cudaMemsetAsync(v.hash, 0xFF, ((size_t)v.hash_mask + 1) * sizeof(HashEntry), g->stream));
   CU(launch_rebuild_hash(v, v.leaf_capacity, g->sm_count, g->stream));
@@ -335,7 +351,6 @@ int rebuild_leaf_hash(stvl_grid * g)
 }
 int rebuild_tiles(stvl_grid * g)
 {
-  { int rc = ensure_folded(g); if (rc != STVL_OK) return rc; }
   GridView & v = g->v;
   CU(cudaMemsetAsync(v.tile_hash_keys, 0xFF, ((size_t)v.tile_hash_mask + 1) * 8, g->stream));
   CU(cudaMemsetAsync(v.tile_hash_vals, 0xFF, ((size_t)v.tile_hash_mask + 1) * 4, g->stream));
@@ -366,10 +381,24 @@ int grow_leaves(stvl_grid * g)
   CU(cudaMemcpyAsync(nv.leaf_time, old.leaf_time, oc * kLeafVoxels * 8, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemsetAsync(nv.leaf_time + oc * kLeafVoxels, 0, (nc - oc) * kLeafVoxels * 8, s));
   CU(cudaMemcpyAsync(nv.leaf_tmin, old.leaf_tmin, oc * 8, cudaMemcpyDeviceToDevice, s));
-  CU(cudaMemcpyAsync(nv.free_slots, old.free_slots, oc * 4, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemsetAsync(&old.ctr->leaf_overflow, 0, 4, s));
+  // the bump pointer ran past the old capacity while the pool was exhausted: clamp it, and rebuild the free ring (its size
+  // changed) from the slots below it that hold no leaf
+  {
+    int rc2 = fetch_counters(g);
+    if (rc2 != STVL_OK) return rc2;
+    const uint32_t bump = std::min<uint32_t>(g->last.bump, old.leaf_capacity);
+    g->h_ctr->bump = bump; g->h_ctr->free_pop = 0; g->h_ctr->free_push = 0;
+    CU(cudaMemcpyAsync(&old.ctr->bump, &g->h_ctr->bump, 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(&old.ctr->free_pop, &g->h_ctr->free_pop, 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(&old.ctr->free_push, &g->h_ctr->free_push, 4, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));
+    g->counters_fresh = false;
+  }
   g->device_bytes += pool_bytes(nv);
   g->v = nv;
+  CU(launch_rebuild_free_ring(g->v, g->sm_count, s));
+  g->launches += 1;
   rc = rebuild_leaf_hash(g);
   if (rc != STVL_OK) return rc;
   CU(cudaStreamSynchronize(s));
@@ -396,46 +425,46 @@ int grow_tiles(stvl_grid * g)
 
 uint32_t tiles_upper(const stvl_grid * g);
 
-// The fused update cycle (stvl_update_cycle_device): the sweep's triage kernel resets the costmap bytes, the costmap pass
-// rides on the Mark kernel, and the kernels are chained by programmatic dependent launch.
+// The fused update cycle (stvl_update_cycle_device): the sweep kernel resets the costmap bytes, the costmap pass rides on
+// the Mark kernel, and the kernels are chained by programmatic dependent launch.
 struct CycleFusion {
   CostmapDev cm{};
   uint8_t * costmap = nullptr;
-  bool pdl = false;            // the Mark launch directly follows this library's sweep kernels on the stream
-  bool costmap_done = false;   // out: a Mark launch carried the costmap pass
+  bool bits = false;           // the costmap pass writes this rank's packed cell bitmap (sharded cycle)
+  bool pdl = false;            // the Mark launch directly follows this library's sweep kernel on the stream
+  bool costmap_done = false;   // out: a launch carried the costmap pass
 };
 
 int launch_batches(stvl_grid * g, const std::vector<MarkBatch> & batches, CycleFusion * fz = nullptr)
 {
   StageTimer timer__(g, STVL_TIME_MARK);
   bool pdl = fz && fz->pdl && !(g->timing_mask & STVL_TIME_MARK);
-  if (fz && fz->costmap && !fz->costmap_done && !batches.empty() && !g->alloc_dirty &&
-      (uint64_t)tiles_upper(g) > (uint64_t)mark_grid_for(batches.back(), g->sm_count) * 64u) {
+  if (fz && fz->costmap && !fz->costmap_done && !batches.empty() &&
+      (uint64_t)tiles_upper(g) > (uint64_t)mark_costmap_tiles_capacity(batches.back(), g->sm_count)) {
     // Mark's grid is too small to carry the costmap pass (small clouds, large map): the costmap kernel goes FIRST — it
-    // only needs the sweep — chained programmatically behind the leaf pass, and Mark behind it, so that Mark's cloud
-    // streaming overlaps it too (Mark's wait for this kernel implies the sweep: this kernel waited for it).
-    CU(launch_costmap(g->v, fz->cm, fz->costmap, tiles_upper(g), g->sm_count, g->stream, false, pdl));
+    // only needs the sweep — chained programmatically behind it, and Mark behind it, so that Mark's cloud streaming
+    // overlaps it too (Mark's wait for this kernel implies the sweep: this kernel waited for it).
+    CU(launch_costmap(g->v, fz->cm, fz->costmap, tiles_upper(g), g->sm_count, g->stream, false, pdl, fz->bits));
     fz->costmap_done = true;
     g->launches += 1;
   }
   for (size_t i = 0; i < batches.size(); ++i) {
-    if (g->alloc_dirty) pdl = false;   // a fold kernel goes in between
-    int rc = ensure_folded(g);   // (only a preceding bulk load leaves the allocator unfolded; Mark kernels fold themselves)
-    if (rc != STVL_OK) return rc;
-    // the costmap pass rides on four warps of every Mark CTA: only worth it when Mark's grid is large enough for the tiles
-    const bool carry = fz && fz->costmap && !fz->costmap_done && i + 1 == batches.size() &&
-                       (uint64_t)tiles_upper(g) <= (uint64_t)mark_grid_for(batches[i], g->sm_count) * 64u;
+    // the costmap pass rides on dedicated warps of every Mark CTA
+    const bool carry = fz && fz->costmap && !fz->costmap_done && i + 1 == batches.size();
     MarkBatch b = batches[i];
     b.cursor_sel = g->mark_cursor_sel;
+    b.cursor_base = g->mark_cursor_base[b.cursor_sel];
+    g->mark_cursor_base[b.cursor_sel] += mark_cursor_advance(b, g->sm_count);
     g->mark_cursor_sel ^= 1u;
     HOST_T(tm0);
-    CU(launch_mark(g->v, b, g->sm_count, g->stream, pdl, carry ? &fz->cm : nullptr, carry ? fz->costmap : nullptr));
+    CU(launch_mark(g->v, b, g->sm_count, g->stream, pdl, carry ? &fz->cm : nullptr, carry ? fz->costmap : nullptr, carry && fz->bits));
     HOST_T(tm1);
     HOST_ADD(3, tm0, tm1);
     if (carry) fz->costmap_done = true;
     pdl = false;                       // only the first launch follows the sweep
     g->launches += 1;
   }
+  CU(cudaEventRecord(g->ev_mark_done, g->stream));   // the staging buffer of host clouds is free again after this
   return STVL_OK;
 }
 
@@ -448,7 +477,7 @@ int verify_marks(stvl_grid * g)
   // everything the Marks since then can have allocated (each reading touches at most the leaves inside its
   // obstacle_range ball) still fits.  `last` is older than those Marks, frees since then only help.
   if (!g->counters_fresh) {
-    const uint64_t leaves_known = (uint64_t)g->last.high_water - g->last.free_n;
+    const uint64_t leaves_known = (uint64_t)ctr_high_water(g, g->last) - ctr_free_n(g->last);
     if (!g->last.leaf_overflow && !g->last.tile_overflow &&
         leaves_known + g->pending_leaf_bound <= g->v.leaf_capacity &&
         (uint64_t)g->last.tile_n + g->pending_tile_bound <= g->v.tile_capacity) {
@@ -488,10 +517,11 @@ int after_fetch(stvl_grid * g)
 // cycles still in flight can add.
 uint32_t slots_upper(const stvl_grid * g)
 {
-  uint64_t n = std::min<uint64_t>(g->v.leaf_capacity, (uint64_t)g->last.high_water + g->pending_leaf_bound + 1);
+  const uint64_t hw = ctr_high_water(g, g->last);
+  uint64_t n = std::min<uint64_t>(g->v.leaf_capacity, hw + g->pending_leaf_bound + 1);
   if (g->h_live && !g->counters_fresh) {
     const uint64_t live = *reinterpret_cast<const volatile uint32_t *>(&g->h_live->high_water);
-    if (live) n = std::min<uint64_t>(n, std::max<uint64_t>(live, g->last.high_water) * 5 / 4 + 8192);
+    if (live) n = std::min<uint64_t>(n, std::max<uint64_t>(live, hw) * 5 / 4 + 8192);
   }
   return (uint32_t)n;
 }
@@ -544,8 +574,15 @@ int build_batches(stvl_grid * g, const stvl_reading_t * readings, uint32_t n, co
     d.oxf = (float)d.ox; d.oyf = (float)d.oy; d.ozf = (float)d.oz;
     {
       const float m = std::fmax(std::fmax(std::fabs(d.oxf), std::fabs(d.oyf)), std::fmax(std::fabs(d.ozf), 1.0f));
-      d.range2_reject = d.mark_range_2 * 1.001f + 1e-3f + 1e-5f * m * (std::sqrt(std::fmax(d.mark_range_2, 0.f)) + 1.0f);
+      // margin >> the float evaluation error of the squared distance: ~2e-7 * d * (m + d) + 2e-7 * d^2 near d^2 = range^2
+      const float margin = d.mark_range_2 * 1e-3f + 1e-3f + 1e-5f * m * (std::sqrt(std::fmax(d.mark_range_2, 0.f)) + 1.0f);
+      d.range2_reject = d.mark_range_2 + margin;
       if (!(d.range2_reject == d.range2_reject)) d.range2_reject = INFINITY;
+      // inside [near_accept, range2_accept] the exact test (.cpp:289: !(d2 > range^2 || d2 < 0.0001)) certainly passes;
+      // NaN / negative thresholds simply send every point to the exact path
+      d.range2_accept = d.mark_range_2 - margin;
+      d.near_accept = 0.0001f + margin;
+      if (!(d.range2_accept == d.range2_accept) || !(d.near_accept == d.near_accept)) { d.range2_accept = -INFINITY; d.near_accept = INFINITY; }
     }
     d.filter = r.filter;
     d.has_tf = r.has_transform ? 1u : 0u;
@@ -707,6 +744,10 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char * (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
 };
@@ -725,8 +766,13 @@ NcclApi * nccl_api()
       api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.lib, "ncclCommInitRank"));
       api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
       api.Reduce = reinterpret_cast<decltype(api.Reduce)>(dlsym(api.lib, "ncclReduce"));
+      api.Send = reinterpret_cast<decltype(api.Send)>(dlsym(api.lib, "ncclSend"));
+      api.Recv = reinterpret_cast<decltype(api.Recv)>(dlsym(api.lib, "ncclRecv"));
+      api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(api.lib, "ncclGroupStart"));
+      api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(api.lib, "ncclGroupEnd"));
       api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
-      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Reduce && api.GetErrorString;
+      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Reduce && api.Send && api.Recv && api.GroupStart &&
+               api.GroupEnd && api.GetErrorString;
     }
   }
   return api.ok ? &api : nullptr;
@@ -770,6 +816,96 @@ int threshold_window(stvl_grid * g, int b, const stvl_costmap_params_t & p, uint
     g->launches += 1;
     g->counters_fresh = false;
   }
+  return STVL_OK;
+}
+
+// ---- bitmap merge of the sharded fused cycle ------------------------------------------------------------------------------
+// 32-cell word interval [w_lo, w_hi) of a costmap row that rank r's x-slabs can mark (hull over its slabs), for every rank
+void shard_word_intervals(stvl_grid * g, const stvl_costmap_params_t & p)
+{
+  const int n = g->comm_n, W = std::max(g->cfg.shard_width, 1);
+  const int wpr = (int)((p.size_x + 31u) >> 5);
+  // leaf-slab range that can touch the costmap's x extent
+  const double x_lo = p.origin_x - 2.0 * g->vs, x_hi = p.origin_x + (double)p.size_x * p.resolution + 2.0 * g->vs;
+  const long long sl_lo = (long long)std::floor(x_lo / (8.0 * g->vs * W)) - 1, sl_hi = (long long)std::floor(x_hi / (8.0 * g->vs * W)) + 1;
+  for (int r = 0; r < n; ++r) { g->bit_w_lo[r] = wpr; g->bit_w_hi[r] = 0; }
+  for (long long sl = sl_lo; sl <= sl_hi; ++sl) {
+    int r = (int)(sl % n); if (r < 0) r += n;
+    if (g->cfg.shard_count <= 1) r = g->comm_rank;
+    // voxel columns of the slab: ix in [sl*W*8, (sl+1)*W*8); centres at ix*vs + vs/2
+    const double cx0 = (double)(sl * W * 8) * g->vs + g->half_vs, cx1 = (double)((sl + 1) * W * 8 - 1) * g->vs + g->half_vs;
+    long long m0 = (long long)std::floor((cx0 - p.origin_x) / p.resolution) - 1, m1 = (long long)std::floor((cx1 - p.origin_x) / p.resolution) + 1;
+    if (m1 < 0 || m0 >= (long long)p.size_x) continue;
+    m0 = std::max<long long>(m0, 0); m1 = std::min<long long>(m1, (long long)p.size_x - 1);
+    g->bit_w_lo[r] = std::min<int>(g->bit_w_lo[r], (int)(m0 >> 5));
+    g->bit_w_hi[r] = std::max<int>(g->bit_w_hi[r], (int)(m1 >> 5) + 1);
+  }
+  for (int r = 0; r < n; ++r) if (g->bit_w_hi[r] <= g->bit_w_lo[r]) { g->bit_w_lo[r] = 0; g->bit_w_hi[r] = 0; }   // nothing of rank r maps here
+}
+
+// every non-root rank sends its bitmap `b`, the root receives them back to back into its staging area (one NCCL group)
+int exchange_bits(stvl_grid * g, int b, uint32_t size_y, int root, cudaStream_t xs)
+{
+  NcclApi * n = nccl_api();
+  if (g->comm_n == 1) return STVL_OK;
+  if (g->comm_rank != root) {
+    const size_t words = (size_t)(g->bit_w_hi[g->comm_rank] - g->bit_w_lo[g->comm_rank]) * size_y;
+    if (words) NC(n->Send(g->bits[b].p, words, ncclUint32, root, g->comm, xs));
+    return STVL_OK;
+  }
+  NC(n->GroupStart());
+  size_t off = 0;
+  for (int r = 0; r < g->comm_n; ++r) {
+    if (r == root) continue;
+    const size_t words = (size_t)(g->bit_w_hi[r] - g->bit_w_lo[r]) * size_y;
+    if (words) NC(n->Recv(g->bits_stage[b].p + off, words, ncclUint32, r, g->comm, xs));
+    off += words;
+  }
+  NC(n->GroupEnd());
+  return STVL_OK;
+}
+
+int launch_expand(stvl_grid * g, int b, const stvl_costmap_params_t & p, uint8_t * costmap_dev, int root, cudaStream_t xs)
+{
+  ExpandParams e{};
+  e.n_ranks = g->comm_n;
+  size_t off = 0;
+  for (int r = 0; r < g->comm_n; ++r) {
+    e.w_lo[r] = g->bit_w_lo[r]; e.w_hi[r] = g->bit_w_hi[r];
+    if (r == root) e.bits[r] = g->bits[b].p;
+    else { e.bits[r] = g->bits_stage[b].p + off; off += (size_t)(g->bit_w_hi[r] - g->bit_w_lo[r]) * p.size_y; }
+  }
+  CU(launch_expand_bitmaps(e, to_dev(p), costmap_dev, g->sm_count, xs));
+  g->launches += 1;
+  return STVL_OK;
+}
+
+// root: expand the pending bitmaps into costmap bytes on the MAIN stream (blocking mode, flush)
+int expand_pending_bits(stvl_grid * g, const stvl_costmap_params_t & p, uint8_t * costmap_dev, int root)
+{
+  if (g->bits_pending < 0) return STVL_OK;
+  const int b = g->bits_pending;
+  g->bits_pending = -1;
+  CU(cudaStreamWaitEvent(g->stream, g->ev_bits_done[b], 0));
+  if (g->comm_rank == root && costmap_dev) return launch_expand(g, b, p, costmap_dev, root, g->stream);
+  return STVL_OK;
+}
+
+// root: expand the pending bitmaps on the SIDE stream, not before everything enqueued on the main stream so far is done;
+// the caller makes the main stream wait for ev_expand at the end of its own enqueue
+int expand_pending_bits_async(stvl_grid * g, const stvl_costmap_params_t & p, uint8_t * costmap_dev, int root)
+{
+  const int b = g->bits_pending;
+  g->bits_pending = -1;
+  g->bits_expanding = -1;
+  if (b < 0 || g->comm_rank != root || !costmap_dev) return STVL_OK;
+  CU(cudaEventRecord(g->ev_main_pos, g->stream));
+  CU(cudaStreamWaitEvent(g->merge_stream, g->ev_main_pos, 0));
+  // (the exchange of buffer b was enqueued on the side stream: stream order covers it)
+  int rc = launch_expand(g, b, p, costmap_dev, root, g->merge_stream);
+  if (rc != STVL_OK) return rc;
+  CU(cudaEventRecord(g->ev_expand[b], g->merge_stream));
+  g->bits_expanding = b;
   return STVL_OK;
 }
 
@@ -879,6 +1015,7 @@ int stvl_destroy(stvl_grid_t * g)
   if (g->copy_stream) cudaStreamSynchronize(g->copy_stream);
   if (g->comm) stvl_comm_destroy(g);
   cudaFree(g->window[0].p); cudaFree(g->window[1].p);
+  cudaFree(g->bits[0].p); cudaFree(g->bits[1].p); cudaFree(g->bits_stage[0].p); cudaFree(g->bits_stage[1].p);
   free_pool(g->v);
   free_tiles(g->v);
   cudaFree(g->v.ctr);
@@ -894,6 +1031,14 @@ int stvl_destroy(stvl_grid_t * g)
   }
   for (auto & iv : g->timing_pending) { cudaEventDestroy(iv.a); cudaEventDestroy(iv.b); }
   for (auto e : g->timing_pool) cudaEventDestroy(e);
+  for (auto & a : g->aslot) {
+    cudaFree(a.stage.p); cudaFree(a.costmap.p); cudaFree(a.d_res);
+    if (a.h_res) cudaFreeHost(a.h_res);
+    if (a.ev_h2d) cudaEventDestroy(a.ev_h2d);
+    if (a.ev_cycle) cudaEventDestroy(a.ev_cycle);
+    if (a.ev_d2h) cudaEventDestroy(a.ev_d2h);
+  }
+  if (g->d2h_stream) cudaStreamDestroy(g->d2h_stream);
   if (g->ev_copy_done) cudaEventDestroy(g->ev_copy_done);
   if (g->ev_mark_done) cudaEventDestroy(g->ev_mark_done);
   if (g->stream) cudaStreamDestroy(g->stream);
@@ -1009,21 +1154,24 @@ int clear_frustums_impl(stvl_grid * g, double now, const stvl_frustum_t * frustu
     rc = ensure(g, g->ambiguous, cap * 3); if (rc != STVL_OK) return rc;
     out.ambiguous = g->ambiguous.p; out.ambiguous_cap = cap;
   }
-  rc = ensure_folded(g);
-  if (rc != STVL_OK) return rc;
   select_sweep_buffers(g, g->sweep_parity ^ 1);   // this sweep's tile buffer / counter set (re-armed by the previous sweep)
   StageTimer timer__(g, STVL_TIME_SWEEP);
   if (fz && fz->costmap) {
     HOST_T(ts0);
-    CU(launch_sweep(g->v, frustums_dev, &fparam, (int)n_frustums, now, out, slots_upper(g), g->sm_count, g->stream, fz->costmap,
-                    (size_t)fz->cm.size_x * fz->cm.size_y, (int)fz->cm.default_value));
+    // fused cycle: the sweep also resets the costmap bytes (or this rank's cell bitmap) and shares the SMs with the Mark
+    // kernel that streams its clouds behind it
+    const size_t reset_bytes = fz->bits ? (size_t)fz->cm.bit_wpr * 4u * fz->cm.size_y : (size_t)fz->cm.size_x * fz->cm.size_y;
+    CU(launch_sweep(g->v, frustums_dev, &fparam, (int)n_frustums, now, out, slots_upper(g), g->sm_count, g->stream, true, true, fz->costmap,
+                    reset_bytes, fz->bits ? 0 : (int)fz->cm.default_value));
     HOST_T(ts1);
     HOST_ADD(2, ts0, ts1);
-    fz->pdl = !(g->timing_mask & STVL_TIME_SWEEP);   // nothing may be enqueued between the leaf pass and Mark
+    fz->pdl = !(g->timing_mask & STVL_TIME_SWEEP);   // nothing may be enqueued between the sweep and Mark
   } else {
-    CU(launch_sweep(g->v, frustums_dev, &fparam, (int)n_frustums, now, out, slots_upper(g), g->sm_count, g->stream));
+    // (the programmatic attribute is safe whatever precedes the sweep on the stream: before its wait it only reads kernel
+    // parameters / the frustum buffer)
+    CU(launch_sweep(g->v, frustums_dev, &fparam, (int)n_frustums, now, out, slots_upper(g), g->sm_count, g->stream, true, false));
   }
-  g->launches += 2;
+  g->launches += 1;
   g->counters_fresh = false;
   g->swept = true;
   g->added_since_sweep = 0;
@@ -1058,8 +1206,7 @@ int stvl_mark(stvl_grid_t * g, const stvl_reading_t * readings, uint32_t n_readi
   if (rc != STVL_OK) return rc;
   // H2D on the copy stream (overlaps a sweep still running on the main stream); the staging buffer may only be
   // overwritten once the previous Mark kernel has consumed it
-  CU(cudaEventRecord(g->ev_mark_done, g->stream));   // everything enqueued so far, the previous Mark kernel included
-  CU(cudaStreamWaitEvent(g->copy_stream, g->ev_mark_done, 0));
+  CU(cudaStreamWaitEvent(g->copy_stream, g->ev_mark_done, 0));   // recorded right behind the previous Mark's launches: the copy overlaps this cycle's sweep
   std::vector<const uint8_t *> dev_ptrs(n_readings, nullptr);
   for (uint32_t i = 0; i < n_readings; ++i) {
     const stvl_reading_t & r = readings[i];
@@ -1243,8 +1390,6 @@ int stvl_reset_area(stvl_grid_t * g, double start_x, double start_y, double end_
   ENTER(g);
   int rc = verify_marks(g);
   if (rc != STVL_OK) return rc;
-  rc = ensure_folded(g);
-  if (rc != STVL_OK) return rc;
   CU(launch_reset_area(g->v, start_x, start_y, end_x, end_y, invert_area, slots_upper(g), g->sm_count, g->stream));
   g->launches += 1;
   return STVL_OK;
@@ -1255,8 +1400,6 @@ int stvl_active_count(stvl_grid_t * g, uint64_t * n)
   ENTER(g);
   if (!n) return fail(STVL_ERR_INVALID, "n is NULL");
   int rc = verify_marks(g);
-  if (rc != STVL_OK) return rc;
-  rc = ensure_folded(g);
   if (rc != STVL_OK) return rc;
   CU(cudaMemsetAsync(&g->v.ctr->n_active, 0, 8, g->stream));
   CU(cudaMemsetAsync(&g->v.ctr->live_leaves, 0, 4, g->stream));
@@ -1281,8 +1424,6 @@ int stvl_get_voxels(stvl_grid_t * g, int32_t * ix, int32_t * iy, int32_t * iz, d
     rc = ensure(g, g->dump_z, cap); if (rc != STVL_OK) return rc;
     rc = ensure(g, g->dump_t, cap); if (rc != STVL_OK) return rc;
   }
-  rc = ensure_folded(g);
-  if (rc != STVL_OK) return rc;
   CU(cudaMemsetAsync(&g->v.ctr->n_voxels_out, 0, 8, g->stream));
   CU(launch_dump_voxels(g->v, cap ? g->dump_x.p : nullptr, cap ? g->dump_y.p : nullptr, cap ? g->dump_z.p : nullptr,
                         cap ? g->dump_t.p : nullptr, cap, slots_upper(g), g->sm_count, g->stream));
@@ -1319,11 +1460,8 @@ int stvl_load_voxels(stvl_grid_t * g, const int32_t * ix, const int32_t * iy, co
   double tmax = -std::numeric_limits<double>::infinity();
   for (uint64_t i = 0; i < n; ++i) tmax = std::max(tmax, t[i]);
   for (int attempt = 0; attempt < 32; ++attempt) {
-    rc = ensure_folded(g);
-    if (rc != STVL_OK) return rc;
     CU(launch_load_voxels(g->v, g->dump_x.p, g->dump_y.p, g->dump_z.p, g->dump_t.p, n, g->stream));
     g->launches += 1;
-    g->alloc_dirty = true;
     rc = fetch_counters(g);
     if (rc != STVL_OK) return rc;
     if (!g->last.leaf_overflow && !g->last.tile_overflow) break;
@@ -1395,7 +1533,12 @@ int stvl_comm_init(stvl_grid_t * g, const uint8_t id[128], int rank, int n_ranks
   for (int k = 0; k < 2; ++k) {
     CU(cudaEventCreateWithFlags(&g->ev_scatter[k], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&g->ev_reduce[k], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&g->ev_bits_done[k], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&g->ev_expand[k], cudaEventDisableTiming));
   }
+  CU(cudaEventCreateWithFlags(&g->ev_main_pos, cudaEventDisableTiming));
+  g->bits_geom_valid = false;
+  g->bits_pending = -1;
   return STVL_OK;
 }
 
@@ -1407,7 +1550,12 @@ int stvl_comm_destroy(stvl_grid_t * g)
   CU(cudaStreamSynchronize(g->merge_stream));
   nccl_api()->CommDestroy(g->comm);
   g->comm = nullptr;
-  for (int k = 0; k < 2; ++k) { cudaEventDestroy(g->ev_scatter[k]); cudaEventDestroy(g->ev_reduce[k]); g->ev_scatter[k] = g->ev_reduce[k] = nullptr; }
+  for (int k = 0; k < 2; ++k) {
+    cudaEventDestroy(g->ev_scatter[k]); cudaEventDestroy(g->ev_reduce[k]); cudaEventDestroy(g->ev_bits_done[k]); cudaEventDestroy(g->ev_expand[k]);
+    g->ev_scatter[k] = g->ev_reduce[k] = g->ev_bits_done[k] = g->ev_expand[k] = nullptr;
+  }
+  cudaEventDestroy(g->ev_main_pos); g->ev_main_pos = nullptr;
+  g->bits_pending = -1;
   cudaStreamDestroy(g->merge_stream);
   g->merge_stream = nullptr;
   g->win_pending = -1;
@@ -1485,6 +1633,10 @@ int stvl_costmap_sharded_flush(stvl_grid_t * g, const stvl_costmap_params_t * p,
   ENTER(g);
   if (!p) return fail(STVL_ERR_INVALID, "NULL argument");
   if (!g->comm) return fail(STVL_ERR_INVALID, "stvl_comm_init has not been called");
+  if (g->bits_pending >= 0) {   // the sharded fused cycle's bitmap exchange: expand the last cycle's cells now
+    int rc = expand_pending_bits(g, *p, costmap_dev, root);
+    if (rc != STVL_OK) return rc;
+  }
   if (g->win_pending < 0) return STVL_OK;
   const int b = g->win_pending;
   g->win_pending = -1;
@@ -1500,8 +1652,8 @@ int stvl_get_pool_stats(stvl_grid_t * g, stvl_pool_stats_t * out)
   std::memset(out, 0, sizeof(*out));
   const Counters & c = g->last;
   out->leaf_capacity = g->v.leaf_capacity;
-  out->leaves_free = c.free_n;
-  out->leaves_in_use = c.high_water - c.free_n;
+  out->leaves_free = ctr_free_n(c);
+  out->leaves_in_use = ctr_high_water(g, c) - ctr_free_n(c);
   out->hash_capacity = (uint64_t)g->v.hash_mask + 1;
   out->hash_tombstones = c.n_tombs;
   out->tiles_in_use = c.tile_n;
@@ -1519,7 +1671,7 @@ namespace {
 // waits for the sweep before it touches the grid) and the costmap pass rides on the Mark kernel.  The clouds must be
 // complete on the device before this call is enqueued (stream order on stvl_get_stream() is enough).
 int fused_cycle(stvl_grid * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums, const stvl_reading_t * readings,
-                uint32_t n_readings, const CostmapDev & cm, uint8_t * costmap_dev)
+                uint32_t n_readings, const CostmapDev & cm, uint8_t * costmap_dev, bool bits = false)
 {
   HOST_T(t0);
   int rc = validate_readings(readings, n_readings);
@@ -1527,6 +1679,7 @@ int fused_cycle(stvl_grid * g, double now, const stvl_frustum_t * frustums, uint
   CycleFusion fz;
   fz.cm = cm;
   fz.costmap = costmap_dev;
+  fz.bits = bits;
   rc = clear_frustums_impl(g, now, frustums, n_frustums, &fz);
   if (rc != STVL_OK) return rc;
   HOST_T(t1);
@@ -1541,7 +1694,7 @@ int fused_cycle(stvl_grid * g, double now, const stvl_frustum_t * frustums, uint
 #endif
   if (!fz.costmap_done) {   // nothing to mark in this cycle: the plain costmap kernel (the bytes are reset already)
     StageTimer timer__(g, STVL_TIME_COSTMAP);
-    CU(launch_costmap(g->v, fz.cm, costmap_dev, tiles_upper(g), g->sm_count, g->stream, false));
+    CU(launch_costmap(g->v, fz.cm, costmap_dev, tiles_upper(g), g->sm_count, g->stream, false, false, bits));
     g->launches += 1;
   }
   g->counters_fresh = false;
@@ -1567,45 +1720,147 @@ int stvl_update_cycle_sharded_device(stvl_grid_t * g, double now, const stvl_fru
   if (!p) return fail(STVL_ERR_INVALID, "NULL argument");
   if (!g->comm) return fail(STVL_ERR_INVALID, "stvl_comm_init has not been called");
   if (root < 0 || root >= g->comm_n) return fail(STVL_ERR_INVALID, "bad root");
+  if (g->comm_n > kMaxShardRanks) return fail(STVL_ERR_INVALID, "at most %d ranks", kMaxShardRanks);
   if (!(p->resolution > 0)) return fail(STVL_ERR_INVALID, "resolution must be positive");
-  // bytes mode of stvl_costmap_sharded_device with the fused cycle in front of it: the cycle's costmap pass writes this
-  // rank's {0, lethal} bytes straight into the reduce window
-  const int geom[4] = {0, 0, (int)p->size_x, (int)p->size_y};
-  const size_t cells = (size_t)p->size_x * p->size_y;
-  if (g->win_pending >= 0 && (g->win_count_bytes != 0 || std::memcmp(geom, g->win_geom, sizeof(geom)) != 0)) {
-    int rc = stvl_costmap_sharded_flush(g, p, nullptr, root);
+  if (g->comm_rank == root && !costmap_dev) return fail(STVL_ERR_INVALID, "costmap_dev is NULL on the root rank");
+  // x-slab shards own whole voxel columns, so the merged costmap is the union of the ranks' lethal cells: every rank's
+  // costmap pass writes a packed BITMAP of the cells of its own x interval (1 bit per cell instead of a byte, and only the
+  // rank's own interval instead of an N-times window), the bitmaps travel to the root with one grouped ncclSend / ncclRecv
+  // on a side stream, and the root expands them into bytes (which is also its Costmap2D::resetMaps).
+  if (g->bits_pending >= 0 && (!g->bits_geom_valid || std::memcmp(&g->bits_params, p, sizeof(*p)) != 0)) {
+    int rc = expand_pending_bits(g, g->bits_params, costmap_dev, root);   // the costmap moved or changed size: finish the old one first
     if (rc != STVL_OK) return rc;
   }
-  const int b = (int)(g->win_k & 1);
-  if (g->window[b].cap < cells) {
+  if (!g->bits_geom_valid || std::memcmp(&g->bits_params, p, sizeof(*p)) != 0) {
     CU(cudaStreamSynchronize(g->merge_stream));
-    int rc = ensure(g, g->window[b], cells);
+    shard_word_intervals(g, *p);
+    g->bits_params = *p;
+    g->bits_geom_valid = true;
+  }
+  const int me = g->comm_rank;
+  const size_t my_words = (size_t)(g->bit_w_hi[me] - g->bit_w_lo[me]) * p->size_y;
+  size_t stage_words = 0;
+  for (int r = 0; r < g->comm_n; ++r) if (r != root) stage_words += (size_t)(g->bit_w_hi[r] - g->bit_w_lo[r]) * p->size_y;
+  const int b = (int)(g->bits_k & 1);
+  if (g->bits[b].cap < std::max<size_t>(my_words, 1) || (me == root && g->bits_stage[b].cap < std::max<size_t>(stage_words, 1))) {
+    CU(cudaStreamSynchronize(g->merge_stream));
+    int rc = ensure(g, g->bits[b], std::max<size_t>(my_words, 1)); if (rc != STVL_OK) return rc;
+    if (me == root) { rc = ensure(g, g->bits_stage[b], std::max<size_t>(stage_words, 1)); if (rc != STVL_OK) return rc; }
+  }
+  if (pipelined && g->bits_pending >= 0) {
+    // cycle k-1's cells: expanded on the side stream while this cycle's kernels run on the main one.  The expansion must
+    // not start before everything the caller enqueued so far (reads of cycle k-2's bytes) is done ...
+    int rc = expand_pending_bits_async(g, *p, costmap_dev, root);
     if (rc != STVL_OK) return rc;
   }
-  std::memcpy(g->win_geom, geom, sizeof(geom));
-  g->win_count_bytes = 0;
-  CU(cudaStreamWaitEvent(g->stream, g->ev_reduce[b], 0));   // the reduce that used this window two calls ago
+  CU(cudaStreamWaitEvent(g->stream, g->ev_bits_done[b], 0));   // the exchange that used this bitmap two cycles ago
   CostmapDev d = to_dev(*p);
-  d.default_value = 0;
-  int rc = fused_cycle(g, now, frustums, n_frustums, readings, n_readings, d, g->window[b].p);
+  d.bit_w_lo = g->bit_w_lo[me];
+  d.bit_wpr = g->bit_w_hi[me] - g->bit_w_lo[me];
+  int rc = fused_cycle(g, now, frustums, n_frustums, readings, n_readings, d, reinterpret_cast<uint8_t *>(g->bits[b].p), true);
   if (rc != STVL_OK) return rc;
-  CU(cudaEventRecord(g->ev_scatter[b], g->stream));
-  NcclApi * n = nccl_api();
-  g->win_k += 1;
-  if (!pipelined) {
-    if (g->win_pending >= 0) { rc = threshold_window(g, g->win_pending, *p, nullptr, root); if (rc != STVL_OK) return rc; g->win_pending = -1; }
-    NC(n->Reduce(g->window[b].p, g->window[b].p, cells, ncclUint8, ncclMax, root, g->comm, g->stream));
-    CU(cudaEventRecord(g->ev_reduce[b], g->stream));
-    return threshold_window(g, b, *p, costmap_dev, root);
+  g->bits_k += 1;
+  cudaStream_t xs = pipelined ? g->merge_stream : g->stream;
+  if (pipelined) {
+    CU(cudaEventRecord(g->ev_scatter[b], g->stream));
+    CU(cudaStreamWaitEvent(g->merge_stream, g->ev_scatter[b], 0));
   }
-  CU(cudaStreamWaitEvent(g->merge_stream, g->ev_scatter[b], 0));
-  NC(n->Reduce(g->window[b].p, g->window[b].p, cells, ncclUint8, ncclMax, root, g->comm, g->merge_stream));
-  CU(cudaEventRecord(g->ev_reduce[b], g->merge_stream));
-  if (g->win_pending >= 0) {
-    rc = threshold_window(g, g->win_pending, *p, costmap_dev, root);   // the PREVIOUS cycle's bytes
-    if (rc != STVL_OK) return rc;
+  rc = exchange_bits(g, b, p->size_y, root, xs);
+  if (rc != STVL_OK) return rc;
+  CU(cudaEventRecord(g->ev_bits_done[b], xs));
+  if (pipelined) {
+    // ... and this call returns with the main stream ordered behind the expansion of cycle k-1: what the caller enqueues
+    // next sees cycle k-1's bytes
+    if (g->bits_expanding >= 0) { CU(cudaStreamWaitEvent(g->stream, g->ev_expand[g->bits_expanding], 0)); g->bits_expanding = -1; }
+    g->bits_pending = b;
+    return STVL_OK;
   }
-  g->win_pending = b;
+  g->bits_pending = b;
+  return expand_pending_bits(g, *p, costmap_dev, root);
+}
+
+int stvl_update_cycle_wait(stvl_grid_t * g, uint64_t ticket, stvl_costmap_result_t * res)
+{
+  ENTER(g);
+  for (auto & a : g->aslot) {
+    if (!a.busy || a.ticket != ticket) continue;
+    CU(cudaEventSynchronize(a.ev_d2h));
+    a.busy = false;
+    if (res) {
+      std::memset(res, 0, sizeof(*res));
+      res->n_marked_columns = a.h_res->n_marked;
+      res->has_bounds = a.h_res->n_marked > 0;
+      if (res->has_bounds) {
+        const int32_t idx[4] = {a.h_res->mk_min_x, a.h_res->mk_min_y, a.h_res->mk_max_x, a.h_res->mk_max_y};
+        world_bbox(g, idx, res->touched);
+      }
+    }
+    return STVL_OK;
+  }
+  return fail(STVL_ERR_INVALID, "ticket %llu is not in flight", (unsigned long long)ticket);
+}
+
+int stvl_update_cycle_async(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
+                            const stvl_reading_t * readings, uint32_t n_readings,
+                            const stvl_costmap_params_t * p, uint8_t * costmap_host, uint64_t * ticket)
+{
+  ENTER(g);
+  if (!p || !ticket) return fail(STVL_ERR_INVALID, "NULL argument");
+  if (!(p->resolution > 0)) return fail(STVL_ERR_INVALID, "resolution must be positive");
+  int rc = validate_readings(readings, n_readings);
+  if (rc != STVL_OK) return rc;
+  const uint64_t t = g->next_ticket;
+  stvl_grid::AsyncSlot & a = g->aslot[t & 1];
+  if (a.busy) {   // two cycles in flight already: the older one has to finish (its result is dropped unless it was waited for)
+    CU(cudaEventSynchronize(a.ev_d2h));
+    a.busy = false;
+  }
+  if (!a.ev_h2d) {
+    CU(cudaEventCreateWithFlags(&a.ev_h2d, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&a.ev_cycle, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&a.ev_d2h, cudaEventDisableTiming));
+    CU(cudaMalloc(&a.d_res, sizeof(CostmapCtr)));
+    CU(cudaMallocHost(&a.h_res, sizeof(CostmapCtr)));
+    if (!g->d2h_stream) CU(cudaStreamCreateWithFlags(&g->d2h_stream, cudaStreamNonBlocking));
+  }
+  // staging layout of this cycle's clouds
+  size_t total = 0;
+  std::vector<size_t> offs(n_readings, 0);
+  for (uint32_t i = 0; i < n_readings; ++i) {
+    const stvl_reading_t & r = readings[i];
+    if (!r.marking || r.n_points == 0) continue;
+    offs[i] = total;
+    total += ((size_t)r.n_points * r.point_step + 255) & ~(size_t)255;
+  }
+  const size_t bytes = (size_t)p->size_x * p->size_y;
+  rc = ensure(g, a.stage, std::max<size_t>(total, 1)); if (rc != STVL_OK) return rc;
+  rc = ensure(g, a.costmap, std::max<size_t>(bytes, 1)); if (rc != STVL_OK) return rc;
+  // H2D on the copy stream: the staging buffer is free once the Mark kernel of the cycle that used it (two cycles ago) has run
+  CU(cudaStreamWaitEvent(g->copy_stream, a.ev_cycle, 0));
+  std::vector<stvl_reading_t> rs(readings, readings + n_readings);
+  for (uint32_t i = 0; i < n_readings; ++i) {
+    const stvl_reading_t & r = readings[i];
+    if (!r.marking || r.n_points == 0) continue;
+    CU(cudaMemcpyAsync(a.stage.p + offs[i], r.data, (size_t)r.n_points * r.point_step, cudaMemcpyHostToDevice, g->copy_stream));
+    rs[i].data = a.stage.p + offs[i];
+  }
+  CU(cudaEventRecord(a.ev_h2d, g->copy_stream));
+  // the fused cycle on the main stream; the device costmap of this slot is free once its previous read-back is done
+  CU(cudaStreamWaitEvent(g->stream, a.ev_h2d, 0));
+  CU(cudaStreamWaitEvent(g->stream, a.ev_d2h, 0));
+  rc = fused_cycle(g, now, frustums, n_frustums, rs.data(), n_readings, to_dev(*p), a.costmap.p);
+  if (rc != STVL_OK) return rc;
+  CU(cudaMemcpyAsync(a.d_res, &g->v.ctr->cm, sizeof(CostmapCtr), cudaMemcpyDeviceToDevice, g->stream));
+  CU(cudaEventRecord(a.ev_cycle, g->stream));
+  // D2H on its own stream: overlaps the next cycle's kernels and H2D copy
+  CU(cudaStreamWaitEvent(g->d2h_stream, a.ev_cycle, 0));
+  if (costmap_host && bytes) CU(cudaMemcpyAsync(costmap_host, a.costmap.p, bytes, cudaMemcpyDeviceToHost, g->d2h_stream));
+  CU(cudaMemcpyAsync(a.h_res, a.d_res, sizeof(CostmapCtr), cudaMemcpyDeviceToHost, g->d2h_stream));
+  CU(cudaEventRecord(a.ev_d2h, g->d2h_stream));
+  a.busy = true;
+  a.ticket = t;
+  g->next_ticket = t + 1;
+  *ticket = t;
   return STVL_OK;
 }
 

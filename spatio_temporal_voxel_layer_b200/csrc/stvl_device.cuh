@@ -42,31 +42,27 @@ struct CostmapCtr {
   int32_t mk_min_x, mk_min_y, mk_max_x, mk_max_y;
 };
 struct Counters {
-  // leaf pool allocator
-  uint32_t alloc_cursor;   // leaves requested by the running Mark kernel
-  uint32_t free_n;         // entries on the free stack
-  uint32_t high_water;     // slots [0, high_water) have been handed out at least once
+  // leaf pool allocator, fold-free: a slot comes from the free ring (entries [free_pop, free_push) of free_slots, indices
+  // taken modulo the ring size) and, when that is empty, from the bump pointer.  Mark / load kernels only pop and bump,
+  // sweeps only push, and the two never run concurrently on a handle.
+  uint32_t free_pop, free_push;   // monotone (wrapping) counters
+  uint32_t bump;           // slots [0, min(bump, capacity)) have been handed out at least once
   uint32_t n_tombs;        // tombstones in the leaf hash
   uint32_t leaf_overflow;  // a Mark ran out of leaves (host grows the pool and replays)
-  uint32_t queue_n;        // leaves queued by the sweep's triage pass for the per-voxel pass
   // tile pool
   uint32_t tile_n;
   uint32_t tile_overflow;
-  // last-CTA-done tickets (each kernel's last CTA commits / re-arms shared state)
-  uint32_t mark_ticket, leaf_ticket, cm_ticket;
-  uint32_t dense_n;        // leaves with more than one 32-voxel batch queued for pass 2, stored from the END of sweep_queue (a CTA each)
-  // next unclaimed 1024-point chunk of the running Mark kernel, re-armed by its last CTA.  Two cursors used alternately:
-  // under programmatic dependent launch the first CTAs of the next cycle's Mark may pull chunks while the last CTA of
-  // this one has not re-armed its cursor yet
+  uint32_t cm_ticket;      // last-CTA-done ticket of the costmap pass (its last CTA publishes cm_acc -> cm)
+  // next unclaimed 1024-point chunk of the running Mark kernel.  Never reset: launch k uses cursor k&1 relative to a base
+  // the host tracks (every CTA of a launch stops at its first out-of-range id, so a launch advances its cursor by exactly
+  // total_chunks + gridDim).  Two cursors because consecutive Mark launches may overlap under programmatic dependent launch.
   uint32_t mark_cursor[2];
+  uint32_t pad1[2];
   // dropped input points
   unsigned long long dropped_range, dropped_nonfinite;
-  // Mark's last-CTA ticket: low 16 bits count the CTAs that are done, the upper 48 accumulate their non-finite point
-  // counts (one atomic per CTA for both; the last CTA folds the sum into dropped_nonfinite and re-arms it)
-  unsigned long long mark_ticket64;
   SweepCtr sw[2];
-  CostmapCtr cm_acc;       // accumulators of the running costmap kernel
-  CostmapCtr cm;           // published result of the last costmap kernel
+  CostmapCtr cm_acc;       // accumulators of the running costmap pass
+  CostmapCtr cm;           // published result of the last costmap pass
   unsigned long long n_columns_out;
   // dumps
   unsigned long long n_voxels_out, n_active;
@@ -78,7 +74,7 @@ struct Counters {
 // stores over PCIe, no stream operation): the host sizes its grids from them between synchronisations.  Estimates
 // only — every kernel takes its real extents from Counters on the device and strides over them.
 struct LiveCounters {
-  uint32_t high_water, free_n, tile_n, seq;
+  uint32_t high_water, free_n, tile_n, seq;   // high_water = min(bump, capacity), free_n = free_push - free_pop
 };
 
 struct __align__(16) HashEntry {
@@ -100,8 +96,8 @@ struct GridView {
   double * leaf_time;      // 512 per leaf
   double * leaf_tmin;      // lower bound of the mark times stored in the leaf (-inf = unknown): lets a sweep skip the
                            // 4 KB time block of leaves in which nothing can expire
-  uint32_t * free_slots;
-  uint32_t * sweep_queue;  // leaf slots that need the per-voxel pass of the current sweep
+  uint32_t * free_slots;   // free ring, free_ring_mask + 1 entries (a power of two >= leaf_capacity)
+  uint32_t free_ring_mask;
   uint32_t leaf_capacity;
   // column tiles
   uint64_t * tile_hash_keys;
@@ -150,7 +146,9 @@ struct DevReading {
   float mark_range_2;
   int32_t filter;         // STVL_FILTER_PASSTHROUGH applies the z window in-kernel
   float zmin_f, zmax_f;   // float thresholds EXACTLY equivalent to the double window for float z: zmin rounded up, zmax rounded down
-  float range2_reject;    // single-precision screen: a float distance^2 above this is certainly out of range
+  float range2_reject;    // single-precision screen: a float distance^2 above this is certainly out of range ...
+  float range2_accept;    // ... and one inside [near_accept, range2_accept] certainly passes the reference's exact test;
+  float near_accept;      //     anything else takes the exact double path
   float oxf, oyf, ozf;    // (float) origin, for that screen
   float tf[12];           // sensor -> global float affine (row-major 3x4), applied first when has_tf
   uint32_t has_tf;
@@ -165,7 +163,7 @@ struct MarkBatch {
   uint32_t use_atomic_max;  // 1: batched mode (monotone clocks), 0: plain stores
   int32_t ref_bx;           // reference leaf x of the batch (first reading's origin): block-local table keys store bx - ref_bx
   uint32_t cursor_sel;      // which Counters::mark_cursor this launch uses (set at launch)
-  uint32_t pad;
+  uint32_t cursor_base;     // value of that cursor when this launch starts (set at launch)
   double min_now;           // smallest clock sample in the batch: initial leaf_tmin of leaves created by it
 };
 

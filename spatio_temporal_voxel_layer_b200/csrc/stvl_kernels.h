@@ -22,6 +22,20 @@ struct CostmapDev {
   uint32_t size_x, size_y;
   int32_t mark_threshold;
   uint8_t default_value, lethal;
+  // bitmap output (sharded cycle): this rank's packed cell bitmap has size_y rows of bit_wpr words and covers the 32-cell
+  // words [bit_w_lo, bit_w_lo + bit_wpr) of a costmap row
+  int32_t bit_w_lo, bit_wpr;
+};
+
+// sharded cycle: the per-rank cell bitmaps the root expands into costmap bytes.  Rank r's bitmap is packed: size_y rows of
+// (w_hi - w_lo) words covering the 32-cell words [w_lo, w_hi) of a costmap row — the x interval its shard can mark (bit
+// mx & 31 of word mx >> 5 = cell (mx, my) is lethal).
+constexpr int kMaxShardRanks = 16;
+struct ExpandParams {
+  const uint32_t * bits[kMaxShardRanks];
+  int32_t w_lo[kMaxShardRanks], w_hi[kMaxShardRanks];   // word interval per row that rank r owns (and sends)
+  int32_t n_ranks;
+  int32_t pad;
 };
 
 // updateCosts on device byte grids (stvl_costs.cu)
@@ -36,18 +50,22 @@ cudaError_t launch_polygon_cost(uint8_t * costmap_dev, const CostmapDev & p, con
 cudaError_t launch_update_costs(const uint8_t * layer_dev, uint8_t * master_dev, uint32_t size_x, int min_i, int min_j, int max_i, int max_j,
                                 int method, int sm_count, cudaStream_t s);
 
-cudaError_t launch_fold_alloc(const GridView & g, cudaStream_t s);
+// batch.cursor_sel / batch.cursor_base must be set by the caller; the launch advances that cursor by mark_cursor_advance()
 cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s, bool pdl = false,
-                        const CostmapDev * fused_costmap = nullptr, uint8_t * costmap_dev = nullptr);
+                        const CostmapDev * fused_costmap = nullptr, uint8_t * costmap_dev = nullptr, bool costmap_bits = false);
 uint32_t mark_blocks_for(unsigned long long n_points);
 uint32_t mark_grid_for(const MarkBatch & batch, int sm_count);
+uint32_t mark_cursor_advance(const MarkBatch & batch, int sm_count);
+uint32_t mark_costmap_tiles_capacity(const MarkBatch & batch, int sm_count);
 cudaError_t launch_load_voxels(const GridView & g, const int32_t * x, const int32_t * y, const int32_t * z, const double * t,
                                unsigned long long n, cudaStream_t s);
 cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, const FrustumParams * fparam, int n_frustums, double now,
-                         const SweepOutputs & out, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s,
+                         const SweepOutputs & out, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s, bool pdl, bool share_sms,
                          uint8_t * costmap_reset = nullptr, size_t costmap_bytes = 0, int costmap_value = 0);
 cudaError_t launch_costmap(const GridView & g, const CostmapDev & p, uint8_t * costmap_dev, uint32_t tiles_upper_bound, int sm_count, cudaStream_t s,
-                           bool fill_default, bool pdl = false);
+                           bool fill_default, bool pdl = false, bool bits = false);
+cudaError_t launch_expand_bitmaps(const ExpandParams & e, const CostmapDev & p, uint8_t * costmap_dev, int sm_count, cudaStream_t s);
+cudaError_t launch_rebuild_free_ring(const GridView & g, int sm_count, cudaStream_t s);
 cudaError_t launch_columns(const GridView & g, int32_t * ix, int32_t * iy, uint32_t * cnt, unsigned long long cap,
                            uint32_t tiles_upper_bound, int sm_count, cudaStream_t s);
 cudaError_t launch_columns_to_dense(const GridView & g, int ix0, int iy0, uint32_t nx, uint32_t ny, uint32_t * dense,
@@ -66,5 +84,19 @@ cudaError_t launch_dump_voxels(const GridView & g, int32_t * x, int32_t * y, int
                                uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s);
 cudaError_t launch_rebuild_hash(const GridView & g, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s);
 cudaError_t launch_reassign_tiles(const GridView & g, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s);
+
+
+// launch with (optionally) the programmatic-stream-serialization attribute, see pdl_wait()
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_ex(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, bool pdl, Args &&... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(static_cast<Args &&>(args))...);
+}
 
 }  // namespace stvl

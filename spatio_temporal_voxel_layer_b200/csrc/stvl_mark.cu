@@ -1,0 +1,589 @@
+// stvl_mark.cu — Mark / operator() (reference spatio_temporal_voxel_grid.cpp:254-309) as a warp-specialised sm_100a kernel.
+//
+// One or two persistent CTAs per SM.  Inside a CTA:
+//   producer warp   one elected lane claims runs of 1024-point chunks from a device-side cursor and streams them
+//                   global -> shared memory with the bulk-copy engine (cp.async.bulk, completion on an mbarrier as
+//                   transaction bytes; SASS UBLKCP / SYNCS), kMarkStages chunks in flight per CTA
+//   consumer warps  wait on the stage's "full" mbarrier, pull their points into registers, release the stage ("empty"
+//                   mbarrier, one arrival per warp) and run the reference's per-point arithmetic: range / z-window tests and
+//                   voxel quantisation on a single-precision fast path that is PROVEN to agree with the reference's
+//                   double arithmetic (see quantise_fast), the exact double sequence for the few points it cannot decide;
+//                   survivors are ORed into a CTA-local table of {(reading, leaf) -> 512-bit mask} in shared memory
+//   costmap warps   (fused cycle only) wait for the sweep, then run the costmap pass over its column counts
+// Nothing before the flush touches the grid, so all of the streaming overlaps the sweep that precedes Mark on the stream
+// (programmatic dependent launch).  The flush resolves every table entry in the global leaf hash once and pushes one
+// 32-bit OR per touched mask word and one 64-bit max (or store) per distinct voxel.
+#include <algorithm>
+#include <cstdlib>
+#include <utility>
+
+#include "stvl_common.cuh"
+
+namespace stvl {
+
+constexpr int kMarkChunk = 1024;                 // points per chunk (16 KB of packed float4 points)
+constexpr int kMarkRun = 4;                      // consecutive chunks claimed per cursor fetch
+constexpr int kMarkConsumerWarps = 16;
+constexpr int kMarkConsumers = kMarkConsumerWarps * 32;
+constexpr int kMarkPPT = kMarkChunk / kMarkConsumers;   // points per consumer thread per chunk
+constexpr int kMarkCmWarps = 8;                  // costmap warps of the fused variant
+constexpr int kMarkTable = 512;                  // CTA-local (reading, leaf) table entries
+constexpr int kMarkProbes = 16;
+constexpr int kMarkStagesMax = 8;
+constexpr uint32_t kChunkEnd = 0xFFFFFFFFu, kChunkFlush = 0xFFFFFFFEu;
+static_assert(kMarkPPT == 2, "the consumer loop is written for two points per thread");
+
+struct PointXYZ { float x, y, z; bool ok; };
+
+// generic PointCloud2 layouts (anything that is not packed x,y,z,pad float4): straight from global memory
+__device__ __forceinline__ PointXYZ load_point_generic(const DevReading & r, unsigned long long i)
+{
+  PointXYZ p;
+  if (i >= r.n_points) { p.x = p.y = p.z = 0.f; p.ok = false; return p; }
+  if (r.vec4) {
+    const float4 v = __ldcs(reinterpret_cast<const float4 *>(r.data) + i);
+    p.x = v.x; p.y = v.y; p.z = v.z;
+  } else {
+    const uint8_t * b = r.data + i * r.point_step;
+    if (((reinterpret_cast<uintptr_t>(b) | r.off_x | r.off_y | r.off_z) & 3u) == 0) {
+      p.x = __ldcs(reinterpret_cast<const float *>(b + r.off_x));
+      p.y = __ldcs(reinterpret_cast<const float *>(b + r.off_y));
+      p.z = __ldcs(reinterpret_cast<const float *>(b + r.off_z));
+    } else {
+      uint32_t w[3];
+      const uint32_t off[3] = {r.off_x, r.off_y, r.off_z};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const uint8_t * q = b + off[a];
+        w[a] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+      }
+      p.x = __uint_as_float(w[0]); p.y = __uint_as_float(w[1]); p.z = __uint_as_float(w[2]);
+    }
+  }
+  p.ok = true;
+  return p;
+}
+
+__device__ __forceinline__ int mark_reading_of(const MarkBatch & batch, uint32_t chunk)
+{
+  int ri = 0;
+#pragma unroll 1
+  for (int k = 1; k < (int)batch.n_readings; ++k) if (chunk >= batch.first_block[k]) ri = k;
+  return ri;
+}
+
+// key of the CTA-local table: reading index (the mark time differs per reading) + leaf coordinate, x relative to the
+// batch's reference leaf so that everything fits 63 bits; leaves farther than 2^16 leaves from it bypass the table
+constexpr int kMarkRelBias = 1 << 16;
+__device__ __forceinline__ uint64_t pack_table_key(int ri, int rx, int by, int bz)
+{
+  return ((uint64_t)(uint32_t)ri << 59) | ((uint64_t)(uint32_t)(rx + kMarkRelBias) << 42) |
+         ((uint64_t)(uint32_t)(by + kLeafBias) << 21) | (uint64_t)(uint32_t)(bz + kLeafBias);
+}
+
+// write one voxel straight to the global store (fallback when the CTA-local table is full or the leaf is out of its reach)
+__device__ __noinline__ void mark_voxel_direct(const GridView & g, int bx, int by, int bz, unsigned l, double now, bool use_max, double tmin_init)
+{
+  const uint32_t slot = leaf_find_or_insert(g, pack_leaf_key(bx, by, bz), bx, by, tmin_init);
+  if (slot == kOverflowSlot) return;
+  atomicOr(&g.leaf_mask[(size_t)slot * 16 + (l >> 5)], 1u << (l & 31));
+  double * tp = &g.leaf_time[(size_t)slot * kLeafVoxels + l];
+  if (use_max) red_max_s64(reinterpret_cast<unsigned long long *>(tp), (unsigned long long)__double_as_longlong(now));
+  else {
+    *tp = now;   // MarkGridPoint: setValueOn overwrite, .cpp:421-430
+    if (g.leaf_tmin[slot] > now) g.leaf_tmin[slot] = -CUDART_INF;   // clocks are not monotone here
+  }
+}
+
+// The reference's per-point arithmetic in double (.cpp:285-303): range test on the float-narrowed squared distance, the
+// -vs shift of negative coordinates (z keyed on y's sign — sic), multiplication by the cached 1/vs, truncation toward zero.
+// Returns (ix, iy, iz, status) by value (registers): status 1 = marked, 0 = skipped, 2 = passed the range test but lies
+// beyond +-2^23 voxels.
+__device__ __noinline__ int4 quantise_exact(float fx, float fy, float fz, double ox, double oy, double oz, float range2, double vs, double inv_vs)
+{
+  const double xd = (double)fx, yd = (double)fy, zd = (double)fz;
+  const double dx = __dsub_rn(xd, ox), dy = __dsub_rn(yd, oy), dz = __dsub_rn(zd, oz);
+  const float distance_2 = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+  if (distance_2 > range2 || (double)distance_2 < 0.0001) return make_int4(0, 0, 0, 0);   // .cpp:289
+  const double X = fx < 0 ? __dsub_rn(xd, vs) : xd;
+  const double Y = fy < 0 ? __dsub_rn(yd, vs) : yd;
+  const double Z = fy < 0 ? __dsub_rn(zd, vs) : zd;
+  const double gx = __dmul_rn(X, inv_vs), gy = __dmul_rn(Y, inv_vs), gz = __dmul_rn(Z, inv_vs);
+  const double lim = 8388608.0;   // 2^23 voxels = 2^20 leaves
+  if (!(fabs(gx) < lim && fabs(gy) < lim && fabs(gz) < lim)) return make_int4(0, 0, 0, 2);
+  return make_int4(__double2int_rz(gx), __double2int_rz(gy), __double2int_rz(gz), 1);
+}
+
+// One axis of the single-precision fast path.  X = shifted coordinate (float: x, or x - vs rounded to float; vs is a float
+// widened to double, so the reference's X differs from ours by at most one float rounding), q = X * (float)(1/vs).
+// Relative error of q against the reference's double product: <= 3 * 2^-24 (shift rounding, rounding of 1/vs to float,
+// product rounding) + 2^-52 < 1.8e-7.  Whenever q is farther than 3e-7 * |q| from the nearest integer, no integer lies
+// between q and the reference's value (nor on it), so both truncate to the same index; otherwise `amb` is raised and the
+// point takes the exact path.  |q| >= 4e6 (float integers get sparse, index limits) is always ambiguous.
+__device__ __forceinline__ int quantise_axis_fast(float X, float inv_vs_f, bool & amb)
+{
+  const float q = __fmul_rn(X, inv_vs_f);
+  const int it = __float2int_rz(q);
+  const float d = fabsf(__fsub_rn(q, __int2float_rn(it)));          // in [0, 1)
+  const float near = fminf(d, __fsub_rn(1.0f, d));
+  amb = amb || !(near > __fmul_rn(fabsf(q), 3e-7f)) || !(fabsf(q) < 4.0e6f);
+  return it;
+}
+
+// kVec4: every reading of the batch is a packed x,y,z,pad float4 cloud (the RGBD / depth-image layout), streamed through
+// the bulk-copy pipeline.  Other layouts are read from global memory by the consumer threads themselves (same chunk
+// hand-out by the producer warp, no staging).
+// kCostmap: the fused update cycle — this launch also runs the costmap pass over the column counts of the sweep that
+// precedes it (they are independent of Mark: the costmap reflects the pre-Mark survivors, reference .cpp:149-224 then
+// spatio_temporal_voxel_layer.cpp:699-718); the costmap bytes were reset by the sweep kernel.  kCmBits: the pass writes a
+// cell bitmap instead of bytes (sharded cycle).
+template <bool kVec4, bool kCostmap, bool kCmBits>
+__global__ void __launch_bounds__((kMarkConsumerWarps + 1 + (kCostmap ? kMarkCmWarps : 0)) * 32, 1)
+mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatch batch, const CostmapDev cm, uint8_t * __restrict__ costmap, const int n_stages)
+{
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  // dynamic shared memory: [stages (kVec4 only)] [table keys] [table masks]
+  float4 * const s_stage = reinterpret_cast<float4 *>(s_dyn);
+  const size_t stage_bytes = kVec4 ? (size_t)n_stages * kMarkChunk * 16 : 0;
+  unsigned long long * const s_key = reinterpret_cast<unsigned long long *>(s_dyn + stage_bytes);
+  uint32_t (* const s_mask)[16] = reinterpret_cast<uint32_t (*)[16]>(s_dyn + stage_bytes + (size_t)kMarkTable * 8);
+  __shared__ uint32_t s_slot[kMarkTable];
+  __shared__ double s_rnow[kMaxBatchReadings];
+  __shared__ __align__(8) uint64_t s_full[kMarkStagesMax], s_empty[kMarkStagesMax];
+  __shared__ uint32_t s_chunk[kMarkStagesMax], s_ri[kMarkStagesMax];
+  __shared__ unsigned int s_fill;          // claimed table entries
+  __shared__ unsigned int s_flushes;       // early flushes done (the producer requests at most one at a time)
+  __shared__ unsigned int s_drop[2];
+
+  TRACE(0, 0);
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned warp = threadIdx.x >> 5;
+  const bool use_max = batch.use_atomic_max != 0;
+  const uint32_t total = batch.total_blocks;
+
+  // ---- set-up (touches only shared memory and kernel parameters) ------------------------------------------------------
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_stages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kMarkConsumerWarps); }
+    mbar_fence_init();
+    s_fill = 0; s_flushes = 0; s_drop[0] = s_drop[1] = 0;
+  }
+  if (threadIdx.x < kMaxBatchReadings) s_rnow[threadIdx.x] = threadIdx.x < batch.n_readings ? batch.r[threadIdx.x].now : 0.0;
+  for (int i = threadIdx.x; i < kMarkTable; i += blockDim.x) s_key[i] = kEmptyKey;
+  for (int i = threadIdx.x; i < kMarkTable * 16; i += blockDim.x) (&s_mask[0][0])[i] = 0;
+  __syncthreads();
+  TRACE(0, 1);
+
+  // =====================================================================================================================
+  // producer warp
+  // =====================================================================================================================
+  if (warp == kMarkConsumerWarps) {
+    if (lane == 0) {
+      uint32_t * const cursor = &g.ctr->mark_cursor[batch.cursor_sel & 1u];
+      const unsigned long long policy = l2_evict_first_policy();
+      unsigned flush_requests = 0;
+      uint32_t it = 0;
+      for (;;) {
+        // a run of kMarkRun consecutive chunks (the cursor is monotone: ids are relative to the launch's base).  Every
+        // producer stops at its first run that starts out of range, so a launch advances the cursor by a known amount.
+        const uint32_t run0 = atomicAdd(cursor, (uint32_t)kMarkRun) - batch.cursor_base;
+        if (run0 >= total) {
+          const int stage = (int)(it % (uint32_t)n_stages);
+          mbar_wait(&s_empty[stage], ((it / (uint32_t)n_stages) & 1u) ^ 1u);
+          s_chunk[stage] = kChunkEnd;
+          mbar_arrive(&s_full[stage]);
+          break;
+        }
+        for (int k = 0; k < kMarkRun; ++k) {
+          const uint32_t id = run0 + (uint32_t)k;
+          if (id >= total) break;
+          int stage = (int)(it % (uint32_t)n_stages);
+          mbar_wait(&s_empty[stage], ((it / (uint32_t)n_stages) & 1u) ^ 1u);
+          // a filling table is flushed early (large or scattered clouds): the marker travels in-band, so every consumer
+          // sees it between the same two chunks
+          if (*reinterpret_cast<volatile unsigned int *>(&s_fill) >= (unsigned)(kMarkTable * 5 / 8) &&
+              *reinterpret_cast<volatile unsigned int *>(&s_flushes) == flush_requests) {
+            ++flush_requests;
+            s_chunk[stage] = kChunkFlush;
+            mbar_arrive(&s_full[stage]);
+            ++it;
+            stage = (int)(it % (uint32_t)n_stages);
+            mbar_wait(&s_empty[stage], ((it / (uint32_t)n_stages) & 1u) ^ 1u);
+          }
+          const int ri = mark_reading_of(batch, id);
+          s_chunk[stage] = id;
+          s_ri[stage] = (uint32_t)ri;
+          if constexpr (kVec4) {
+            const DevReading & rd = batch.r[ri];
+            const unsigned long long base = (unsigned long long)(id - batch.first_block[ri]) * kMarkChunk;
+            const unsigned long long left = rd.n_points - base;
+            const uint32_t bytes = (uint32_t)(left < (unsigned long long)kMarkChunk ? left : (unsigned long long)kMarkChunk) * 16u;
+            mbar_arrive_expect_tx(&s_full[stage], bytes);
+            bulk_load(s_stage + (size_t)stage * kMarkChunk, rd.data + base * 16ull, bytes, &s_full[stage], policy);
+          } else {
+            mbar_arrive(&s_full[stage]);
+          }
+          ++it;
+        }
+      }
+    }
+    return;
+  }
+
+  // =====================================================================================================================
+  // costmap warps (fused cycle): the pass needs the sweep's column counts, nothing of Mark
+  // =====================================================================================================================
+  if constexpr (kCostmap) {
+    if (warp > kMarkConsumerWarps) {
+      pdl_wait();
+      const uint32_t n_tiles = min(ld_volatile_u32(&g.ctr->tile_n), g.tile_capacity);
+      constexpr uint32_t kCmBatch = 4;
+      const uint32_t cw = blockIdx.x * kMarkCmWarps + (warp - kMarkConsumerWarps - 1);
+      unsigned cm_n = 0;
+      int cm_mnx = INT_MAX, cm_mny = INT_MAX, cm_mxx = INT_MIN, cm_mxy = INT_MIN;
+      for (uint32_t t0 = cw * kCmBatch; t0 < n_tiles; t0 += gridDim.x * kMarkCmWarps * kCmBatch)
+        costmap_tile_batch<(int)kCmBatch, kCmBits>(g, cm, costmap, t0, n_tiles, lane, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy);
+      costmap_warp_accumulate(g.ctr, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy);
+      if (lane == 0) __threadfence();   // this warp's accumulator updates are visible before the CTA takes its ticket
+      named_bar_sync(2, kMarkCmWarps * 32);
+      if (warp == kMarkConsumerWarps + 1 && lane == 0) {
+        __threadfence();
+        if (atomicAdd(&g.ctr->cm_ticket, 1u) == gridDim.x - 1) {   // last CTA publishes the result and re-arms the accumulators
+          __threadfence();
+          costmap_publish_result(g.ctr);
+          g.ctr->cm_ticket = 0;
+          __threadfence();
+        }
+      }
+      return;
+    }
+  }
+
+  // =====================================================================================================================
+  // consumer warps
+  // =====================================================================================================================
+  bool grid_ok = false;       // this thread has waited for the predecessor grid (the sweep)
+  auto sync_with_predecessor = [&]() { if (!grid_ok) { pdl_wait(); grid_ok = true; } };
+  unsigned int drop_range = 0, drop_nonfinite = 0;
+  uint64_t last_key = kEmptyKey;   // this thread's most recent table key and its entry
+  int last_e = -1;
+  const float vs_f = (float)g.vs;              // exact: vs is a float widened to double
+  const float inv_vs_f = (float)g.inv_vs;
+
+  // ---- flush: resolve the table's leaves in the global hash, push masks and times, empty the table ----------------------
+  auto flush = [&](const bool final) {
+    named_bar_sync(1, kMarkConsumers);   // every consumer warp is done with the chunks before the flush point
+    if (final) TRACE(0, 3);
+    sync_with_predecessor();
+    // launch_dependents only AFTER our own wait: the next cycle's sweep (and the Mark behind it) cannot become resident
+    // before the grid preceding this one has completed, which bounds the programmatic-launch chain to two kernels in flight
+    if (final) pdl_launch_dependents();
+    for (int e = threadIdx.x; e < kMarkTable; e += kMarkConsumers) {   // one thread per distinct (reading, leaf)
+      const unsigned long long tkey = s_key[e];
+      uint32_t slot = kOverflowSlot;
+      if (tkey != kEmptyKey) {
+        const int bx = (int)((tkey >> 42) & 0x1FFFF) - kMarkRelBias + batch.ref_bx;
+        const int by = (int)((tkey >> 21) & 0x1FFFFF) - kLeafBias, bz = (int)(tkey & 0x1FFFFF) - kLeafBias;
+        slot = leaf_find_or_insert(g, pack_leaf_key(bx, by, bz), bx, by, batch.min_now);
+      }
+      s_slot[e] = slot;
+    }
+    last_key = kEmptyKey; last_e = -1;
+    named_bar_sync(1, kMarkConsumers);
+    if (final) TRACE(0, 4);
+    // per touched mask word one 32-bit OR, per distinct voxel one 64-bit max (batched launch, monotone clocks) or a
+    // plain store (per-reading launches: exact overwrite semantics of MarkGridPoint, .cpp:421-430)
+    for (int i = threadIdx.x; i < kMarkTable * 16; i += kMarkConsumers) {
+      uint32_t m = (&s_mask[0][0])[i];
+      if (!m) continue;
+      (&s_mask[0][0])[i] = 0;
+      const int e = i >> 4;
+      const uint32_t slot = s_slot[e];
+      if (slot == kOverflowSlot) continue;
+      const double now = s_rnow[(int)(s_key[e] >> 59)];
+      const unsigned long long now_bits = (unsigned long long)__double_as_longlong(now);
+      const unsigned w = i & 15;
+      red_or_u32(&g.leaf_mask[(size_t)slot * 16 + w], m);
+      double * tp = g.leaf_time + (size_t)slot * kLeafVoxels + w * 32;
+      if (!use_max && g.leaf_tmin[slot] > now) g.leaf_tmin[slot] = -CUDART_INF;   // clocks are not monotone here
+      while (m) {
+        const int b = __ffs(m) - 1; m &= m - 1;
+        if (use_max) red_max_s64(reinterpret_cast<unsigned long long *>(tp + b), now_bits);
+        else tp[b] = now;
+      }
+    }
+    if (!final) {
+      named_bar_sync(1, kMarkConsumers);   // the keys were still needed for the per-reading clock above
+      for (int e = threadIdx.x; e < kMarkTable; e += kMarkConsumers) s_key[e] = kEmptyKey;
+      if (threadIdx.x == 0) { s_fill = 0; atomicAdd(&s_flushes, 1u); }
+      named_bar_sync(1, kMarkConsumers);
+    }
+  };
+
+  // find-or-claim the (reading, leaf) entry of the CTA-local table and set the voxel's bit
+  auto table_insert = [&](int ri, int ix, int iy, int iz, double now_r) {
+    const int bx = ix >> 3, by = iy >> 3, bz = iz >> 3;
+    if (g.shard_count > 1 && !shard_owns(bx, g.shard_index, g.shard_count, g.shard_width)) return;
+    const unsigned l = (unsigned)(((ix & 7) * 8 + (iy & 7)) * 8 + (iz & 7));
+    const int rx = bx - batch.ref_bx;
+    int e = -1;
+    if (rx >= -kMarkRelBias && rx < kMarkRelBias) {
+      const uint64_t key = pack_table_key(ri, rx, by, bz);
+      if (key == last_key) e = last_e;
+      else {
+        uint32_t h = ((uint32_t)bx * 73856093u ^ (uint32_t)by * 19349663u ^ (uint32_t)bz * 83492791u ^ (uint32_t)ri * 2654435761u) & (kMarkTable - 1);
+#pragma unroll 1
+        for (int p = 0; p < kMarkProbes; ++p) {
+          unsigned long long cur = s_key[h];
+          if (cur == kEmptyKey) {
+            cur = atomicCAS(&s_key[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
+            if (cur == kEmptyKey) { atomicAdd(&s_fill, 1u); cur = key; }
+          }
+          if (cur == key) { e = (int)h; break; }
+          h = (h + 1) & (kMarkTable - 1);
+        }
+        last_key = key; last_e = e;
+      }
+    }
+    if (e >= 0) {
+      const uint32_t bit = 1u << (l & 31);
+      if (!(s_mask[e][l >> 5] & bit)) atomicOr(&s_mask[e][l >> 5], bit);
+    } else {   // table full (scattered cloud) or leaf out of the table's reach: straight to the global store
+      sync_with_predecessor();
+      mark_voxel_direct(g, bx, by, bz, l, now_r, use_max, batch.min_now);
+    }
+  };
+
+  for (uint32_t it = 0;; ++it) {
+    const int stage = (int)(it % (uint32_t)n_stages);
+    mbar_wait(&s_full[stage], (it / (uint32_t)n_stages) & 1u);
+    const uint32_t chunk = s_chunk[stage];
+    if (chunk == kChunkEnd) break;
+    if (chunk == kChunkFlush) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[stage]);
+      flush(false);
+      continue;
+    }
+    const int ri = (int)s_ri[stage];
+    const DevReading & par = batch.r[ri];   // warp-uniform parameter-bank reads
+    PointXYZ pts[kMarkPPT];
+    if constexpr (kVec4) {
+      const unsigned long long base = (unsigned long long)(chunk - batch.first_block[ri]) * kMarkChunk;
+      const unsigned long long left = par.n_points - base;
+      const unsigned in_chunk = left < (unsigned long long)kMarkChunk ? (unsigned)left : (unsigned)kMarkChunk;
+#pragma unroll
+      for (int k = 0; k < kMarkPPT; ++k) {
+        const unsigned idx = (unsigned)k * kMarkConsumers + threadIdx.x;
+        const float4 v = s_stage[(size_t)stage * kMarkChunk + idx];
+        pts[k].x = v.x; pts[k].y = v.y; pts[k].z = v.z;
+        pts[k].ok = idx < in_chunk;
+      }
+    } else {
+      const unsigned long long base = (unsigned long long)(chunk - batch.first_block[ri]) * kMarkChunk;
+#pragma unroll
+      for (int k = 0; k < kMarkPPT; ++k) pts[k] = load_point_generic(par, base + (unsigned long long)k * kMarkConsumers + threadIdx.x);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[stage]);   // the stage may be refilled: this warp holds its points in registers
+    if (it == 0) TRACE(0, 2);
+
+    const float range2 = par.mark_range_2, range2_reject = par.range2_reject, range2_accept = par.range2_accept;
+    const float near_accept = par.near_accept;
+    const float oxf = par.oxf, oyf = par.oyf, ozf = par.ozf;
+    const bool zwin = par.filter == 2;
+    const float zlo = zwin ? par.zmin_f : -CUDART_INF_F, zhi = zwin ? par.zmax_f : CUDART_INF_F;
+    if (par.has_tf) {   // cloud still in the sensor frame: tf2::doTransform first (measurement_buffer.cpp:141-146)
+#pragma unroll
+      for (int k = 0; k < kMarkPPT; ++k) transform_point(par.tf, pts[k].x, pts[k].y, pts[k].z);
+    }
+    // ---- single-precision fast path, both points of the thread interleaved ------------------------------------------------
+    int ix[kMarkPPT], iy[kMarkPPT], iz[kMarkPPT];
+    bool take[kMarkPPT], amb[kMarkPPT];
+#pragma unroll
+    for (int k = 0; k < kMarkPPT; ++k) {
+      const float fx = pts[k].x, fy = pts[k].y, fz = pts[k].z;
+      // non-finite coordinates: (x*0 + y*0 + z*0) is NaN exactly when one of them is NaN or infinite
+      const float nf = fmaf(fz, 0.0f, fmaf(fy, 0.0f, __fmul_rn(fx, 0.0f)));
+      const bool finite = nf == nf;
+      drop_nonfinite += (pts[k].ok && !finite) ? 1u : 0u;
+      // PassThrough z window (reference measurement_buffer.cpp:165-175) on exactly equivalent float thresholds; the range
+      // test on a float evaluation of the squared distance whose error is far below the margins of the two thresholds:
+      // above range2_reject the exact test certainly rejects, inside [near_accept, range2_accept] it certainly accepts
+      const float ax = __fsub_rn(fx, oxf), ay = __fsub_rn(fy, oyf), az = __fsub_rn(fz, ozf);
+      const float d2f = fmaf(az, az, fmaf(ay, ay, __fmul_rn(ax, ax)));
+      const bool cand = pts[k].ok && finite && !(fz < zlo || fz > zhi) && !(d2f > range2_reject);
+      bool a = !(d2f <= range2_accept && d2f >= near_accept);
+      // .cpp:293-303 in float: shift negatives by one voxel (z tests y's sign — sic), multiply by 1/vs, truncate toward zero
+      const float X = fx < 0 ? __fsub_rn(fx, vs_f) : fx;
+      const float Y = fy < 0 ? __fsub_rn(fy, vs_f) : fy;
+      const float Z = fy < 0 ? __fsub_rn(fz, vs_f) : fz;
+      ix[k] = quantise_axis_fast(X, inv_vs_f, a);
+      iy[k] = quantise_axis_fast(Y, inv_vs_f, a);
+      iz[k] = quantise_axis_fast(Z, inv_vs_f, a);
+      take[k] = cand && !a;
+      amb[k] = cand && a;
+    }
+    // ---- the exact double sequence for the points the fast path could not decide (rare; whole warps skip it) ----------------
+#pragma unroll
+    for (int k = 0; k < kMarkPPT; ++k) {
+      if (__any_sync(kFull, amb[k])) {
+        if (amb[k]) {
+          const int4 q = quantise_exact(pts[k].x, pts[k].y, pts[k].z, par.ox, par.oy, par.oz, range2, g.vs, g.inv_vs);
+          ix[k] = q.x; iy[k] = q.y; iz[k] = q.z;
+          take[k] = q.w == 1;
+          drop_range += q.w == 2 ? 1u : 0u;
+        }
+      }
+    }
+    // ---- CTA-local dedupe ----------------------------------------------------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < kMarkPPT; ++k) {
+      if (take[k]) table_insert(ri, ix[k], iy[k], iz[k], par.now);
+    }
+  }
+  flush(true);
+  TRACE(0, 5);
+
+  // dropped-point statistics: warp reduce, shared-memory add, one fire-and-forget global reduction per CTA
+  if (__any_sync(kFull, (drop_range | drop_nonfinite) != 0)) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      drop_range += __shfl_xor_sync(kFull, drop_range, d);
+      drop_nonfinite += __shfl_xor_sync(kFull, drop_nonfinite, d);
+    }
+    if (lane == 0) {
+      if (drop_range) atomicAdd(&s_drop[0], drop_range);
+      if (drop_nonfinite) atomicAdd(&s_drop[1], drop_nonfinite);
+    }
+  }
+  named_bar_sync(1, kMarkConsumers);
+  if (threadIdx.x == 0) {
+    if (s_drop[0]) red_add_u64(&g.ctr->dropped_range, (unsigned long long)s_drop[0]);   // rare: points beyond +-2^23 voxels
+    if (s_drop[1]) red_add_u64(&g.ctr->dropped_nonfinite, (unsigned long long)s_drop[1]);
+    TRACE(0, 6);
+  }
+}
+
+// bulk load of (index, time) pairs — MarkGridPoint semantics (overwrite), for tests / restore
+__global__ void __launch_bounds__(256)
+load_voxels_kernel(const GridView g, const int32_t * __restrict__ vx, const int32_t * __restrict__ vy,
+                   const int32_t * __restrict__ vz, const double * __restrict__ vt, unsigned long long n)
+{
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int ix = vx[i], iy = vy[i], iz = vz[i];
+    const int bx = ix >> 3, by = iy >> 3, bz = iz >> 3;
+    if (!(leaf_coord_ok(bx) && leaf_coord_ok(by) && leaf_coord_ok(bz))) {
+      atomicAdd(&g.ctr->dropped_range, 1ull);
+    } else if (shard_owns(bx, g.shard_index, g.shard_count, g.shard_width)) {
+      const uint32_t slot = leaf_find_or_insert(g, pack_leaf_key(bx, by, bz), bx, by, CUDART_INF);
+      if (slot != kOverflowSlot) {
+        // keep the leaf's lower bound of mark times exact (CAS loop: loaded times are arbitrary doubles, NaN = unknown)
+        {
+          const double tv = vt[i];
+          unsigned long long * tp = reinterpret_cast<unsigned long long *>(&g.leaf_tmin[slot]);
+          unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tp);
+          for (;;) {
+            const double c = __longlong_as_double((long long)cur);
+            const double want = (tv == tv) ? fmin(c, tv) : -CUDART_INF;
+            if (__double_as_longlong(want) == (long long)cur) break;
+            const unsigned long long old = atomicCAS(tp, cur, (unsigned long long)__double_as_longlong(want));
+            if (old == cur) break;
+            cur = old;
+          }
+        }
+        const unsigned li = (unsigned)(((ix & 7) * 8 + (iy & 7)) * 8 + (iz & 7));
+        atomicOr(&g.leaf_mask[(size_t)slot * 16 + (li >> 5)], 1u << (li & 31));
+        g.leaf_time[(size_t)slot * kLeafVoxels + li] = vt[i];
+      }
+    }
+  }
+}
+
+// =====================================================================================
+// host-callable launchers
+// =====================================================================================
+namespace {
+int env_int(const char * name, int dflt, int lo, int hi)
+{
+  const char * v = std::getenv(name);
+  if (!v || !*v) return dflt;
+  const int x = std::atoi(v);
+  return x < lo ? lo : (x > hi ? hi : x);
+}
+// launch geometry of the Mark kernel: CTAs per SM and bulk-copy stages per CTA.  (STVL_MARK_CTAS_PER_SM / STVL_MARK_STAGES
+// are tuning knobs for profiling; the defaults are what the measurements in DESIGN.md were taken with.)
+int mark_ctas_per_sm() { static const int v = env_int("STVL_MARK_CTAS_PER_SM", 1, 1, 2); return v; }
+int mark_stages(bool vec4) { static const int v = env_int("STVL_MARK_STAGES", 6, 2, kMarkStagesMax); return vec4 ? v : 2; }
+size_t mark_smem_bytes(bool vec4) { return (vec4 ? (size_t)mark_stages(true) * kMarkChunk * 16 : 0) + (size_t)kMarkTable * (8 + 64); }
+}  // namespace
+
+uint32_t mark_grid_for(const MarkBatch & batch, int sm_count)
+{
+  const uint32_t runs = (batch.total_blocks + kMarkRun - 1) / kMarkRun;
+  return std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)(sm_count * mark_ctas_per_sm()), runs));
+}
+// column tiles the fused variant's costmap warps can take without becoming the critical path of the launch
+uint32_t mark_costmap_tiles_capacity(const MarkBatch & batch, int sm_count)
+{
+  return mark_grid_for(batch, sm_count) * (uint32_t)kMarkCmWarps * 16u;
+}
+uint32_t mark_cursor_advance(const MarkBatch & batch, int sm_count)
+{
+  // every producer stops at its first out-of-range run: the cursor ends at (runs + grid) * kMarkRun past the launch's base
+  const uint32_t runs = (batch.total_blocks + kMarkRun - 1) / kMarkRun;
+  return (runs + mark_grid_for(batch, sm_count)) * (uint32_t)kMarkRun;
+}
+
+template <bool kVec4, bool kCostmap, bool kCmBits>
+static cudaError_t launch_mark_variant(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s, bool pdl,
+                                       const CostmapDev & cm, uint8_t * costmap)
+{
+  static bool configured = false;
+  const size_t smem = mark_smem_bytes(kVec4);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(mark_kernel<kVec4, kCostmap, kCmBits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    // All kernels of the cycle ask for the same (maximum) shared-memory carve-out: they overlap on the same SMs under
+    // programmatic dependent launch, and an SM only changes its L1 / shared split when it is empty.
+    cudaFuncSetAttribute(mark_kernel<kVec4, kCostmap, kCmBits>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  const unsigned block = (kMarkConsumerWarps + 1 + (kCostmap ? kMarkCmWarps : 0)) * 32;
+  return launch_ex(mark_kernel<kVec4, kCostmap, kCmBits>, mark_grid_for(batch, sm_count), block, smem, s, pdl, g, batch, cm, costmap,
+                   mark_stages(kVec4));
+}
+
+// pdl: the caller guarantees that the kernel's inputs (clouds) were complete before the PREDECESSOR of this launch in the
+// stream started, and that the predecessor is this library's sweep kernel.  cm / costmap != NULL: fused costmap pass
+// (cm_bits: into a cell bitmap).  batch.cursor_sel / cursor_base must have been set by the caller (see mark_cursor_advance).
+cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s, bool pdl,
+                        const CostmapDev * cm, uint8_t * costmap, bool cm_bits)
+{
+  if (batch.total_blocks == 0) return cudaSuccess;
+  bool all_vec4 = true;
+  for (uint32_t i = 0; i < batch.n_readings; ++i) all_vec4 = all_vec4 && batch.r[i].vec4 != 0;
+  const CostmapDev none{};
+  if (cm && costmap) {
+    if (cm_bits)
+      return all_vec4 ? launch_mark_variant<true, true, true>(g, batch, sm_count, s, pdl, *cm, costmap)
+                      : launch_mark_variant<false, true, true>(g, batch, sm_count, s, pdl, *cm, costmap);
+    return all_vec4 ? launch_mark_variant<true, true, false>(g, batch, sm_count, s, pdl, *cm, costmap)
+                    : launch_mark_variant<false, true, false>(g, batch, sm_count, s, pdl, *cm, costmap);
+  }
+  return all_vec4 ? launch_mark_variant<true, false, false>(g, batch, sm_count, s, pdl, none, nullptr)
+                  : launch_mark_variant<false, false, false>(g, batch, sm_count, s, pdl, none, nullptr);
+}
+uint32_t mark_blocks_for(unsigned long long n_points)
+{
+  return (uint32_t)((n_points + kMarkChunk - 1) / kMarkChunk);
+}
+cudaError_t launch_load_voxels(const GridView & g, const int32_t * x, const int32_t * y, const int32_t * z, const double * t,
+                               unsigned long long n, cudaStream_t s)
+{
+  if (n == 0) return cudaSuccess;
+  load_voxels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g, x, y, z, t, n);
+  return cudaGetLastError();
+}
+
+}  // namespace stvl

@@ -1,0 +1,508 @@
+// stvl_sweep.cu — ClearFrustums / TemporalClearAndGenerateCostmap (reference spatio_temporal_voxel_grid.cpp:96-224) as ONE
+// kernel.
+//
+// Every CTA walks tiles of leaf slots in three phases:
+//   A  one THREAD per leaf: header (key, tmin, tile, 64 B value mask) in one round trip.  A leaf outside every frustum whose
+//      oldest voxel is too young to expire cannot change: its survivors are counted straight from the mask (two adjacent u32
+//      column counters per 64-bit reduction) and its 4 KB time block is never touched.  Every other leaf is split into
+//      batches of 32 active voxels that go into a work queue in SHARED memory (its time sectors are prefetched into L2).
+//   B  one WARP per queued batch, taken dynamically: leaf-level frustum classification, the reference's exact per-voxel
+//      arithmetic (decay model, first containing frustum, acceleration, strict <), rewrite of accelerated times, bit clears,
+//      per-column survivor counts, optional lists.
+//   C  the thread that queued a leaf folds its batches' minima into the leaf's lower time bound.
+// No global work queue, no second launch, no grid-wide synchronisation: a leaf's whole sweep stays inside one CTA.
+#include <algorithm>
+#include <cstdlib>
+#include <utility>
+
+#include "stvl_common.cuh"
+
+namespace stvl {
+
+constexpr int kSweepThreads = 512;
+constexpr int kSweepWarps = kSweepThreads / 32;
+constexpr int kSweepQueue = 2048;       // batches per tile pass (a tile whose leaves need more is finished in further rounds)
+
+// classify a whole leaf against one frustum: 0 = no voxel centre can be inside, 1 = test per voxel, 2 = all inside
+__device__ __forceinline__ int classify_leaf(const DevFrustum & f, int bx, int by, int bz, double vs, double half_vs)
+{
+  if (f.type < 0) return 0;
+  if (!f.cull) return 1;
+  const int x0 = bx * 8, y0 = by * 8, z0 = bz * 8;
+  if (x0 + 7 < f.lo[0] || x0 > f.hi[0] || y0 + 7 < f.lo[1] || y0 > f.hi[1] || z0 + 7 < f.lo[2] || z0 > f.hi[2]) return 0;
+  // bounding sphere of the 512 voxel centres (conservative radius)
+  const double cx = ((double)x0 + 3.5) * vs + half_vs, cy = ((double)y0 + 3.5) * vs + half_vs, cz = ((double)z0 + 3.5) * vs + half_vs;
+  const double rad = 6.0621778264910705 * vs * 1.000001 + 1e-6;   // 3.5*sqrt(3)
+  if (f.type == 0) {
+    bool all_in = true;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double s = f.p[6 * k] * (cx - f.p[6 * k + 3]) + f.p[6 * k + 1] * (cy - f.p[6 * k + 4]) + f.p[6 * k + 2] * (cz - f.p[6 * k + 5]);
+      if (s > rad) return 0;
+      if (s > -rad) all_in = false;
+    }
+    return all_in ? 2 : 1;
+  }
+  // lidar hourglass: radial range and vertical cone, in the sensor frame (approximate transform + margins)
+  double tx, ty, tz;
+  quat_rotate_exact(f.p[3], f.p[4], f.p[5], f.p[6], cx - f.p[0], cy - f.p[1], cz - f.p[2], tx, ty, tz);
+  const double rc = sqrt(tx * tx + ty * ty);
+  if (rc - rad > f.aux[1] || rc + rad < f.aux[0]) return 0;
+  const double zmin = fabs(tz) - rad;
+  if (zmin > 0 && zmin - f.aux[3] > f.aux[2] * (rc + rad) + 1e-6) return 0;
+  return 1;
+}
+
+struct SweepAcc {
+  unsigned int swept = 0, surv = 0, clear = 0, rewr = 0, amb = 0;
+  int min_x = INT_MAX, min_y = INT_MAX, max_x = INT_MIN, max_y = INT_MIN;
+};
+
+// can a leaf whose oldest mark time is tmin contain a voxel that expires by decay alone?  The decay duration is
+// non-increasing in a voxel's age for the linear model; the exponential / persistent ones never go negative for
+// voxel_decay >= 0 (reference .cpp:320-331).  tmin = -inf ("unknown") always answers yes.
+__device__ __forceinline__ bool leaf_may_expire(const GridView & g, double now, double tmin)
+{
+  if (g.decay_model == 0) return __dsub_rn(g.voxel_decay, __dsub_rn(now, tmin)) < 0.;
+  return !(g.voxel_decay >= 0.0);
+}
+
+__global__ void __launch_bounds__(kSweepThreads, 2)
+sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ FrustumParams fparam, const DevFrustum * __restrict__ frustums_gmem,
+             const int n_frustums, const double now, const SweepOutputs out, uint8_t * __restrict__ cm_reset,
+             const unsigned long long cm_bytes, const int cm_value, const uint32_t tile_leaves)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DevFrustum * fr = reinterpret_cast<DevFrustum *>(smem_raw);   // frustum parameter blocks, staged for the whole kernel
+  __shared__ uint32_t s_q_slot[kSweepQueue];
+  __shared__ uint8_t s_q_batch[kSweepQueue];
+  __shared__ double s_q_min[kSweepQueue];       // smallest surviving time of the batch
+  __shared__ uint32_t s_q_clear[kSweepQueue];   // which of the batch's 32 voxels were cleared (bit = position in the batch)
+  __shared__ uint16_t s_list[kSweepWarps][32];  // local voxel indices of the batch a warp is working on
+  __shared__ uint32_t s_part[kSweepWarps][kMaxFrustums / 32];
+  __shared__ uint32_t s_full[kSweepWarps][kMaxFrustums / 32];
+  __shared__ unsigned int s_qn, s_qlimit, s_qnext;
+  __shared__ unsigned int s_red[5];
+  __shared__ int s_bb[4];
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned warp = threadIdx.x >> 5;
+  TRACE(1, 0);
+  // Programmatic dependent launch: the Mark kernel behind this one may become resident now and stream its clouds; it waits
+  // for this grid before it touches the store.  The frustum blocks come from the kernel parameters (small sets) or from a
+  // device buffer an earlier stream operation filled; neither is written by the predecessor kernel.
+  pdl_launch_dependents();
+  {
+    const int words = n_frustums * (int)(sizeof(DevFrustum) / 8);
+    const double * src = reinterpret_cast<const double *>(frustums_gmem ? frustums_gmem : fparam.f);
+    double * dst = reinterpret_cast<double *>(fr);
+    for (int i = threadIdx.x; i < words; i += kSweepThreads) dst[i] = src[i];
+  }
+  if (threadIdx.x == 0) {
+    s_qn = 0; s_qlimit = kSweepQueue; s_qnext = 0;
+    s_red[0] = s_red[1] = s_red[2] = s_red[3] = s_red[4] = 0;
+    s_bb[0] = s_bb[1] = INT_MAX; s_bb[2] = s_bb[3] = INT_MIN;
+  }
+  __syncthreads();
+  pdl_wait();                // launched programmatically behind the previous cycle's Mark kernel: the grid is ours from here
+  const uint32_t n_slots = slots_in_use(g);
+  TRACE(1, 1);
+  // re-arm the state of the NEXT sweep while this one runs: zero the other tile buffer and the other counter set
+  {
+    const uint32_t n_tiles = min(ld_volatile_u32(&g.ctr->tile_n), g.tile_capacity);
+    const uint32_t n_words = n_tiles * 64u;
+    uint4 * t4 = reinterpret_cast<uint4 *>(g.tile_count_next);
+    for (uint32_t i = blockIdx.x * kSweepThreads + threadIdx.x; i < n_words / 4; i += gridDim.x * kSweepThreads) t4[i] = make_uint4(0, 0, 0, 0);
+    // fused update cycle: Costmap2D::resetMaps (spatio_temporal_voxel_layer.cpp:705) for the costmap pass that rides on
+    // this cycle's Mark kernel — saves the memset launch between Mark and the costmap
+    if (cm_reset) {
+      const unsigned head = (unsigned)((16u - (unsigned)(reinterpret_cast<uintptr_t>(cm_reset) & 15u)) & 15u);
+      const unsigned long long h = head < cm_bytes ? head : cm_bytes;
+      const unsigned long long n16 = (cm_bytes - h) / 16;
+      const unsigned v = (unsigned)cm_value * 0x01010101u;
+      uint4 * c4 = reinterpret_cast<uint4 *>(cm_reset + h);
+      for (unsigned long long i = (unsigned long long)blockIdx.x * kSweepThreads + threadIdx.x; i < n16; i += (unsigned long long)gridDim.x * kSweepThreads)
+        c4[i] = make_uint4(v, v, v, v);
+      if (blockIdx.x == 0) {
+        for (unsigned long long i = threadIdx.x; i < h; i += kSweepThreads) cm_reset[i] = (uint8_t)cm_value;
+        for (unsigned long long i = h + n16 * 16 + threadIdx.x; i < cm_bytes; i += kSweepThreads) cm_reset[i] = (uint8_t)cm_value;
+      }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      SweepCtr * c = &g.ctr->sw[g.sw_cur ^ 1];
+      c->n_swept = c->n_survived = c->n_cleared = c->n_rewritten = c->n_ambiguous = 0;
+      c->cb_min_x = c->cb_min_y = INT_MAX; c->cb_max_x = c->cb_max_y = INT_MIN;
+      c->n_points_out = c->n_cleared_out = c->n_ambiguous_out = 0;
+      if (g.live) {   // mirror of the allocator counters for the host's grid sizing (posted stores only)
+        volatile LiveCounters * l = g.live;
+        l->high_water = n_slots; l->free_n = ld_volatile_u32(&g.ctr->free_push) - ld_volatile_u32(&g.ctr->free_pop); l->tile_n = n_tiles;
+      }
+    }
+  }
+  const bool force_full = out.points != nullptr;   // pub_voxels needs every survivor's coordinates
+  const int n_chunks = (n_frustums + 31) >> 5;
+  const uint16_t * mask16 = reinterpret_cast<const uint16_t *>(g.leaf_mask);
+  SweepAcc acc;
+  TRACE(1, 2);
+
+  // Tiles of `tile_leaves` consecutive slots, dealt round-robin to the CTAs in groups of 32 (a contiguous run of leaves
+  // that all need the per-voxel pass — a frustum's interior — is spread over many CTAs).
+  const uint32_t groups_per_tile = tile_leaves / 32;          // <= kSweepWarps
+  const uint32_t n_groups = (n_slots + 31) / 32;
+  for (uint32_t g0 = 0; g0 < n_groups; g0 += gridDim.x * groups_per_tile) {
+    // ---- phase A: one thread per leaf -------------------------------------------------------------------------------------
+    // group index of this warp in the tile: warp w handles group (g0 + w * gridDim + blockIdx) — interleaved across CTAs
+    bool pending = false;
+    uint32_t slot = 0, my_q0 = 0, my_nb = 0;
+    if (warp < groups_per_tile) {
+      const uint32_t grp = g0 + warp * gridDim.x + blockIdx.x;
+      slot = grp * 32 + lane;
+      if (grp < n_groups && slot < n_slots) {
+        const uint64_t key = g.leaf_key[slot];
+        const double tmin = g.leaf_tmin[slot];
+        const uint32_t tile = g.leaf_tile[slot];
+        const uint4 * mp = reinterpret_cast<const uint4 *>(g.leaf_mask + (size_t)slot * 16);
+        uint4 mw[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mw[q] = mp[q];
+        if (key != kEmptyKey) {
+          uint32_t any = 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) any |= mw[q].x | mw[q].y | mw[q].z | mw[q].w;
+          if (any == 0) {
+            free_leaf(g, slot);   // nothing left in this leaf: pruneGrid, .cpp:223
+          } else {
+            bool full_path = force_full || leaf_may_expire(g, now, tmin);
+            if (!full_path) {
+              int bx, by, bz;
+              unpack_leaf_key(key, bx, by, bz);
+              const int x0 = bx * 8, y0 = by * 8, z0 = bz * 8;
+              for (int f = 0; f < n_frustums && !full_path; ++f) {
+                const DevFrustum & F = fr[f];
+                if (F.type < 0) continue;
+                if (F.cull && (x0 + 7 < F.lo[0] || x0 > F.hi[0] || y0 + 7 < F.lo[1] || y0 > F.hi[1] || z0 + 7 < F.lo[2] || z0 > F.hi[2])) continue;
+                // inside the frustum's bounding box: bounding sphere of the leaf against the plane set / hourglass
+                full_path = classify_leaf(F, bx, by, bz, g.vs, g.half_vs) != 0;
+              }
+            }
+            if (full_path) {
+              unsigned pc = 0;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) pc += __popc(mw[q].x) + __popc(mw[q].y) + __popc(mw[q].z) + __popc(mw[q].w);
+              my_nb = (pc + 31) / 32;
+              pending = true;
+              // the leaf's mark times will be needed in phase B: pull the touched 64 B column runs into L2 now
+              const double * tb = g.leaf_time + (size_t)slot * kLeafVoxels;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t wv[4] = {mw[q].x, mw[q].y, mw[q].z, mw[q].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint32_t x = wv[j];
+                  if (!x) continue;
+                  const double * wb = tb + (q * 4 + j) * 32;
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                    if ((x >> (8 * c)) & 0xFFu) prefetch_l2(wb + 8 * c);
+                }
+              }
+            } else {
+              // PopulateCostmapAndPointcloud .cpp:242-250 for every (surviving) voxel: per-column popcounts, two adjacent u32
+              // column counters per 64-bit reduction (no carry: counts stay < 2^32)
+              unsigned cnt = 0;
+              unsigned long long * tc = reinterpret_cast<unsigned long long *>(g.tile_count + (size_t)tile * 64);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t wv[4] = {mw[q].x, mw[q].y, mw[q].z, mw[q].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint32_t x = wv[j];
+                  if (!x) continue;
+                  cnt += __popc(x);
+                  x = x - ((x >> 1) & 0x55555555u);
+                  x = (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
+                  x = (x + (x >> 4)) & 0x0F0F0F0Fu;   // four per-column counts, one per byte
+                  if (tile != kOverflowSlot) {
+                    const unsigned long long lo = (unsigned long long)(x & 0xFFu) | ((unsigned long long)((x >> 8) & 0xFFu) << 32);
+                    const unsigned long long hi = (unsigned long long)((x >> 16) & 0xFFu) | ((unsigned long long)(x >> 24) << 32);
+                    if (lo) red_add_u64(tc + (q * 4 + j) * 2, lo);
+                    if (hi) red_add_u64(tc + (q * 4 + j) * 2 + 1, hi);
+                  }
+                }
+              }
+              acc.swept += cnt; acc.surv += cnt;
+            }
+          }
+        }
+      }
+    }
+    // ---- rounds of (queue fill, phase B, phase C) until every leaf of the tile that needs the per-voxel pass has had it --------
+    for (;;) {
+      if (pending) {
+        const uint32_t q0 = atomicAdd(&s_qn, my_nb);
+        if (q0 + my_nb <= (uint32_t)kSweepQueue) {
+          for (uint32_t b = 0; b < my_nb; ++b) { s_q_slot[q0 + b] = slot; s_q_batch[q0 + b] = (uint8_t)b; }
+          my_q0 = q0;
+          pending = false;
+        } else {
+          atomicMin(&s_qlimit, q0);   // entries from here on were not written: this leaf waits for the next round
+          my_q0 = 0xFFFFFFFFu;
+        }
+      }
+      __syncthreads();
+      const uint32_t n_items = min(s_qn, s_qlimit);
+      // ---- phase B: one warp per batch ----------------------------------------------------------------------------------------
+      for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(&s_qnext, 1u);
+        item = __shfl_sync(kFull, item, 0);
+        if (item >= n_items) break;
+        const uint32_t bslot = s_q_slot[item];
+        const uint32_t batch = s_q_batch[item];
+        const uint64_t key = g.leaf_key[bslot];
+        const uint32_t tile = g.leaf_tile[bslot];
+        const uint32_t m16 = mask16[(size_t)bslot * 32 + lane];   // each lane owns two voxel columns = local indices [lane*16, lane*16+16)
+        int bx, by, bz;
+        unpack_leaf_key(key, bx, by, bz);
+        // leaf-level culling: one lane per frustum
+        unsigned any_cand = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+          const int f = c * 32 + (int)lane;
+          const int cls = f < n_frustums ? classify_leaf(fr[f], bx, by, bz, g.vs, g.half_vs) : 0;
+          const unsigned pm = __ballot_sync(kFull, cls == 1), fm = __ballot_sync(kFull, cls == 2);
+          if (lane == 0) { s_part[warp][c] = pm; s_full[warp][c] = fm; }
+          any_cand |= pm | fm;
+        }
+        // the batch's voxels: entries [32*batch, 32*batch + 32) of the leaf's active voxels in ascending local index
+        const int cnt = __popc(m16);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(kFull, incl, d); if ((int)lane >= d) incl += v; }
+        const int total = __shfl_sync(kFull, incl, 31);
+        {
+          int pos = incl - cnt - 32 * (int)batch;
+          uint32_t m = m16;
+          while (m) {
+            const int b = __ffs(m) - 1; m &= m - 1;
+            if (pos >= 0 && pos < 32) s_list[warp][pos] = (uint16_t)(lane * 16 + b);
+            ++pos;
+          }
+        }
+        __syncwarp();
+        const int i = 32 * (int)batch + (int)lane;
+        const bool have = i < total;
+        bool cleared = false, survived = false;
+        int ix = 0, iy = 0, iz = 0;
+        unsigned li = 0;
+        double vmin = CUDART_INF;   // smallest mark time among this batch's survivors
+        if (have) {
+          li = s_list[warp][lane];
+          const double v = __ldcs(g.leaf_time + (size_t)bslot * kLeafVoxels + li);
+          ix = bx * 8 + (int)(li >> 6); iy = by * 8 + (int)((li >> 3) & 7); iz = bz * 8 + (int)(li & 7);
+          ++acc.swept;
+          // .cpp:167-169
+          const double t = __dsub_rn(now, v);
+          double base_dur;
+          bool amb = false;
+          if (g.decay_model == 0) base_dur = __dsub_rn(g.voxel_decay, t);
+          else if (g.decay_model == 1) base_dur = __dmul_rn(g.voxel_decay, exp(-t));
+          else base_dur = g.voxel_decay;
+          // .cpp:171-198: first containing frustum, in reading order, decides
+          int hit = -1;
+          if (any_cand) {
+            const double wx = index_to_world(ix, g.vs, g.half_vs), wy = index_to_world(iy, g.vs, g.half_vs), wz = index_to_world(iz, g.vs, g.half_vs);
+            for (int c = 0; c < n_chunks && hit < 0; ++c) {
+              const unsigned fm = s_full[warp][c];
+              unsigned m = s_part[warp][c] | fm;
+              while (m) {
+                const int b = __ffs(m) - 1; m &= m - 1;
+                const int f = c * 32 + b;
+                bool in;
+                if ((fm >> b) & 1u) in = true;
+                else if (fr[f].type == 0) in = depth_is_inside(fr[f].p, wx, wy, wz);
+                else in = lidar_is_inside(fr[f].p, wx, wy, wz, amb);
+                if (in) { hit = f; break; }
+              }
+            }
+          }
+          if (hit >= 0) {
+            // .cpp:179-197; GetFrustumAcceleration .cpp:334-341 = ((1./6.)*factor) * ((t*t)*t)
+            const double accel = __dmul_rn(fr[hit].c16f, __dmul_rn(__dmul_rn(t, t), t));
+            const double tud = __dsub_rn(base_dur, accel);
+            if (g.decay_model == 1 && fabs(tud) <= 1e-12 * fmax(fabs(base_dur), fabs(accel))) amb = true;
+            if (tud < 0.) cleared = true;
+            else {
+              const double nv = __dsub_rn(v, accel);
+              if (__double_as_longlong(nv) != __double_as_longlong(v)) { g.leaf_time[(size_t)bslot * kLeafVoxels + li] = nv; ++acc.rewr; }
+              vmin = nv;
+            }
+          } else if (base_dur < 0.) {
+            cleared = true;   // .cpp:203-211
+          } else {
+            vmin = v;
+          }
+          survived = !cleared;
+          if (cleared) {
+            // (the bit is cleared in phase C: the batches of a leaf are defined on the mask as phase A saw it, so nothing
+            // may change it while other warps still compact it)
+            ++acc.clear;
+            acc.min_x = min(acc.min_x, ix); acc.max_x = max(acc.max_x, ix);
+            acc.min_y = min(acc.min_y, iy); acc.max_y = max(acc.max_y, iy);
+          } else {
+            ++acc.surv;
+            // PopulateCostmapAndPointcloud .cpp:242-250: _cost_map[(x,y)] += 1 per surviving voxel
+            if (tile != kOverflowSlot) red_add_u32(g.tile_count + (size_t)tile * 64 + (li >> 3), 1u);
+          }
+          if (amb) {
+            ++acc.amb;
+            if (out.ambiguous) {
+              const unsigned long long a = atomicAdd(&g.ctr->sw[g.sw_cur].n_ambiguous_out, 1ull);
+              if (a < out.ambiguous_cap) { out.ambiguous[3 * a] = ix; out.ambiguous[3 * a + 1] = iy; out.ambiguous[3 * a + 2] = iz; }
+            }
+          }
+        }
+        // optional lists: warp-aggregated appends
+        if (out.points) {   // PopulateCostmapAndPointcloud .cpp:234-240: Point32 = (float) voxel centre
+          const unsigned sm = __ballot_sync(kFull, survived);
+          if (sm) {
+            unsigned long long b0 = 0;
+            if (lane == (unsigned)(__ffs(sm) - 1)) b0 = atomicAdd(&g.ctr->sw[g.sw_cur].n_points_out, (unsigned long long)__popc(sm));
+            b0 = __shfl_sync(kFull, b0, __ffs(sm) - 1);
+            if (survived) {
+              const unsigned long long o = b0 + __popc(sm & ((1u << lane) - 1));
+              if (o < out.points_cap) {
+                out.points[3 * o] = (float)index_to_world(ix, g.vs, g.half_vs);
+                out.points[3 * o + 1] = (float)index_to_world(iy, g.vs, g.half_vs);
+                out.points[3 * o + 2] = (float)index_to_world(iz, g.vs, g.half_vs);
+              }
+            }
+          }
+        }
+        if (out.cleared) {   // cleared_cells.insert, .cpp:213-215
+          const unsigned cmk = __ballot_sync(kFull, cleared);
+          if (cmk) {
+            unsigned long long b0 = 0;
+            if (lane == (unsigned)(__ffs(cmk) - 1)) b0 = atomicAdd(&g.ctr->sw[g.sw_cur].n_cleared_out, (unsigned long long)__popc(cmk));
+            b0 = __shfl_sync(kFull, b0, __ffs(cmk) - 1);
+            if (cleared) {
+              const unsigned long long o = b0 + __popc(cmk & ((1u << lane) - 1));
+              if (o < out.cleared_cap) { out.cleared[2 * o] = ix; out.cleared[2 * o + 1] = iy; }
+            }
+          }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) vmin = fmin(vmin, __shfl_xor_sync(kFull, vmin, d));
+        const unsigned cleared_lanes = __ballot_sync(kFull, cleared);
+        if (lane == 0) { s_q_min[item] = vmin; s_q_clear[item] = cleared_lanes; }
+        __syncwarp();
+      }
+      __syncthreads();
+      // ---- phase C: the leaf's lower time bound = minimum over its batches (+inf when nothing survived: the next sweep frees it)
+      if (my_nb && my_q0 != 0xFFFFFFFFu) {
+        double m = CUDART_INF;
+        uint32_t any_clear = 0;
+        for (uint32_t b = 0; b < my_nb; ++b) { m = fmin(m, s_q_min[my_q0 + b]); any_clear |= s_q_clear[my_q0 + b]; }
+        if (any_clear) {
+          // clear the bits of the expired voxels: walk the leaf's active voxels in the order the batches were cut from
+          // (ascending local index); this thread is the only writer of the leaf's mask in this kernel
+          uint32_t * mp = g.leaf_mask + (size_t)slot * 16;
+          uint32_t k = 0;
+          for (int w = 0; w < 16; ++w) {
+            const uint32_t orig = mp[w];
+            uint32_t x = orig, nx = orig;
+            while (x) {
+              const int b = __ffs(x) - 1; x &= x - 1;
+              if ((s_q_clear[my_q0 + (k >> 5)] >> (k & 31)) & 1u) nx &= ~(1u << b);
+              ++k;
+            }
+            if (nx != orig) mp[w] = nx;
+          }
+        }
+        if (m == CUDART_INF) free_leaf(g, slot);   // every voxel of the leaf was cleared: pruneGrid, .cpp:223
+        else g.leaf_tmin[slot] = m;               // exact lower bound again
+        my_nb = 0;
+      }
+      const int more = __syncthreads_or(pending ? 1 : 0);
+      if (threadIdx.x == 0) { s_qn = 0; s_qlimit = kSweepQueue; s_qnext = 0; }
+      __syncthreads();
+      if (!more) break;
+    }
+  }
+  TRACE(1, 3);
+
+  // ---- statistics: warp reduce, shared-memory add, a handful of global reductions per CTA -------------------------------------
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    acc.swept += __shfl_xor_sync(kFull, acc.swept, d); acc.surv += __shfl_xor_sync(kFull, acc.surv, d);
+    acc.clear += __shfl_xor_sync(kFull, acc.clear, d); acc.rewr += __shfl_xor_sync(kFull, acc.rewr, d);
+    acc.amb += __shfl_xor_sync(kFull, acc.amb, d);
+    acc.min_x = min(acc.min_x, __shfl_xor_sync(kFull, acc.min_x, d)); acc.min_y = min(acc.min_y, __shfl_xor_sync(kFull, acc.min_y, d));
+    acc.max_x = max(acc.max_x, __shfl_xor_sync(kFull, acc.max_x, d)); acc.max_y = max(acc.max_y, __shfl_xor_sync(kFull, acc.max_y, d));
+  }
+  if (lane == 0 && (acc.swept | acc.surv | acc.clear | acc.rewr | acc.amb)) {
+    atomicAdd(&s_red[0], acc.swept); atomicAdd(&s_red[1], acc.surv); atomicAdd(&s_red[2], acc.clear);
+    atomicAdd(&s_red[3], acc.rewr); atomicAdd(&s_red[4], acc.amb);
+    atomicMin(&s_bb[0], acc.min_x); atomicMin(&s_bb[1], acc.min_y); atomicMax(&s_bb[2], acc.max_x); atomicMax(&s_bb[3], acc.max_y);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    SweepCtr * c = &g.ctr->sw[g.sw_cur];
+    if (s_red[0]) atomicAdd(&c->n_swept, (unsigned long long)s_red[0]);
+    if (s_red[1]) atomicAdd(&c->n_survived, (unsigned long long)s_red[1]);
+    if (s_red[2]) {
+      atomicAdd(&c->n_cleared, (unsigned long long)s_red[2]);
+      atomicMin(&c->cb_min_x, s_bb[0]); atomicMin(&c->cb_min_y, s_bb[1]);
+      atomicMax(&c->cb_max_x, s_bb[2]); atomicMax(&c->cb_max_y, s_bb[3]);
+    }
+    if (s_red[3]) atomicAdd(&c->n_rewritten, (unsigned long long)s_red[3]);
+    if (s_red[4]) atomicAdd(&c->n_ambiguous, (unsigned long long)s_red[4]);
+  }
+  TRACE(1, 4);
+}
+
+// =====================================================================================
+// host-callable launcher
+// =====================================================================================
+namespace {
+int env_int(const char * name, int dflt, int lo, int hi)
+{
+  const char * v = std::getenv(name);
+  if (!v || !*v) return dflt;
+  const int x = std::atoi(v);
+  return x < lo ? lo : (x > hi ? hi : x);
+}
+}  // namespace
+
+// frustums_dev == NULL: the (<= kParamFrustums) blocks travel in *fparam
+cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, const FrustumParams * fparam, int n_frustums, double now,
+                         const SweepOutputs & out, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s, bool pdl, bool share_sms,
+                         uint8_t * costmap_reset, size_t costmap_bytes, int costmap_value)
+{
+  static const FrustumParams no_params{};
+  const FrustumParams & fp = (frustums_dev == nullptr && fparam) ? *fparam : no_params;
+  static bool carveout_set = false;
+  if (!carveout_set) {   // see launch_mark_variant
+    cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    carveout_set = true;
+  }
+  const size_t dyn = (size_t)n_frustums * sizeof(DevFrustum);
+  static size_t dyn_max = 0;
+  if (dyn > 16 * 1024 && dyn > dyn_max) {
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    dyn_max = dyn;
+  }
+  // Persistent grid: one CTA per SM while a Mark kernel is to share the SMs with it (fused cycle), two otherwise.  Small
+  // stores get small tiles so that every CTA has leaves: the per-voxel pass is a latency-bound dependent chain per batch,
+  // what matters is how many warps work on batches at the same time.
+  static const int ctas_alone = env_int("STVL_SWEEP_CTAS_PER_SM", 2, 1, 2), ctas_shared = env_int("STVL_SWEEP_CTAS_PER_SM_FUSED", 2, 1, 2);
+  const unsigned max_ctas = (unsigned)(sm_count * (share_sms ? ctas_shared : ctas_alone));
+  const unsigned long long groups = ((unsigned long long)leaf_slots_upper_bound + 31) / 32;
+  unsigned grid = (unsigned)std::min<unsigned long long>(max_ctas, std::max<unsigned long long>(groups, 1));
+  unsigned long long gpt = (groups + grid - 1) / grid;          // groups of 32 leaves per CTA if one tile pass were to cover everything
+  if (gpt < 1) gpt = 1;
+  if (gpt > (unsigned long long)kSweepWarps) gpt = kSweepWarps;
+  return launch_ex(sweep_kernel, grid, (unsigned)kSweepThreads, dyn, s, pdl, g, fp, frustums_dev, n_frustums, now, out, costmap_reset, (unsigned long long)costmap_bytes,
+                         costmap_value, (uint32_t)(gpt * 32));
+}
+
+}  // namespace stvl

@@ -761,3 +761,97 @@ def test_config2_full_size_parity_and_properties(stvl, oracle):
     assert_same_voxels(gg.voxels(), before)
     assert st.n_swept > 600000 and st.n_cleared > 100 and st.n_rewritten > 100
     gg.close()
+
+
+def test_async_host_cycle_matches_oracle(stvl, oracle):
+    """stvl_update_cycle_async / stvl_update_cycle_wait — the pipelined host-buffer cycle (H2D copy, fused cycle and D2H
+    read-back on three streams, two cycles in flight) — against the oracle: every cycle's costmap bytes and marked-cell
+    count, and the final voxel store."""
+    import spatio_temporal_voxel_layer_b200.synth as synth
+    scene = synth.retail_scene(size=30.0, seed=5)
+    gg = stvl.SpatioTemporalVoxelGrid(0.05, decay_model=0, voxel_decay=3.0, leaf_capacity=1 << 14)
+    og = oracle.OracleGrid(0.05, decay_model=0, voxel_decay=3.0)
+    size, res, ox, oy = 400, 0.05, -10.0, -10.0
+    params = stvl.CostmapParams(ox, oy, res, size, size, 1, 0, 254)
+    outs = [np.full((size, size), 9, np.uint8) for _ in range(3)]
+    expected, tickets = [], []
+    n_cycles = 9
+    for cyc in range(n_cycles):
+        now = 50.0 + 0.5 * cyc
+        centre = (-6.0 + 0.6 * cyc, 2.3 - 13.5 + 12.0, 0.0)
+        readings = [rgbd_reading(stvl, synth, scene, o, q, seed=10 * cyc + k, now=now + 0.001 * k)
+                    for k, (o, q) in enumerate(synth.camera_ring(centre, 0.2 * cyc, n_cams=3))]
+        tickets.append(gg.update_cycle_async(now, readings, readings, params, outs[cyc % 3]))
+        og.clear_frustums(now, oracle_frustums(oracle, readings))
+        for r in readings:
+            oracle_mark(oracle, og, r, now)
+        ocm, _, on = og.update_ros_costmap(ox, oy, res, size, size, mark_threshold=1, default_value=0)
+        expected.append((ocm, on))
+        if cyc >= 1:      # wait for the previous cycle while this one is in flight
+            r = gg.update_cycle_wait(tickets[cyc - 1])
+            assert np.array_equal(outs[(cyc - 1) % 3], expected[cyc - 1][0]), "costmap bytes differ in cycle %d" % (cyc - 1)
+            assert r.n_marked_columns == expected[cyc - 1][1]
+    r = gg.update_cycle_wait(tickets[-1])
+    assert np.array_equal(outs[(n_cycles - 1) % 3], expected[-1][0])
+    assert r.n_marked_columns == expected[-1][1]
+    with pytest.raises(stvl.StvlError):
+        gg.update_cycle_wait(tickets[-1])      # already consumed
+    assert_same_voxels(gg.voxels(), og.voxels())
+    assert og.active_count() > 1000
+    gg.close()
+
+
+def test_fused_cycles_tiny_clouds_back_to_back(stvl, oracle):
+    """Many fused cycles with tiny clouds and a tiny store, enqueued back to back without any synchronisation: every
+    kernel's grid is a single CTA, so under programmatic dependent launch consecutive cycles' kernels are resident together
+    (the chunk cursors of consecutive Mark launches alternate and are never reset).  Marked counts and the final store must
+    match the oracle exactly."""
+    import torch
+    rng = np.random.default_rng(9)
+    gg = stvl.SpatioTemporalVoxelGrid(0.05, decay_model=0, voxel_decay=50.0, leaf_capacity=1 << 12)
+    og = oracle.OracleGrid(0.05, decay_model=0, voxel_decay=50.0)
+    size, res, ox, oy = 128, 0.05, -3.2, -3.2
+    cm_dev = torch.zeros((size, size), dtype=torch.uint8, device="cuda")
+    clouds = [np.concatenate([rng.uniform(-2.5, 2.5, (n, 3)), np.zeros((n, 1))], 1).astype(np.float32) for n in (37, 1500, 1024, 1, 2049, 300)]
+    dev = [torch.from_numpy(c).cuda() for c in clouds]
+    torch.cuda.synchronize()
+    n_cycles = 240
+    for cyc in range(n_cycles):
+        now = 10.0 + 0.01 * cyc
+        k = cyc % len(clouds)
+        rd = stvl.MeasurementReading((dev[k].data_ptr(), len(clouds[k]), 16, (0, 4, 8)), origin=(0.1, -0.2, 0.3), obstacle_range=2.4, now=now)
+        gg.update_cycle_device(now, [], [rd], ox, oy, res, size, size, cm_dev.data_ptr())
+        og.clear_frustums(now, None)
+        og.mark(np.ascontiguousarray(clouds[k][:, :3]), (0.1, -0.2, 0.3), 2.4, now)
+    ocm, _, on = og.update_ros_costmap(ox, oy, res, size, size)
+    assert gg.costmap_result().n_marked_columns == on
+    assert np.array_equal(cm_dev.cpu().numpy(), ocm)
+    assert_same_voxels(gg.voxels(), og.voxels())
+    gg.close()
+
+
+def test_remark_over_negative_stored_times(stvl, oracle):
+    """Clocks near zero (sim time): an accelerated sweep rewrites mark times to value - accel < 0; a later batched Mark must
+    still overwrite them (signed 64-bit max on the bit pattern — a negative double is a huge unsigned integer)."""
+    rng = np.random.default_rng(4)
+    pts = np.concatenate([rng.uniform(0.5, 2.5, (4000, 3)), np.zeros((4000, 1))], 1).astype(np.float32)
+    pts[:, 1] = rng.uniform(-0.8, 0.8, 4000).astype(np.float32)
+    pts[:, 2] = rng.uniform(-0.5, 0.5, 4000).astype(np.float32)
+    gg = stvl.SpatioTemporalVoxelGrid(0.05, decay_model=2, voxel_decay=1e6)
+    og = oracle.OracleGrid(0.05, decay_model=2, voxel_decay=1e6)
+    quat = (0.5, -0.5, 0.5, -0.5)      # optical frame looking along +x
+    def reading(now):
+        return stvl.MeasurementReading(pts, origin=(0.0, 0.0, 0.0), orientation=quat, obstacle_range=4.0, min_z=0.05, max_z=6.0,
+                                       vfov=1.2, hfov=1.4, decay_acceleration=15.0, now=now)
+    for now in (1.5, 3.0, 3.2, 6.0):
+        r = reading(now)
+        gg.ClearFrustums([r], now)
+        og.clear_frustums(now, oracle_frustums(oracle, [r]))
+        gg.Mark([r])
+        oracle_mark(oracle, og, r, now)
+        assert_same_voxels(gg.voxels(), og.voxels())
+    gg.ClearFrustums([reading(6.5)], 6.5)
+    og.clear_frustums(6.5, oracle_frustums(oracle, [reading(6.5)]))
+    compare_cycle_outputs(gg, og)
+    assert og.active_count() > 500
+    gg.close()
