@@ -1,0 +1,1 @@
+// stand-in: not used by the translation units compiled under oracle/_ref

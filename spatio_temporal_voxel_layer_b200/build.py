@@ -36,12 +36,34 @@ def _nvcc():
 def needs_build():
     if not os.path.exists(LIB_PATH):
         return True
+    if os.path.exists(STAMP_PATH):
+        return not library_matches_sources()
     t = os.path.getmtime(LIB_PATH)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(REPO_ROOT, "include", "stvl_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 TRACE_LIB_PATH = os.path.join(PKG_DIR, "libstvl_b200_trace.so")
+STAMP_PATH = LIB_PATH + ".srchash"
+
+
+def sources_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(SOURCES + HEADERS):
+        h.update(f.encode())
+        h.update(open(os.path.join(CSRC, f), "rb").read())
+    h.update(open(os.path.join(REPO_ROOT, "include", "stvl_b200.h"), "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def library_matches_sources():
+    """The library on disk was built from exactly the sources on disk (mtimes lie after a checkout or a snapshot copy)."""
+    try:
+        return os.path.exists(LIB_PATH) and open(STAMP_PATH).read().strip() == sources_hash()
+    except OSError:
+        return False
 
 
 def build_library(force=False, verbose=False, trace=False, csrc=None, out=None):
@@ -78,6 +100,9 @@ def build_library(force=False, verbose=False, trace=False, csrc=None, out=None):
             raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     if verbose:
         sys.stderr.write(log)
+    if out == LIB_PATH:
+        with open(STAMP_PATH, "w") as f:
+            f.write(sources_hash() + "\n")
     return out
 
 
