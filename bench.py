@@ -234,6 +234,179 @@ def bench_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# BASELINE config 5: warehouse map, ~50 M active voxels at 0.02 m, STRONG-scaled over the ranks (x-slab shards)
+# ------------------------------------------------------------------------------------------------
+def config5_record(args, torch, stvl, dist, rank, world, local_rank):
+    """Every rank loads and sweeps only its x-slab of the fixed 50 M-voxel map; per cycle the ranks' lethal cells are merged
+    into rank 0's costmap (packed cell bitmaps over ncclSend / ncclRecv, expanded on the root).  Size-independent checks (the
+    oracle is too slow at this size; tests/ compare a 5 M-voxel instance with it): every loaded voxel is swept, survivors +
+    cleared == swept, and the merged costmap holds exactly the cells the ranks marked."""
+    import math
+    from spatio_temporal_voxel_layer_b200 import workloads
+    w = workloads.Config5(target=args.config5_voxels, dt=DT_HEADLINE)
+    p = w.p
+    bx_lo, bx_hi = w.x_lo >> 3, w.x_hi >> 3
+    width = max(1, int(math.ceil((bx_hi - bx_lo + 1) / world)))
+    slabs = [sl for sl in range(bx_lo // width, bx_hi // width + 1) if sl % world == rank]
+    n_expected = sum(max(0, min(w.x_hi + 1, (sl + 1) * width * 8) - max(w.x_lo, sl * width * 8)) for sl in slabs) * len(w.faces) * (w.z_range[1] - w.z_range[0] + 1)
+    g = stvl.SpatioTemporalVoxelGrid(w.voxel_size, 0.0, w.decay_model, w.voxel_decay, pub_voxels=False, device=local_rank,
+                                     leaf_capacity=max(1 << 16, int(n_expected / 44) + (1 << 15)),
+                                     shard_index=rank if world > 1 else 0, shard_count=world, shard_width=width)
+    g.set_outputs(0)
+    t0 = time.perf_counter()
+    n_local, step = 0, 8_000_000
+    for sl in slabs:
+        ix, iy, iz, t = w.voxels(x_range=(sl * width * 8, (sl + 1) * width * 8))
+        n_local += len(ix)
+        for s in range(0, len(ix), step):
+            g.load_voxels(ix[s:s + step], iy[s:s + step], iz[s:s + step], t[s:s + step])
+        del ix, iy, iz, t
+    n_active = g.active_count()
+    load_s = time.perf_counter() - t0
+    assert n_active == n_local == n_expected, (n_active, n_local, n_expected)
+    ring = len(w.cycles)
+    dev_clouds = [[torch.from_numpy(c).cuda() for c in cyc.clouds] for cyc in w.cycles]
+    frustums = [np.concatenate([stvl.build_depth_frustum(p["vfov"], p["hfov"], p["min_z"], p["max_z"], o, q, p["accel"])
+                                for o, q in cyc.poses]) for cyc in w.cycles]
+    args_dev = []
+    for slot in range(ring):
+        arr = (stvl.Reading * w.n_cams)()
+        keep = []
+        for k, ((o, q), c) in enumerate(zip(w.cycles[slot].poses, dev_clouds[slot])):
+            stvl.MeasurementReading((c.data_ptr(), c.shape[0], 16, (0, 4, 8)), origin=o, orientation=q,
+                                    obstacle_range=p["obstacle_range"], now=0.0, filter=stvl.FILTER_PASSTHROUGH,
+                                    min_obstacle_height=p["min_obstacle_height"], max_obstacle_height=p["max_obstacle_height"])._fill(arr[k], 0.0, keep)
+        args_dev.append(arr)
+    cp = w.costmap_params()
+    params = stvl.CostmapParams(cp["origin_x"], cp["origin_y"], cp["resolution"], cp["size_x"], cp["size_y"], 0, 0, 254)
+    costmap_dev = torch.zeros((cp["size_y"], cp["size_x"]), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.ExternalStream(g.stream())
+    if world > 1:
+        uid = [stvl.SpatioTemporalVoxelGrid.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        g.comm_init(uid[0], rank, world)
+    L, h, check = g.L, g.h, stvl._check
+    fr_ptrs = [f.ctypes.data_as(C.c_void_p) for f in frustums]
+
+    def cycle(step_no, fused=True):
+        slot = step_no % ring
+        now = w.now0 + w.dt * (step_no + 1)
+        arr = args_dev[slot]
+        for k in range(w.n_cams):
+            arr[k].now = now + 1e-4 * k
+        if not fused:
+            check(L.stvl_clear_frustums(h, now, fr_ptrs[slot], w.n_cams))
+            check(L.stvl_mark_device(h, arr, w.n_cams))
+        elif world == 1:
+            check(L.stvl_update_cycle_device(h, now, fr_ptrs[slot], w.n_cams, arr, w.n_cams, C.byref(params), costmap_dev.data_ptr()))
+        else:
+            check(L.stvl_update_cycle_sharded_device(h, now, fr_ptrs[slot], w.n_cams, arr, w.n_cams, C.byref(params),
+                                                     costmap_dev.data_ptr(), 0, 1))
+
+    def drain():
+        if world > 1:
+            check(L.stvl_costmap_sharded_flush(h, C.byref(params), costmap_dev.data_ptr(), 0))
+
+    def barrier():
+        g.synchronize(); torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        g.synchronize(); torch.cuda.synchronize()
+
+    n, warm, steps = 0, 3, args.config5_steps
+    for _ in range(warm):
+        cycle(n); n += 1
+    drain(); barrier()
+    st0 = g.sweep_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        cycle(n); n += 1
+    drain()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    st1 = g.sweep_stats()
+    own_marked = int(g.costmap_result().n_marked_columns)
+    merged_marked = int((costmap_dev == 254).sum().item()) if rank == 0 else 0
+    # the sweep kernel's own duration: the next cycles stage by stage, the sweep bracketed by CUDA events inside the library
+    g.enable_timing(stvl.TIME_SWEEP)
+    g.timing()
+    for _ in range(5):
+        cycle(n, fused=False); n += 1
+    barrier()
+    tm = g.timing()
+    g.enable_timing(0)
+    st2 = g.sweep_stats()
+    vals = torch.tensor([float(st1.n_swept), float(st1.n_survived + st1.n_cleared), float(own_marked), float(st0.n_swept), float(st2.n_swept)],
+                        dtype=torch.float64, device="cuda")
+    tmax = torch.tensor([ms, tm.sweep_ms / max(tm.n_sweep, 1)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(vals)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    rec = None
+    if rank == 0:
+        swept = int(vals[0].item())
+        peak, _ = measured_peak_gbs()
+        sweep_ms = float(tmax[1])
+        algo = int(vals[4].item()) * 16 // world          # 16 B per active voxel, per rank (max-rank time against the mean share)
+        wpr = (cp["size_x"] + 31) // 32
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+                traffic = json.load(f).get("config5_sweep_kernel")
+        except Exception:
+            pass
+        rec = {"workload": w.name, "scaling": "strong", "n_gpus": world, "dt_s": w.dt, "steps": steps, "warmup": warm,
+               "us_per_cycle": 1e3 * float(tmax[0]) / steps, "cycles_per_s": steps / (float(tmax[0]) / 1e3),
+               "active_voxels_swept_first_timed_cycle": int(vals[3].item()), "active_voxels_swept_last_timed_cycle": swept,
+               "voxels_per_s": swept / (float(tmax[0]) / steps / 1e3),
+               "sweep_kernel": {"us_max_rank": 1e3 * sweep_ms, "algorithmic_bytes_per_rank": algo,
+                                "algorithmic_gbs": algo / (sweep_ms / 1e3) / 1e9, "algorithmic_frac_of_measured_peak": algo / (sweep_ms / 1e3) / 1e9 / peak,
+                                "note": "16 B per active voxel (SURVEY §8d) over the sweep kernel's CUDA-event time; leaves that cannot change are decided from their 84 B header, so the DRAM bytes actually moved are fewer — see dram_measured",
+                                "dram_measured": traffic},
+               "merge": {"what": "packed cell bitmaps of each rank's own x interval, ncclSend/ncclRecv to rank 0 on a side stream, expanded to bytes on the root; pipelined one cycle behind",
+                         "nvlink_bytes_per_cycle": int((world - 1) * (wpr * 4 * cp["size_y"]) / max(world, 1)) if world > 1 else 0,
+                         "dense_window_bytes_per_cycle_r1": int(world * cp["size_x"] * cp["size_y"]) if world > 1 else 0},
+               "costmap_cells": cp["size_x"] * cp["size_y"], "marked_cells_merged": merged_marked, "marked_cells_sum_of_ranks": int(vals[2].item()),
+               "checks": {"every_voxel_swept": swept == int(vals[1].item()), "merged_equals_union_of_ranks": merged_marked == int(vals[2].item())},
+               "load_s": load_s}
+    barrier()
+    if world > 1:
+        g.comm_destroy()
+    del costmap_dev, dev_clouds
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    g.close()
+    return rec
+
+
+def other_configs_record(args, stvl):
+    """Configs 1, 3 and 4 (N = 1): device-resident fused cycles per second at full size, the CPU oracle on the same cycles, and a
+    bit-exact comparison of the final state (voxels + mark times, per-column counts, last costmap bytes)."""
+    import bench_configs as BC
+    from spatio_temporal_voxel_layer_b200 import workloads
+    out = {}
+    for name, cls, kw in (("config1", workloads.Config1, dict(n_cycles=20)), ("config3", workloads.Config3, dict(n_cycles=20)),
+                          ("config4", workloads.Config4, dict(n_cycles=8))):
+        w = cls(**kw)
+        warm = 5 if w.n_cycles >= 15 else 3
+        gpu = BC.run_gpu(stvl, w, warmup=warm)
+        ora = BC.run_oracle(w, warmup=warm)
+        cmpr = BC.compare(gpu, ora)
+        st = gpu["grid"].sweep_stats()
+        out[name] = {"workload": w.name, "points_per_cycle": w.points_per_cycle, "cycles_timed": gpu["n_timed"], "dt_s": w.dt,
+                     "cycles_per_s": gpu.get("cycles_per_s"), "us_per_cycle": gpu.get("us_per_cycle"), "gpu_launches": gpu.get("launches"),
+                     "mark_bytes_per_cycle": w.points_per_cycle * 16,
+                     "mark_bytes_rate_gbs": (w.points_per_cycle * 16 / (gpu["us_per_cycle"] * 1e-6) / 1e9) if gpu.get("us_per_cycle") else None,
+                     "active_voxels_end": cmpr["n_voxels"], "swept_last_cycle": int(st.n_swept),
+                     "cpu_oracle_cycles_per_s": len(ora["times"]) / sum(ora["times"]) if ora["times"] else None,
+                     "parity_checked": bool(cmpr["voxels"] and cmpr["columns"] and cmpr["costmap"]), "parity": cmpr}
+        gpu["grid"].close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def sorted_voxels(v):
@@ -540,6 +713,14 @@ def bench_ours(args):
     value = world * args.steps / (dev_ms / 1e3)
     e2e = world * args.steps / e2e_s
 
+    # tear the headline handle's buffers down before the other configs allocate theirs
+    others = None
+    if world == 1 and not args.no_other_configs:
+        others = other_configs_record(args, stvl)
+    c5 = None
+    if not args.no_config5:
+        c5 = config5_record(args, torch, stvl, dist, rank, world, local_rank)
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         line = {
@@ -565,6 +746,10 @@ def bench_ours(args):
             line["parity"] = parity
         if sensitivity:
             line["sensitivity"] = sensitivity
+        if others is not None:
+            line["other_configs"] = others
+        if c5 is not None:
+            line["config5"] = c5
         if t_all is not None and t_all.n_mark:
             mark_s = t_all.mark_ms / t_all.n_mark / 1e3
             algo_mark = w.points_per_cycle * 16          # 16 B read per input point
@@ -620,6 +805,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-sensitivity", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the configs 1, 3, 4 records (N = 1)")
+    ap.add_argument("--no-config5", action="store_true", help="skip the strong-scaled config-5 record")
+    ap.add_argument("--config5-voxels", type=int, default=50_000_000)
+    ap.add_argument("--config5-steps", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

@@ -83,6 +83,91 @@ class Config2:
                     mark_threshold=0, default_value=0)
 
 
+class Sensor:
+    """One observation source of a cycle: pose, cloud (float32 (N,4), global frame) and the reference's per-source parameters."""
+
+    def __init__(self, model_type, origin, quat, cloud, params, filter_name):
+        self.model_type = model_type      # 0 depth camera, 1 3-D lidar (measurement_reading.h:49-53)
+        self.origin, self.quat, self.cloud = origin, quat, cloud
+        self.p = params                   # synth.RGBD / synth.VLP16 style dict
+        self.filter = filter_name         # "passthrough" | "voxel" | "none"
+
+
+class GrowingConfig:
+    """Configs 1, 3 and 4 of BASELINE.json: the store starts EMPTY and grows while the robot drives (`n_cycles` distinct
+    cycles, dt seconds apart).  cycle(j) -> (now, [Sensor...]); clearing and marking use the same sensors, as in the
+    reference's example configs."""
+    voxel_size = 0.05
+    decay_model = 0
+    voxel_decay = 15.0
+    voxel_min_points = 0
+
+    def __init__(self, n_cycles, dt=0.2, now0=1.7e9):
+        self.n_cycles, self.dt, self.now0 = n_cycles, dt, now0
+        self.cycles = []
+
+    def cycle(self, j):
+        return self.now0 + self.dt * (j + 1), self.cycles[j % len(self.cycles)]
+
+    @property
+    def points_per_cycle(self):
+        return sum(len(s.cloud) for s in self.cycles[0])
+
+    def costmap_params(self):
+        return dict(origin_x=-16.0, origin_y=-16.0, resolution=self.voxel_size, size_x=int(round(32.0 / self.voxel_size)),
+                    size_y=int(round(32.0 / self.voxel_size)), mark_threshold=0, default_value=255)   # track_unknown_space: true
+
+
+class Config1(GrowingConfig):
+    name = "config1: single depth camera 640x480, 0.05 m, linear decay 15 s, store grows from empty"
+
+    def __init__(self, n_cycles=20, width=IMG_W, height=IMG_H, seed=1001, **kw):
+        super().__init__(n_cycles, **kw)
+        scene = synth.retail_scene(size=30.0, seed=3)
+        for c in range(n_cycles):
+            yaw = 0.05 + 0.04 * c
+            o = (-6.0 + 0.15 * c, 2.3 - 13.5 + 12.0, 0.6)
+            q = synth.optical_quat(yaw)
+            self.cycles.append([Sensor(0, o, q, synth.depth_cloud(scene, o, q, width=width, height=height, seed=seed * 100 + c), synth.RGBD, "passthrough")])
+
+
+class Config3(GrowingConfig):
+    name = "config3: VLP-16 hourglass lidar (16 x 1800), 360 deg hFOV, exponential decay, VOXEL pre-filter, 0.05 m"
+    decay_model = 1
+
+    def __init__(self, n_cycles=20, rings=16, azimuths=1800, seed=1003, **kw):
+        super().__init__(n_cycles, **kw)
+        scene = synth.retail_scene(size=30.0, seed=3)
+        for c in range(n_cycles):
+            o = (-6.0 + 0.15 * c, 2.3 - 13.5 + 12.0, 0.9)
+            q = synth.yaw_quat(0.03 * c)
+            # (the reference example marks with obstacle_range 3.0 and a 0.3 .. 2.0 m window, vlp16_config.yaml:26-28)
+            prm = dict(synth.VLP16, obstacle_range=3.0, min_obstacle_height=0.3, max_obstacle_height=2.0)
+            self.cycles.append([Sensor(1, o, q, synth.lidar_cloud(scene, o, q, rings=rings, azimuths=azimuths, seed=seed * 100 + c), prm, "voxel")])
+
+
+class Config4(GrowingConfig):
+    name = "config4: Ouster-128 (128 x 1024) + 4 RGBD 640x480, VOXEL pre-filter on, 0.02 m, linear decay 15 s"
+    voxel_size = 0.02
+    voxel_min_points = 1
+
+    def __init__(self, n_cycles=12, rings=128, azimuths=1024, width=IMG_W, height=IMG_H, seed=1004, **kw):
+        super().__init__(n_cycles, **kw)
+        scene = synth.retail_scene(size=30.0, seed=3)
+        for c in range(n_cycles):
+            centre = (-6.0 + 0.15 * c, 2.3 - 13.5 + 12.0, 0.0)
+            lo, lq = (centre[0], centre[1], 1.0), synth.yaw_quat(0.03 * c)
+            lidar = dict(vfov=0.785, vpad=0.03, hfov=6.29, min_z=0.5, max_z=8.0, accel=5.0, obstacle_range=6.0,
+                         min_obstacle_height=0.1, max_obstacle_height=2.2)
+            sensors = [Sensor(1, lo, lq, synth.lidar_cloud(scene, lo, lq, rings=rings, azimuths=azimuths, vfov=0.785, seed=seed * 100 + c), lidar, "voxel")]
+            for k, (o, q) in enumerate(synth.camera_ring(centre, 0.1 + 0.03 * c, n_cams=4)):
+                sensors.append(Sensor(0, o, q, synth.depth_cloud(scene, o, q, width=width, height=height, seed=seed * 100 + 10 * c + k), synth.RGBD, "voxel"))
+            self.cycles.append(sensors)
+
+    def costmap_params(self):
+        return dict(origin_x=-16.0, origin_y=-16.0, resolution=0.05, size_x=640, size_y=640, mark_threshold=0, default_value=255)
+
+
 class Config5:
     """BASELINE config 5: warehouse map, ~50 M active voxels at 0.02 m (thin vertical rack faces: no solid 8^3 blocks),
     7 RGBD cameras on the robot (small mark load), linear decay.  The map is built procedurally as disjoint sheets, so the

@@ -855,3 +855,70 @@ def test_remark_over_negative_stored_times(stvl, oracle):
     compare_cycle_outputs(gg, og)
     assert og.active_count() > 500
     gg.close()
+
+
+@pytest.mark.parametrize("config", ["config1", "config3", "config4"])
+def test_full_size_configs_fused_cycle(stvl, oracle, config):
+    """BASELINE configs 1, 3 and 4 at FULL size (640x480 depth images, 16 x 1800 VLP-16 scans, 128 x 1024 Ouster scans + 4
+    RGBD with the VOXEL pre-filter at 0.02 m) through the fused device cycle, cycle for cycle against the oracle: final voxel
+    store with mark times, per-column counts and the last costmap bytes, bit-exact."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench_configs as BC
+    from spatio_temporal_voxel_layer_b200 import workloads
+    w = {"config1": lambda: workloads.Config1(n_cycles=8), "config3": lambda: workloads.Config3(n_cycles=8),
+         "config4": lambda: workloads.Config4(n_cycles=3)}[config]()
+    gpu = BC.run_gpu(stvl, w, warmup=0, timed=False)
+    ora = BC.run_oracle(w, warmup=0)
+    c = BC.compare(gpu, ora)
+    gpu["grid"].close()
+    assert c["voxels"] and c["columns"] and c["costmap"], c
+    assert c["n_voxels"] > 1000 and c["marked_cells"] > 50, c
+
+
+def test_config5_five_million_voxels_against_oracle(stvl, oracle):
+    """Config 5 mechanics at a size the oracle still handles (5 M voxels at 0.02 m, ~1 s per oracle cycle): two fused cycles on
+    one unsharded grid — costmap bytes of a 10000 x 6000 map, per-column counts, the whole voxel store with its mark times."""
+    import torch
+    from spatio_temporal_voxel_layer_b200 import synth, workloads
+    w = workloads.Config5(target=5_000_000, dt=0.2)
+    p = w.p
+    ix, iy, iz, t = w.voxels()
+    assert 4_000_000 < len(ix) < 7_000_000
+    gg = stvl.SpatioTemporalVoxelGrid(w.voxel_size, 0.0, w.decay_model, w.voxel_decay, leaf_capacity=len(ix) // 40 + (1 << 15))
+    gg.set_outputs(0)
+    og = oracle.OracleGrid(w.voxel_size, 0.0, w.decay_model, w.voxel_decay, False)
+    gg.load_voxels(ix, iy, iz, t)
+    og.load_voxels(ix, iy, iz, t)
+    cp = w.costmap_params()
+    cm_dev = torch.zeros((cp["size_y"], cp["size_x"]), dtype=torch.uint8, device="cuda")
+    keep = []
+    for cyc in range(2):
+        now, poses, clouds = w.cycle(cyc)
+        readings, dev_readings = [], []
+        for k, ((o, q), cl) in enumerate(zip(poses, clouds)):
+            r = stvl.MeasurementReading(cl, origin=o, orientation=q, obstacle_range=p["obstacle_range"], min_z=p["min_z"], max_z=p["max_z"],
+                                        vfov=p["vfov"], hfov=p["hfov"], decay_acceleration=p["accel"], now=now + 1e-4 * k,
+                                        filter=stvl.FILTER_PASSTHROUGH, min_obstacle_height=p["min_obstacle_height"],
+                                        max_obstacle_height=p["max_obstacle_height"])
+            readings.append(r)
+            td = torch.from_numpy(np.ascontiguousarray(cl, np.float32)).cuda()
+            keep.append(td)
+            dev_readings.append(stvl.MeasurementReading((td.data_ptr(), len(cl), 16, (0, 4, 8)), origin=o, orientation=q,
+                                                        obstacle_range=p["obstacle_range"], now=now + 1e-4 * k, filter=stvl.FILTER_PASSTHROUGH,
+                                                        min_obstacle_height=p["min_obstacle_height"], max_obstacle_height=p["max_obstacle_height"]))
+        gg.update_cycle_device(now, readings, dev_readings, cp["origin_x"], cp["origin_y"], cp["resolution"], cp["size_x"], cp["size_y"],
+                               cm_dev.data_ptr(), mark_threshold=0, default_value=0)
+        og.clear_frustums(now, oracle_frustums(oracle, readings))
+        for r in readings:
+            oracle_mark(oracle, og, r, now)
+        ocm, _, on = og.update_ros_costmap(cp["origin_x"], cp["origin_y"], cp["resolution"], cp["size_x"], cp["size_y"], 0, 0)
+        assert gg.costmap_result().n_marked_columns == on
+        assert np.array_equal(cm_dev.cpu().numpy(), ocm), "costmap bytes differ in cycle %d" % cyc
+        gx, gy, gc = gg.GetFlattenedCostmap()
+        assert_same_columns((gx, gy, gc), og.costmap())
+        st = gg.sweep_stats()
+        assert st.n_swept == st.n_survived + st.n_cleared and st.n_swept > 4_000_000
+    assert_same_voxels(gg.voxels(), og.voxels())
+    gg.close()
