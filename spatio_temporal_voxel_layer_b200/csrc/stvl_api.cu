@@ -97,10 +97,9 @@ struct stvl_grid {
   DevBuf<int32_t> cleared, ambiguous;
   DevBuf<uint8_t> costmap;
   // VOXEL pre-filter scratch (keys / point indices double-buffered for the radix sort, CUB temp, filtered clouds)
-  DevBuf<unsigned long long> vf_keys_a, vf_keys_b;
-  DevBuf<uint32_t> vf_vals_a, vf_vals_b;
-  DevBuf<uint8_t> vf_temp;
+  DevBuf<uint8_t> vf_scratch;
   DevBuf<float4> vf_out;
+  DevBuf<unsigned long long> vf_nout;   // per filtered reading: number of centroids (device counters read by Mark)
   size_t costmap_clean_bytes = 0;     // the internal costmap buffer is already filled with costmap_clean_value ...
   int costmap_clean_value = -1;       // ... over this many bytes (re-armed after every copy-out)
   DevBuf<int32_t> col_ix, col_iy;
@@ -536,7 +535,7 @@ uint32_t tiles_upper(const stvl_grid * g)
 }
 
 int build_batches(stvl_grid * g, const stvl_reading_t * readings, uint32_t n, const std::vector<const uint8_t *> & dev_ptrs,
-                  std::vector<MarkBatch> * out, uint64_t * total_points, double * max_now, bool * monotone)
+                  const std::vector<const unsigned long long *> & n_dev, std::vector<MarkBatch> * out, uint64_t * total_points, double * max_now, bool * monotone)
 {
   MarkBatch cur{};
   double prev_now = -std::numeric_limits<double>::infinity();
@@ -559,6 +558,7 @@ int build_batches(stvl_grid * g, const stvl_reading_t * readings, uint32_t n, co
     DevReading & d = cur.r[cur.n_readings++];
     d.data = dev_ptrs[i];
     d.n_points = r.n_points;
+    d.n_points_dev = n_dev[i];
     d.point_step = r.point_step; d.off_x = r.off_x; d.off_y = r.off_y; d.off_z = r.off_z;
     d.ox = r.origin[0]; d.oy = r.origin[1]; d.oz = r.origin[2];
     d.now = r.now;
@@ -620,35 +620,34 @@ int validate_readings(const stvl_reading_t * readings, uint32_t n)
 }
 
 // VOXEL pre-filter (reference measurement_buffer.cpp:153-164) for the readings that ask for it: each such reading is
-// replaced by its filtered cloud (one float4 slot per input point, see stvl_voxel_filter.cu) before Mark sees it.
-int apply_voxel_filters(stvl_grid * g, std::vector<stvl_reading_t> & rs, std::vector<const uint8_t *> & dev_ptrs)
+// replaced by its filtered cloud — compact centroids, their count in a device counter (see stvl_voxel_filter.cu) — before
+// Mark sees it.  n_dev[i] receives the counter's address (NULL for unfiltered readings).
+int apply_voxel_filters(stvl_grid * g, std::vector<stvl_reading_t> & rs, std::vector<const uint8_t *> & dev_ptrs,
+                        std::vector<const unsigned long long *> & n_dev)
 {
-  size_t total = 0, max_n = 0;
+  size_t total = 0, max_n = 0, n_filtered = 0;
   for (const stvl_reading_t & r : rs)
-    if (r.marking && r.n_points && r.filter == STVL_FILTER_VOXEL) { total += (size_t)r.n_points; max_n = std::max<size_t>(max_n, (size_t)r.n_points); }
+    if (r.marking && r.n_points && r.filter == STVL_FILTER_VOXEL) { total += (size_t)r.n_points; max_n = std::max<size_t>(max_n, (size_t)r.n_points); ++n_filtered; }
   if (total == 0) return STVL_OK;
   int rc;
-  rc = ensure(g, g->vf_keys_a, max_n); if (rc != STVL_OK) return rc;
-  rc = ensure(g, g->vf_keys_b, max_n); if (rc != STVL_OK) return rc;
-  rc = ensure(g, g->vf_vals_a, max_n); if (rc != STVL_OK) return rc;
-  rc = ensure(g, g->vf_vals_b, max_n); if (rc != STVL_OK) return rc;
-  const size_t temp_bytes = voxel_filter_temp_bytes(max_n);
-  rc = ensure(g, g->vf_temp, temp_bytes + 256); if (rc != STVL_OK) return rc;
+  rc = ensure(g, g->vf_scratch, voxel_filter_scratch_bytes(max_n)); if (rc != STVL_OK) return rc;
   rc = ensure(g, g->vf_out, total); if (rc != STVL_OK) return rc;
-  size_t off = 0;
+  rc = ensure(g, g->vf_nout, n_filtered); if (rc != STVL_OK) return rc;
+  size_t off = 0, k = 0;
   for (size_t i = 0; i < rs.size(); ++i) {
     stvl_reading_t & r = rs[i];
     if (!(r.marking && r.n_points && r.filter == STVL_FILTER_VOXEL)) continue;
     CU(launch_voxel_filter(dev_ptrs[i], r.n_points, r.point_step, r.off_x, r.off_y, r.off_z, g->cfg.voxel_size,
-                           r.min_obstacle_height, r.max_obstacle_height, r.voxel_min_points, r.origin, r.has_transform ? r.transform : nullptr,
-                           g->vf_keys_a.p, g->vf_keys_b.p, g->vf_vals_a.p, g->vf_vals_b.p, g->vf_temp.p, temp_bytes,
-                           g->vf_out.p + off, g->stream));
-    g->launches += 3;
+                           r.min_obstacle_height, r.max_obstacle_height, r.voxel_min_points, r.has_transform ? r.transform : nullptr,
+                           g->vf_scratch.p, g->vf_out.p + off, g->vf_nout.p + k, g->sm_count, g->stream));
+    g->launches += 4;
     dev_ptrs[i] = reinterpret_cast<const uint8_t *>(g->vf_out.p + off);
+    n_dev[i] = g->vf_nout.p + k;
     r.point_step = 16; r.off_x = 0; r.off_y = 4; r.off_z = 8;
     r.filter = STVL_FILTER_NONE;   // the z window was applied by the filter
     r.has_transform = 0;           // ... and so was the sensor -> global transform
     off += (size_t)r.n_points;
+    ++k;
   }
   return STVL_OK;
 }
@@ -658,9 +657,10 @@ int run_mark(stvl_grid * g, const stvl_reading_t * readings_in, uint32_t n, cons
 {
   std::vector<stvl_reading_t> rs(readings_in, readings_in + n);
   std::vector<const uint8_t *> dev_ptrs(dev_ptrs_in);
+  std::vector<const unsigned long long *> n_dev(n, nullptr);
   {
     const uint64_t launches_before = g->launches;
-    const int rc = apply_voxel_filters(g, rs, dev_ptrs);
+    const int rc = apply_voxel_filters(g, rs, dev_ptrs, n_dev);
     if (rc != STVL_OK) return rc;
     if (fz && g->launches != launches_before) fz->pdl = false;   // filter kernels sit between the sweep and Mark
   }
@@ -669,7 +669,7 @@ int run_mark(stvl_grid * g, const stvl_reading_t * readings_in, uint32_t n, cons
   uint64_t total_points = 0;
   double max_now = 0;
   bool monotone = true;
-  int rc = build_batches(g, readings, n, dev_ptrs, &batches, &total_points, &max_now, &monotone);
+  int rc = build_batches(g, readings, n, dev_ptrs, n_dev, &batches, &total_points, &max_now, &monotone);
   if (rc != STVL_OK) return rc;
   if (batches.empty()) return STVL_OK;
   // batched launches resolve "later reading overwrites" by atomicMax, which is only the same thing when clocks are
@@ -1022,7 +1022,7 @@ int stvl_destroy(stvl_grid_t * g)
   cudaFree(g->stage.p); cudaFree(g->frustums.p); cudaFree(g->points.p); cudaFree(g->cleared.p); cudaFree(g->ambiguous.p);
   cudaFree(g->costmap.p); cudaFree(g->col_ix.p); cudaFree(g->col_iy.p); cudaFree(g->col_cnt.p);
   cudaFree(g->dump_x.p); cudaFree(g->dump_y.p); cudaFree(g->dump_z.p); cudaFree(g->dump_t.p);
-  cudaFree(g->vf_keys_a.p); cudaFree(g->vf_keys_b.p); cudaFree(g->vf_vals_a.p); cudaFree(g->vf_vals_b.p); cudaFree(g->vf_temp.p); cudaFree(g->vf_out.p);
+  cudaFree(g->vf_scratch.p); cudaFree(g->vf_out.p); cudaFree(g->vf_nout.p);
   if (g->h_ctr) cudaFreeHost(g->h_ctr);
   if (g->h_live) cudaFreeHost(g->h_live);
   for (int i = 0; i < stvl_grid::kFrustumRing; ++i) {

@@ -31,6 +31,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t * p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t * p) { return *reinterpret_cast<const volatile uint64_t *>(p); }
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long * p) { return *reinterpret_cast<const volatile unsigned long long *>(p); }
 __device__ __forceinline__ void prefetch_l2(const void * p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 // ---- mbarrier + 1-D bulk copy (TMA engine, SASS UBLKCP / SYNCS) -----------------------------------------------------------

@@ -138,7 +138,8 @@ struct FrustumParams {
 // -------- one marking reading on the device -----------------------------------------
 struct DevReading {
   const uint8_t * data;
-  unsigned long long n_points;
+  unsigned long long n_points;                  // number of points (an upper bound when n_points_dev is set)
+  const unsigned long long * n_points_dev;      // non-NULL: the actual count lives on the device (output of the VOXEL pre-filter)
   uint32_t point_step, off_x, off_y, off_z;
   double ox, oy, oz;
   double now;

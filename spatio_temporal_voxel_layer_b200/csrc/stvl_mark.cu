@@ -36,10 +36,10 @@ static_assert(kMarkPPT == 2, "the consumer loop is written for two points per th
 struct PointXYZ { float x, y, z; bool ok; };
 
 // generic PointCloud2 layouts (anything that is not packed x,y,z,pad float4): straight from global memory
-__device__ __forceinline__ PointXYZ load_point_generic(const DevReading & r, unsigned long long i)
+__device__ __forceinline__ PointXYZ load_point_generic(const DevReading & r, unsigned long long i, bool exists)
 {
   PointXYZ p;
-  if (i >= r.n_points) { p.x = p.y = p.z = 0.f; p.ok = false; return p; }
+  if (!exists) { p.x = p.y = p.z = 0.f; p.ok = false; return p; }
   if (r.vec4) {
     const float4 v = __ldcs(reinterpret_cast<const float4 *>(r.data) + i);
     p.x = v.x; p.y = v.y; p.z = v.z;
@@ -150,7 +150,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
   __shared__ uint32_t s_slot[kMarkTable];
   __shared__ double s_rnow[kMaxBatchReadings];
   __shared__ __align__(8) uint64_t s_full[kMarkStagesMax], s_empty[kMarkStagesMax];
-  __shared__ uint32_t s_chunk[kMarkStagesMax], s_ri[kMarkStagesMax];
+  __shared__ uint32_t s_chunk[kMarkStagesMax], s_ri[kMarkStagesMax], s_cnt[kMarkStagesMax];   // per stage: chunk id, reading, points in it
   __shared__ unsigned int s_fill;          // claimed table entries
   __shared__ unsigned int s_flushes;       // early flushes done (the producer requests at most one at a time)
   __shared__ unsigned int s_drop[2];
@@ -210,15 +210,20 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
             mbar_wait(&s_empty[stage], ((it / (uint32_t)n_stages) & 1u) ^ 1u);
           }
           const int ri = mark_reading_of(batch, id);
+          const DevReading & rd = batch.r[ri];
+          // points of the reading: the host's count, or (output of the VOXEL pre-filter) a device counter below that bound
+          unsigned long long n_pts = rd.n_points;
+          if (rd.n_points_dev) { const unsigned long long nd = ld_volatile_u64(rd.n_points_dev); if (nd < n_pts) n_pts = nd; }
+          const unsigned long long base = (unsigned long long)(id - batch.first_block[ri]) * kMarkChunk;
+          if (base >= n_pts) continue;   // chunk beyond the actual count: nothing to hand out
+          const unsigned long long left = n_pts - base;
+          const uint32_t in_chunk = (uint32_t)(left < (unsigned long long)kMarkChunk ? left : (unsigned long long)kMarkChunk);
           s_chunk[stage] = id;
           s_ri[stage] = (uint32_t)ri;
+          s_cnt[stage] = in_chunk;
           if constexpr (kVec4) {
-            const DevReading & rd = batch.r[ri];
-            const unsigned long long base = (unsigned long long)(id - batch.first_block[ri]) * kMarkChunk;
-            const unsigned long long left = rd.n_points - base;
-            const uint32_t bytes = (uint32_t)(left < (unsigned long long)kMarkChunk ? left : (unsigned long long)kMarkChunk) * 16u;
-            mbar_arrive_expect_tx(&s_full[stage], bytes);
-            bulk_load(s_stage + (size_t)stage * kMarkChunk, rd.data + base * 16ull, bytes, &s_full[stage], policy);
+            mbar_arrive_expect_tx(&s_full[stage], in_chunk * 16u);
+            bulk_load(s_stage + (size_t)stage * kMarkChunk, rd.data + base * 16ull, in_chunk * 16u, &s_full[stage], policy);
           } else {
             mbar_arrive(&s_full[stage]);
           }
@@ -367,10 +372,8 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
     const int ri = (int)s_ri[stage];
     const DevReading & par = batch.r[ri];   // warp-uniform parameter-bank reads
     PointXYZ pts[kMarkPPT];
+    const unsigned in_chunk = s_cnt[stage];
     if constexpr (kVec4) {
-      const unsigned long long base = (unsigned long long)(chunk - batch.first_block[ri]) * kMarkChunk;
-      const unsigned long long left = par.n_points - base;
-      const unsigned in_chunk = left < (unsigned long long)kMarkChunk ? (unsigned)left : (unsigned)kMarkChunk;
 #pragma unroll
       for (int k = 0; k < kMarkPPT; ++k) {
         const unsigned idx = (unsigned)k * kMarkConsumers + threadIdx.x;
@@ -381,7 +384,10 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
     } else {
       const unsigned long long base = (unsigned long long)(chunk - batch.first_block[ri]) * kMarkChunk;
 #pragma unroll
-      for (int k = 0; k < kMarkPPT; ++k) pts[k] = load_point_generic(par, base + (unsigned long long)k * kMarkConsumers + threadIdx.x);
+      for (int k = 0; k < kMarkPPT; ++k) {
+        const unsigned idx = (unsigned)k * kMarkConsumers + threadIdx.x;
+        pts[k] = load_point_generic(par, base + idx, idx < in_chunk);
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[stage]);   // the stage may be refilled: this warp holds its points in registers
