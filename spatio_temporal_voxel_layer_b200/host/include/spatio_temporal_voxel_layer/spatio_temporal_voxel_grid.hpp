@@ -83,6 +83,9 @@ public:
 
   // Save the grid with size information (simple binary dump of (ix,iy,iz,time); .vdb needs OpenVDB)
   bool SaveGrid(const std::string & file_name, double & map_size_bytes);
+  // Extension (the reference has no loader; its saved .vdb files are read back by vdb2pc only): replaces the grid's
+  // contents with the voxels of a file written by SaveGrid ("<file_name>.stvl"; the voxel size must match).
+  bool LoadGrid(const std::string & file_name);
 
   // ---- additions for the fused GPU path (not in the reference) ----------------------------------------------------
   // UpdateROSCostmap's grid loop on the device: bytes of the layer's costmap + touched bounds, no host map in between

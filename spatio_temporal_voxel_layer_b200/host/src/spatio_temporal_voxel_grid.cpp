@@ -312,6 +312,40 @@ bool SpatioTemporalVoxelGrid::SaveGrid(const std::string & file_name, double & m
 }
 
 /*****************************************************************************/
+bool SpatioTemporalVoxelGrid::LoadGrid(const std::string & file_name)
+/*****************************************************************************/
+{
+  // reader of SaveGrid's flat binary: "STVLGRD1", voxel_size f64, n u64, then n x (ix,iy,iz i32, t f64)
+  std::unique_lock<std::mutex> lock(_grid_lock);
+  try {
+    std::ifstream f(file_name + ".stvl", std::ios::binary);
+    char magic[8];
+    double vs = 0.;
+    uint64_t n = 0;
+    if (!f || !f.read(magic, 8) || std::memcmp(magic, "STVLGRD1", 8) != 0) {return false;}
+    f.read(reinterpret_cast<char *>(&vs), 8);
+    f.read(reinterpret_cast<char *>(&n), 8);
+    if (!f || vs != stvl_voxel_size(_grid)) {
+      std::cout << "Saved grid has another voxel size." << std::endl;
+      return false;
+    }
+    std::vector<int32_t> ix(n), iy(n), iz(n);
+    std::vector<double> t(n);
+    for (uint64_t i = 0; i < n; ++i) {
+      f.read(reinterpret_cast<char *>(&ix[i]), 4);
+      f.read(reinterpret_cast<char *>(&iy[i]), 4);
+      f.read(reinterpret_cast<char *>(&iz[i]), 4);
+      f.read(reinterpret_cast<char *>(&t[i]), 8);
+    }
+    if (!f) {return false;}
+    if (stvl_reset(_grid) != STVL_OK) {return false;}
+    return n == 0 || stvl_load_voxels(_grid, ix.data(), iy.data(), iz.data(), t.data(), n) == STVL_OK;
+  } catch (...) {
+    return false;
+  }
+}
+
+/*****************************************************************************/
 bool SpatioTemporalVoxelGrid::FlattenToCostmap(
   double origin_x, double origin_y, double resolution, unsigned int size_x, unsigned int size_y, int mark_threshold,
   unsigned char default_value, unsigned char * costmap, stvl_costmap_result_t * result)

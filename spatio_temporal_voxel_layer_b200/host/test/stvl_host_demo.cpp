@@ -115,7 +115,10 @@ int main(int argc, char ** argv)
   out.write(reinterpret_cast<const char *>(parent.getCostmap()->getCharMap()), (std::streamsize)sx * sy);
   double bytes = 0.;
   const bool saved = layer.SaveGrid(std::string(argv[2]) + ".grid", bytes);
-  const uint32_t ok = saved ? 1u : 0u;
+  // round trip of the saved grid: load it back (replaces the store) and save it again
+  double bytes2 = 0.;
+  const bool reloaded = saved && layer.Grid()->LoadGrid(std::string(argv[2]) + ".grid") && layer.SaveGrid(std::string(argv[2]) + ".grid2", bytes2);
+  const uint32_t ok = saved ? (reloaded ? 1u : 2u) : 0u;
   wr(out, ok);
   std::printf("stvl_host_demo: %u cycles, %s costmap path, grid saved=%u (%.0f device bytes)\n", n_cycles, literal ? "literal host" : "fused GPU", ok, bytes);
   return 0;

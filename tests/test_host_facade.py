@@ -63,6 +63,33 @@ def read_output(path, n_cells):
     return out, master, saved
 
 
+def test_stvl2pc_converter(tmp_path):
+    """stvl2pc (pure host code) on a hand-written .stvl file: lower corners like vdb2pc, centres and times on request."""
+    subprocess.check_call(["make", "-C", HOST, "-s", "stvl2pc"])
+    vs = float(np.float32(0.05))
+    rec = np.array([(-3, 2, 7, 100.25), (0, 0, 0, -1.5), (123456, -654321, 40, 1.7e9)], np.dtype([("x", "<i4"), ("y", "<i4"), ("z", "<i4"), ("t", "<f8")]))
+    path = tmp_path / "g.stvl"
+    with open(path, "wb") as f:
+        f.write(b"STVLGRD1" + struct.pack("<dQ", vs, len(rec)))
+        for r in rec:
+            f.write(struct.pack("<iiid", int(r["x"]), int(r["y"]), int(r["z"]), float(r["t"])))
+    tool = os.path.join(HOST, "stvl2pc")
+    out = tmp_path / "g.pcd"
+    assert subprocess.run([tool, str(path), str(out)]).returncode == 0
+    lines = open(out).read().splitlines()
+    assert "FIELDS x y z" in lines and "POINTS 3" in lines
+    pts = np.loadtxt(out, skiprows=11, dtype=np.float32).reshape(-1, 3)
+    want = np.stack([(rec[k].astype(np.float64) * vs).astype(np.float32) for k in ("x", "y", "z")], 1)
+    assert np.array_equal(pts, want)
+    assert subprocess.run([tool, str(path), str(out), "--centres", "--times"]).returncode == 0
+    full = np.loadtxt(out, skiprows=11).reshape(-1, 4)
+    assert np.array_equal(full[:, :3].astype(np.float32), np.stack([(rec[k].astype(np.float64) * vs + vs / 2).astype(np.float32) for k in ("x", "y", "z")], 1))
+    assert np.array_equal(full[:, 3], rec["t"])
+    bad = tmp_path / "bad.stvl"
+    bad.write_bytes(b"NOTAGRID" + b"\0" * 16)
+    assert subprocess.run([tool, str(bad), str(out)], capture_output=True).returncode == 1
+
+
 def test_host_code_builds_and_refuses_without_gpu(tmp_path, stvl):
     build_host()
     scen = tmp_path / "s.bin"
@@ -148,3 +175,14 @@ def test_plugin_cycle_matches_oracle(tmp_path, stvl, oracle, literal):
     a = np.sort(rec, order=["x", "y", "z"])
     o = np.sort(np.rec.fromarrays([ix, iy, iz, t], names="x,y,z,t"), order=["x", "y", "z"])
     assert np.array_equal(a["x"], o["x"]) and np.array_equal(a["z"], o["z"]) and np.array_equal(a["t"], o["t"])
+    # SaveGrid -> LoadGrid -> SaveGrid round trip (the demo reloads the saved grid and saves it again): same voxels, same times
+    raw2 = open(str(outp) + ".grid2.stvl", "rb").read()
+    rec2 = np.frombuffer(raw2[24:], rec.dtype)
+    assert raw2[:24] == raw[:24] and np.array_equal(np.sort(rec2, order=["x", "y", "z"]), a)
+    # ... and the converter (the counterpart of the reference's vdb2pc) lists every voxel's lower corner, coord * voxel_size
+    pcd = str(outp) + ".pcd"
+    r2 = subprocess.run([os.path.join(HOST, "stvl2pc"), str(outp) + ".grid.stvl", pcd], capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stderr
+    pts = np.loadtxt(pcd, skiprows=11, dtype=np.float32).reshape(-1, 3)
+    want = np.stack([(rec[k].astype(np.float64) * vs).astype(np.float32) for k in ("x", "y", "z")], 1)
+    assert np.array_equal(pts, want)
