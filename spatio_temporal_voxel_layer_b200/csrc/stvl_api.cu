@@ -348,7 +348,10 @@ int rebuild_leaf_hash(stvl_grid * g)
   g->launches += 1;
   return STVL_OK;
 }
-int rebuild_tiles(stvl_grid * g)
+// Rebuild the tile table from the live leaves (drops the tiles of emptied leaf columns, renumbers the rest).
+// old_keys / old_counts (n_old tiles): the tile keys and the count rows of the LAST sweep as they were before the rebuild;
+// they are carried over to the renumbered tiles, so the reference's _cost_map survives until the next sweep refills it.
+int rebuild_tiles(stvl_grid * g, const uint64_t * old_keys = nullptr, const uint32_t * old_counts = nullptr, uint32_t n_old = 0)
 {
   GridView & v = g->v;
   CU(cudaMemsetAsync(v.tile_hash_keys, 0xFF, ((size_t)v.tile_hash_mask + 1) * 8, g->stream));
@@ -358,6 +361,10 @@ int rebuild_tiles(stvl_grid * g)
   CU(cudaMemsetAsync(&v.ctr->tile_overflow, 0, 4, g->stream));
   CU(launch_reassign_tiles(v, v.leaf_capacity, g->sm_count, g->stream));
   g->launches += 1;
+  if (old_keys && old_counts && n_old) {
+    CU(launch_remap_tile_counts(v, old_keys, old_counts, n_old, g->sm_count, g->stream));
+    g->launches += 1;
+  }
   return STVL_OK;
 }
 
@@ -414,7 +421,8 @@ int grow_tiles(stvl_grid * g)
   g->device_bytes += tile_bytes(nv);
   g->v = nv;
   select_sweep_buffers(g, g->sweep_parity);
-  rc = rebuild_tiles(g);
+  // the old pool is still intact: its keys and the last sweep's count rows are carried over to the new tiles
+  rc = rebuild_tiles(g, old.tile_key, old.tile_count, std::min<uint32_t>(g->last.tile_n, old.tile_capacity));
   if (rc != STVL_OK) return rc;
   CU(cudaStreamSynchronize(g->stream));
   g->device_bytes -= tile_bytes(old);

@@ -289,6 +289,23 @@ __global__ void __launch_bounds__(256) reassign_tiles_kernel(const GridView g)
   }
 }
 
+// after a tile rebuild renumbered the tiles: carry the last sweep's per-column counts (the reference's _cost_map) over from a
+// copy of the old tile keys / count rows, so that a costmap query between the rebuild and the next sweep still sees them
+__global__ void __launch_bounds__(256) remap_tile_counts_kernel(const GridView g, const uint64_t * __restrict__ old_keys,
+                                                                const uint32_t * __restrict__ old_counts, uint32_t n_old)
+{
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_old; t += warps_total) {
+    const uint2 c = reinterpret_cast<const uint2 *>(old_counts + (size_t)t * 64)[lane];
+    if (!__any_sync(kFull, (c.x | c.y) != 0)) continue;
+    uint32_t nt = 0;
+    if (lane == 0) { int bx, by; unpack_tile_key(old_keys[t], bx, by); nt = tile_find_or_insert(g, bx, by); }
+    nt = __shfl_sync(kFull, nt, 0);
+    if (nt != kOverflowSlot) reinterpret_cast<uint2 *>(g.tile_count + (size_t)nt * 64)[lane] = c;
+  }
+}
+
 // =====================================================================================
 // host-callable launchers
 // =====================================================================================
@@ -441,6 +458,13 @@ cudaError_t launch_dump_voxels(const GridView & g, int32_t * x, int32_t * y, int
 cudaError_t launch_rebuild_hash(const GridView & g, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s)
 {
   rebuild_hash_kernel<<<grid_for(leaf_slots_upper_bound, 256, sm_count * 8), 256, 0, s>>>(g);
+  return cudaGetLastError();
+}
+cudaError_t launch_remap_tile_counts(const GridView & g, const uint64_t * old_keys, const uint32_t * old_counts, uint32_t n_old, int sm_count,
+                                     cudaStream_t s)
+{
+  if (n_old == 0) return cudaSuccess;
+  remap_tile_counts_kernel<<<grid_for(n_old, 8, sm_count * 8), 256, 0, s>>>(g, old_keys, old_counts, n_old);
   return cudaGetLastError();
 }
 cudaError_t launch_reassign_tiles(const GridView & g, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s)

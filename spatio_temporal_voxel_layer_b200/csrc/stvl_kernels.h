@@ -83,6 +83,8 @@ cudaError_t launch_count_active(const GridView & g, uint32_t leaf_slots_upper_bo
 cudaError_t launch_dump_voxels(const GridView & g, int32_t * x, int32_t * y, int32_t * z, double * t, unsigned long long cap,
                                uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s);
 cudaError_t launch_rebuild_hash(const GridView & g, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s);
+cudaError_t launch_remap_tile_counts(const GridView & g, const uint64_t * old_keys, const uint32_t * old_counts, uint32_t n_old, int sm_count,
+                                     cudaStream_t s);
 cudaError_t launch_reassign_tiles(const GridView & g, uint32_t leaf_slots_upper_bound, int sm_count, cudaStream_t s);
 
 

@@ -922,3 +922,30 @@ def test_config5_five_million_voxels_against_oracle(stvl, oracle):
         assert st.n_swept == st.n_survived + st.n_cleared and st.n_swept > 4_000_000
     assert_same_voxels(gg.voxels(), og.voxels())
     gg.close()
+
+
+def test_costmap_survives_pool_growth_after_mark(stvl, oracle):
+    """The per-column counts of the last sweep (the reference's _cost_map, which reflects the pre-Mark survivors) must survive
+    a leaf / tile pool growth triggered by the Mark that follows the sweep: costmap and column queries made before the next
+    sweep still see them."""
+    rng = np.random.default_rng(23)
+    a = np.zeros((400, 4), np.float32)
+    a[:, :3] = rng.uniform(-1.5, 1.5, (400, 3))
+    b = np.zeros((30000, 4), np.float32)
+    b[:, :3] = rng.uniform(-40, 40, (30000, 3))          # scattered: almost one leaf (and many tiles) per point
+    gg = stvl.SpatioTemporalVoxelGrid(0.05, leaf_capacity=64)
+    og = oracle.OracleGrid(0.05)
+    gg.Mark([stvl.MeasurementReading(a, origin=(0, 0, 0), obstacle_range=100.0, now=3.0)])
+    og.mark(a, (0, 0, 0), 100.0, 3.0)
+    gg.ClearFrustums([], 4.0); og.clear_frustums(4.0)
+    gg.Mark([stvl.MeasurementReading(b, origin=(0, 0, 0), obstacle_range=100.0, now=4.5)])     # exhausts both pools
+    og.mark(b, (0, 0, 0), 100.0, 4.5)
+    cm, res = gg.UpdateROSCostmap(-4.0, -4.0, 0.05, 160, 160, mark_threshold=1, default_value=0)   # first call after the Mark: grows + replays
+    ocm, _, on = og.update_ros_costmap(-4.0, -4.0, 0.05, 160, 160, mark_threshold=1, default_value=0)
+    assert on > 100 and res.n_marked_columns == on
+    assert np.array_equal(cm, ocm)
+    gx, gy, gc = gg.GetFlattenedCostmap()
+    assert_same_columns((gx, gy, gc), og.costmap())
+    assert_same_voxels(gg.voxels(), og.voxels())
+    assert gg.pool_stats().leaf_capacity >= 16384
+    gg.close()
