@@ -241,7 +241,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
     if (warp > kMarkConsumerWarps) {
       pdl_wait();
       const uint32_t n_tiles = min(ld_volatile_u32(&g.ctr->tile_n), g.tile_capacity);
-      constexpr uint32_t kCmBatch = 4;
+      constexpr uint32_t kCmBatch = 8;
       const uint32_t cw = blockIdx.x * kMarkCmWarps + (warp - kMarkConsumerWarps - 1);
       unsigned cm_n = 0;
       int cm_mnx = INT_MAX, cm_mny = INT_MAX, cm_mxx = INT_MIN, cm_mxy = INT_MIN;
@@ -532,7 +532,7 @@ uint32_t mark_grid_for(const MarkBatch & batch, int sm_count)
 // column tiles the fused variant's costmap warps can take without becoming the critical path of the launch
 uint32_t mark_costmap_tiles_capacity(const MarkBatch & batch, int sm_count)
 {
-  return mark_grid_for(batch, sm_count) * (uint32_t)kMarkCmWarps * 16u;
+  return mark_grid_for(batch, sm_count) * (uint32_t)kMarkCmWarps * 24u;
 }
 uint32_t mark_cursor_advance(const MarkBatch & batch, int sm_count)
 {
