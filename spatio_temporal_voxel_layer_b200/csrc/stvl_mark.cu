@@ -181,14 +181,15 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
       uint32_t * const cursor = &g.ctr->mark_cursor[batch.cursor_sel & 1u];
       const unsigned long long policy = l2_evict_first_policy();
       unsigned flush_requests = 0;
-      uint32_t it = 0;
+      int stage = 0;            // ring position of the next hand-out ...
+      uint32_t phase = 0;       // ... and how often the ring has wrapped (parity)
+      auto advance = [&]() { if (++stage == n_stages) { stage = 0; phase ^= 1u; } };
       for (;;) {
         // a run of kMarkRun consecutive chunks (the cursor is monotone: ids are relative to the launch's base).  Every
         // producer stops at its first run that starts out of range, so a launch advances the cursor by a known amount.
         const uint32_t run0 = atomicAdd(cursor, (uint32_t)kMarkRun) - batch.cursor_base;
         if (run0 >= total) {
-          const int stage = (int)(it % (uint32_t)n_stages);
-          mbar_wait(&s_empty[stage], ((it / (uint32_t)n_stages) & 1u) ^ 1u);
+          mbar_wait(&s_empty[stage], phase ^ 1u);
           s_chunk[stage] = kChunkEnd;
           mbar_arrive(&s_full[stage]);
           break;
@@ -196,8 +197,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
         for (int k = 0; k < kMarkRun; ++k) {
           const uint32_t id = run0 + (uint32_t)k;
           if (id >= total) break;
-          int stage = (int)(it % (uint32_t)n_stages);
-          mbar_wait(&s_empty[stage], ((it / (uint32_t)n_stages) & 1u) ^ 1u);
+          mbar_wait(&s_empty[stage], phase ^ 1u);
           // a filling table is flushed early (large or scattered clouds): the marker travels in-band, so every consumer
           // sees it between the same two chunks
           if (*reinterpret_cast<volatile unsigned int *>(&s_fill) >= (unsigned)(kMarkTable * 5 / 8) &&
@@ -205,9 +205,8 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
             ++flush_requests;
             s_chunk[stage] = kChunkFlush;
             mbar_arrive(&s_full[stage]);
-            ++it;
-            stage = (int)(it % (uint32_t)n_stages);
-            mbar_wait(&s_empty[stage], ((it / (uint32_t)n_stages) & 1u) ^ 1u);
+            advance();
+            mbar_wait(&s_empty[stage], phase ^ 1u);
           }
           const int ri = mark_reading_of(batch, id);
           const DevReading & rd = batch.r[ri];
@@ -227,7 +226,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
           } else {
             mbar_arrive(&s_full[stage]);
           }
-          ++it;
+          advance();
         }
       }
     }
@@ -358,9 +357,11 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
     }
   };
 
-  for (uint32_t it = 0;; ++it) {
-    const int stage = (int)(it % (uint32_t)n_stages);
-    mbar_wait(&s_full[stage], (it / (uint32_t)n_stages) & 1u);
+  int stage = -1;
+  uint32_t phase = 1;
+  for (bool first = true;; first = false) {
+    if (++stage == n_stages || first) { stage = 0; phase ^= 1u; }
+    mbar_wait(&s_full[stage], phase);
     const uint32_t chunk = s_chunk[stage];
     if (chunk == kChunkEnd) break;
     if (chunk == kChunkFlush) {
@@ -391,7 +392,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[stage]);   // the stage may be refilled: this warp holds its points in registers
-    if (it == 0) TRACE(0, 2);
+    if (first) TRACE(0, 2);
 
     const float range2 = par.mark_range_2, range2_reject = par.range2_reject, range2_accept = par.range2_accept;
     const float near_accept = par.near_accept;
