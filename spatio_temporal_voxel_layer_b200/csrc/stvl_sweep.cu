@@ -4,8 +4,10 @@
 // Every CTA walks tiles of leaf slots in three phases:
 //   A  one THREAD per leaf: header (key, tmin, tile, 64 B value mask) in one round trip.  A leaf outside every frustum whose
 //      oldest voxel is too young to expire cannot change: its survivors are counted straight from the mask (two adjacent u32
-//      column counters per 64-bit reduction) and its 4 KB time block is never touched.  Every other leaf is split into
-//      batches of 32 active voxels that go into a work queue in SHARED memory (its time sectors are prefetched into L2).
+//      column counters per 64-bit reduction) and its 4 KB time block is never touched.  A leaf no frustum can touch but in
+//      which something may have expired gets the plain decay test from the same thread (phase A', sweep_leaf_decay_only).
+//      Every leaf a frustum may touch is split into batches of 32 active voxels that go into a work queue in SHARED
+//      memory (its time sectors are prefetched into L2).
 //   B  one WARP per queued batch, taken dynamically: leaf-level frustum classification, the reference's exact per-voxel
 //      arithmetic (decay model, first containing frustum, acceleration, strict <), rewrite of accelerated times, bit clears,
 //      per-column survivor counts, optional lists.
@@ -67,9 +69,86 @@ __device__ __forceinline__ bool leaf_may_expire(const GridView & g, double now, 
   return !(g.voxel_decay >= 0.0);
 }
 
+// reference .cpp:167-169 / :320-331: remaining time of a voxel marked at v when no frustum accelerates it
+__device__ __forceinline__ double base_duration(const GridView & g, double now, double v)
+{
+  const double t = __dsub_rn(now, v);
+  if (g.decay_model == 0) return __dsub_rn(g.voxel_decay, t);
+  if (g.decay_model == 1) return __dmul_rn(g.voxel_decay, exp(-t));
+  return g.voxel_decay;
+}
+
+// Phase A', ONE THREAD PER LEAF: a leaf that no frustum can touch but whose oldest voxel may have expired only needs the
+// decay test of .cpp:203-211 per voxel — no warp cooperation, no queue.  The thread walks its leaf's occupied voxel columns
+// (8 mark times = one 64 B run, fetched with four independent 128-bit loads), clears the expired bits (it is the only writer
+// of the mask), counts the survivors per column from the new mask bytes and refreshes the leaf's lower time bound.  With
+// thousands of threads doing this at once the SM has far more loads in flight than a warp-per-leaf schedule gives it.
+struct DecayOnlyResult { unsigned n_in, n_clear; int min_x, min_y, max_x, max_y; };
+__device__ __noinline__ DecayOnlyResult sweep_leaf_decay_only(const GridView & g, uint32_t slot, uint64_t key, uint32_t tile, double now,
+                                                              const SweepOutputs & out)
+{
+  DecayOnlyResult acc{0u, 0u, INT_MAX, INT_MAX, INT_MIN, INT_MIN};
+  int bx, by, bz;
+  unpack_leaf_key(key, bx, by, bz);
+  uint32_t * mp = g.leaf_mask + (size_t)slot * 16;
+  const double * tb = g.leaf_time + (size_t)slot * kLeafVoxels;
+  unsigned long long * tc = reinterpret_cast<unsigned long long *>(g.tile_count + (size_t)tile * 64);
+  double vmin = CUDART_INF;
+  unsigned n_in = 0, n_clear = 0;
+  uint32_t alive = 0;
+#pragma unroll 1
+  for (int w = 0; w < 16; ++w) {
+    const uint32_t x = mp[w];
+    if (!x) continue;
+    n_in += __popc(x);
+    uint32_t nx = x;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t byte = (x >> (8 * c)) & 0xFFu;
+      if (!byte) continue;
+      const double2 * p = reinterpret_cast<const double2 *>(tb + w * 32 + c * 8);
+      const double2 t01 = __ldcs(p), t23 = __ldcs(p + 1), t45 = __ldcs(p + 2), t67 = __ldcs(p + 3);
+      const double tv[8] = {t01.x, t01.y, t23.x, t23.y, t45.x, t45.y, t67.x, t67.y};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (!((byte >> k) & 1u)) continue;
+        if (base_duration(g, now, tv[k]) < 0.) {   // expired by temporal clearing, .cpp:203-211
+          nx &= ~(1u << (8 * c + k));
+          ++n_clear;
+          const int ix = bx * 8 + (w >> 1), iy = by * 8 + ((w & 1) * 4 + c);
+          acc.min_x = min(acc.min_x, ix); acc.max_x = max(acc.max_x, ix);
+          acc.min_y = min(acc.min_y, iy); acc.max_y = max(acc.max_y, iy);
+          if (out.cleared) {   // cleared_cells.insert, .cpp:213-215
+            const unsigned long long o = atomicAdd(&g.ctr->sw[g.sw_cur].n_cleared_out, 1ull);
+            if (o < out.cleared_cap) { out.cleared[2 * o] = ix; out.cleared[2 * o + 1] = iy; }
+          }
+        } else {
+          vmin = fmin(vmin, tv[k]);
+        }
+      }
+    }
+    if (nx != x) mp[w] = nx;
+    alive |= nx;
+    if (nx && tile != kOverflowSlot) {
+      // PopulateCostmapAndPointcloud .cpp:242-250: per-column survivor counts, two adjacent u32 counters per 64-bit reduction
+      uint32_t y = nx - ((nx >> 1) & 0x55555555u);
+      y = (y & 0x33333333u) + ((y >> 2) & 0x33333333u);
+      y = (y + (y >> 4)) & 0x0F0F0F0Fu;
+      const unsigned long long lo = (unsigned long long)(y & 0xFFu) | ((unsigned long long)((y >> 8) & 0xFFu) << 32);
+      const unsigned long long hi = (unsigned long long)((y >> 16) & 0xFFu) | ((unsigned long long)(y >> 24) << 32);
+      if (lo) red_add_u64(tc + w * 2, lo);
+      if (hi) red_add_u64(tc + w * 2 + 1, hi);
+    }
+  }
+  acc.n_in = n_in; acc.n_clear = n_clear;
+  if (!alive) free_leaf(g, slot);            // pruneGrid, .cpp:223
+  else g.leaf_tmin[slot] = vmin;             // exact lower bound again
+  return acc;
+}
+
 __global__ void __launch_bounds__(kSweepThreads, 2)
 sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ FrustumParams fparam, const DevFrustum * __restrict__ frustums_gmem,
-             const int n_frustums, const double now, const SweepOutputs out, uint8_t * __restrict__ cm_reset,
+             const int n_frustums, const double now, const __grid_constant__ SweepOutputs out, uint8_t * __restrict__ cm_reset,
              const unsigned long long cm_bytes, const int cm_value, const uint32_t tile_leaves)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -171,20 +250,27 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
           if (any == 0) {
             free_leaf(g, slot);   // nothing left in this leaf: pruneGrid, .cpp:223
           } else {
-            bool full_path = force_full || leaf_may_expire(g, now, tmin);
-            if (!full_path) {
+            // can a frustum contain a voxel centre of this leaf?  (bounding box, then the leaf's bounding sphere against the
+            // plane set / hourglass)
+            bool touches = force_full;
+            {
               int bx, by, bz;
               unpack_leaf_key(key, bx, by, bz);
               const int x0 = bx * 8, y0 = by * 8, z0 = bz * 8;
-              for (int f = 0; f < n_frustums && !full_path; ++f) {
+              for (int f = 0; f < n_frustums && !touches; ++f) {
                 const DevFrustum & F = fr[f];
                 if (F.type < 0) continue;
                 if (F.cull && (x0 + 7 < F.lo[0] || x0 > F.hi[0] || y0 + 7 < F.lo[1] || y0 > F.hi[1] || z0 + 7 < F.lo[2] || z0 > F.hi[2])) continue;
-                // inside the frustum's bounding box: bounding sphere of the leaf against the plane set / hourglass
-                full_path = classify_leaf(F, bx, by, bz, g.vs, g.half_vs) != 0;
+                touches = classify_leaf(F, bx, by, bz, g.vs, g.half_vs) != 0;
               }
             }
-            if (full_path) {
+            if (!touches && leaf_may_expire(g, now, tmin)) {
+              // phase A': decay test only, this thread alone
+              const DecayOnlyResult r = sweep_leaf_decay_only(g, slot, key, tile, now, out);
+              acc.swept += r.n_in; acc.clear += r.n_clear; acc.surv += r.n_in - r.n_clear;
+              acc.min_x = min(acc.min_x, r.min_x); acc.min_y = min(acc.min_y, r.min_y);
+              acc.max_x = max(acc.max_x, r.max_x); acc.max_y = max(acc.max_y, r.max_y);
+            } else if (touches) {
               unsigned pc = 0;
 #pragma unroll
               for (int q = 0; q < 4; ++q) pc += __popc(mw[q].x) + __popc(mw[q].y) + __popc(mw[q].z) + __popc(mw[q].w);
