@@ -233,6 +233,31 @@ def bench_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Best effort: run this rank (and therefore first-touch its pinned staging memory) on the CPUs of the NUMA node its GPU
+    hangs off, so that N ranks' host->device streams do not all cross one node's memory controllers."""
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        if not hasattr(props, "pci_bus_id"):
+            return "pci bus id unavailable in this torch build"
+        dom = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, getattr(props, "pci_device_id", 0))
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % dom).read().strip())
+        if node < 0:
+            return "device reports no NUMA node"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use:
+            return "node %d CPUs are outside this process's cpuset (%d allowed CPUs)" % (node, len(allowed))
+        os.sched_setaffinity(0, use)
+        return "rank bound to NUMA node %d (%d CPUs)" % (node, len(use))
+    except Exception as e:      # noqa: BLE001 — affinity is an optimisation, never a failure
+        return "not bound (%s)" % type(e).__name__
+
+
 # ------------------------------------------------------------------------------------------------
 # BASELINE config 5: warehouse map, ~50 M active voxels at 0.02 m, STRONG-scaled over the ranks (x-slab shards)
 # ------------------------------------------------------------------------------------------------
@@ -425,6 +450,7 @@ def bench_ours(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a B200: the library has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_note = bind_to_gpu_numa_node(torch, local_rank)   # before any pinned allocation: first touch decides the node
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -545,20 +571,17 @@ def bench_ours(args):
         step_host(0)
         barrier()
         t0 = time.perf_counter()
-        if world == 1:
-            # two cycles in flight: cycle j+1's H2D copy overlaps cycle j's kernels and read-back; every cycle's bytes and
-            # result are waited for (stvl_update_cycle_wait) inside the timed region
-            prev = None
-            res = stvl.CostmapResult()
-            for j in range(1, n_cycles + 1):
-                t = submit_host(j)
-                if prev is not None:
-                    check(L.stvl_update_cycle_wait(h, prev, C.byref(res)))
-                prev = t
-            check(L.stvl_update_cycle_wait(h, prev, C.byref(res)))
-        else:
-            for j in range(1, n_cycles + 1):
-                step_host(j)
+        # two cycles in flight: cycle j+1's H2D copy overlaps cycle j's kernels and read-back; every cycle's bytes and result
+        # are waited for (stvl_update_cycle_wait) inside the timed region.  N > 1: every rank uploads its own slab's clouds, the
+        # ranks' cells are merged into rank 0 inside the cycle and rank 0 reads the merged map back.
+        prev = None
+        res = stvl.CostmapResult()
+        for j in range(1, n_cycles + 1):
+            t = submit_host(j)
+            if prev is not None:
+                check(L.stvl_update_cycle_wait(h, prev, C.byref(res)))
+            prev = t
+        check(L.stvl_update_cycle_wait(h, prev, C.byref(res)))
         barrier()
         return time.perf_counter() - t0
 
@@ -736,7 +759,8 @@ def bench_ours(args):
                         "parallelism": "1 GPU" if world == 1 else "%d spatial x-slab shards, fused cycle per shard + in-library merge of the per-shard costmap cells into rank 0, pipelined one cycle behind" % world},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": bytes_h2d, "d2h_bytes_per_step": bytes_d2h,
                     "how": "stvl_update_cycle_async / stvl_update_cycle_wait, two cycles in flight (H2D of cycle k+1 overlaps kernels and D2H of cycle k); wall clock over the episodes' timed cycles, every cycle's bytes waited for"
-                           if world == 1 else "stvl_clear_frustums / stvl_mark / blocking sharded merge + D2H on rank 0, sequential",
+                           + ("" if world == 1 else "; every rank uploads its own slab's clouds, in-cycle merge into rank 0, rank 0 reads the merged map back"),
+                    "numa": numa_note,
                     "pcie_bound_cycles_per_s": 53e9 / bytes_h2d, "readback_matches_device_leg": e2e_cm_ok},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -241,7 +241,10 @@ int stvl_update_costs_device(stvl_grid_t * g, const stvl_costmap_params_t * p, u
  * device staging and returns a ticket at once; cycle k+1's H2D copy overlaps cycle k's kernels and read-back.
  * The clouds of a cycle and its costmap_host belong to the library until stvl_update_cycle_wait(ticket) has returned
  * (which also delivers the marked-cell count / bounds of that cycle).  At most two cycles may be in flight: submitting a
- * third waits for the oldest.  Cycles complete in submission order. */
+ * third waits for the oldest.  Cycles complete in submission order.
+ * On a handle with a communicator (a shard of a multi-GPU map, stvl_comm_init) the cycle is the sharded one: every rank
+ * uploads its own clouds, the ranks' cells are merged into rank 0 (blocking merge on the cycle's stream) and only rank 0
+ * reads bytes back into its costmap_host (the merged map); the result counts are each rank's own. */
 int stvl_update_cycle_async(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
                             const stvl_reading_t * readings, uint32_t n_readings,
                             const stvl_costmap_params_t * p, uint8_t * costmap_host, uint64_t * ticket);

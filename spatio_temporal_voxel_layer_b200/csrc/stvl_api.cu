@@ -1720,11 +1720,25 @@ int stvl_update_cycle_device(stvl_grid_t * g, double now, const stvl_frustum_t *
   return fused_cycle(g, now, frustums, n_frustums, readings, n_readings, to_dev(*p), costmap_dev);
 }
 
+namespace {
+int sharded_cycle(stvl_grid * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
+                  const stvl_reading_t * readings, uint32_t n_readings,
+                  const stvl_costmap_params_t * p, uint8_t * costmap_dev, int root, int pipelined);
+}  // namespace
+
 int stvl_update_cycle_sharded_device(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
                                      const stvl_reading_t * readings, uint32_t n_readings,
                                      const stvl_costmap_params_t * p, uint8_t * costmap_dev, int root, int pipelined)
 {
   ENTER(g);
+  return sharded_cycle(g, now, frustums, n_frustums, readings, n_readings, p, costmap_dev, root, pipelined);
+}
+
+namespace {
+int sharded_cycle(stvl_grid * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
+                  const stvl_reading_t * readings, uint32_t n_readings,
+                  const stvl_costmap_params_t * p, uint8_t * costmap_dev, int root, int pipelined)
+{
   if (!p) return fail(STVL_ERR_INVALID, "NULL argument");
   if (!g->comm) return fail(STVL_ERR_INVALID, "stvl_comm_init has not been called");
   if (root < 0 || root >= g->comm_n) return fail(STVL_ERR_INVALID, "bad root");
@@ -1786,6 +1800,7 @@ int stvl_update_cycle_sharded_device(stvl_grid_t * g, double now, const stvl_fru
   g->bits_pending = b;
   return expand_pending_bits(g, *p, costmap_dev, root);
 }
+}  // namespace
 
 int stvl_update_cycle_wait(stvl_grid_t * g, uint64_t ticket, stvl_costmap_result_t * res)
 {
@@ -1856,13 +1871,16 @@ int stvl_update_cycle_async(stvl_grid_t * g, double now, const stvl_frustum_t * 
   // the fused cycle on the main stream; the device costmap of this slot is free once its previous read-back is done
   CU(cudaStreamWaitEvent(g->stream, a.ev_h2d, 0));
   CU(cudaStreamWaitEvent(g->stream, a.ev_d2h, 0));
-  rc = fused_cycle(g, now, frustums, n_frustums, rs.data(), n_readings, to_dev(*p), a.costmap.p);
+  const bool sharded = g->comm != nullptr;     // a shard of a multi-GPU map: this rank's cells are merged into rank 0's costmap
+  if (sharded) rc = sharded_cycle(g, now, frustums, n_frustums, rs.data(), n_readings, p, a.costmap.p, 0, 0);
+  else rc = fused_cycle(g, now, frustums, n_frustums, rs.data(), n_readings, to_dev(*p), a.costmap.p);
   if (rc != STVL_OK) return rc;
   CU(cudaMemcpyAsync(a.d_res, &g->v.ctr->cm, sizeof(CostmapCtr), cudaMemcpyDeviceToDevice, g->stream));
   CU(cudaEventRecord(a.ev_cycle, g->stream));
   // D2H on its own stream: overlaps the next cycle's kernels and H2D copy
   CU(cudaStreamWaitEvent(g->d2h_stream, a.ev_cycle, 0));
-  if (costmap_host && bytes) CU(cudaMemcpyAsync(costmap_host, a.costmap.p, bytes, cudaMemcpyDeviceToHost, g->d2h_stream));
+  if (costmap_host && bytes && (!sharded || g->comm_rank == 0))
+    CU(cudaMemcpyAsync(costmap_host, a.costmap.p, bytes, cudaMemcpyDeviceToHost, g->d2h_stream));
   CU(cudaMemcpyAsync(a.h_res, a.d_res, sizeof(CostmapCtr), cudaMemcpyDeviceToHost, g->d2h_stream));
   CU(cudaEventRecord(a.ev_d2h, g->d2h_stream));
   a.busy = true;
