@@ -949,3 +949,55 @@ def test_costmap_survives_pool_growth_after_mark(stvl, oracle):
     assert_same_voxels(gg.voxels(), og.voxels())
     assert gg.pool_stats().leaf_capacity >= 16384
     gg.close()
+
+
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_sharded_cycle_single_rank_bitmap_path(stvl, oracle, pipelined):
+    """stvl_update_cycle_sharded_device on a ONE-rank communicator (runs on a 1-GPU box): the fused cycle's costmap pass
+    writes the packed cell bitmap, the (empty) exchange runs, and the root's expand kernel turns the bits into costmap bytes —
+    blocking, and pipelined one cycle behind with the flush at the end — against the oracle, with an odd-sized map, a
+    non-zero default value and a mark threshold."""
+    import torch
+    import spatio_temporal_voxel_layer_b200.synth as synth
+    scene = synth.retail_scene(size=30.0, seed=3)
+    gg = stvl.SpatioTemporalVoxelGrid(0.05, decay_model=0, voxel_decay=2.0, leaf_capacity=1 << 14)
+    gg.comm_init(stvl.SpatioTemporalVoxelGrid.nccl_unique_id(), 0, 1)
+    og = oracle.OracleGrid(0.05, decay_model=0, voxel_decay=2.0)
+    sx, sy, res, ox, oy = 397, 411, 0.05, -10.0, -10.0
+    params = stvl.CostmapParams(ox, oy, res, sx, sy, 2, 255, 254)
+    cm_dev = torch.full((sy, sx), 77, dtype=torch.uint8, device="cuda")
+    expected, keep = [], []
+    n_cycles = 6
+    for cyc in range(n_cycles):
+        now = 100.0 + 0.4 * cyc
+        centre = (-6.0 + 0.5 * cyc, 2.3 - 13.5 + 12.0, 0.0)
+        readings = [rgbd_reading(stvl, synth, scene, o, q, seed=100 * cyc + k, now=now + 0.001 * k)
+                    for k, (o, q) in enumerate(synth.camera_ring(centre, 0.1 * cyc, n_cams=3))]
+        dev_readings = []
+        for r in readings:
+            t = torch.from_numpy(np.ascontiguousarray(r.cloud, np.float32)).cuda()
+            keep.append(t)
+            dev_readings.append(stvl.MeasurementReading((t.data_ptr(), t.shape[0], 16, (0, 4, 8)), origin=r.origin, orientation=r.orientation,
+                                                        obstacle_range=r.obstacle_range, now=r.now, filter=r.filter,
+                                                        min_obstacle_height=r.min_obstacle_height, max_obstacle_height=r.max_obstacle_height))
+        gg.update_cycle_sharded_device(now, readings, dev_readings, params, cm_dev.data_ptr(), root=0, pipelined=pipelined)
+        og.clear_frustums(now, oracle_frustums(oracle, readings))
+        for r in readings:
+            oracle_mark(oracle, og, r, now)
+        ocm, _, on = og.update_ros_costmap(ox, oy, res, sx, sy, mark_threshold=2, default_value=255)
+        expected.append(ocm)
+        gg.synchronize()
+        got = cm_dev.cpu().numpy()
+        if not pipelined:
+            assert np.array_equal(got, expected[cyc]), "cycle %d" % cyc
+            assert gg.costmap_result().n_marked_columns == on
+        elif cyc >= 1:
+            assert np.array_equal(got, expected[cyc - 1]), "bytes of cycle %d must be complete after call %d" % (cyc - 1, cyc)
+    if pipelined:
+        gg.costmap_sharded_flush(params, cm_dev.data_ptr(), root=0)
+        gg.synchronize()
+        assert np.array_equal(cm_dev.cpu().numpy(), expected[-1])
+    assert_same_voxels(gg.voxels(), og.voxels())
+    assert int((expected[-1] == 254).sum()) > 50
+    gg.comm_destroy()
+    gg.close()
