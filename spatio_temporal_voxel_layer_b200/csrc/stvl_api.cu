@@ -122,6 +122,7 @@ struct stvl_grid {
   uint32_t * tile_buf[2] = {nullptr, nullptr};   // double-buffered column tiles (see GridView::tile_count)
   int sweep_parity = 0;
   uint64_t launches = 0;
+  bool record_mark_event = false;   // set by stvl_mark around its launches (ev_mark_done guards the host-cloud staging buffer)
   uint32_t mark_cursor_sel = 0;     // chunk cursor of the next Mark launch (they alternate) ...
   uint32_t mark_cursor_base[2] = {0, 0};   // ... and the value each cursor will have when its next launch starts
   size_t device_bytes = 0;
@@ -471,7 +472,8 @@ int launch_batches(stvl_grid * g, const std::vector<MarkBatch> & batches, CycleF
     pdl = false;                       // only the first launch follows the sweep
     g->launches += 1;
   }
-  CU(cudaEventRecord(g->ev_mark_done, g->stream));   // the staging buffer of host clouds is free again after this
+  // (stvl_mark only: the staging buffer of host clouds is free again once these launches have run)
+  if (g->record_mark_event) CU(cudaEventRecord(g->ev_mark_done, g->stream));
   return STVL_OK;
 }
 
@@ -1224,7 +1226,9 @@ int stvl_mark(stvl_grid_t * g, const stvl_reading_t * readings, uint32_t n_readi
   }
   CU(cudaEventRecord(g->ev_copy_done, g->copy_stream));
   CU(cudaStreamWaitEvent(g->stream, g->ev_copy_done, 0));
+  g->record_mark_event = true;
   rc = run_mark(g, readings, n_readings, dev_ptrs);
+  g->record_mark_event = false;
   if (rc != STVL_OK) return rc;
   // the caller owns the clouds again as soon as they are on the device
   CU(cudaEventSynchronize(g->ev_copy_done));
