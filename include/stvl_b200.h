@@ -224,6 +224,12 @@ int stvl_update_cycle_device(stvl_grid_t * g, double now, const stvl_frustum_t *
 int stvl_update_cycle_sharded_device(stvl_grid_t * g, double now, const stvl_frustum_t * frustums, uint32_t n_frustums,
                                      const stvl_reading_t * readings, uint32_t n_readings,
                                      const stvl_costmap_params_t * p, uint8_t * costmap_dev, int root, int pipelined);
+/* The geometry of that exchange (host arithmetic only, no GPU): for every rank r of an n_ranks-way x-slab sharding
+ * (rank r keeps the leaves with floor(bx / shard_width) mod shard_count == r), the interval [w_lo[r], w_hi[r]) of 32-cell
+ * words of a costmap row that its voxel columns can map into.  Rank r's packed bitmap has size_y rows of
+ * (w_hi[r] - w_lo[r]) words; bit (mx & 31) of word (mx >> 5) - w_lo[r] of row my is cell (mx, my). */
+int stvl_shard_word_intervals(float voxel_size, int shard_count, int shard_width, int n_ranks, const stvl_costmap_params_t * p,
+                              int32_t * w_lo, int32_t * w_hi);
 /* SpatioTemporalVoxelLayer::updateCosts (stvl/src/spatio_temporal_voxel_layer.cpp:666-696) on DEVICE byte grids of
  * p->size_x * p->size_y cells: if n_footprint >= 3, the footprint polygon (world x,y pairs, convex) is set to
  * FREE_SPACE (0) in the layer's costmap — nav2 Costmap2D::setConvexPolygonCost(_transformed_footprint, FREE_SPACE), :682-684

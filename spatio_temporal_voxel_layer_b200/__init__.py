@@ -89,7 +89,7 @@ EXPORTED_SYMBOLS = [
     "stvl_get_cleared", "stvl_get_points", "stvl_get_ambiguous", "stvl_reset", "stvl_reset_area", "stvl_active_count",
     "stvl_get_voxels", "stvl_load_voxels", "stvl_index_to_world", "stvl_voxel_size", "stvl_columns_to_dense",
     "stvl_costmap_from_dense", "stvl_get_pool_stats", "stvl_get_stream", "stvl_synchronize",
-    "stvl_update_cycle_device", "stvl_update_cycle_sharded_device", "stvl_update_cycle_async", "stvl_update_cycle_wait", "stvl_update_costs_device", "stvl_get_costmap_result", "stvl_enable_timing", "stvl_get_timing",
+    "stvl_update_cycle_device", "stvl_update_cycle_sharded_device", "stvl_update_cycle_async", "stvl_update_cycle_wait", "stvl_shard_word_intervals", "stvl_update_costs_device", "stvl_get_costmap_result", "stvl_enable_timing", "stvl_get_timing",
     "stvl_nccl_unique_id", "stvl_comm_init", "stvl_comm_destroy", "stvl_costmap_sharded_device", "stvl_costmap_sharded_flush",
 ]
 
@@ -149,6 +149,7 @@ def load_library(build_if_missing=True):
     L.stvl_update_cycle_device.argtypes = [vp, d, vp, u32, C.POINTER(Reading), u32, C.POINTER(CostmapParams), vp]
     L.stvl_update_cycle_async.argtypes = [vp, d, vp, u32, C.POINTER(Reading), u32, C.POINTER(CostmapParams), vp, C.POINTER(u64)]
     L.stvl_update_cycle_wait.argtypes = [vp, u64, C.POINTER(CostmapResult)]
+    L.stvl_shard_word_intervals.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.POINTER(CostmapParams), vp, vp]
     L.stvl_get_costmap_result.argtypes = [vp, C.POINTER(CostmapResult)]
     L.stvl_update_costs_device.argtypes = [vp, C.POINTER(CostmapParams), vp, vp, vp, u32, C.c_int, i32, i32, i32, i32]
     L.stvl_update_cycle_sharded_device.argtypes = [vp, d, vp, u32, C.POINTER(Reading), u32, C.POINTER(CostmapParams), vp, C.c_int, C.c_int]
@@ -194,6 +195,14 @@ def build_lidar_frustum(vfov, vpad, hfov, min_d, max_d, origin, quat_xyzw, accel
     q = np.ascontiguousarray(quat_xyzw, np.float64)
     _check(load_library().stvl_build_lidar_frustum(vfov, vpad, hfov, min_d, max_d, _ptr(o), _ptr(q), accel, _ptr(out)))
     return out
+
+
+def shard_word_intervals(voxel_size, shard_count, shard_width, n_ranks, params):
+    """stvl_shard_word_intervals (host only): per rank, the [w_lo, w_hi) interval of 32-cell words of a costmap row its x-slabs map into."""
+    lo = np.zeros(n_ranks, np.int32)
+    hi = np.zeros(n_ranks, np.int32)
+    _check(load_library().stvl_shard_word_intervals(np.float32(voxel_size), shard_count, shard_width, n_ranks, C.byref(params), _ptr(lo), _ptr(hi)))
+    return lo, hi
 
 
 def build_transform(translation, quat_xyzw):

@@ -830,27 +830,34 @@ int threshold_window(stvl_grid * g, int b, const stvl_costmap_params_t & p, uint
 }
 
 // ---- bitmap merge of the sharded fused cycle ------------------------------------------------------------------------------
-// 32-cell word interval [w_lo, w_hi) of a costmap row that rank r's x-slabs can mark (hull over its slabs), for every rank
-void shard_word_intervals(stvl_grid * g, const stvl_costmap_params_t & p)
+// 32-cell word interval [w_lo, w_hi) of a costmap row that rank r's x-slabs can mark (hull over its slabs), for every rank.
+// Pure host arithmetic (exposed as stvl_shard_word_intervals).
+void compute_word_intervals(double vs, int shard_count, int shard_width, int n_ranks, int own_rank, const stvl_costmap_params_t & p,
+                            int * w_lo, int * w_hi)
 {
-  const int n = g->comm_n, W = std::max(g->cfg.shard_width, 1);
+  const int n = n_ranks, W = std::max(shard_width, 1);
+  const double half_vs = vs / 2.0;
   const int wpr = (int)((p.size_x + 31u) >> 5);
   // leaf-slab range that can touch the costmap's x extent
-  const double x_lo = p.origin_x - 2.0 * g->vs, x_hi = p.origin_x + (double)p.size_x * p.resolution + 2.0 * g->vs;
-  const long long sl_lo = (long long)std::floor(x_lo / (8.0 * g->vs * W)) - 1, sl_hi = (long long)std::floor(x_hi / (8.0 * g->vs * W)) + 1;
-  for (int r = 0; r < n; ++r) { g->bit_w_lo[r] = wpr; g->bit_w_hi[r] = 0; }
+  const double x_lo = p.origin_x - 2.0 * vs, x_hi = p.origin_x + (double)p.size_x * p.resolution + 2.0 * vs;
+  const long long sl_lo = (long long)std::floor(x_lo / (8.0 * vs * W)) - 1, sl_hi = (long long)std::floor(x_hi / (8.0 * vs * W)) + 1;
+  for (int r = 0; r < n; ++r) { w_lo[r] = wpr; w_hi[r] = 0; }
   for (long long sl = sl_lo; sl <= sl_hi; ++sl) {
     int r = (int)(sl % n); if (r < 0) r += n;
-    if (g->cfg.shard_count <= 1) r = g->comm_rank;
+    if (shard_count <= 1) r = own_rank;
     // voxel columns of the slab: ix in [sl*W*8, (sl+1)*W*8); centres at ix*vs + vs/2
-    const double cx0 = (double)(sl * W * 8) * g->vs + g->half_vs, cx1 = (double)((sl + 1) * W * 8 - 1) * g->vs + g->half_vs;
+    const double cx0 = (double)(sl * W * 8) * vs + half_vs, cx1 = (double)((sl + 1) * W * 8 - 1) * vs + half_vs;
     long long m0 = (long long)std::floor((cx0 - p.origin_x) / p.resolution) - 1, m1 = (long long)std::floor((cx1 - p.origin_x) / p.resolution) + 1;
     if (m1 < 0 || m0 >= (long long)p.size_x) continue;
     m0 = std::max<long long>(m0, 0); m1 = std::min<long long>(m1, (long long)p.size_x - 1);
-    g->bit_w_lo[r] = std::min<int>(g->bit_w_lo[r], (int)(m0 >> 5));
-    g->bit_w_hi[r] = std::max<int>(g->bit_w_hi[r], (int)(m1 >> 5) + 1);
+    w_lo[r] = std::min<int>(w_lo[r], (int)(m0 >> 5));
+    w_hi[r] = std::max<int>(w_hi[r], (int)(m1 >> 5) + 1);
   }
-  for (int r = 0; r < n; ++r) if (g->bit_w_hi[r] <= g->bit_w_lo[r]) { g->bit_w_lo[r] = 0; g->bit_w_hi[r] = 0; }   // nothing of rank r maps here
+  for (int r = 0; r < n; ++r) if (w_hi[r] <= w_lo[r]) { w_lo[r] = 0; w_hi[r] = 0; }   // nothing of rank r maps here
+}
+void shard_word_intervals(stvl_grid * g, const stvl_costmap_params_t & p)
+{
+  compute_word_intervals(g->vs, g->cfg.shard_count, g->cfg.shard_width, g->comm_n, g->comm_rank, p, g->bit_w_lo, g->bit_w_hi);
 }
 
 // every non-root rank sends its bitmap `b`, the root receives them back to back into its staging area (one NCCL group)
@@ -1516,6 +1523,18 @@ int stvl_costmap_from_dense(stvl_grid_t * g, const uint32_t * dense_dev, int32_t
   if (rc != STVL_OK) return rc;
   fill_costmap_result(g, res);
   return after_fetch(g);
+}
+
+int stvl_shard_word_intervals(float voxel_size, int shard_count, int shard_width, int n_ranks, const stvl_costmap_params_t * p,
+                              int32_t * w_lo, int32_t * w_hi)
+{
+  if (!p || !w_lo || !w_hi) return fail(STVL_ERR_INVALID, "NULL argument");
+  if (n_ranks < 1 || n_ranks > kMaxShardRanks) return fail(STVL_ERR_INVALID, "n_ranks must be 1..%d", kMaxShardRanks);
+  if (!(voxel_size > 0.f) || !(p->resolution > 0)) return fail(STVL_ERR_INVALID, "voxel_size and resolution must be positive");
+  int lo[kMaxShardRanks], hi[kMaxShardRanks];
+  compute_word_intervals((double)voxel_size, shard_count, shard_width, n_ranks, 0, *p, lo, hi);
+  for (int r = 0; r < n_ranks; ++r) { w_lo[r] = lo[r]; w_hi[r] = hi[r]; }
+  return STVL_OK;
 }
 
 int stvl_nccl_unique_id(uint8_t id[128])

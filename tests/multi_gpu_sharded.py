@@ -94,6 +94,28 @@ def main():
     if rank == 0:
         ok = ok and torch.equal(cm, fused_expected[3])
         n_ref = ref.active_count()
+    # the pipelined host-buffer cycle on sharded handles (stvl_update_cycle_async): every rank uploads the same host cloud, keeps
+    # its own slabs, the cells are merged into rank 0 inside the cycle and rank 0 reads the merged bytes back
+    host_cloud = torch.from_numpy(cloud).pin_memory()
+    host_out = [np.zeros((size, size), np.uint8) for _ in range(2)]
+    async_expected, tickets = [], []
+    for cyc in range(3):
+        now += 1.0
+        origin = (0.3 * cyc - 0.4, 0.2, 0.5)
+        hr = stvl.MeasurementReading((host_cloud.data_ptr(), len(cloud), 16, (0, 4, 8)), origin=origin, obstacle_range=7.0, now=now + 0.001)
+        if rank == 0:
+            dr = stvl.MeasurementReading((cloud_dev.data_ptr(), len(cloud), 16, (0, 4, 8)), origin=origin, obstacle_range=7.0, now=now + 0.001)
+            ref.update_cycle_device(now, [], [dr], ox, oy, res, size, size, cm_ref.data_ptr(), mark_threshold=2, default_value=0)
+            ref.synchronize()
+            async_expected.append(cm_ref.cpu().numpy().copy())
+        tickets.append(g.update_cycle_async(now, [], [hr], params, host_out[cyc % 2]))
+        if cyc >= 1:
+            g.update_cycle_wait(tickets[cyc - 1])
+            if rank == 0:
+                ok = ok and np.array_equal(host_out[(cyc - 1) % 2], async_expected[cyc - 1])
+    g.update_cycle_wait(tickets[-1])
+    if rank == 0:
+        ok = ok and np.array_equal(host_out[0], async_expected[2]) and int((async_expected[2] == 254).sum()) > 1000
     n_local = torch.tensor([g.active_count()], device="cuda")
     dist.all_reduce(n_local)
     if rank == 0:
