@@ -123,8 +123,6 @@ struct stvl_grid {
   int sweep_parity = 0;
   uint64_t launches = 0;
   bool record_mark_event = false;   // set by stvl_mark around its launches (ev_mark_done guards the host-cloud staging buffer)
-  uint32_t mark_cursor_sel = 0;     // chunk cursor of the next Mark launch (they alternate) ...
-  uint32_t mark_cursor_base[2] = {0, 0};   // ... and the value each cursor will have when its next launch starts
   size_t device_bytes = 0;
   // in-library sharded merge (stvl_comm_init / stvl_costmap_sharded_device)
   ncclComm_t comm = nullptr;
@@ -319,8 +317,6 @@ int clear_pool(stvl_grid * g)
   g->time_bound = 0.0;
   g->time_bound_inf = false;
   g->swept = false;
-  g->mark_cursor_sel = 0;
-  g->mark_cursor_base[0] = g->mark_cursor_base[1] = 0;   // (the counters, cursors included, were just zeroed)
   return STVL_OK;
 }
 
@@ -415,19 +411,32 @@ int grow_leaves(stvl_grid * g)
 }
 int grow_tiles(stvl_grid * g)
 {
-  GridView old = g->v;
-  GridView nv = g->v;
-  int rc = alloc_tiles(g, old.tile_capacity * 2, &nv);
-  if (rc != STVL_OK) return fail(STVL_ERR_CAPACITY, "growing the column tile pool failed: %s", g_err);
-  g->device_bytes += tile_bytes(nv);
-  g->v = nv;
-  select_sweep_buffers(g, g->sweep_parity);
-  // the old pool is still intact: its keys and the last sweep's count rows are carried over to the new tiles
-  rc = rebuild_tiles(g, old.tile_key, old.tile_count, std::min<uint32_t>(g->last.tile_n, old.tile_capacity));
-  if (rc != STVL_OK) return rc;
-  CU(cudaStreamSynchronize(g->stream));
+  const GridView old = g->v;
+  const uint32_t n_old = std::min<uint32_t>(g->last.tile_n, old.tile_capacity);
+  // The rebuild inserts a tile for every live leaf column AND for every old tile that still carries counts of the last
+  // sweep; a doubled pool may still be too small for that (scattered clouds: about one tile per leaf), in which case count
+  // rows would be dropped.  So: double until the rebuild fits, always carrying over from the ORIGINAL pool, which stays
+  // intact until then.
+  for (uint64_t cap = (uint64_t)old.tile_capacity * 2;; cap *= 2) {
+    if (cap > (1ull << 28)) { g->v = old; return fail(STVL_ERR_CAPACITY, "column tile pool cannot grow beyond 2^28 tiles"); }
+    GridView nv = old;
+    int rc = alloc_tiles(g, (uint32_t)cap, &nv);
+    if (rc != STVL_OK) { free_tiles(nv); g->v = old; return fail(STVL_ERR_CAPACITY, "growing the column tile pool failed: %s", g_err); }
+    g->v = nv;
+    select_sweep_buffers(g, g->sweep_parity);
+    rc = rebuild_tiles(g, old.tile_key, old.tile_count, n_old);
+    if (rc != STVL_OK) return rc;
+    uint32_t overflow = 0;
+    CU(cudaMemcpyAsync(&overflow, &g->v.ctr->tile_overflow, 4, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    if (!overflow) break;
+    GridView failed = g->v;
+    free_tiles(failed);
+  }
+  g->counters_fresh = false;
+  g->device_bytes += tile_bytes(g->v);
   g->device_bytes -= tile_bytes(old);
-  free_tiles(old);
+  { GridView o = old; free_tiles(o); }
   return STVL_OK;
 }
 
@@ -459,11 +468,7 @@ int launch_batches(stvl_grid * g, const std::vector<MarkBatch> & batches, CycleF
   for (size_t i = 0; i < batches.size(); ++i) {
     // the costmap pass rides on dedicated warps of every Mark CTA
     const bool carry = fz && fz->costmap && !fz->costmap_done && i + 1 == batches.size();
-    MarkBatch b = batches[i];
-    b.cursor_sel = g->mark_cursor_sel;
-    b.cursor_base = g->mark_cursor_base[b.cursor_sel];
-    g->mark_cursor_base[b.cursor_sel] += mark_cursor_advance(b, g->sm_count);
-    g->mark_cursor_sel ^= 1u;
+    const MarkBatch & b = batches[i];
     HOST_T(tm0);
     CU(launch_mark(g->v, b, g->sm_count, g->stream, pdl, carry ? &fz->cm : nullptr, carry ? fz->costmap : nullptr, carry && fz->bits));
     HOST_T(tm1);

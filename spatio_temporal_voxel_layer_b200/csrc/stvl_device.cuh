@@ -53,11 +53,7 @@ struct Counters {
   uint32_t tile_n;
   uint32_t tile_overflow;
   uint32_t cm_ticket;      // last-CTA-done ticket of the costmap pass (its last CTA publishes cm_acc -> cm)
-  // next unclaimed 1024-point chunk of the running Mark kernel.  Never reset: launch k uses cursor k&1 relative to a base
-  // the host tracks (every CTA of a launch stops at its first out-of-range id, so a launch advances its cursor by exactly
-  // total_chunks + gridDim).  Two cursors because consecutive Mark launches may overlap under programmatic dependent launch.
-  uint32_t mark_cursor[2];
-  uint32_t pad1[2];
+  uint32_t pad1[4];
   // dropped input points
   unsigned long long dropped_range, dropped_nonfinite;
   SweepCtr sw[2];
@@ -153,18 +149,19 @@ struct DevReading {
   float oxf, oyf, ozf;    // (float) origin, for that screen
   float tf[12];           // sensor -> global float affine (row-major 3x4), applied first when has_tf
   uint32_t has_tf;
-  uint32_t first_block;   // first CTA of this reading in the batched launch
+  uint32_t first_block;   // first 128-point block of this reading in the batch's block index space
   uint32_t vec4;          // 1: point_step==16, offsets 0/4/8, 16 B aligned -> float4 loads
 };
 struct MarkBatch {
-  uint32_t first_block[kMaxBatchReadings];   // copy of r[k].first_block, one cache line: every CTA scans it to find its reading
+  uint32_t first_block[kMaxBatchReadings];   // copy of r[k].first_block, one cache line: the producers scan it to find their readings
   DevReading r[kMaxBatchReadings];
   uint32_t n_readings;
   uint32_t total_blocks;
   uint32_t use_atomic_max;  // 1: batched mode (monotone clocks), 0: plain stores
   int32_t ref_bx;           // reference leaf x of the batch (first reading's origin): block-local table keys store bx - ref_bx
-  uint32_t cursor_sel;      // which Counters::mark_cursor this launch uses (set at launch)
-  uint32_t cursor_base;     // value of that cursor when this launch starts (set at launch)
+  float vs_f;               // (float)vs
+  float c_lo, c_hi;         // (float)(1/vs) scaled down / up by a few ulps: the two ends of the fast quantisation (set at launch)
+  uint32_t pad;
   double min_now;           // smallest clock sample in the batch: initial leaf_tmin of leaves created by it
 };
 

@@ -50,12 +50,10 @@ cudaError_t launch_polygon_cost(uint8_t * costmap_dev, const CostmapDev & p, con
 cudaError_t launch_update_costs(const uint8_t * layer_dev, uint8_t * master_dev, uint32_t size_x, int min_i, int min_j, int max_i, int max_j,
                                 int method, int sm_count, cudaStream_t s);
 
-// batch.cursor_sel / batch.cursor_base must be set by the caller; the launch advances that cursor by mark_cursor_advance()
 cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s, bool pdl = false,
                         const CostmapDev * fused_costmap = nullptr, uint8_t * costmap_dev = nullptr, bool costmap_bits = false);
 uint32_t mark_blocks_for(unsigned long long n_points);
 uint32_t mark_grid_for(const MarkBatch & batch, int sm_count);
-uint32_t mark_cursor_advance(const MarkBatch & batch, int sm_count);
 uint32_t mark_costmap_tiles_capacity(const MarkBatch & batch, int sm_count);
 cudaError_t launch_load_voxels(const GridView & g, const int32_t * x, const int32_t * y, const int32_t * z, const double * t,
                                unsigned long long n, cudaStream_t s);

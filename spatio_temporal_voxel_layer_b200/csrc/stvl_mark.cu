@@ -1,18 +1,21 @@
 // stvl_mark.cu — Mark / operator() (reference spatio_temporal_voxel_grid.cpp:254-309) as a warp-specialised sm_100a kernel.
 //
-// One or two persistent CTAs per SM.  Inside a CTA:
-//   producer warp   one elected lane claims runs of 1024-point chunks from a device-side cursor and streams them
-//                   global -> shared memory with the bulk-copy engine (cp.async.bulk, completion on an mbarrier as
-//                   transaction bytes; SASS UBLKCP / SYNCS), kMarkStages chunks in flight per CTA
-//   consumer warps  wait on the stage's "full" mbarrier, pull their points into registers, release the stage ("empty"
-//                   mbarrier, one arrival per warp) and run the reference's per-point arithmetic: range / z-window tests and
-//                   voxel quantisation on a single-precision fast path that is PROVEN to agree with the reference's
-//                   double arithmetic (see quantise_fast), the exact double sequence for the few points it cannot decide;
-//                   survivors are ORed into a CTA-local table of {(reading, leaf) -> 512-bit mask} in shared memory
-//   costmap warps   (fused cycle only) wait for the sweep, then run the costmap pass over its column counts
-// Nothing before the flush touches the grid, so all of the streaming overlaps the sweep that precedes Mark on the stream
+// One persistent CTA of 32 warps per SM; every CTA owns one contiguous, equally sized slice of the batch's points (no work
+// cursor, no atomics on the hand-out, and a slice of a depth image touches few distinct leaves).  Inside a CTA:
+//   producer warp   one elected lane streams the slice global -> shared memory in chunks of up to 3968 points (62 KB) with
+//                   the bulk-copy engine (cp.async.bulk, completion on an mbarrier as transaction bytes; SASS UBLKCP /
+//                   SYNCS), three chunks in flight per SM; the first copies are issued before the CTA has finished
+//                   setting up its tables
+//   31 consumer     wait on the stage's "full" mbarrier, pull their points into registers two at a time, release the stage
+//   warps           ("empty" mbarrier, one arrival per warp) and run the reference's per-point arithmetic: range / z-window
+//                   tests and voxel quantisation on a single-precision fast path that is PROVEN to agree with the
+//                   reference's double arithmetic (see quantise_axis_fast), the exact double sequence for the few points it
+//                   cannot decide; survivors are ORed into a CTA-local table of {(reading, leaf) -> 512-bit mask} in
+//                   shared memory
+// Nothing before the flush touches the grid, so all of the streaming may overlap the sweep that precedes Mark on the stream
 // (programmatic dependent launch).  The flush resolves every table entry in the global leaf hash once and pushes one
-// 32-bit OR per touched mask word and one 64-bit max (or store) per distinct voxel.
+// 32-bit OR per touched mask word and one 64-bit max (or store) per distinct voxel.  In the fused cycle all 32 warps then
+// run the costmap pass over the sweep's column counts.
 #include <algorithm>
 #include <cstdlib>
 #include <utility>
@@ -21,17 +24,19 @@
 
 namespace stvl {
 
-constexpr int kMarkChunk = 1024;                 // points per chunk (16 KB of packed float4 points)
-constexpr int kMarkRun = 4;                      // consecutive chunks claimed per cursor fetch
-constexpr int kMarkConsumerWarps = 16;
+constexpr int kMarkBlock = 128;                  // hand-out unit: readings start on block boundaries of the batch's index space
+constexpr int kMarkConsumerWarps = 31;
 constexpr int kMarkConsumers = kMarkConsumerWarps * 32;
-constexpr int kMarkPPT = kMarkChunk / kMarkConsumers;   // points per consumer thread per chunk
-constexpr int kMarkCmWarps = 8;                  // costmap warps of the fused variant
+constexpr int kMarkThreads = kMarkConsumers + 32;
+constexpr int kMarkPPT = 4;                      // points per consumer thread per chunk, worked on in pairs
+constexpr int kMarkChunk = kMarkConsumers * kMarkPPT;   // 3968 points = 31 blocks = 62 KB of packed float4 points
+constexpr int kMarkChunkBlocks = kMarkChunk / kMarkBlock;
 constexpr int kMarkTable = 512;                  // CTA-local (reading, leaf) table entries
 constexpr int kMarkProbes = 16;
-constexpr int kMarkStagesMax = 8;
-constexpr uint32_t kChunkEnd = 0xFFFFFFFFu, kChunkFlush = 0xFFFFFFFEu;
-static_assert(kMarkPPT == 2, "the consumer loop is written for two points per thread");
+constexpr int kMarkStagesMax = 3;
+constexpr uint32_t kStageData = 0, kStageEnd = 1, kStageFlush = 2;
+static_assert(kMarkThreads == 1024 && kMarkChunk % kMarkBlock == 0, "one CTA of 32 warps; chunks are whole blocks");
+static_assert(kMarkPPT == 4, "the consumer loop is written for two pairs of points per thread");
 
 struct PointXYZ { float x, y, z; bool ok; };
 
@@ -64,14 +69,6 @@ __device__ __forceinline__ PointXYZ load_point_generic(const DevReading & r, uns
   return p;
 }
 
-__device__ __forceinline__ int mark_reading_of(const MarkBatch & batch, uint32_t chunk)
-{
-  int ri = 0;
-#pragma unroll 1
-  for (int k = 1; k < (int)batch.n_readings; ++k) if (chunk >= batch.first_block[k]) ri = k;
-  return ri;
-}
-
 // key of the CTA-local table: reading index (the mark time differs per reading) + leaf coordinate, x relative to the
 // batch's reference leaf so that everything fits 63 bits; leaves farther than 2^16 leaves from it bypass the table
 constexpr int kMarkRelBias = 1 << 16;
@@ -98,9 +95,12 @@ __device__ __noinline__ void mark_voxel_direct(const GridView & g, int bx, int b
 // The reference's per-point arithmetic in double (.cpp:285-303): range test on the float-narrowed squared distance, the
 // -vs shift of negative coordinates (z keyed on y's sign — sic), multiplication by the cached 1/vs, truncation toward zero.
 // Returns (ix, iy, iz, status) by value (registers): status 1 = marked, 0 = skipped, 2 = passed the range test but lies
-// beyond +-2^23 voxels.
-__device__ __noinline__ int4 quantise_exact(float fx, float fy, float fz, double ox, double oy, double oz, float range2, double vs, double inv_vs)
+// beyond +-2^23 voxels, 3 = a coordinate is not finite (UB upstream: dropped and counted here), 4 = outside the z window.
+__device__ __noinline__ int4 quantise_exact(float fx, float fy, float fz, double ox, double oy, double oz, float range2, double vs, double inv_vs,
+                                            float zlo, float zhi)
 {
+  if (!(fabsf(fx) <= 3.402823466e38f && fabsf(fy) <= 3.402823466e38f && fabsf(fz) <= 3.402823466e38f)) return make_int4(0, 0, 0, 3);
+  if (fz < zlo || fz > zhi) return make_int4(0, 0, 0, 4);   // PassThrough z window, measurement_buffer.cpp:165-175
   const double xd = (double)fx, yd = (double)fy, zd = (double)fz;
   const double dx = __dsub_rn(xd, ox), dy = __dsub_rn(yd, oy), dz = __dsub_rn(zd, oz);
   const float distance_2 = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
@@ -114,20 +114,25 @@ __device__ __noinline__ int4 quantise_exact(float fx, float fy, float fz, double
   return make_int4(__double2int_rz(gx), __double2int_rz(gy), __double2int_rz(gz), 1);
 }
 
-// One axis of the single-precision fast path.  X = shifted coordinate (float: x, or x - vs rounded to float; vs is a float
-// widened to double, so the reference's X differs from ours by at most one float rounding), q = X * (float)(1/vs).
-// Relative error of q against the reference's double product: <= 3 * 2^-24 (shift rounding, rounding of 1/vs to float,
-// product rounding) + 2^-52 < 1.8e-7.  Whenever q is farther than 3e-7 * |q| from the nearest integer, no integer lies
-// between q and the reference's value (nor on it), so both truncate to the same index; otherwise `amb` is raised and the
-// point takes the exact path.  |q| >= 4e6 (float integers get sparse, index limits) is always ambiguous.
-__device__ __forceinline__ int quantise_axis_fast(float X, float inv_vs_f, bool & amb)
+// One axis of the single-precision fast path.  S = shifted coordinate in float (x, or x - vs rounded to float; vs is a float
+// widened to double, so the reference's S differs from ours by at most one float rounding); a = |S|.  The reference's
+// |S * (1/vs)| in double differs from a * (float)(1/vs) by a relative error below 3 * 2^-24 + 2^-52 (shift rounding, rounding
+// of 1/vs to float, and the float product we do NOT form), so it lies in the real interval [a * c_lo, a * c_hi] with
+//   c_lo = fl((float)(1/vs) * (1 - 5 * 2^-24)),   c_hi = fl((float)(1/vs) * (1 + 3 * 2^-23))
+// (one more rounding each: 1 - 5 * 2^-24 leaves two ulps of slack below 1 - 4 * 2^-24, likewise above).  A fused
+// multiply-add rounded toward zero gives floor(a * c) EXACTLY: a * c + 2^23 is formed without rounding and truncated to a
+// float in [2^23, 2^24), whose ulp is 1.  If both ends of the interval have the same floor, no integer lies in it or on its
+// ends, so the reference truncates to that same integer; otherwise `diff` gets a non-zero bit and the point takes the
+// exact path.  Sums of 2^24 and more (indices beyond 2^23) always differ: the ends are more than two ulps apart there.
+// (Infinite products compare equal — such points never get here: their squared distance is not finite either.)
+__device__ __forceinline__ int quantise_axis_fast(float S, float c_lo, float c_hi, uint32_t & diff)
 {
-  const float q = __fmul_rn(X, inv_vs_f);
-  const int it = __float2int_rz(q);
-  const float d = fabsf(__fsub_rn(q, __int2float_rn(it)));          // in [0, 1)
-  const float near = fminf(d, __fsub_rn(1.0f, d));
-  amb = amb || !(near > __fmul_rn(fabsf(q), 3e-7f)) || !(fabsf(q) < 4.0e6f);
-  return it;
+  const float a = fabsf(S);
+  const uint32_t t_lo = __float_as_uint(__fmaf_rz(a, c_lo, 8388608.0f));
+  const uint32_t t_hi = __float_as_uint(__fmaf_rz(a, c_hi, 8388608.0f));
+  diff |= t_lo ^ t_hi;
+  const int fl = (int)(t_lo & 0x7FFFFFu);   // floor(|S| / vs)
+  return S < 0.0f ? -fl : fl;              // the reference truncates toward zero
 }
 
 // kVec4: every reading of the batch is a packed x,y,z,pad float4 cloud (the RGBD / depth-image layout), streamed through
@@ -138,8 +143,9 @@ __device__ __forceinline__ int quantise_axis_fast(float X, float inv_vs_f, bool 
 // spatio_temporal_voxel_layer.cpp:699-718); the costmap bytes were reset by the sweep kernel.  kCmBits: the pass writes a
 // cell bitmap instead of bytes (sharded cycle).
 template <bool kVec4, bool kCostmap, bool kCmBits>
-__global__ void __launch_bounds__((kMarkConsumerWarps + 1 + (kCostmap ? kMarkCmWarps : 0)) * 32, 1)
-mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatch batch, const CostmapDev cm, uint8_t * __restrict__ costmap, const int n_stages)
+__global__ void __launch_bounds__(kMarkThreads, 1)
+mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatch batch, const __grid_constant__ CostmapDev cm,
+            uint8_t * __restrict__ costmap, const int n_stages)
 {
   extern __shared__ __align__(128) unsigned char s_dyn[];
   // dynamic shared memory: [stages (kVec4 only)] [table keys] [table masks]
@@ -150,7 +156,8 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
   __shared__ uint32_t s_slot[kMarkTable];
   __shared__ double s_rnow[kMaxBatchReadings];
   __shared__ __align__(8) uint64_t s_full[kMarkStagesMax], s_empty[kMarkStagesMax];
-  __shared__ uint32_t s_chunk[kMarkStagesMax], s_ri[kMarkStagesMax], s_cnt[kMarkStagesMax];   // per stage: chunk id, reading, points in it
+  __shared__ unsigned long long s_base[kMarkStagesMax];                                      // per stage: first point of the chunk in its reading,
+  __shared__ uint32_t s_kind[kMarkStagesMax], s_ri[kMarkStagesMax], s_cnt[kMarkStagesMax];   // what it holds, reading, points in it
   __shared__ unsigned int s_fill;          // claimed table entries
   __shared__ unsigned int s_flushes;       // early flushes done (the producer requests at most one at a time)
   __shared__ unsigned int s_drop[2];
@@ -159,315 +166,337 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
   const unsigned lane = threadIdx.x & 31;
   const unsigned warp = threadIdx.x >> 5;
   const bool use_max = batch.use_atomic_max != 0;
-  const uint32_t total = batch.total_blocks;
-
-  // ---- set-up (touches only shared memory and kernel parameters) ------------------------------------------------------
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < n_stages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kMarkConsumerWarps); }
-    mbar_fence_init();
-    s_fill = 0; s_flushes = 0; s_drop[0] = s_drop[1] = 0;
-  }
-  if (threadIdx.x < kMaxBatchReadings) s_rnow[threadIdx.x] = threadIdx.x < batch.n_readings ? batch.r[threadIdx.x].now : 0.0;
-  for (int i = threadIdx.x; i < kMarkTable; i += blockDim.x) s_key[i] = kEmptyKey;
-  for (int i = threadIdx.x; i < kMarkTable * 16; i += blockDim.x) (&s_mask[0][0])[i] = 0;
-  __syncthreads();
-  TRACE(0, 1);
 
   // =====================================================================================================================
   // producer warp
   // =====================================================================================================================
   if (warp == kMarkConsumerWarps) {
-    if (lane == 0) {
-      uint32_t * const cursor = &g.ctr->mark_cursor[batch.cursor_sel & 1u];
-      const unsigned long long policy = l2_evict_first_policy();
-      unsigned flush_requests = 0;
-      int stage = 0;            // ring position of the next hand-out ...
-      uint32_t phase = 0;       // ... and how often the ring has wrapped (parity)
-      auto advance = [&]() { if (++stage == n_stages) { stage = 0; phase ^= 1u; } };
+    // this CTA's slice of the batch's block index space
+    uint32_t blk = (uint32_t)(((unsigned long long)batch.total_blocks * blockIdx.x) / gridDim.x);
+    const uint32_t blk_end = (uint32_t)(((unsigned long long)batch.total_blocks * (blockIdx.x + 1)) / gridDim.x);
+    int ri = 0;
+    int stage = 0;            // ring position of the next hand-out ...
+    uint32_t phase = 0;       // ... and how often the ring has wrapped (parity)
+    unsigned flush_requests = 0;
+    unsigned long long policy = 0;
+    bool done = false;
+    auto advance = [&]() { if (++stage == n_stages) { stage = 0; phase ^= 1u; } };
+    // hand out the next chunk (or the end marker); false once the end marker has been posted
+    auto produce = [&]() -> bool {
       for (;;) {
-        // a run of kMarkRun consecutive chunks (the cursor is monotone: ids are relative to the launch's base).  Every
-        // producer stops at its first run that starts out of range, so a launch advances the cursor by a known amount.
-        const uint32_t run0 = atomicAdd(cursor, (uint32_t)kMarkRun) - batch.cursor_base;
-        if (run0 >= total) {
+        if (blk >= blk_end) {
           mbar_wait(&s_empty[stage], phase ^ 1u);
-          s_chunk[stage] = kChunkEnd;
+          s_kind[stage] = kStageEnd;
           mbar_arrive(&s_full[stage]);
-          break;
+          return false;
         }
-        for (int k = 0; k < kMarkRun; ++k) {
-          const uint32_t id = run0 + (uint32_t)k;
-          if (id >= total) break;
-          mbar_wait(&s_empty[stage], phase ^ 1u);
-          // a filling table is flushed early (large or scattered clouds): the marker travels in-band, so every consumer
-          // sees it between the same two chunks
-          if (*reinterpret_cast<volatile unsigned int *>(&s_fill) >= (unsigned)(kMarkTable * 5 / 8) &&
-              *reinterpret_cast<volatile unsigned int *>(&s_flushes) == flush_requests) {
-            ++flush_requests;
-            s_chunk[stage] = kChunkFlush;
-            mbar_arrive(&s_full[stage]);
-            advance();
-            mbar_wait(&s_empty[stage], phase ^ 1u);
-          }
-          const int ri = mark_reading_of(batch, id);
-          const DevReading & rd = batch.r[ri];
-          // points of the reading: the host's count, or (output of the VOXEL pre-filter) a device counter below that bound
-          unsigned long long n_pts = rd.n_points;
-          if (rd.n_points_dev) { const unsigned long long nd = ld_volatile_u64(rd.n_points_dev); if (nd < n_pts) n_pts = nd; }
-          const unsigned long long base = (unsigned long long)(id - batch.first_block[ri]) * kMarkChunk;
-          if (base >= n_pts) continue;   // chunk beyond the actual count: nothing to hand out
-          const unsigned long long left = n_pts - base;
-          const uint32_t in_chunk = (uint32_t)(left < (unsigned long long)kMarkChunk ? left : (unsigned long long)kMarkChunk);
-          s_chunk[stage] = id;
-          s_ri[stage] = (uint32_t)ri;
-          s_cnt[stage] = in_chunk;
-          if constexpr (kVec4) {
-            mbar_arrive_expect_tx(&s_full[stage], in_chunk * 16u);
-            bulk_load(s_stage + (size_t)stage * kMarkChunk, rd.data + base * 16ull, in_chunk * 16u, &s_full[stage], policy);
-          } else {
-            mbar_arrive(&s_full[stage]);
-          }
+        while (ri + 1 < (int)batch.n_readings && blk >= batch.first_block[ri + 1]) ++ri;
+        const DevReading & rd = batch.r[ri];
+        const uint32_t rd_end = ri + 1 < (int)batch.n_readings ? batch.first_block[ri + 1] : batch.total_blocks;
+        uint32_t take = min(min(blk_end, rd_end) - blk, (uint32_t)kMarkChunkBlocks);
+        // points of the reading: the host's count, or (output of the VOXEL pre-filter) a device counter below that bound
+        unsigned long long n_pts = rd.n_points;
+        if (rd.n_points_dev) { const unsigned long long nd = ld_volatile_u64(rd.n_points_dev); if (nd < n_pts) n_pts = nd; }
+        const unsigned long long base = (unsigned long long)(blk - batch.first_block[ri]) * kMarkBlock;
+        blk += take;
+        if (base >= n_pts) continue;   // beyond the actual count: nothing to hand out
+        const unsigned long long left = n_pts - base;
+        const uint32_t cnt = (uint32_t)(left < (unsigned long long)take * kMarkBlock ? left : (unsigned long long)take * kMarkBlock);
+        mbar_wait(&s_empty[stage], phase ^ 1u);
+        // a filling table is flushed early (large or scattered clouds): the marker travels in-band, so every consumer
+        // sees it between the same two chunks
+        if (*reinterpret_cast<volatile unsigned int *>(&s_fill) >= (unsigned)(kMarkTable * 5 / 8) &&
+            *reinterpret_cast<volatile unsigned int *>(&s_flushes) == flush_requests) {
+          ++flush_requests;
+          s_kind[stage] = kStageFlush;
+          mbar_arrive(&s_full[stage]);
           advance();
+          mbar_wait(&s_empty[stage], phase ^ 1u);
         }
-      }
-    }
-    return;
-  }
-
-  // =====================================================================================================================
-  // costmap warps (fused cycle): the pass needs the sweep's column counts, nothing of Mark
-  // =====================================================================================================================
-  if constexpr (kCostmap) {
-    if (warp > kMarkConsumerWarps) {
-      pdl_wait();
-      const uint32_t n_tiles = min(ld_volatile_u32(&g.ctr->tile_n), g.tile_capacity);
-      constexpr uint32_t kCmBatch = 8;
-      const uint32_t cw = blockIdx.x * kMarkCmWarps + (warp - kMarkConsumerWarps - 1);
-      unsigned cm_n = 0;
-      int cm_mnx = INT_MAX, cm_mny = INT_MAX, cm_mxx = INT_MIN, cm_mxy = INT_MIN;
-      for (uint32_t t0 = cw * kCmBatch; t0 < n_tiles; t0 += gridDim.x * kMarkCmWarps * kCmBatch)
-        costmap_tile_batch<(int)kCmBatch, kCmBits>(g, cm, costmap, t0, n_tiles, lane, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy);
-      costmap_warp_accumulate(g.ctr, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy);
-      if (lane == 0) __threadfence();   // this warp's accumulator updates are visible before the CTA takes its ticket
-      named_bar_sync(2, kMarkCmWarps * 32);
-      if (warp == kMarkConsumerWarps + 1 && lane == 0) {
-        __threadfence();
-        if (atomicAdd(&g.ctr->cm_ticket, 1u) == gridDim.x - 1) {   // last CTA publishes the result and re-arms the accumulators
-          __threadfence();
-          costmap_publish_result(g.ctr);
-          g.ctr->cm_ticket = 0;
-          __threadfence();
+        s_kind[stage] = kStageData;
+        s_ri[stage] = (uint32_t)ri;
+        s_cnt[stage] = cnt;
+        s_base[stage] = base;
+        if constexpr (kVec4) {
+          mbar_arrive_expect_tx(&s_full[stage], cnt * 16u);
+          bulk_load(s_stage + (size_t)stage * kMarkChunk, rd.data + base * 16ull, cnt * 16u, &s_full[stage], policy);
+        } else {
+          mbar_arrive(&s_full[stage]);
         }
+        advance();
+        return true;
       }
-      return;
-    }
-  }
-
-  // =====================================================================================================================
-  // consumer warps
-  // =====================================================================================================================
-  bool grid_ok = false;       // this thread has waited for the predecessor grid (the sweep)
-  auto sync_with_predecessor = [&]() { if (!grid_ok) { pdl_wait(); grid_ok = true; } };
-  unsigned int drop_range = 0, drop_nonfinite = 0;
-  uint64_t last_key = kEmptyKey;   // this thread's most recent table key and its entry
-  int last_e = -1;
-  const float vs_f = (float)g.vs;              // exact: vs is a float widened to double
-  const float inv_vs_f = (float)g.inv_vs;
-
-  // ---- flush: resolve the table's leaves in the global hash, push masks and times, empty the table ----------------------
-  auto flush = [&](const bool final) {
-    named_bar_sync(1, kMarkConsumers);   // every consumer warp is done with the chunks before the flush point
-    if (final) TRACE(0, 3);
-    sync_with_predecessor();
-    // launch_dependents only AFTER our own wait: the next cycle's sweep (and the Mark behind it) cannot become resident
-    // before the grid preceding this one has completed, which bounds the programmatic-launch chain to two kernels in flight
-    if (final) pdl_launch_dependents();
-    for (int e = threadIdx.x; e < kMarkTable; e += kMarkConsumers) {   // one thread per distinct (reading, leaf)
-      const unsigned long long tkey = s_key[e];
-      uint32_t slot = kOverflowSlot;
-      if (tkey != kEmptyKey) {
-        const int bx = (int)((tkey >> 42) & 0x1FFFF) - kMarkRelBias + batch.ref_bx;
-        const int by = (int)((tkey >> 21) & 0x1FFFFF) - kLeafBias, bz = (int)(tkey & 0x1FFFFF) - kLeafBias;
-        slot = leaf_find_or_insert(g, pack_leaf_key(bx, by, bz), bx, by, batch.min_now);
-      }
-      s_slot[e] = slot;
-    }
-    last_key = kEmptyKey; last_e = -1;
-    named_bar_sync(1, kMarkConsumers);
-    if (final) TRACE(0, 4);
-    // per touched mask word one 32-bit OR, per distinct voxel one 64-bit max (batched launch, monotone clocks) or a
-    // plain store (per-reading launches: exact overwrite semantics of MarkGridPoint, .cpp:421-430)
-    for (int i = threadIdx.x; i < kMarkTable * 16; i += kMarkConsumers) {
-      uint32_t m = (&s_mask[0][0])[i];
-      if (!m) continue;
-      (&s_mask[0][0])[i] = 0;
-      const int e = i >> 4;
-      const uint32_t slot = s_slot[e];
-      if (slot == kOverflowSlot) continue;
-      const double now = s_rnow[(int)(s_key[e] >> 59)];
-      const unsigned long long now_bits = (unsigned long long)__double_as_longlong(now);
-      const unsigned w = i & 15;
-      red_or_u32(&g.leaf_mask[(size_t)slot * 16 + w], m);
-      double * tp = g.leaf_time + (size_t)slot * kLeafVoxels + w * 32;
-      if (!use_max && g.leaf_tmin[slot] > now) g.leaf_tmin[slot] = -CUDART_INF;   // clocks are not monotone here
-      while (m) {
-        const int b = __ffs(m) - 1; m &= m - 1;
-        if (use_max) red_max_s64(reinterpret_cast<unsigned long long *>(tp + b), now_bits);
-        else tp[b] = now;
-      }
-    }
-    if (!final) {
-      named_bar_sync(1, kMarkConsumers);   // the keys were still needed for the per-reading clock above
-      for (int e = threadIdx.x; e < kMarkTable; e += kMarkConsumers) s_key[e] = kEmptyKey;
-      if (threadIdx.x == 0) { s_fill = 0; atomicAdd(&s_flushes, 1u); }
-      named_bar_sync(1, kMarkConsumers);
-    }
-  };
-
-  // find-or-claim the (reading, leaf) entry of the CTA-local table and set the voxel's bit
-  auto table_insert = [&](int ri, int ix, int iy, int iz, double now_r) {
-    const int bx = ix >> 3, by = iy >> 3, bz = iz >> 3;
-    if (g.shard_count > 1 && !shard_owns(bx, g.shard_index, g.shard_count, g.shard_width)) return;
-    const unsigned l = (unsigned)(((ix & 7) * 8 + (iy & 7)) * 8 + (iz & 7));
-    const int rx = bx - batch.ref_bx;
-    int e = -1;
-    if (rx >= -kMarkRelBias && rx < kMarkRelBias) {
-      const uint64_t key = pack_table_key(ri, rx, by, bz);
-      if (key == last_key) e = last_e;
-      else {
-        uint32_t h = ((uint32_t)bx * 73856093u ^ (uint32_t)by * 19349663u ^ (uint32_t)bz * 83492791u ^ (uint32_t)ri * 2654435761u) & (kMarkTable - 1);
-#pragma unroll 1
-        for (int p = 0; p < kMarkProbes; ++p) {
-          unsigned long long cur = s_key[h];
-          if (cur == kEmptyKey) {
-            cur = atomicCAS(&s_key[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
-            if (cur == kEmptyKey) { atomicAdd(&s_fill, 1u); cur = key; }
-          }
-          if (cur == key) { e = (int)h; break; }
-          h = (h + 1) & (kMarkTable - 1);
-        }
-        last_key = key; last_e = e;
-      }
-    }
-    if (e >= 0) {
-      const uint32_t bit = 1u << (l & 31);
-      if (!(s_mask[e][l >> 5] & bit)) atomicOr(&s_mask[e][l >> 5], bit);
-    } else {   // table full (scattered cloud) or leaf out of the table's reach: straight to the global store
-      sync_with_predecessor();
-      mark_voxel_direct(g, bx, by, bz, l, now_r, use_max, batch.min_now);
-    }
-  };
-
-  int stage = -1;
-  uint32_t phase = 1;
-  for (bool first = true;; first = false) {
-    if (++stage == n_stages || first) { stage = 0; phase ^= 1u; }
-    mbar_wait(&s_full[stage], phase);
-    const uint32_t chunk = s_chunk[stage];
-    if (chunk == kChunkEnd) break;
-    if (chunk == kChunkFlush) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[stage]);
-      flush(false);
-      continue;
-    }
-    const int ri = (int)s_ri[stage];
-    const DevReading & par = batch.r[ri];   // warp-uniform parameter-bank reads
-    PointXYZ pts[kMarkPPT];
-    const unsigned in_chunk = s_cnt[stage];
-    if constexpr (kVec4) {
-#pragma unroll
-      for (int k = 0; k < kMarkPPT; ++k) {
-        const unsigned idx = (unsigned)k * kMarkConsumers + threadIdx.x;
-        const float4 v = s_stage[(size_t)stage * kMarkChunk + idx];
-        pts[k].x = v.x; pts[k].y = v.y; pts[k].z = v.z;
-        pts[k].ok = idx < in_chunk;
-      }
-    } else {
-      const unsigned long long base = (unsigned long long)(chunk - batch.first_block[ri]) * kMarkChunk;
-#pragma unroll
-      for (int k = 0; k < kMarkPPT; ++k) {
-        const unsigned idx = (unsigned)k * kMarkConsumers + threadIdx.x;
-        pts[k] = load_point_generic(par, base + idx, idx < in_chunk);
-      }
+    };
+    if (lane == 0) {
+      for (int s = 0; s < n_stages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kMarkConsumerWarps); }
+      mbar_fence_init();
+      s_fill = 0; s_flushes = 0; s_drop[0] = s_drop[1] = 0;
+      policy = l2_evict_first_policy();
+      // the first copies go out while the consumer warps are still clearing the table (s_fill is 0: no flush marker yet)
+      for (int s = 0; s < n_stages && !done; ++s) done = !produce();
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&s_empty[stage]);   // the stage may be refilled: this warp holds its points in registers
-    if (first) TRACE(0, 2);
+    named_bar_sync(3, kMarkThreads);
+    if (lane == 0) { while (!done) done = !produce(); }
+    __syncwarp();
+  } else {
+    // ===================================================================================================================
+    // consumer warps
+    // ===================================================================================================================
+    if (threadIdx.x < kMaxBatchReadings) s_rnow[threadIdx.x] = threadIdx.x < batch.n_readings ? batch.r[threadIdx.x].now : 0.0;
+    for (int i = threadIdx.x; i < kMarkTable; i += kMarkConsumers) s_key[i] = kEmptyKey;
+    for (int i = threadIdx.x; i < kMarkTable * 16; i += kMarkConsumers) (&s_mask[0][0])[i] = 0;
+    named_bar_sync(3, kMarkThreads);   // barriers initialised (producer), table cleared
+    TRACE(0, 1);
 
-    const float range2 = par.mark_range_2, range2_reject = par.range2_reject, range2_accept = par.range2_accept;
-    const float near_accept = par.near_accept;
-    const float oxf = par.oxf, oyf = par.oyf, ozf = par.ozf;
-    const bool zwin = par.filter == 2;
-    const float zlo = zwin ? par.zmin_f : -CUDART_INF_F, zhi = zwin ? par.zmax_f : CUDART_INF_F;
-    if (par.has_tf) {   // cloud still in the sensor frame: tf2::doTransform first (measurement_buffer.cpp:141-146)
-#pragma unroll
-      for (int k = 0; k < kMarkPPT; ++k) transform_point(par.tf, pts[k].x, pts[k].y, pts[k].z);
-    }
-    // ---- single-precision fast path, both points of the thread interleaved ------------------------------------------------
-    int ix[kMarkPPT], iy[kMarkPPT], iz[kMarkPPT];
-    bool take[kMarkPPT], amb[kMarkPPT];
-#pragma unroll
-    for (int k = 0; k < kMarkPPT; ++k) {
-      const float fx = pts[k].x, fy = pts[k].y, fz = pts[k].z;
-      // non-finite coordinates: (x*0 + y*0 + z*0) is NaN exactly when one of them is NaN or infinite
-      const float nf = fmaf(fz, 0.0f, fmaf(fy, 0.0f, __fmul_rn(fx, 0.0f)));
-      const bool finite = nf == nf;
-      drop_nonfinite += (pts[k].ok && !finite) ? 1u : 0u;
-      // PassThrough z window (reference measurement_buffer.cpp:165-175) on exactly equivalent float thresholds; the range
-      // test on a float evaluation of the squared distance whose error is far below the margins of the two thresholds:
-      // above range2_reject the exact test certainly rejects, inside [near_accept, range2_accept] it certainly accepts
-      const float ax = __fsub_rn(fx, oxf), ay = __fsub_rn(fy, oyf), az = __fsub_rn(fz, ozf);
-      const float d2f = fmaf(az, az, fmaf(ay, ay, __fmul_rn(ax, ax)));
-      const bool cand = pts[k].ok && finite && !(fz < zlo || fz > zhi) && !(d2f > range2_reject);
-      bool a = !(d2f <= range2_accept && d2f >= near_accept);
-      // .cpp:293-303 in float: shift negatives by one voxel (z tests y's sign — sic), multiply by 1/vs, truncate toward zero
-      const float X = fx < 0 ? __fsub_rn(fx, vs_f) : fx;
-      const float Y = fy < 0 ? __fsub_rn(fy, vs_f) : fy;
-      const float Z = fy < 0 ? __fsub_rn(fz, vs_f) : fz;
-      ix[k] = quantise_axis_fast(X, inv_vs_f, a);
-      iy[k] = quantise_axis_fast(Y, inv_vs_f, a);
-      iz[k] = quantise_axis_fast(Z, inv_vs_f, a);
-      take[k] = cand && !a;
-      amb[k] = cand && a;
-    }
-    // ---- the exact double sequence for the points the fast path could not decide (rare; whole warps skip it) ----------------
-#pragma unroll
-    for (int k = 0; k < kMarkPPT; ++k) {
-      if (__any_sync(kFull, amb[k])) {
-        if (amb[k]) {
-          const int4 q = quantise_exact(pts[k].x, pts[k].y, pts[k].z, par.ox, par.oy, par.oz, range2, g.vs, g.inv_vs);
-          ix[k] = q.x; iy[k] = q.y; iz[k] = q.z;
-          take[k] = q.w == 1;
-          drop_range += q.w == 2 ? 1u : 0u;
+    bool grid_ok = false;       // this thread has waited for the predecessor grid (the sweep)
+    auto sync_with_predecessor = [&]() { if (!grid_ok) { pdl_wait(); grid_ok = true; } };
+    unsigned int drop_range = 0, drop_nonfinite = 0;
+    // this thread's most recent voxel that went through the table, and its entry (l_ix = 2^30: no voxel index can share a
+    // leaf with it, fast-path indices are below 2^23)
+    int l_ix = 1 << 30, l_iy = 0, l_iz = 0, l_ri = -1;
+    // this thread's current leaf in the CTA-local table: shared-window address of its 16 mask words (0: none — the table was
+    // full or the leaf is out of its reach, voxels go straight to the global store)
+    uint32_t l_mask = 0;
+    const float vs_f = batch.vs_f, c_lo = batch.c_lo, c_hi = batch.c_hi;   // (float)vs and the two ends of 1/vs, see launch_mark
+
+    // ---- flush: resolve the table's leaves in the global hash, push masks and times, empty the table ----------------------
+    auto flush = [&](const bool final) {
+      named_bar_sync(1, kMarkConsumers);   // every consumer warp is done with the chunks before the flush point
+      if (final) TRACE(0, 3);
+      sync_with_predecessor();
+      // launch_dependents only AFTER our own wait: the next cycle's sweep (and the Mark behind it) cannot become resident
+      // before the grid preceding this one has completed, which bounds the programmatic-launch chain to two kernels in flight
+      if (final) pdl_launch_dependents();
+      for (int e = threadIdx.x; e < kMarkTable; e += kMarkConsumers) {   // one thread per distinct (reading, leaf)
+        const unsigned long long tkey = s_key[e];
+        uint32_t slot = kOverflowSlot;
+        if (tkey != kEmptyKey) {
+          const int bx = (int)((tkey >> 42) & 0x1FFFF) - kMarkRelBias + batch.ref_bx;
+          const int by = (int)((tkey >> 21) & 0x1FFFFF) - kLeafBias, bz = (int)(tkey & 0x1FFFFF) - kLeafBias;
+          slot = leaf_find_or_insert(g, pack_leaf_key(bx, by, bz), bx, by, batch.min_now);
+        }
+        s_slot[e] = slot;
+      }
+      l_ix = 1 << 30; l_mask = 0;
+      named_bar_sync(1, kMarkConsumers);
+      if (final) TRACE(0, 4);
+      // per touched mask word one 32-bit OR, per distinct voxel one 64-bit max (batched launch, monotone clocks) or a
+      // plain store (per-reading launches: exact overwrite semantics of MarkGridPoint, .cpp:421-430)
+      for (int i = threadIdx.x; i < kMarkTable * 16; i += kMarkConsumers) {
+        uint32_t m = (&s_mask[0][0])[i];
+        if (!m) continue;
+        (&s_mask[0][0])[i] = 0;
+        const int e = i >> 4;
+        const uint32_t slot = s_slot[e];
+        if (slot == kOverflowSlot) continue;
+        const double now = s_rnow[(int)(s_key[e] >> 59)];
+        const unsigned long long now_bits = (unsigned long long)__double_as_longlong(now);
+        const unsigned w = i & 15;
+        red_or_u32(&g.leaf_mask[(size_t)slot * 16 + w], m);
+        double * tp = g.leaf_time + (size_t)slot * kLeafVoxels + w * 32;
+        if (!use_max && g.leaf_tmin[slot] > now) g.leaf_tmin[slot] = -CUDART_INF;   // clocks are not monotone here
+        while (m) {
+          const int b = __ffs(m) - 1; m &= m - 1;
+          if (use_max) red_max_s64(reinterpret_cast<unsigned long long *>(tp + b), now_bits);
+          else tp[b] = now;
         }
       }
-    }
-    // ---- CTA-local dedupe ----------------------------------------------------------------------------------------------------
-#pragma unroll
-    for (int k = 0; k < kMarkPPT; ++k) {
-      if (take[k]) table_insert(ri, ix[k], iy[k], iz[k], par.now);
-    }
-  }
-  flush(true);
-  TRACE(0, 5);
+      if (!final) {
+        named_bar_sync(1, kMarkConsumers);   // the keys were still needed for the per-reading clock above
+        for (int e = threadIdx.x; e < kMarkTable; e += kMarkConsumers) s_key[e] = kEmptyKey;
+        if (threadIdx.x == 0) { s_fill = 0; atomicAdd(&s_flushes, 1u); }
+        named_bar_sync(1, kMarkConsumers);
+      }
+    };
 
-  // dropped-point statistics: warp reduce, shared-memory add, one fire-and-forget global reduction per CTA
-  if (__any_sync(kFull, (drop_range | drop_nonfinite) != 0)) {
+    // a voxel whose leaf differs from the thread's previous one: find-or-claim the (reading, leaf) entry of the CTA-local
+    // table; -1 = table full (scattered cloud) or leaf out of the table's reach
+    auto table_lookup = [&](int ri, int bx, int by, int bz) -> int {
+      const int rx = bx - batch.ref_bx;
+      if (rx < -kMarkRelBias || rx >= kMarkRelBias) return -1;
+      const uint64_t key = pack_table_key(ri, rx, by, bz);
+      uint32_t h = ((uint32_t)bx * 73856093u ^ (uint32_t)by * 19349663u ^ (uint32_t)bz * 83492791u ^ (uint32_t)ri * 2654435761u) & (kMarkTable - 1);
+#pragma unroll 1
+      for (int p = 0; p < kMarkProbes; ++p) {
+        unsigned long long cur = s_key[h];
+        if (cur == kEmptyKey) {
+          cur = atomicCAS(&s_key[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
+          if (cur == kEmptyKey) {
+            atomicAdd(&s_fill, 1u);
+            // the flush will probe the global hash for this leaf: pull the line towards L2 now (a hint, no data is read)
+            prefetch_l2(&g.hash[(uint32_t)mix64(pack_leaf_key(bx, by, bz)) & g.hash_mask]);
+            cur = key;
+          }
+        }
+        if (cur == key) return (int)h;
+        h = (h + 1) & (kMarkTable - 1);
+      }
+      return -1;
+    };
+
+    int stage = 0;
+    uint32_t phase = 0;
+    bool first = true;
+    for (;; first = false) {
+      mbar_wait(&s_full[stage], phase);
+      const uint32_t kind = s_kind[stage];
+      if (kind == kStageEnd) break;
+      if (kind == kStageFlush) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[stage]);
+        flush(false);
+        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+        continue;
+      }
+      const int ri = (int)s_ri[stage];
+      const unsigned in_chunk = s_cnt[stage];
+      const unsigned long long base = s_base[stage];
+      const DevReading & par = batch.r[ri];   // warp-uniform parameter-bank reads
+      const float range2_reject = par.range2_reject, range2_accept = par.range2_accept, near_accept = par.near_accept;
+      const float oxf = par.oxf, oyf = par.oyf, ozf = par.ozf;
+      const bool zwin = par.filter == 2;
+      const float zlo = zwin ? par.zmin_f : -CUDART_INF_F, zhi = zwin ? par.zmax_f : CUDART_INF_F;
+      if (ri != l_ri) { l_ri = ri; l_ix = 1 << 30; }   // table entries are per reading
+      const float4 * const sp = s_stage + (size_t)stage * kMarkChunk;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        PointXYZ pts[2];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      drop_range += __shfl_xor_sync(kFull, drop_range, d);
-      drop_nonfinite += __shfl_xor_sync(kFull, drop_nonfinite, d);
+        for (int k = 0; k < 2; ++k) {
+          const unsigned idx = (unsigned)(half * 2 + k) * kMarkConsumers + threadIdx.x;
+          if constexpr (kVec4) {
+            const float4 v = sp[idx];
+            pts[k].x = v.x; pts[k].y = v.y; pts[k].z = v.z;
+            pts[k].ok = idx < in_chunk;
+          } else {
+            pts[k] = load_point_generic(par, base + idx, idx < in_chunk);
+          }
+        }
+        if (half == 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[stage]);   // the stage may be refilled: this warp holds its last points in registers
+          if (first) TRACE(0, 2);
+        }
+        if (!__any_sync(kFull, pts[0].ok | pts[1].ok)) continue;   // (the tail of a CTA's last chunk)
+        if (par.has_tf) {   // cloud still in the sensor frame: tf2::doTransform first (measurement_buffer.cpp:141-146)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) transform_point(par.tf, pts[k].x, pts[k].y, pts[k].z);
+        }
+        // ---- single-precision fast path, both points of the pair interleaved ------------------------------------------------
+        int ix[2], iy[2], iz[2];
+        bool take[2], slow[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float fx = pts[k].x, fy = pts[k].y, fz = pts[k].z;
+          // the range test on a float evaluation of the squared distance whose error is far below the margins of the two
+          // thresholds: above range2_reject the exact test certainly rejects, inside [near_accept, range2_accept] it
+          // certainly accepts.  A NaN or infinite coordinate makes d2f NaN or +inf.
+          const float ax = __fsub_rn(fx, oxf), ay = __fsub_rn(fy, oyf), az = __fsub_rn(fz, ozf);
+          const float d2f = fmaf(az, az, fmaf(ay, ay, __fmul_rn(ax, ax)));
+          // PassThrough z window (reference measurement_buffer.cpp:165-175) on exactly equivalent float thresholds
+          const bool zok = !((fz < zlo) | (fz > zhi));
+          const bool inwin = (d2f <= range2_accept) & (d2f >= near_accept);
+          // .cpp:293-303 in float: shift negatives by one voxel (z tests y's sign — sic), multiply by 1/vs, truncate toward zero
+          const float X = fx < 0 ? __fsub_rn(fx, vs_f) : fx;
+          const float Y = fy < 0 ? __fsub_rn(fy, vs_f) : fy;
+          const float Z = fy < 0 ? __fsub_rn(fz, vs_f) : fz;
+          uint32_t diff = 0;
+          ix[k] = quantise_axis_fast(X, c_lo, c_hi, diff);
+          iy[k] = quantise_axis_fast(Y, c_lo, c_hi, diff);
+          iz[k] = quantise_axis_fast(Z, c_lo, c_hi, diff);
+          const bool decided = inwin & (diff == 0);
+          take[k] = pts[k].ok & zok & decided;
+          // everything the fast path cannot decide, and everything that is not finite (counted), takes the exact sequence
+          slow[k] = pts[k].ok & (!(d2f < CUDART_INF_F) | (zok & !(d2f > range2_reject) & !decided));
+        }
+        // ---- the exact double sequence for the points the fast path could not decide (rare; whole warps skip it) ----------------
+        if (__any_sync(kFull, slow[0] | slow[1])) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            if (slow[k]) {
+              const int4 q = quantise_exact(pts[k].x, pts[k].y, pts[k].z, par.ox, par.oy, par.oz, par.mark_range_2, g.vs, g.inv_vs, zlo, zhi);
+              ix[k] = q.x; iy[k] = q.y; iz[k] = q.z;
+              take[k] = q.w == 1;
+              drop_range += q.w == 2 ? 1u : 0u;
+              drop_nonfinite += q.w == 3 ? 1u : 0u;
+            }
+          }
+        }
+        // ---- CTA-local dedupe ----------------------------------------------------------------------------------------------------
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (!take[k]) continue;
+          const int x = ix[k], y = iy[k], z = iz[k];
+          if (g.shard_count > 1 && !shard_owns(x >> 3, g.shard_index, g.shard_count, g.shard_width)) continue;
+          if ((uint32_t)((x ^ l_ix) | (y ^ l_iy) | (z ^ l_iz)) >= 8u) {   // another leaf than the thread's last one
+            const int e = table_lookup(ri, x >> 3, y >> 3, z >> 3);
+            l_mask = e >= 0 ? smem_u32(&s_mask[e][0]) : 0u;
+            l_ix = x; l_iy = y; l_iz = z;   // (a failed lookup is remembered too: the leaf's next voxels go the same way)
+          }
+          // local index l = ((x & 7) * 8 + (y & 7)) * 8 + (z & 7): mask word l >> 5, bit l & 31 (the shift takes its count modulo 32)
+          const uint32_t bit = 1u << ((((uint32_t)y << 3) | ((uint32_t)z & 7u)) & 31u);
+          const uint32_t word_off = (((uint32_t)x << 3) & 0x38u) | ((uint32_t)y & 4u);   // (l >> 5) * 4
+          if (l_mask) {
+            uint32_t cur;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(l_mask + word_off));
+            if (!(cur & bit)) asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(l_mask + word_off), "r"(bit) : "memory");
+          } else {   // table full or leaf out of the table's reach: straight to the global store
+            sync_with_predecessor();
+            mark_voxel_direct(g, x >> 3, y >> 3, z >> 3, (unsigned)(((x & 7) * 8 + (y & 7)) * 8 + (z & 7)), par.now, use_max, batch.min_now);
+          }
+        }
+      }
+      if (++stage == n_stages) { stage = 0; phase ^= 1u; }
     }
-    if (lane == 0) {
-      if (drop_range) atomicAdd(&s_drop[0], drop_range);
-      if (drop_nonfinite) atomicAdd(&s_drop[1], drop_nonfinite);
+    flush(true);
+    TRACE(0, 5);
+
+    // dropped-point statistics: warp reduce, shared-memory add, one fire-and-forget global reduction per CTA
+    if (__any_sync(kFull, (drop_range | drop_nonfinite) != 0)) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        drop_range += __shfl_xor_sync(kFull, drop_range, d);
+        drop_nonfinite += __shfl_xor_sync(kFull, drop_nonfinite, d);
+      }
+      if (lane == 0) {
+        if (drop_range) atomicAdd(&s_drop[0], drop_range);
+        if (drop_nonfinite) atomicAdd(&s_drop[1], drop_nonfinite);
+      }
+    }
+    named_bar_sync(1, kMarkConsumers);
+    if (threadIdx.x == 0) {
+      if (s_drop[0]) red_add_u64(&g.ctr->dropped_range, (unsigned long long)s_drop[0]);   // rare: points beyond +-2^23 voxels
+      if (s_drop[1]) red_add_u64(&g.ctr->dropped_nonfinite, (unsigned long long)s_drop[1]);
+      TRACE(0, 6);
     }
   }
-  named_bar_sync(1, kMarkConsumers);
-  if (threadIdx.x == 0) {
-    if (s_drop[0]) red_add_u64(&g.ctr->dropped_range, (unsigned long long)s_drop[0]);   // rare: points beyond +-2^23 voxels
-    if (s_drop[1]) red_add_u64(&g.ctr->dropped_nonfinite, (unsigned long long)s_drop[1]);
-    TRACE(0, 6);
+
+  // =====================================================================================================================
+  // costmap pass (fused cycle), all 32 warps: it needs the sweep's column counts, nothing of Mark
+  // =====================================================================================================================
+  if constexpr (kCostmap) {
+    pdl_wait();
+    const uint32_t n_tiles = min(ld_volatile_u32(&g.ctr->tile_n), g.tile_capacity);
+    constexpr uint32_t kCmBatch = 4;
+    constexpr uint32_t kCmWarps = kMarkThreads / 32;
+    const uint32_t cw = blockIdx.x * kCmWarps + warp;
+    unsigned cm_n = 0;
+    int cm_mnx = INT_MAX, cm_mny = INT_MAX, cm_mxx = INT_MIN, cm_mxy = INT_MIN;
+    for (uint32_t t0 = cw * kCmBatch; t0 < n_tiles; t0 += gridDim.x * kCmWarps * kCmBatch)
+      costmap_tile_batch<(int)kCmBatch, kCmBits>(g, cm, costmap, t0, n_tiles, lane, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy);
+    costmap_warp_accumulate(g.ctr, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy);
+    if (lane == 0) __threadfence();   // this warp's accumulator updates are visible before the CTA takes its ticket
+    named_bar_sync(2, kMarkThreads);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(&g.ctr->cm_ticket, 1u) == gridDim.x - 1) {   // last CTA publishes the result and re-arms the accumulators
+        __threadfence();
+        costmap_publish_result(g.ctr);
+        g.ctr->cm_ticket = 0;
+        __threadfence();
+      }
+    }
   }
 }
 
@@ -518,28 +547,22 @@ int env_int(const char * name, int dflt, int lo, int hi)
   const int x = std::atoi(v);
   return x < lo ? lo : (x > hi ? hi : x);
 }
-// launch geometry of the Mark kernel: CTAs per SM and bulk-copy stages per CTA.  (STVL_MARK_CTAS_PER_SM / STVL_MARK_STAGES
-// are tuning knobs for profiling; the defaults are what the measurements in DESIGN.md were taken with.)
-int mark_ctas_per_sm() { static const int v = env_int("STVL_MARK_CTAS_PER_SM", 1, 1, 2); return v; }
-int mark_stages(bool vec4) { static const int v = env_int("STVL_MARK_STAGES", 6, 2, kMarkStagesMax); return vec4 ? v : 2; }
+// bulk-copy stages per CTA (STVL_MARK_STAGES is a tuning knob for profiling; the default is what the measurements in
+// DESIGN.md were taken with)
+int mark_stages(bool vec4) { static const int v = env_int("STVL_MARK_STAGES", kMarkStagesMax, 2, kMarkStagesMax); return vec4 ? v : 2; }
 size_t mark_smem_bytes(bool vec4) { return (vec4 ? (size_t)mark_stages(true) * kMarkChunk * 16 : 0) + (size_t)kMarkTable * (8 + 64); }
 }  // namespace
 
+// one CTA per SM; small batches get fewer CTAs (at least 8 blocks = 1024 points each)
 uint32_t mark_grid_for(const MarkBatch & batch, int sm_count)
 {
-  const uint32_t runs = (batch.total_blocks + kMarkRun - 1) / kMarkRun;
-  return std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)(sm_count * mark_ctas_per_sm()), runs));
+  const uint32_t want = (batch.total_blocks + 7) / 8;
+  return std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)sm_count, want));
 }
-// column tiles the fused variant's costmap warps can take without becoming the critical path of the launch
+// column tiles the fused variant's costmap pass can take without becoming the critical path of the launch
 uint32_t mark_costmap_tiles_capacity(const MarkBatch & batch, int sm_count)
 {
-  return mark_grid_for(batch, sm_count) * (uint32_t)kMarkCmWarps * 24u;
-}
-uint32_t mark_cursor_advance(const MarkBatch & batch, int sm_count)
-{
-  // every producer stops at its first out-of-range run: the cursor ends at (runs + grid) * kMarkRun past the launch's base
-  const uint32_t runs = (batch.total_blocks + kMarkRun - 1) / kMarkRun;
-  return (runs + mark_grid_for(batch, sm_count)) * (uint32_t)kMarkRun;
+  return mark_grid_for(batch, sm_count) * (uint32_t)(kMarkThreads / 32) * 64u;
 }
 
 template <bool kVec4, bool kCostmap, bool kCmBits>
@@ -556,14 +579,18 @@ static cudaError_t launch_mark_variant(const GridView & g, const MarkBatch & bat
     cudaFuncSetAttribute(mark_kernel<kVec4, kCostmap, kCmBits>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
-  const unsigned block = (kMarkConsumerWarps + 1 + (kCostmap ? kMarkCmWarps : 0)) * 32;
-  return launch_ex(mark_kernel<kVec4, kCostmap, kCmBits>, mark_grid_for(batch, sm_count), block, smem, s, pdl, g, batch, cm, costmap,
+  // constants of the single-precision quantisation (quantise_axis_fast), rounded here exactly as the proof there assumes
+  MarkBatch b = batch;
+  b.vs_f = (float)g.vs;                                              // exact: vs is a float widened to double
+  b.c_lo = (float)g.inv_vs * 0.999999701976776123046875f;            // (float)(1/vs) * (1 - 5 * 2^-24), one rounding
+  b.c_hi = (float)g.inv_vs * 1.00000035762786865234375f;             // (float)(1/vs) * (1 + 3 * 2^-23), one rounding
+  return launch_ex(mark_kernel<kVec4, kCostmap, kCmBits>, mark_grid_for(batch, sm_count), (unsigned)kMarkThreads, smem, s, pdl, g, b, cm, costmap,
                    mark_stages(kVec4));
 }
 
 // pdl: the caller guarantees that the kernel's inputs (clouds) were complete before the PREDECESSOR of this launch in the
 // stream started, and that the predecessor is this library's sweep kernel.  cm / costmap != NULL: fused costmap pass
-// (cm_bits: into a cell bitmap).  batch.cursor_sel / cursor_base must have been set by the caller (see mark_cursor_advance).
+// (cm_bits: into a cell bitmap).
 cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s, bool pdl,
                         const CostmapDev * cm, uint8_t * costmap, bool cm_bits)
 {
@@ -583,7 +610,7 @@ cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_coun
 }
 uint32_t mark_blocks_for(unsigned long long n_points)
 {
-  return (uint32_t)((n_points + kMarkChunk - 1) / kMarkChunk);
+  return (uint32_t)((n_points + kMarkBlock - 1) / kMarkBlock);
 }
 cudaError_t launch_load_voxels(const GridView & g, const int32_t * x, const int32_t * y, const int32_t * z, const double * t,
                                unsigned long long n, cudaStream_t s)

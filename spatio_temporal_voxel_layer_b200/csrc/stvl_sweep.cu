@@ -1,17 +1,17 @@
 // stvl_sweep.cu — ClearFrustums / TemporalClearAndGenerateCostmap (reference spatio_temporal_voxel_grid.cpp:96-224) as ONE
 // kernel.
 //
-// Every CTA walks tiles of leaf slots in three phases:
+// Every CTA walks tile passes over the leaf slots, two phases per pass and ONE CTA barrier between them:
 //   A  one THREAD per leaf: header (key, tmin, tile, 64 B value mask) in one round trip.  A leaf outside every frustum whose
 //      oldest voxel is too young to expire cannot change: its survivors are counted straight from the mask (two adjacent u32
-//      column counters per 64-bit reduction) and its 4 KB time block is never touched.  A leaf no frustum can touch but in
-//      which something may have expired gets the plain decay test from the same thread (phase A', sweep_leaf_decay_only).
-//      Every leaf a frustum may touch is split into batches of 32 active voxels that go into a work queue in SHARED
-//      memory (its time sectors are prefetched into L2).
-//   B  one WARP per queued batch, taken dynamically: leaf-level frustum classification, the reference's exact per-voxel
-//      arithmetic (decay model, first containing frustum, acceleration, strict <), rewrite of accelerated times, bit clears,
-//      per-column survivor counts, optional lists.
-//   C  the thread that queued a leaf folds its batches' minima into the leaf's lower time bound.
+//      column counters per 64-bit reduction) and its 4 KB time block is never touched.  Every other leaf goes into a work
+//      queue in SHARED memory and its occupied 64 B time runs are prefetched into L2.
+//   B  one WARP per queued leaf, taken dynamically.  Lane l owns bit l of every 32-bit mask word, so the mark times of a
+//      word are one coalesced 256 B run and the survivors come back as one ballot — the new mask word.  The next word's
+//      times are requested before the current word is worked on.  Per voxel: the reference's exact arithmetic (decay model,
+//      first containing frustum in reading order, acceleration, strict <), rewrite of accelerated times, per-column survivor
+//      counts, optional lists; per leaf: frustum classification (one lane per frustum), new lower time bound, pruning.
+// Three queues rotate, so a warp that runs out of phase-B work starts phase A of the next pass while the others finish.
 // No global work queue, no second launch, no grid-wide synchronisation: a leaf's whole sweep stays inside one CTA.
 #include <algorithm>
 #include <cstdlib>
@@ -23,7 +23,6 @@ namespace stvl {
 
 constexpr int kSweepThreads = 512;
 constexpr int kSweepWarps = kSweepThreads / 32;
-constexpr int kSweepQueue = 2048;       // batches per tile pass (a tile whose leaves need more is finished in further rounds)
 
 // classify a whole leaf against one frustum: 0 = no voxel centre can be inside, 1 = test per voxel, 2 = all inside
 __device__ __forceinline__ int classify_leaf(const DevFrustum & f, int bx, int by, int bz, double vs, double half_vs)
@@ -69,82 +68,8 @@ __device__ __forceinline__ bool leaf_may_expire(const GridView & g, double now, 
   return !(g.voxel_decay >= 0.0);
 }
 
-// reference .cpp:167-169 / :320-331: remaining time of a voxel marked at v when no frustum accelerates it
-__device__ __forceinline__ double base_duration(const GridView & g, double now, double v)
-{
-  const double t = __dsub_rn(now, v);
-  if (g.decay_model == 0) return __dsub_rn(g.voxel_decay, t);
-  if (g.decay_model == 1) return __dmul_rn(g.voxel_decay, exp(-t));
-  return g.voxel_decay;
-}
-
-// Phase A', ONE THREAD PER LEAF: a leaf that no frustum can touch but whose oldest voxel may have expired only needs the
-// decay test of .cpp:203-211 per voxel — no warp cooperation, no queue.  The thread walks its leaf's occupied voxel columns
-// (8 mark times = one 64 B run, fetched with four independent 128-bit loads), clears the expired bits (it is the only writer
-// of the mask), counts the survivors per column from the new mask bytes and refreshes the leaf's lower time bound.  With
-// thousands of threads doing this at once the SM has far more loads in flight than a warp-per-leaf schedule gives it.
-struct DecayOnlyResult { unsigned n_in, n_clear; int min_x, min_y, max_x, max_y; };
-__device__ __noinline__ DecayOnlyResult sweep_leaf_decay_only(const GridView & g, uint32_t slot, uint64_t key, uint32_t tile, double now,
-                                                              const SweepOutputs & out)
-{
-  DecayOnlyResult acc{0u, 0u, INT_MAX, INT_MAX, INT_MIN, INT_MIN};
-  int bx, by, bz;
-  unpack_leaf_key(key, bx, by, bz);
-  uint32_t * mp = g.leaf_mask + (size_t)slot * 16;
-  const double * tb = g.leaf_time + (size_t)slot * kLeafVoxels;
-  unsigned long long * tc = reinterpret_cast<unsigned long long *>(g.tile_count + (size_t)tile * 64);
-  double vmin = CUDART_INF;
-  unsigned n_in = 0, n_clear = 0;
-  uint32_t alive = 0;
-#pragma unroll 1
-  for (int w = 0; w < 16; ++w) {
-    const uint32_t x = mp[w];
-    if (!x) continue;
-    n_in += __popc(x);
-    uint32_t nx = x;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      const uint32_t byte = (x >> (8 * c)) & 0xFFu;
-      if (!byte) continue;
-      const double2 * p = reinterpret_cast<const double2 *>(tb + w * 32 + c * 8);
-      const double2 t01 = __ldcs(p), t23 = __ldcs(p + 1), t45 = __ldcs(p + 2), t67 = __ldcs(p + 3);
-      const double tv[8] = {t01.x, t01.y, t23.x, t23.y, t45.x, t45.y, t67.x, t67.y};
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (!((byte >> k) & 1u)) continue;
-        if (base_duration(g, now, tv[k]) < 0.) {   // expired by temporal clearing, .cpp:203-211
-          nx &= ~(1u << (8 * c + k));
-          ++n_clear;
-          const int ix = bx * 8 + (w >> 1), iy = by * 8 + ((w & 1) * 4 + c);
-          acc.min_x = min(acc.min_x, ix); acc.max_x = max(acc.max_x, ix);
-          acc.min_y = min(acc.min_y, iy); acc.max_y = max(acc.max_y, iy);
-          if (out.cleared) {   // cleared_cells.insert, .cpp:213-215
-            const unsigned long long o = atomicAdd(&g.ctr->sw[g.sw_cur].n_cleared_out, 1ull);
-            if (o < out.cleared_cap) { out.cleared[2 * o] = ix; out.cleared[2 * o + 1] = iy; }
-          }
-        } else {
-          vmin = fmin(vmin, tv[k]);
-        }
-      }
-    }
-    if (nx != x) mp[w] = nx;
-    alive |= nx;
-    if (nx && tile != kOverflowSlot) {
-      // PopulateCostmapAndPointcloud .cpp:242-250: per-column survivor counts, two adjacent u32 counters per 64-bit reduction
-      uint32_t y = nx - ((nx >> 1) & 0x55555555u);
-      y = (y & 0x33333333u) + ((y >> 2) & 0x33333333u);
-      y = (y + (y >> 4)) & 0x0F0F0F0Fu;
-      const unsigned long long lo = (unsigned long long)(y & 0xFFu) | ((unsigned long long)((y >> 8) & 0xFFu) << 32);
-      const unsigned long long hi = (unsigned long long)((y >> 16) & 0xFFu) | ((unsigned long long)(y >> 24) << 32);
-      if (lo) red_add_u64(tc + w * 2, lo);
-      if (hi) red_add_u64(tc + w * 2 + 1, hi);
-    }
-  }
-  acc.n_in = n_in; acc.n_clear = n_clear;
-  if (!alive) free_leaf(g, slot);            // pruneGrid, .cpp:223
-  else g.leaf_tmin[slot] = vmin;             // exact lower bound again
-  return acc;
-}
+// queue entry: pool slot of a leaf that needs the per-voxel pass | kTouched when a frustum may contain one of its voxels
+constexpr uint32_t kTouched = 0x80000000u;
 
 __global__ void __launch_bounds__(kSweepThreads, 2)
 sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ FrustumParams fparam, const DevFrustum * __restrict__ frustums_gmem,
@@ -153,14 +78,13 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevFrustum * fr = reinterpret_cast<DevFrustum *>(smem_raw);   // frustum parameter blocks, staged for the whole kernel
-  __shared__ uint32_t s_q_slot[kSweepQueue];
-  __shared__ uint8_t s_q_batch[kSweepQueue];
-  __shared__ double s_q_min[kSweepQueue];       // smallest surviving time of the batch
-  __shared__ uint32_t s_q_clear[kSweepQueue];   // which of the batch's 32 voxels were cleared (bit = position in the batch)
-  __shared__ uint16_t s_list[kSweepWarps][32];  // local voxel indices of the batch a warp is working on
+  // three work queues in rotation: tile pass t fills queue t % 3 in phase A and drains it in phase B; a warp that runs out
+  // of phase-B work goes on to phase A of pass t + 1 (queue (t + 1) % 3) without waiting for the others, and queue
+  // (t + 2) % 3 — drained in pass t - 1 — is re-armed meanwhile.  ONE CTA barrier per pass.
+  __shared__ uint32_t s_q[3][kSweepThreads];
+  __shared__ unsigned int s_qn[3], s_qnext[3];
   __shared__ uint32_t s_part[kSweepWarps][kMaxFrustums / 32];
   __shared__ uint32_t s_full[kSweepWarps][kMaxFrustums / 32];
-  __shared__ unsigned int s_qn, s_qlimit, s_qnext;
   __shared__ unsigned int s_red[5];
   __shared__ int s_bb[4];
   const unsigned lane = threadIdx.x & 31;
@@ -177,7 +101,7 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
     for (int i = threadIdx.x; i < words; i += kSweepThreads) dst[i] = src[i];
   }
   if (threadIdx.x == 0) {
-    s_qn = 0; s_qlimit = kSweepQueue; s_qnext = 0;
+    s_qn[0] = s_qn[1] = s_qn[2] = 0; s_qnext[0] = s_qnext[1] = s_qnext[2] = 0;
     s_red[0] = s_red[1] = s_red[2] = s_red[3] = s_red[4] = 0;
     s_bb[0] = s_bb[1] = INT_MAX; s_bb[2] = s_bb[3] = INT_MIN;
   }
@@ -219,22 +143,22 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
   }
   const bool force_full = out.points != nullptr;   // pub_voxels needs every survivor's coordinates
   const int n_chunks = (n_frustums + 31) >> 5;
-  const uint16_t * mask16 = reinterpret_cast<const uint16_t *>(g.leaf_mask);
   SweepAcc acc;
   TRACE(1, 2);
 
-  // Tiles of `tile_leaves` consecutive slots, dealt round-robin to the CTAs in groups of 32 (a contiguous run of leaves
-  // that all need the per-voxel pass — a frustum's interior — is spread over many CTAs).
+  // Tile passes over `tile_leaves` leaf slots per CTA, dealt round-robin to the CTAs in groups of 32 (a contiguous run of
+  // leaves that all need the per-voxel pass — a frustum's interior — is spread over many CTAs).
   const uint32_t groups_per_tile = tile_leaves / 32;          // <= kSweepWarps
   const uint32_t n_groups = (n_slots + 31) / 32;
-  for (uint32_t g0 = 0; g0 < n_groups; g0 += gridDim.x * groups_per_tile) {
+  uint32_t qi = 0;   // queue of this pass (pass number modulo 3)
+  for (uint32_t g0 = 0; g0 < n_groups; g0 += gridDim.x * groups_per_tile, qi = qi == 2 ? 0 : qi + 1) {
     // ---- phase A: one thread per leaf -------------------------------------------------------------------------------------
     // group index of this warp in the tile: warp w handles group (g0 + w * gridDim + blockIdx) — interleaved across CTAs
-    bool pending = false;
-    uint32_t slot = 0, my_q0 = 0, my_nb = 0;
     if (warp < groups_per_tile) {
       const uint32_t grp = g0 + warp * gridDim.x + blockIdx.x;
-      slot = grp * 32 + lane;
+      const uint32_t slot = grp * 32 + lane;
+      uint32_t entry = 0;
+      bool queue_it = false;
       if (grp < n_groups && slot < n_slots) {
         const uint64_t key = g.leaf_key[slot];
         const double tmin = g.leaf_tmin[slot];
@@ -264,26 +188,17 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
                 touches = classify_leaf(F, bx, by, bz, g.vs, g.half_vs) != 0;
               }
             }
-            if (!touches && leaf_may_expire(g, now, tmin)) {
-              // phase A': decay test only, this thread alone
-              const DecayOnlyResult r = sweep_leaf_decay_only(g, slot, key, tile, now, out);
-              acc.swept += r.n_in; acc.clear += r.n_clear; acc.surv += r.n_in - r.n_clear;
-              acc.min_x = min(acc.min_x, r.min_x); acc.min_y = min(acc.min_y, r.min_y);
-              acc.max_x = max(acc.max_x, r.max_x); acc.max_y = max(acc.max_y, r.max_y);
-            } else if (touches) {
-              unsigned pc = 0;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) pc += __popc(mw[q].x) + __popc(mw[q].y) + __popc(mw[q].z) + __popc(mw[q].w);
-              my_nb = (pc + 31) / 32;
-              pending = true;
-              // the leaf's mark times will be needed in phase B: pull the touched 64 B column runs into L2 now
+            if (touches || leaf_may_expire(g, now, tmin)) {
+              queue_it = true;
+              entry = slot | (touches ? kTouched : 0u);
+              // the leaf's mark times will be needed in phase B: pull the occupied 64 B column runs into L2 now
               const double * tb = g.leaf_time + (size_t)slot * kLeafVoxels;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const uint32_t wv[4] = {mw[q].x, mw[q].y, mw[q].z, mw[q].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  uint32_t x = wv[j];
+                  const uint32_t x = wv[j];
                   if (!x) continue;
                   const double * wb = tb + (q * 4 + j) * 32;
 #pragma unroll
@@ -292,8 +207,8 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
                 }
               }
             } else {
-              // PopulateCostmapAndPointcloud .cpp:242-250 for every (surviving) voxel: per-column popcounts, two adjacent u32
-              // column counters per 64-bit reduction (no carry: counts stay < 2^32)
+              // nothing in this leaf can change: PopulateCostmapAndPointcloud .cpp:242-250 for every voxel straight from the
+              // mask — per-column popcounts, two adjacent u32 column counters per 64-bit reduction (no carry: counts < 2^32)
               unsigned cnt = 0;
               unsigned long long * tc = reinterpret_cast<unsigned long long *>(g.tile_count + (size_t)tile * 64);
 #pragma unroll
@@ -320,37 +235,43 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
           }
         }
       }
-    }
-    // ---- rounds of (queue fill, phase B, phase C) until every leaf of the tile that needs the per-voxel pass has had it --------
-    for (;;) {
-      if (pending) {
-        const uint32_t q0 = atomicAdd(&s_qn, my_nb);
-        if (q0 + my_nb <= (uint32_t)kSweepQueue) {
-          for (uint32_t b = 0; b < my_nb; ++b) { s_q_slot[q0 + b] = slot; s_q_batch[q0 + b] = (uint8_t)b; }
-          my_q0 = q0;
-          pending = false;
-        } else {
-          atomicMin(&s_qlimit, q0);   // entries from here on were not written: this leaf waits for the next round
-          my_q0 = 0xFFFFFFFFu;
-        }
+      // warp-aggregated push
+      const unsigned qm = __ballot_sync(kFull, queue_it);
+      if (qm) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&s_qn[qi], (unsigned)__popc(qm));
+        base = __shfl_sync(kFull, base, 0);
+        if (queue_it) s_q[qi][base + __popc(qm & ((1u << lane) - 1u))] = entry;
       }
-      __syncthreads();
-      const uint32_t n_items = min(s_qn, s_qlimit);
-      // ---- phase B: one warp per batch ----------------------------------------------------------------------------------------
-      for (;;) {
-        uint32_t item = 0;
-        if (lane == 0) item = atomicAdd(&s_qnext, 1u);
-        item = __shfl_sync(kFull, item, 0);
-        if (item >= n_items) break;
-        const uint32_t bslot = s_q_slot[item];
-        const uint32_t batch = s_q_batch[item];
-        const uint64_t key = g.leaf_key[bslot];
-        const uint32_t tile = g.leaf_tile[bslot];
-        const uint32_t m16 = mask16[(size_t)bslot * 32 + lane];   // each lane owns two voxel columns = local indices [lane*16, lane*16+16)
-        int bx, by, bz;
-        unpack_leaf_key(key, bx, by, bz);
-        // leaf-level culling: one lane per frustum
-        unsigned any_cand = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { const uint32_t qz = qi == 0 ? 2 : qi - 1; s_qn[qz] = 0; s_qnext[qz] = 0; }   // (t + 2) % 3 == (t - 1) % 3
+    const uint32_t n_items = s_qn[qi];
+    // ---- phase B: one warp per queued leaf, taken dynamically.  Lane l owns bit l of every mask word: the 32 mark times of
+    // a word are one coalesced 256 B run, survivors come back as one ballot = the new mask word --------------------------------
+    for (;;) {
+      uint32_t item = 0;
+      if (lane == 0) item = atomicAdd(&s_qnext[qi], 1u);
+      item = __shfl_sync(kFull, item, 0);
+      if (item >= n_items) break;
+      const uint32_t ent = s_q[qi][item];
+      const uint32_t bslot = ent & ~kTouched;
+      const bool touched = (ent & kTouched) != 0;
+      const uint64_t key = g.leaf_key[bslot];
+      const uint32_t tile = g.leaf_tile[bslot];
+      const uint32_t mword = lane < 16 ? g.leaf_mask[(size_t)bslot * 16 + lane] : 0u;
+      const double * tb = g.leaf_time + (size_t)bslot * kLeafVoxels;
+      unsigned nz = __ballot_sync(kFull, mword != 0);
+      // first word's times are requested before anything else is looked at
+      int w = __ffs(nz) - 1;
+      nz &= nz - 1;
+      uint32_t m = __shfl_sync(kFull, mword, w & 15);
+      double v = ((m >> lane) & 1u) ? __ldcs(tb + w * 32 + (int)lane) : 0.0;
+      int bx, by, bz;
+      unpack_leaf_key(key, bx, by, bz);
+      // leaf-level culling: one lane per frustum
+      unsigned any_cand = 0;
+      if (touched) {
         for (int c = 0; c < n_chunks; ++c) {
           const int f = c * 32 + (int)lane;
           const int cls = f < n_frustums ? classify_leaf(fr[f], bx, by, bz, g.vs, g.half_vs) : 0;
@@ -358,32 +279,23 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
           if (lane == 0) { s_part[warp][c] = pm; s_full[warp][c] = fm; }
           any_cand |= pm | fm;
         }
-        // the batch's voxels: entries [32*batch, 32*batch + 32) of the leaf's active voxels in ascending local index
-        const int cnt = __popc(m16);
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(kFull, incl, d); if ((int)lane >= d) incl += v; }
-        const int total = __shfl_sync(kFull, incl, 31);
-        {
-          int pos = incl - cnt - 32 * (int)batch;
-          uint32_t m = m16;
-          while (m) {
-            const int b = __ffs(m) - 1; m &= m - 1;
-            if (pos >= 0 && pos < 32) s_list[warp][pos] = (uint16_t)(lane * 16 + b);
-            ++pos;
-          }
-        }
         __syncwarp();
-        const int i = 32 * (int)batch + (int)lane;
-        const bool have = i < total;
-        bool cleared = false, survived = false;
-        int ix = 0, iy = 0, iz = 0;
-        unsigned li = 0;
-        double vmin = CUDART_INF;   // smallest mark time among this batch's survivors
+      }
+      double vmin = CUDART_INF;   // smallest mark time among the leaf's survivors
+      uint32_t alive = 0;
+      unsigned long long * tc = reinterpret_cast<unsigned long long *>(g.tile_count + (size_t)tile * 64);
+      while (w >= 0) {
+        // request the next word's times, then work on this one
+        const int wn = __ffs(nz) - 1;
+        nz &= nz - 1;
+        const uint32_t mn = wn >= 0 ? __shfl_sync(kFull, mword, wn & 15) : 0u;
+        const double vn = ((mn >> lane) & 1u) ? __ldcs(tb + wn * 32 + (int)lane) : 0.0;
+
+        const bool have = ((m >> lane) & 1u) != 0;
+        const unsigned li = (unsigned)w * 32u + lane;
+        const int ix = bx * 8 + (int)(li >> 6), iy = by * 8 + (int)((li >> 3) & 7), iz = bz * 8 + (int)(li & 7);
+        bool cleared = false;
         if (have) {
-          li = s_list[warp][lane];
-          const double v = __ldcs(g.leaf_time + (size_t)bslot * kLeafVoxels + li);
-          ix = bx * 8 + (int)(li >> 6); iy = by * 8 + (int)((li >> 3) & 7); iz = bz * 8 + (int)(li & 7);
           ++acc.swept;
           // .cpp:167-169
           const double t = __dsub_rn(now, v);
@@ -398,9 +310,9 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
             const double wx = index_to_world(ix, g.vs, g.half_vs), wy = index_to_world(iy, g.vs, g.half_vs), wz = index_to_world(iz, g.vs, g.half_vs);
             for (int c = 0; c < n_chunks && hit < 0; ++c) {
               const unsigned fm = s_full[warp][c];
-              unsigned m = s_part[warp][c] | fm;
-              while (m) {
-                const int b = __ffs(m) - 1; m &= m - 1;
+              unsigned cm = s_part[warp][c] | fm;
+              while (cm) {
+                const int b = __ffs(cm) - 1; cm &= cm - 1;
                 const int f = c * 32 + b;
                 bool in;
                 if ((fm >> b) & 1u) in = true;
@@ -419,24 +331,19 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
             else {
               const double nv = __dsub_rn(v, accel);
               if (__double_as_longlong(nv) != __double_as_longlong(v)) { g.leaf_time[(size_t)bslot * kLeafVoxels + li] = nv; ++acc.rewr; }
-              vmin = nv;
+              vmin = fmin(vmin, nv);
             }
           } else if (base_dur < 0.) {
             cleared = true;   // .cpp:203-211
           } else {
-            vmin = v;
+            vmin = fmin(vmin, v);
           }
-          survived = !cleared;
           if (cleared) {
-            // (the bit is cleared in phase C: the batches of a leaf are defined on the mask as phase A saw it, so nothing
-            // may change it while other warps still compact it)
             ++acc.clear;
             acc.min_x = min(acc.min_x, ix); acc.max_x = max(acc.max_x, ix);
             acc.min_y = min(acc.min_y, iy); acc.max_y = max(acc.max_y, iy);
           } else {
             ++acc.surv;
-            // PopulateCostmapAndPointcloud .cpp:242-250: _cost_map[(x,y)] += 1 per surviving voxel
-            if (tile != kOverflowSlot) red_add_u32(g.tile_count + (size_t)tile * 64 + (li >> 3), 1u);
           }
           if (amb) {
             ++acc.amb;
@@ -446,71 +353,52 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
             }
           }
         }
+        const unsigned cmk = __ballot_sync(kFull, cleared);
+        const uint32_t sm = m & ~cmk;                                    // the word's survivors = its new mask
+        if (cmk && lane == 0) g.leaf_mask[(size_t)bslot * 16 + w] = sm;   // this warp is the only writer of the leaf's mask
+        alive |= sm;
+        // PopulateCostmapAndPointcloud .cpp:242-250: _cost_map[(x,y)] += 1 per surviving voxel — the word holds four voxel
+        // columns, one per byte; lanes 0 and 1 each push a pair of adjacent u32 column counters as one 64-bit reduction
+        if (sm && tile != kOverflowSlot && lane < 2) {
+          uint32_t y = sm - ((sm >> 1) & 0x55555555u);
+          y = (y & 0x33333333u) + ((y >> 2) & 0x33333333u);
+          y = (y + (y >> 4)) & 0x0F0F0F0Fu;
+          y >>= 16 * lane;
+          const unsigned long long pair = (unsigned long long)(y & 0xFFu) | ((unsigned long long)((y >> 8) & 0xFFu) << 32);
+          if (pair) red_add_u64(tc + w * 2 + (int)lane, pair);
+        }
         // optional lists: warp-aggregated appends
-        if (out.points) {   // PopulateCostmapAndPointcloud .cpp:234-240: Point32 = (float) voxel centre
-          const unsigned sm = __ballot_sync(kFull, survived);
-          if (sm) {
-            unsigned long long b0 = 0;
-            if (lane == (unsigned)(__ffs(sm) - 1)) b0 = atomicAdd(&g.ctr->sw[g.sw_cur].n_points_out, (unsigned long long)__popc(sm));
-            b0 = __shfl_sync(kFull, b0, __ffs(sm) - 1);
-            if (survived) {
-              const unsigned long long o = b0 + __popc(sm & ((1u << lane) - 1));
-              if (o < out.points_cap) {
-                out.points[3 * o] = (float)index_to_world(ix, g.vs, g.half_vs);
-                out.points[3 * o + 1] = (float)index_to_world(iy, g.vs, g.half_vs);
-                out.points[3 * o + 2] = (float)index_to_world(iz, g.vs, g.half_vs);
-              }
+        if (out.points && sm) {   // PopulateCostmapAndPointcloud .cpp:234-240: Point32 = (float) voxel centre
+          unsigned long long b0 = 0;
+          if (lane == 0) b0 = atomicAdd(&g.ctr->sw[g.sw_cur].n_points_out, (unsigned long long)__popc(sm));
+          b0 = __shfl_sync(kFull, b0, 0);
+          if ((sm >> lane) & 1u) {
+            const unsigned long long o = b0 + __popc(sm & ((1u << lane) - 1u));
+            if (o < out.points_cap) {
+              out.points[3 * o] = (float)index_to_world(ix, g.vs, g.half_vs);
+              out.points[3 * o + 1] = (float)index_to_world(iy, g.vs, g.half_vs);
+              out.points[3 * o + 2] = (float)index_to_world(iz, g.vs, g.half_vs);
             }
           }
         }
-        if (out.cleared) {   // cleared_cells.insert, .cpp:213-215
-          const unsigned cmk = __ballot_sync(kFull, cleared);
-          if (cmk) {
-            unsigned long long b0 = 0;
-            if (lane == (unsigned)(__ffs(cmk) - 1)) b0 = atomicAdd(&g.ctr->sw[g.sw_cur].n_cleared_out, (unsigned long long)__popc(cmk));
-            b0 = __shfl_sync(kFull, b0, __ffs(cmk) - 1);
-            if (cleared) {
-              const unsigned long long o = b0 + __popc(cmk & ((1u << lane) - 1));
-              if (o < out.cleared_cap) { out.cleared[2 * o] = ix; out.cleared[2 * o + 1] = iy; }
-            }
+        if (out.cleared && cmk) {   // cleared_cells.insert, .cpp:213-215
+          unsigned long long b0 = 0;
+          if (lane == 0) b0 = atomicAdd(&g.ctr->sw[g.sw_cur].n_cleared_out, (unsigned long long)__popc(cmk));
+          b0 = __shfl_sync(kFull, b0, 0);
+          if (cleared) {
+            const unsigned long long o = b0 + __popc(cmk & ((1u << lane) - 1u));
+            if (o < out.cleared_cap) { out.cleared[2 * o] = ix; out.cleared[2 * o + 1] = iy; }
           }
         }
+        w = wn; m = mn; v = vn;
+      }
+      // the leaf's lower time bound = minimum over its survivors; a leaf with none goes back to the pool (pruneGrid, .cpp:223)
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) vmin = fmin(vmin, __shfl_xor_sync(kFull, vmin, d));
-        const unsigned cleared_lanes = __ballot_sync(kFull, cleared);
-        if (lane == 0) { s_q_min[item] = vmin; s_q_clear[item] = cleared_lanes; }
-        __syncwarp();
+      for (int d = 16; d > 0; d >>= 1) vmin = fmin(vmin, __shfl_xor_sync(kFull, vmin, d));
+      if (lane == 0) {
+        if (!alive) free_leaf(g, bslot);
+        else g.leaf_tmin[bslot] = vmin;
       }
-      __syncthreads();
-      // ---- phase C: the leaf's lower time bound = minimum over its batches (+inf when nothing survived: the next sweep frees it)
-      if (my_nb && my_q0 != 0xFFFFFFFFu) {
-        double m = CUDART_INF;
-        uint32_t any_clear = 0;
-        for (uint32_t b = 0; b < my_nb; ++b) { m = fmin(m, s_q_min[my_q0 + b]); any_clear |= s_q_clear[my_q0 + b]; }
-        if (any_clear) {
-          // clear the bits of the expired voxels: walk the leaf's active voxels in the order the batches were cut from
-          // (ascending local index); this thread is the only writer of the leaf's mask in this kernel
-          uint32_t * mp = g.leaf_mask + (size_t)slot * 16;
-          uint32_t k = 0;
-          for (int w = 0; w < 16; ++w) {
-            const uint32_t orig = mp[w];
-            uint32_t x = orig, nx = orig;
-            while (x) {
-              const int b = __ffs(x) - 1; x &= x - 1;
-              if ((s_q_clear[my_q0 + (k >> 5)] >> (k & 31)) & 1u) nx &= ~(1u << b);
-              ++k;
-            }
-            if (nx != orig) mp[w] = nx;
-          }
-        }
-        if (m == CUDART_INF) free_leaf(g, slot);   // every voxel of the leaf was cleared: pruneGrid, .cpp:223
-        else g.leaf_tmin[slot] = m;               // exact lower bound again
-        my_nb = 0;
-      }
-      const int more = __syncthreads_or(pending ? 1 : 0);
-      if (threadIdx.x == 0) { s_qn = 0; s_qlimit = kSweepQueue; s_qnext = 0; }
-      __syncthreads();
-      if (!more) break;
     }
   }
   TRACE(1, 3);
