@@ -1,12 +1,12 @@
-"""Per-CTA phase timeline of the four cycle kernels (profiling only).
+"""Per-CTA phase timeline of the sweep and Mark kernels (profiling only).
 
 Needs the trace variant of the library (never the product):
     python -m spatio_temporal_voxel_layer_b200.build --trace
     STVL_B200_LIB=spatio_temporal_voxel_layer_b200/libstvl_b200_trace.so python profiles/trace_phases.py [--cycles 60]
 
 Thread 0 of every CTA stamps %globaltimer at phase boundaries (csrc/stvl_kernels.cu, TRACE(kernel, phase)); this script
-runs config-2 cycles back to back (the bench's device-resident loop), reads the stamps of the LAST cycle and prints,
-per kernel and phase, when the first / median / last CTA reached it, relative to the first CTA start of the cycle.
+runs config-2 cycles back to back on the 710,765-voxel seed (dt 0.2 s), reads the stamps of the LAST cycle and prints, per
+kernel and phase, when the first / median / last CTA reached it, relative to the kernel's first CTA entry.
 """
 import argparse
 import ctypes as C
@@ -20,16 +20,15 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault("STVL_B200_LIB", os.path.join(ROOT, "spatio_temporal_voxel_layer_b200", "libstvl_b200_trace.so"))
 
 PHASES = {
-    0: ("mark_kernel", ["entry", "setup done", "chunk0 arrived", "chunks done", "leaves resolved", "flushed", "exit"]),
-    1: ("sweep_triage", ["entry", "high_water read", "re-arm issued", "leaves done", "published"]),
-    2: ("sweep_leaf", ["entry", "predecessor done", "queue_n read", "leaves done", "published"]),
-    3: ("costmap_kernel", ["entry", "tile_n read", "tiles done", "published"]),
+    0: ("mark_kernel", ["entry", "setup done", "chunk0 consumed", "chunks done", "leaves resolved", "flushed", "exit"]),
+    1: ("sweep_kernel", ["entry", "predecessor done", "re-arm issued", "leaves done", "published"]),
 }
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--cycles", type=int, default=60)
+    ap.add_argument("--cycles", type=int, default=16)
+    ap.add_argument("--dt", type=float, default=0.2)
     ap.add_argument("--staged", action="store_true", help="enqueue the cycle stage by stage (three C-ABI calls, no overlap) instead of the fused call")
     args = ap.parse_args()
     import torch
@@ -66,7 +65,7 @@ def main():
             e0.record(stream)
         th = time.perf_counter()
         slot = step % len(w.cycles)
-        now = w.now0 + w.dt * (step + 1)
+        now = w.now0 + args.dt * (step + 1)
         for k in range(w.n_cams):
             arrs[slot][k].now = now + 1e-4 * k
         if args.staged:
@@ -86,60 +85,28 @@ def main():
     L.stvl_debug_trace.argtypes = [C.c_void_p, C.c_size_t]
     rc = L.stvl_debug_trace(tr.ctypes.data_as(C.c_void_p), tr.nbytes)
     assert rc == 0, rc
-    order = [1, 2, 0, 3]   # stream order inside a cycle
-    # the stamps are those of the last launch of each kernel; the last cycle is triage -> leaf -> mark -> costmap
-    t0 = min(int(tr[1, :, 0][tr[1, :, 0] > 0].min()), int(tr[0, :, 0][tr[0, :, 0] > 0].min()))
-    t0 = int(tr[1, :, 0][tr[1, :, 0] > 0].min())
-    print("times in us relative to the first CTA of sweep_triage of the last cycle; first / median / last CTA")
+    order = [1, 0]   # stream order inside a cycle
     for k in order:
         name, phases = PHASES[k]
         used = tr[k, :, 0] > 0
         n = int(used.sum())
+        if n == 0:
+            continue
+        t0 = int(tr[k, used, 0].min())
         sms = len(np.unique(tr[k, used, 7] & 0xFFFF))
-        print("== %-15s %4d CTAs traced on %3d SMs" % (name, n, sms))
+        print("== %-15s %4d CTAs traced on %3d SMs; times in us relative to the kernel's first CTA entry: first / median / last CTA" % (name, n, sms))
         for ph, label in enumerate(phases):
             v = tr[k, used, ph].astype(np.int64)
             v = v[v > 0] - t0
             if len(v) == 0:
                 continue
             print("   %-18s n=%4d  first %8.2f  median %8.2f  last %8.2f" % (label, len(v), v.min() / 1e3, np.median(v) / 1e3, v.max() / 1e3))
-        # per-CTA phase durations (median / max)
         for ph in range(1, len(phases)):
             a, b = tr[k, used, ph - 1].astype(np.int64), tr[k, used, ph].astype(np.int64)
             ok = (a > 0) & (b > 0)
             if ok.any():
                 d = (b - a)[ok] / 1e3
                 print("     d(%s -> %s): median %.2f  p90 %.2f  max %.2f us" % (phases[ph - 1], phases[ph], np.median(d), np.percentile(d, 90), d.max()))
-    # Mark: when the CTAs became resident, how many chunks each took, how long a chunk took
-    mk = tr[0]
-    used = mk[:, 0] > 0
-    ent = (mk[used, 0].astype(np.int64) - t0) / 1e3
-    nch = (mk[used, 7] >> 16).astype(np.int64)
-    dur = (mk[used, 3].astype(np.int64) - mk[used, 2].astype(np.int64)) / 1e3
-    print("mark entry percentiles (us): p10 %.1f p25 %.1f p50 %.1f p75 %.1f p90 %.1f; CTAs with chunks: %d; chunks per CTA p10 %d p50 %d p90 %d max %d"
-          % (*np.percentile(ent, [10, 25, 50, 75, 90]), int((nch > 0).sum()), *np.percentile(nch[nch > 0], [10, 50, 90]), nch.max()))
-    ok = (nch > 0) & (dur > 0) & (dur < 1000)
-    per = dur[ok] / nch[ok]
-    print("time per chunk per CTA (us): p10 %.2f p50 %.2f p90 %.2f" % tuple(np.percentile(per, [10, 50, 90])))
-    for lo, hi in ((0, 24), (24, 28), (28, 32), (32, 100)):
-        sel = ok & (ent >= lo) & (ent < hi)
-        if sel.any():
-            print("  CTAs entering in [%d, %d) us: %d, chunks %d, time/chunk p50 %.2f" % (lo, hi, sel.sum(), nch[sel].sum(), np.median(dur[sel] / nch[sel])))
-    # the slowest CTAs of the leaf pass (blockIdx < n_dense_ctas = 2 x SMs take the dense leaves)
-    k = 2
-    a, b = tr[k, :, 2].astype(np.int64), tr[k, :, 3].astype(np.int64)
-    ok = (a > 0) & (b > a)
-    idx = np.nonzero(ok)[0]
-    d = (b - a)[ok] / 1e3
-    top = np.argsort(-d)[:12]
-    print("slowest leaf-pass CTAs (queue_n read -> leaves done): " + ", ".join(
-        "cta %d: %.2f us (warp0: %d leaves, lane0 %d voxels)" % (idx[t], d[t], tr[k, idx[t], 5], tr[k, idx[t], 6]) for t in top))
-    dd = d[idx < 296]
-    ds = d[idx >= 296]
-    if len(dd):
-        print("dense CTAs: n=%d median %.2f p90 %.2f max %.2f us" % (len(dd), np.median(dd), np.percentile(dd, 90), dd.max()))
-    if len(ds):
-        print("sparse CTAs: n=%d median %.2f p90 %.2f max %.2f us" % (len(ds), np.median(ds), np.percentile(ds, 90), ds.max()))
     g.close()
 
 
