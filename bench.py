@@ -661,19 +661,25 @@ def bench_ours(args):
         # library's stream around the burst — the kernel's average launch duration without the event-to-kernel latency that a
         # bracket around a single launch includes
         n_burst = 24
-        def mark_burst():
-            for j in range(n_burst):
-                now, slot = cycle_inputs(w, EPISODE_CYCLES + 1 + j)
+        def mark_burst(j0):
+            for j in range(j0, j0 + n_burst):
+                now, slot = cycle_inputs(w, EPISODE_CYCLES + 1 + j)      # clocks keep advancing: one batched launch per call
                 arr = args_dev[slot]
                 stamp(arr, now)
                 check(L.stvl_mark_device(h, arr, n_cams))
-        mark_burst()
+        mark_burst(0)
         barrier()
+        # the host needs longer to enqueue a launch than the kernel runs: a 2 x 2 GB fill goes first, so that the whole burst
+        # is already queued when the GPU reaches the first event
+        scratch = torch.empty(2 << 30, dtype=torch.uint8, device="cuda")
         eb0, eb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            scratch.zero_(); scratch.zero_()
         eb0.record(stream)
-        mark_burst()
+        mark_burst(n_burst)
         eb1.record(stream)
         barrier()
+        del scratch
         mark_burst_ms = eb0.elapsed_time(eb1) / n_burst
 
     # ---- sensitivity of the device-resident cycle to the cycle period (2-3 s of simulated time each, fresh seed) ----------

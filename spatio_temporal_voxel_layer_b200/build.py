@@ -79,7 +79,7 @@ def build_library(force=False, verbose=False, trace=False, csrc=None, out=None):
     out = out or (TRACE_LIB_PATH if trace else LIB_PATH)
     base = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(REPO_ROOT, "include"), "-I", src_dir]
     if trace:
-        base += ["-DSTVL_TRACE"]
+        base += ["-DSTVL_TRACE", "-rdc=true"]   # the stamp buffer is one device symbol shared by the kernel files
     if verbose:
         base += ["-Xptxas", "-v"]
     with tempfile.TemporaryDirectory(prefix="stvl_build_") as tmp:
