@@ -53,7 +53,10 @@ struct Counters {
   uint32_t tile_n;
   uint32_t tile_overflow;
   uint32_t cm_ticket;      // last-CTA-done ticket of the costmap pass (its last CTA publishes cm_acc -> cm)
-  uint32_t pad1[4];
+  // Mark's unit hand-out: next unclaimed unit beyond the first gridDim.x ones, and how many CTAs are done claiming (the
+  // last one puts both back to zero).  Two sets: consecutive Mark launches may overlap under programmatic dependent launch.
+  uint32_t mark_cursor[2];
+  uint32_t mark_ticket[2];
   // dropped input points
   unsigned long long dropped_range, dropped_nonfinite;
   SweepCtr sw[2];
@@ -149,7 +152,7 @@ struct DevReading {
   float oxf, oyf, ozf;    // (float) origin, for that screen
   float tf[12];           // sensor -> global float affine (row-major 3x4), applied first when has_tf
   uint32_t has_tf;
-  uint32_t first_block;   // first 128-point block of this reading in the batch's block index space
+  uint32_t first_block;   // first unit of this reading in the batch's unit index space (units of 1984 points)
   uint32_t vec4;          // 1: point_step==16, offsets 0/4/8, 16 B aligned -> float4 loads
 };
 struct MarkBatch {
@@ -161,7 +164,7 @@ struct MarkBatch {
   int32_t ref_bx;           // reference leaf x of the batch (first reading's origin): block-local table keys store bx - ref_bx
   float vs_f;               // (float)vs
   float c_lo, c_hi;         // (float)(1/vs) scaled down / up by a few ulps: the two ends of the fast quantisation (set at launch)
-  uint32_t pad;
+  uint32_t cursor_sel;      // which Counters::mark_cursor / mark_ticket this launch uses (set at launch, alternating)
   double min_now;           // smallest clock sample in the batch: initial leaf_tmin of leaves created by it
 };
 

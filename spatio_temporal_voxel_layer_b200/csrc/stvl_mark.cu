@@ -1,17 +1,16 @@
 // stvl_mark.cu — Mark / operator() (reference spatio_temporal_voxel_grid.cpp:254-309) as a warp-specialised sm_100a kernel.
 //
-// One persistent CTA of 32 warps per SM; every CTA owns one contiguous, equally sized slice of the batch's points (no work
-// cursor, no atomics on the hand-out, and a slice of a depth image touches few distinct leaves).  Inside a CTA:
-//   producer warp   one elected lane streams the slice global -> shared memory in chunks of up to 3968 points (62 KB) with
-//                   the bulk-copy engine (cp.async.bulk, completion on an mbarrier as transaction bytes; SASS UBLKCP /
-//                   SYNCS), three chunks in flight per SM; the first copies are issued before the CTA has finished
-//                   setting up its tables
-//   31 consumer     wait on the stage's "full" mbarrier, pull their points into registers two at a time, release the stage
-//   warps           ("empty" mbarrier, one arrival per warp) and run the reference's per-point arithmetic: range / z-window
-//                   tests and voxel quantisation on a single-precision fast path that is PROVEN to agree with the
-//                   reference's double arithmetic (see quantise_axis_fast), the exact double sequence for the few points it
-//                   cannot decide; survivors are ORed into a CTA-local table of {(reading, leaf) -> 512-bit mask} in
-//                   shared memory
+// One persistent CTA of 32 warps per SM.  The batch's points are cut into units of up to 1984 points (31 KB, never across two
+// readings); a CTA takes unit blockIdx.x first and claims further ones from a device-side cursor, one claim ahead of the copy
+// it is issuing, so CTAs whose points are cheap (rejected by the range test) take more of them.  Inside a CTA:
+//   producer warp   one elected lane streams the units global -> shared memory with the bulk-copy engine (cp.async.bulk,
+//                   completion on an mbarrier as transaction bytes; SASS UBLKCP / SYNCS), six units in flight per SM; the
+//                   first copies are issued before the CTA has finished setting up its tables
+//   31 consumer     wait on the stage's "full" mbarrier, pull two points each into registers, release the stage ("empty"
+//   warps           mbarrier, one arrival per warp) and run the reference's per-point arithmetic: range / z-window tests and
+//                   voxel quantisation on a single-precision fast path that is PROVEN to agree with the reference's double
+//                   arithmetic (see quantise_axis_fast), the exact double sequence for the few points it cannot decide;
+//                   survivors are ORed into a CTA-local table of {(reading, leaf) -> 512-bit mask} in shared memory
 // Nothing before the flush touches the grid, so all of the streaming may overlap the sweep that precedes Mark on the stream
 // (programmatic dependent launch).  The flush resolves every table entry in the global leaf hash once and pushes one
 // 32-bit OR per touched mask word and one 64-bit max (or store) per distinct voxel.  In the fused cycle all 32 warps then
@@ -24,19 +23,18 @@
 
 namespace stvl {
 
-constexpr int kMarkBlock = 128;                  // hand-out unit: readings start on block boundaries of the batch's index space
 constexpr int kMarkConsumerWarps = 31;
 constexpr int kMarkConsumers = kMarkConsumerWarps * 32;
 constexpr int kMarkThreads = kMarkConsumers + 32;
-constexpr int kMarkPPT = 4;                      // points per consumer thread per chunk, worked on in pairs
-constexpr int kMarkChunk = kMarkConsumers * kMarkPPT;   // 3968 points = 31 blocks = 62 KB of packed float4 points
-constexpr int kMarkChunkBlocks = kMarkChunk / kMarkBlock;
+constexpr int kMarkPPT = 2;                      // points per consumer thread per unit
+constexpr int kMarkChunk = kMarkConsumers * kMarkPPT;   // 1984 points = 31 KB of packed float4 points: the unit of hand-out
 constexpr int kMarkTable = 512;                  // CTA-local (reading, leaf) table entries
 constexpr int kMarkProbes = 16;
-constexpr int kMarkStagesMax = 3;
-constexpr uint32_t kStageData = 0, kStageEnd = 1, kStageFlush = 2;
-static_assert(kMarkThreads == 1024 && kMarkChunk % kMarkBlock == 0, "one CTA of 32 warps; chunks are whole blocks");
-static_assert(kMarkPPT == 4, "the consumer loop is written for two pairs of points per thread");
+constexpr int kMarkStagesMax = 6;
+// per-stage word the producer posts: what the stage holds | reading | sensor-frame cloud | points
+constexpr uint32_t kMetaEnd = 1u << 31, kMetaFlush = 1u << 30, kMetaTf = 1u << 29;
+static_assert(kMarkThreads == 1024, "one CTA of 32 warps");
+static_assert(kMarkPPT == 2, "the consumer loop is written for one pair of points per thread");
 
 struct PointXYZ { float x, y, z; bool ok; };
 
@@ -149,15 +147,16 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
 {
   extern __shared__ __align__(128) unsigned char s_dyn[];
   // dynamic shared memory: [stages (kVec4 only)] [table keys] [table masks]
-  float4 * const s_stage = reinterpret_cast<float4 *>(s_dyn);
   const size_t stage_bytes = kVec4 ? (size_t)n_stages * kMarkChunk * 16 : 0;
   unsigned long long * const s_key = reinterpret_cast<unsigned long long *>(s_dyn + stage_bytes);
   uint32_t (* const s_mask)[16] = reinterpret_cast<uint32_t (*)[16]>(s_dyn + stage_bytes + (size_t)kMarkTable * 8);
   __shared__ uint32_t s_slot[kMarkTable];
   __shared__ double s_rnow[kMaxBatchReadings];
+  // per reading, the single-precision screen of the range / z tests: {range2_reject, range2_accept, near_accept, ox} {oy, oz, zlo, zhi}
+  __shared__ __align__(16) float s_par[kMaxBatchReadings][8];
   __shared__ __align__(8) uint64_t s_full[kMarkStagesMax], s_empty[kMarkStagesMax];
-  __shared__ unsigned long long s_base[kMarkStagesMax];                                      // per stage: first point of the chunk in its reading,
-  __shared__ uint32_t s_kind[kMarkStagesMax], s_ri[kMarkStagesMax], s_cnt[kMarkStagesMax];   // what it holds, reading, points in it
+  __shared__ unsigned long long s_base[kMarkStagesMax];   // per stage: first point of the unit in its reading (generic layouts)
+  __shared__ uint32_t s_meta[kMarkStagesMax];
   __shared__ unsigned int s_fill;          // claimed table entries
   __shared__ unsigned int s_flushes;       // early flushes done (the producer requests at most one at a time)
   __shared__ unsigned int s_drop[2];
@@ -171,9 +170,9 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
   // producer warp
   // =====================================================================================================================
   if (warp == kMarkConsumerWarps) {
-    // this CTA's slice of the batch's block index space
-    uint32_t blk = (uint32_t)(((unsigned long long)batch.total_blocks * blockIdx.x) / gridDim.x);
-    const uint32_t blk_end = (uint32_t)(((unsigned long long)batch.total_blocks * (blockIdx.x + 1)) / gridDim.x);
+    const uint32_t total = batch.total_blocks;
+    uint32_t * const cursor = &g.ctr->mark_cursor[batch.cursor_sel & 1u];
+    uint32_t unit = blockIdx.x;     // the first unit is fixed, further ones are claimed: unit = gridDim.x + (cursor++)
     int ri = 0;
     int stage = 0;            // ring position of the next hand-out ...
     uint32_t phase = 0;       // ... and how often the ring has wrapped (parity)
@@ -181,45 +180,51 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
     unsigned long long policy = 0;
     bool done = false;
     auto advance = [&]() { if (++stage == n_stages) { stage = 0; phase ^= 1u; } };
-    // hand out the next chunk (or the end marker); false once the end marker has been posted
+    // hand out the current unit and claim the next one (or post the end marker); false once the end marker has been posted
     auto produce = [&]() -> bool {
       for (;;) {
-        if (blk >= blk_end) {
+        if (unit >= total) {
           mbar_wait(&s_empty[stage], phase ^ 1u);
-          s_kind[stage] = kStageEnd;
+          s_meta[stage] = kMetaEnd;
           mbar_arrive(&s_full[stage]);
+          // every CTA's last claim is its first out-of-range one: when the last producer gets here, nobody needs the cursor any more
+          __threadfence();
+          if (atomicAdd(&g.ctr->mark_ticket[batch.cursor_sel & 1u], 1u) == gridDim.x - 1) {
+            *cursor = 0;
+            g.ctr->mark_ticket[batch.cursor_sel & 1u] = 0;
+            __threadfence();
+          }
           return false;
         }
-        while (ri + 1 < (int)batch.n_readings && blk >= batch.first_block[ri + 1]) ++ri;
+        const uint32_t cur = unit;
+        unit = gridDim.x + atomicAdd(cursor, 1u);   // in flight while this unit's copy is set up: needed one hand-out later
+        ri = 0;
+#pragma unroll 1
+        for (int k = 1; k < (int)batch.n_readings; ++k) if (cur >= batch.first_block[k]) ri = k;
         const DevReading & rd = batch.r[ri];
-        const uint32_t rd_end = ri + 1 < (int)batch.n_readings ? batch.first_block[ri + 1] : batch.total_blocks;
-        uint32_t take = min(min(blk_end, rd_end) - blk, (uint32_t)kMarkChunkBlocks);
         // points of the reading: the host's count, or (output of the VOXEL pre-filter) a device counter below that bound
         unsigned long long n_pts = rd.n_points;
         if (rd.n_points_dev) { const unsigned long long nd = ld_volatile_u64(rd.n_points_dev); if (nd < n_pts) n_pts = nd; }
-        const unsigned long long base = (unsigned long long)(blk - batch.first_block[ri]) * kMarkBlock;
-        blk += take;
+        const unsigned long long base = (unsigned long long)(cur - batch.first_block[ri]) * kMarkChunk;
         if (base >= n_pts) continue;   // beyond the actual count: nothing to hand out
         const unsigned long long left = n_pts - base;
-        const uint32_t cnt = (uint32_t)(left < (unsigned long long)take * kMarkBlock ? left : (unsigned long long)take * kMarkBlock);
+        const uint32_t cnt = (uint32_t)(left < (unsigned long long)kMarkChunk ? left : (unsigned long long)kMarkChunk);
         mbar_wait(&s_empty[stage], phase ^ 1u);
         // a filling table is flushed early (large or scattered clouds): the marker travels in-band, so every consumer
-        // sees it between the same two chunks
+        // sees it between the same two units
         if (*reinterpret_cast<volatile unsigned int *>(&s_fill) >= (unsigned)(kMarkTable * 5 / 8) &&
             *reinterpret_cast<volatile unsigned int *>(&s_flushes) == flush_requests) {
           ++flush_requests;
-          s_kind[stage] = kStageFlush;
+          s_meta[stage] = kMetaFlush;
           mbar_arrive(&s_full[stage]);
           advance();
           mbar_wait(&s_empty[stage], phase ^ 1u);
         }
-        s_kind[stage] = kStageData;
-        s_ri[stage] = (uint32_t)ri;
-        s_cnt[stage] = cnt;
+        s_meta[stage] = ((uint32_t)ri << 24) | (rd.has_tf ? kMetaTf : 0u) | cnt;
         s_base[stage] = base;
         if constexpr (kVec4) {
           mbar_arrive_expect_tx(&s_full[stage], cnt * 16u);
-          bulk_load(s_stage + (size_t)stage * kMarkChunk, rd.data + base * 16ull, cnt * 16u, &s_full[stage], policy);
+          bulk_load(s_dyn + (size_t)stage * kMarkChunk * 16, rd.data + base * 16ull, cnt * 16u, &s_full[stage], policy);
         } else {
           mbar_arrive(&s_full[stage]);
         }
@@ -243,7 +248,14 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
     // ===================================================================================================================
     // consumer warps
     // ===================================================================================================================
-    if (threadIdx.x < kMaxBatchReadings) s_rnow[threadIdx.x] = threadIdx.x < batch.n_readings ? batch.r[threadIdx.x].now : 0.0;
+    if (threadIdx.x < kMaxBatchReadings) {
+      const DevReading & r = batch.r[threadIdx.x < batch.n_readings ? threadIdx.x : 0];
+      s_rnow[threadIdx.x] = r.now;
+      const bool zwin = r.filter == 2;
+      float * sp = s_par[threadIdx.x];
+      sp[0] = r.range2_reject; sp[1] = r.range2_accept; sp[2] = r.near_accept; sp[3] = r.oxf;
+      sp[4] = r.oyf; sp[5] = r.ozf; sp[6] = zwin ? r.zmin_f : -CUDART_INF_F; sp[7] = zwin ? r.zmax_f : CUDART_INF_F;
+    }
     for (int i = threadIdx.x; i < kMarkTable; i += kMarkConsumers) s_key[i] = kEmptyKey;
     for (int i = threadIdx.x; i < kMarkTable * 16; i += kMarkConsumers) (&s_mask[0][0])[i] = 0;
     named_bar_sync(3, kMarkThreads);   // barriers initialised (producer), table cleared
@@ -252,17 +264,18 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
     bool grid_ok = false;       // this thread has waited for the predecessor grid (the sweep)
     auto sync_with_predecessor = [&]() { if (!grid_ok) { pdl_wait(); grid_ok = true; } };
     unsigned int drop_range = 0, drop_nonfinite = 0;
-    // this thread's most recent voxel that went through the table, and its entry (l_ix = 2^30: no voxel index can share a
-    // leaf with it, fast-path indices are below 2^23)
+    // this thread's most recent voxel that went through the table (l_ix = 2^30: no voxel index can share a leaf with it,
+    // fast-path indices are below 2^23), its reading, and ...
     int l_ix = 1 << 30, l_iy = 0, l_iz = 0, l_ri = -1;
-    // this thread's current leaf in the CTA-local table: shared-window address of its 16 mask words (0: none — the table was
-    // full or the leaf is out of its reach, voxels go straight to the global store)
+    // ... its leaf in the CTA-local table: shared-window address of the leaf's 16 mask words (0: none — the table was full
+    // or the leaf is out of its reach, voxels go straight to the global store)
     uint32_t l_mask = 0;
     const float vs_f = batch.vs_f, c_lo = batch.c_lo, c_hi = batch.c_hi;   // (float)vs and the two ends of 1/vs, see launch_mark
+    const uint32_t my_point = smem_u32(s_dyn) + threadIdx.x * 16u;       // this thread's first point of stage 0
 
     // ---- flush: resolve the table's leaves in the global hash, push masks and times, empty the table ----------------------
     auto flush = [&](const bool final) {
-      named_bar_sync(1, kMarkConsumers);   // every consumer warp is done with the chunks before the flush point
+      named_bar_sync(1, kMarkConsumers);   // every consumer warp is done with the units before the flush point
       if (final) TRACE(0, 3);
       sync_with_predecessor();
       // launch_dependents only AFTER our own wait: the next cycle's sweep (and the Mark behind it) cannot become resident
@@ -340,114 +353,123 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
     bool first = true;
     for (;; first = false) {
       mbar_wait(&s_full[stage], phase);
-      const uint32_t kind = s_kind[stage];
-      if (kind == kStageEnd) break;
-      if (kind == kStageFlush) {
+      const uint32_t meta = s_meta[stage];
+      if (meta & kMetaEnd) break;
+      if (meta & kMetaFlush) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[stage]);
         flush(false);
         if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         continue;
       }
-      const int ri = (int)s_ri[stage];
-      const unsigned in_chunk = s_cnt[stage];
-      const unsigned long long base = s_base[stage];
-      const DevReading & par = batch.r[ri];   // warp-uniform parameter-bank reads
-      const float range2_reject = par.range2_reject, range2_accept = par.range2_accept, near_accept = par.near_accept;
-      const float oxf = par.oxf, oyf = par.oyf, ozf = par.ozf;
-      const bool zwin = par.filter == 2;
-      const float zlo = zwin ? par.zmin_f : -CUDART_INF_F, zhi = zwin ? par.zmax_f : CUDART_INF_F;
+      const int ri = (int)((meta >> 24) & 15u);
+      const unsigned in_chunk = meta & 0xFFFFu;
+      const float4 pa = *reinterpret_cast<const float4 *>(&s_par[ri][0]), pb = *reinterpret_cast<const float4 *>(&s_par[ri][4]);
+      PointXYZ pts[2];
+      if constexpr (kVec4) {
+        const uint32_t addr = my_point + (uint32_t)stage * (uint32_t)(kMarkChunk * 16);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr + (uint32_t)k * (kMarkConsumers * 16u)));
+          pts[k].x = v.x; pts[k].y = v.y; pts[k].z = v.z;
+          pts[k].ok = (unsigned)k * kMarkConsumers + threadIdx.x < in_chunk;
+        }
+      } else {
+        const DevReading & par = batch.r[ri];
+        const unsigned long long base = s_base[stage];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const unsigned idx = (unsigned)k * kMarkConsumers + threadIdx.x;
+          pts[k] = load_point_generic(par, base + idx, idx < in_chunk);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[stage]);   // the stage may be refilled: this warp holds its points in registers
+      if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+      if (first) TRACE(0, 2);
+      if (meta & kMetaTf) {   // cloud still in the sensor frame: tf2::doTransform first (measurement_buffer.cpp:141-146)
+        const DevReading & par = batch.r[ri];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) transform_point(par.tf, pts[k].x, pts[k].y, pts[k].z);
+      }
       if (ri != l_ri) { l_ri = ri; l_ix = 1 << 30; }   // table entries are per reading
-      const float4 * const sp = s_stage + (size_t)stage * kMarkChunk;
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        PointXYZ pts[2];
+      const float range2_reject = pa.x, range2_accept = pa.y, near_accept = pa.z, oxf = pa.w, oyf = pb.x, ozf = pb.y, zlo = pb.z, zhi = pb.w;
+      // ---- single-precision screen of the range and z tests, both points of the pair interleaved -----------------------------
+      float d2f[2];
+      bool cand[2], nonfin[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float fx = pts[k].x, fy = pts[k].y, fz = pts[k].z;
+        // a float evaluation of the squared distance whose error is far below the margins of the thresholds: above
+        // range2_reject the exact test certainly rejects, inside [near_accept, range2_accept] it certainly accepts.  A NaN or
+        // infinite coordinate makes d2f NaN or +inf.
+        const float ax = __fsub_rn(fx, oxf), ay = __fsub_rn(fy, oyf), az = __fsub_rn(fz, ozf);
+        d2f[k] = fmaf(az, az, fmaf(ay, ay, __fmul_rn(ax, ax)));
+        // PassThrough z window (reference measurement_buffer.cpp:165-175) on exactly equivalent float thresholds
+        const bool zok = !((fz < zlo) | (fz > zhi));
+        nonfin[k] = pts[k].ok & !(d2f[k] < CUDART_INF_F);
+        cand[k] = pts[k].ok & zok & !(d2f[k] > range2_reject);
+      }
+      // whole warps of rejected points (floor, ceiling, beyond the obstacle range) stop here
+      if (!__any_sync(kFull, cand[0] | cand[1] | nonfin[0] | nonfin[1])) continue;
+      // ---- single-precision quantisation ---------------------------------------------------------------------------------------
+      int ix[2], iy[2], iz[2];
+      bool take[2], slow[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float fx = pts[k].x, fy = pts[k].y, fz = pts[k].z;
+        const bool inwin = (d2f[k] <= range2_accept) & (d2f[k] >= near_accept);
+        // .cpp:293-303 in float: shift negatives by one voxel (z tests y's sign — sic), multiply by 1/vs, truncate toward zero
+        const float X = fx < 0 ? __fsub_rn(fx, vs_f) : fx;
+        const float Y = fy < 0 ? __fsub_rn(fy, vs_f) : fy;
+        const float Z = fy < 0 ? __fsub_rn(fz, vs_f) : fz;
+        uint32_t diff = 0;
+        ix[k] = quantise_axis_fast(X, c_lo, c_hi, diff);
+        iy[k] = quantise_axis_fast(Y, c_lo, c_hi, diff);
+        iz[k] = quantise_axis_fast(Z, c_lo, c_hi, diff);
+        const bool decided = inwin & (diff == 0);
+        take[k] = cand[k] & decided;
+        // everything the fast path cannot decide, and everything that is not finite (counted), takes the exact sequence
+        slow[k] = nonfin[k] | (cand[k] & !decided);
+      }
+      // ---- the exact double sequence for the points the fast path could not decide (rare; whole warps skip it) ------------------
+      if (__any_sync(kFull, slow[0] | slow[1])) {
+        const DevReading & par = batch.r[ri];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          const unsigned idx = (unsigned)(half * 2 + k) * kMarkConsumers + threadIdx.x;
-          if constexpr (kVec4) {
-            const float4 v = sp[idx];
-            pts[k].x = v.x; pts[k].y = v.y; pts[k].z = v.z;
-            pts[k].ok = idx < in_chunk;
-          } else {
-            pts[k] = load_point_generic(par, base + idx, idx < in_chunk);
-          }
-        }
-        if (half == 1) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[stage]);   // the stage may be refilled: this warp holds its last points in registers
-          if (first) TRACE(0, 2);
-        }
-        if (!__any_sync(kFull, pts[0].ok | pts[1].ok)) continue;   // (the tail of a CTA's last chunk)
-        if (par.has_tf) {   // cloud still in the sensor frame: tf2::doTransform first (measurement_buffer.cpp:141-146)
-#pragma unroll
-          for (int k = 0; k < 2; ++k) transform_point(par.tf, pts[k].x, pts[k].y, pts[k].z);
-        }
-        // ---- single-precision fast path, both points of the pair interleaved ------------------------------------------------
-        int ix[2], iy[2], iz[2];
-        bool take[2], slow[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const float fx = pts[k].x, fy = pts[k].y, fz = pts[k].z;
-          // the range test on a float evaluation of the squared distance whose error is far below the margins of the two
-          // thresholds: above range2_reject the exact test certainly rejects, inside [near_accept, range2_accept] it
-          // certainly accepts.  A NaN or infinite coordinate makes d2f NaN or +inf.
-          const float ax = __fsub_rn(fx, oxf), ay = __fsub_rn(fy, oyf), az = __fsub_rn(fz, ozf);
-          const float d2f = fmaf(az, az, fmaf(ay, ay, __fmul_rn(ax, ax)));
-          // PassThrough z window (reference measurement_buffer.cpp:165-175) on exactly equivalent float thresholds
-          const bool zok = !((fz < zlo) | (fz > zhi));
-          const bool inwin = (d2f <= range2_accept) & (d2f >= near_accept);
-          // .cpp:293-303 in float: shift negatives by one voxel (z tests y's sign — sic), multiply by 1/vs, truncate toward zero
-          const float X = fx < 0 ? __fsub_rn(fx, vs_f) : fx;
-          const float Y = fy < 0 ? __fsub_rn(fy, vs_f) : fy;
-          const float Z = fy < 0 ? __fsub_rn(fz, vs_f) : fz;
-          uint32_t diff = 0;
-          ix[k] = quantise_axis_fast(X, c_lo, c_hi, diff);
-          iy[k] = quantise_axis_fast(Y, c_lo, c_hi, diff);
-          iz[k] = quantise_axis_fast(Z, c_lo, c_hi, diff);
-          const bool decided = inwin & (diff == 0);
-          take[k] = pts[k].ok & zok & decided;
-          // everything the fast path cannot decide, and everything that is not finite (counted), takes the exact sequence
-          slow[k] = pts[k].ok & (!(d2f < CUDART_INF_F) | (zok & !(d2f > range2_reject) & !decided));
-        }
-        // ---- the exact double sequence for the points the fast path could not decide (rare; whole warps skip it) ----------------
-        if (__any_sync(kFull, slow[0] | slow[1])) {
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            if (slow[k]) {
-              const int4 q = quantise_exact(pts[k].x, pts[k].y, pts[k].z, par.ox, par.oy, par.oz, par.mark_range_2, g.vs, g.inv_vs, zlo, zhi);
-              ix[k] = q.x; iy[k] = q.y; iz[k] = q.z;
-              take[k] = q.w == 1;
-              drop_range += q.w == 2 ? 1u : 0u;
-              drop_nonfinite += q.w == 3 ? 1u : 0u;
-            }
-          }
-        }
-        // ---- CTA-local dedupe ----------------------------------------------------------------------------------------------------
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          if (!take[k]) continue;
-          const int x = ix[k], y = iy[k], z = iz[k];
-          if (g.shard_count > 1 && !shard_owns(x >> 3, g.shard_index, g.shard_count, g.shard_width)) continue;
-          if ((uint32_t)((x ^ l_ix) | (y ^ l_iy) | (z ^ l_iz)) >= 8u) {   // another leaf than the thread's last one
-            const int e = table_lookup(ri, x >> 3, y >> 3, z >> 3);
-            l_mask = e >= 0 ? smem_u32(&s_mask[e][0]) : 0u;
-            l_ix = x; l_iy = y; l_iz = z;   // (a failed lookup is remembered too: the leaf's next voxels go the same way)
-          }
-          // local index l = ((x & 7) * 8 + (y & 7)) * 8 + (z & 7): mask word l >> 5, bit l & 31 (the shift takes its count modulo 32)
-          const uint32_t bit = 1u << ((((uint32_t)y << 3) | ((uint32_t)z & 7u)) & 31u);
-          const uint32_t word_off = (((uint32_t)x << 3) & 0x38u) | ((uint32_t)y & 4u);   // (l >> 5) * 4
-          if (l_mask) {
-            uint32_t cur;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(l_mask + word_off));
-            if (!(cur & bit)) asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(l_mask + word_off), "r"(bit) : "memory");
-          } else {   // table full or leaf out of the table's reach: straight to the global store
-            sync_with_predecessor();
-            mark_voxel_direct(g, x >> 3, y >> 3, z >> 3, (unsigned)(((x & 7) * 8 + (y & 7)) * 8 + (z & 7)), par.now, use_max, batch.min_now);
+          if (slow[k]) {
+            const int4 q = quantise_exact(pts[k].x, pts[k].y, pts[k].z, par.ox, par.oy, par.oz, par.mark_range_2, g.vs, g.inv_vs, zlo, zhi);
+            ix[k] = q.x; iy[k] = q.y; iz[k] = q.z;
+            take[k] = q.w == 1;
+            drop_range += q.w == 2 ? 1u : 0u;
+            drop_nonfinite += q.w == 3 ? 1u : 0u;
           }
         }
       }
-      if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+      // ---- CTA-local dedupe ------------------------------------------------------------------------------------------------------
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (!take[k]) continue;
+        const int x = ix[k], y = iy[k], z = iz[k];
+        if (g.shard_count > 1 && !shard_owns(x >> 3, g.shard_index, g.shard_count, g.shard_width)) continue;
+        if ((uint32_t)((x ^ l_ix) | (y ^ l_iy) | (z ^ l_iz)) >= 8u) {   // another leaf than the thread's last one
+          const int e = table_lookup(ri, x >> 3, y >> 3, z >> 3);
+          l_mask = e >= 0 ? smem_u32(&s_mask[e][0]) : 0u;
+          l_ix = x; l_iy = y; l_iz = z;   // (a failed lookup is remembered too: the leaf's next voxels go the same way)
+        }
+        // local index l = ((x & 7) * 8 + (y & 7)) * 8 + (z & 7): mask word l >> 5, bit l & 31 (the shift takes its count modulo 32)
+        const uint32_t bit = 1u << ((((uint32_t)y << 3) | ((uint32_t)z & 7u)) & 31u);
+        const uint32_t word_off = (((uint32_t)x << 3) & 0x38u) | ((uint32_t)y & 4u);   // (l >> 5) * 4
+        if (l_mask) {
+          uint32_t cur;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(l_mask + word_off));
+          if (!(cur & bit)) asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(l_mask + word_off), "r"(bit) : "memory");
+        } else {   // table full or leaf out of the table's reach: straight to the global store
+          sync_with_predecessor();
+          mark_voxel_direct(g, x >> 3, y >> 3, z >> 3, (unsigned)(((x & 7) * 8 + (y & 7)) * 8 + (z & 7)), s_rnow[ri], use_max, batch.min_now);
+        }
+      }
     }
     flush(true);
     TRACE(0, 5);
@@ -553,11 +575,10 @@ int mark_stages(bool vec4) { static const int v = env_int("STVL_MARK_STAGES", kM
 size_t mark_smem_bytes(bool vec4) { return (vec4 ? (size_t)mark_stages(true) * kMarkChunk * 16 : 0) + (size_t)kMarkTable * (8 + 64); }
 }  // namespace
 
-// one CTA per SM; small batches get fewer CTAs (at least 8 blocks = 1024 points each)
+// one CTA per SM; small batches get one CTA per unit
 uint32_t mark_grid_for(const MarkBatch & batch, int sm_count)
 {
-  const uint32_t want = (batch.total_blocks + 7) / 8;
-  return std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)sm_count, want));
+  return std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)sm_count, batch.total_blocks));
 }
 // column tiles the fused variant's costmap pass can take without becoming the critical path of the launch
 uint32_t mark_costmap_tiles_capacity(const MarkBatch & batch, int sm_count)
@@ -590,7 +611,8 @@ static cudaError_t launch_mark_variant(const GridView & g, const MarkBatch & bat
 
 // pdl: the caller guarantees that the kernel's inputs (clouds) were complete before the PREDECESSOR of this launch in the
 // stream started, and that the predecessor is this library's sweep kernel.  cm / costmap != NULL: fused costmap pass
-// (cm_bits: into a cell bitmap).
+// (cm_bits: into a cell bitmap).  batch.cursor_sel must alternate between consecutive launches on a handle (two launches
+// may overlap under programmatic dependent launch; each launch leaves its cursor at zero).
 cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s, bool pdl,
                         const CostmapDev * cm, uint8_t * costmap, bool cm_bits)
 {
@@ -610,7 +632,7 @@ cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_coun
 }
 uint32_t mark_blocks_for(unsigned long long n_points)
 {
-  return (uint32_t)((n_points + kMarkBlock - 1) / kMarkBlock);
+  return (uint32_t)((n_points + kMarkChunk - 1) / kMarkChunk);
 }
 cudaError_t launch_load_voxels(const GridView & g, const int32_t * x, const int32_t * y, const int32_t * z, const double * t,
                                unsigned long long n, cudaStream_t s)
