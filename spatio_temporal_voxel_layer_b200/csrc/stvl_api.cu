@@ -121,7 +121,6 @@ struct stvl_grid {
   bool swept = false;
   uint32_t * tile_buf[2] = {nullptr, nullptr};   // double-buffered column tiles (see GridView::tile_count)
   int sweep_parity = 0;
-  uint32_t mark_cursor_sel = 0;     // unit cursor of the next Mark launch (they alternate)
   uint64_t launches = 0;
   bool record_mark_event = false;   // set by stvl_mark around its launches (ev_mark_done guards the host-cloud staging buffer)
   size_t device_bytes = 0;
@@ -469,9 +468,7 @@ int launch_batches(stvl_grid * g, const std::vector<MarkBatch> & batches, CycleF
   for (size_t i = 0; i < batches.size(); ++i) {
     // the costmap pass rides on dedicated warps of every Mark CTA
     const bool carry = fz && fz->costmap && !fz->costmap_done && i + 1 == batches.size();
-    MarkBatch b = batches[i];
-    b.cursor_sel = g->mark_cursor_sel;
-    g->mark_cursor_sel ^= 1u;
+    const MarkBatch & b = batches[i];
     HOST_T(tm0);
     CU(launch_mark(g->v, b, g->sm_count, g->stream, pdl, carry ? &fz->cm : nullptr, carry ? fz->costmap : nullptr, carry && fz->bits));
     HOST_T(tm1);

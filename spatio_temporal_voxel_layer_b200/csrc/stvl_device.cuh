@@ -53,10 +53,7 @@ struct Counters {
   uint32_t tile_n;
   uint32_t tile_overflow;
   uint32_t cm_ticket;      // last-CTA-done ticket of the costmap pass (its last CTA publishes cm_acc -> cm)
-  // Mark's unit hand-out: next unclaimed unit beyond the first gridDim.x ones, and how many CTAs are done claiming (the
-  // last one puts both back to zero).  Two sets: consecutive Mark launches may overlap under programmatic dependent launch.
-  uint32_t mark_cursor[2];
-  uint32_t mark_ticket[2];
+  uint32_t pad1[4];
   // dropped input points
   unsigned long long dropped_range, dropped_nonfinite;
   SweepCtr sw[2];
@@ -164,8 +161,12 @@ struct MarkBatch {
   int32_t ref_bx;           // reference leaf x of the batch (first reading's origin): block-local table keys store bx - ref_bx
   float vs_f;               // (float)vs
   float c_lo, c_hi;         // (float)(1/vs) scaled down / up by a few ulps: the two ends of the fast quantisation (set at launch)
-  uint32_t cursor_sel;      // which Counters::mark_cursor / mark_ticket this launch uses (set at launch, alternating)
+  uint32_t pad;
   double min_now;           // smallest clock sample in the batch: initial leaf_tmin of leaves created by it
+  // the batch's point index space (set at launch): reading k holds points [first_point[k], first_point[k + 1]); the CTAs take
+  // slices of slice_len points of it round-robin
+  unsigned long long first_point[kMaxBatchReadings + 1];
+  unsigned long long slice_len;           // smallest clock sample in the batch: initial leaf_tmin of leaves created by it
 };
 
 // -------- helpers -------------------------------------------------------------------

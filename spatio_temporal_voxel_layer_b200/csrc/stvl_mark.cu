@@ -1,8 +1,9 @@
 // stvl_mark.cu — Mark / operator() (reference spatio_temporal_voxel_grid.cpp:254-309) as a warp-specialised sm_100a kernel.
 //
-// One persistent CTA of 32 warps per SM.  The batch's points are cut into units of up to 1984 points (31 KB, never across two
-// readings); a CTA takes unit blockIdx.x first and claims further ones from a device-side cursor, one claim ahead of the copy
-// it is issuing, so CTAs whose points are cheap (rejected by the range test) take more of them.  Inside a CTA:
+// One persistent CTA of 32 warps per SM.  The batch's points (all readings laid end to end) are cut into equal slices, four
+// per CTA, dealt round-robin: every CTA gets the same number of points from four distant places of the batch (floor rows
+// that the range screen rejects are cheap, wall rows are not), with no work cursor and no atomics on the hand-out.  A slice
+// is streamed as units of up to 1984 points (31 KB, never across two readings).  Inside a CTA:
 //   producer warp   one elected lane streams the units global -> shared memory with the bulk-copy engine (cp.async.bulk,
 //                   completion on an mbarrier as transaction bytes; SASS UBLKCP / SYNCS), six units in flight per SM; the
 //                   first copies are issued before the CTA has finished setting up its tables
@@ -27,11 +28,13 @@ constexpr int kMarkConsumerWarps = 31;
 constexpr int kMarkConsumers = kMarkConsumerWarps * 32;
 constexpr int kMarkThreads = kMarkConsumers + 32;
 constexpr int kMarkPPT = 2;                      // points per consumer thread per unit
-constexpr int kMarkChunk = kMarkConsumers * kMarkPPT;   // 1984 points = 31 KB of packed float4 points: the unit of hand-out
+constexpr int kMarkChunk = kMarkConsumers * kMarkPPT;   // 1984 points = 31 KB of packed float4 points: one stage of the ring
+constexpr int kMarkSlices = 4;                   // slices per CTA
 constexpr int kMarkTable = 512;                  // CTA-local (reading, leaf) table entries
 constexpr int kMarkProbes = 16;
 constexpr int kMarkStagesMax = 6;
-// per-stage word the producer posts: what the stage holds | reading | sensor-frame cloud | points
+// per-stage word the producer posts: what the stage holds | sensor-frame cloud | reading | threads with two points | points.
+// Thread t < half holds points t and half + t of the unit (half = a multiple of 32: warps beyond it sit the unit out).
 constexpr uint32_t kMetaEnd = 1u << 31, kMetaFlush = 1u << 30, kMetaTf = 1u << 29;
 static_assert(kMarkThreads == 1024, "one CTA of 32 warps");
 static_assert(kMarkPPT == 2, "the consumer loop is written for one pair of points per thread");
@@ -123,14 +126,15 @@ __device__ __noinline__ int4 quantise_exact(float fx, float fy, float fz, double
 // ends, so the reference truncates to that same integer; otherwise `diff` gets a non-zero bit and the point takes the
 // exact path.  Sums of 2^24 and more (indices beyond 2^23) always differ: the ends are more than two ulps apart there.
 // (Infinite products compare equal — such points never get here: their squared distance is not finite either.)
-__device__ __forceinline__ int quantise_axis_fast(float S, float c_lo, float c_hi, uint32_t & diff)
+// `neg`: S < 0 (for x and y that is the sign test the shift already made: the shift never changes the sign).
+__device__ __forceinline__ int quantise_axis_fast(float S, bool neg, float c_lo, float c_hi, uint32_t & diff)
 {
   const float a = fabsf(S);
   const uint32_t t_lo = __float_as_uint(__fmaf_rz(a, c_lo, 8388608.0f));
   const uint32_t t_hi = __float_as_uint(__fmaf_rz(a, c_hi, 8388608.0f));
   diff |= t_lo ^ t_hi;
   const int fl = (int)(t_lo & 0x7FFFFFu);   // floor(|S| / vs)
-  return S < 0.0f ? -fl : fl;              // the reference truncates toward zero
+  return neg ? -fl : fl;                   // the reference truncates toward zero
 }
 
 // kVec4: every reading of the batch is a packed x,y,z,pad float4 cloud (the RGBD / depth-image layout), streamed through
@@ -151,6 +155,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
   unsigned long long * const s_key = reinterpret_cast<unsigned long long *>(s_dyn + stage_bytes);
   uint32_t (* const s_mask)[16] = reinterpret_cast<uint32_t (*)[16]>(s_dyn + stage_bytes + (size_t)kMarkTable * 8);
   __shared__ uint32_t s_slot[kMarkTable];
+  __shared__ uint16_t s_list[kMarkTable];   // claimed table entries, in claim order (s_fill of them)
   __shared__ double s_rnow[kMaxBatchReadings];
   // per reading, the single-precision screen of the range / z tests: {range2_reject, range2_accept, near_accept, ox} {oy, oz, zlo, zhi}
   __shared__ __align__(16) float s_par[kMaxBatchReadings][8];
@@ -170,45 +175,49 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
   // producer warp
   // =====================================================================================================================
   if (warp == kMarkConsumerWarps) {
-    const uint32_t total = batch.total_blocks;
-    uint32_t * const cursor = &g.ctr->mark_cursor[batch.cursor_sel & 1u];
-    uint32_t unit = blockIdx.x;     // the first unit is fixed, further ones are claimed: unit = gridDim.x + (cursor++)
-    int ri = 0;
+    // slices of `slice_len` points of the batch's point index space; this CTA takes slices blockIdx.x, blockIdx.x + gridDim.x, ...
+    const unsigned long long total = batch.first_point[batch.n_readings];
+    const unsigned long long slice_len = batch.slice_len;
+    unsigned long long slice0 = (unsigned long long)blockIdx.x * slice_len;   // first point of the current slice
+    unsigned long long pos = slice0;                                          // next point to hand out
     int stage = 0;            // ring position of the next hand-out ...
     uint32_t phase = 0;       // ... and how often the ring has wrapped (parity)
     unsigned flush_requests = 0;
     unsigned long long policy = 0;
     bool done = false;
     auto advance = [&]() { if (++stage == n_stages) { stage = 0; phase ^= 1u; } };
-    // hand out the current unit and claim the next one (or post the end marker); false once the end marker has been posted
+    // hand out the next unit (or the end marker); false once the end marker has been posted
     auto produce = [&]() -> bool {
       for (;;) {
-        if (unit >= total) {
+        unsigned long long slice_end = slice0 + slice_len < total ? slice0 + slice_len : total;
+        if (pos >= slice_end) {   // next slice of this CTA
+          slice0 += (unsigned long long)gridDim.x * slice_len;
+          pos = slice0;
+          if (slice0 < total) continue;
           mbar_wait(&s_empty[stage], phase ^ 1u);
           s_meta[stage] = kMetaEnd;
           mbar_arrive(&s_full[stage]);
-          // every CTA's last claim is its first out-of-range one: when the last producer gets here, nobody needs the cursor any more
-          __threadfence();
-          if (atomicAdd(&g.ctr->mark_ticket[batch.cursor_sel & 1u], 1u) == gridDim.x - 1) {
-            *cursor = 0;
-            g.ctr->mark_ticket[batch.cursor_sel & 1u] = 0;
-            __threadfence();
-          }
           return false;
         }
-        const uint32_t cur = unit;
-        unit = gridDim.x + atomicAdd(cursor, 1u);   // in flight while this unit's copy is set up: needed one hand-out later
-        ri = 0;
+        int ri = 0;
 #pragma unroll 1
-        for (int k = 1; k < (int)batch.n_readings; ++k) if (cur >= batch.first_block[k]) ri = k;
+        for (int k = 1; k < (int)batch.n_readings; ++k) if (pos >= batch.first_point[k]) ri = k;
         const DevReading & rd = batch.r[ri];
+        const unsigned long long base = pos - batch.first_point[ri];
+        // what is left of the slice inside this reading, in equal units of at most kMarkChunk points (multiples of 64, so
+        // that a unit splits into two halves of whole warps)
+        const unsigned long long piece_end = slice_end < batch.first_point[ri + 1] ? slice_end : batch.first_point[ri + 1];
+        const unsigned long long piece = piece_end - pos;
+        const unsigned long long n_units = (piece + kMarkChunk - 1) / kMarkChunk;
+        unsigned long long want = ((piece + n_units - 1) / n_units + 63) & ~63ull;
+        if (want > piece) want = piece;
+        pos += want;
         // points of the reading: the host's count, or (output of the VOXEL pre-filter) a device counter below that bound
         unsigned long long n_pts = rd.n_points;
         if (rd.n_points_dev) { const unsigned long long nd = ld_volatile_u64(rd.n_points_dev); if (nd < n_pts) n_pts = nd; }
-        const unsigned long long base = (unsigned long long)(cur - batch.first_block[ri]) * kMarkChunk;
         if (base >= n_pts) continue;   // beyond the actual count: nothing to hand out
-        const unsigned long long left = n_pts - base;
-        const uint32_t cnt = (uint32_t)(left < (unsigned long long)kMarkChunk ? left : (unsigned long long)kMarkChunk);
+        const uint32_t cnt = (uint32_t)(n_pts - base < want ? n_pts - base : want);
+        const uint32_t half = (((cnt + 1) >> 1) + 31u) & ~31u;
         mbar_wait(&s_empty[stage], phase ^ 1u);
         // a filling table is flushed early (large or scattered clouds): the marker travels in-band, so every consumer
         // sees it between the same two units
@@ -220,7 +229,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
           advance();
           mbar_wait(&s_empty[stage], phase ^ 1u);
         }
-        s_meta[stage] = ((uint32_t)ri << 24) | (rd.has_tf ? kMetaTf : 0u) | cnt;
+        s_meta[stage] = (rd.has_tf ? kMetaTf : 0u) | ((uint32_t)ri << 24) | ((half >> 5) << 16) | cnt;
         s_base[stage] = base;
         if constexpr (kVec4) {
           mbar_arrive_expect_tx(&s_full[stage], cnt * 16u);
@@ -272,6 +281,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
     uint32_t l_mask = 0;
     const float vs_f = batch.vs_f, c_lo = batch.c_lo, c_hi = batch.c_hi;   // (float)vs and the two ends of 1/vs, see launch_mark
     const uint32_t my_point = smem_u32(s_dyn) + threadIdx.x * 16u;       // this thread's first point of stage 0
+    const bool sharded = g.shard_count > 1;
 
     // ---- flush: resolve the table's leaves in the global hash, push masks and times, empty the table ----------------------
     auto flush = [&](const bool final) {
@@ -281,31 +291,29 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
       // launch_dependents only AFTER our own wait: the next cycle's sweep (and the Mark behind it) cannot become resident
       // before the grid preceding this one has completed, which bounds the programmatic-launch chain to two kernels in flight
       if (final) pdl_launch_dependents();
-      for (int e = threadIdx.x; e < kMarkTable; e += kMarkConsumers) {   // one thread per distinct (reading, leaf)
+      const int n_claimed = (int)*reinterpret_cast<volatile unsigned int *>(&s_fill);
+      for (int c = threadIdx.x; c < n_claimed; c += kMarkConsumers) {   // one thread per distinct (reading, leaf)
+        const int e = s_list[c];
         const unsigned long long tkey = s_key[e];
-        uint32_t slot = kOverflowSlot;
-        if (tkey != kEmptyKey) {
-          const int bx = (int)((tkey >> 42) & 0x1FFFF) - kMarkRelBias + batch.ref_bx;
-          const int by = (int)((tkey >> 21) & 0x1FFFFF) - kLeafBias, bz = (int)(tkey & 0x1FFFFF) - kLeafBias;
-          slot = leaf_find_or_insert(g, pack_leaf_key(bx, by, bz), bx, by, batch.min_now);
-        }
-        s_slot[e] = slot;
+        const int bx = (int)((tkey >> 42) & 0x1FFFF) - kMarkRelBias + batch.ref_bx;
+        const int by = (int)((tkey >> 21) & 0x1FFFFF) - kLeafBias, bz = (int)(tkey & 0x1FFFFF) - kLeafBias;
+        s_slot[e] = leaf_find_or_insert(g, pack_leaf_key(bx, by, bz), bx, by, batch.min_now);
       }
       l_ix = 1 << 30; l_mask = 0;
       named_bar_sync(1, kMarkConsumers);
       if (final) TRACE(0, 4);
       // per touched mask word one 32-bit OR, per distinct voxel one 64-bit max (batched launch, monotone clocks) or a
       // plain store (per-reading launches: exact overwrite semantics of MarkGridPoint, .cpp:421-430)
-      for (int i = threadIdx.x; i < kMarkTable * 16; i += kMarkConsumers) {
-        uint32_t m = (&s_mask[0][0])[i];
+      for (int i = threadIdx.x; i < n_claimed * 16; i += kMarkConsumers) {
+        const int e = s_list[i >> 4];
+        const unsigned w = i & 15;
+        uint32_t m = s_mask[e][w];
         if (!m) continue;
-        (&s_mask[0][0])[i] = 0;
-        const int e = i >> 4;
+        s_mask[e][w] = 0;
         const uint32_t slot = s_slot[e];
         if (slot == kOverflowSlot) continue;
         const double now = s_rnow[(int)(s_key[e] >> 59)];
         const unsigned long long now_bits = (unsigned long long)__double_as_longlong(now);
-        const unsigned w = i & 15;
         red_or_u32(&g.leaf_mask[(size_t)slot * 16 + w], m);
         double * tp = g.leaf_time + (size_t)slot * kLeafVoxels + w * 32;
         if (!use_max && g.leaf_tmin[slot] > now) g.leaf_tmin[slot] = -CUDART_INF;   // clocks are not monotone here
@@ -317,7 +325,8 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
       }
       if (!final) {
         named_bar_sync(1, kMarkConsumers);   // the keys were still needed for the per-reading clock above
-        for (int e = threadIdx.x; e < kMarkTable; e += kMarkConsumers) s_key[e] = kEmptyKey;
+        for (int c = threadIdx.x; c < n_claimed; c += kMarkConsumers) s_key[s_list[c]] = kEmptyKey;
+        named_bar_sync(1, kMarkConsumers);   // (the list is read above, s_fill re-armed below)
         if (threadIdx.x == 0) { s_fill = 0; atomicAdd(&s_flushes, 1u); }
         named_bar_sync(1, kMarkConsumers);
       }
@@ -336,7 +345,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
         if (cur == kEmptyKey) {
           cur = atomicCAS(&s_key[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
           if (cur == kEmptyKey) {
-            atomicAdd(&s_fill, 1u);
+            s_list[atomicAdd(&s_fill, 1u)] = (uint16_t)h;
             // the flush will probe the global hash for this leaf: pull the line towards L2 now (a hint, no data is read)
             prefetch_l2(&g.hash[(uint32_t)mix64(pack_leaf_key(bx, by, bz)) & g.hash_mask]);
             cur = key;
@@ -364,6 +373,12 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
       }
       const int ri = (int)((meta >> 24) & 15u);
       const unsigned in_chunk = meta & 0xFFFFu;
+      const unsigned half = ((meta >> 16) & 0xFFu) << 5;
+      if (warp * 32u >= half) {   // this warp has no points in the unit
+        if (lane == 0) mbar_arrive(&s_empty[stage]);
+        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+        continue;
+      }
       const float4 pa = *reinterpret_cast<const float4 *>(&s_par[ri][0]), pb = *reinterpret_cast<const float4 *>(&s_par[ri][4]);
       PointXYZ pts[2];
       if constexpr (kVec4) {
@@ -371,16 +386,16 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           float4 v;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr + (uint32_t)k * (kMarkConsumers * 16u)));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr + (uint32_t)k * (half * 16u)));
           pts[k].x = v.x; pts[k].y = v.y; pts[k].z = v.z;
-          pts[k].ok = (unsigned)k * kMarkConsumers + threadIdx.x < in_chunk;
+          pts[k].ok = (unsigned)k * half + threadIdx.x < in_chunk;
         }
       } else {
         const DevReading & par = batch.r[ri];
         const unsigned long long base = s_base[stage];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          const unsigned idx = (unsigned)k * kMarkConsumers + threadIdx.x;
+          const unsigned idx = (unsigned)k * half + threadIdx.x;
           pts[k] = load_point_generic(par, base + idx, idx < in_chunk);
         }
       }
@@ -421,13 +436,14 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
         const float fx = pts[k].x, fy = pts[k].y, fz = pts[k].z;
         const bool inwin = (d2f[k] <= range2_accept) & (d2f[k] >= near_accept);
         // .cpp:293-303 in float: shift negatives by one voxel (z tests y's sign — sic), multiply by 1/vs, truncate toward zero
-        const float X = fx < 0 ? __fsub_rn(fx, vs_f) : fx;
-        const float Y = fy < 0 ? __fsub_rn(fy, vs_f) : fy;
-        const float Z = fy < 0 ? __fsub_rn(fz, vs_f) : fz;
+        const bool xneg = fx < 0, yneg = fy < 0;
+        const float X = xneg ? __fsub_rn(fx, vs_f) : fx;
+        const float Y = yneg ? __fsub_rn(fy, vs_f) : fy;
+        const float Z = yneg ? __fsub_rn(fz, vs_f) : fz;
         uint32_t diff = 0;
-        ix[k] = quantise_axis_fast(X, c_lo, c_hi, diff);
-        iy[k] = quantise_axis_fast(Y, c_lo, c_hi, diff);
-        iz[k] = quantise_axis_fast(Z, c_lo, c_hi, diff);
+        ix[k] = quantise_axis_fast(X, xneg, c_lo, c_hi, diff);
+        iy[k] = quantise_axis_fast(Y, yneg, c_lo, c_hi, diff);
+        iz[k] = quantise_axis_fast(Z, Z < 0.0f, c_lo, c_hi, diff);
         const bool decided = inwin & (diff == 0);
         take[k] = cand[k] & decided;
         // everything the fast path cannot decide, and everything that is not finite (counted), takes the exact sequence
@@ -447,12 +463,15 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
           }
         }
       }
+      if (sharded) {   // spatial shard: foreign leaves are dropped
+#pragma unroll
+        for (int k = 0; k < 2; ++k) take[k] = take[k] && shard_owns(ix[k] >> 3, g.shard_index, g.shard_count, g.shard_width);
+      }
       // ---- CTA-local dedupe ------------------------------------------------------------------------------------------------------
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         if (!take[k]) continue;
         const int x = ix[k], y = iy[k], z = iz[k];
-        if (g.shard_count > 1 && !shard_owns(x >> 3, g.shard_index, g.shard_count, g.shard_width)) continue;
         if ((uint32_t)((x ^ l_ix) | (y ^ l_iy) | (z ^ l_iz)) >= 8u) {   // another leaf than the thread's last one
           const int e = table_lookup(ri, x >> 3, y >> 3, z >> 3);
           l_mask = e >= 0 ? smem_u32(&s_mask[e][0]) : 0u;
@@ -580,6 +599,16 @@ uint32_t mark_grid_for(const MarkBatch & batch, int sm_count)
 {
   return std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)sm_count, batch.total_blocks));
 }
+// the batch's point index space (readings laid end to end) and the slice length: kMarkSlices slices per CTA, a multiple of 64
+static void mark_set_slices(MarkBatch & b, uint32_t grid)
+{
+  unsigned long long total = 0;
+  for (uint32_t k = 0; k < b.n_readings; ++k) { b.first_point[k] = total; total += b.r[k].n_points; }
+  for (uint32_t k = b.n_readings; k <= (uint32_t)kMaxBatchReadings; ++k) b.first_point[k] = total;
+  const unsigned long long n_slices = (unsigned long long)grid * kMarkSlices;
+  unsigned long long len = ((total + n_slices - 1) / n_slices + 63ull) & ~63ull;
+  b.slice_len = std::max<unsigned long long>(len, 1024ull);
+}
 // column tiles the fused variant's costmap pass can take without becoming the critical path of the launch
 uint32_t mark_costmap_tiles_capacity(const MarkBatch & batch, int sm_count)
 {
@@ -605,14 +634,14 @@ static cudaError_t launch_mark_variant(const GridView & g, const MarkBatch & bat
   b.vs_f = (float)g.vs;                                              // exact: vs is a float widened to double
   b.c_lo = (float)g.inv_vs * 0.999999701976776123046875f;            // (float)(1/vs) * (1 - 5 * 2^-24), one rounding
   b.c_hi = (float)g.inv_vs * 1.00000035762786865234375f;             // (float)(1/vs) * (1 + 3 * 2^-23), one rounding
+  mark_set_slices(b, mark_grid_for(batch, sm_count));
   return launch_ex(mark_kernel<kVec4, kCostmap, kCmBits>, mark_grid_for(batch, sm_count), (unsigned)kMarkThreads, smem, s, pdl, g, b, cm, costmap,
                    mark_stages(kVec4));
 }
 
 // pdl: the caller guarantees that the kernel's inputs (clouds) were complete before the PREDECESSOR of this launch in the
 // stream started, and that the predecessor is this library's sweep kernel.  cm / costmap != NULL: fused costmap pass
-// (cm_bits: into a cell bitmap).  batch.cursor_sel must alternate between consecutive launches on a handle (two launches
-// may overlap under programmatic dependent launch; each launch leaves its cursor at zero).
+// (cm_bits: into a cell bitmap).
 cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s, bool pdl,
                         const CostmapDev * cm, uint8_t * costmap, bool cm_bits)
 {
