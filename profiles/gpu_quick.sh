@@ -7,9 +7,9 @@ OUT=gpurun_out
 mkdir -p $OUT
 echo "== quick session $TAG $(date -u +%H:%M:%S)"; nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv,noheader
 if [ -n "$KEXPR" ]; then
-  timeout 900 python -m pytest tests -m gpu -q --timeout 240 -p no:cacheprovider -k "$KEXPR" > $OUT/${TAG}_pytest.log 2>&1
+  timeout 600 python -m pytest tests -m gpu -q --timeout 150 --timeout-method thread -p no:cacheprovider -k "$KEXPR" > $OUT/${TAG}_pytest.log 2>&1
 else
-  timeout 900 python -m pytest tests -m gpu -q --timeout 240 -p no:cacheprovider > $OUT/${TAG}_pytest.log 2>&1
+  timeout 600 python -m pytest tests -m gpu -q --timeout 150 --timeout-method thread -p no:cacheprovider > $OUT/${TAG}_pytest.log 2>&1
 fi
 echo "pytest rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed" $OUT/${TAG}_pytest.log | cut -c1-300 | tail -30
 grep -E "^E  " $OUT/${TAG}_pytest.log | cut -c1-300 | head -30

@@ -375,6 +375,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
       const unsigned in_chunk = meta & 0xFFFFu;
       const unsigned half = ((meta >> 16) & 0xFFu) << 5;
       if (warp * 32u >= half) {   // this warp has no points in the unit
+        __syncwarp();   // every lane has seen the stage's phase: after the arrival below the barrier may complete again
         if (lane == 0) mbar_arrive(&s_empty[stage]);
         if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         continue;
@@ -590,7 +591,7 @@ int env_int(const char * name, int dflt, int lo, int hi)
 }
 // bulk-copy stages per CTA (STVL_MARK_STAGES is a tuning knob for profiling; the default is what the measurements in
 // DESIGN.md were taken with)
-int mark_stages(bool vec4) { static const int v = env_int("STVL_MARK_STAGES", kMarkStagesMax, 2, kMarkStagesMax); return vec4 ? v : 2; }
+int mark_stages(bool vec4) { static const int v = env_int("STVL_MARK_STAGES", 3, 2, kMarkStagesMax); return vec4 ? v : 2; }
 size_t mark_smem_bytes(bool vec4) { return (vec4 ? (size_t)mark_stages(true) * kMarkChunk * 16 : 0) + (size_t)kMarkTable * (8 + 64); }
 }  // namespace
 
