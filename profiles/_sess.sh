@@ -1,5 +1,3 @@
-OUT=gpurun_out
-timeout 200 python profiles/ncu_target.py > $OUT/t_plain.log 2>&1; echo "plain rc=$?"; tail -2 $OUT/t_plain.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:mark_kernel -s 3 -c 1 -o $OUT/n1_mark python profiles/ncu_target.py > $OUT/n1_mark.log 2>&1; echo "ncu mark rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:sweep_kernel -s 3 -c 1 -o $OUT/n1_sweep python profiles/ncu_target.py > $OUT/n1_sweep.log 2>&1; echo "ncu sweep rc=$?"
-ls -la $OUT | tail -5
+bash profiles/gpu_quick.sh q5
+STVL_B200_LIB=spatio_temporal_voxel_layer_b200/libstvl_b200_trace.so timeout 300 python profiles/trace_phases.py --staged 2>&1 | grep -A30 "mark_kernel" | cut -c1-160
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:mark_kernel -s 3 -c 1 -o gpurun_out/n2_mark python profiles/ncu_target.py > gpurun_out/n2_mark.log 2>&1; echo "ncu mark rc=$?"

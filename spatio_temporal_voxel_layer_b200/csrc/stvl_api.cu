@@ -584,13 +584,15 @@ int build_batches(stvl_grid * g, const stvl_reading_t * readings, uint32_t n, co
     if (std::isnan(d.zmin)) d.zmin_f = -INFINITY;   // comparisons with NaN limits are false upstream: nothing is rejected
     if (std::isnan(d.zmax)) d.zmax_f = INFINITY;
     d.mark_range_2 = (float)(r.obstacle_range * r.obstacle_range);   // `float mark_range_2 = range * range`, .cpp:274
-    // single-precision screening threshold: points whose float distance^2 exceeds it are certainly out of range (float
-    // evaluation error << 1e-3 relative at map-scale coordinates); everything else takes the exact double test
+    // single-precision screen: a point whose float distance^2 exceeds range2_reject is certainly out of range, one inside
+    // [near_accept, range2_accept] certainly passes; everything else takes the exact double test
     d.oxf = (float)d.ox; d.oyf = (float)d.oy; d.ozf = (float)d.oz;
     {
       const float m = std::fmax(std::fmax(std::fabs(d.oxf), std::fabs(d.oyf)), std::fmax(std::fabs(d.ozf), 1.0f));
-      // margin >> the float evaluation error of the squared distance: ~2e-7 * d * (m + d) + 2e-7 * d^2 near d^2 = range^2
-      const float margin = d.mark_range_2 * 1e-3f + 1e-3f + 1e-5f * m * (std::sqrt(std::fmax(d.mark_range_2, 0.f)) + 1.0f);
+      // The float evaluation d2f of the squared distance differs from the reference's float-narrowed double sum by at most
+      // 2.1e-7 * d * (m + d) (the origin rounded to float, the three float differences) + 4.5e-7 * d^2 (squares, sums, the
+      // reference's own narrowing); the margin is more than four times that at d^2 = range^2 and at d^2 = 1e-4
+      const float margin = d.mark_range_2 * 2e-6f + 1e-6f * m * (std::sqrt(std::fmax(d.mark_range_2, 0.f)) + 1.0f) + 1e-7f;
       d.range2_reject = d.mark_range_2 + margin;
       if (!(d.range2_reject == d.range2_reject)) d.range2_reject = INFINITY;
       // inside [near_accept, range2_accept] the exact test (.cpp:289: !(d2 > range^2 || d2 < 0.0001)) certainly passes;

@@ -151,6 +151,7 @@ struct DevReading {
   uint32_t has_tf;
   uint32_t first_block;   // first unit of this reading in the batch's unit index space (units of 1984 points)
   uint32_t vec4;          // 1: point_step==16, offsets 0/4/8, 16 B aligned -> float4 loads
+  int32_t ref_ix, ref_iy, ref_iz;   // voxel of the reading's origin: frame of Mark's 32-bit voxel codes (set at launch)
 };
 struct MarkBatch {
   uint32_t first_block[kMaxBatchReadings];   // copy of r[k].first_block, one cache line: the producers scan it to find their readings

@@ -17,6 +17,7 @@
 // 32-bit OR per touched mask word and one 64-bit max (or store) per distinct voxel.  In the fused cycle all 32 warps then
 // run the costmap pass over the sweep's column counts.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <utility>
 
@@ -30,9 +31,16 @@ constexpr int kMarkThreads = kMarkConsumers + 32;
 constexpr int kMarkPPT = 2;                      // points per consumer thread per unit
 constexpr int kMarkChunk = kMarkConsumers * kMarkPPT;   // 1984 points = 31 KB of packed float4 points: one stage of the ring
 constexpr int kMarkSlices = 4;                   // slices per CTA
-constexpr int kMarkTable = 512;                  // CTA-local (reading, leaf) table entries
-constexpr int kMarkProbes = 16;
-constexpr int kMarkStagesMax = 6;
+constexpr int kMarkFilter = 8192;                // direct-mapped filter of voxel codes, entries (a power of two)
+constexpr int kMarkFilterShift = 19;             // 32 - log2(kMarkFilter)
+constexpr int kMarkQueue = 8192;                 // voxels to write, entries
+constexpr int kMarkQueueFlush = 2048;            // the producer asks for an early flush above this fill; at most kMarkStagesMax
+                                                 // units (5952 points) are still consumed before every warp has seen the request
+constexpr int kMarkStagesMax = 3;
+// voxel code: reading (4 bits) | x (10) | y (10) | z (8), relative to the voxel of the reading's origin
+constexpr int kCodeBiasXY = 512, kCodeBiasZ = 128;
+static_assert(kMarkQueueFlush + kMarkStagesMax * kMarkChunk <= kMarkQueue, "queue sized for the consumers' lag behind a flush request");
+static_assert((1 << (32 - kMarkFilterShift)) == kMarkFilter, "filter index = upper bits of the multiplicative hash");
 // per-stage word the producer posts: what the stage holds | sensor-frame cloud | reading | threads with two points | points.
 // Thread t < half holds points t and half + t of the unit (half = a multiple of 32: warps beyond it sit the unit out).
 constexpr uint32_t kMetaEnd = 1u << 31, kMetaFlush = 1u << 30, kMetaTf = 1u << 29;
@@ -70,16 +78,7 @@ __device__ __forceinline__ PointXYZ load_point_generic(const DevReading & r, uns
   return p;
 }
 
-// key of the CTA-local table: reading index (the mark time differs per reading) + leaf coordinate, x relative to the
-// batch's reference leaf so that everything fits 63 bits; leaves farther than 2^16 leaves from it bypass the table
-constexpr int kMarkRelBias = 1 << 16;
-__device__ __forceinline__ uint64_t pack_table_key(int ri, int rx, int by, int bz)
-{
-  return ((uint64_t)(uint32_t)ri << 59) | ((uint64_t)(uint32_t)(rx + kMarkRelBias) << 42) |
-         ((uint64_t)(uint32_t)(by + kLeafBias) << 21) | (uint64_t)(uint32_t)(bz + kLeafBias);
-}
-
-// write one voxel straight to the global store (fallback when the CTA-local table is full or the leaf is out of its reach)
+// write one voxel straight to the global store (a voxel beyond the reach of the 32-bit code, or a full queue)
 __device__ __noinline__ void mark_voxel_direct(const GridView & g, int bx, int by, int bz, unsigned l, double now, bool use_max, double tmin_init)
 {
   const uint32_t slot = leaf_find_or_insert(g, pack_leaf_key(bx, by, bz), bx, by, tmin_init);
@@ -126,15 +125,30 @@ __device__ __noinline__ int4 quantise_exact(float fx, float fy, float fz, double
 // ends, so the reference truncates to that same integer; otherwise `diff` gets a non-zero bit and the point takes the
 // exact path.  Sums of 2^24 and more (indices beyond 2^23) always differ: the ends are more than two ulps apart there.
 // (Infinite products compare equal — such points never get here: their squared distance is not finite either.)
-// `neg`: S < 0 (for x and y that is the sign test the shift already made: the shift never changes the sign).
-__device__ __forceinline__ int quantise_axis_fast(float S, bool neg, float c_lo, float c_hi, uint32_t & diff)
+__device__ __forceinline__ int quantise_axis_fast(float S, float c_lo, float c_hi, uint32_t & diff)
 {
   const float a = fabsf(S);
   const uint32_t t_lo = __float_as_uint(__fmaf_rz(a, c_lo, 8388608.0f));
   const uint32_t t_hi = __float_as_uint(__fmaf_rz(a, c_hi, 8388608.0f));
   diff |= t_lo ^ t_hi;
   const int fl = (int)(t_lo & 0x7FFFFFu);   // floor(|S| / vs)
-  return neg ? -fl : fl;                   // the reference truncates toward zero
+  return S < 0.0f ? -fl : fl;              // the reference truncates toward zero
+}
+// x and y, whose shift hangs on their own sign (.cpp:293-298): for f < 0 the reference computes trunc((f - vs) * (1/vs)) =
+// -floor((|f| + vs) / vs) = -(floor(|f| / vs) + 1) = ~floor(|f| / vs), so the shift never has to be formed: floor(|f| / vs)
+// from the interval test above (a = |f| exactly, one rounding fewer), complemented for negative f.  What the reference adds
+// to u = |f| / vs on the way — rounding (f - vs), 1/vs and the product in double — is below (u + 1) * 4e-16, far inside the
+// interval's slack of 1.8e-7 * u around every integer >= 1; around 0 the slack is u itself, so negatives with |f| < 1e-12
+// (u < 4e-16 needs vs > 2500 m) and -0.0 (whose sign bit is set although the reference does not shift it) are left to the
+// exact path: as signed integers exactly those bit patterns are below that of -1e-12f.
+__device__ __forceinline__ int quantise_xy_fast(float f, float c_lo, float c_hi, uint32_t & diff, bool & tiny)
+{
+  const float a = fabsf(f);
+  const uint32_t t_lo = __float_as_uint(__fmaf_rz(a, c_lo, 8388608.0f));
+  const uint32_t t_hi = __float_as_uint(__fmaf_rz(a, c_hi, 8388608.0f));
+  diff |= t_lo ^ t_hi;
+  tiny = tiny | (__float_as_int(f) < (int)0xAB8CBCCC);      // -1e-12f
+  return (int)(t_lo & 0x7FFFFFu) ^ (__float_as_int(f) >> 31);
 }
 
 // kVec4: every reading of the batch is a packed x,y,z,pad float4 cloud (the RGBD / depth-image layout), streamed through
@@ -150,19 +164,18 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
             uint8_t * __restrict__ costmap, const int n_stages)
 {
   extern __shared__ __align__(128) unsigned char s_dyn[];
-  // dynamic shared memory: [stages (kVec4 only)] [table keys] [table masks]
+  // dynamic shared memory: [stages (kVec4 only)] [filter] [queue]
   const size_t stage_bytes = kVec4 ? (size_t)n_stages * kMarkChunk * 16 : 0;
-  unsigned long long * const s_key = reinterpret_cast<unsigned long long *>(s_dyn + stage_bytes);
-  uint32_t (* const s_mask)[16] = reinterpret_cast<uint32_t (*)[16]>(s_dyn + stage_bytes + (size_t)kMarkTable * 8);
-  __shared__ uint32_t s_slot[kMarkTable];
-  __shared__ uint16_t s_list[kMarkTable];   // claimed table entries, in claim order (s_fill of them)
+  uint32_t * const s_filter = reinterpret_cast<uint32_t *>(s_dyn + stage_bytes);
+  uint32_t * const s_queue = s_filter + kMarkFilter;
   __shared__ double s_rnow[kMaxBatchReadings];
-  // per reading, the single-precision screen of the range / z tests: {range2_reject, range2_accept, near_accept, ox} {oy, oz, zlo, zhi}
-  __shared__ __align__(16) float s_par[kMaxBatchReadings][8];
+  // per reading: the single-precision screen of the range / z tests {range2_reject, range2_accept, near_accept, ox}
+  // {oy, oz, zlo, zhi} and the voxel code's frame {ref_ix - bias, ref_iy - bias, ref_iz - bias, reading << 28}
+  __shared__ __align__(16) float s_par[kMaxBatchReadings][12];
   __shared__ __align__(8) uint64_t s_full[kMarkStagesMax], s_empty[kMarkStagesMax];
   __shared__ unsigned long long s_base[kMarkStagesMax];   // per stage: first point of the unit in its reading (generic layouts)
   __shared__ uint32_t s_meta[kMarkStagesMax];
-  __shared__ unsigned int s_fill;          // claimed table entries
+  __shared__ unsigned int s_qn;            // queued voxels (may run past kMarkQueue: the excess went straight to the store)
   __shared__ unsigned int s_flushes;       // early flushes done (the producer requests at most one at a time)
   __shared__ unsigned int s_drop[2];
 
@@ -219,9 +232,9 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
         const uint32_t cnt = (uint32_t)(n_pts - base < want ? n_pts - base : want);
         const uint32_t half = (((cnt + 1) >> 1) + 31u) & ~31u;
         mbar_wait(&s_empty[stage], phase ^ 1u);
-        // a filling table is flushed early (large or scattered clouds): the marker travels in-band, so every consumer
+        // a filling queue is flushed early (large or scattered clouds): the marker travels in-band, so every consumer
         // sees it between the same two units
-        if (*reinterpret_cast<volatile unsigned int *>(&s_fill) >= (unsigned)(kMarkTable * 5 / 8) &&
+        if (*reinterpret_cast<volatile unsigned int *>(&s_qn) >= (unsigned)kMarkQueueFlush &&
             *reinterpret_cast<volatile unsigned int *>(&s_flushes) == flush_requests) {
           ++flush_requests;
           s_meta[stage] = kMetaFlush;
@@ -244,9 +257,9 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
     if (lane == 0) {
       for (int s = 0; s < n_stages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kMarkConsumerWarps); }
       mbar_fence_init();
-      s_fill = 0; s_flushes = 0; s_drop[0] = s_drop[1] = 0;
+      s_qn = 0; s_flushes = 0; s_drop[0] = s_drop[1] = 0;
       policy = l2_evict_first_policy();
-      // the first copies go out while the consumer warps are still clearing the table (s_fill is 0: no flush marker yet)
+      // the first copies go out while the consumer warps are still clearing the filter (s_qn is 0: no flush marker yet)
       for (int s = 0; s < n_stages && !done; ++s) done = !produce();
     }
     __syncwarp();
@@ -264,26 +277,23 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
       float * sp = s_par[threadIdx.x];
       sp[0] = r.range2_reject; sp[1] = r.range2_accept; sp[2] = r.near_accept; sp[3] = r.oxf;
       sp[4] = r.oyf; sp[5] = r.ozf; sp[6] = zwin ? r.zmin_f : -CUDART_INF_F; sp[7] = zwin ? r.zmax_f : CUDART_INF_F;
+      sp[8] = __int_as_float(r.ref_ix - kCodeBiasXY); sp[9] = __int_as_float(r.ref_iy - kCodeBiasXY);
+      sp[10] = __int_as_float(r.ref_iz - kCodeBiasZ); sp[11] = __uint_as_float(threadIdx.x << 28);
     }
-    for (int i = threadIdx.x; i < kMarkTable; i += kMarkConsumers) s_key[i] = kEmptyKey;
-    for (int i = threadIdx.x; i < kMarkTable * 16; i += kMarkConsumers) (&s_mask[0][0])[i] = 0;
-    named_bar_sync(3, kMarkThreads);   // barriers initialised (producer), table cleared
+    // an entry starts out holding a code that hashes to ANOTHER entry, so no lookup can ever match it
+    for (int i = threadIdx.x; i < kMarkFilter; i += kMarkConsumers) s_filter[i] = i == 0 ? 1u : 0u;
+    named_bar_sync(3, kMarkThreads);   // barriers initialised (producer), filter cleared
     TRACE(0, 1);
 
     bool grid_ok = false;       // this thread has waited for the predecessor grid (the sweep)
     auto sync_with_predecessor = [&]() { if (!grid_ok) { pdl_wait(); grid_ok = true; } };
     unsigned int drop_range = 0, drop_nonfinite = 0;
-    // this thread's most recent voxel that went through the table (l_ix = 2^30: no voxel index can share a leaf with it,
-    // fast-path indices are below 2^23), its reading, and ...
-    int l_ix = 1 << 30, l_iy = 0, l_iz = 0, l_ri = -1;
-    // ... its leaf in the CTA-local table: shared-window address of the leaf's 16 mask words (0: none — the table was full
-    // or the leaf is out of its reach, voxels go straight to the global store)
-    uint32_t l_mask = 0;
     const float vs_f = batch.vs_f, c_lo = batch.c_lo, c_hi = batch.c_hi;   // (float)vs and the two ends of 1/vs, see launch_mark
     const uint32_t my_point = smem_u32(s_dyn) + threadIdx.x * 16u;       // this thread's first point of stage 0
+    const uint32_t filter_addr = smem_u32(s_filter), qn_addr = smem_u32(&s_qn);
     const bool sharded = g.shard_count > 1;
 
-    // ---- flush: resolve the table's leaves in the global hash, push masks and times, empty the table ----------------------
+    // ---- flush: write the queued voxels to the store, empty the queue (and, between units, the filter) -------------------
     auto flush = [&](const bool final) {
       named_bar_sync(1, kMarkConsumers);   // every consumer warp is done with the units before the flush point
       if (final) TRACE(0, 3);
@@ -291,70 +301,36 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
       // launch_dependents only AFTER our own wait: the next cycle's sweep (and the Mark behind it) cannot become resident
       // before the grid preceding this one has completed, which bounds the programmatic-launch chain to two kernels in flight
       if (final) pdl_launch_dependents();
-      const int n_claimed = (int)*reinterpret_cast<volatile unsigned int *>(&s_fill);
-      for (int c = threadIdx.x; c < n_claimed; c += kMarkConsumers) {   // one thread per distinct (reading, leaf)
-        const int e = s_list[c];
-        const unsigned long long tkey = s_key[e];
-        const int bx = (int)((tkey >> 42) & 0x1FFFF) - kMarkRelBias + batch.ref_bx;
-        const int by = (int)((tkey >> 21) & 0x1FFFFF) - kLeafBias, bz = (int)(tkey & 0x1FFFFF) - kLeafBias;
-        s_slot[e] = leaf_find_or_insert(g, pack_leaf_key(bx, by, bz), bx, by, batch.min_now);
-      }
-      l_ix = 1 << 30; l_mask = 0;
-      named_bar_sync(1, kMarkConsumers);
-      if (final) TRACE(0, 4);
-      // per touched mask word one 32-bit OR, per distinct voxel one 64-bit max (batched launch, monotone clocks) or a
-      // plain store (per-reading launches: exact overwrite semantics of MarkGridPoint, .cpp:421-430)
-      for (int i = threadIdx.x; i < n_claimed * 16; i += kMarkConsumers) {
-        const int e = s_list[i >> 4];
-        const unsigned w = i & 15;
-        uint32_t m = s_mask[e][w];
-        if (!m) continue;
-        s_mask[e][w] = 0;
-        const uint32_t slot = s_slot[e];
+      const int n_queued = (int)min(*reinterpret_cast<volatile unsigned int *>(&s_qn), (unsigned)kMarkQueue);
+      // per queued voxel: one probe of the global leaf hash, one 32-bit OR into the leaf's mask, one 64-bit max (batched
+      // launch, monotone clocks) or a plain store (per-reading launches: exact overwrite semantics of MarkGridPoint,
+      // .cpp:421-430) of the mark time
+      for (int i = threadIdx.x; i < n_queued; i += kMarkConsumers) {
+        const uint32_t code = s_queue[i];
+        const int ri = (int)(code >> 28);
+        const int x = (int)((code >> 18) & 1023u) + __float_as_int(s_par[ri][8]);
+        const int y = (int)((code >> 8) & 1023u) + __float_as_int(s_par[ri][9]);
+        const int z = (int)(code & 255u) + __float_as_int(s_par[ri][10]);
+        const int bx = x >> 3, by = y >> 3, bz = z >> 3;
+        const uint32_t slot = leaf_find_or_insert(g, pack_leaf_key(bx, by, bz), bx, by, batch.min_now);
         if (slot == kOverflowSlot) continue;
-        const double now = s_rnow[(int)(s_key[e] >> 59)];
-        const unsigned long long now_bits = (unsigned long long)__double_as_longlong(now);
-        red_or_u32(&g.leaf_mask[(size_t)slot * 16 + w], m);
-        double * tp = g.leaf_time + (size_t)slot * kLeafVoxels + w * 32;
-        if (!use_max && g.leaf_tmin[slot] > now) g.leaf_tmin[slot] = -CUDART_INF;   // clocks are not monotone here
-        while (m) {
-          const int b = __ffs(m) - 1; m &= m - 1;
-          if (use_max) red_max_s64(reinterpret_cast<unsigned long long *>(tp + b), now_bits);
-          else tp[b] = now;
+        const unsigned l = (unsigned)(((x & 7) * 8 + (y & 7)) * 8 + (z & 7));
+        const double now = s_rnow[ri];
+        red_or_u32(&g.leaf_mask[(size_t)slot * 16 + (l >> 5)], 1u << (l & 31));
+        double * tp = g.leaf_time + (size_t)slot * kLeafVoxels + l;
+        if (use_max) red_max_s64(reinterpret_cast<unsigned long long *>(tp), (unsigned long long)__double_as_longlong(now));
+        else {
+          *tp = now;
+          if (g.leaf_tmin[slot] > now) g.leaf_tmin[slot] = -CUDART_INF;   // clocks are not monotone here
         }
       }
+      if (final) TRACE(0, 4);
       if (!final) {
-        named_bar_sync(1, kMarkConsumers);   // the keys were still needed for the per-reading clock above
-        for (int c = threadIdx.x; c < n_claimed; c += kMarkConsumers) s_key[s_list[c]] = kEmptyKey;
-        named_bar_sync(1, kMarkConsumers);   // (the list is read above, s_fill re-armed below)
-        if (threadIdx.x == 0) { s_fill = 0; atomicAdd(&s_flushes, 1u); }
+        named_bar_sync(1, kMarkConsumers);   // the queue has been read
+        for (int i = threadIdx.x; i < kMarkFilter; i += kMarkConsumers) s_filter[i] = i == 0 ? 1u : 0u;
+        if (threadIdx.x == 0) { s_qn = 0; atomicAdd(&s_flushes, 1u); }
         named_bar_sync(1, kMarkConsumers);
       }
-    };
-
-    // a voxel whose leaf differs from the thread's previous one: find-or-claim the (reading, leaf) entry of the CTA-local
-    // table; -1 = table full (scattered cloud) or leaf out of the table's reach
-    auto table_lookup = [&](int ri, int bx, int by, int bz) -> int {
-      const int rx = bx - batch.ref_bx;
-      if (rx < -kMarkRelBias || rx >= kMarkRelBias) return -1;
-      const uint64_t key = pack_table_key(ri, rx, by, bz);
-      uint32_t h = ((uint32_t)bx * 73856093u ^ (uint32_t)by * 19349663u ^ (uint32_t)bz * 83492791u ^ (uint32_t)ri * 2654435761u) & (kMarkTable - 1);
-#pragma unroll 1
-      for (int p = 0; p < kMarkProbes; ++p) {
-        unsigned long long cur = s_key[h];
-        if (cur == kEmptyKey) {
-          cur = atomicCAS(&s_key[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
-          if (cur == kEmptyKey) {
-            s_list[atomicAdd(&s_fill, 1u)] = (uint16_t)h;
-            // the flush will probe the global hash for this leaf: pull the line towards L2 now (a hint, no data is read)
-            prefetch_l2(&g.hash[(uint32_t)mix64(pack_leaf_key(bx, by, bz)) & g.hash_mask]);
-            cur = key;
-          }
-        }
-        if (cur == key) return (int)h;
-        h = (h + 1) & (kMarkTable - 1);
-      }
-      return -1;
     };
 
     int stage = 0;
@@ -381,6 +357,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
         continue;
       }
       const float4 pa = *reinterpret_cast<const float4 *>(&s_par[ri][0]), pb = *reinterpret_cast<const float4 *>(&s_par[ri][4]);
+      const float4 pc = *reinterpret_cast<const float4 *>(&s_par[ri][8]);
       PointXYZ pts[2];
       if constexpr (kVec4) {
         const uint32_t addr = my_point + (uint32_t)stage * (uint32_t)(kMarkChunk * 16);
@@ -409,7 +386,6 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
 #pragma unroll
         for (int k = 0; k < 2; ++k) transform_point(par.tf, pts[k].x, pts[k].y, pts[k].z);
       }
-      if (ri != l_ri) { l_ri = ri; l_ix = 1 << 30; }   // table entries are per reading
       const float range2_reject = pa.x, range2_accept = pa.y, near_accept = pa.z, oxf = pa.w, oyf = pb.x, ozf = pb.y, zlo = pb.z, zhi = pb.w;
       // ---- single-precision screen of the range and z tests, both points of the pair interleaved -----------------------------
       float d2f[2];
@@ -436,16 +412,14 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
       for (int k = 0; k < 2; ++k) {
         const float fx = pts[k].x, fy = pts[k].y, fz = pts[k].z;
         const bool inwin = (d2f[k] <= range2_accept) & (d2f[k] >= near_accept);
-        // .cpp:293-303 in float: shift negatives by one voxel (z tests y's sign — sic), multiply by 1/vs, truncate toward zero
-        const bool xneg = fx < 0, yneg = fy < 0;
-        const float X = xneg ? __fsub_rn(fx, vs_f) : fx;
-        const float Y = yneg ? __fsub_rn(fy, vs_f) : fy;
-        const float Z = yneg ? __fsub_rn(fz, vs_f) : fz;
+        // .cpp:293-303 in float: negatives are shifted by one voxel (z tests y's sign — sic), scaled by 1/vs, truncated toward zero
+        const float Z = fy < 0 ? __fsub_rn(fz, vs_f) : fz;
         uint32_t diff = 0;
-        ix[k] = quantise_axis_fast(X, xneg, c_lo, c_hi, diff);
-        iy[k] = quantise_axis_fast(Y, yneg, c_lo, c_hi, diff);
-        iz[k] = quantise_axis_fast(Z, Z < 0.0f, c_lo, c_hi, diff);
-        const bool decided = inwin & (diff == 0);
+        bool tiny = false;
+        ix[k] = quantise_xy_fast(fx, c_lo, c_hi, diff, tiny);
+        iy[k] = quantise_xy_fast(fy, c_lo, c_hi, diff, tiny);
+        iz[k] = quantise_axis_fast(Z, c_lo, c_hi, diff);
+        const bool decided = inwin & (diff == 0) & !tiny;
         take[k] = cand[k] & decided;
         // everything the fast path cannot decide, and everything that is not finite (counted), takes the exact sequence
         slow[k] = nonfin[k] | (cand[k] & !decided);
@@ -468,26 +442,43 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
 #pragma unroll
         for (int k = 0; k < 2; ++k) take[k] = take[k] && shard_owns(ix[k] >> 3, g.shard_index, g.shard_count, g.shard_width);
       }
-      // ---- CTA-local dedupe ------------------------------------------------------------------------------------------------------
+      // ---- CTA-local dedupe: 32-bit voxel code, direct-mapped filter, queue of voxels to write --------------------------------
+      const int fx0 = __float_as_int(pc.x), fy0 = __float_as_int(pc.y), fz0 = __float_as_int(pc.z);
+      const uint32_t ri28 = __float_as_uint(pc.w);
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        if (!take[k]) continue;
-        const int x = ix[k], y = iy[k], z = iz[k];
-        if ((uint32_t)((x ^ l_ix) | (y ^ l_iy) | (z ^ l_iz)) >= 8u) {   // another leaf than the thread's last one
-          const int e = table_lookup(ri, x >> 3, y >> 3, z >> 3);
-          l_mask = e >= 0 ? smem_u32(&s_mask[e][0]) : 0u;
-          l_ix = x; l_iy = y; l_iz = z;   // (a failed lookup is remembered too: the leaf's next voxels go the same way)
+        bool push = false;
+        uint32_t code = 0;
+        if (take[k]) {
+          const uint32_t rx = (uint32_t)(ix[k] - fx0), ry = (uint32_t)(iy[k] - fy0), rz = (uint32_t)(iz[k] - fz0);
+          if ((((rx | ry) >> 10) | (rz >> 8)) == 0u) {
+            code = ri28 | (rx << 18) | (ry << 8) | rz;
+            const uint32_t fa = filter_addr + (((code * 0x9E3779B1u) >> kMarkFilterShift) << 2);
+            uint32_t cur;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(fa));
+            if (cur != code) {   // not seen (or forgotten): remember it and queue it
+              asm volatile("st.shared.u32 [%0], %1;" :: "r"(fa), "r"(code) : "memory");
+              push = true;
+            }
+          } else {   // farther from the sensor than the code reaches: straight to the global store
+            sync_with_predecessor();
+            mark_voxel_direct(g, ix[k] >> 3, iy[k] >> 3, iz[k] >> 3, (unsigned)(((ix[k] & 7) * 8 + (iy[k] & 7)) * 8 + (iz[k] & 7)), s_rnow[ri], use_max,
+                              batch.min_now);
+          }
         }
-        // local index l = ((x & 7) * 8 + (y & 7)) * 8 + (z & 7): mask word l >> 5, bit l & 31 (the shift takes its count modulo 32)
-        const uint32_t bit = 1u << ((((uint32_t)y << 3) | ((uint32_t)z & 7u)) & 31u);
-        const uint32_t word_off = (((uint32_t)x << 3) & 0x38u) | ((uint32_t)y & 4u);   // (l >> 5) * 4
-        if (l_mask) {
-          uint32_t cur;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(l_mask + word_off));
-          if (!(cur & bit)) asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(l_mask + word_off), "r"(bit) : "memory");
-        } else {   // table full or leaf out of the table's reach: straight to the global store
-          sync_with_predecessor();
-          mark_voxel_direct(g, x >> 3, y >> 3, z >> 3, (unsigned)(((x & 7) * 8 + (y & 7)) * 8 + (z & 7)), s_rnow[ri], use_max, batch.min_now);
+        const unsigned pm = __ballot_sync(kFull, push);
+        if (pm) {   // warp-aggregated append
+          unsigned q0 = 0;
+          if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(q0) : "r"(qn_addr), "r"((unsigned)__popc(pm)) : "memory");
+          q0 = __shfl_sync(kFull, q0, 0) + __popc(pm & ((1u << lane) - 1u));
+          if (push) {
+            if (q0 < (unsigned)kMarkQueue) s_queue[q0] = code;
+            else {   // (cannot happen while the flush threshold holds; kept for safety)
+              sync_with_predecessor();
+              mark_voxel_direct(g, ix[k] >> 3, iy[k] >> 3, iz[k] >> 3, (unsigned)(((ix[k] & 7) * 8 + (iy[k] & 7)) * 8 + (iz[k] & 7)), s_rnow[ri],
+                                use_max, batch.min_now);
+            }
+          }
         }
       }
     }
@@ -592,7 +583,7 @@ int env_int(const char * name, int dflt, int lo, int hi)
 // bulk-copy stages per CTA (STVL_MARK_STAGES is a tuning knob for profiling; the default is what the measurements in
 // DESIGN.md were taken with)
 int mark_stages(bool vec4) { static const int v = env_int("STVL_MARK_STAGES", 3, 2, kMarkStagesMax); return vec4 ? v : 2; }
-size_t mark_smem_bytes(bool vec4) { return (vec4 ? (size_t)mark_stages(true) * kMarkChunk * 16 : 0) + (size_t)kMarkTable * (8 + 64); }
+size_t mark_smem_bytes(bool vec4) { return (vec4 ? (size_t)mark_stages(true) * kMarkChunk * 16 : 0) + (size_t)(kMarkFilter + kMarkQueue) * 4; }
 }  // namespace
 
 // one CTA per SM; small batches get one CTA per unit
@@ -636,6 +627,15 @@ static cudaError_t launch_mark_variant(const GridView & g, const MarkBatch & bat
   b.c_lo = (float)g.inv_vs * 0.999999701976776123046875f;            // (float)(1/vs) * (1 - 5 * 2^-24), one rounding
   b.c_hi = (float)g.inv_vs * 1.00000035762786865234375f;             // (float)(1/vs) * (1 + 3 * 2^-23), one rounding
   mark_set_slices(b, mark_grid_for(batch, sm_count));
+  for (uint32_t k = 0; k < b.n_readings; ++k) {   // frame of the 32-bit voxel codes: the voxel the reading's origin falls into
+    const double o[3] = {b.r[k].ox, b.r[k].oy, b.r[k].oz};
+    int32_t ref[3];
+    for (int a = 0; a < 3; ++a) {
+      const double q = std::floor(o[a] / g.vs);
+      ref[a] = (std::isfinite(q) && std::fabs(q) < 1e9) ? (int32_t)q : 0;
+    }
+    b.r[k].ref_ix = ref[0]; b.r[k].ref_iy = ref[1]; b.r[k].ref_iz = ref[2];
+  }
   return launch_ex(mark_kernel<kVec4, kCostmap, kCmBits>, mark_grid_for(batch, sm_count), (unsigned)kMarkThreads, smem, s, pdl, g, b, cm, costmap,
                    mark_stages(kVec4));
 }
