@@ -456,9 +456,10 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
             const uint32_t fa = filter_addr + (((code * 0x9E3779B1u) >> kMarkFilterShift) << 2);
             uint32_t cur;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(fa));
-            if (cur != code) {   // not seen (or forgotten): remember it and queue it
-              asm volatile("st.shared.u32 [%0], %1;" :: "r"(fa), "r"(code) : "memory");
-              push = true;
+            if (cur != code) {   // not seen (or forgotten): remember it and queue it.  The exchange lets exactly one of the
+              uint32_t old;      // lanes (and warps) that find the same voxel missing at the same time do the queueing
+              asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"(fa), "r"(code) : "memory");
+              push = old != code;
             }
           } else {   // farther from the sensor than the code reaches: straight to the global store
             sync_with_predecessor();
