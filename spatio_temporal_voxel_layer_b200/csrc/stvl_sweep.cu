@@ -1,17 +1,24 @@
 // stvl_sweep.cu — ClearFrustums / TemporalClearAndGenerateCostmap (reference spatio_temporal_voxel_grid.cpp:96-224) as ONE
 // kernel.
 //
-// Every CTA walks tile passes over the leaf slots, two phases per pass and ONE CTA barrier between them:
+// Every CTA walks passes over the leaf slots (dealt to the CTAs in groups of four consecutive slots, so that a run of leaves
+// that all need work — a frustum's interior, a part of the map that expires together — is spread over the whole grid); a
+// pass has ONE CTA barrier:
 //   A  one THREAD per leaf: header (key, tmin, tile, 64 B value mask) in one round trip.  A leaf outside every frustum whose
 //      oldest voxel is too young to expire cannot change: its survivors are counted straight from the mask (two adjacent u32
-//      column counters per 64-bit reduction) and its 4 KB time block is never touched.  Every other leaf goes into a work
-//      queue in SHARED memory and its occupied 64 B time runs are prefetched into L2.
+//      column counters per 64-bit reduction) and its 4 KB time block is never touched.  A leaf no frustum can touch but in
+//      which something may have expired puts its occupied voxel COLUMNS (8 mark times = one 64 B run) on a column queue;
+//      a leaf a frustum may touch goes on the leaf queue.  Both queues live in shared memory; the occupied 64 B time runs
+//      are prefetched into L2.
+//   B' one THREAD per queued column: 64 B of mark times, the plain decay test of .cpp:203-211 per voxel, the new mask byte,
+//      the column's survivor count; the leaf's new lower time bound is gathered in shared memory.
 //   B  one WARP per queued leaf, taken dynamically.  Lane l owns bit l of every 32-bit mask word, so the mark times of a
 //      word are one coalesced 256 B run and the survivors come back as one ballot — the new mask word.  The next word's
 //      times are requested before the current word is worked on.  Per voxel: the reference's exact arithmetic (decay model,
 //      first containing frustum in reading order, acceleration, strict <), rewrite of accelerated times, per-column survivor
 //      counts, optional lists; per leaf: frustum classification (one lane per frustum), new lower time bound, pruning.
-// Three queues rotate, so a warp that runs out of phase-B work starts phase A of the next pass while the others finish.
+//   C  (after the next pass's barrier) the thread that queued a leaf's columns writes its new lower time bound or frees it.
+// Three sets of queues rotate, so a warp that runs out of work starts phase A of the next pass while the others finish.
 // No global work queue, no second launch, no grid-wide synchronisation: a leaf's whole sweep stays inside one CTA.
 #include <algorithm>
 #include <cstdlib>
@@ -68,21 +75,45 @@ __device__ __forceinline__ bool leaf_may_expire(const GridView & g, double now, 
   return !(g.voxel_decay >= 0.0);
 }
 
-// queue entry: pool slot of a leaf that needs the per-voxel pass | kTouched when a frustum may contain one of its voxels
+// leaf queue entry: pool slot of a leaf that needs the per-voxel pass | kTouched when a frustum may contain one of its voxels
 constexpr uint32_t kTouched = 0x80000000u;
+// column queue entry: (thread that owns the leaf in this pass) << 14 | column << 8 | the column's mask byte
+constexpr int kColQueue = 4096;
+
+// total order of doubles as unsigned integers (for the shared-memory minimum of a leaf's surviving mark times)
+__device__ __forceinline__ unsigned long long ordered_bits(double x)
+{
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ordered_value(unsigned long long e)
+{
+  return __longlong_as_double((long long)((e >> 63) ? (e & 0x7FFFFFFFFFFFFFFFull) : ~e));
+}
+constexpr unsigned long long kNoSurvivor = ~0ull;
+
+// dynamic shared memory behind the frustum blocks
+struct SweepShared {
+  uint32_t cq[3][kColQueue];                  // column queues
+  unsigned long long lmin[2][kSweepThreads];  // per leaf whose columns are queued (indexed by the owning thread): minimum of the
+  unsigned long long lkey[2][kSweepThreads];  //   surviving mark times (ordered_bits), key, slot, tile
+  uint32_t lslot[2][kSweepThreads];
+  uint32_t ltile[2][kSweepThreads];
+};
 
 __global__ void __launch_bounds__(kSweepThreads, 2)
 sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ FrustumParams fparam, const DevFrustum * __restrict__ frustums_gmem,
              const int n_frustums, const double now, const __grid_constant__ SweepOutputs out, uint8_t * __restrict__ cm_reset,
-             const unsigned long long cm_bytes, const int cm_value, const uint32_t tile_leaves)
+             const unsigned long long cm_bytes, const int cm_value)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevFrustum * fr = reinterpret_cast<DevFrustum *>(smem_raw);   // frustum parameter blocks, staged for the whole kernel
+  SweepShared & sh = *reinterpret_cast<SweepShared *>(smem_raw + (((size_t)n_frustums * sizeof(DevFrustum) + 15) & ~(size_t)15));
   // three work queues in rotation: tile pass t fills queue t % 3 in phase A and drains it in phase B; a warp that runs out
   // of phase-B work goes on to phase A of pass t + 1 (queue (t + 1) % 3) without waiting for the others, and queue
   // (t + 2) % 3 — drained in pass t - 1 — is re-armed meanwhile.  ONE CTA barrier per pass.
   __shared__ uint32_t s_q[3][kSweepThreads];
-  __shared__ unsigned int s_qn[3], s_qnext[3];
+  __shared__ unsigned int s_qn[3], s_qnext[3], s_cn[3], s_climit[3];
   __shared__ uint32_t s_part[kSweepWarps][kMaxFrustums / 32];
   __shared__ uint32_t s_full[kSweepWarps][kMaxFrustums / 32];
   __shared__ unsigned int s_red[5];
@@ -101,7 +132,7 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
     for (int i = threadIdx.x; i < words; i += kSweepThreads) dst[i] = src[i];
   }
   if (threadIdx.x == 0) {
-    s_qn[0] = s_qn[1] = s_qn[2] = 0; s_qnext[0] = s_qnext[1] = s_qnext[2] = 0;
+    s_qn[0] = s_qn[1] = s_qn[2] = 0; s_qnext[0] = s_qnext[1] = s_qnext[2] = 0; s_cn[0] = s_cn[1] = s_cn[2] = 0; s_climit[0] = s_climit[1] = s_climit[2] = kColQueue;
     s_red[0] = s_red[1] = s_red[2] = s_red[3] = s_red[4] = 0;
     s_bb[0] = s_bb[1] = INT_MAX; s_bb[2] = s_bb[3] = INT_MIN;
   }
@@ -146,20 +177,33 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
   SweepAcc acc;
   TRACE(1, 2);
 
-  // Tile passes over `tile_leaves` leaf slots per CTA, dealt round-robin to the CTAs in groups of 32 (a contiguous run of
-  // leaves that all need the per-voxel pass — a frustum's interior — is spread over many CTAs).
-  const uint32_t groups_per_tile = tile_leaves / 32;          // <= kSweepWarps
-  const uint32_t n_groups = (n_slots + 31) / 32;
-  uint32_t qi = 0;   // queue of this pass (pass number modulo 3)
-  for (uint32_t g0 = 0; g0 < n_groups; g0 += gridDim.x * groups_per_tile, qi = qi == 2 ? 0 : qi + 1) {
+  // Passes: thread t of CTA b takes, in pass p, the leaf (p * 512 + t) of the CTA's share; slots are dealt to the CTAs in groups
+  // of four consecutive ones (the 8-byte header fields of a group fill one 32 B sector).
+  const uint32_t n_quads = (n_slots + 3) / 4;
+  const uint32_t n_passes = (n_quads + gridDim.x * (kSweepThreads / 4) - 1) / (gridDim.x * (kSweepThreads / 4));
+  uint32_t qi = 0;   // queues of this pass (pass number modulo 3)
+  // bit p & 1: this thread queued the columns of a leaf in pass p and has not yet written the leaf's new bound (that happens
+  // behind the NEXT pass's barrier, i.e. after this thread's phase A of that pass — hence two bits, and the leaf's slot is
+  // kept in the parity-indexed shared arrays)
+  uint32_t col_pending = 0;
+  auto finish_columns = [&](uint32_t pb) {   // phase C
+    if ((col_pending >> pb) & 1u) {
+      const uint32_t cslot = sh.lslot[pb][threadIdx.x];
+      const unsigned long long m = sh.lmin[pb][threadIdx.x];
+      if (m == kNoSurvivor) free_leaf(g, cslot);            // every voxel of the leaf was cleared: pruneGrid, .cpp:223
+      else g.leaf_tmin[cslot] = ordered_value(m);           // exact lower bound again
+      col_pending &= ~(1u << pb);
+    }
+  };
+  for (uint32_t pass = 0; pass < n_passes; ++pass, qi = qi == 2 ? 0 : qi + 1) {
+    const uint32_t pb = pass & 1u;
     // ---- phase A: one thread per leaf -------------------------------------------------------------------------------------
-    // group index of this warp in the tile: warp w handles group (g0 + w * gridDim + blockIdx) — interleaved across CTAs
-    if (warp < groups_per_tile) {
-      const uint32_t grp = g0 + warp * gridDim.x + blockIdx.x;
-      const uint32_t slot = grp * 32 + lane;
+    {
+      const uint32_t q = pass * kSweepThreads + threadIdx.x;
+      const uint32_t slot = ((q >> 2) * gridDim.x + blockIdx.x) * 4 + (q & 3u);
       uint32_t entry = 0;
       bool queue_it = false;
-      if (grp < n_groups && slot < n_slots) {
+      if (slot < n_slots) {
         const uint64_t key = g.leaf_key[slot];
         const double tmin = g.leaf_tmin[slot];
         const uint32_t tile = g.leaf_tile[slot];
@@ -189,8 +233,42 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
               }
             }
             if (touches || leaf_may_expire(g, now, tmin)) {
-              queue_it = true;
-              entry = slot | (touches ? kTouched : 0u);
+              const uint32_t wv[16] = {mw[0].x, mw[0].y, mw[0].z, mw[0].w, mw[1].x, mw[1].y, mw[1].z, mw[1].w,
+                                       mw[2].x, mw[2].y, mw[2].z, mw[2].w, mw[3].x, mw[3].y, mw[3].z, mw[3].w};
+              bool as_columns = false;
+              if (!touches) {
+                // decay test only: one queue entry per occupied voxel column, if the queue has room for all of them
+                unsigned n_cols = 0;
+#pragma unroll
+                for (int w = 0; w < 16; ++w) {
+                  uint32_t t = wv[w] | (wv[w] >> 4);
+                  t |= t >> 2; t |= t >> 1;
+                  n_cols += __popc(t & 0x01010101u);
+                }
+                unsigned c0 = atomicAdd(&s_cn[qi], n_cols);
+                if (c0 + n_cols <= (unsigned)kColQueue) {
+                  as_columns = true;
+                  sh.lmin[pb][threadIdx.x] = kNoSurvivor;
+                  sh.lkey[pb][threadIdx.x] = key;
+                  sh.lslot[pb][threadIdx.x] = slot;
+                  sh.ltile[pb][threadIdx.x] = tile;
+                  col_pending |= 1u << pb;
+#pragma unroll
+                  for (int w = 0; w < 16; ++w) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                      const uint32_t byte = (wv[w] >> (8 * c)) & 0xFFu;
+                      if (byte) sh.cq[qi][c0++] = (threadIdx.x << 14) | ((uint32_t)(w * 4 + c) << 8) | byte;
+                    }
+                  }
+                } else {
+                  atomicMin(&s_climit[qi], c0);   // no room (nor for anybody after this reservation): the leaf takes the warp-per-leaf pass
+                }
+              }
+              if (!as_columns) {
+                queue_it = true;
+                entry = slot | (touches ? kTouched : 0u);
+              }
               // the leaf's mark times will be needed in phase B: pull the occupied 64 B column runs into L2 now
               const double * tb = g.leaf_time + (size_t)slot * kLeafVoxels;
 #pragma unroll
@@ -245,8 +323,59 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0) { const uint32_t qz = qi == 0 ? 2 : qi - 1; s_qn[qz] = 0; s_qnext[qz] = 0; }   // (t + 2) % 3 == (t - 1) % 3
+    if (threadIdx.x == 0) {   // re-arm the queues of pass t + 2 (those of pass t - 1: everybody is done with them)
+      const uint32_t qz = qi == 0 ? 2 : qi - 1;
+      s_qn[qz] = 0; s_qnext[qz] = 0; s_cn[qz] = 0; s_climit[qz] = kColQueue;
+    }
     const uint32_t n_items = s_qn[qi];
+    const uint32_t n_cols_queued = min(s_cn[qi], s_climit[qi]);
+    // ---- phase C of the previous pass: its columns have all been worked on ---------------------------------------------------
+    if (pass > 0) finish_columns(pb ^ 1u);
+    // ---- phase B': one thread per queued voxel column (leaves no frustum can touch): the decay test of .cpp:203-211 ----------
+    for (uint32_t i = threadIdx.x; i < n_cols_queued; i += kSweepThreads) {
+      const uint32_t it = sh.cq[qi][i];
+      const uint32_t owner = it >> 14, col = (it >> 8) & 63u, byte = it & 0xFFu;
+      const uint32_t cslot = sh.lslot[pb][owner];
+      const double2 * tp = reinterpret_cast<const double2 *>(g.leaf_time + (size_t)cslot * kLeafVoxels + col * 8);
+      const double2 t01 = __ldcs(tp), t23 = __ldcs(tp + 1), t45 = __ldcs(tp + 2), t67 = __ldcs(tp + 3);
+      const double tv[8] = {t01.x, t01.y, t23.x, t23.y, t45.x, t45.y, t67.x, t67.y};
+      uint32_t nb = byte;
+      double vmin = CUDART_INF;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (!((byte >> k) & 1u)) continue;
+        const double v = tv[k];
+        const double t = __dsub_rn(now, v);   // .cpp:167-169
+        double base_dur;
+        if (g.decay_model == 0) base_dur = __dsub_rn(g.voxel_decay, t);
+        else if (g.decay_model == 1) base_dur = __dmul_rn(g.voxel_decay, exp(-t));
+        else base_dur = g.voxel_decay;
+        if (base_dur < 0.) nb &= ~(1u << k);
+        else vmin = fmin(vmin, v);
+      }
+      const unsigned n_in = __popc(byte), n_left = __popc(nb);
+      acc.swept += n_in; acc.surv += n_left; acc.clear += n_in - n_left;
+      if (nb != byte) {
+        reinterpret_cast<uint8_t *>(g.leaf_mask)[(size_t)cslot * 64 + col] = (uint8_t)nb;   // this thread alone owns the column's mask byte
+        int bx, by, bz;
+        unpack_leaf_key(sh.lkey[pb][owner], bx, by, bz);
+        const int ix = bx * 8 + (int)(col >> 3), iy = by * 8 + (int)(col & 7u);
+        acc.min_x = min(acc.min_x, ix); acc.max_x = max(acc.max_x, ix);
+        acc.min_y = min(acc.min_y, iy); acc.max_y = max(acc.max_y, iy);
+        if (out.cleared) {   // cleared_cells.insert, .cpp:213-215: one entry per cleared voxel
+          const unsigned n_cl = n_in - n_left;
+          const unsigned long long o = atomicAdd(&g.ctr->sw[g.sw_cur].n_cleared_out, (unsigned long long)n_cl);
+          for (unsigned c = 0; c < n_cl; ++c)
+            if (o + c < out.cleared_cap) { out.cleared[2 * (o + c)] = ix; out.cleared[2 * (o + c) + 1] = iy; }
+        }
+      }
+      if (nb) {
+        // PopulateCostmapAndPointcloud .cpp:242-250: _cost_map[(x,y)] += 1 per surviving voxel of the column
+        const uint32_t ctile = sh.ltile[pb][owner];
+        if (ctile != kOverflowSlot) red_add_u32(g.tile_count + (size_t)ctile * 64 + col, n_left);
+        atomicMin(&sh.lmin[pb][owner], ordered_bits(vmin));
+      }
+    }
     // ---- phase B: one warp per queued leaf, taken dynamically.  Lane l owns bit l of every mask word: the 32 mark times of
     // a word are one coalesced 256 B run, survivors come back as one ballot = the new mask word --------------------------------
     for (;;) {
@@ -401,6 +530,10 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
       }
     }
   }
+  if (n_passes > 0) {   // phase C of the last pass
+    __syncthreads();
+    finish_columns((n_passes - 1) & 1u);
+  }
   TRACE(1, 3);
 
   // ---- statistics: warp reduce, shared-memory add, a handful of global reductions per CTA -------------------------------------
@@ -458,25 +591,21 @@ cudaError_t launch_sweep(const GridView & g, const DevFrustum * frustums_dev, co
     cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     carveout_set = true;
   }
-  const size_t dyn = (size_t)n_frustums * sizeof(DevFrustum);
+  const size_t dyn = (((size_t)n_frustums * sizeof(DevFrustum) + 15) & ~(size_t)15) + sizeof(SweepShared);
   static size_t dyn_max = 0;
-  if (dyn > 16 * 1024 && dyn > dyn_max) {
+  if (dyn > dyn_max) {
     cudaError_t e = cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
     dyn_max = dyn;
   }
-  // Persistent grid: one CTA per SM while a Mark kernel is to share the SMs with it (fused cycle), two otherwise.  Small
-  // stores get small tiles so that every CTA has leaves: the per-voxel pass is a latency-bound dependent chain per batch,
-  // what matters is how many warps work on batches at the same time.
+  // Persistent grid, two CTAs per SM (one while a Mark kernel is to share the SMs, see STVL_SWEEP_CTAS_PER_SM_FUSED); small
+  // stores get one CTA per 128 leaves, so that a CTA's warps have leaves to share.
   static const int ctas_alone = env_int("STVL_SWEEP_CTAS_PER_SM", 2, 1, 2), ctas_shared = env_int("STVL_SWEEP_CTAS_PER_SM_FUSED", 2, 1, 2);
   const unsigned max_ctas = (unsigned)(sm_count * (share_sms ? ctas_shared : ctas_alone));
-  const unsigned long long groups = ((unsigned long long)leaf_slots_upper_bound + 31) / 32;
-  unsigned grid = (unsigned)std::min<unsigned long long>(max_ctas, std::max<unsigned long long>(groups, 1));
-  unsigned long long gpt = (groups + grid - 1) / grid;          // groups of 32 leaves per CTA if one tile pass were to cover everything
-  if (gpt < 1) gpt = 1;
-  if (gpt > (unsigned long long)kSweepWarps) gpt = kSweepWarps;
+  const unsigned long long want = ((unsigned long long)leaf_slots_upper_bound + 127) / 128;
+  const unsigned grid = (unsigned)std::min<unsigned long long>(max_ctas, std::max<unsigned long long>(want, 1));
   return launch_ex(sweep_kernel, grid, (unsigned)kSweepThreads, dyn, s, pdl, g, fp, frustums_dev, n_frustums, now, out, costmap_reset, (unsigned long long)costmap_bytes,
-                         costmap_value, (uint32_t)(gpt * 32));
+                         costmap_value);
 }
 
 }  // namespace stvl
