@@ -107,6 +107,19 @@ def main():
             if ok.any():
                 d = (b - a)[ok] / 1e3
                 print("     d(%s -> %s): median %.2f  p90 %.2f  max %.2f us" % (phases[ph - 1], phases[ph], np.median(d), np.percentile(d, 90), d.max()))
+    sw = tr[1]
+    used = sw[:, 0] > 0
+    if used.any():
+        nl = (sw[used, 5] & 0xFFFFFFFF).astype(np.int64)
+        nc = (sw[used, 5] >> 32).astype(np.int64)
+        tb = (sw[used, 3].astype(np.int64) - sw[used, 6].astype(np.int64)) / 1e3
+        ta = (sw[used, 6].astype(np.int64) - sw[used, 2].astype(np.int64)) / 1e3
+        print("sweep pass 0 per CTA: leaves queued for the warp pass  min %d median %d max %d (sum %d); columns queued  min %d median %d max %d (sum %d)"
+              % (nl.min(), np.median(nl), nl.max(), nl.sum(), nc.min(), np.median(nc), nc.max(), nc.sum()))
+        print("   re-arm -> end of column pass (A + B'): median %.2f p90 %.2f max %.2f us;  warp pass (B) + C: median %.2f p90 %.2f max %.2f us"
+              % (np.median(ta), np.percentile(ta, 90), ta.max(), np.median(tb), np.percentile(tb, 90), tb.max()))
+        order = np.argsort(-tb)[:8]
+        print("   slowest warp passes: " + ", ".join("%.1f us (%d leaves, %d columns)" % (tb[i], nl[i], nc[i]) for i in order))
     g.close()
 
 

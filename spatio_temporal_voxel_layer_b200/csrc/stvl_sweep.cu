@@ -12,12 +12,12 @@
 //      are prefetched into L2.
 //   B' one THREAD per queued column: 64 B of mark times, the plain decay test of .cpp:203-211 per voxel, the new mask byte,
 //      the column's survivor count; the leaf's new lower time bound is gathered in shared memory.
-//   B  one WARP per queued leaf, taken dynamically.  Lane l owns bit l of every 32-bit mask word, so the mark times of a
-//      word are one coalesced 256 B run and the survivors come back as one ballot — the new mask word.  The next word's
-//      times are requested before the current word is worked on.  Per voxel: the reference's exact arithmetic (decay model,
-//      first containing frustum in reading order, acceleration, strict <), rewrite of accelerated times, per-column survivor
-//      counts, optional lists; per leaf: frustum classification (one lane per frustum), new lower time bound, pruning.
-//   C  (after the next pass's barrier) the thread that queued a leaf's columns writes its new lower time bound or frees it.
+//   B  one WARP per (queued leaf, occupied 32-bit mask word), taken dynamically.  Lane l owns bit l of the word, so its mark
+//      times are one coalesced 256 B run and the survivors come back as one ballot — the new mask word.  Per voxel: the
+//      reference's exact arithmetic (decay model, first containing frustum in reading order, acceleration, strict <),
+//      rewrite of accelerated times, per-column survivor counts, optional lists; the leaf's frustum classification (one lane
+//      per frustum) is redone per word, its new lower time bound is gathered in shared memory like the columns'.
+//   C  (after the next pass's barrier) the thread that queued a leaf writes its new lower time bound or frees it.
 // Three sets of queues rotate, so a warp that runs out of work starts phase A of the next pass while the others finish.
 // No global work queue, no second launch, no grid-wide synchronisation: a leaf's whole sweep stays inside one CTA.
 #include <algorithm>
@@ -75,8 +75,9 @@ __device__ __forceinline__ bool leaf_may_expire(const GridView & g, double now, 
   return !(g.voxel_decay >= 0.0);
 }
 
-// leaf queue entry: pool slot of a leaf that needs the per-voxel pass | kTouched when a frustum may contain one of its voxels
-constexpr uint32_t kTouched = 0x80000000u;
+// leaf queue entry: pool slot (bits 0-31) | thread that owns the leaf in this pass (32-40) | which of its 16 mask words are
+// occupied (41-56) | kTouched when a frustum may contain one of its voxels.  The warps take (leaf, word) tasks from it.
+constexpr unsigned long long kTouched = 1ull << 57;
 // column queue entry: (thread that owns the leaf in this pass) << 14 | column << 8 | the column's mask byte
 constexpr int kColQueue = 4096;
 
@@ -112,7 +113,7 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
   // three work queues in rotation: tile pass t fills queue t % 3 in phase A and drains it in phase B; a warp that runs out
   // of phase-B work goes on to phase A of pass t + 1 (queue (t + 1) % 3) without waiting for the others, and queue
   // (t + 2) % 3 — drained in pass t - 1 — is re-armed meanwhile.  ONE CTA barrier per pass.
-  __shared__ uint32_t s_q[3][kSweepThreads];
+  __shared__ unsigned long long s_q[3][kSweepThreads];
   __shared__ unsigned int s_qn[3], s_qnext[3], s_cn[3], s_climit[3];
   __shared__ uint32_t s_part[kSweepWarps][kMaxFrustums / 32];
   __shared__ uint32_t s_full[kSweepWarps][kMaxFrustums / 32];
@@ -185,14 +186,14 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
   // bit p & 1: this thread queued the columns of a leaf in pass p and has not yet written the leaf's new bound (that happens
   // behind the NEXT pass's barrier, i.e. after this thread's phase A of that pass — hence two bits, and the leaf's slot is
   // kept in the parity-indexed shared arrays)
-  uint32_t col_pending = 0;
-  auto finish_columns = [&](uint32_t pb) {   // phase C
-    if ((col_pending >> pb) & 1u) {
+  uint32_t leaf_pending = 0;
+  auto finish_leaf = [&](uint32_t pb) {   // phase C
+    if ((leaf_pending >> pb) & 1u) {
       const uint32_t cslot = sh.lslot[pb][threadIdx.x];
       const unsigned long long m = sh.lmin[pb][threadIdx.x];
       if (m == kNoSurvivor) free_leaf(g, cslot);            // every voxel of the leaf was cleared: pruneGrid, .cpp:223
       else g.leaf_tmin[cslot] = ordered_value(m);           // exact lower bound again
-      col_pending &= ~(1u << pb);
+      leaf_pending &= ~(1u << pb);
     }
   };
   for (uint32_t pass = 0; pass < n_passes; ++pass, qi = qi == 2 ? 0 : qi + 1) {
@@ -201,7 +202,7 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
     {
       const uint32_t q = pass * kSweepThreads + threadIdx.x;
       const uint32_t slot = ((q >> 2) * gridDim.x + blockIdx.x) * 4 + (q & 3u);
-      uint32_t entry = 0;
+      unsigned long long entry = 0;
       bool queue_it = false;
       if (slot < n_slots) {
         const uint64_t key = g.leaf_key[slot];
@@ -252,7 +253,7 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
                   sh.lkey[pb][threadIdx.x] = key;
                   sh.lslot[pb][threadIdx.x] = slot;
                   sh.ltile[pb][threadIdx.x] = tile;
-                  col_pending |= 1u << pb;
+                  leaf_pending |= 1u << pb;
 #pragma unroll
                   for (int w = 0; w < 16; ++w) {
 #pragma unroll
@@ -266,8 +267,16 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
                 }
               }
               if (!as_columns) {
+                unsigned nz = 0;
+#pragma unroll
+                for (int w = 0; w < 16; ++w) nz |= wv[w] ? (1u << w) : 0u;
                 queue_it = true;
-                entry = slot | (touches ? kTouched : 0u);
+                entry = (unsigned long long)slot | ((unsigned long long)threadIdx.x << 32) | ((unsigned long long)nz << 41) | (touches ? kTouched : 0ull);
+                sh.lmin[pb][threadIdx.x] = kNoSurvivor;
+                sh.lkey[pb][threadIdx.x] = key;
+                sh.lslot[pb][threadIdx.x] = slot;
+                sh.ltile[pb][threadIdx.x] = tile;
+                leaf_pending |= 1u << pb;
               }
               // the leaf's mark times will be needed in phase B: pull the occupied 64 B column runs into L2 now
               const double * tb = g.leaf_time + (size_t)slot * kLeafVoxels;
@@ -330,7 +339,7 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
     const uint32_t n_items = s_qn[qi];
     const uint32_t n_cols_queued = min(s_cn[qi], s_climit[qi]);
     // ---- phase C of the previous pass: its columns have all been worked on ---------------------------------------------------
-    if (pass > 0) finish_columns(pb ^ 1u);
+    if (pass > 0) finish_leaf(pb ^ 1u);
     // ---- phase B': one thread per queued voxel column (leaves no frustum can touch): the decay test of .cpp:203-211 ----------
     for (uint32_t i = threadIdx.x; i < n_cols_queued; i += kSweepThreads) {
       const uint32_t it = sh.cq[qi][i];
@@ -376,26 +385,25 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
         atomicMin(&sh.lmin[pb][owner], ordered_bits(vmin));
       }
     }
-    // ---- phase B: one warp per queued leaf, taken dynamically.  Lane l owns bit l of every mask word: the 32 mark times of
-    // a word are one coalesced 256 B run, survivors come back as one ballot = the new mask word --------------------------------
+    if (pass == 0) { TRACE(1, 6); TRACE_VAL(1, 5, (unsigned long long)n_items | ((unsigned long long)n_cols_queued << 32)); }
+    // ---- phase B: one warp per (queued leaf, mask word), taken dynamically.  Lane l owns bit l of the word: its 32 mark times
+    // are one coalesced 256 B run, the survivors come back as one ballot = the new mask word -----------------------------------
     for (;;) {
-      uint32_t item = 0;
-      if (lane == 0) item = atomicAdd(&s_qnext[qi], 1u);
-      item = __shfl_sync(kFull, item, 0);
-      if (item >= n_items) break;
-      const uint32_t ent = s_q[qi][item];
-      const uint32_t bslot = ent & ~kTouched;
+      uint32_t task = 0;
+      if (lane == 0) task = atomicAdd(&s_qnext[qi], 1u);
+      task = __shfl_sync(kFull, task, 0);
+      if (task >= n_items * 16u) break;
+      const unsigned long long ent = s_q[qi][task >> 4];
+      const int w = (int)(task & 15u);
+      if (!((ent >> (41 + w)) & 1ull)) continue;   // an empty word of the leaf
+      const uint32_t bslot = (uint32_t)ent;
+      const uint32_t owner = (uint32_t)(ent >> 32) & 0x1FFu;
       const bool touched = (ent & kTouched) != 0;
-      const uint64_t key = g.leaf_key[bslot];
-      const uint32_t tile = g.leaf_tile[bslot];
-      const uint32_t mword = lane < 16 ? g.leaf_mask[(size_t)bslot * 16 + lane] : 0u;
-      const double * tb = g.leaf_time + (size_t)bslot * kLeafVoxels;
-      unsigned nz = __ballot_sync(kFull, mword != 0);
-      // first word's times are requested before anything else is looked at
-      int w = __ffs(nz) - 1;
-      nz &= nz - 1;
-      uint32_t m = __shfl_sync(kFull, mword, w & 15);
-      double v = ((m >> lane) & 1u) ? __ldcs(tb + w * 32 + (int)lane) : 0.0;
+      const uint32_t m = g.leaf_mask[(size_t)bslot * 16 + w];
+      const bool have = ((m >> lane) & 1u) != 0;
+      const double v = have ? __ldcs(g.leaf_time + (size_t)bslot * kLeafVoxels + w * 32 + (int)lane) : 0.0;
+      const uint64_t key = sh.lkey[pb][owner];
+      const uint32_t tile = sh.ltile[pb][owner];
       int bx, by, bz;
       unpack_leaf_key(key, bx, by, bz);
       // leaf-level culling: one lane per frustum
@@ -410,129 +418,116 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
         }
         __syncwarp();
       }
-      double vmin = CUDART_INF;   // smallest mark time among the leaf's survivors
-      uint32_t alive = 0;
-      unsigned long long * tc = reinterpret_cast<unsigned long long *>(g.tile_count + (size_t)tile * 64);
-      while (w >= 0) {
-        // request the next word's times, then work on this one
-        const int wn = __ffs(nz) - 1;
-        nz &= nz - 1;
-        const uint32_t mn = wn >= 0 ? __shfl_sync(kFull, mword, wn & 15) : 0u;
-        const double vn = ((mn >> lane) & 1u) ? __ldcs(tb + wn * 32 + (int)lane) : 0.0;
-
-        const bool have = ((m >> lane) & 1u) != 0;
-        const unsigned li = (unsigned)w * 32u + lane;
-        const int ix = bx * 8 + (int)(li >> 6), iy = by * 8 + (int)((li >> 3) & 7), iz = bz * 8 + (int)(li & 7);
-        bool cleared = false;
-        if (have) {
-          ++acc.swept;
-          // .cpp:167-169
-          const double t = __dsub_rn(now, v);
-          double base_dur;
-          bool amb = false;
-          if (g.decay_model == 0) base_dur = __dsub_rn(g.voxel_decay, t);
-          else if (g.decay_model == 1) base_dur = __dmul_rn(g.voxel_decay, exp(-t));
-          else base_dur = g.voxel_decay;
-          // .cpp:171-198: first containing frustum, in reading order, decides
-          int hit = -1;
-          if (any_cand) {
-            const double wx = index_to_world(ix, g.vs, g.half_vs), wy = index_to_world(iy, g.vs, g.half_vs), wz = index_to_world(iz, g.vs, g.half_vs);
-            for (int c = 0; c < n_chunks && hit < 0; ++c) {
-              const unsigned fm = s_full[warp][c];
-              unsigned cm = s_part[warp][c] | fm;
-              while (cm) {
-                const int b = __ffs(cm) - 1; cm &= cm - 1;
-                const int f = c * 32 + b;
-                bool in;
-                if ((fm >> b) & 1u) in = true;
-                else if (fr[f].type == 0) in = depth_is_inside(fr[f].p, wx, wy, wz);
-                else in = lidar_is_inside(fr[f].p, wx, wy, wz, amb);
-                if (in) { hit = f; break; }
-              }
-            }
-          }
-          if (hit >= 0) {
-            // .cpp:179-197; GetFrustumAcceleration .cpp:334-341 = ((1./6.)*factor) * ((t*t)*t)
-            const double accel = __dmul_rn(fr[hit].c16f, __dmul_rn(__dmul_rn(t, t), t));
-            const double tud = __dsub_rn(base_dur, accel);
-            if (g.decay_model == 1 && fabs(tud) <= 1e-12 * fmax(fabs(base_dur), fabs(accel))) amb = true;
-            if (tud < 0.) cleared = true;
-            else {
-              const double nv = __dsub_rn(v, accel);
-              if (__double_as_longlong(nv) != __double_as_longlong(v)) { g.leaf_time[(size_t)bslot * kLeafVoxels + li] = nv; ++acc.rewr; }
-              vmin = fmin(vmin, nv);
-            }
-          } else if (base_dur < 0.) {
-            cleared = true;   // .cpp:203-211
-          } else {
-            vmin = fmin(vmin, v);
-          }
-          if (cleared) {
-            ++acc.clear;
-            acc.min_x = min(acc.min_x, ix); acc.max_x = max(acc.max_x, ix);
-            acc.min_y = min(acc.min_y, iy); acc.max_y = max(acc.max_y, iy);
-          } else {
-            ++acc.surv;
-          }
-          if (amb) {
-            ++acc.amb;
-            if (out.ambiguous) {
-              const unsigned long long a = atomicAdd(&g.ctr->sw[g.sw_cur].n_ambiguous_out, 1ull);
-              if (a < out.ambiguous_cap) { out.ambiguous[3 * a] = ix; out.ambiguous[3 * a + 1] = iy; out.ambiguous[3 * a + 2] = iz; }
+      double vmin = CUDART_INF;   // smallest mark time among the word's survivors
+      const unsigned li = (unsigned)w * 32u + lane;
+      const int ix = bx * 8 + (int)(li >> 6), iy = by * 8 + (int)((li >> 3) & 7), iz = bz * 8 + (int)(li & 7);
+      bool cleared = false;
+      if (have) {
+        ++acc.swept;
+        // .cpp:167-169
+        const double t = __dsub_rn(now, v);
+        double base_dur;
+        bool amb = false;
+        if (g.decay_model == 0) base_dur = __dsub_rn(g.voxel_decay, t);
+        else if (g.decay_model == 1) base_dur = __dmul_rn(g.voxel_decay, exp(-t));
+        else base_dur = g.voxel_decay;
+        // .cpp:171-198: first containing frustum, in reading order, decides
+        int hit = -1;
+        if (any_cand) {
+          const double wx = index_to_world(ix, g.vs, g.half_vs), wy = index_to_world(iy, g.vs, g.half_vs), wz = index_to_world(iz, g.vs, g.half_vs);
+          for (int c = 0; c < n_chunks && hit < 0; ++c) {
+            const unsigned fm = s_full[warp][c];
+            unsigned cm = s_part[warp][c] | fm;
+            while (cm) {
+              const int b = __ffs(cm) - 1; cm &= cm - 1;
+              const int f = c * 32 + b;
+              bool in;
+              if ((fm >> b) & 1u) in = true;
+              else if (fr[f].type == 0) in = depth_is_inside(fr[f].p, wx, wy, wz);
+              else in = lidar_is_inside(fr[f].p, wx, wy, wz, amb);
+              if (in) { hit = f; break; }
             }
           }
         }
-        const unsigned cmk = __ballot_sync(kFull, cleared);
-        const uint32_t sm = m & ~cmk;                                    // the word's survivors = its new mask
-        if (cmk && lane == 0) g.leaf_mask[(size_t)bslot * 16 + w] = sm;   // this warp is the only writer of the leaf's mask
-        alive |= sm;
-        // PopulateCostmapAndPointcloud .cpp:242-250: _cost_map[(x,y)] += 1 per surviving voxel — the word holds four voxel
-        // columns, one per byte; lanes 0 and 1 each push a pair of adjacent u32 column counters as one 64-bit reduction
-        if (sm && tile != kOverflowSlot && lane < 2) {
-          uint32_t y = sm - ((sm >> 1) & 0x55555555u);
-          y = (y & 0x33333333u) + ((y >> 2) & 0x33333333u);
-          y = (y + (y >> 4)) & 0x0F0F0F0Fu;
-          y >>= 16 * lane;
-          const unsigned long long pair = (unsigned long long)(y & 0xFFu) | ((unsigned long long)((y >> 8) & 0xFFu) << 32);
-          if (pair) red_add_u64(tc + w * 2 + (int)lane, pair);
+        if (hit >= 0) {
+          // .cpp:179-197; GetFrustumAcceleration .cpp:334-341 = ((1./6.)*factor) * ((t*t)*t)
+          const double accel = __dmul_rn(fr[hit].c16f, __dmul_rn(__dmul_rn(t, t), t));
+          const double tud = __dsub_rn(base_dur, accel);
+          if (g.decay_model == 1 && fabs(tud) <= 1e-12 * fmax(fabs(base_dur), fabs(accel))) amb = true;
+          if (tud < 0.) cleared = true;
+          else {
+            const double nv = __dsub_rn(v, accel);
+            if (__double_as_longlong(nv) != __double_as_longlong(v)) { g.leaf_time[(size_t)bslot * kLeafVoxels + li] = nv; ++acc.rewr; }
+            vmin = nv;
+          }
+        } else if (base_dur < 0.) {
+          cleared = true;   // .cpp:203-211
+        } else {
+          vmin = v;
         }
-        // optional lists: warp-aggregated appends
-        if (out.points && sm) {   // PopulateCostmapAndPointcloud .cpp:234-240: Point32 = (float) voxel centre
-          unsigned long long b0 = 0;
-          if (lane == 0) b0 = atomicAdd(&g.ctr->sw[g.sw_cur].n_points_out, (unsigned long long)__popc(sm));
-          b0 = __shfl_sync(kFull, b0, 0);
-          if ((sm >> lane) & 1u) {
-            const unsigned long long o = b0 + __popc(sm & ((1u << lane) - 1u));
-            if (o < out.points_cap) {
-              out.points[3 * o] = (float)index_to_world(ix, g.vs, g.half_vs);
-              out.points[3 * o + 1] = (float)index_to_world(iy, g.vs, g.half_vs);
-              out.points[3 * o + 2] = (float)index_to_world(iz, g.vs, g.half_vs);
-            }
+        if (cleared) {
+          ++acc.clear;
+          acc.min_x = min(acc.min_x, ix); acc.max_x = max(acc.max_x, ix);
+          acc.min_y = min(acc.min_y, iy); acc.max_y = max(acc.max_y, iy);
+        } else {
+          ++acc.surv;
+        }
+        if (amb) {
+          ++acc.amb;
+          if (out.ambiguous) {
+            const unsigned long long a = atomicAdd(&g.ctr->sw[g.sw_cur].n_ambiguous_out, 1ull);
+            if (a < out.ambiguous_cap) { out.ambiguous[3 * a] = ix; out.ambiguous[3 * a + 1] = iy; out.ambiguous[3 * a + 2] = iz; }
           }
         }
-        if (out.cleared && cmk) {   // cleared_cells.insert, .cpp:213-215
-          unsigned long long b0 = 0;
-          if (lane == 0) b0 = atomicAdd(&g.ctr->sw[g.sw_cur].n_cleared_out, (unsigned long long)__popc(cmk));
-          b0 = __shfl_sync(kFull, b0, 0);
-          if (cleared) {
-            const unsigned long long o = b0 + __popc(cmk & ((1u << lane) - 1u));
-            if (o < out.cleared_cap) { out.cleared[2 * o] = ix; out.cleared[2 * o + 1] = iy; }
-          }
-        }
-        w = wn; m = mn; v = vn;
       }
-      // the leaf's lower time bound = minimum over its survivors; a leaf with none goes back to the pool (pruneGrid, .cpp:223)
+      const unsigned cmk = __ballot_sync(kFull, cleared);
+      const uint32_t sm = m & ~cmk;                                    // the word's survivors = its new mask
+      if (cmk && lane == 0) g.leaf_mask[(size_t)bslot * 16 + w] = sm;   // this warp is the only writer of the word
+      // PopulateCostmapAndPointcloud .cpp:242-250: _cost_map[(x,y)] += 1 per surviving voxel — the word holds four voxel
+      // columns, one per byte; lanes 0 and 1 each push a pair of adjacent u32 column counters as one 64-bit reduction
+      if (sm && tile != kOverflowSlot && lane < 2) {
+        unsigned long long * tc = reinterpret_cast<unsigned long long *>(g.tile_count + (size_t)tile * 64);
+        uint32_t y = sm - ((sm >> 1) & 0x55555555u);
+        y = (y & 0x33333333u) + ((y >> 2) & 0x33333333u);
+        y = (y + (y >> 4)) & 0x0F0F0F0Fu;
+        y >>= 16 * lane;
+        const unsigned long long pair = (unsigned long long)(y & 0xFFu) | ((unsigned long long)((y >> 8) & 0xFFu) << 32);
+        if (pair) red_add_u64(tc + w * 2 + (int)lane, pair);
+      }
+      // optional lists: warp-aggregated appends
+      if (out.points && sm) {   // PopulateCostmapAndPointcloud .cpp:234-240: Point32 = (float) voxel centre
+        unsigned long long b0 = 0;
+        if (lane == 0) b0 = atomicAdd(&g.ctr->sw[g.sw_cur].n_points_out, (unsigned long long)__popc(sm));
+        b0 = __shfl_sync(kFull, b0, 0);
+        if ((sm >> lane) & 1u) {
+          const unsigned long long o = b0 + __popc(sm & ((1u << lane) - 1u));
+          if (o < out.points_cap) {
+            out.points[3 * o] = (float)index_to_world(ix, g.vs, g.half_vs);
+            out.points[3 * o + 1] = (float)index_to_world(iy, g.vs, g.half_vs);
+            out.points[3 * o + 2] = (float)index_to_world(iz, g.vs, g.half_vs);
+          }
+        }
+      }
+      if (out.cleared && cmk) {   // cleared_cells.insert, .cpp:213-215
+        unsigned long long b0 = 0;
+        if (lane == 0) b0 = atomicAdd(&g.ctr->sw[g.sw_cur].n_cleared_out, (unsigned long long)__popc(cmk));
+        b0 = __shfl_sync(kFull, b0, 0);
+        if (cleared) {
+          const unsigned long long o = b0 + __popc(cmk & ((1u << lane) - 1u));
+          if (o < out.cleared_cap) { out.cleared[2 * o] = ix; out.cleared[2 * o + 1] = iy; }
+        }
+      }
+      // the word's share of the leaf's new lower time bound (phase C turns the minimum into the bound, or frees the leaf)
+      if (sm) {
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) vmin = fmin(vmin, __shfl_xor_sync(kFull, vmin, d));
-      if (lane == 0) {
-        if (!alive) free_leaf(g, bslot);
-        else g.leaf_tmin[bslot] = vmin;
+        for (int d = 16; d > 0; d >>= 1) vmin = fmin(vmin, __shfl_xor_sync(kFull, vmin, d));
+        if (lane == 0) atomicMin(&sh.lmin[pb][owner], ordered_bits(vmin));
       }
     }
   }
   if (n_passes > 0) {   // phase C of the last pass
     __syncthreads();
-    finish_columns((n_passes - 1) & 1u);
+    finish_leaf((n_passes - 1) & 1u);
   }
   TRACE(1, 3);
 
