@@ -1,2 +1,2 @@
-bash profiles/gpu_quick.sh q7
-STVL_B200_LIB=spatio_temporal_voxel_layer_b200/libstvl_b200_trace.so timeout 300 python profiles/trace_phases.py --staged 2>&1 | grep -v "mark_kernel" | grep -B1 -A14 "sweep_kernel\|sweep pass" | cut -c1-330
+bash profiles/gpu_quick.sh q8
+STVL_B200_LIB=spatio_temporal_voxel_layer_b200/libstvl_b200_trace.so timeout 300 python profiles/trace_phases.py --staged 2>&1 | grep -A12 "sweep pass" | cut -c1-330

@@ -118,6 +118,15 @@ def main():
               % (nl.min(), np.median(nl), nl.max(), nl.sum(), nc.min(), np.median(nc), nc.max(), nc.sum()))
         print("   re-arm -> end of column pass (A + B'): median %.2f p90 %.2f max %.2f us;  warp pass (B) + C: median %.2f p90 %.2f max %.2f us"
               % (np.median(ta), np.percentile(ta, 90), ta.max(), np.median(tb), np.percentile(tb, 90), tb.max()))
+        x = tr[2]
+        if (x[:, 0] > 0).any():
+            ok = used & (x[:, 0] > 0) & (x[:, 1] > 0) & (x[:, 2] > 0)
+            d0 = (x[ok, 0].astype(np.int64) - sw[ok, 2].astype(np.int64)) / 1e3
+            d1 = (x[ok, 1].astype(np.int64) - x[ok, 0].astype(np.int64)) / 1e3
+            d2 = (x[ok, 2].astype(np.int64) - x[ok, 1].astype(np.int64)) / 1e3
+            d3 = (sw[ok, 6].astype(np.int64) - x[ok, 2].astype(np.int64)) / 1e3
+            for nm, d in (("re-arm -> headers loaded (warp 0)", d0), ("headers -> phase A done (warp 0)", d1), ("phase A done -> barrier passed", d2), ("barrier -> column pass done (warp 0)", d3)):
+                print("   %-40s median %.2f p90 %.2f max %.2f us" % (nm, np.median(d), np.percentile(d, 90), d.max()))
         order = np.argsort(-tb)[:8]
         print("   slowest warp passes: " + ", ".join("%.1f us (%d leaves, %d columns)" % (tb[i], nl[i], nc[i]) for i in order))
     g.close()

@@ -100,6 +100,7 @@ struct SweepShared {
   unsigned long long lkey[2][kSweepThreads];  //   surviving mark times (ordered_bits), key, slot, tile
   uint32_t lslot[2][kSweepThreads];
   uint32_t ltile[2][kSweepThreads];
+  uint32_t lcls[2][kSweepThreads];            // frustum classes of the leaf, two bits per frustum (sets of up to 16 frustums)
 };
 
 __global__ void __launch_bounds__(kSweepThreads, 2)
@@ -175,6 +176,7 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
   }
   const bool force_full = out.points != nullptr;   // pub_voxels needs every survivor's coordinates
   const int n_chunks = (n_frustums + 31) >> 5;
+  const bool cache_classes = n_frustums <= 16;   // phase A classifies a leaf against every frustum once, the warp pass reuses it
   SweepAcc acc;
   TRACE(1, 2);
 
@@ -212,6 +214,7 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
         uint4 mw[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) mw[q] = mp[q];
+        if (pass == 0) TRACE(2, 0);
         if (key != kEmptyKey) {
           uint32_t any = 0;
 #pragma unroll
@@ -222,15 +225,18 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
             // can a frustum contain a voxel centre of this leaf?  (bounding box, then the leaf's bounding sphere against the
             // plane set / hourglass)
             bool touches = force_full;
+            uint32_t classes = 0;   // (small frustum sets: every frustum's class, kept for the warp pass)
             {
               int bx, by, bz;
               unpack_leaf_key(key, bx, by, bz);
               const int x0 = bx * 8, y0 = by * 8, z0 = bz * 8;
-              for (int f = 0; f < n_frustums && !touches; ++f) {
+              for (int f = 0; f < n_frustums && (cache_classes || !touches); ++f) {
                 const DevFrustum & F = fr[f];
                 if (F.type < 0) continue;
                 if (F.cull && (x0 + 7 < F.lo[0] || x0 > F.hi[0] || y0 + 7 < F.lo[1] || y0 > F.hi[1] || z0 + 7 < F.lo[2] || z0 > F.hi[2])) continue;
-                touches = classify_leaf(F, bx, by, bz, g.vs, g.half_vs) != 0;
+                const int cls = classify_leaf(F, bx, by, bz, g.vs, g.half_vs);
+                touches = touches || cls != 0;
+                if (cache_classes) classes |= (uint32_t)cls << (2 * f);
               }
             }
             if (touches || leaf_may_expire(g, now, tmin)) {
@@ -276,6 +282,7 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
                 sh.lkey[pb][threadIdx.x] = key;
                 sh.lslot[pb][threadIdx.x] = slot;
                 sh.ltile[pb][threadIdx.x] = tile;
+                sh.lcls[pb][threadIdx.x] = classes;
                 leaf_pending |= 1u << pb;
               }
               // the leaf's mark times will be needed in phase B: pull the occupied 64 B column runs into L2 now
@@ -331,7 +338,9 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
         if (queue_it) s_q[qi][base + __popc(qm & ((1u << lane) - 1u))] = entry;
       }
     }
+    if (pass == 0) TRACE(2, 1);
     __syncthreads();
+    if (pass == 0) TRACE(2, 2);
     if (threadIdx.x == 0) {   // re-arm the queues of pass t + 2 (those of pass t - 1: everybody is done with them)
       const uint32_t qz = qi == 0 ? 2 : qi - 1;
       s_qn[qz] = 0; s_qnext[qz] = 0; s_cn[qz] = 0; s_climit[qz] = kColQueue;
@@ -350,17 +359,25 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
       const double tv[8] = {t01.x, t01.y, t23.x, t23.y, t45.x, t45.y, t67.x, t67.y};
       uint32_t nb = byte;
       double vmin = CUDART_INF;
+      if (g.decay_model == 0) {   // linear: duration = decay - (now - v), .cpp:167-169 / :320-324
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (!((byte >> k) & 1u)) continue;
-        const double v = tv[k];
-        const double t = __dsub_rn(now, v);   // .cpp:167-169
-        double base_dur;
-        if (g.decay_model == 0) base_dur = __dsub_rn(g.voxel_decay, t);
-        else if (g.decay_model == 1) base_dur = __dmul_rn(g.voxel_decay, exp(-t));
-        else base_dur = g.voxel_decay;
-        if (base_dur < 0.) nb &= ~(1u << k);
-        else vmin = fmin(vmin, v);
+        for (int k = 0; k < 8; ++k) {
+          const bool expired = __dsub_rn(g.voxel_decay, __dsub_rn(now, tv[k])) < 0.;
+          if ((byte >> k) & 1u) {
+            if (expired) nb &= ~(1u << k);
+            else vmin = fmin(vmin, tv[k]);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) {
+          if (!((byte >> k) & 1u)) continue;
+          const double v = tv[k];
+          const double t = __dsub_rn(now, v);
+          const double base_dur = g.decay_model == 1 ? __dmul_rn(g.voxel_decay, exp(-t)) : g.voxel_decay;
+          if (base_dur < 0.) nb &= ~(1u << k);
+          else vmin = fmin(vmin, v);
+        }
       }
       const unsigned n_in = __popc(byte), n_left = __popc(nb);
       acc.swept += n_in; acc.surv += n_left; acc.clear += n_in - n_left;
@@ -409,9 +426,10 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
       // leaf-level culling: one lane per frustum
       unsigned any_cand = 0;
       if (touched) {
+        const uint32_t classes = sh.lcls[pb][owner];
         for (int c = 0; c < n_chunks; ++c) {
           const int f = c * 32 + (int)lane;
-          const int cls = f < n_frustums ? classify_leaf(fr[f], bx, by, bz, g.vs, g.half_vs) : 0;
+          const int cls = f >= n_frustums ? 0 : cache_classes ? (int)((classes >> (2 * (f & 15))) & 3u) : classify_leaf(fr[f], bx, by, bz, g.vs, g.half_vs);
           const unsigned pm = __ballot_sync(kFull, cls == 1), fm = __ballot_sync(kFull, cls == 2);
           if (lane == 0) { s_part[warp][c] = pm; s_full[warp][c] = fm; }
           any_cand |= pm | fm;
