@@ -735,6 +735,7 @@ CostmapDev to_dev(const stvl_costmap_params_t & p)
 {
   CostmapDev d;
   d.origin_x = p.origin_x; d.origin_y = p.origin_y; d.resolution = p.resolution;
+  d.inv_resolution = 1.0 / p.resolution;
   d.size_x = p.size_x; d.size_y = p.size_y; d.mark_threshold = p.mark_threshold;
   d.default_value = p.default_value; d.lethal = p.lethal_value;
   return d;

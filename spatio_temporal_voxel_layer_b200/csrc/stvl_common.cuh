@@ -212,12 +212,24 @@ __device__ __forceinline__ void trace_stamp(int kernel, int phase)
 // =====================================================================================
 // Costmap — reference spatio_temporal_voxel_layer.cpp:699-718 (grid loop) on the tile counts
 // =====================================================================================
+// One coordinate of nav2 Costmap2D::worldToMap (external): (unsigned)((w - origin) / resolution), w >= origin.  The division
+// is the reference's; a product with the cached 1/resolution decides it wherever that is safe: the product differs from the
+// correctly rounded quotient by less than 5e-16 relative, i.e. by less than 1.1e-6 for cell indices below 2^31, so unless it
+// lies within 1e-5 of an integer both truncate to the same cell (with the origin a multiple of the resolution the product
+// sits half a cell away from the integers for every voxel centre).  Larger quotients and near-integers take the division.
+__device__ __forceinline__ unsigned map_cell(double d, double resolution, double inv_resolution)
+{
+  const double q = __dmul_rn(d, inv_resolution);
+  const double r = rint(q);
+  if (q < 2147483648.0 && fabs(__dsub_rn(q, r)) > 1e-5) return __double2uint_rz(q);
+  return __double2uint_rz(__ddiv_rn(d, resolution));
+}
 // nav2 Costmap2D::worldToMap (external): wx >= origin, (unsigned)((wx-origin)/resolution) < size
 __device__ __forceinline__ bool world_to_map(double wx, double wy, const CostmapDev & p, unsigned & mx, unsigned & my)
 {
   if (wx < p.origin_x || wy < p.origin_y) return false;
-  mx = __double2uint_rz(__ddiv_rn(__dsub_rn(wx, p.origin_x), p.resolution));
-  my = __double2uint_rz(__ddiv_rn(__dsub_rn(wy, p.origin_y), p.resolution));
+  mx = map_cell(__dsub_rn(wx, p.origin_x), p.resolution, p.inv_resolution);
+  my = map_cell(__dsub_rn(wy, p.origin_y), p.resolution, p.inv_resolution);
   return mx < p.size_x && my < p.size_y;
 }
 

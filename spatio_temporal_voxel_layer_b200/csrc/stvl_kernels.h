@@ -19,6 +19,7 @@ struct SweepOutputs {
 
 struct CostmapDev {
   double origin_x, origin_y, resolution;
+  double inv_resolution;     // 1 / resolution (rounded): shortcut of worldToMap's division, see map_cell
   uint32_t size_x, size_y;
   int32_t mark_threshold;
   uint8_t default_value, lethal;
