@@ -22,6 +22,7 @@ os.environ.setdefault("STVL_B200_LIB", os.path.join(ROOT, "spatio_temporal_voxel
 PHASES = {
     0: ("mark_kernel", ["entry", "setup done", "chunk0 consumed", "chunks done", "leaves resolved", "flushed", "exit"]),
     1: ("sweep_kernel", ["entry", "predecessor done", "re-arm issued", "leaves done", "published"]),
+    3: ("costmap pass", ["entry", "tile_n read", "tiles done (thread 0)", "CTA done", "ticket taken"]),
 }
 
 
@@ -85,7 +86,7 @@ def main():
     L.stvl_debug_trace.argtypes = [C.c_void_p, C.c_size_t]
     rc = L.stvl_debug_trace(tr.ctypes.data_as(C.c_void_p), tr.nbytes)
     assert rc == 0, rc
-    order = [1, 0]   # stream order inside a cycle
+    order = [1, 0, 3]   # stream order inside a cycle
     for k in order:
         name, phases = PHASES[k]
         used = tr[k, :, 0] > 0

@@ -510,18 +510,29 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
   // costmap pass (fused cycle), all 32 warps: it needs the sweep's column counts, nothing of Mark
   // =====================================================================================================================
   if constexpr (kCostmap) {
+    TRACE(3, 0);
     pdl_wait();
     const uint32_t n_tiles = min(ld_volatile_u32(&g.ctr->tile_n), g.tile_capacity);
-    constexpr uint32_t kCmBatch = 4;
+    TRACE(3, 1);
     constexpr uint32_t kCmWarps = kMarkThreads / 32;
-    const uint32_t cw = blockIdx.x * kCmWarps + warp;
+    const uint32_t cw = blockIdx.x * kCmWarps + warp, n_cw = gridDim.x * kCmWarps;
     unsigned cm_n = 0;
     int cm_mnx = INT_MAX, cm_mny = INT_MAX, cm_mxx = INT_MIN, cm_mxy = INT_MIN;
-    for (uint32_t t0 = cw * kCmBatch; t0 < n_tiles; t0 += gridDim.x * kCmWarps * kCmBatch)
-      costmap_tile_batch<(int)kCmBatch, kCmBits>(g, cm, costmap, t0, n_tiles, lane, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy);
+    // tiles per warp and round trip: as few as keep every warp of the grid busy (the pass is a chain of dependent round
+    // trips, not a stream)
+    if (n_tiles <= n_cw) {
+      if (cw < n_tiles) costmap_tile_batch<1, kCmBits>(g, cm, costmap, cw, n_tiles, lane, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy);
+    } else if (n_tiles <= 2 * n_cw) {
+      if (cw * 2 < n_tiles) costmap_tile_batch<2, kCmBits>(g, cm, costmap, cw * 2, n_tiles, lane, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy);
+    } else {
+      for (uint32_t t0 = cw * 4; t0 < n_tiles; t0 += n_cw * 4)
+        costmap_tile_batch<4, kCmBits>(g, cm, costmap, t0, n_tiles, lane, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy);
+    }
+    TRACE(3, 2);
     costmap_warp_accumulate(g.ctr, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy);
     if (lane == 0) __threadfence();   // this warp's accumulator updates are visible before the CTA takes its ticket
     named_bar_sync(2, kMarkThreads);
+    TRACE(3, 3);
     if (threadIdx.x == 0) {
       __threadfence();
       if (atomicAdd(&g.ctr->cm_ticket, 1u) == gridDim.x - 1) {   // last CTA publishes the result and re-arms the accumulators
@@ -530,6 +541,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
         g.ctr->cm_ticket = 0;
         __threadfence();
       }
+      TRACE(3, 4);
     }
   }
 }
