@@ -117,8 +117,14 @@ def make_workload(rank, world):
 
 
 def costmap_geometry(w, world):
+    """Costmap parameters of the run.  N > 1: ONE costmap over all slabs, with slab 0's origin — identical on every rank (the
+    ranks' cell intervals of the merge are derived from it, and the exchange sizes must agree)."""
     cp = w.costmap_params()
-    if world > 1:   # one costmap over all slabs (origin of slab 0's)
+    if world > 1:
+        from spatio_temporal_voxel_layer_b200 import synth
+        slab0 = synth.retail_scene(size=75.0, seed=7, origin=(SLAB_PITCH / 2, 0.0))
+        cp["origin_x"] = float(slab0.lo[:, 0].min() - 1.0)
+        cp["origin_y"] = float(slab0.lo[:, 1].min() - 1.0)
         cp["size_x"] = int(1600 + (world - 1) * SLAB_PITCH / cp["resolution"])
     return cp
 
@@ -847,6 +853,9 @@ def bench_ours(args):
 
 
 def main():
+    if os.environ.get("STVL_BENCH_WATCHDOG"):   # debugging aid: dump every thread's Python stack and exit if the run takes too long
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["STVL_BENCH_WATCHDOG"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

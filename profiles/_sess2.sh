@@ -1,6 +1,5 @@
-nvidia-smi --query-gpu=name --format=csv,noheader | head -4
-timeout 600 python -m pytest tests/test_multi_gpu.py -m gpu -q --timeout 300 -p no:cacheprovider 2>&1 | tail -5
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu-baseline --no-sensitivity --no-other-configs > gpurun_out/m2_bench.json 2> gpurun_out/m2_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/m2_bench.err | cut -c1-300
+STVL_BENCH_WATCHDOG=240 timeout 280 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu-baseline --no-sensitivity --no-other-configs > gpurun_out/m2_bench.json 2> gpurun_out/m2_bench.err; echo "bench rc=$?"
+grep -v "^$\|OMP_NUM\|\*\*\*\*\|frame #" gpurun_out/m2_bench.err | grep -A12 "Timeout\|Error\|error" | head -40 | cut -c1-200
 python - <<PY
 import json
 try:

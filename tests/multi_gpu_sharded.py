@@ -12,6 +12,25 @@ sys.path.insert(0, ROOT)
 import spatio_temporal_voxel_layer_b200 as stvl  # noqa: E402
 
 
+FAILED = []
+
+
+def check(label, cond):
+    """Record a failed comparison (reported by rank 0 at the end) and return whether it held."""
+    if not cond:
+        FAILED.append(label)
+    return bool(cond)
+
+
+def voxel_totals(g, ref, rank, label):
+    """Active voxels summed over the shards against the unsharded grid's (a failed check names the stage)."""
+    n = torch.tensor([g.active_count()], device="cuda")
+    dist.all_reduce(n)
+    if rank == 0:
+        return check("voxel total after %s: shards %d, unsharded %d" % (label, int(n.item()), ref.active_count()), int(n.item()) == ref.active_count())
+    return True
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
@@ -51,22 +70,23 @@ def main():
             g.costmap_sharded_device(pc, cm.data_ptr(), root=0, count_bytes=(4, 1, 0)[cyc], pipelined=False)
             g.synchronize()
             if rank == 0:
-                ok = ok and torch.equal(cm, expected[cyc]) and int((cm == 254).sum()) > 1000
+                ok = check("window merge, blocking, cycle %d" % cyc, torch.equal(cm, expected[cyc]) and int((cm == 254).sum()) > 1000) and ok
         else:
             if cyc == 5:   # mode switch: drain the count-window pipeline first
                 g.costmap_sharded_flush(params, cm.data_ptr(), root=0)
                 g.synchronize()
                 if rank == 0:
-                    ok = ok and torch.equal(cm, expected[4])
+                    ok = check("window pipeline drain", torch.equal(cm, expected[4])) and ok
             g.costmap_sharded_device(params, cm.data_ptr(), root=0, count_bytes=1 if cyc < 5 else 0, pipelined=True)
             g.synchronize()
             if rank == 0 and cyc in (4, 6, 7):   # the bytes of cycle k arrive with call k+1
-                ok = ok and torch.equal(cm, expected[cyc - 1])
+                ok = check("window / bytes merge, pipelined, cycle %d" % cyc, torch.equal(cm, expected[cyc - 1])) and ok
         now += 1.0
     g.costmap_sharded_flush(params, cm.data_ptr(), root=0)
     g.synchronize()
     if rank == 0:
-        ok = ok and torch.equal(cm, expected[n_cycles - 1])
+        ok = check("final flush of the merge", torch.equal(cm, expected[n_cycles - 1])) and ok
+    ok = voxel_totals(g, ref, rank, "the window merges") and ok
     # fused sharded cycles (stvl_update_cycle_sharded_device): sweep + Mark of a device-resident cloud + costmap pass into
     # the reduce window + NCCL merge, blocking then pipelined, against the unsharded grid's fused cycle
     cloud = np.zeros((200000, 4), np.float32)
@@ -86,14 +106,14 @@ def main():
         g.synchronize()
         if rank == 0:
             if cyc < 2:
-                ok = ok and torch.equal(cm, fused_expected[cyc]) and int((cm == 254).sum()) > 1000
+                ok = check("fused sharded cycle, blocking, %d" % cyc, torch.equal(cm, fused_expected[cyc]) and int((cm == 254).sum()) > 1000) and ok
             elif cyc == 3:
-                ok = ok and torch.equal(cm, fused_expected[2])
+                ok = check("fused sharded cycle, pipelined", torch.equal(cm, fused_expected[2])) and ok
     g.costmap_sharded_flush(params, cm.data_ptr(), root=0)
     g.synchronize()
     if rank == 0:
-        ok = ok and torch.equal(cm, fused_expected[3])
-        n_ref = ref.active_count()
+        ok = check("fused sharded cycle, flush", torch.equal(cm, fused_expected[3])) and ok
+    ok = voxel_totals(g, ref, rank, "the fused sharded cycles") and ok
     # the pipelined host-buffer cycle on sharded handles (stvl_update_cycle_async): every rank uploads the same host cloud, keeps
     # its own slabs, the cells are merged into rank 0 inside the cycle and rank 0 reads the merged bytes back
     host_cloud = torch.from_numpy(cloud).pin_memory()
@@ -112,18 +132,18 @@ def main():
         if cyc >= 1:
             g.update_cycle_wait(tickets[cyc - 1])
             if rank == 0:
-                ok = ok and np.array_equal(host_out[(cyc - 1) % 2], async_expected[cyc - 1])
+                ok = check("async host cycle %d" % (cyc - 1), np.array_equal(host_out[(cyc - 1) % 2], async_expected[cyc - 1])) and ok
     g.update_cycle_wait(tickets[-1])
     if rank == 0:
-        ok = ok and np.array_equal(host_out[0], async_expected[2]) and int((async_expected[2] == 254).sum()) > 1000
+        ok = check("async host cycle, last", np.array_equal(host_out[0], async_expected[2]) and int((async_expected[2] == 254).sum()) > 1000) and ok
+    ok = voxel_totals(g, ref, rank, "the pipelined host-buffer cycles") and ok   # the shards together hold exactly the unsharded grid's voxels
     n_local = torch.tensor([g.active_count()], device="cuda")
     dist.all_reduce(n_local)
-    if rank == 0:
-        ok = ok and int(n_local.item()) == n_ref          # the shards together hold exactly the unsharded grid's voxels
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     if rank == 0:
-        print("MULTI_GPU_OK" if bool(flag.item()) else "MULTI_GPU_MISMATCH", "ranks", world, "voxels", int(n_local.item()))
+        print("MULTI_GPU_OK" if bool(flag.item()) else "MULTI_GPU_MISMATCH", "ranks", world, "voxels", int(n_local.item()),
+              ("failed checks: " + ", ".join(FAILED)) if FAILED else "")
     g.comm_destroy()
     g.close()
     if ref is not None:
