@@ -33,13 +33,28 @@ extern "C" int stvl_debug_trace(void * out, size_t bytes)
 }
 #endif
 
-// block reduction of the marked-cell count / bounds into the device accumulators; the last CTA of the grid publishes
-__device__ __forceinline__ void costmap_reduce_and_publish(Counters * c, unsigned n, int mnx, int mny, int mxx, int mxy)
+// block reduction of the marked-cell count / bounds (warp shuffle, shared memory, then ONE set of global atomics per CTA:
+// a thousand warps updating the same five words would serialise in L2); the last CTA of the grid publishes.
+// s_cm: five ints of shared memory, initialised {0, INT_MAX, INT_MAX, INT_MIN, INT_MIN} before the CTA's previous barrier.
+__device__ __forceinline__ void costmap_reduce_and_publish(Counters * c, int * s_cm, unsigned n, int mnx, int mny, int mxx, int mxy)
 {
-  costmap_warp_accumulate(c, n, mnx, mny, mxx, mxy);
-  if ((threadIdx.x & 31) == 0) __threadfence();   // every warp's accumulator updates are visible before the CTA takes its ticket
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    n += __shfl_xor_sync(kFull, n, d);
+    mnx = min(mnx, __shfl_xor_sync(kFull, mnx, d)); mny = min(mny, __shfl_xor_sync(kFull, mny, d));
+    mxx = max(mxx, __shfl_xor_sync(kFull, mxx, d)); mxy = max(mxy, __shfl_xor_sync(kFull, mxy, d));
+  }
+  if ((threadIdx.x & 31) == 0 && n) {
+    atomicAdd(&s_cm[0], (int)n);
+    atomicMin(&s_cm[1], mnx); atomicMin(&s_cm[2], mny); atomicMax(&s_cm[3], mxx); atomicMax(&s_cm[4], mxy);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (s_cm[0]) {
+      atomicAdd(&c->cm_acc.n_marked, (unsigned long long)s_cm[0]);
+      atomicMin(&c->cm_acc.mk_min_x, s_cm[1]); atomicMin(&c->cm_acc.mk_min_y, s_cm[2]);
+      atomicMax(&c->cm_acc.mk_max_x, s_cm[3]); atomicMax(&c->cm_acc.mk_max_y, s_cm[4]);
+    }
     __threadfence();
     if (atomicAdd(&c->cm_ticket, 1u) == gridDim.x - 1) {
       __threadfence();
@@ -58,6 +73,8 @@ template <bool kBits>
 __global__ void __launch_bounds__(256) costmap_kernel(const GridView g, const CostmapDev p, uint8_t * __restrict__ costmap)
 {
   const unsigned lane = threadIdx.x & 31;
+  __shared__ int s_cm[5];
+  if (threadIdx.x == 0) { s_cm[0] = 0; s_cm[1] = s_cm[2] = INT_MAX; s_cm[3] = s_cm[4] = INT_MIN; }
   TRACE(3, 0);
   // (fused cycle with a small Mark grid: launched programmatically between the leaf pass and Mark — the column counts are
   // ready when the sweep is, and Mark's cloud streaming overlaps this kernel as well; no-ops otherwise)
@@ -76,7 +93,7 @@ __global__ void __launch_bounds__(256) costmap_kernel(const GridView g, const Co
   }
   __syncthreads();
   TRACE(3, 2);
-  costmap_reduce_and_publish(g.ctr, n, mnx, mny, mxx, mxy);
+  costmap_reduce_and_publish(g.ctr, s_cm, n, mnx, mny, mxx, mxy);
   TRACE(3, 3);
 }
 
@@ -123,6 +140,8 @@ __global__ void __launch_bounds__(256) costmap_from_dense_kernel(const GridView 
                                                                  uint32_t nx, uint32_t ny, const CostmapDev p, uint8_t * __restrict__ costmap)
 {
   const unsigned long long total = (unsigned long long)nx * ny;
+  __shared__ int s_cm[5];
+  if (threadIdx.x == 0) { s_cm[0] = 0; s_cm[1] = s_cm[2] = INT_MAX; s_cm[3] = s_cm[4] = INT_MIN; }
   unsigned n = 0;
   int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
@@ -135,7 +154,8 @@ __global__ void __launch_bounds__(256) costmap_from_dense_kernel(const GridView 
       ++n; mnx = min(mnx, ix); mny = min(mny, iy); mxx = max(mxx, ix); mxy = max(mxy, iy);
     }
   }
-  costmap_reduce_and_publish(g.ctr, n, mnx, mny, mxx, mxy);
+  __syncthreads();
+  costmap_reduce_and_publish(g.ctr, s_cm, n, mnx, mny, mxx, mxy);
 }
 
 // typed variants for the in-library sharded merge (u8 windows move 4x fewer bytes over NVLink than u32 ones; a column
@@ -161,6 +181,8 @@ __global__ void __launch_bounds__(256) costmap_from_window_kernel(const GridView
                                                                   uint32_t nx, uint32_t ny, const CostmapDev p, uint8_t * __restrict__ costmap)
 {
   const unsigned long long total = (unsigned long long)nx * ny;
+  __shared__ int s_cm[5];
+  if (threadIdx.x == 0) { s_cm[0] = 0; s_cm[1] = s_cm[2] = INT_MAX; s_cm[3] = s_cm[4] = INT_MIN; }
   unsigned n = 0;
   int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
@@ -173,7 +195,8 @@ __global__ void __launch_bounds__(256) costmap_from_window_kernel(const GridView
       ++n; mnx = min(mnx, ix); mny = min(mny, iy); mxx = max(mxx, ix); mxy = max(mxy, iy);
     }
   }
-  costmap_reduce_and_publish(g.ctr, n, mnx, mny, mxx, mxy);
+  __syncthreads();
+  costmap_reduce_and_publish(g.ctr, s_cm, n, mnx, mny, mxx, mxy);
 }
 
 // =====================================================================================

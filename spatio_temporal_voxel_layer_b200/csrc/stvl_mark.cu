@@ -178,6 +178,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
   __shared__ unsigned int s_qn;            // queued voxels (may run past kMarkQueue: the excess went straight to the store)
   __shared__ unsigned int s_flushes;       // early flushes done (the producer requests at most one at a time)
   __shared__ unsigned int s_drop[2];
+  __shared__ int s_cm[5];                  // fused costmap pass: marked cells and their bounds, gathered per CTA
 
   TRACE(0, 0);
   const unsigned lane = threadIdx.x & 31;
@@ -258,6 +259,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
       for (int s = 0; s < n_stages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kMarkConsumerWarps); }
       mbar_fence_init();
       s_qn = 0; s_flushes = 0; s_drop[0] = s_drop[1] = 0;
+      s_cm[0] = 0; s_cm[1] = s_cm[2] = INT_MAX; s_cm[3] = s_cm[4] = INT_MIN;
       policy = l2_evict_first_policy();
       // the first copies go out while the consumer warps are still clearing the filter (s_qn is 0: no flush marker yet)
       for (int s = 0; s < n_stages && !done; ++s) done = !produce();
@@ -529,11 +531,26 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
         costmap_tile_batch<4, kCmBits>(g, cm, costmap, t0, n_tiles, lane, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy);
     }
     TRACE(3, 2);
-    costmap_warp_accumulate(g.ctr, cm_n, cm_mnx, cm_mny, cm_mxx, cm_mxy);
-    if (lane == 0) __threadfence();   // this warp's accumulator updates are visible before the CTA takes its ticket
+    // marked cells and bounds: warp shuffle, then shared memory, then ONE set of global atomics per CTA (thousands of warps
+    // updating the same five words would serialise in L2)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      cm_n += __shfl_xor_sync(kFull, cm_n, d);
+      cm_mnx = min(cm_mnx, __shfl_xor_sync(kFull, cm_mnx, d)); cm_mny = min(cm_mny, __shfl_xor_sync(kFull, cm_mny, d));
+      cm_mxx = max(cm_mxx, __shfl_xor_sync(kFull, cm_mxx, d)); cm_mxy = max(cm_mxy, __shfl_xor_sync(kFull, cm_mxy, d));
+    }
+    if (lane == 0 && cm_n) {
+      atomicAdd(&s_cm[0], (int)cm_n);
+      atomicMin(&s_cm[1], cm_mnx); atomicMin(&s_cm[2], cm_mny); atomicMax(&s_cm[3], cm_mxx); atomicMax(&s_cm[4], cm_mxy);
+    }
     named_bar_sync(2, kMarkThreads);
     TRACE(3, 3);
     if (threadIdx.x == 0) {
+      if (s_cm[0]) {
+        atomicAdd(&g.ctr->cm_acc.n_marked, (unsigned long long)s_cm[0]);
+        atomicMin(&g.ctr->cm_acc.mk_min_x, s_cm[1]); atomicMin(&g.ctr->cm_acc.mk_min_y, s_cm[2]);
+        atomicMax(&g.ctr->cm_acc.mk_max_x, s_cm[3]); atomicMax(&g.ctr->cm_acc.mk_max_y, s_cm[4]);
+      }
       __threadfence();
       if (atomicAdd(&g.ctr->cm_ticket, 1u) == gridDim.x - 1) {   // last CTA publishes the result and re-arms the accumulators
         __threadfence();
