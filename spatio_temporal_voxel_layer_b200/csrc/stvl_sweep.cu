@@ -1,7 +1,7 @@
 // stvl_sweep.cu — ClearFrustums / TemporalClearAndGenerateCostmap (reference spatio_temporal_voxel_grid.cpp:96-224) as ONE
 // kernel.
 //
-// Every CTA walks passes over the leaf slots (dealt to the CTAs in groups of four consecutive slots, so that a run of leaves
+// Every CTA walks passes over the leaf slots (dealt to the CTAs in pairs or fours of consecutive slots, so that a run of leaves
 // that all need work — a frustum's interior, a part of the map that expires together — is spread over the whole grid); a
 // pass has ONE CTA barrier:
 //   A  one THREAD per leaf: header (key, tmin, tile, 64 B value mask) in one round trip.  A leaf outside every frustum whose
@@ -180,10 +180,17 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
   SweepAcc acc;
   TRACE(1, 2);
 
-  // Passes: thread t of CTA b takes, in pass p, the leaf (p * 512 + t) of the CTA's share; slots are dealt to the CTAs in groups
-  // of four consecutive ones (the 8-byte header fields of a group fill one 32 B sector).
-  const uint32_t n_quads = (n_slots + 3) / 4;
-  const uint32_t n_passes = (n_quads + gridDim.x * (kSweepThreads / 4) - 1) / (gridDim.x * (kSweepThreads / 4));
+  // Passes: thread t of CTA b takes, in pass p, the leaf (p * 512 + t) of the CTA's share.  Slots are dealt to the CTAs in
+  // pairs of consecutive ones (fine enough that the few hundred leaves a frustum touches — consecutive slots — end up in as
+  // many CTAs; the 8-byte header fields still fill half a 32 B sector), large stores in fours (full sectors: there the
+  // header traffic matters and every CTA has many leaves of every kind anyway).
+  const uint32_t kDeal = n_slots > 262144u ? 4u : 2u;
+  const uint32_t n_deals = (n_slots + kDeal - 1) / kDeal;
+  const uint32_t n_passes = (n_deals + gridDim.x * (kSweepThreads / kDeal) - 1) / (gridDim.x * (kSweepThreads / kDeal));
+  auto slot_of = [&](uint32_t pass) {
+    const uint32_t q = pass * kSweepThreads + threadIdx.x;
+    return ((q / kDeal) * gridDim.x + blockIdx.x) * kDeal + (q % kDeal);
+  };
   uint32_t qi = 0;   // queues of this pass (pass number modulo 3)
   // bit p & 1: this thread queued the columns of a leaf in pass p and has not yet written the leaf's new bound (that happens
   // behind the NEXT pass's barrier, i.e. after this thread's phase A of that pass — hence two bits, and the leaf's slot is
@@ -202,8 +209,7 @@ sweep_kernel(const __grid_constant__ GridView g, const __grid_constant__ Frustum
     const uint32_t pb = pass & 1u;
     // ---- phase A: one thread per leaf -------------------------------------------------------------------------------------
     {
-      const uint32_t q = pass * kSweepThreads + threadIdx.x;
-      const uint32_t slot = ((q >> 2) * gridDim.x + blockIdx.x) * 4 + (q & 3u);
+      const uint32_t slot = slot_of(pass);
       unsigned long long entry = 0;
       bool queue_it = false;
       if (slot < n_slots) {
