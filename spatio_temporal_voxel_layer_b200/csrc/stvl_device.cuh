@@ -149,12 +149,20 @@ struct DevReading {
   float oxf, oyf, ozf;    // (float) origin, for that screen
   float tf[12];           // sensor -> global float affine (row-major 3x4), applied first when has_tf
   uint32_t has_tf;
-  uint32_t first_block;   // first unit of this reading in the batch's unit index space (units of 1984 points)
+  uint32_t first_block;   // first unit of this reading in the batch's unit index space (units of 128 points)
   uint32_t vec4;          // 1: point_step==16, offsets 0/4/8, 16 B aligned -> float4 loads
   int32_t ref_ix, ref_iy, ref_iz;   // voxel of the reading's origin: frame of Mark's 32-bit voxel codes (set at launch)
 };
+// what Mark's unit hand-out needs of a reading (copied from DevReading at launch)
+struct MarkStreamSource {
+  const uint8_t * data;
+  unsigned long long n_points;
+  const unsigned long long * n_points_dev;
+  uint32_t has_tf, pad;
+};
 struct MarkBatch {
-  uint32_t first_block[kMaxBatchReadings];   // copy of r[k].first_block, one cache line: the producers scan it to find their readings
+  uint32_t first_block[kMaxBatchReadings];   // copy of r[k].first_block, one cache line: lane k of every warp keeps entry k
+  MarkStreamSource src[kMaxBatchReadings];
   DevReading r[kMaxBatchReadings];
   uint32_t n_readings;
   uint32_t total_blocks;
@@ -162,12 +170,10 @@ struct MarkBatch {
   int32_t ref_bx;           // reference leaf x of the batch (first reading's origin): block-local table keys store bx - ref_bx
   float vs_f;               // (float)vs
   float c_lo, c_hi;         // (float)(1/vs) scaled down / up by a few ulps: the two ends of the fast quantisation (set at launch)
-  uint32_t pad;
+  uint32_t units_per_cta;   // total_blocks / grid and ...
+  uint32_t units_extra;     // ... total_blocks % grid: the first units_extra CTAs take one unit more (set at launch)
+  uint32_t dynamic_units;   // 1: a CTA hands its units to whichever warp asks next; 0: round-robin over its warps (set at launch)
   double min_now;           // smallest clock sample in the batch: initial leaf_tmin of leaves created by it
-  // the batch's point index space (set at launch): reading k holds points [first_point[k], first_point[k + 1]); the CTAs take
-  // slices of slice_len points of it round-robin
-  unsigned long long first_point[kMaxBatchReadings + 1];
-  unsigned long long slice_len;           // smallest clock sample in the batch: initial leaf_tmin of leaves created by it
 };
 
 // -------- helpers -------------------------------------------------------------------
