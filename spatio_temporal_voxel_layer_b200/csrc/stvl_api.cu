@@ -122,6 +122,7 @@ struct stvl_grid {
   uint32_t * tile_buf[2] = {nullptr, nullptr};   // double-buffered column tiles (see GridView::tile_count)
   int sweep_parity = 0;
   uint64_t launches = 0;
+  uint32_t mark_cursor_host = 0;   // value of *v.mark_cursor once every Mark launched so far has run
   bool record_mark_event = false;   // set by stvl_mark around its launches (ev_mark_done guards the host-cloud staging buffer)
   size_t device_bytes = 0;
   // in-library sharded merge (stvl_comm_init / stvl_costmap_sharded_device)
@@ -470,7 +471,8 @@ int launch_batches(stvl_grid * g, const std::vector<MarkBatch> & batches, CycleF
     const bool carry = fz && fz->costmap && !fz->costmap_done && i + 1 == batches.size();
     const MarkBatch & b = batches[i];
     HOST_T(tm0);
-    CU(launch_mark(g->v, b, g->sm_count, g->stream, pdl, carry ? &fz->cm : nullptr, carry ? fz->costmap : nullptr, carry && fz->bits));
+    CU(launch_mark(g->v, b, g->sm_count, g->stream, pdl, carry ? &fz->cm : nullptr, carry ? fz->costmap : nullptr, carry && fz->bits,
+                   &g->mark_cursor_host));
     HOST_T(tm1);
     HOST_ADD(3, tm0, tm1);
     if (carry) fz->costmap_done = true;
@@ -1005,6 +1007,8 @@ int stvl_create(const stvl_config_t * cfg, stvl_grid_t ** out)
   }
   CUB(cudaMalloc(&g->v.ctr, sizeof(Counters)));
   g->device_bytes += sizeof(Counters);
+  CUB(cudaMalloc(&g->v.mark_cursor, sizeof(uint32_t)));
+  CUB(cudaMemset(g->v.mark_cursor, 0, sizeof(uint32_t)));
 
   const uint32_t leaf_cap = cfg->leaf_capacity ? std::max<uint32_t>(cfg->leaf_capacity, 64u) : (1u << 18);
   GridView nv = g->v;
@@ -1044,6 +1048,7 @@ int stvl_destroy(stvl_grid_t * g)
   free_pool(g->v);
   free_tiles(g->v);
   cudaFree(g->v.ctr);
+  cudaFree(g->v.mark_cursor);
   cudaFree(g->stage.p); cudaFree(g->frustums.p); cudaFree(g->points.p); cudaFree(g->cleared.p); cudaFree(g->ambiguous.p);
   cudaFree(g->costmap.p); cudaFree(g->col_ix.p); cudaFree(g->col_iy.p); cudaFree(g->col_cnt.p);
   cudaFree(g->dump_x.p); cudaFree(g->dump_y.p); cudaFree(g->dump_z.p); cudaFree(g->dump_t.p);

@@ -105,6 +105,7 @@ struct GridView {
   int sw_cur;              // which SweepCtr set / tile buffer the current (last) sweep uses
   uint32_t tile_capacity;
   Counters * ctr;
+  uint32_t * mark_cursor;   // Mark's group hand-out: a monotone (wrapping) counter, never reset (every launch is told where it stands)
   LiveCounters * live;     // host-mapped mirror (may be NULL)
   // constants
   double vs, inv_vs, half_vs;
@@ -170,9 +171,15 @@ struct MarkBatch {
   int32_t ref_bx;           // reference leaf x of the batch (first reading's origin): block-local table keys store bx - ref_bx
   float vs_f;               // (float)vs
   float c_lo, c_hi;         // (float)(1/vs) scaled down / up by a few ulps: the two ends of the fast quantisation (set at launch)
+  // unit hand-out (set at launch).  Static: units round-robin over the CTAs and, inside a CTA, over its warps.  Dynamic (fused
+  // cycle, whose CTAs start at different times as the sweep leaves the SMs): groups of kMarkGroup units; CTA c starts with
+  // group c, further groups come from GridView::mark_cursor, whose value when this launch starts is cursor_base
   uint32_t units_per_cta;   // total_blocks / grid and ...
-  uint32_t units_extra;     // ... total_blocks % grid: the first units_extra CTAs take one unit more (set at launch)
-  uint32_t dynamic_units;   // 1: a CTA hands its units to whichever warp asks next; 0: round-robin over its warps (set at launch)
+  uint32_t units_extra;     // ... total_blocks % grid: the first units_extra CTAs take one unit more
+  uint32_t dynamic_units;
+  uint32_t cursor_base;
+  uint32_t n_groups;        // ceil(total_blocks / kMarkGroup)
+  uint32_t pad2;
   double min_now;           // smallest clock sample in the batch: initial leaf_tmin of leaves created by it
 };
 

@@ -52,7 +52,8 @@ cudaError_t launch_update_costs(const uint8_t * layer_dev, uint8_t * master_dev,
                                 int method, int sm_count, cudaStream_t s);
 
 cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s, bool pdl = false,
-                        const CostmapDev * fused_costmap = nullptr, uint8_t * costmap_dev = nullptr, bool costmap_bits = false);
+                        const CostmapDev * fused_costmap = nullptr, uint8_t * costmap_dev = nullptr, bool costmap_bits = false,
+                        uint32_t * cursor_host = nullptr);   // cursor_host: where GridView::mark_cursor stands (advanced by the launch)
 uint32_t mark_blocks_for(unsigned long long n_points);
 uint32_t mark_grid_for(const MarkBatch & batch, int sm_count);
 uint32_t mark_costmap_tiles_capacity(const MarkBatch & batch, int sm_count);

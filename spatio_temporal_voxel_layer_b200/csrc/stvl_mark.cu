@@ -34,6 +34,7 @@ constexpr int kMarkWarpsShared = 16;             // ... and of one that shares i
 constexpr int kMarkPPT = 4;                      // points per lane per unit
 constexpr int kMarkChunk = 32 * kMarkPPT;        // a unit: 128 points = 2 KB of packed float4 points, one warp-private buffer
 constexpr int kMarkCostmapWarps = 8;             // warps of a CTA that run the fused cycle's costmap pass before they join the unit stream
+constexpr int kMarkGroup = 32;                  // dynamic hand-out: units a CTA claims at a time
 constexpr int kMarkBufs = 2;                     // buffers (units in flight) per warp
 constexpr int kMarkFilter = 8192;                // direct-mapped filter of voxel codes, entries (a power of two)
 constexpr int kMarkFilterShift = 19;             // 32 - log2(kMarkFilter)
@@ -46,6 +47,7 @@ static_assert(kMarkQueueFlush + kMarkWarps * kMarkChunk <= kMarkQueue, "queue si
 static_assert((1 << (32 - kMarkFilterShift)) == kMarkFilter, "filter index = upper bits of the multiplicative hash");
 // what a warp knows about the unit in one of its buffers: points (8 bits, 0 = empty unit) | reading << 8 | sensor-frame cloud
 constexpr uint32_t kMetaEnd = 0xFFFFFFFFu, kMetaTf = 1u << 16;
+constexpr uint32_t kNoUnit = 0xFFFFFFFFu;
 constexpr uint32_t kNoCode = 0xFFFFFFFFu;   // "nothing to queue" (the one voxel whose code this is goes straight to the store)
 static_assert(kMarkPPT == 4 && kMarkChunk == 128, "the unit arithmetic is written for four points per lane");
 
@@ -209,7 +211,10 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
   volatile unsigned int * const s_qn = reinterpret_cast<volatile unsigned int *>(s_dyn + kSmQn);
   volatile unsigned int * const s_flush_req = reinterpret_cast<volatile unsigned int *>(s_dyn + kSmFlushReq);
   __shared__ unsigned int s_done;          // warps that have run out of units
-  __shared__ unsigned int s_next;          // next unit of the CTA to hand out (dynamic hand-out)
+  // dynamic hand-out: {end << 32 | next} of the group of units the CTA is working through, the group claimed ahead of need
+  // (index + 1, 0 = not there yet), and "no more groups"
+  __shared__ unsigned long long s_units;
+  __shared__ unsigned int s_claimed, s_exhausted;
   __shared__ unsigned int s_drop[2];
   __shared__ int s_cm[5];                  // fused costmap pass: marked cells and their bounds, gathered per CTA
 
@@ -225,13 +230,45 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
 
   // ---- unit hand-out: units are dealt round-robin to the CTAs, a CTA's units round-robin to its warps ---------------------
   // reading k holds units [first_block[k], first_block[k + 1]) of kMarkChunk points; lane k keeps first_block[k]
-  const uint32_t n_tickets = batch.units_per_cta + (blockIdx.x < batch.units_extra ? 1u : 0u);   // units of this CTA
+  const uint32_t n_tickets = batch.units_per_cta + (blockIdx.x < batch.units_extra ? 1u : 0u);   // units of this CTA (static hand-out)
+  const bool dynamic = batch.dynamic_units != 0;
   const uint32_t first_unit = lane < batch.n_readings ? batch.first_block[lane] : 0xFFFFFFFFu;
-  // what buffer b will hold for the CTA's unit number i; lane 0 starts the copy.  Returns the unit's meta word (kMetaEnd: no
-  // such unit).
-  auto issue = [&](const uint32_t i, const uint32_t b, unsigned long long & base_out) -> uint32_t {
-    if (i >= n_tickets) return kMetaEnd;
-    const uint32_t u = blockIdx.x + i * gridDim.x;
+  // one more group for the CTA (dynamic hand-out; one lane): its index, beyond n_groups when there is none left.  Every CTA
+  // claims until it is told so ONCE, so a launch advances the cursor by exactly n_groups - gridDim.x + gridDim.x = n_groups.
+  auto claim_group = [&]() -> uint32_t { return gridDim.x + (atomicAdd(g.mark_cursor, 1u) - batch.cursor_base); };
+  // the warp's next unit.  Static: the CTA's unit number `ticket`.  Dynamic: the next unit of the CTA's current group; the lane
+  // that takes a group's first unit claims the group after it, the lane that finds the group used up installs that one.
+  auto next_unit = [&](const uint32_t ticket) -> uint32_t {
+    if (!dynamic) return ticket < n_tickets ? blockIdx.x + ticket * gridDim.x : kNoUnit;
+    uint32_t u = kNoUnit;
+    if (lane == 0) {
+      for (;;) {
+        const unsigned long long old = atomicAdd(&s_units, 1ull);
+        const uint32_t cur = (uint32_t)old, end = (uint32_t)(old >> 32);
+        if (cur < end) {
+          if ((cur & (uint32_t)(kMarkGroup - 1)) == 0u) *reinterpret_cast<volatile unsigned int *>(&s_claimed) = claim_group() + 1u;
+          u = cur;
+          break;
+        }
+        if (*reinterpret_cast<volatile unsigned int *>(&s_exhausted)) break;
+        if (cur == end) {   // first to find the group used up: install the one claimed ahead
+          unsigned int c;
+          while ((c = *reinterpret_cast<volatile unsigned int *>(&s_claimed)) == 0u) { }
+          *reinterpret_cast<volatile unsigned int *>(&s_claimed) = 0u;
+          const uint32_t grp = c - 1u;
+          if (grp >= batch.n_groups) { *reinterpret_cast<volatile unsigned int *>(&s_exhausted) = 1u; break; }
+          const uint32_t lo = grp * (uint32_t)kMarkGroup, hi = min(lo + (uint32_t)kMarkGroup, batch.total_blocks);
+          atomicExch(&s_units, ((unsigned long long)hi << 32) | lo);
+        } else {
+          __nanosleep(32);   // another warp is installing the next group
+        }
+      }
+    }
+    return __shfl_sync(kFull, u, 0);
+  };
+  // what buffer b will hold for unit u; lane 0 starts the copy.  Returns the unit's meta word (kMetaEnd: no such unit).
+  auto issue = [&](const uint32_t u, const uint32_t b, unsigned long long & base_out) -> uint32_t {
+    if (u == kNoUnit) return kMetaEnd;
     const int ri = __popc(__ballot_sync(kFull, u >= first_unit)) - 1;   // lane 0 holds 0: ri >= 0
     const MarkStreamSource & rd = batch.src[ri];   // (the few fields the hand-out needs, packed next to first_block: the batch
                                                    // description is cold in the constant cache when the kernel starts)
@@ -267,8 +304,22 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
     }
     __syncwarp();
   }
-  uint32_t meta_cur = issue(warp, 0, base_cur);
-  uint32_t meta_nxt = issue(warp + kWarps, 1, base_nxt);
+  // (dynamic hand-out: unit `warp` of the CTA's first group, group blockIdx.x; the claim of its second group is under way
+  // while the tables are set up, and every warp takes its second unit from it after the barrier below)
+  // The warps that run the costmap pass first (fused variant) take no unit before it; the rest of the first group is handed out
+  // like every later group.
+  constexpr uint32_t kLateWarps = kCostmap ? (uint32_t)kMarkCostmapWarps : 0u;
+  static_assert(kWarps - (int)kLateWarps <= kMarkGroup, "a CTA's first group gives every early warp one unit");
+  uint32_t meta_cur, meta_nxt = kMetaEnd;
+  uint32_t claimed_first = 0;
+  if (dynamic) {
+    if (threadIdx.x == 0) claimed_first = claim_group();
+    const uint32_t u = blockIdx.x * (uint32_t)kMarkGroup + (warp - kLateWarps);
+    meta_cur = issue((warp >= kLateWarps && u < batch.total_blocks) ? u : kNoUnit, 0, base_cur);
+  } else {
+    meta_cur = issue(next_unit(warp), 0, base_cur);
+    meta_nxt = issue(next_unit(warp + kWarps), 1, base_nxt);
+  }
 
   if (warp == 0) {
     if (lane < kMaxBatchReadings) {
@@ -282,7 +333,14 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
       sp[10] = __int_as_float(r.ref_iz - kCodeBiasZ); sp[11] = __uint_as_float(lane << 28);
     }
     if (lane == 0) {
-      *s_qn = 0; *s_flush_req = 0; s_done = 0; s_next = 2 * kWarps; s_drop[0] = s_drop[1] = 0;
+      *s_qn = 0; *s_flush_req = 0; s_done = 0; s_drop[0] = s_drop[1] = 0;
+      s_claimed = 0; s_exhausted = 0; s_units = 0;
+      if (dynamic) {   // what the early warps left of the first group; the group claimed above comes next
+        const uint32_t hi = min((blockIdx.x + 1u) * (uint32_t)kMarkGroup, batch.total_blocks);
+        const uint32_t lo = min(blockIdx.x * (uint32_t)kMarkGroup + ((uint32_t)kWarps - kLateWarps), hi);
+        s_units = ((unsigned long long)hi << 32) | lo;
+        s_claimed = claimed_first + 1u;
+      }
       s_cm[0] = 0; s_cm[1] = s_cm[2] = INT_MAX; s_cm[3] = s_cm[4] = INT_MIN;
     }
   }
@@ -390,6 +448,11 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
     }
   }
 
+  if (dynamic) {
+    // (a warp without a first unit — a short first group, or more warps than a group has units — still takes part)
+    if (meta_cur == kMetaEnd) { meta_cur = issue(next_unit(0), 0, base_cur); if (meta_cur != kMetaEnd) meta_nxt = issue(next_unit(0), 1, base_nxt); }
+    else meta_nxt = issue(next_unit(0), 1, base_nxt);
+  }
   // ---- the warp's stream of units ---------------------------------------------------------------------------------------------
   // unit number `it` of the warp (the CTA's unit warp + 32 * it) sits in buffer it & 1; every unit completes one phase of its
   // buffer's barrier
@@ -426,12 +489,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
     // the buffer may be refilled: the warp holds its points in registers
     __syncwarp();
     meta_cur = meta_nxt; base_cur = base_nxt;
-    uint32_t ticket = warp + (it + 2u) * (uint32_t)kWarps;
-    if (batch.dynamic_units) {   // whichever warp asks next takes the CTA's next unit
-      if (lane == 0) ticket = atomicAdd(&s_next, 1u);
-      ticket = __shfl_sync(kFull, ticket, 0);
-    }
-    meta_nxt = issue(ticket, b, base_nxt);
+    meta_nxt = issue(next_unit(warp + (it + 2u) * (uint32_t)kWarps), b, base_nxt);
     if (first) { TRACE(0, 2); first = false; }
     if (in_unit) {
       const uint32_t par_addr = sbase + kSmPar + ri * 48u;
@@ -636,19 +694,19 @@ int mark_warps_shared()
 }  // namespace
 
 // one CTA per SM; small batches get one CTA per unit
-uint32_t mark_grid_for(const MarkBatch & batch, int sm_count)
-{
-  return std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)sm_count, batch.total_blocks));
-}
+uint32_t mark_grid_for(const MarkBatch & batch, int sm_count) { return std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)sm_count, batch.total_blocks)); }
+// ... and with the dynamic hand-out (fused cycle) one CTA per group of units
+static uint32_t mark_groups(const MarkBatch & batch) { return (batch.total_blocks + (uint32_t)kMarkGroup - 1) / (uint32_t)kMarkGroup; }
+static uint32_t mark_grid_dynamic(const MarkBatch & batch, int sm_count) { return std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)sm_count, mark_groups(batch))); }
 // column tiles the fused variant's costmap pass can take without becoming the critical path of the launch
 uint32_t mark_costmap_tiles_capacity(const MarkBatch & batch, int sm_count)
 {
-  return mark_grid_for(batch, sm_count) * (uint32_t)kMarkCostmapWarps * 64u;
+  return mark_grid_dynamic(batch, sm_count) * (uint32_t)kMarkCostmapWarps * 64u;
 }
 
 template <bool kVec4, bool kCostmap, bool kCmBits, int kWarps>
 static cudaError_t launch_mark_variant(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s, bool pdl,
-                                       const CostmapDev & cm, uint8_t * costmap)
+                                       const CostmapDev & cm, uint8_t * costmap, uint32_t * cursor)
 {
   static bool configured = false;
   const size_t smem = mark_smem_bytes(kVec4, kWarps);
@@ -665,13 +723,17 @@ static cudaError_t launch_mark_variant(const GridView & g, const MarkBatch & bat
   b.vs_f = (float)g.vs;                                              // exact: vs is a float widened to double
   b.c_lo = (float)g.inv_vs * 0.999999701976776123046875f;            // (float)(1/vs) * (1 - 5 * 2^-24), one rounding
   b.c_hi = (float)g.inv_vs * 1.00000035762786865234375f;             // (float)(1/vs) * (1 + 3 * 2^-23), one rounding
-  {   // units are dealt round-robin to the CTAs: CTA c takes units c, c + grid, c + 2 grid, ...
-    const uint32_t grid = mark_grid_for(batch, sm_count);
-    b.units_per_cta = b.total_blocks / grid;
-    b.units_extra = b.total_blocks % grid;
-    static const bool dynamic_units = std::getenv("STVL_MARK_DYNAMIC") && std::atoi(std::getenv("STVL_MARK_DYNAMIC")) != 0;   // tuning knob
-    b.dynamic_units = (dynamic_units || kCostmap) ? 1u : 0u;   // (the costmap warps of the fused variant join the stream late)
-  }
+  // Unit hand-out.  A launch of the fused cycle starts its CTAs one by one as the sweep leaves the SMs (and its costmap warps
+  // join the stream late), so there the units are handed out dynamically, in groups, from the handle's cursor; a launch that has
+  // the GPU to itself deals them round-robin: CTA c takes units c, c + grid, c + 2 grid, ...  (STVL_MARK_DYNAMIC=0/1 forces either.)
+  static const int force_dynamic = std::getenv("STVL_MARK_DYNAMIC") ? std::atoi(std::getenv("STVL_MARK_DYNAMIC")) : -1;
+  const bool dynamic = cursor != nullptr && g.mark_cursor != nullptr && (kCostmap || (force_dynamic < 0 ? pdl : force_dynamic != 0));
+  const uint32_t grid = dynamic ? mark_grid_dynamic(batch, sm_count) : mark_grid_for(batch, sm_count);
+  b.units_per_cta = b.total_blocks / grid;
+  b.units_extra = b.total_blocks % grid;
+  b.dynamic_units = dynamic ? 1u : 0u;
+  b.n_groups = mark_groups(batch);
+  b.cursor_base = cursor ? *cursor : 0u;
   for (uint32_t k = 0; k < b.n_readings; ++k) {
     b.src[k].data = b.r[k].data; b.src[k].n_points = b.r[k].n_points; b.src[k].n_points_dev = b.r[k].n_points_dev; b.src[k].has_tf = b.r[k].has_tf;
   }
@@ -684,7 +746,10 @@ static cudaError_t launch_mark_variant(const GridView & g, const MarkBatch & bat
     }
     b.r[k].ref_ix = ref[0]; b.r[k].ref_iy = ref[1]; b.r[k].ref_iz = ref[2];
   }
-  return launch_ex(mark_kernel<kVec4, kCostmap, kCmBits, kWarps>, mark_grid_for(batch, sm_count), (unsigned)(kWarps * 32), smem, s, pdl, g, b, cm, costmap);
+  const cudaError_t e = launch_ex(mark_kernel<kVec4, kCostmap, kCmBits, kWarps>, grid, (unsigned)(kWarps * 32), smem, s, pdl, g, b, cm, costmap);
+  // every CTA claims groups until it is told ONCE that there is none left: the launch moves the cursor by this much
+  if (e == cudaSuccess && dynamic) *cursor += (b.n_groups > grid ? b.n_groups - grid : 0u) + grid;
+  return e;
 }
 
 // pdl: the caller guarantees that the kernel's inputs (clouds) were complete before the PREDECESSOR of this launch in the
@@ -692,16 +757,16 @@ static cudaError_t launch_mark_variant(const GridView & g, const MarkBatch & bat
 // (cm_bits: into a cell bitmap).
 template <bool kCostmap, bool kCmBits>
 static cudaError_t launch_mark_layout(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s, bool pdl,
-                                      const CostmapDev & cm, uint8_t * costmap, bool all_vec4, bool shared_sm)
+                                      const CostmapDev & cm, uint8_t * costmap, bool all_vec4, bool shared_sm, uint32_t * cursor)
 {
   if (shared_sm && mark_warps_shared() == kMarkWarpsShared)
-    return all_vec4 ? launch_mark_variant<true, kCostmap, kCmBits, kMarkWarpsShared>(g, batch, sm_count, s, pdl, cm, costmap)
-                    : launch_mark_variant<false, kCostmap, kCmBits, kMarkWarpsShared>(g, batch, sm_count, s, pdl, cm, costmap);
-  return all_vec4 ? launch_mark_variant<true, kCostmap, kCmBits, kMarkWarps>(g, batch, sm_count, s, pdl, cm, costmap)
-                  : launch_mark_variant<false, kCostmap, kCmBits, kMarkWarps>(g, batch, sm_count, s, pdl, cm, costmap);
+    return all_vec4 ? launch_mark_variant<true, kCostmap, kCmBits, kMarkWarpsShared>(g, batch, sm_count, s, pdl, cm, costmap, cursor)
+                    : launch_mark_variant<false, kCostmap, kCmBits, kMarkWarpsShared>(g, batch, sm_count, s, pdl, cm, costmap, cursor);
+  return all_vec4 ? launch_mark_variant<true, kCostmap, kCmBits, kMarkWarps>(g, batch, sm_count, s, pdl, cm, costmap, cursor)
+                  : launch_mark_variant<false, kCostmap, kCmBits, kMarkWarps>(g, batch, sm_count, s, pdl, cm, costmap, cursor);
 }
 cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_count, cudaStream_t s, bool pdl,
-                        const CostmapDev * cm, uint8_t * costmap, bool cm_bits)
+                        const CostmapDev * cm, uint8_t * costmap, bool cm_bits, uint32_t * cursor)
 {
   if (batch.total_blocks == 0) return cudaSuccess;
   bool all_vec4 = true;
@@ -710,10 +775,10 @@ cudaError_t launch_mark(const GridView & g, const MarkBatch & batch, int sm_coun
   // a launch of the fused cycle (chained behind the sweep, or carrying the costmap pass) shares the SMs with the sweep kernel
   const bool shared_sm = pdl || (cm && costmap);
   if (cm && costmap) {
-    if (cm_bits) return launch_mark_layout<true, true>(g, batch, sm_count, s, pdl, *cm, costmap, all_vec4, shared_sm);
-    return launch_mark_layout<true, false>(g, batch, sm_count, s, pdl, *cm, costmap, all_vec4, shared_sm);
+    if (cm_bits) return launch_mark_layout<true, true>(g, batch, sm_count, s, pdl, *cm, costmap, all_vec4, shared_sm, cursor);
+    return launch_mark_layout<true, false>(g, batch, sm_count, s, pdl, *cm, costmap, all_vec4, shared_sm, cursor);
   }
-  return launch_mark_layout<false, false>(g, batch, sm_count, s, pdl, none, nullptr, all_vec4, shared_sm);
+  return launch_mark_layout<false, false>(g, batch, sm_count, s, pdl, none, nullptr, all_vec4, shared_sm, cursor);
 }
 uint32_t mark_blocks_for(unsigned long long n_points)
 {
