@@ -2,23 +2,25 @@
 //
 // One persistent CTA of 32 warps per SM, every warp a self-contained pipeline (no producer warp, no CTA-wide barrier while
 // the clouds stream).  The batch's points (all readings laid end to end) are cut into UNITS of 128 points (2 KB of packed
-// float4 points, never across two readings).  Units are dealt round-robin to the CTAs — every CTA gets the same number of
-// points from all over the batch (floor rows that the range screen rejects are cheap, wall rows are not) — and, inside a
-// CTA, handed to whichever warp asks next (one shared-memory ticket per unit).  A warp owns two 2 KB buffers and one
-// mbarrier each:
-//   * lane 0 takes a ticket and streams the unit global -> shared memory with the bulk-copy engine (cp.async.bulk,
-//     completion on the buffer's mbarrier as transaction bytes; SASS UBLKCP / SYNCS), evict-first in L2;
+// float4 points, never across two readings).  A warp owns two 2 KB buffers and one mbarrier each:
+//   * lane 0 streams a unit global -> shared memory with the bulk-copy engine (cp.async.bulk, completion on the buffer's
+//     mbarrier as transaction bytes; SASS UBLKCP / SYNCS), evict-first in L2;
 //   * the warp waits for its OLDER buffer, pulls four points per lane into registers, re-issues that buffer right away
 //     (64 units = 128 KB in flight per SM) and runs the reference's per-point arithmetic on the four points: range /
 //     z-window tests and voxel quantisation on a single-precision fast path that is PROVEN to agree with the reference's
 //     double arithmetic (see quantise_axis_fast), the exact double sequence for the few points it cannot decide;
 //   * survivors go through a CTA-wide direct-mapped filter of 32-bit voxel codes (dedupe) into a queue of voxels to write.
+// Hand-out of the units.  A launch that has the GPU to itself deals them round-robin to the CTAs — every CTA gets the same
+// number of points from all over the batch (floor rows that the range screen rejects are cheap, wall rows are not) — and,
+// inside a CTA, round-robin to its warps: no atomics.  A launch of the fused cycle starts its CTAs one by one as the sweep
+// leaves the SMs; there a CTA takes GROUPS of 32 units from a global cursor (never reset: every launch is told where it
+// stands) and hands a group's units to whichever warp asks next.
 // The first copies are in flight before the CTA has set up its tables.  Nothing before the flush touches the grid, so all
 // of the streaming may overlap the sweep that precedes Mark on the stream (programmatic dependent launch).  The flush
 // resolves every queued voxel in the global leaf hash once and pushes one 32-bit OR into the leaf's mask and one 64-bit max
 // (or store) of the mark time.  A queue that fills up (huge or scattered clouds) is flushed early: the warp that notices
-// raises a flag, every warp joins at its next unit.  In the fused cycle all 32 warps then run the costmap pass over the
-// sweep's column counts.
+// raises a flag, every warp joins at its next unit.  In the fused cycle the first eight warps of every CTA run the costmap
+// pass over the sweep's column counts BEFORE they join the unit stream.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -294,7 +296,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
     return cnt | ((uint32_t)ri << 8) | (rd.has_tf ? kMetaTf : 0u);
   };
 
-  // the first two units of every warp are on their way before the CTA sets up its tables
+  // the first units are on their way before the CTA sets up its tables
   unsigned long long base_cur = 0, base_nxt = 0;   // first point of the unit in its reading (generic layouts read from there)
   if constexpr (kVec4) {
     if (lane == 0) {
