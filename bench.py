@@ -462,6 +462,9 @@ def bench_ours(args):
         import torch.distributed as dist_mod
         dist = dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # The per-cycle exchange is a few hundred KB of cell bitmaps per peer: one NCCL point-to-point channel (one copy CTA per
+        # peer) moves that in a fraction of a cycle and leaves the SMs to the cycle's persistent kernels.
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     w = make_workload(rank, world)
@@ -604,6 +607,8 @@ def bench_ours(args):
         grid.ResetGrid()
         grid.load_voxels(*w.seed_vox, w.seed_t)
 
+    host_enqueue_s = []   # per episode: wall-clock seconds the host spent enqueuing one cycle (this rank)
+
     def device_episode(n_cycles, dt=None, fused=True, timed=True):
         """reset + seed + settle + n_cycles; returns (CUDA-event ms of the n_cycles, kernel launches inside them)."""
         merge_drain()
@@ -615,8 +620,10 @@ def bench_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
+        th0 = time.perf_counter()
         for j in range(1, n_cycles + 1):
             step_device(j, dt, fused)
+        host_enqueue_s.append((time.perf_counter() - th0) / max(n_cycles, 1))   # the calls only enqueue: host time per cycle
         merge_drain()                      # N>1: the last cycle's merge is part of the timed region
         e1.record(stream)
         barrier()
@@ -624,6 +631,7 @@ def bench_ours(args):
 
     # ---- value leg: inputs resident in HBM ---------------------------------------------------------------------------
     device_episode(min(args.warmup, EPISODE_CYCLES))           # warm-up episode (W cycles after the settle cycle)
+    host_enqueue_s.clear()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -634,6 +642,7 @@ def bench_ours(args):
         dev_ms += ms
         launches += nl
         episode_ms.append(ms / n)
+    host_enqueue_us = 1e6 * float(np.median(host_enqueue_s)) if host_enqueue_s else None
     st_end = g.sweep_stats()               # the last timed cycle's sweep
     active_end = g.active_count()
     # The timed region lasts a few hundred microseconds per episode — less than one nvidia-smi sampling period — so the
@@ -786,6 +795,9 @@ def bench_ours(args):
                         "rewritten_last_timed_cycle": int(st_end.n_rewritten),
                         "e2e_active_voxels_end": int(e2e_active_end), "us_per_cycle_by_episode": [round(1e3 * v, 2) for v in episode_ms],
                         "leaf_pool_gb": g.pool_stats().device_bytes / 1e9,
+                        "host_enqueue_us_per_cycle_rank0": None if host_enqueue_us is None else round(host_enqueue_us, 2),
+                        "host_enqueue_note": "wall clock of the enqueue-only C-ABI call(s) of one cycle from Python (median over the timed episodes); "
+                                             "at or above ms_per_step the cycle rate is set by the host, not by the kernels",
                         "parallelism": "1 GPU" if world == 1 else "%d spatial x-slab shards, fused cycle per shard + in-library merge of the per-shard costmap cells into rank 0, pipelined one cycle behind" % world},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": bytes_h2d, "d2h_bytes_per_step": bytes_d2h,
                     "how": "stvl_update_cycle_async / stvl_update_cycle_wait, two cycles in flight (H2D of cycle k+1 overlaps kernels and D2H of cycle k); wall clock over the episodes' timed cycles, every cycle's bytes waited for"

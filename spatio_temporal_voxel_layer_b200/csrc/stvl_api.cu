@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -80,6 +81,7 @@ struct stvl_grid {
   stvl_config_t cfg{};
   int device = 0;
   int sm_count = 148;
+  int sm_spare = 0;     // SMs the persistent kernels of the running cycle leave free (sharded cycle: NCCL's copy kernels run beside them)
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_copy_done = nullptr, ev_mark_done = nullptr;
   GridView v{};
@@ -458,7 +460,7 @@ int launch_batches(stvl_grid * g, const std::vector<MarkBatch> & batches, CycleF
   StageTimer timer__(g, STVL_TIME_MARK);
   bool pdl = fz && fz->pdl && !(g->timing_mask & STVL_TIME_MARK);
   if (fz && fz->costmap && !fz->costmap_done && !batches.empty() &&
-      (uint64_t)tiles_upper(g) > (uint64_t)mark_costmap_tiles_capacity(batches.back(), g->sm_count)) {
+      (uint64_t)tiles_upper(g) > (uint64_t)mark_costmap_tiles_capacity(batches.back(), g->sm_count - g->sm_spare)) {
     // Mark's grid is too small to carry the costmap pass (small clouds, large map): the costmap kernel goes FIRST — it
     // only needs the sweep — chained programmatically behind it, and Mark behind it, so that Mark's cloud streaming
     // overlaps it too (Mark's wait for this kernel implies the sweep: this kernel waited for it).
@@ -471,7 +473,7 @@ int launch_batches(stvl_grid * g, const std::vector<MarkBatch> & batches, CycleF
     const bool carry = fz && fz->costmap && !fz->costmap_done && i + 1 == batches.size();
     const MarkBatch & b = batches[i];
     HOST_T(tm0);
-    CU(launch_mark(g->v, b, g->sm_count, g->stream, pdl, carry ? &fz->cm : nullptr, carry ? fz->costmap : nullptr, carry && fz->bits,
+    CU(launch_mark(g->v, b, g->sm_count - g->sm_spare, g->stream, pdl, carry ? &fz->cm : nullptr, carry ? fz->costmap : nullptr, carry && fz->bits,
                    &g->mark_cursor_host));
     HOST_T(tm1);
     HOST_ADD(3, tm0, tm1);
@@ -1191,7 +1193,7 @@ int clear_frustums_impl(stvl_grid * g, double now, const stvl_frustum_t * frustu
     // fused cycle: the sweep also resets the costmap bytes (or this rank's cell bitmap) and shares the SMs with the Mark
     // kernel that streams its clouds behind it
     const size_t reset_bytes = fz->bits ? (size_t)fz->cm.bit_wpr * 4u * fz->cm.size_y : (size_t)fz->cm.size_x * fz->cm.size_y;
-    CU(launch_sweep(g->v, frustums_dev, &fparam, (int)n_frustums, now, out, slots_upper(g), g->sm_count, g->stream, true, true, fz->costmap,
+    CU(launch_sweep(g->v, frustums_dev, &fparam, (int)n_frustums, now, out, slots_upper(g), g->sm_count - g->sm_spare, g->stream, true, true, fz->costmap,
                     reset_bytes, fz->bits ? 0 : (int)fz->cm.default_value));
     HOST_T(ts1);
     HOST_ADD(2, ts0, ts1);
@@ -1815,7 +1817,16 @@ int sharded_cycle(stvl_grid * g, double now, const stvl_frustum_t * frustums, ui
   CostmapDev d = to_dev(*p);
   d.bit_w_lo = g->bit_w_lo[me];
   d.bit_wpr = g->bit_w_hi[me] - g->bit_w_lo[me];
+  // NCCL's send / receive kernels of the previous cycle's exchange run on the side stream while this cycle's kernels run: a
+  // persistent grid of one (Mark) or two (sweep) register-file-filling CTAs per SM would have to wait for every SM such a copy
+  // CTA sits on, so the sharded cycle leaves a few SMs to them: 4 on a sending rank, 2 + 2 per peer (at most 16) on the root,
+  // which receives from every peer (STVL_SHARD_SPARE_SMS overrides; measured at N = 2: 60.1 us per cycle with none, 57.6 with 4,
+  // 53.7 with 4 and NCCL_MAX_P2P_NCHANNELS=1)
+  static const int spare_env = [] { const char * v = std::getenv("STVL_SHARD_SPARE_SMS"); const int x = v ? std::atoi(v) : -1; return x > 32 ? 32 : x; }();
+  const int spare_dflt = g->comm_rank == root ? std::min(2 + 2 * (g->comm_n - 1), 16) : 4;
+  g->sm_spare = g->comm_n > 1 ? std::min(spare_env >= 0 ? spare_env : spare_dflt, g->sm_count / 2) : 0;
   int rc = fused_cycle(g, now, frustums, n_frustums, readings, n_readings, d, reinterpret_cast<uint8_t *>(g->bits[b].p), true);
+  g->sm_spare = 0;
   if (rc != STVL_OK) return rc;
   g->bits_k += 1;
   cudaStream_t xs = pipelined ? g->merge_stream : g->stream;
