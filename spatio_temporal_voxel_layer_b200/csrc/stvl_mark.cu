@@ -257,6 +257,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
           unsigned int c;
           while ((c = *reinterpret_cast<volatile unsigned int *>(&s_claimed)) == 0u) { }
           *reinterpret_cast<volatile unsigned int *>(&s_claimed) = 0u;
+          __threadfence_block();   // ... before the group below becomes visible: its first taker writes s_claimed again
           const uint32_t grp = c - 1u;
           if (grp >= batch.n_groups) { *reinterpret_cast<volatile unsigned int *>(&s_exhausted) = 1u; break; }
           const uint32_t lo = grp * (uint32_t)kMarkGroup, hi = min(lo + (uint32_t)kMarkGroup, batch.total_blocks);
