@@ -457,7 +457,7 @@ mark_kernel(const __grid_constant__ GridView g, const __grid_constant__ MarkBatc
     else meta_nxt = issue(next_unit(0), 1, base_nxt);
   }
   // ---- the warp's stream of units ---------------------------------------------------------------------------------------------
-  // unit number `it` of the warp (the CTA's unit warp + 32 * it) sits in buffer it & 1; every unit completes one phase of its
+  // the warp's it-th unit sits in buffer it & 1; every unit (an empty one too) completes one phase of its
   // buffer's barrier
   bool first = true;
   for (uint32_t it = 0;; ++it) {
@@ -728,7 +728,7 @@ static cudaError_t launch_mark_variant(const GridView & g, const MarkBatch & bat
   b.c_hi = (float)g.inv_vs * 1.00000035762786865234375f;             // (float)(1/vs) * (1 + 3 * 2^-23), one rounding
   // Unit hand-out.  A launch of the fused cycle starts its CTAs one by one as the sweep leaves the SMs (and its costmap warps
   // join the stream late), so there the units are handed out dynamically, in groups, from the handle's cursor; a launch that has
-  // the GPU to itself deals them round-robin: CTA c takes units c, c + grid, c + 2 grid, ...  (STVL_MARK_DYNAMIC=0/1 forces either.)
+  // the GPU to itself deals them round-robin: CTA c takes units c, c + grid, c + 2 grid, ...  (STVL_MARK_DYNAMIC=0/1 forces either for launches that do not carry the costmap pass.)
   static const int force_dynamic = std::getenv("STVL_MARK_DYNAMIC") ? std::atoi(std::getenv("STVL_MARK_DYNAMIC")) : -1;
   const bool dynamic = cursor != nullptr && g.mark_cursor != nullptr && (kCostmap || (force_dynamic < 0 ? pdl : force_dynamic != 0));
   const uint32_t grid = dynamic ? mark_grid_dynamic(batch, sm_count) : mark_grid_for(batch, sm_count);
